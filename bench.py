@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (contract in the task statement).
+
+Workload (BASELINE.json configs[1]): FLAT 10M x 768 fp32, cosine, k=10, batch=256 queries, 1 x B200.
+A "step" is one pass of the KNN hot path over one batch of 256 synthetic queries.
+
+  value   queries/s with queries and corpus already resident in HBM (VecSimB200_TopKQueryBatchDevice),
+          timed with CUDA events on the launching stream, max over ranks.
+  e2e     the same through the host-facing C-ABI (VecSimB200_TopKQueryBatch): host query blobs in,
+          host labels/scores out, H2D + D2H inside the timed region.
+  roofline  the dominant kernel (scan_topk_kernel) against measured HBM bandwidth
+            (MEASURED_PEAKS.json): algorithmic bytes = N*D*4 per launch / its CUDA-event duration.
+  cpu_baseline  the reference's own brute-force code (oracle/_ref, built from /root/reference) or,
+            if that library is absent, our C restatement, on a bounded sample.
+
+N > 1 (torchrun): every rank owns its own 10M-row shard of an (N x 10M)-row corpus (weak scaling);
+a step scans the local shard for the same 256 queries, all-gathers the per-shard top-k over NCCL and
+merges on device (VecSimB200_MergeShardTopK).  value = N*256 / step time = throughput in units of
+"query x 10M-row shard".
+
+--impl reference: times the reference CPU implementation on the host cores (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "KNN QPS @k=10 on 10M x 768 fp32 (cosine, batch=256)"
+N_ROWS, DIM, K, BATCH = 10_000_000, 768, 10, 256
+SEED_ROWS, SEED_QUERIES = 42, 43
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop = threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=3)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi samples"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU code on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_qps(sample_rows, queries_per_thread, threads):
+    """Times BruteForceIndex::topKQuery (oracle/_ref = the reference's sources) — or our C restatement
+    if that library was not built — on `sample_rows` x 768 cosine rows; scales QPS linearly to 10M rows
+    (the scan is a streaming pass).  Returns (qps_at_10M, info)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+
+    import oracle_lib as ol
+
+    rows = ol.synth_rows(ol.F32, SEED_ROWS, 0, sample_rows, DIM)
+    nq = queries_per_thread * threads
+    qs = ol.synth_rows(ol.F32, SEED_QUERIES, 0, nq, DIM)
+    ref = ol.ref_vecsim()
+    if ref is not None:
+        kind = "reference"
+        ix = ol.RefIndex(ol.F32, DIM, ol.COS)
+        ix.add_many(rows, 1)
+        secs = ref.Ref_TimeTopK(ix.h, ol._p(qs), qs.strides[0], nq, K, threads, None, None)
+    else:
+        kind = "port"
+        ix = ol.PortIndex(ol.F32, DIM, ol.COS, tier=ol.TIER_AVX512)
+        ix.add_many(rows, 1)
+        secs = ol.port().orc_index_time_topk(ix.h, ol._p(qs), qs.strides[0], nq, K, threads, None, None)
+    qps_sample = nq / secs
+    qps_full = qps_sample * sample_rows / N_ROWS
+    info = {"value": qps_full, "unit": "queries/s", "cores": threads, "kind": kind,
+            "sample": f"{nq} queries x {sample_rows} rows x {DIM} fp32 cosine, {threads} threads, one query per "
+                      f"thread (brute_force.h:243-291); QPS scaled x{sample_rows}/{N_ROWS} to 10M rows",
+            "sample_seconds": secs}
+    del ix
+    return qps_full, info
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = []
+    info = None
+    total = args.warmup + args.steps
+    for i in range(total):
+        t0 = time.perf_counter()
+        qps, info = cpu_reference_qps(args.ref_sample_rows, 1, threads)
+        if i >= args.warmup:
+            steps.append((qps, time.perf_counter() - t0))
+        if time.perf_counter() - t0 > 120:
+            break
+    qps = statistics.mean(s[0] for s in steps)
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": len(steps), "warmup": args.warmup, "ms_per_step": 1000.0 * BATCH / qps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "FLAT 10M x 768 fp32 cosine k=10 batch=256 (reference CPU path, bounded sample)"},
+            "cpu_baseline": info,
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=N_ROWS, help="rows per GPU (default = the BASELINE workload)")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--ref-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from redisearch_b200 import vecsim as vs
+    from redisearch_b200._lib import load_library
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(3, args.warmup)
+    rows, nq = args.rows, args.batch
+
+    L = vs.lib()
+    S = load_library("libsynth_b200.so")
+    S.Synth_FillRows.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
+    S.Synth_NormalizeRowsF32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_void_p]
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    # ---- build the shard in HBM: generate + normalise on device, ingest device-to-device
+    index = vs.VecSimIndex(vs.VecSimType_FLOAT32, DIM, vs.VecSimMetric_Cosine)
+    assert L.VecSimB200_Reserve(index.h, rows) == 0, "cannot reserve HBM for the corpus"
+    chunk = min(rows, 1_000_000)
+    buf = torch.empty((chunk, DIM), dtype=torch.float32, device=dev)
+    row0_global = rank * rows
+    t_build = time.perf_counter()
+    done = 0
+    while done < rows:
+        n = min(chunk, rows - done)
+        assert S.Synth_FillRows(buf.data_ptr(), DIM * 4, 0, SEED_ROWS, row0_global + done, n, DIM, sp) == 0
+        assert S.Synth_NormalizeRowsF32(buf.data_ptr(), DIM * 4, n, DIM, sp) == 0
+        torch.cuda.synchronize()
+        assert L.VecSimB200_AddVectorsDevice(index.h, buf.data_ptr(), n, row0_global + done + 1) == n
+        done += n
+    del buf
+    build_s = time.perf_counter() - t_build
+
+    # ---- queries: same generator, normalised like VecSimIndex_TopKQuery would (preprocessors.h:121-131)
+    qdev = torch.empty((nq, DIM), dtype=torch.float32, device=dev)
+    assert S.Synth_FillRows(qdev.data_ptr(), DIM * 4, 0, SEED_QUERIES, 0, nq, DIM, sp) == 0
+    q_host_raw = qdev.cpu().numpy().copy()  # raw (un-normalised) host blobs for the e2e arm
+    assert S.Synth_NormalizeRowsF32(qdev.data_ptr(), DIM * 4, nq, DIM, sp) == 0
+    out_labels = torch.empty((nq, K), dtype=torch.int64, device=dev)
+    out_scores = torch.empty((nq, K), dtype=torch.float32, device=dev)
+    if world > 1:
+        gath_s = torch.empty((world, nq, K), dtype=torch.float32, device=dev)
+        gath_l = torch.empty((world, nq, K), dtype=torch.int64, device=dev)
+        fin_s = torch.empty((nq, K), dtype=torch.float32, device=dev)
+        fin_l = torch.empty((nq, K), dtype=torch.int64, device=dev)
+
+    def step_device():
+        rc = L.VecSimB200_TopKQueryBatchDevice(index.h, qdev.data_ptr(), nq, K, out_labels.data_ptr(),
+                                               out_scores.data_ptr(), sp)
+        assert rc == 0
+        if world > 1:  # the one exchange step: per-shard top-k -> all ranks -> G-way merge on device
+            dist.all_gather_into_tensor(gath_s, out_scores)
+            dist.all_gather_into_tensor(gath_l, out_labels)
+            assert L.VecSimB200_MergeShardTopK(gath_s.data_ptr(), gath_l.data_ptr(), world, nq, K, fin_s.data_ptr(),
+                                               fin_l.data_ptr(), sp) == 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    index.stats(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        ev1.record(stream)
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    st = index.stats(reset=True)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * nq / (ms_step / 1000.0)
+
+    # ---- e2e through the host-facing C-ABI: host blobs in, host results out
+    h_labels = np.empty((nq, K), dtype=np.uint64)
+    h_scores = np.empty((nq, K), dtype=np.float64)
+    qh = np.ascontiguousarray(q_host_raw)
+    for _ in range(2):
+        assert L.VecSimB200_TopKQueryBatch(index.h, qh.ctypes.data, qh.strides[0], nq, K, None, h_labels.ctypes.data,
+                                           h_scores.ctypes.data) == 0
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        assert L.VecSimB200_TopKQueryBatch(index.h, qh.ctypes.data, qh.strides[0], nq, K, None, h_labels.ctypes.data,
+                                           h_scores.ctypes.data) == 0
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * nq / e2e_s
+    # host-path and device-path answers must agree (same kernels)
+    dl = out_labels.cpu().numpy()
+    agree = bool((dl == h_labels.astype(np.int64)).all())
+
+    # ---- roofline of the dominant kernel
+    peak, peak_src = load_peaks()
+    scan_us = st.scan_device_us / max(1, st.scan_launches) if st.scan_device_us > 0 else None
+    st2 = index.stats(reset=True)  # e2e arm: scan launches timed with CUDA events inside the library
+    if st2.scan_launches:
+        scan_us = st2.scan_device_us / st2.scan_launches
+    alg_bytes = rows * DIM * 4 + nq * DIM * 4 + nq * K * 12
+    achieved = alg_bytes / (scan_us * 1e-6) / 1e9 if scan_us else None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"FLAT {rows} x {DIM} fp32 cosine k={K} batch={nq} per GPU"
+                                   + (f"; corpus = {world} shards, NCCL all-gather of per-shard top-k + device merge" if world > 1 else ""),
+                       "rows_per_gpu": rows, "dim": DIM, "k": K, "batch": nq,
+                       "l2_policy": "corpus (30.7 GB) >> 126 MB L2, no flush needed",
+                       "value_unit_note": "queries x 10M-row shards per second" if world > 1 else "queries per second",
+                       "build_seconds": round(build_s, 2), "host_device_results_agree": agree},
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(nq * DIM * 4),
+                    "d2h_bytes_per_step": int(nq * K * 8), "ms_per_step": e2e_s * 1000.0},
+            "gpu_launches": int(st.kernel_launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "scan_topk_kernel<f32,IP,4,8>", "avg_launch_us": scan_us,
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                _, info = cpu_reference_qps(args.ref_sample_rows, 2, os.cpu_count() or 1)
+                line["cpu_baseline"] = info
+            except Exception as e:  # the baseline is a reported side number; never fail the bench on it
+                line["cpu_baseline"] = {"value": None, "error": repr(e)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

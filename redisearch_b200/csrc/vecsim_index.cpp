@@ -1,0 +1,1124 @@
+// Host logic of the B200 FLAT index.  See vecsim_index.h for the reference files mirrored.
+#include "vecsim_index.h"
+#include "host_numeric.h"
+#include "topk_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+namespace rsb200 {
+
+Globals &globals() {
+    static Globals g;
+    return g;
+}
+
+#define CU_OK(expr)                                                                                 \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            fprintf(stderr, "[vecsim_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__,  \
+                    cudaGetErrorString(_e));                                                        \
+            return false;                                                                           \
+        }                                                                                           \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// QueryCtx
+// ------------------------------------------------------------------------------------------------
+QueryCtx::~QueryCtx() {
+    if (stream) cudaStreamSynchronize(stream);
+    cudaFree(d_query);
+    cudaFreeHost(h_query);
+    cudaFree(d_cand);
+    cudaFree(d_out);
+    cudaFreeHost(h_out);
+    cudaFree(d_scores);
+    cudaFree(d_count);
+    cudaFreeHost(h_count);
+    cudaFree(d_ids);
+    cudaFreeHost(h_ids);
+    cudaFree(d_dist);
+    cudaFreeHost(h_dist);
+    if (ev_start) cudaEventDestroy(ev_start);
+    if (ev_stop) cudaEventDestroy(ev_stop);
+    if (stream) cudaStreamDestroy(stream);
+}
+bool QueryCtx::init() {
+    CU_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CU_OK(cudaEventCreate(&ev_start));
+    CU_OK(cudaEventCreate(&ev_stop));
+    CU_OK(cudaMalloc(&d_count, 16));
+    CU_OK(cudaMallocHost(&h_count, 16));
+    return true;
+}
+bool QueryCtx::need_query(size_t bytes) {
+    if (bytes <= query_cap) return true;
+    cudaStreamSynchronize(stream);
+    cudaFree(d_query);
+    cudaFreeHost(h_query);
+    d_query = nullptr;
+    h_query = nullptr;
+    query_cap = 0;
+    const size_t cap = std::max<size_t>(bytes, 64 * 1024);
+    CU_OK(cudaMalloc(&d_query, cap));
+    CU_OK(cudaMallocHost(&h_query, cap));
+    query_cap = cap;
+    return true;
+}
+bool QueryCtx::need_cand(size_t elems) {
+    if (elems <= cand_cap) return true;
+    cudaStreamSynchronize(stream);
+    cudaFree(d_cand);
+    d_cand = nullptr;
+    cand_cap = 0;
+    const size_t cap = std::max<size_t>(elems, 64 * 1024);
+    CU_OK(cudaMalloc(&d_cand, cap * sizeof(uint64_t)));
+    cand_cap = cap;
+    return true;
+}
+bool QueryCtx::need_out(size_t elems) {
+    if (elems <= out_cap) return true;
+    cudaStreamSynchronize(stream);
+    cudaFree(d_out);
+    cudaFreeHost(h_out);
+    d_out = nullptr;
+    h_out = nullptr;
+    out_cap = 0;
+    const size_t cap = std::max<size_t>(elems, 4096);
+    CU_OK(cudaMalloc(&d_out, cap * sizeof(uint64_t)));
+    CU_OK(cudaMallocHost(&h_out, cap * sizeof(uint64_t)));
+    out_cap = cap;
+    return true;
+}
+bool QueryCtx::need_scores(size_t n) {
+    if (n <= scores_cap) return true;
+    cudaStreamSynchronize(stream);
+    cudaFree(d_scores);
+    d_scores = nullptr;
+    scores_cap = 0;
+    const size_t cap = n + n / 8 + 1024;
+    CU_OK(cudaMalloc(&d_scores, cap * sizeof(float)));
+    scores_cap = cap;
+    return true;
+}
+bool QueryCtx::need_ids(size_t n) {
+    if (n <= ids_cap) return true;
+    cudaStreamSynchronize(stream);
+    cudaFree(d_ids);
+    cudaFreeHost(h_ids);
+    cudaFree(d_dist);
+    cudaFreeHost(h_dist);
+    d_ids = h_ids = nullptr;
+    d_dist = h_dist = nullptr;
+    ids_cap = 0;
+    const size_t cap = std::max<size_t>(n, 1024);
+    CU_OK(cudaMalloc(&d_ids, cap * 4));
+    CU_OK(cudaMallocHost(&h_ids, cap * 4));
+    CU_OK(cudaMalloc(&d_dist, cap * 4));
+    CU_OK(cudaMallocHost(&h_dist, cap * 4));
+    ids_cap = cap;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// construction
+// ------------------------------------------------------------------------------------------------
+static size_t elem_size(VecSimType t) {
+    switch (t) {
+    case VecSimType_FLOAT32: return 4;
+    case VecSimType_FLOAT16:
+    case VecSimType_BFLOAT16: return 2;
+    case VecSimType_INT8:
+    case VecSimType_UINT8: return 1;
+    default: return 0;
+    }
+}
+
+void FlatIndex::log(const char *level, const char *fmt, ...) const {
+    logCallbackFunction cb = globals().log_cb.load();
+    if (!cb) return;
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    cb(log_ctx_, level, buf);
+}
+
+FlatIndex *FlatIndex::create(const BFParams &p, void *log_ctx) {
+    const size_t es = elem_size(p.type);
+    if (es == 0 || p.dim == 0) return nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        logCallbackFunction cb = globals().log_cb.load();
+        const char *msg = "vecsim_b200: no CUDA device available; this library has no CPU fallback";
+        if (cb)
+            cb(log_ctx, "warning", msg);
+        else
+            fprintf(stderr, "%s\n", msg);
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::unique_ptr<FlatIndex> ix(new FlatIndex());
+    ix->type_ = p.type;
+    ix->metric_ = p.metric;
+    ix->dim_ = p.dim;
+    ix->multi_ = p.multi;
+    ix->block_size_ = p.blockSize ? p.blockSize : DEFAULT_BLOCK_SIZE;
+    ix->log_ctx_ = log_ctx;
+    ix->elem_bytes_ = es;
+    switch (p.type) {
+    case VecSimType_FLOAT32: ix->dtype_ = DT_F32; break;
+    case VecSimType_FLOAT16: ix->dtype_ = DT_F16; break;
+    case VecSimType_BFLOAT16: ix->dtype_ = DT_BF16; break;
+    case VecSimType_INT8: ix->dtype_ = DT_I8; break;
+    default: ix->dtype_ = DT_U8; break;
+    }
+    const bool is_int = (ix->dtype_ == DT_I8 || ix->dtype_ == DT_U8);
+    ix->mkind_ = (p.metric == VecSimMetric_L2) ? MT_L2 : (p.metric == VecSimMetric_IP || !is_int) ? MT_IP : MT_COS;
+    ix->stored_bytes_ = p.dim * es + ((is_int && p.metric == VecSimMetric_Cosine) ? sizeof(float) : 0);
+    // fp32 rows are read with 4-byte lane loads (any dim); the narrower types with 16-byte vectors.
+    ix->pitch_ = (ix->dtype_ == DT_F32) ? ix->stored_bytes_ : ((ix->stored_bytes_ + 15) & ~(size_t)15);
+    if (cudaStreamCreateWithFlags(&ix->copy_stream_, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    // pinned staging: up to 32 MiB of appended rows between flushes
+    ix->stage_cap_rows_ = std::max<size_t>(1, std::min<size_t>((32u << 20) / ix->pitch_, 1u << 20));
+    if (cudaMallocHost(&ix->h_stage_, ix->stage_cap_rows_ * ix->pitch_) != cudaSuccess) return nullptr;
+    memset(ix->h_stage_, 0, ix->stage_cap_rows_ * ix->pitch_);
+    if (p.initialCapacity && !ix->reserve(p.initialCapacity)) return nullptr;
+    return ix.release();
+}
+
+FlatIndex::~FlatIndex() {
+    {
+        std::lock_guard<std::mutex> g(pool_mu_);
+        pool_.clear();
+    }
+    if (copy_stream_) {
+        cudaStreamSynchronize(copy_stream_);
+        cudaStreamDestroy(copy_stream_);
+    }
+    cudaFree(d_rows_);
+    cudaFree(d_id_to_label_);
+    cudaFreeHost(h_stage_);
+}
+
+CorpusView FlatIndex::view() const {
+    CorpusView v;
+    v.rows = d_rows_;
+    v.pitch = pitch_;
+    v.n_rows = (uint32_t)count_;
+    v.dim = (uint32_t)dim_;
+    v.dtype = dtype_;
+    v.metric = mkind_;
+    return v;
+}
+
+std::unique_ptr<QueryCtx> FlatIndex::checkout() {
+    {
+        std::lock_guard<std::mutex> g(pool_mu_);
+        if (!pool_.empty()) {
+            auto c = std::move(pool_.back());
+            pool_.pop_back();
+            return c;
+        }
+    }
+    std::unique_ptr<QueryCtx> c(new QueryCtx());
+    if (!c->init()) return nullptr;
+    return c;
+}
+void FlatIndex::checkin(std::unique_ptr<QueryCtx> c) {
+    if (!c) return;
+    std::lock_guard<std::mutex> g(pool_mu_);
+    if (pool_.size() < 64) pool_.push_back(std::move(c));
+}
+
+bool FlatIndex::timed_out(void *ctx) const {
+    timeoutCallbackFunction cb = globals().timeout_cb.load();
+    return cb && cb(ctx) != 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// preprocessing (VS/spaces/computer/preprocessors.h:49-146)
+// ------------------------------------------------------------------------------------------------
+void FlatIndex::preprocess_storage(const void *blob, uint8_t *dst) const {
+    memcpy(dst, blob, dim_ * elem_bytes_);
+    if (metric_ != VecSimMetric_Cosine) return;
+    switch (dtype_) {
+    case DT_F32: normalize_f32(reinterpret_cast<float *>(dst), dim_); break;
+    case DT_F16: normalize_f16(reinterpret_cast<uint16_t *>(dst), dim_); break;
+    case DT_BF16: normalize_bf16(reinterpret_cast<uint16_t *>(dst), dim_); break;
+    case DT_I8: append_int_norm(reinterpret_cast<int8_t *>(dst), dim_); break;
+    case DT_U8: append_int_norm(reinterpret_cast<uint8_t *>(dst), dim_); break;
+    }
+}
+void FlatIndex::preprocess_query(const void *blob, uint8_t *dst) const { preprocess_storage(blob, dst); }
+
+// ------------------------------------------------------------------------------------------------
+// storage
+// ------------------------------------------------------------------------------------------------
+bool FlatIndex::grow_to(size_t rows) {
+    if (rows <= capacity_) return true;
+    size_t cap = std::max(rows, capacity_ + capacity_ / 2);
+    cap = ((cap + block_size_ - 1) / block_size_) * block_size_;
+    uint8_t *nu = nullptr;
+    cudaError_t e = cudaMalloc(&nu, cap * pitch_);
+    if (e != cudaSuccess && cap > rows) { // retry with the exact size
+        cudaGetLastError();
+        cap = ((rows + block_size_ - 1) / block_size_) * block_size_;
+        e = cudaMalloc(&nu, cap * pitch_);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        log("warning", "vecsim_b200: cannot allocate %zu bytes of HBM", cap * pitch_);
+        return false;
+    }
+    if (resident_) {
+        CU_OK(cudaMemcpyAsync(nu, d_rows_, resident_ * pitch_, cudaMemcpyDeviceToDevice, copy_stream_));
+        CU_OK(cudaStreamSynchronize(copy_stream_));
+    }
+    cudaFree(d_rows_);
+    d_rows_ = nu;
+    capacity_ = cap;
+    return true;
+}
+
+bool FlatIndex::reserve(size_t rows) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (id_to_label_.capacity() < rows) id_to_label_.reserve(rows);
+    return grow_to(rows);
+}
+
+// caller holds mu_
+static bool flush_locked(uint8_t *d_rows, size_t pitch, uint8_t *h_stage, size_t &resident, size_t count,
+                         cudaStream_t s) {
+    if (resident == count) return true;
+    const size_t n = count - resident;
+    CU_OK(cudaMemcpyAsync(d_rows + resident * pitch, h_stage, n * pitch, cudaMemcpyHostToDevice, s));
+    CU_OK(cudaStreamSynchronize(s));
+    resident = count;
+    return true;
+}
+
+bool FlatIndex::flush() {
+    std::lock_guard<std::mutex> g(mu_);
+    return flush_locked(d_rows_, pitch_, h_stage_, resident_, count_, copy_stream_);
+}
+
+int FlatIndex::add(const void *blob, size_t label) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!multi_) {
+        auto it = label_to_id_.find(label);
+        if (it != label_to_id_.end()) {
+            // brute_force_single.h:139-144: overwrite in place with the RAW blob (the reference does
+            // not re-run the storage preprocessor here).  For int8/uint8 cosine the reference reads
+            // 4 bytes past the caller's blob; we recompute the norm instead of reading out of bounds.
+            const idType id = it->second;
+            std::vector<uint8_t> tmp(pitch_, 0);
+            memcpy(tmp.data(), blob, dim_ * elem_bytes_);
+            if (mkind_ == MT_COS) {
+                if (dtype_ == DT_I8)
+                    append_int_norm(reinterpret_cast<int8_t *>(tmp.data()), dim_);
+                else
+                    append_int_norm(tmp.data(), dim_);
+            }
+            if (id >= resident_) {
+                memcpy(h_stage_ + (id - resident_) * pitch_, tmp.data(), pitch_);
+            } else {
+                if (cudaMemcpy(d_rows_ + (size_t)id * pitch_, tmp.data(), pitch_, cudaMemcpyHostToDevice) != cudaSuccess)
+                    return 0;
+            }
+            return 0;
+        }
+    }
+    if (count_ >= (size_t)std::numeric_limits<uint32_t>::max() - 1) return 0;
+    if (count_ - resident_ >= stage_cap_rows_) {
+        if (!grow_to(count_ + 1)) return 0;
+        if (!flush_locked(d_rows_, pitch_, h_stage_, resident_, count_, copy_stream_)) return 0;
+    }
+    if (!grow_to(count_ + 1)) return 0;
+    uint8_t *slot = h_stage_ + (count_ - resident_) * pitch_;
+    preprocess_storage(blob, slot);
+    const idType id = (idType)count_++;
+    id_to_label_.push_back(label);
+    if (multi_)
+        label_to_ids_[label].push_back(id);
+    else
+        label_to_id_[label] = id;
+    labels_dirty_ = true;
+    return 1;
+}
+
+int FlatIndex::add_bulk(const void *blobs, size_t stride, size_t n, const size_t *labels, size_t label0) {
+    int added = 0;
+    for (size_t i = 0; i < n; i++)
+        added += add(static_cast<const uint8_t *>(blobs) + i * stride, labels ? labels[i] : label0 + i);
+    return added;
+}
+
+int FlatIndex::add_bulk_device(const void *d_src, size_t n, size_t label0) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (n == 0) return 0;
+    if (!flush_locked(d_rows_, pitch_, h_stage_, resident_, count_, copy_stream_)) return -1;
+    if (!grow_to(count_ + n)) return -1;
+    if (cudaMemcpyAsync(d_rows_ + count_ * pitch_, d_src, n * pitch_, cudaMemcpyDeviceToDevice, copy_stream_) !=
+            cudaSuccess ||
+        cudaStreamSynchronize(copy_stream_) != cudaSuccess)
+        return -1;
+    id_to_label_.reserve(count_ + n);
+    for (size_t i = 0; i < n; i++) {
+        const idType id = (idType)(count_ + i);
+        id_to_label_.push_back(label0 + i);
+        if (multi_)
+            label_to_ids_[label0 + i].push_back(id);
+        else
+            label_to_id_[label0 + i] = id;
+    }
+    count_ += n;
+    resident_ = count_;
+    labels_dirty_ = true;
+    return (int)n;
+}
+
+int FlatIndex::remove(size_t label) {
+    std::lock_guard<std::mutex> g(mu_);
+    std::vector<idType> victims;
+    if (multi_) {
+        auto it = label_to_ids_.find(label);
+        if (it == label_to_ids_.end()) return 0;
+        victims = it->second;
+        label_to_ids_.erase(it);
+    } else {
+        auto it = label_to_id_.find(label);
+        if (it == label_to_id_.end()) return 0;
+        victims.push_back(it->second);
+        label_to_id_.erase(it);
+    }
+    if (!flush_locked(d_rows_, pitch_, h_stage_, resident_, count_, copy_stream_)) return 0;
+    // brute_force.h:196-224 — move the last row into the hole; with several victims process them
+    // one by one (brute_force_multi.h:143-165), re-reading ids that a previous swap relocated.
+    int removed = 0;
+    std::sort(victims.begin(), victims.end(), std::greater<idType>());
+    for (idType id : victims) {
+        const idType last = (idType)(count_ - 1);
+        if (id != last) {
+            const size_t last_label = id_to_label_[last];
+            cudaMemcpyAsync(d_rows_ + (size_t)id * pitch_, d_rows_ + (size_t)last * pitch_, pitch_,
+                            cudaMemcpyDeviceToDevice, copy_stream_);
+            id_to_label_[id] = last_label;
+            if (multi_) {
+                auto &v = label_to_ids_[last_label];
+                for (auto &x : v)
+                    if (x == last) x = id;
+            } else {
+                label_to_id_[last_label] = id;
+            }
+        }
+        id_to_label_.pop_back();
+        count_--;
+        removed++;
+    }
+    cudaStreamSynchronize(copy_stream_);
+    resident_ = count_;
+    labels_dirty_ = true;
+    return removed;
+}
+
+bool FlatIndex::sync_labels_to_device() {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!labels_dirty_ && d_id_to_label_) return true;
+    if (count_ > d_labels_cap_) {
+        cudaFree(d_id_to_label_);
+        d_id_to_label_ = nullptr;
+        const size_t cap = std::max(capacity_, count_);
+        CU_OK(cudaMalloc(&d_id_to_label_, cap * sizeof(uint64_t)));
+        d_labels_cap_ = cap;
+    }
+    static_assert(sizeof(size_t) == sizeof(uint64_t), "labels are 64-bit");
+    if (count_)
+        CU_OK(cudaMemcpy(d_id_to_label_, id_to_label_.data(), count_ * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    labels_dirty_ = false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// queries
+// ------------------------------------------------------------------------------------------------
+bool FlatIndex::upload_query(QueryCtx &c, const uint8_t *stored_q, size_t nq) {
+    const size_t qp = (stored_bytes_ + 15) & ~(size_t)15;
+    if (!c.need_query(qp * nq)) return false;
+    if (stored_q != c.h_query) {
+        for (size_t i = 0; i < nq; i++) {
+            memcpy(c.h_query + i * qp, stored_q + i * stored_bytes_, stored_bytes_);
+            memset(c.h_query + i * qp + stored_bytes_, 0, qp - stored_bytes_);
+        }
+    }
+    CU_OK(cudaMemcpyAsync(c.d_query, c.h_query, qp * nq, cudaMemcpyHostToDevice, c.stream));
+    return true;
+}
+
+namespace {
+struct KeyedResult {
+    uint32_t key;
+    size_t label;
+};
+} // namespace
+
+// reply ordering: (score asc, label asc) — the order the reference's heap drains in
+// (vecsim_stl.h:64-84) — or by label (vec_utils.cpp:100-103).
+void FlatIndex::finish_reply(VecSimQueryReply *rep, VecSimQueryReply_Order order) const {
+    auto &r = rep->results;
+    if (order == BY_ID) {
+        std::sort(r.begin(), r.end(), [](const VecSimQueryResult &a, const VecSimQueryResult &b) { return a.id < b.id; });
+    } else {
+        std::sort(r.begin(), r.end(), [](const VecSimQueryResult &a, const VecSimQueryResult &b) {
+            const bool an = std::isnan(a.score), bn = std::isnan(b.score);
+            if (an != bn) return bn; // NaN last
+            if (!an && a.score != b.score) return a.score < b.score;
+            return a.id < b.id;
+        });
+    }
+}
+
+long FlatIndex::select_from_scores(QueryCtx &c, uint32_t n, bool has_cursor, uint64_t cursor, size_t want) {
+    if (want == 0 || n == 0) return 0;
+    if (!c.need_out(want + 1)) return -1;
+    LaunchCounters lc;
+    const uint64_t *cur_ptr = nullptr;
+    if (has_cursor) {
+        *reinterpret_cast<uint64_t *>(c.h_count) = cursor;
+        if (cudaMemcpyAsync(c.d_out + want, c.h_count, 8, cudaMemcpyHostToDevice, c.stream) != cudaSuccess) return -1;
+        cur_ptr = c.d_out + want;
+    }
+    const uint32_t lists = plan_select_scores_lists(n);
+    size_t found = 0;
+    while (found < want) {
+        const uint32_t chunk = (uint32_t)std::min<size_t>(kMaxFusedK, want - found);
+        if (!c.need_cand((size_t)lists * chunk)) return -1;
+        if (launch_select_scores(c.d_scores, n, cur_ptr, chunk, c.d_cand, c.stream, &lc) != cudaSuccess) return -1;
+        if (launch_final_select(c.d_cand, 1, lists * chunk, chunk, c.d_out + found, c.stream, &lc) != cudaSuccess)
+            return -1;
+        found += chunk;
+        cur_ptr = c.d_out + found - 1;
+    }
+    if (cudaMemcpyAsync(c.h_out, c.d_out, want * 8, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess) return -1;
+    launches_total_ += lc.launches;
+    size_t real = 0;
+    while (real < want && c.h_out[real] != kEmptySlot) real++;
+    return (long)real;
+}
+
+VecSimQueryReply *FlatIndex::topk(const void *q, size_t k, VecSimQueryParams *qp, VecSimQueryReply_Order order) {
+    auto *rep = new VecSimQueryReply();
+    last_mode_ = STANDARD_KNN;
+    void *tctx = qp ? qp->timeoutCtx : nullptr;
+    if (k == 0) return rep; // brute_force.h:251-253
+    if (!flush()) return rep;
+    const size_t n = count_;
+    if (n == 0) return rep;
+    if (timed_out(tctx)) {
+        rep->code = VecSim_QueryReply_TimedOut;
+        return rep;
+    }
+    auto c = checkout();
+    if (!c) return rep;
+    const size_t qpitch = (stored_bytes_ + 15) & ~(size_t)15;
+    bool ok = c->need_query(qpitch);
+    if (ok) {
+        memset(c->h_query, 0, qpitch);
+        preprocess_query(q, c->h_query);
+        ok = upload_query(*c, c->h_query, 1);
+    }
+    const CorpusView v = view();
+    LaunchCounters lc;
+    if (ok && !multi_ && std::min(k, n) <= (size_t)kMaxFusedK) {
+        const uint32_t ke = (uint32_t)std::min(k, n);
+        const ScanPlan plan = plan_scan_topk(v, 1, ke);
+        ok = c->need_cand(plan.cand_elems) && c->need_out(ke);
+        if (ok) {
+            cudaEventRecord(c->ev_start, c->stream);
+            ok = launch_scan_topk(v, c->d_query, qpitch, 1, ke, plan, c->d_cand, c->stream, &lc) == cudaSuccess;
+            cudaEventRecord(c->ev_stop, c->stream);
+        }
+        ok = ok && launch_final_select(c->d_cand, 1, plan.lists_per_query * ke, ke, c->d_out, c->stream, &lc) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(c->h_out, c->d_out, ke * 8, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+        if (ok) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop) == cudaSuccess) {
+                std::lock_guard<std::mutex> g(stats_mu_);
+                scan_us_ += ms * 1000.0;
+                scan_launches_++;
+                scan_bytes_ += (uint64_t)n * stored_bytes_;
+            }
+            for (uint32_t i = 0; i < ke; i++) {
+                const uint64_t comp = c->h_out[i];
+                if (comp == kEmptySlot) break;
+                rep->results.push_back({id_to_label_[(uint32_t)comp], (double)key_to_float((uint32_t)(comp >> 32))});
+            }
+        }
+    } else if (ok) {
+        // k > kMaxFusedK or multi-value: materialise all scores, then cursor-select in chunks.
+        ok = c->need_scores(n);
+        if (ok) {
+            cudaEventRecord(c->ev_start, c->stream);
+            ok = launch_scan_scores(v, c->d_query, c->d_scores, c->stream, &lc) == cudaSuccess;
+            cudaEventRecord(c->ev_stop, c->stream);
+        }
+        if (ok) {
+            const size_t want_labels = std::min(k, label_count());
+            bool has_cursor = false;
+            uint64_t cursor = 0;
+            std::unordered_set<size_t> seen;
+            size_t scanned = 0;
+            while (ok && rep->results.size() < want_labels && scanned < n) {
+                const size_t want = multi_ ? std::min<size_t>(std::max<size_t>(2 * (want_labels - rep->results.size()), 64), n - scanned)
+                                           : std::min(want_labels - rep->results.size(), n - scanned);
+                const long got = select_from_scores(*c, (uint32_t)n, has_cursor, cursor, want);
+                if (got < 0) {
+                    ok = false;
+                    break;
+                }
+                for (long i = 0; i < got && rep->results.size() < want_labels; i++) {
+                    const uint64_t comp = c->h_out[i];
+                    const size_t label = id_to_label_[(uint32_t)comp];
+                    if (multi_ && !seen.insert(label).second) continue; // best score per label comes first
+                    rep->results.push_back({label, (double)key_to_float((uint32_t)(comp >> 32))});
+                }
+                scanned += (size_t)got;
+                if ((size_t)got < want) break;
+                has_cursor = true;
+                cursor = c->h_out[got - 1];
+            }
+            float ms = 0;
+            if (ok && cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop) == cudaSuccess) {
+                std::lock_guard<std::mutex> g(stats_mu_);
+                scan_us_ += ms * 1000.0;
+                scan_launches_++;
+                scan_bytes_ += (uint64_t)n * stored_bytes_;
+            }
+        }
+    }
+    launches_total_ += lc.launches;
+    if (!ok) {
+        log("warning", "vecsim_b200: top-k query failed on device");
+        rep->results.clear();
+    }
+    checkin(std::move(c));
+    if (timed_out(tctx)) {
+        rep->results.clear();
+        rep->code = VecSim_QueryReply_TimedOut;
+        return rep;
+    }
+    finish_reply(rep, order);
+    return rep;
+}
+
+int FlatIndex::topk_batch(const void *qs, size_t qstride, size_t nq, size_t k, VecSimQueryParams *qp, size_t *out_labels,
+                          double *out_scores) {
+    void *tctx = qp ? qp->timeoutCtx : nullptr;
+    last_mode_ = STANDARD_KNN;
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (size_t i = 0; i < nq * k; i++) {
+        out_labels[i] = SIZE_MAX;
+        out_scores[i] = nan;
+    }
+    if (nq == 0 || k == 0) return VecSim_QueryReply_OK;
+    if (!flush()) return -1;
+    const size_t n = count_;
+    if (n == 0) return VecSim_QueryReply_OK;
+    if (timed_out(tctx)) return VecSim_QueryReply_TimedOut;
+    if (multi_ || std::min(k, n) > (size_t)kMaxFusedK) { // generic path, one query at a time
+        for (size_t i = 0; i < nq; i++) {
+            VecSimQueryReply *r = topk(static_cast<const uint8_t *>(qs) + i * qstride, k, qp, BY_SCORE);
+            const int code = r->code;
+            for (size_t j = 0; j < r->results.size() && j < k; j++) {
+                out_labels[i * k + j] = r->results[j].id;
+                out_scores[i * k + j] = r->results[j].score;
+            }
+            delete r;
+            if (code != VecSim_QueryReply_OK) return code;
+        }
+        return VecSim_QueryReply_OK;
+    }
+    auto c = checkout();
+    if (!c) return -1;
+    const size_t qpitch = (stored_bytes_ + 15) & ~(size_t)15;
+    const uint32_t ke = (uint32_t)std::min(k, n);
+    const CorpusView v = view();
+    const ScanPlan plan = plan_scan_topk(v, (uint32_t)nq, ke);
+    LaunchCounters lc;
+    bool ok = c->need_query(qpitch * nq) && c->need_cand(plan.cand_elems) && c->need_out(nq * ke);
+    if (ok) {
+        memset(c->h_query, 0, qpitch * nq);
+        for (size_t i = 0; i < nq; i++) preprocess_query(static_cast<const uint8_t *>(qs) + i * qstride, c->h_query + i * qpitch);
+        ok = cudaMemcpyAsync(c->d_query, c->h_query, qpitch * nq, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+    }
+    if (ok) {
+        cudaEventRecord(c->ev_start, c->stream);
+        ok = launch_scan_topk(v, c->d_query, qpitch, (uint32_t)nq, ke, plan, c->d_cand, c->stream, &lc) == cudaSuccess;
+        cudaEventRecord(c->ev_stop, c->stream);
+    }
+    ok = ok && launch_final_select(c->d_cand, (uint32_t)nq, plan.lists_per_query * ke, ke, c->d_out, c->stream, &lc) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->h_out, c->d_out, nq * ke * 8, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    launches_total_ += lc.launches;
+    if (ok) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop) == cudaSuccess) {
+            std::lock_guard<std::mutex> g(stats_mu_);
+            scan_us_ += ms * 1000.0;
+            scan_launches_++;
+            scan_bytes_ += (uint64_t)n * stored_bytes_;
+        }
+        std::vector<VecSimQueryResult> tmp;
+        VecSimQueryReply rr;
+        for (size_t i = 0; i < nq; i++) {
+            rr.results.clear();
+            for (uint32_t j = 0; j < ke; j++) {
+                const uint64_t comp = c->h_out[i * ke + j];
+                if (comp == kEmptySlot) break;
+                rr.results.push_back({id_to_label_[(uint32_t)comp], (double)key_to_float((uint32_t)(comp >> 32))});
+            }
+            finish_reply(&rr, BY_SCORE);
+            for (size_t j = 0; j < rr.results.size(); j++) {
+                out_labels[i * k + j] = rr.results[j].id;
+                out_scores[i * k + j] = rr.results[j].score;
+            }
+        }
+    }
+    checkin(std::move(c));
+    if (!ok) return -1;
+    if (timed_out(tctx)) return VecSim_QueryReply_TimedOut;
+    return VecSim_QueryReply_OK;
+}
+
+int FlatIndex::topk_batch_device(const void *d_q, size_t nq, size_t k, int64_t *d_labels, float *d_scores, cudaStream_t s) {
+    if (nq == 0 || k == 0) return 0;
+    if (!flush() || !sync_labels_to_device()) return -1;
+    const size_t n = count_;
+    if (multi_ || k > (size_t)kMaxFusedK) return -1;
+    // Scratch of this entry point is stream-ordered: one dedicated context, reused call after call.
+    // Callers enqueue on one stream (or synchronise between streams), as with any async API.
+    std::lock_guard<std::mutex> dg(dev_mu_);
+    if (!dev_ctx_) dev_ctx_ = checkout();
+    QueryCtx *c = dev_ctx_.get();
+    if (!c) return -1;
+    collect_dev_timing_locked(); // the previous call's scan events (stream-ordered before this call)
+    const size_t qpitch = (stored_bytes_ + 15) & ~(size_t)15;
+    const uint32_t ke = (uint32_t)std::min(k, std::max<size_t>(n, 1));
+    cudaStream_t st = s ? s : c->stream;
+    LaunchCounters lc;
+    bool ok = true;
+    if (n == 0) {
+        ok = cudaMemsetAsync(d_labels, 0xFF, nq * k * 8, st) == cudaSuccess;
+    } else {
+        const CorpusView v = view();
+        const ScanPlan plan = plan_scan_topk(v, (uint32_t)nq, ke);
+        ok = c->need_cand(plan.cand_elems) && c->need_out(nq * k);
+        if (ok && ke < k) ok = cudaMemsetAsync(c->d_out, 0xFF, nq * k * 8, st) == cudaSuccess;
+        if (ok) {
+            cudaEventRecord(c->ev_start, st);
+            ok = launch_scan_topk(v, d_q, qpitch, (uint32_t)nq, ke, plan, c->d_cand, st, &lc) == cudaSuccess;
+            cudaEventRecord(c->ev_stop, st);
+        }
+        if (ok && ke == k) {
+            ok = launch_final_select(c->d_cand, (uint32_t)nq, plan.lists_per_query * ke, ke, c->d_out, st, &lc) == cudaSuccess;
+        } else if (ok) {
+            // fewer rows than k: select into a compact [nq][ke] area, then scatter rows
+            ok = c->need_out(nq * k + nq * ke);
+            uint64_t *compact = c->d_out + nq * k;
+            ok = ok && launch_final_select(c->d_cand, (uint32_t)nq, plan.lists_per_query * ke, ke, compact, st, &lc) == cudaSuccess;
+            ok = ok && cudaMemcpy2DAsync(c->d_out, k * 8, compact, ke * 8, ke * 8, nq, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
+        }
+        ok = ok && launch_unpack_results(c->d_out, (uint32_t)nq, (uint32_t)k, d_id_to_label_, d_labels, d_scores, st, &lc) == cudaSuccess;
+        dev_timing_pending_ = ok;
+        dev_timing_bytes_ = (uint64_t)n * stored_bytes_;
+    }
+    launches_total_ += lc.launches;
+    return ok ? 0 : -1;
+}
+
+VecSimQueryReply *FlatIndex::range(const void *q, double radius, VecSimQueryParams *qp, VecSimQueryReply_Order order) {
+    auto *rep = new VecSimQueryReply();
+    last_mode_ = RANGE_QUERY;
+    void *tctx = qp ? qp->timeoutCtx : nullptr;
+    if (!flush()) return rep;
+    const size_t n = count_;
+    if (n == 0) return rep;
+    if (timed_out(tctx)) {
+        rep->code = VecSim_QueryReply_TimedOut;
+        return rep;
+    }
+    auto c = checkout();
+    if (!c) return rep;
+    const size_t qpitch = (stored_bytes_ + 15) & ~(size_t)15;
+    LaunchCounters lc;
+    bool ok = c->need_query(qpitch) && c->need_scores(n) && c->need_cand(n);
+    if (ok) {
+        memset(c->h_query, 0, qpitch);
+        preprocess_query(q, c->h_query);
+        ok = upload_query(*c, c->h_query, 1);
+    }
+    const CorpusView v = view();
+    ok = ok && launch_scan_scores(v, c->d_query, c->d_scores, c->stream, &lc) == cudaSuccess;
+    ok = ok && launch_range_compact(c->d_scores, (uint32_t)n, (float)radius, c->d_cand, c->d_count, c->stream, &lc) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->h_count, c->d_count, 4, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    if (ok) {
+        const uint32_t m = *c->h_count;
+        ok = c->need_out(m);
+        ok = ok && cudaMemcpyAsync(c->h_out, c->d_cand, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+        if (ok) {
+            if (multi_) { // best score per label (brute_force_multi.h range container)
+                std::unordered_map<size_t, uint32_t> best;
+                for (uint32_t i = 0; i < m; i++) {
+                    const uint64_t comp = c->h_out[i];
+                    const size_t label = id_to_label_[(uint32_t)comp];
+                    const uint32_t key = (uint32_t)(comp >> 32);
+                    auto it = best.find(label);
+                    if (it == best.end() || key < it->second) best[label] = key;
+                }
+                for (auto &kv : best) rep->results.push_back({kv.first, (double)key_to_float(kv.second)});
+            } else {
+                rep->results.reserve(m);
+                for (uint32_t i = 0; i < m; i++) {
+                    const uint64_t comp = c->h_out[i];
+                    rep->results.push_back({id_to_label_[(uint32_t)comp], (double)key_to_float((uint32_t)(comp >> 32))});
+                }
+            }
+        }
+    }
+    launches_total_ += lc.launches;
+    checkin(std::move(c));
+    if (!ok) rep->results.clear();
+    if (timed_out(tctx)) rep->code = VecSim_QueryReply_TimedOut; // brute_force.h:306-309 keeps partial results
+    finish_reply(rep, order);
+    return rep;
+}
+
+double FlatIndex::distance_from(size_t label, const void *blob) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    std::vector<idType> ids;
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        if (multi_) {
+            auto it = label_to_ids_.find(label);
+            if (it == label_to_ids_.end()) return nan;
+            ids = it->second;
+        } else {
+            auto it = label_to_id_.find(label);
+            if (it == label_to_id_.end()) return nan;
+            ids.push_back(it->second);
+        }
+    }
+    if (!flush()) return nan;
+    auto c = checkout();
+    if (!c) return nan;
+    LaunchCounters lc;
+    bool ok = c->need_ids(ids.size()) && upload_query(*c, static_cast<const uint8_t *>(blob), 1);
+    if (ok) {
+        for (size_t i = 0; i < ids.size(); i++) c->h_ids[i] = ids[i];
+        ok = cudaMemcpyAsync(c->d_ids, c->h_ids, ids.size() * 4, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+    }
+    ok = ok && launch_gather_distances(view(), c->d_query, c->d_ids, (uint32_t)ids.size(), c->d_dist, c->stream, &lc) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->h_dist, c->d_dist, ids.size() * 4, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    double best = nan;
+    if (ok) { // brute_force_multi.h:224-241: min over the label's vectors
+        for (size_t i = 0; i < ids.size(); i++) {
+            const double d = (double)c->h_dist[i];
+            if (i == 0 || d < best || std::isnan(best)) best = d;
+        }
+    }
+    launches_total_ += lc.launches;
+    checkin(std::move(c));
+    return best;
+}
+
+// brute_force.h:380-451, thresholds and float/double comparison types reproduced exactly.
+bool FlatIndex::prefer_adhoc(size_t subset, size_t k, bool initial) {
+    (void)k;
+    const size_t index_size = count_;
+    subset = std::min(subset, index_size);
+    const size_t d = dim_;
+    const float r = (index_size == 0) ? 0.0f : (float)subset / (float)label_count();
+    bool res;
+    if (index_size <= 5500) {
+        res = true;
+    } else if (d <= 300) {
+        if (r <= 0.15)
+            res = true;
+        else if (r <= 0.35)
+            res = (d <= 75) ? false : (index_size <= 550000);
+        else
+            res = false;
+    } else {
+        if (r <= 0.55)
+            res = true;
+        else if (d <= 750)
+            res = false;
+        else
+            res = (r <= 0.75);
+    }
+    last_mode_ = res ? (initial ? HYBRID_ADHOC_BF : HYBRID_BATCHES_TO_ADHOC_BF) : HYBRID_BATCHES;
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch iterator
+// ------------------------------------------------------------------------------------------------
+BatchIter *FlatIndex::batch_new(const void *q, VecSimQueryParams *qp) {
+    auto *it = new BatchIter();
+    it->index = this;
+    it->query.assign((stored_bytes_ + 15) & ~(size_t)15, 0);
+    preprocess_query(q, it->query.data()); // forced copy, brute_force.h:371-372
+    it->timeout_ctx = qp ? qp->timeoutCtx : nullptr;
+    it->label_count = label_count();
+    return it;
+}
+
+VecSimQueryReply *FlatIndex::batch_next(BatchIter *it, size_t n_res, VecSimQueryReply_Order order) {
+    auto *rep = new VecSimQueryReply();
+    if (!it->scored) {
+        // first call: the only time the index is read (bf_batch_iterator.h:176-189)
+        if (!flush()) return rep;
+        it->n_rows = (uint32_t)count_;
+        it->label_count = label_count();
+        it->id_to_label_snap = id_to_label_;
+        if (timed_out(it->timeout_ctx)) {
+            rep->code = VecSim_QueryReply_TimedOut;
+            return rep;
+        }
+        if (!it->ctx) it->ctx = checkout();
+        if (!it->ctx) return rep;
+        if (it->n_rows) {
+            LaunchCounters lc;
+            bool ok = it->ctx->need_scores(it->n_rows) && upload_query(*it->ctx, it->query.data(), 1);
+            // upload_query copies stored_bytes_ from a tightly packed source
+            ok = ok && launch_scan_scores(view(), it->ctx->d_query, it->ctx->d_scores, it->ctx->stream, &lc) == cudaSuccess;
+            ok = ok && cudaStreamSynchronize(it->ctx->stream) == cudaSuccess;
+            launches_total_ += lc.launches;
+            {
+                std::lock_guard<std::mutex> g(stats_mu_);
+                scan_launches_++;
+                scan_bytes_ += (uint64_t)it->n_rows * stored_bytes_;
+            }
+            if (!ok) return rep;
+        }
+        it->scored = true;
+    }
+    if (timed_out(it->timeout_ctx)) {
+        rep->code = VecSim_QueryReply_TimedOut;
+        return rep;
+    }
+    const size_t remaining_labels = it->label_count - it->returned;
+    const size_t want_labels = std::min(n_res, remaining_labels);
+    size_t produced = 0;
+    while (produced < want_labels) {
+        const size_t want = multi_ ? std::max<size_t>(2 * (want_labels - produced), 64) : (want_labels - produced);
+        const long got = select_from_scores(*it->ctx, it->n_rows, it->has_cursor, it->cursor, std::min<size_t>(want, it->n_rows));
+        if (got <= 0) break;
+        for (long i = 0; i < got; i++) {
+            const uint64_t comp = it->ctx->h_out[i];
+            if (produced < want_labels) {
+                const size_t label = it->id_to_label_snap[(uint32_t)comp];
+                it->has_cursor = true;
+                it->cursor = comp;
+                if (multi_ && !it->seen.insert(label).second) continue;
+                rep->results.push_back({label, (double)key_to_float((uint32_t)(comp >> 32))});
+                produced++;
+            } else {
+                break; // leave the rest for the next call: cursor stays on the last consumed entry
+            }
+        }
+        if ((size_t)got < std::min<size_t>(want, it->n_rows)) break;
+    }
+    it->returned += rep->results.size();
+    finish_reply(rep, order == BY_ID ? BY_ID : BY_SCORE);
+    return rep;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ad-hoc context
+// ------------------------------------------------------------------------------------------------
+AdhocCtx *FlatIndex::adhoc_new(const void *q) {
+    auto *a = new AdhocCtx();
+    a->index = this;
+    a->query.assign(stored_bytes_, 0);
+    preprocess_query(q, a->query.data()); // the context normalises internally (hybrid_reader.c:212-214)
+    a->ctx = checkout();
+    if (!a->ctx) {
+        delete a;
+        return nullptr;
+    }
+    return a;
+}
+
+void FlatIndex::adhoc_distances(AdhocCtx *a, const size_t *labels, double *out, size_t n) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (size_t i = 0; i < n; i++) out[i] = nan;
+    if (n == 0 || !flush()) return;
+    QueryCtx &c = *a->ctx;
+    LaunchCounters lc;
+    // expand labels to row ids (multi: several rows per label, min taken on the host)
+    std::vector<uint32_t> ids;
+    std::vector<uint32_t> owner;
+    ids.reserve(n);
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        for (size_t i = 0; i < n; i++) {
+            if (multi_) {
+                auto it = label_to_ids_.find(labels[i]);
+                if (it == label_to_ids_.end()) continue;
+                for (idType id : it->second) {
+                    ids.push_back(id);
+                    owner.push_back((uint32_t)i);
+                }
+            } else {
+                auto it = label_to_id_.find(labels[i]);
+                if (it == label_to_id_.end()) continue;
+                ids.push_back(it->second);
+                owner.push_back((uint32_t)i);
+            }
+        }
+    }
+    if (ids.empty()) return;
+    bool ok = c.need_ids(ids.size());
+    if (ok && !a->query_on_device) {
+        ok = upload_query(c, a->query.data(), 1);
+        a->query_on_device = ok;
+    }
+    if (ok) {
+        memcpy(c.h_ids, ids.data(), ids.size() * 4);
+        ok = cudaMemcpyAsync(c.d_ids, c.h_ids, ids.size() * 4, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+    }
+    ok = ok && launch_gather_distances(view(), c.d_query, c.d_ids, (uint32_t)ids.size(), c.d_dist, c.stream, &lc) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c.h_dist, c.d_dist, ids.size() * 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+    launches_total_ += lc.launches;
+    if (!ok) return;
+    for (size_t i = 0; i < ids.size(); i++) {
+        const double d = (double)c.h_dist[i];
+        double &o = out[owner[i]];
+        if (std::isnan(o) || d < o) o = d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// info
+// ------------------------------------------------------------------------------------------------
+VecSimIndexBasicInfo FlatIndex::basic_info() const {
+    VecSimIndexBasicInfo i{};
+    i.algo = VecSimAlgo_BF;
+    i.metric = metric_;
+    i.type = type_;
+    i.isMulti = multi_;
+    i.isTiered = false;
+    i.isDisk = false;
+    i.blockSize = block_size_;
+    i.dim = dim_;
+    return i;
+}
+VecSimIndexStatsInfo FlatIndex::stats_info() const {
+    VecSimIndexStatsInfo s{};
+    s.memory = capacity_ * pitch_ + d_labels_cap_ * 8 + stage_cap_rows_ * pitch_ + id_to_label_.capacity() * sizeof(size_t) +
+               (label_to_id_.size() + label_to_ids_.size()) * (sizeof(size_t) + sizeof(void *) * 2 + sizeof(idType));
+    return s;
+}
+
+static const char *type_name(VecSimType t) {
+    switch (t) {
+    case VecSimType_FLOAT32: return "FLOAT32";
+    case VecSimType_FLOAT64: return "FLOAT64";
+    case VecSimType_BFLOAT16: return "BFLOAT16";
+    case VecSimType_FLOAT16: return "FLOAT16";
+    case VecSimType_INT8: return "INT8";
+    case VecSimType_UINT8: return "UINT8";
+    case VecSimType_INT32: return "INT32";
+    default: return "INT64";
+    }
+}
+static const char *mode_name(VecSearchMode m) { // vec_utils.cpp VecSimSearchMode_ToString
+    switch (m) {
+    case EMPTY_MODE: return "EMPTY_MODE";
+    case STANDARD_KNN: return "STANDARD_KNN";
+    case HYBRID_ADHOC_BF: return "HYBRID_ADHOC_BF";
+    case HYBRID_BATCHES: return "HYBRID_BATCHES";
+    case HYBRID_BATCHES_TO_ADHOC_BF: return "HYBRID_BATCHES_TO_ADHOC_BF";
+    default: return "RANGE_QUERY";
+    }
+}
+
+VecSimDebugInfoIterator *FlatIndex::debug_iterator() const {
+    auto *it = new VecSimDebugInfoIterator();
+    auto str = [&](const char *name, const char *v) {
+        VecSim_InfoField f{};
+        f.fieldName = name;
+        f.fieldType = INFOFIELD_STRING;
+        f.fieldValue.stringValue = v;
+        it->fields.push_back(f);
+    };
+    auto u64 = [&](const char *name, uint64_t v) {
+        VecSim_InfoField f{};
+        f.fieldName = name;
+        f.fieldType = INFOFIELD_UINT64;
+        f.fieldValue.uintegerValue = v;
+        it->fields.push_back(f);
+    };
+    // order and names: brute_force.h:327-365 + vec_sim_index.h addCommonInfoToIterator
+    str("ALGORITHM", "FLAT");
+    str("TYPE", type_name(type_));
+    u64("DIMENSION", dim_);
+    str("METRIC", metric_ == VecSimMetric_L2 ? "L2" : metric_ == VecSimMetric_IP ? "IP" : "COSINE");
+    u64("IS_MULTI_VALUE", multi_);
+    u64("IS_DISK", 0);
+    u64("INDEX_SIZE", count_);
+    u64("INDEX_LABEL_COUNT", multi_ ? label_to_ids_.size() : label_to_id_.size());
+    u64("MEMORY", stats_info().memory);
+    str("LAST_SEARCH_MODE", mode_name(last_mode_));
+    u64("BLOCK_SIZE", block_size_);
+    return it;
+}
+
+// dev_mu_ held.  Folds the CUDA-event timing of the last topk_batch_device scan into the stats.
+void FlatIndex::collect_dev_timing_locked() {
+    if (!dev_timing_pending_ || !dev_ctx_) return;
+    float ms = 0;
+    if (cudaEventSynchronize(dev_ctx_->ev_stop) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, dev_ctx_->ev_start, dev_ctx_->ev_stop) == cudaSuccess) {
+        std::lock_guard<std::mutex> g(stats_mu_);
+        scan_us_ += ms * 1000.0;
+        scan_launches_++;
+        scan_bytes_ += dev_timing_bytes_;
+    }
+    dev_timing_pending_ = false;
+}
+
+VecSimB200_Stats FlatIndex::get_stats(bool reset) {
+    {
+        std::lock_guard<std::mutex> dg(dev_mu_);
+        collect_dev_timing_locked();
+    }
+    std::lock_guard<std::mutex> g(stats_mu_);
+    VecSimB200_Stats s{};
+    s.kernel_launches = launches_total_.load();
+    s.scan_launches = scan_launches_;
+    s.scan_device_us = scan_us_;
+    s.scan_bytes = scan_bytes_;
+    if (reset) {
+        launches_total_ = 0;
+        scan_launches_ = 0;
+        scan_us_ = 0;
+        scan_bytes_ = 0;
+    }
+    return s;
+}
+
+} // namespace rsb200

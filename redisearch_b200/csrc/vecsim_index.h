@@ -1,0 +1,203 @@
+// Host-side FLAT index object behind the VecSim C API: label<->row bookkeeping, preprocessing,
+// staging of appended rows, query contexts (stream + scratch), reply objects.  The vectors
+// themselves live only in HBM.  Mirrors the host logic of
+//   VS/algorithms/brute_force/brute_force.h            (append / swap-delete / queries / heuristics)
+//   VS/algorithms/brute_force/brute_force_single.h     (label -> id, update in place)
+//   VS/algorithms/brute_force/brute_force_multi.h      (label -> ids)
+//   VS/algorithms/brute_force/bf_batch_iterator.h      (batch iterator state machine)
+#pragma once
+#include "../../include/vecsim_b200.h"
+#include "vecsim_kernels.h"
+
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+struct VecSimQueryResult {
+    size_t id;
+    double score;
+};
+struct VecSimQueryReply {
+    std::vector<VecSimQueryResult> results;
+    VecSimQueryReply_Code code = VecSim_QueryReply_OK;
+};
+struct VecSimQueryReply_Iterator {
+    VecSimQueryReply *reply;
+    size_t pos;
+};
+struct VecSimDebugInfoIterator {
+    std::vector<VecSim_InfoField> fields;
+    std::vector<std::string> owned;
+    size_t pos = 0;
+};
+
+namespace rsb200 {
+
+struct Globals {
+    std::atomic<timeoutCallbackFunction> timeout_cb{nullptr};
+    std::atomic<logCallbackFunction> log_cb{nullptr};
+    VecSimMemoryFunctions mem{};
+};
+Globals &globals();
+
+// Device + pinned scratch for one in-flight query (or query batch).  Checked out of a pool so
+// that many RediSearch worker threads can query one index concurrently (SURVEY.md §8b threading).
+struct QueryCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    uint8_t *d_query = nullptr, *h_query = nullptr; // staged query blobs
+    size_t query_cap = 0;
+    uint64_t *d_cand = nullptr;
+    size_t cand_cap = 0;
+    uint64_t *d_out = nullptr, *h_out = nullptr;
+    size_t out_cap = 0;
+    float *d_scores = nullptr; // unfused path: one score per row
+    size_t scores_cap = 0;
+    uint32_t *d_count = nullptr, *h_count = nullptr;
+    uint32_t *d_ids = nullptr, *h_ids = nullptr;
+    float *d_dist = nullptr, *h_dist = nullptr;
+    size_t ids_cap = 0;
+    ~QueryCtx();
+    bool init();
+    bool need_query(size_t bytes);
+    bool need_cand(size_t elems);
+    bool need_out(size_t elems);
+    bool need_scores(size_t n);
+    bool need_ids(size_t n);
+};
+
+class FlatIndex;
+
+struct BatchIter {
+    FlatIndex *index;
+    std::vector<uint8_t> query; // stored-form query blob (normalised for cosine)
+    void *timeout_ctx;
+    std::unique_ptr<QueryCtx> ctx; // owns the score array between Next calls
+    bool scored = false;
+    uint32_t n_rows = 0;        // rows at scoring time
+    size_t label_count = 0;     // labels at scoring time (bf_batch_iterator.h:29)
+    size_t returned = 0;
+    bool has_cursor = false;
+    uint64_t cursor = 0;                  // last composite handed out
+    std::unordered_set<size_t> seen;      // multi-value: labels already returned
+    std::vector<size_t> id_to_label_snap; // label table at scoring time
+};
+
+struct AdhocCtx {
+    FlatIndex *index;
+    std::vector<uint8_t> query; // stored-form query
+    std::unique_ptr<QueryCtx> ctx;
+    bool query_on_device = false;
+};
+
+class FlatIndex {
+  public:
+    static FlatIndex *create(const BFParams &p, void *log_ctx);
+    ~FlatIndex();
+
+    int add(const void *blob, size_t label);
+    int add_bulk(const void *blobs, size_t stride, size_t n, const size_t *labels, size_t label0);
+    int add_bulk_device(const void *d_rows, size_t n, size_t label0);
+    int remove(size_t label);
+    size_t size() const { return count_; }
+    size_t label_count() const { return multi_ ? label_to_ids_.size() : label_to_id_.size(); }
+    bool reserve(size_t rows);
+    bool flush();
+
+    VecSimQueryReply *topk(const void *q, size_t k, VecSimQueryParams *qp, VecSimQueryReply_Order order);
+    int topk_batch(const void *qs, size_t qstride, size_t nq, size_t k, VecSimQueryParams *qp, size_t *out_labels,
+                   double *out_scores);
+    int topk_batch_device(const void *d_q, size_t nq, size_t k, int64_t *d_labels, float *d_scores, cudaStream_t s);
+    VecSimQueryReply *range(const void *q, double radius, VecSimQueryParams *qp, VecSimQueryReply_Order order);
+    double distance_from(size_t label, const void *stored_form_blob);
+    bool prefer_adhoc(size_t subset, size_t k, bool initial);
+
+    BatchIter *batch_new(const void *q, VecSimQueryParams *qp);
+    VecSimQueryReply *batch_next(BatchIter *it, size_t n, VecSimQueryReply_Order order);
+
+    AdhocCtx *adhoc_new(const void *q);
+    void adhoc_distances(AdhocCtx *c, const size_t *labels, double *out, size_t n);
+
+    VecSimIndexBasicInfo basic_info() const;
+    VecSimIndexStatsInfo stats_info() const;
+    VecSimDebugInfoIterator *debug_iterator() const;
+    void set_last_mode(VecSearchMode m) { last_mode_ = m; }
+    VecSimB200_Stats get_stats(bool reset);
+    const void *device_rows(size_t *pitch, size_t *rows) {
+        flush();
+        *pitch = pitch_;
+        *rows = count_;
+        return d_rows_;
+    }
+
+    size_t query_blob_bytes() const { return stored_bytes_; } // VecSimParams_GetQueryBlobSize
+    void preprocess_query(const void *blob, uint8_t *dst) const;   // -> stored form
+    void preprocess_storage(const void *blob, uint8_t *dst) const; // -> stored form
+
+    VecSimType type_;
+    VecSimMetric metric_;
+    size_t dim_;
+    bool multi_;
+    size_t block_size_;
+    void *log_ctx_;
+
+    void log(const char *level, const char *fmt, ...) const;
+
+  private:
+    FlatIndex() = default;
+    CorpusView view() const;
+    std::unique_ptr<QueryCtx> checkout();
+    void checkin(std::unique_ptr<QueryCtx> c);
+    bool grow_to(size_t rows);
+    bool sync_labels_to_device();
+    bool timed_out(void *ctx) const;
+    // k smallest composites (> cursor) over ctx->d_scores[0..n) into ctx->h_out, chunked by
+    // kMaxFusedK; returns the number found or -1.
+    long select_from_scores(QueryCtx &c, uint32_t n, bool has_cursor, uint64_t cursor, size_t want);
+    bool upload_query(QueryCtx &c, const uint8_t *stored_q, size_t nq);
+    void finish_reply(VecSimQueryReply *rep, VecSimQueryReply_Order order) const;
+
+    DType dtype_;
+    MetricKind mkind_;
+    size_t elem_bytes_ = 0;   // sizeof element
+    size_t stored_bytes_ = 0; // VS/utils/vec_utils.cpp:296-302
+    size_t pitch_ = 0;        // HBM row pitch (>= stored_bytes_)
+
+    uint8_t *d_rows_ = nullptr;
+    size_t capacity_ = 0; // rows of HBM allocated
+    size_t count_ = 0;    // rows in the index (incl. staged)
+    size_t resident_ = 0; // rows already copied to HBM
+    uint8_t *h_stage_ = nullptr; // pinned; rows [resident_, count_)
+    size_t stage_cap_rows_ = 0;
+    cudaStream_t copy_stream_ = nullptr;
+
+    std::vector<size_t> id_to_label_;
+    std::unordered_map<size_t, idType> label_to_id_;
+    std::unordered_map<size_t, std::vector<idType>> label_to_ids_;
+    uint64_t *d_id_to_label_ = nullptr;
+    size_t d_labels_cap_ = 0;
+    bool labels_dirty_ = true;
+
+    mutable std::mutex mu_;      // guards mutation + staging
+    std::mutex pool_mu_;
+    std::vector<std::unique_ptr<QueryCtx>> pool_;
+    mutable VecSearchMode last_mode_ = EMPTY_MODE;
+
+    std::atomic<uint64_t> launches_total_{0};
+    std::unique_ptr<QueryCtx> dev_ctx_; // scratch of topk_batch_device (stream-ordered)
+    std::mutex dev_mu_;
+    bool dev_timing_pending_ = false;
+    uint64_t dev_timing_bytes_ = 0;
+    void collect_dev_timing_locked();
+    std::atomic<uint64_t> scan_launches_{0};
+    std::atomic<uint64_t> scan_bytes_{0};
+    double scan_us_ = 0;
+    std::mutex stats_mu_;
+    friend struct BatchIter;
+};
+
+} // namespace rsb200
