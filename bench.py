@@ -291,6 +291,23 @@ def main():
     dl = out_labels.cpu().numpy()
     agree = bool((dl == h_labels.astype(np.int64)).all())
 
+    # ---- B=1 through the stock VecSimIndex_TopKQuery (what hybrid_reader.c:374 calls): the
+    # north_star's ">= 10x CPU at >= 70% of HBM roofline" figure
+    index.stats(reset=True)
+    q1 = np.ascontiguousarray(q_host_raw[0])
+    for _ in range(3):
+        index.topk(q1, K)
+    index.stats(reset=True)
+    n1 = 20
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n1):
+        index.topk(np.ascontiguousarray(q_host_raw[i % nq]), K)
+    b1_s = (time.perf_counter() - t0) / n1
+    st1 = index.stats(reset=True)
+    b1_scan_us = st1.scan_device_us / max(1, st1.scan_launches)
+    b1_bytes = rows * DIM * 4 + DIM * 4 + K * 12
+
     # ---- roofline of the dominant kernel
     peak, peak_src = load_peaks()
     scan_us = st.scan_device_us / max(1, st.scan_launches) if st.scan_device_us > 0 else None
@@ -319,6 +336,13 @@ def main():
                          "kernel": "scan_topk_kernel<f32,IP,4,8>", "avg_launch_us": scan_us,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
             "clocks": clocks.summary(),
+            "single_query": {"api": "VecSimIndex_TopKQuery (host blob in, reply out)", "value": 1.0 / b1_s,
+                             "unit": "queries/s", "ms_per_query": b1_s * 1000.0,
+                             "roofline": {"bound": "hbm", "achieved": b1_bytes / (b1_scan_us * 1e-6) / 1e9,
+                                          "peak": peak, "unit": "GB/s",
+                                          "frac": b1_bytes / (b1_scan_us * 1e-6) / 1e9 / peak,
+                                          "kernel": "scan_topk_kernel<f32,IP,4,1>", "avg_launch_us": b1_scan_us,
+                                          "algorithmic_bytes_per_launch": b1_bytes}},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -20,6 +20,7 @@ from oracle_lib import BF16, COS, F16, F32, I8, IP, L2, TIER_AVX512, U8
 pytestmark = pytest.mark.gpu
 
 VS_TYPE = {F32: 0, BF16: 2, F16: 3, I8: 4, U8: 5}  # identical numbering by construction
+_KEEPALIVE = []
 
 
 @pytest.fixture(scope="module")
@@ -455,6 +456,8 @@ def test_timeout_callback(vs):
     g = vs.VecSimIndex(F32, 8, L2)
     g.add_many(np.zeros((100, 8), dtype=np.float32), label0=0)
     cb = vs.TIMEOUT_CB(lambda ctx: 1)
+    cb_off = vs.TIMEOUT_CB(lambda ctx: 0)
+    _KEEPALIVE.extend([cb, cb_off])  # ctypes trampolines must outlive their registration
     L.VecSim_SetTimeoutCallbackFunction(cb)
     try:
         q = np.zeros(8, dtype=np.float32)
@@ -464,7 +467,7 @@ def test_timeout_callback(vs):
         assert it.next(5)[2] == vs.VecSim_QueryReply_TimedOut
         it.free()
     finally:
-        L.VecSim_SetTimeoutCallbackFunction(vs.TIMEOUT_CB(lambda ctx: 0))
+        L.VecSim_SetTimeoutCallbackFunction(cb_off)
     assert g.topk(np.zeros(8, dtype=np.float32), 5)[2] == vs.VecSim_QueryReply_OK
 
 
