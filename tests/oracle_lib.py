@@ -280,3 +280,190 @@ def to_type(x32: np.ndarray, vtype: int) -> np.ndarray:
     if vtype == I8:
         return np.rint(127.0 * x32).astype(np.int8)
     return np.rint(127.5 * x32 + 127.5).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# postings / scorers (oracle/postings_oracle.c, scorer_oracle.c, oracle/_ref/libscorers_ref.so)
+# ---------------------------------------------------------------------------------------------
+CODEC_FULL, CODEC_FREQS_ONLY, CODEC_FREQS_FIELDS, CODEC_FIELDS_ONLY, CODEC_DOCIDS_ONLY, CODEC_RAW_DOCIDS_ONLY = range(6)
+SCORER_BM25STD, SCORER_BM25, SCORER_TFIDF, SCORER_TFIDF_DOCNORM, SCORER_DOCSCORE, SCORER_BM25STD_TANH, SCORER_DISMAX = range(7)
+SCORER_NAMES = {SCORER_BM25STD: b"BM25STD", SCORER_BM25: b"BM25", SCORER_TFIDF: b"TFIDF",
+                SCORER_TFIDF_DOCNORM: b"TFIDF.DOCNORM", SCORER_DOCSCORE: b"DOCSCORE",
+                SCORER_BM25STD_TANH: b"BM25STD.TANH", SCORER_DISMAX: b"DISMAX"}
+
+
+class OrcHit(C.Structure):
+    _fields_ = [("doc_id", C.c_uint64), ("n_children", C.c_uint32), ("child_index", C.c_uint32 * 16),
+                ("child_freq", C.c_uint32 * 16)]
+
+
+class OrcScoreDoc(C.Structure):
+    _fields_ = [("n_terms", C.c_uint32), ("freq", C.POINTER(C.c_uint32)), ("idf", C.POINTER(C.c_double)),
+                ("bm25_idf", C.POINTER(C.c_double)), ("weight", C.POINTER(C.c_double)), ("agg_weight", C.c_double),
+                ("doc_len", C.c_uint32), ("max_freq", C.c_uint32), ("doc_score", C.c_float)]
+
+
+class OrcIndexStats(C.Structure):
+    _fields_ = [("num_docs", C.c_uint64), ("num_terms", C.c_uint64), ("avg_doc_len", C.c_double)]
+
+
+_post_bound = False
+
+
+def postings():
+    """liboracle.so with the postings / scorer prototypes bound."""
+    global _post_bound
+    L = port()
+    if not _post_bound:
+        L.orc_qint_encode.restype = _SZ
+        L.orc_qint_encode.argtypes = [_P, C.c_int, _P]
+        L.orc_qint_decode.restype = _SZ
+        L.orc_qint_decode.argtypes = [_P, C.c_int, _P]
+        L.orc_varint_encode.restype = _SZ
+        L.orc_varint_encode.argtypes = [C.c_uint64, _P]
+        L.orc_varint_decode.restype = _SZ
+        L.orc_varint_decode.argtypes = [_P, _P]
+        L.orc_ii_new.restype = _P
+        L.orc_ii_new.argtypes = [C.c_int]
+        L.orc_ii_free.argtypes = [_P]
+        L.orc_ii_add.restype = _SZ
+        L.orc_ii_add.argtypes = [_P, C.c_uint64, C.c_uint32, C.c_uint32, _P, C.c_uint32]
+        L.orc_ii_num_blocks.restype = _SZ
+        L.orc_ii_num_blocks.argtypes = [_P]
+        L.orc_ii_num_docs.restype = _SZ
+        L.orc_ii_num_docs.argtypes = [_P]
+        L.orc_ii_block.argtypes = [_P, _SZ, _P, _P, _P, _P, _P]
+        L.orc_reader_new.restype = _P
+        L.orc_reader_new.argtypes = [_P, C.c_uint32]
+        L.orc_reader_free.argtypes = [_P]
+        L.orc_reader_rewind.argtypes = [_P]
+        L.orc_reader_next.restype = C.c_int
+        L.orc_reader_next.argtypes = [_P, _P, _P, _P]
+        L.orc_reader_seek.restype = C.c_int
+        L.orc_reader_seek.argtypes = [_P, C.c_uint64, _P, _P, _P]
+        L.orc_intersect.restype = _SZ
+        L.orc_intersect.argtypes = [_P, _SZ, _P, _SZ]
+        L.orc_union.restype = _SZ
+        L.orc_union.argtypes = [_P, _SZ, C.c_int, _P, _SZ]
+        L.orc_intersect_skipto.restype = _SZ
+        L.orc_intersect_skipto.argtypes = [_P, _SZ, _P, _SZ, _P, _P]
+        L.orc_union_skipto.restype = _SZ
+        L.orc_union_skipto.argtypes = [_P, _SZ, _P, _SZ, _P, _P]
+        L.orc_idf.restype = C.c_double
+        L.orc_idf.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_idf_bm25.restype = C.c_double
+        L.orc_idf_bm25.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_score.restype = C.c_double
+        L.orc_score.argtypes = [C.c_int, C.POINTER(OrcIndexStats), C.POINTER(OrcScoreDoc), C.c_int, C.c_double, C.c_double]
+        L.orc_synth_df.restype = C.c_uint64
+        L.orc_synth_df.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_synth_member.restype = C.c_int
+        L.orc_synth_member.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, _P]
+        L.orc_synth_doclen.restype = C.c_uint32
+        L.orc_synth_doclen.argtypes = [C.c_uint64]
+        _post_bound = True
+    return L
+
+
+_ref_scorers = None
+
+
+def ref_scorers():
+    global _ref_scorers
+    if _ref_scorers is None:
+        path = os.path.join(ODIR, "_ref", "libscorers_ref.so")
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        L.RefScore.restype = C.c_double
+        L.RefScore.argtypes = [C.c_char_p, C.c_int, _SZ, _P, _P, _P, _P, C.c_double, C.c_uint32, C.c_uint32, C.c_float,
+                               _SZ, C.c_double, C.c_int, C.c_double, C.c_uint64]
+        _ref_scorers = L
+    return _ref_scorers
+
+
+class InvIndex:
+    """oracle InvertedIndex + helpers."""
+
+    def __init__(self, codec, doc_ids=None, freqs=None, masks=None):
+        self.L = postings()
+        self.codec = codec
+        self.h = self.L.orc_ii_new(codec)
+        if doc_ids is not None:
+            for i, d in enumerate(doc_ids):
+                self.add(int(d), int(freqs[i]) if freqs is not None else 1, int(masks[i]) if masks is not None else 1)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_ii_free(self.h)
+            self.h = None
+
+    def add(self, doc_id, freq=1, mask=1, offsets=b""):
+        buf = (C.c_uint8 * max(1, len(offsets))).from_buffer_copy(offsets or b"\0")
+        return self.L.orc_ii_add(self.h, doc_id, freq, mask, buf, len(offsets))
+
+    def num_docs(self):
+        return self.L.orc_ii_num_docs(self.h)
+
+    def blocks(self):
+        out = []
+        for b in range(self.L.orc_ii_num_blocks(self.h)):
+            first, last, n = C.c_uint64(), C.c_uint64(), C.c_uint16()
+            buf, ln = C.POINTER(C.c_uint8)(), C.c_size_t()
+            self.L.orc_ii_block(self.h, b, C.byref(first), C.byref(last), C.byref(n), C.byref(buf), C.byref(ln))
+            out.append((first.value, last.value, n.value, bytes(buf[: ln.value])))
+        return out
+
+    def reader(self, mask=0):
+        return self.L.orc_reader_new(self.h, mask)
+
+    def read_all(self, mask=0):
+        r = self.reader(mask)
+        d, f, m = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        out = []
+        while self.L.orc_reader_next(r, C.byref(d), C.byref(f), C.byref(m)):
+            out.append((d.value, f.value, m.value))
+        self.L.orc_reader_free(r)
+        return out
+
+
+def run_intersect(indexes, union=False, quick=False):
+    """Full iteration; returns list of (docId, [(orig_child, freq), ...])."""
+    L = postings()
+    readers = [ix.reader() for ix in indexes]
+    arr = (C.c_void_p * len(readers))(*readers)
+    cap = max(1, sum(ix.num_docs() for ix in indexes) if union else min(ix.num_docs() for ix in indexes))
+    hits = (OrcHit * cap)()
+    if union:
+        n = L.orc_union(arr, len(readers), int(quick), hits, cap)
+    else:
+        n = L.orc_intersect(arr, len(readers), hits, cap)
+    out = [(hits[i].doc_id, [(hits[i].child_index[j], hits[i].child_freq[j]) for j in range(hits[i].n_children)]) for i in range(n)]
+    for r in readers:
+        L.orc_reader_free(r)
+    return out
+
+
+def oracle_score(scorer, freqs, idf, bm25_idf, weights, agg_weight, doc_len, max_freq, doc_score, num_docs, avg_doc_len,
+                 slop=1, min_score=0.0, tanh_factor=4.0):
+    L = postings()
+    n = len(freqs)
+    fa = (C.c_uint32 * n)(*freqs)
+    ia = (C.c_double * n)(*idf)
+    ba = (C.c_double * n)(*bm25_idf)
+    wa = (C.c_double * n)(*weights)
+    d = OrcScoreDoc(n, fa, ia, ba, wa, agg_weight, doc_len, max_freq, doc_score)
+    st = OrcIndexStats(num_docs, 0, avg_doc_len)
+    return L.orc_score(scorer, C.byref(st), C.byref(d), slop, min_score, tanh_factor)
+
+
+def reference_score(scorer, freqs, idf, bm25_idf, weights, agg_weight, doc_len, max_freq, doc_score, num_docs,
+                    avg_doc_len, slop=1, min_score=0.0, tanh_factor=4, is_union=False):
+    L = ref_scorers()
+    n = len(freqs)
+    fa = (C.c_uint32 * n)(*freqs)
+    ia = (C.c_double * n)(*idf)
+    ba = (C.c_double * n)(*bm25_idf)
+    wa = (C.c_double * n)(*weights)
+    return L.RefScore(SCORER_NAMES[scorer], int(is_union), n, fa, ia, ba, wa, agg_weight, doc_len, max_freq, doc_score,
+                      num_docs, avg_doc_len, slop, min_score, int(tanh_factor))
