@@ -1,0 +1,213 @@
+/* ii_b200.h — C-ABI of libii_b200.so: posting-list intersection / union and BM25 / TF-IDF scoring on
+ * B200, behind the reference's QueryIterator and scorer surfaces.
+ *
+ * How it slots under FT.SEARCH (details and the exact call sites in INTEGRATION.md):
+ *   - term readers are opened by RediSearch as today; their IndexBlocks
+ *     (RS/headers/inverted_index_ffi.h:102-132 IndexBlock_{Data,FirstId,LastId,NumEntries},
+ *     :286 InvertedIndex_BlockRef) are handed to II_PostingList_FromBlocks, which decodes them on the
+ *     host (all cores) or on the device and keeps (docId, freq) arrays resident in HBM;
+ *   - where query evaluation would call NewIntersectionIterator / NewUnionIterator
+ *     (RS/headers/iterators_ffi.h:309,594) over term leaves, it calls II_Intersect / II_Union; the whole
+ *     iterator tree runs as a few kernels and yields an II_ResultSet of ascending docIds;
+ *   - II_Score applies one of the reference's default scorers (src/ext/default.c) to every hit on
+ *     device with the reference's exact expression trees;
+ *   - II_NewResultIterator wraps the result set in an object whose first member is layout-identical
+ *     to the reference's `QueryIterator` (src/iterators/iterator_api.h:46-151): Read / SkipTo / Rewind /
+ *     NumEstimated / Revalidate / Free honour the contract at :88-117, and `current` points at a
+ *     struct layout-identical to `RSIndexResult` (RS/headers/index_result_rs.h:584-621) carrying the
+ *     docId and the pre-computed score as a Metric value, so RPScorer can return it unchanged
+ *     (the "pre-score inside a custom iterator" route of SURVEY.md §8b).
+ * Layouts are checked against tests/golden/ii_abi_layout.txt (generated from the reference headers).
+ *
+ * No CPU fallback: constructors return NULL when no CUDA device is usable.  docIds above 2^32-2 are
+ * not representable on the device (t_docId is 64-bit in the reference; the BASELINE corpora are <= 50M).
+ */
+#ifndef II_B200_H
+#define II_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint64_t t_docId;
+
+/* ---- reference-compatible iterator surface (src/iterators/iterator_api.h) ------------------- */
+typedef enum { ITERATOR_OK = 0, ITERATOR_NOTFOUND = 1, ITERATOR_EOF = 2, ITERATOR_TIMEOUT = 3 } IteratorStatus;
+typedef enum { VALIDATE_OK = 0, VALIDATE_MOVED = 1, VALIDATE_ABORTED = 2, VALIDATE_TIMEOUT = 3 } ValidateStatus;
+/* RS/headers/rqe_iterator_type.h */
+enum { II_IteratorType_Union = 6, II_IteratorType_Intersect = 7, II_IteratorType_Empty = 13,
+       II_IteratorType_MetricSortedById = 16 };
+/* RS/headers/index_result_rs.h RawResultData_Active_Tag */
+enum { II_ResultData_Union = 1, II_ResultData_Intersection = 2, II_ResultData_Term = 4, II_ResultData_Virtual = 8,
+       II_ResultData_Numeric = 16, II_ResultData_Metric = 32 };
+
+/* Layout-identical to RSIndexResult (112 bytes): docId@0 dmd@8 fieldMask@16 freq@32 data@40
+ * metrics@80 weight@88 hasFieldExpiration@96. */
+typedef struct II_IndexResult {
+    t_docId docId;
+    const void *dmd;            /* RSDocumentMetadata*, filled by RPQueryIterator's DocTable_Borrow */
+    unsigned __int128 fieldMask; /* t_fieldMask */
+    uint32_t freq;              /* aggregate freq = sum over matched children */
+    struct {
+        uint8_t tag;            /* II_ResultData_Metric */
+        uint8_t _pad[7];
+        double metric;          /* the pre-computed score (or 0 when unscored) */
+        uint8_t _rest[24];
+    } data;
+    void *metrics;              /* MetricsVec: empty */
+    double weight;
+    bool hasFieldExpiration;
+} II_IndexResult;
+
+struct IndexSpec;
+/* Layout-identical to QueryIterator (88 bytes). */
+typedef struct II_QueryIterator {
+    uint32_t type; /* enum IteratorType */
+    bool atEOF;
+    t_docId lastDocId;
+    II_IndexResult *current;
+    size_t (*NumEstimated)(const struct II_QueryIterator *self);
+    IteratorStatus (*Read)(struct II_QueryIterator *self);
+    IteratorStatus (*SkipTo)(struct II_QueryIterator *self, t_docId docId);
+    ValidateStatus (*Revalidate)(struct II_QueryIterator *self, struct IndexSpec *spec);
+    void (*Free)(struct II_QueryIterator *self);
+    void (*Rewind)(struct II_QueryIterator *self);
+    struct II_QueryIterator *(*ProfileChildren)(struct II_QueryIterator *self);
+    void (*PrintProfile)(const struct II_QueryIterator *self, void *map, void *ctx);
+} II_QueryIterator;
+
+/* RSIndexStats (src/redisearch.h:245-249) */
+typedef struct {
+    size_t numDocs;
+    size_t numTerms;
+    double avgDocLen;
+} II_IndexStats;
+
+/* ---- posting lists ---------------------------------------------------------------------------- */
+typedef enum {
+    II_CODEC_FULL = 0,        /* qint4[delta,freq,fieldMask,offsetsLen]+offsets  RS/inverted_index/src/codec/full.rs:66-69 */
+    II_CODEC_FREQS_ONLY = 1,  /* qint2[delta,freq]                               codec/freqs_only.rs:33 */
+    II_CODEC_FREQS_FIELDS = 2,/* qint3[delta,freq,fieldMask]                     codec/freqs_fields.rs:43 */
+    II_CODEC_FIELDS_ONLY = 3, /* qint2[delta,fieldMask]                          codec/fields_only.rs:43 */
+    II_CODEC_DOCIDS_ONLY = 4, /* varint(delta)                                   codec/doc_ids_only.rs:33 */
+    II_CODEC_RAW_DOCIDS_ONLY = 5 /* u32 (docId - block.first_doc_id)             codec/raw_doc_ids_only.rs:31-37 */
+} II_Codec;
+
+/* One IndexBlock as the reference exposes it (RS/inverted_index/src/index/core.rs:76-94). */
+typedef struct {
+    uint64_t first_doc_id;
+    uint64_t last_doc_id;
+    uint16_t num_entries;
+    const uint8_t *data;
+    size_t len;
+} II_BlockView;
+
+typedef struct II_PostingList II_PostingList; /* (docId u32, freq u32) arrays resident in HBM */
+
+/* Decode `nblocks` IndexBlocks into a device-resident posting list.  field_mask_filter != 0 keeps only
+ * records with (fieldMask & filter) != 0, like FilterMaskReader (RS/inverted_index/src/reader/field_mask.rs);
+ * the estimate reported to the intersection sort stays the unfiltered entry count.
+ * decode_on_device: 0 = host decode on all cores then one H2D copy; 1 = ship the raw block bytes and
+ * decode in a kernel (one thread per block). */
+II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nblocks, II_Codec codec,
+                                          uint32_t field_mask_filter, int decode_on_device);
+/* From already-decoded host arrays (freqs may be NULL = all 1).  docIds strictly ascending. */
+II_PostingList *II_PostingList_FromArrays(const uint64_t *doc_ids, const uint32_t *freqs, size_t n);
+/* Adopt COPIES of device arrays (docIds u32 ascending, freqs u32). */
+II_PostingList *II_PostingList_FromDevice(const uint32_t *d_doc_ids, const uint32_t *d_freqs, size_t n);
+size_t II_PostingList_Len(const II_PostingList *pl);
+size_t II_PostingList_NumEstimated(const II_PostingList *pl); /* InvIndIterator::num_estimated = unique_docs */
+void II_PostingList_Free(II_PostingList *pl);
+
+/* ---- per-document metadata the scorers read (RSDocumentMetadata: score, docLen, maxTermFreq) ---- */
+typedef struct II_DocTable II_DocTable;
+/* Arrays are indexed by docId (entry 0 unused); any of them may be NULL (docLen defaults to 0,
+ * score to 1.0f, maxFreq to 1). */
+II_DocTable *II_DocTable_New(size_t max_doc_id, const uint32_t *doc_len, const float *doc_score,
+                             const uint32_t *max_term_freq);
+/* Same from device arrays (copied). */
+II_DocTable *II_DocTable_FromDevice(size_t max_doc_id, const uint32_t *d_doc_len, const float *d_doc_score,
+                                    const uint32_t *d_max_term_freq);
+void II_DocTable_Free(II_DocTable *dt);
+
+/* ---- iterator algebra on device ---------------------------------------------------------------- */
+typedef struct II_ResultSet II_ResultSet;
+
+/* AND of n (1..16) posting lists: ascending docIds present in all of them — Intersection::read
+ * (RS/rqe_iterators/src/intersection.rs:428-452) run to EOF.  Children are ordered by
+ * num_estimated ascending, stable, exactly like Intersection::new (:103-169); per-hit child freqs
+ * are kept in that order for the scorers. */
+II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n);
+/* OR of n (1..16) posting lists — UnionFlat::read_full (RS/rqe_iterators/src/union_flat.rs:324-348)
+ * run to EOF; quick_exit != 0 keeps docIds only (quick mode reports a single child, :433-524). */
+II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit);
+size_t II_ResultSet_Len(const II_ResultSet *rs);
+void II_ResultSet_Free(II_ResultSet *rs);
+
+/* ---- scoring ------------------------------------------------------------------------------------ */
+typedef enum {
+    II_SCORER_BM25STD = 0,      /* default scorer; src/ext/default.c:241-316 */
+    II_SCORER_BM25 = 1,         /* legacy; :164-233 (slop taken as 1: offsets are not shipped) */
+    II_SCORER_TFIDF = 2,        /* :68-146 (slop 1) */
+    II_SCORER_TFIDF_DOCNORM = 3,/* :148-153 */
+    II_SCORER_DOCSCORE = 4,     /* :366-371 */
+    II_SCORER_BM25STD_TANH = 5, /* :339-359 */
+    II_SCORER_DISMAX = 6        /* :378-461 */
+} II_Scorer;
+
+/* Per query term, in the ORIGINAL order of the `lists` argument. */
+typedef struct {
+    double weight;   /* leaf result weight (query node weight, default 1.0) */
+    double idf;      /* QueryTerm_GetIDF      — II_CalculateIDF      */
+    double bm25_idf; /* QueryTerm_GetBM25_IDF — II_CalculateIDF_BM25 */
+} II_TermParams;
+
+double II_CalculateIDF(size_t total_docs, size_t term_docs);      /* RS/idf/src/lib.rs:67 */
+double II_CalculateIDF_BM25(size_t total_docs, size_t term_docs); /* RS/idf/src/lib.rs:103 */
+
+/* Score every hit of `rs` on device.  agg_weight = weight of the intersection/union node.
+ * Returns 0, or -1 on failure. */
+int II_Score(II_ResultSet *rs, II_Scorer scorer, const II_TermParams *terms, double agg_weight,
+             const II_IndexStats *stats, const II_DocTable *docs, double min_score, uint64_t tanh_factor);
+
+/* Copy results to the host.  Any output pointer may be NULL.  child_freqs is [n_children][len]
+ * (children in aggregate order; 0 = child absent, union only).  scores are 0 before II_Score. */
+int II_ResultSet_Fetch(const II_ResultSet *rs, uint64_t *doc_ids, double *scores, uint32_t *child_freqs);
+size_t II_ResultSet_NumChildren(const II_ResultSet *rs);
+/* child_order[i] = index in the `lists` argument of aggregate child i. */
+void II_ResultSet_ChildOrder(const II_ResultSet *rs, uint32_t *child_order);
+/* Best `n` hits by (score desc, docId asc) — RPSorter's cmpByScore, src/result_processor.c:834-850 —
+ * selected on device.  Returns the number written. */
+size_t II_ResultSet_TopN(const II_ResultSet *rs, size_t n, uint64_t *doc_ids, double *scores);
+/* Device views (valid until the result set is freed): docIds u32[len], scores f64[len]. */
+const uint32_t *II_ResultSet_DeviceDocIds(const II_ResultSet *rs);
+const double *II_ResultSet_DeviceScores(const II_ResultSet *rs);
+
+/* One call for the common query: AND (or OR) of term lists, score, top-N; host arrays out. */
+size_t II_SearchTopN(II_PostingList *const *lists, size_t n, int is_union, II_Scorer scorer,
+                     const II_TermParams *terms, double agg_weight, const II_IndexStats *stats,
+                     const II_DocTable *docs, size_t top_n, uint64_t *doc_ids, double *scores, size_t *total_hits);
+
+/* ---- QueryIterator facade ------------------------------------------------------------------------ */
+/* Takes ownership of `rs` (downloads docIds/scores once).  Free through it->Free(it). */
+II_QueryIterator *II_NewResultIterator(II_ResultSet *rs, double weight);
+
+/* ---- statistics for bench / roofline ---------------------------------------------------------------- */
+typedef struct {
+    uint64_t kernel_launches;
+    double intersect_device_us; /* CUDA-event time of the last II_Intersect / II_Union kernels */
+    double score_device_us;     /* ... of the last II_Score */
+    double decode_host_us;      /* host decode wall time of the last II_PostingList_FromBlocks */
+    double h2d_us;
+} II_Stats;
+II_Stats II_GetStats(bool reset);
+const char *II_Version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* II_B200_H */

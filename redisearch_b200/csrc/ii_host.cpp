@@ -1,0 +1,795 @@
+// Host side of libii_b200.so: posting-list objects, block decoding, the iterator algebra entry
+// points, scoring, ranking and the QueryIterator facade.  Contract: include/ii_b200.h.
+#include "../../include/ii_b200.h"
+#include "ii_kernels.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+using namespace rsb200;
+
+namespace {
+
+struct Ctx { // one stream; calls are serialised (RediSearch runs one iterator tree per worker thread)
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    uint32_t *d_total = nullptr, *h_total = nullptr;
+    II_Stats stats{};
+    bool ok = false;
+    bool init() {
+        if (ok) return true;
+        int nd = 0;
+        if (cudaGetDeviceCount(&nd) != cudaSuccess || nd <= 0) {
+            cudaGetLastError();
+            fprintf(stderr, "ii_b200: no CUDA device available; this library has no CPU fallback\n");
+            return false;
+        }
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        if (cudaMalloc(&d_total, 16) != cudaSuccess || cudaMallocHost(&h_total, 16) != cudaSuccess) return false;
+        ok = true;
+        return true;
+    }
+};
+Ctx &ctx() {
+    static Ctx c;
+    return c;
+}
+
+template <typename T>
+T *dalloc(size_t n) {
+    T *p = nullptr;
+    if (n == 0) n = 1;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+struct II_PostingList {
+    uint32_t *d_ids = nullptr, *d_freqs = nullptr;
+    size_t n = 0;
+    size_t estimated = 0; // unfiltered unique docs (num_estimated of the leaf iterator)
+    uint32_t last_id = 0;
+    ~II_PostingList() {
+        cudaFree(d_ids);
+        cudaFree(d_freqs);
+    }
+};
+
+struct II_DocTable {
+    uint32_t *d_len = nullptr, *d_maxf = nullptr;
+    float *d_score = nullptr;
+    size_t max_doc = 0;
+    ~II_DocTable() {
+        cudaFree(d_len);
+        cudaFree(d_maxf);
+        cudaFree(d_score);
+    }
+};
+
+struct II_ResultSet {
+    uint32_t *d_docs = nullptr, *d_freqs = nullptr; // freqs [n_children][cap]
+    double *d_scores = nullptr;
+    size_t cap = 0, len = 0;
+    uint32_t n_children = 0;
+    uint32_t child_order[kIIMaxLists] = {0};
+    bool is_union = false, has_freqs = true, scored = false;
+    ~II_ResultSet() {
+        cudaFree(d_docs);
+        cudaFree(d_freqs);
+        cudaFree(d_scores);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// host decoders (one block at a time; blocks are independent: the delta base restarts at first_doc_id)
+// ------------------------------------------------------------------------------------------------
+namespace {
+inline uint32_t rd(const uint8_t *p, int nb) {
+    uint32_t v = p[0];
+    if (nb > 1) v |= (uint32_t)p[1] << 8;
+    if (nb > 2) v |= (uint32_t)p[2] << 16;
+    if (nb > 3) v |= (uint32_t)p[3] << 24;
+    return v;
+}
+// returns false on a malformed block (cursor ran past the buffer)
+bool decode_block(const II_BlockView &b, II_Codec codec, uint32_t *ids, uint32_t *freqs, uint32_t *masks) {
+    const uint8_t *p = b.data, *end = b.data + b.len;
+    uint64_t last = b.first_doc_id;
+    for (uint32_t e = 0; e < b.num_entries; e++) {
+        uint32_t freq = 1, mask = 0xFFFFFFFFu;
+        uint64_t id;
+        if (p >= end) return false;
+        switch (codec) {
+        case II_CODEC_RAW_DOCIDS_ONLY:
+            if (p + 4 > end) return false;
+            id = b.first_doc_id + rd(p, 4);
+            p += 4;
+            break;
+        case II_CODEC_DOCIDS_ONLY: {
+            uint8_t c = *p++;
+            uint64_t val = c & 0x7f;
+            while (c & 0x80) {
+                if (p >= end) return false;
+                val += 1;
+                c = *p++;
+                val = (val << 7) | (c & 0x7f);
+            }
+            id = last + val;
+            break;
+        }
+        default: {
+            const uint8_t lead = *p++;
+            const int nvals = (codec == II_CODEC_FULL) ? 4 : (codec == II_CODEC_FREQS_FIELDS) ? 3 : 2;
+            uint32_t v[4] = {0, 0, 0, 0};
+            for (int i = 0; i < nvals; i++) {
+                const int nb = ((lead >> (2 * i)) & 3) + 1;
+                if (p + nb > end) return false;
+                v[i] = rd(p, nb);
+                p += nb;
+            }
+            id = last + v[0];
+            if (codec == II_CODEC_FULL) {
+                freq = v[1];
+                mask = v[2];
+                if (p + v[3] > end) return false;
+                p += v[3];
+            } else if (codec == II_CODEC_FREQS_ONLY) {
+                freq = v[1];
+            } else if (codec == II_CODEC_FREQS_FIELDS) {
+                freq = v[1];
+                mask = v[2];
+            } else {
+                mask = v[1];
+            }
+        }
+        }
+        if (id > 0xFFFFFFFEull) return false;
+        last = id;
+        ids[e] = (uint32_t)id;
+        freqs[e] = freq;
+        if (masks) masks[e] = mask;
+    }
+    return true;
+}
+} // namespace
+
+extern "C" {
+
+II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nblocks, II_Codec codec,
+                                          uint32_t field_mask_filter, int decode_on_device) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    std::vector<uint32_t> entry_off(nblocks + 1, 0);
+    std::vector<uint64_t> byte_off(nblocks + 1, 0);
+    for (size_t b = 0; b < nblocks; b++) {
+        entry_off[b + 1] = entry_off[b] + blocks[b].num_entries;
+        byte_off[b + 1] = byte_off[b] + blocks[b].len;
+        if (blocks[b].last_doc_id > 0xFFFFFFFEull) return nullptr;
+    }
+    const size_t n = entry_off[nblocks];
+    auto *pl = new II_PostingList();
+    pl->estimated = n;
+    const bool need_mask = field_mask_filter != 0 &&
+                           (codec == II_CODEC_FULL || codec == II_CODEC_FREQS_FIELDS || codec == II_CODEC_FIELDS_ONLY);
+    uint32_t *d_ids = dalloc<uint32_t>(n), *d_freqs = dalloc<uint32_t>(n), *d_masks = need_mask ? dalloc<uint32_t>(n) : nullptr;
+    bool ok = d_ids && d_freqs && (!need_mask || d_masks);
+    if (ok && n) {
+        if (decode_on_device) {
+            // ship the raw block bytes, decode with one thread per block
+            std::vector<uint8_t> bytes(byte_off[nblocks]);
+            std::vector<uint64_t> first(nblocks);
+            for (size_t b = 0; b < nblocks; b++) {
+                memcpy(bytes.data() + byte_off[b], blocks[b].data, blocks[b].len);
+                first[b] = blocks[b].first_doc_id;
+            }
+            uint8_t *d_bytes = dalloc<uint8_t>(bytes.size() + 8);
+            uint64_t *d_boff = dalloc<uint64_t>(nblocks + 1), *d_first = dalloc<uint64_t>(nblocks);
+            uint32_t *d_eoff = dalloc<uint32_t>(nblocks + 1);
+            ok = d_bytes && d_boff && d_first && d_eoff;
+            const double t0 = now_us();
+            ok = ok && cudaMemcpyAsync(d_bytes, bytes.data(), bytes.size(), cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(d_boff, byte_off.data(), (nblocks + 1) * 8, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(d_first, first.data(), nblocks * 8, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(d_eoff, entry_off.data(), (nblocks + 1) * 4, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+            ok = ok && ii_launch_decode(d_bytes, d_boff, d_first, d_eoff, (uint32_t)nblocks, (int)codec, d_ids, d_freqs, d_masks,
+                                        c.stream) == cudaSuccess;
+            ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+            c.stats.h2d_us = now_us() - t0;
+            c.stats.decode_host_us = 0;
+            c.stats.kernel_launches += 1;
+            cudaFree(d_bytes);
+            cudaFree(d_boff);
+            cudaFree(d_first);
+            cudaFree(d_eoff);
+        } else {
+            uint32_t *h_ids = nullptr, *h_freqs = nullptr, *h_masks = nullptr;
+            ok = cudaMallocHost(&h_ids, n * 4) == cudaSuccess && cudaMallocHost(&h_freqs, n * 4) == cudaSuccess &&
+                 (!need_mask || cudaMallocHost(&h_masks, n * 4) == cudaSuccess);
+            if (ok) {
+                const double t0 = now_us();
+                unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 64u, (unsigned)(nblocks / 256 + 1)}));
+                std::vector<std::thread> th;
+                std::vector<char> good(nt, 1);
+                for (unsigned t = 0; t < nt; t++)
+                    th.emplace_back([&, t] {
+                        for (size_t b = t; b < nblocks; b += nt)
+                            if (!decode_block(blocks[b], codec, h_ids + entry_off[b], h_freqs + entry_off[b],
+                                              h_masks ? h_masks + entry_off[b] : nullptr))
+                                good[t] = 0;
+                    });
+                for (auto &x : th) x.join();
+                for (char gd : good) ok = ok && gd;
+                c.stats.decode_host_us = now_us() - t0;
+                const double t1 = now_us();
+                ok = ok && cudaMemcpyAsync(d_ids, h_ids, n * 4, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+                ok = ok && cudaMemcpyAsync(d_freqs, h_freqs, n * 4, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+                if (need_mask) ok = ok && cudaMemcpyAsync(d_masks, h_masks, n * 4, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+                ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+                c.stats.h2d_us = now_us() - t1;
+            }
+            cudaFreeHost(h_ids);
+            cudaFreeHost(h_freqs);
+            cudaFreeHost(h_masks);
+        }
+    }
+    size_t kept = n;
+    if (ok && need_mask && n) { // FilterMaskReader: drop records whose mask misses the filter, order kept
+        const uint32_t chunks = (uint32_t)((n + 1023) / 1024);
+        uint32_t *d_counts = dalloc<uint32_t>(chunks), *d_offs = dalloc<uint32_t>(chunks);
+        uint32_t *d_ids2 = dalloc<uint32_t>(n), *d_freqs2 = dalloc<uint32_t>(n);
+        ok = d_counts && d_offs && d_ids2 && d_freqs2;
+        ok = ok && ii_launch_mask_filter(d_ids, d_freqs, d_masks, (uint32_t)n, field_mask_filter, d_counts, d_offs, c.d_total,
+                                         d_ids2, d_freqs2, c.stream) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(c.h_total, c.d_total, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+        c.stats.kernel_launches += 3;
+        if (ok) {
+            kept = *c.h_total;
+            std::swap(d_ids, d_ids2);
+            std::swap(d_freqs, d_freqs2);
+        }
+        cudaFree(d_ids2);
+        cudaFree(d_freqs2);
+        cudaFree(d_counts);
+        cudaFree(d_offs);
+    }
+    cudaFree(d_masks);
+    if (!ok) {
+        cudaFree(d_ids);
+        cudaFree(d_freqs);
+        delete pl;
+        return nullptr;
+    }
+    pl->d_ids = d_ids;
+    pl->d_freqs = d_freqs;
+    pl->n = kept;
+    if (kept) cudaMemcpy(&pl->last_id, d_ids + kept - 1, 4, cudaMemcpyDeviceToHost);
+    return pl;
+}
+
+II_PostingList *II_PostingList_FromArrays(const uint64_t *doc_ids, const uint32_t *freqs, size_t n) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    std::vector<uint32_t> ids32(n), f32(n, 1);
+    for (size_t i = 0; i < n; i++) {
+        if (doc_ids[i] > 0xFFFFFFFEull || (i && doc_ids[i] <= doc_ids[i - 1])) return nullptr;
+        ids32[i] = (uint32_t)doc_ids[i];
+        if (freqs) f32[i] = freqs[i];
+    }
+    auto *pl = new II_PostingList();
+    pl->d_ids = dalloc<uint32_t>(n);
+    pl->d_freqs = dalloc<uint32_t>(n);
+    if (!pl->d_ids || !pl->d_freqs ||
+        (n && (cudaMemcpy(pl->d_ids, ids32.data(), n * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+               cudaMemcpy(pl->d_freqs, f32.data(), n * 4, cudaMemcpyHostToDevice) != cudaSuccess))) {
+        delete pl;
+        return nullptr;
+    }
+    pl->n = pl->estimated = n;
+    pl->last_id = n ? ids32[n - 1] : 0;
+    return pl;
+}
+
+II_PostingList *II_PostingList_FromDevice(const uint32_t *d_doc_ids, const uint32_t *d_freqs, size_t n) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    auto *pl = new II_PostingList();
+    pl->d_ids = dalloc<uint32_t>(n);
+    pl->d_freqs = dalloc<uint32_t>(n);
+    bool ok = pl->d_ids && pl->d_freqs;
+    if (ok && n) {
+        ok = cudaMemcpy(pl->d_ids, d_doc_ids, n * 4, cudaMemcpyDeviceToDevice) == cudaSuccess;
+        if (d_freqs)
+            ok = ok && cudaMemcpy(pl->d_freqs, d_freqs, n * 4, cudaMemcpyDeviceToDevice) == cudaSuccess;
+        else {
+            std::vector<uint32_t> ones(n, 1);
+            ok = ok && cudaMemcpy(pl->d_freqs, ones.data(), n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+        ok = ok && cudaMemcpy(&pl->last_id, pl->d_ids + n - 1, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    if (!ok) {
+        delete pl;
+        return nullptr;
+    }
+    pl->n = pl->estimated = n;
+    return pl;
+}
+
+size_t II_PostingList_Len(const II_PostingList *pl) { return pl->n; }
+size_t II_PostingList_NumEstimated(const II_PostingList *pl) { return pl->estimated; }
+void II_PostingList_Free(II_PostingList *pl) { delete pl; }
+
+// ------------------------------------------------------------------------------------------------
+static II_DocTable *doctable_from(size_t max_doc_id, const uint32_t *len, const float *score, const uint32_t *maxf,
+                                  cudaMemcpyKind kind) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    auto *dt = new II_DocTable();
+    dt->max_doc = max_doc_id;
+    const size_t n = max_doc_id + 1;
+    bool ok = true;
+    if (len) {
+        dt->d_len = dalloc<uint32_t>(n);
+        ok = ok && dt->d_len && cudaMemcpy(dt->d_len, len, n * 4, kind) == cudaSuccess;
+    }
+    if (score) {
+        dt->d_score = dalloc<float>(n);
+        ok = ok && dt->d_score && cudaMemcpy(dt->d_score, score, n * 4, kind) == cudaSuccess;
+    }
+    if (maxf) {
+        dt->d_maxf = dalloc<uint32_t>(n);
+        ok = ok && dt->d_maxf && cudaMemcpy(dt->d_maxf, maxf, n * 4, kind) == cudaSuccess;
+    }
+    if (!ok) {
+        delete dt;
+        return nullptr;
+    }
+    return dt;
+}
+II_DocTable *II_DocTable_New(size_t max_doc_id, const uint32_t *doc_len, const float *doc_score, const uint32_t *max_term_freq) {
+    return doctable_from(max_doc_id, doc_len, doc_score, max_term_freq, cudaMemcpyHostToDevice);
+}
+II_DocTable *II_DocTable_FromDevice(size_t max_doc_id, const uint32_t *d_doc_len, const float *d_doc_score,
+                                    const uint32_t *d_max_term_freq) {
+    return doctable_from(max_doc_id, d_doc_len, d_doc_score, d_max_term_freq, cudaMemcpyDeviceToDevice);
+}
+void II_DocTable_Free(II_DocTable *dt) { delete dt; }
+
+// ------------------------------------------------------------------------------------------------
+// AND
+// ------------------------------------------------------------------------------------------------
+II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n) {
+    if (n == 0 || n > (size_t)kIIMaxLists) return nullptr;
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    // Intersection::new: stable sort ascending by num_estimated (leaf weight 1.0), intersection.rs:110-145
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](uint32_t a, uint32_t b) { return lists[a]->estimated < lists[b]->estimated; });
+    // the kernel is driven by the list with the fewest actual entries (a field-mask filter may make
+    // that differ from the estimate order); the aggregate child order stays the reference's
+    size_t drv = 0;
+    for (size_t i = 1; i < n; i++)
+        if (lists[order[i]]->n < lists[order[drv]]->n) drv = i;
+    auto *rs = new II_ResultSet();
+    rs->n_children = (uint32_t)n;
+    for (size_t i = 0; i < n; i++) rs->child_order[i] = order[i];
+    const II_PostingList *A = lists[order[drv]];
+    bool empty = false;
+    for (size_t i = 0; i < n; i++) empty |= lists[i]->n == 0;
+    if (empty) return rs;
+    const uint32_t nchunks = (uint32_t)((A->n + kIIChunk - 1) / kIIChunk);
+    const size_t stride = (size_t)nchunks * kIIChunk;
+    rs->cap = A->n;
+    rs->d_docs = dalloc<uint32_t>(rs->cap);
+    rs->d_freqs = dalloc<uint32_t>(rs->cap * n);
+    rs->d_scores = dalloc<double>(rs->cap);
+    uint32_t *tmp_idx = dalloc<uint32_t>(stride), *tmp_pos = dalloc<uint32_t>(stride * n);
+    uint32_t *counts = dalloc<uint32_t>(nchunks), *offsets = dalloc<uint32_t>(nchunks);
+    bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && tmp_idx && tmp_pos && counts && offsets;
+    if (ok) {
+        // kernel list order: driver first, then the rest ascending by length (cheap rejections first)
+        std::vector<uint32_t> korder;
+        korder.push_back((uint32_t)drv);
+        std::vector<uint32_t> rest;
+        for (size_t i = 0; i < n; i++)
+            if (i != drv) rest.push_back((uint32_t)i);
+        std::stable_sort(rest.begin(), rest.end(), [&](uint32_t a, uint32_t b) { return lists[order[a]]->n < lists[order[b]]->n; });
+        korder.insert(korder.end(), rest.begin(), rest.end());
+        IntersectArgs a{};
+        a.n = (uint32_t)n;
+        for (size_t i = 0; i < n; i++) {
+            a.ids[i] = lists[order[korder[i]]]->d_ids;
+            a.len[i] = (uint32_t)lists[order[korder[i]]]->n;
+        }
+        a.tmp_idx = tmp_idx;
+        a.tmp_pos = tmp_pos;
+        a.counts = counts;
+        a.stride = stride;
+        cudaEventRecord(c.e0, c.stream);
+        ok = ii_launch_intersect(a, nchunks, offsets, c.d_total, c.stream) == cudaSuccess;
+        // gather in AGGREGATE child order: kernel slot k holds aggregate child korder[k]
+        GatherArgs ga{};
+        ga.ids0 = A->d_ids;
+        ga.n = (uint32_t)n;
+        ga.tmp_idx = tmp_idx;
+        ga.tmp_pos = tmp_pos;
+        ga.counts = counts;
+        ga.offsets = offsets;
+        ga.stride = stride;
+        ga.out_doc = rs->d_docs;
+        ga.fstride = rs->cap;
+        // out_freq row for kernel slot k must land at aggregate row korder[k]: gather writes row j of
+        // its own numbering, so hand it a per-slot base through the freqs/out mapping below
+        for (size_t k = 0; k < n; k++) ga.freqs[k] = lists[order[korder[k]]]->d_freqs;
+        // rows are written in kernel-slot order into a scratch, then permuted by row copies
+        uint32_t *scratch = (n > 1) ? dalloc<uint32_t>(rs->cap * n) : rs->d_freqs;
+        ok = ok && scratch;
+        ga.out_freq = scratch;
+        ok = ok && ii_launch_gather(ga, nchunks, c.stream) == cudaSuccess;
+        if (ok && n > 1)
+            for (size_t k = 0; k < n; k++)
+                ok = ok && cudaMemcpyAsync(rs->d_freqs + (size_t)korder[k] * rs->cap, scratch + k * rs->cap, rs->cap * 4,
+                                           cudaMemcpyDeviceToDevice, c.stream) == cudaSuccess;
+        cudaEventRecord(c.e1, c.stream);
+        ok = ok && cudaMemcpyAsync(c.h_total, c.d_total, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+        if (n > 1) cudaFree(scratch);
+        if (ok) {
+            rs->len = *c.h_total;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c.e0, c.e1);
+            c.stats.intersect_device_us = ms * 1000.0;
+            c.stats.kernel_launches += 3;
+        }
+    }
+    cudaFree(tmp_idx);
+    cudaFree(tmp_pos);
+    cudaFree(counts);
+    cudaFree(offsets);
+    if (!ok) {
+        delete rs;
+        return nullptr;
+    }
+    return rs;
+}
+
+// ------------------------------------------------------------------------------------------------
+// OR
+// ------------------------------------------------------------------------------------------------
+II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit) {
+    if (n == 0 || n > (size_t)kIIMaxLists) return nullptr;
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    auto *rs = new II_ResultSet();
+    rs->is_union = true;
+    rs->n_children = (uint32_t)n;
+    rs->has_freqs = !quick_exit;
+    for (size_t i = 0; i < n; i++) rs->child_order[i] = (uint32_t)i;
+    uint32_t max_id = 0;
+    size_t total_in = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (lists[i]->n) max_id = std::max(max_id, lists[i]->last_id);
+        total_in += lists[i]->n;
+    }
+    if (total_in == 0) return rs;
+    const uint32_t nwords = max_id / 32 + 1, nblk = (nwords + 31) / 32;
+    rs->cap = std::min<size_t>(total_in, (size_t)max_id + 1);
+    rs->d_docs = dalloc<uint32_t>(rs->cap);
+    rs->d_freqs = dalloc<uint32_t>(rs->has_freqs ? rs->cap * n : 1);
+    rs->d_scores = dalloc<double>(rs->cap);
+    uint32_t *bitmap = dalloc<uint32_t>(nwords), *blocksum = dalloc<uint32_t>(nblk), *blockoff = dalloc<uint32_t>(nblk);
+    uint32_t *wordoff = dalloc<uint32_t>(nwords);
+    bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && bitmap && blocksum && blockoff && wordoff;
+    if (ok) {
+        std::vector<const uint32_t *> ids(n), freqs(n);
+        std::vector<uint32_t> lens(n);
+        for (size_t i = 0; i < n; i++) {
+            ids[i] = lists[i]->d_ids;
+            freqs[i] = lists[i]->d_freqs;
+            lens[i] = (uint32_t)lists[i]->n;
+        }
+        cudaEventRecord(c.e0, c.stream);
+        if (rs->has_freqs) ok = cudaMemsetAsync(rs->d_freqs, 0, rs->cap * n * 4, c.stream) == cudaSuccess;
+        ok = ok && ii_launch_union(ids.data(), freqs.data(), lens.data(), (uint32_t)n, nwords, bitmap, blocksum, blockoff, wordoff,
+                                   c.d_total, rs->d_docs, rs->d_freqs, rs->cap, rs->has_freqs, c.stream) == cudaSuccess;
+        cudaEventRecord(c.e1, c.stream);
+        ok = ok && cudaMemcpyAsync(c.h_total, c.d_total, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+        if (ok) {
+            rs->len = *c.h_total;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c.e0, c.e1);
+            c.stats.intersect_device_us = ms * 1000.0;
+            c.stats.kernel_launches += 3 + 2 * n;
+        }
+    }
+    cudaFree(bitmap);
+    cudaFree(blocksum);
+    cudaFree(blockoff);
+    cudaFree(wordoff);
+    if (!ok) {
+        delete rs;
+        return nullptr;
+    }
+    return rs;
+}
+
+size_t II_ResultSet_Len(const II_ResultSet *rs) { return rs->len; }
+size_t II_ResultSet_NumChildren(const II_ResultSet *rs) { return rs->n_children; }
+void II_ResultSet_ChildOrder(const II_ResultSet *rs, uint32_t *child_order) {
+    for (uint32_t i = 0; i < rs->n_children; i++) child_order[i] = rs->child_order[i];
+}
+void II_ResultSet_Free(II_ResultSet *rs) { delete rs; }
+const uint32_t *II_ResultSet_DeviceDocIds(const II_ResultSet *rs) { return rs->d_docs; }
+const double *II_ResultSet_DeviceScores(const II_ResultSet *rs) { return rs->d_scores; }
+
+// ------------------------------------------------------------------------------------------------
+// scoring
+// ------------------------------------------------------------------------------------------------
+double II_CalculateIDF(size_t total_docs, size_t term_docs) { // RS/idf/src/lib.rs:36-70
+    if (term_docs == 0) term_docs = 1;
+    const double value = 1.0 + (double)(total_docs + 1) / (double)term_docs;
+    uint64_t bits;
+    memcpy(&bits, &value, 8);
+    return (double)((int)((bits >> 52) & 0x7FF) - 1023);
+}
+double II_CalculateIDF_BM25(size_t total_docs, size_t term_docs) { // :103-110
+    total_docs = std::max(total_docs, term_docs);
+    const double total = (double)total_docs, term = (double)term_docs;
+    return std::log(1.0 + (total - term + 0.5) / (term + 0.5));
+}
+
+int II_Score(II_ResultSet *rs, II_Scorer scorer, const II_TermParams *terms, double agg_weight, const II_IndexStats *stats,
+             const II_DocTable *docs, double min_score, uint64_t tanh_factor) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init() || !rs) return -1;
+    if (rs->len == 0) {
+        rs->scored = true;
+        return 0;
+    }
+    if (!rs->has_freqs) return -1;
+    ScoreArgs sa{};
+    sa.scorer = (int)scorer;
+    sa.is_union = rs->is_union;
+    sa.n_children = rs->n_children;
+    for (uint32_t i = 0; i < rs->n_children; i++) {
+        const II_TermParams &t = terms[rs->child_order[i]];
+        sa.weight[i] = t.weight;
+        sa.idf[i] = t.idf;
+        sa.bm25_idf[i] = t.bm25_idf;
+    }
+    sa.agg_weight = agg_weight;
+    sa.avg_doc_len = stats ? stats->avgDocLen : 0.0;
+    sa.min_score = min_score;
+    sa.tanh_factor = tanh_factor ? tanh_factor : 1;
+    sa.doc_len = docs ? docs->d_len : nullptr;
+    sa.doc_score = docs ? docs->d_score : nullptr;
+    sa.max_freq = docs ? docs->d_maxf : nullptr;
+    cudaEventRecord(c.e0, c.stream);
+    bool ok = ii_launch_score(sa, rs->d_docs, rs->d_freqs, rs->cap, nullptr, (uint32_t)rs->len, rs->d_scores, c.stream) == cudaSuccess;
+    cudaEventRecord(c.e1, c.stream);
+    ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+    if (!ok) return -1;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.e0, c.e1);
+    c.stats.score_device_us = ms * 1000.0;
+    c.stats.kernel_launches += 1;
+    rs->scored = true;
+    return 0;
+}
+
+int II_ResultSet_Fetch(const II_ResultSet *rs, uint64_t *doc_ids, double *scores, uint32_t *child_freqs) {
+    const size_t m = rs->len;
+    if (m == 0) return 0;
+    if (doc_ids) {
+        std::vector<uint32_t> tmp(m);
+        if (cudaMemcpy(tmp.data(), rs->d_docs, m * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        for (size_t i = 0; i < m; i++) doc_ids[i] = tmp[i];
+    }
+    if (scores) {
+        if (rs->scored) {
+            if (cudaMemcpy(scores, rs->d_scores, m * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        } else {
+            for (size_t i = 0; i < m; i++) scores[i] = 0.0;
+        }
+    }
+    if (child_freqs) {
+        if (!rs->has_freqs) return -1;
+        if (cudaMemcpy2D(child_freqs, m * 4, rs->d_freqs, rs->cap * 4, m * 4, rs->n_children, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return -1;
+    }
+    return 0;
+}
+
+size_t II_ResultSet_TopN(const II_ResultSet *rs, size_t n, uint64_t *doc_ids, double *scores) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init() || rs->len == 0 || n == 0) return 0;
+    const uint32_t k = (uint32_t)std::min<size_t>(n, rs->len);
+    if (k > 1024) { // large LIMIT: download and partial-sort (rare; RPSorter heaps are offset+limit wide)
+        std::vector<uint64_t> ids(rs->len);
+        std::vector<double> sc(rs->len);
+        if (II_ResultSet_Fetch(rs, ids.data(), sc.data(), nullptr) != 0) return 0;
+        std::vector<uint32_t> idx(rs->len);
+        for (size_t i = 0; i < rs->len; i++) idx[i] = (uint32_t)i;
+        std::partial_sort(idx.begin(), idx.begin() + k, idx.end(), [&](uint32_t a, uint32_t b) {
+            return sc[a] > sc[b] || (sc[a] == sc[b] && ids[a] < ids[b]);
+        });
+        for (uint32_t i = 0; i < k; i++) {
+            doc_ids[i] = ids[idx[i]];
+            scores[i] = sc[idx[i]];
+        }
+        return k;
+    }
+    const uint32_t lists = ii_topn_lists((uint32_t)rs->len);
+    uint64_t *d_keys = dalloc<uint64_t>((size_t)lists * k);
+    uint32_t *d_ids = dalloc<uint32_t>((size_t)lists * k);
+    bool ok = d_keys && d_ids;
+    ok = ok && ii_launch_topn(rs->d_docs, rs->d_scores, nullptr, (uint32_t)rs->len, k, d_keys, d_ids, c.stream) == cudaSuccess;
+    std::vector<uint64_t> keys((size_t)lists * k);
+    std::vector<uint32_t> ids((size_t)lists * k);
+    ok = ok && cudaMemcpyAsync(keys.data(), d_keys, keys.size() * 8, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(ids.data(), d_ids, ids.size() * 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+    cudaFree(d_keys);
+    cudaFree(d_ids);
+    c.stats.kernel_launches += 1;
+    if (!ok) return 0;
+    // merge the per-warp lists (device did the selection; this orders <= lists*k survivors)
+    std::vector<uint32_t> idx;
+    for (uint32_t i = 0; i < keys.size(); i++)
+        if (ids[i] != 0xFFFFFFFFu) idx.push_back(i);
+    const size_t kk = std::min<size_t>(k, idx.size());
+    std::partial_sort(idx.begin(), idx.begin() + kk, idx.end(), [&](uint32_t a, uint32_t b) {
+        return keys[a] < keys[b] || (keys[a] == keys[b] && ids[a] < ids[b]);
+    });
+    for (size_t i = 0; i < kk; i++) {
+        doc_ids[i] = ids[idx[i]];
+        uint64_t u = ~keys[idx[i]];
+        u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+        memcpy(&scores[i], &u, 8);
+    }
+    return kk;
+}
+
+size_t II_SearchTopN(II_PostingList *const *lists, size_t n, int is_union, II_Scorer scorer, const II_TermParams *terms,
+                     double agg_weight, const II_IndexStats *stats, const II_DocTable *docs, size_t top_n, uint64_t *doc_ids,
+                     double *scores, size_t *total_hits) {
+    II_ResultSet *rs = is_union ? II_Union(lists, n, 0) : II_Intersect(lists, n);
+    if (!rs) return 0;
+    if (total_hits) *total_hits = rs->len;
+    size_t got = 0;
+    if (II_Score(rs, scorer, terms, agg_weight, stats, docs, 0.0, 4) == 0) got = II_ResultSet_TopN(rs, top_n, doc_ids, scores);
+    II_ResultSet_Free(rs);
+    return got;
+}
+
+// ------------------------------------------------------------------------------------------------
+// QueryIterator facade (src/iterators/iterator_api.h:46-151 contract)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct ResultIter {
+    II_QueryIterator base; // MUST be first: RediSearch sees a QueryIterator*
+    II_IndexResult res;
+    std::vector<uint64_t> ids;
+    std::vector<double> scores;
+    std::vector<uint32_t> freq_sum;
+    size_t pos = 0; // index of the NEXT entry to yield
+};
+inline ResultIter *RI(II_QueryIterator *b) { return reinterpret_cast<ResultIter *>(b); }
+
+void ri_publish(ResultIter *it, size_t i) {
+    it->res.docId = it->ids[i];
+    it->res.freq = it->freq_sum.empty() ? 1u : it->freq_sum[i];
+    it->res.data.metric = it->scores[i];
+    it->base.lastDocId = it->ids[i];
+    it->base.current = &it->res;
+}
+size_t ri_num_estimated(const II_QueryIterator *b) { return reinterpret_cast<const ResultIter *>(b)->ids.size(); }
+IteratorStatus ri_read(II_QueryIterator *b) {
+    ResultIter *it = RI(b);
+    if (it->pos >= it->ids.size()) {
+        b->atEOF = true;
+        b->current = nullptr;
+        return ITERATOR_EOF;
+    }
+    ri_publish(it, it->pos++);
+    return ITERATOR_OK;
+}
+IteratorStatus ri_skip_to(II_QueryIterator *b, t_docId doc) {
+    ResultIter *it = RI(b);
+    auto first = it->ids.begin() + it->pos;
+    auto lb = std::lower_bound(first, it->ids.end(), doc);
+    if (lb == it->ids.end()) {
+        it->pos = it->ids.size();
+        b->atEOF = true;
+        b->current = nullptr;
+        return ITERATOR_EOF;
+    }
+    const size_t i = (size_t)(lb - it->ids.begin());
+    ri_publish(it, i);
+    it->pos = i + 1;
+    return *lb == doc ? ITERATOR_OK : ITERATOR_NOTFOUND;
+}
+ValidateStatus ri_revalidate(II_QueryIterator *, struct IndexSpec *) { return VALIDATE_OK; } // a snapshot never moves
+void ri_rewind(II_QueryIterator *b) {
+    ResultIter *it = RI(b);
+    it->pos = 0;
+    b->atEOF = false;
+    b->lastDocId = 0;
+    b->current = nullptr;
+}
+void ri_free(II_QueryIterator *b) { delete RI(b); }
+} // namespace
+
+II_QueryIterator *II_NewResultIterator(II_ResultSet *rs, double weight) {
+    if (!rs) return nullptr;
+    auto *it = new ResultIter();
+    memset(&it->base, 0, sizeof(it->base));
+    memset(&it->res, 0, sizeof(it->res));
+    const size_t m = rs->len;
+    it->ids.resize(m);
+    it->scores.assign(m, 0.0);
+    bool ok = II_ResultSet_Fetch(rs, it->ids.data(), it->scores.data(), nullptr) == 0;
+    if (ok && rs->has_freqs && m) {
+        std::vector<uint32_t> fr((size_t)rs->n_children * m);
+        ok = II_ResultSet_Fetch(rs, nullptr, nullptr, fr.data()) == 0;
+        it->freq_sum.assign(m, 0);
+        for (uint32_t ch = 0; ch < rs->n_children; ch++)
+            for (size_t i = 0; i < m; i++) it->freq_sum[i] += fr[(size_t)ch * m + i];
+    }
+    it->base.type = rs->is_union ? II_IteratorType_Union : II_IteratorType_Intersect;
+    it->base.NumEstimated = ri_num_estimated;
+    it->base.Read = ri_read;
+    it->base.SkipTo = ri_skip_to;
+    it->base.Revalidate = ri_revalidate;
+    it->base.Free = ri_free;
+    it->base.Rewind = ri_rewind;
+    it->res.data.tag = II_ResultData_Metric;
+    it->res.weight = weight;
+    it->res.fieldMask = ~(unsigned __int128)0; // RS_FIELDMASK_ALL
+    II_ResultSet_Free(rs);
+    if (!ok) {
+        delete it;
+        return nullptr;
+    }
+    return &it->base;
+}
+
+II_Stats II_GetStats(bool reset) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    II_Stats s = c.stats;
+    if (reset) c.stats = II_Stats{};
+    return s;
+}
+const char *II_Version(void) { return "ii_b200 0.1 (sm_100a)"; }
+
+} // extern "C"

@@ -1,0 +1,547 @@
+// sm_100a kernels of the posting-list path (HBM-bound integer work: no tensor cores here).
+//
+//   decode_blocks_kernel   IndexBlock bytes -> (docId, freq) arrays, one thread per block
+//   intersect_kernel       k-way AND: the shortest list is cut into 1024-entry chunks (one CTA each);
+//                          for every other list the CTA gallops to the chunk's docId window with two
+//                          binary searches, stages the window in shared memory (coalesced) and
+//                          resolves membership there; survivors are compacted in order
+//   scan_kernel            exclusive prefix sum of per-chunk counts (single CTA)
+//   gather_score_kernel    survivors -> ascending docIds + per-child freqs + score
+//   union: mark / popc / expand / fill kernels over a docId bitmap (order-preserving, O(sum |L|))
+//   score_kernel           the reference's scorers, expression tree by expression tree
+//   topn_kernel            (score desc, docId asc) selection
+//
+// Replaces on device: Intersection::read / find_consensus (RS/rqe_iterators/src/intersection.rs:245-452),
+// UnionFlat::read_full (union_flat.rs:324-348), IndexReader::next_record + codecs
+// (RS/inverted_index/src/reader/core.rs:245-277, codec/*.rs), the default scorers
+// (src/ext/default.c:68-461) and RPSorter's ranking (src/result_processor.c:752-850).
+#include "ii_kernels.h"
+#include "topk_common.cuh"
+
+#include <algorithm>
+
+namespace rsb200 {
+
+// ------------------------------------------------------------------------------------------------
+// device decode: one thread per IndexBlock
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t qint_value(const uint8_t *p, int bytes) {
+    uint32_t v = p[0];
+    if (bytes > 1) v |= (uint32_t)p[1] << 8;
+    if (bytes > 2) v |= (uint32_t)p[2] << 16;
+    if (bytes > 3) v |= (uint32_t)p[3] << 24;
+    return v;
+}
+
+__global__ void decode_blocks_kernel(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ byte_off,
+                                     const uint64_t *__restrict__ first_id, const uint32_t *__restrict__ entry_off,
+                                     uint32_t nblocks, int codec, uint32_t *__restrict__ out_ids,
+                                     uint32_t *__restrict__ out_freqs, uint32_t *__restrict__ out_masks) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const uint8_t *p = bytes + byte_off[b];
+    const uint32_t n = entry_off[b + 1] - entry_off[b];
+    uint32_t o = entry_off[b];
+    const uint64_t base0 = first_id[b];
+    uint64_t last = base0; // reader resets the delta base to first_doc_id on block entry (reader/core.rs:430-440)
+    for (uint32_t e = 0; e < n; e++, o++) {
+        uint32_t freq = 1, mask = 0xFFFFFFFFu;
+        uint64_t id;
+        if (codec == 5) { // raw doc ids: u32 delta from the block's first id
+            id = base0 + qint_value(p, 4);
+            p += 4;
+        } else if (codec == 4) { // varint delta (RS/varint/src/lib.rs read_as_varint)
+            uint8_t c = *p++;
+            uint64_t val = c & 0x7f;
+            while (c & 0x80) {
+                val += 1;
+                c = *p++;
+                val = (val << 7) | (c & 0x7f);
+            }
+            id = last + val;
+        } else {
+            const uint8_t lead = *p++;
+            const int nvals = (codec == 0) ? 4 : (codec == 2) ? 3 : 2;
+            uint32_t v[4] = {0, 0, 0, 0};
+            for (int i = 0; i < nvals; i++) {
+                const int nb = ((lead >> (2 * i)) & 3) + 1;
+                v[i] = qint_value(p, nb);
+                p += nb;
+            }
+            id = last + v[0];
+            if (codec == 0) { // Full: delta, freq, fieldMask, offsetsLen + offsets bytes
+                freq = v[1];
+                mask = v[2];
+                p += v[3];
+            } else if (codec == 1) { // FreqsOnly
+                freq = v[1];
+            } else if (codec == 2) { // FreqsFields
+                freq = v[1];
+                mask = v[2];
+            } else { // FieldsOnly
+                mask = v[1];
+            }
+        }
+        last = id;
+        out_ids[o] = (uint32_t)id;
+        out_freqs[o] = freq;
+        if (out_masks) out_masks[o] = mask;
+    }
+}
+
+// keep records with (mask & filter) != 0, in order: flags -> scan done by the caller (scan_kernel)
+__global__ void mask_flags_kernel(const uint32_t *__restrict__ masks, uint32_t n, uint32_t filter,
+                                  uint32_t *__restrict__ chunk_counts) {
+    // one CTA per 1024 entries
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * 1024u;
+    uint32_t c = 0;
+    for (uint32_t i = threadIdx.x; i < 1024u; i += blockDim.x)
+        if (base + i < n && (masks[base + i] & filter)) c++;
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_counts[blockIdx.x] = s_cnt;
+}
+__global__ void mask_compact_kernel(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ freqs,
+                                    const uint32_t *__restrict__ masks, uint32_t n, uint32_t filter,
+                                    const uint32_t *__restrict__ chunk_off, uint32_t *__restrict__ out_ids,
+                                    uint32_t *__restrict__ out_freqs) {
+    // one warp-serial pass per 1024-entry chunk keeps the order (chunks are small)
+    if (threadIdx.x != 0) return;
+    const uint32_t base = blockIdx.x * 1024u;
+    uint32_t o = chunk_off[blockIdx.x];
+    for (uint32_t i = 0; i < 1024u && base + i < n; i++)
+        if (masks[base + i] & filter) {
+            out_ids[o] = ids[base + i];
+            out_freqs[o] = freqs[base + i];
+            o++;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// intersection
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t lo, uint32_t hi, uint32_t key) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (a[mid] < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kIIThreads) intersect_kernel(const IntersectArgs a) {
+    __shared__ uint32_t sB[kIISmemElems];
+    __shared__ uint32_t s_lo, s_hi;
+    __shared__ uint32_t s_warp[kIIThreads / 32];
+    const uint32_t chunk = blockIdx.x;
+    const uint32_t start = chunk * kIIChunk;
+    const uint32_t end = min(start + (uint32_t)kIIChunk, a.len[0]);
+    const uint32_t *A = a.ids[0];
+    uint32_t doc[kIIItems];
+    bool alive[kIIItems];
+#pragma unroll
+    for (int i = 0; i < kIIItems; i++) {
+        const uint32_t idx = start + threadIdx.x * kIIItems + i; // blocked: a thread owns consecutive entries
+        alive[i] = idx < end;
+        doc[i] = alive[i] ? A[idx] : 0xFFFFFFFFu;
+    }
+    const uint32_t a_lo = A[start], a_hi = A[end - 1];
+    for (uint32_t j = 1; j < a.n; j++) {
+        const uint32_t *B = a.ids[j];
+        if (threadIdx.x == 0) s_lo = lower_bound_u32(B, 0, a.len[j], a_lo);
+        if (threadIdx.x == 32) s_hi = lower_bound_u32(B, 0, a.len[j], a_hi + 1u); // a_hi < 2^32-1
+        __syncthreads();
+        const uint32_t lo = s_lo, hi = s_hi, range = hi - lo;
+        uint32_t *posj = a.tmp_pos + (size_t)j * a.stride;
+        if (range <= (uint32_t)kIISmemElems) {
+            for (uint32_t t = threadIdx.x; t < range; t += kIIThreads) sB[t] = B[lo + t];
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < kIIItems; i++) {
+                if (alive[i]) {
+                    const uint32_t p = lower_bound_u32(sB, 0, range, doc[i]);
+                    alive[i] = (p < range) && sB[p] == doc[i];
+                    if (alive[i]) posj[start + threadIdx.x * kIIItems + i] = lo + p;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kIIItems; i++) {
+                if (alive[i]) {
+                    const uint32_t p = lower_bound_u32(B, lo, hi, doc[i]);
+                    alive[i] = (p < hi) && B[p] == doc[i];
+                    if (alive[i]) posj[start + threadIdx.x * kIIItems + i] = p;
+                }
+            }
+        }
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < kIIItems; i++) any |= alive[i];
+        if (!__syncthreads_or(any)) break; // also fences sB before the next list reuses it
+    }
+    // ordered compaction of the survivors
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int i = 0; i < kIIItems; i++) cnt += alive[i];
+    uint32_t incl = cnt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t warp_base = 0, total = 0;
+    for (int w = 0; w < kIIThreads / 32; w++) {
+        if (w < warp) warp_base += s_warp[w];
+        total += s_warp[w];
+    }
+    uint32_t rank = warp_base + incl - cnt;
+#pragma unroll
+    for (int i = 0; i < kIIItems; i++)
+        if (alive[i]) a.tmp_idx[start + rank++] = start + threadIdx.x * kIIItems + i;
+    if (threadIdx.x == 0) a.counts[chunk] = total;
+}
+
+// exclusive scan of `n` counts by one CTA; total written to *total
+__global__ void __launch_bounds__(1024) scan_kernel(const uint32_t *__restrict__ counts, uint32_t n,
+                                                    uint32_t *__restrict__ offsets, uint32_t *__restrict__ total) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = (i < n) ? counts[i] : 0;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; w++) wb += s_warp[w];
+        const uint32_t carry = s_carry;
+        if (i < n) offsets[i] = carry + wb + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + wb + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scorers — src/ext/default.c, same operations in the same order and precision
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double bm25std_leaf(double idf, double f, int doc_len, double avg, double weight) {
+    const float b = 0.75f, k1 = 1.2f; // default.c:255-256
+    const float one_minus_b = __fsub_rn(1.0f, b);
+    const float b_len = __fmul_rn(b, (float)doc_len);
+    const float k1p1 = __fadd_rn(k1, 1.0f);
+    const double ratio = __ddiv_rn((double)b_len, avg);
+    const double inner = __dadd_rn((double)one_minus_b, ratio);
+    const double denom = __dadd_rn(f, __dmul_rn((double)k1, inner));
+    const double num = __dmul_rn(__dmul_rn(__dmul_rn(weight, idf), f), (double)k1p1);
+    return __ddiv_rn(num, denom); // :244
+}
+__device__ __forceinline__ double bm25_leaf(double idf, double f, double avg, double weight) {
+    const float b = 0.5f, k1 = 1.2f; // default.c:166-167
+    const float one_minus_b = __fsub_rn(1.0f, b);
+    const double inner = __dadd_rn((double)one_minus_b, __dmul_rn((double)b, avg));
+    const double denom = __dadd_rn(f, __dmul_rn((double)k1, inner));
+    return __ddiv_rn(__dmul_rn(__dmul_rn(weight, idf), f), denom); // :173
+}
+
+__device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *freqs, size_t fstride, size_t o) {
+    const float doc_score = s.doc_score ? s.doc_score[doc] : 1.0f;
+    const uint32_t doc_len = s.doc_len ? s.doc_len[doc] : 0u;
+    switch (s.scorer) {
+    case 0:   // BM25STD            :253-316
+    case 5: { // BM25STD.TANH       :339-359
+        double ret = 0;
+        for (uint32_t c = 0; c < s.n_children; c++) {
+            const uint32_t f = freqs[c * fstride + o];
+            if (f) ret = __dadd_rn(ret, bm25std_leaf(s.bm25_idf[c], (double)f, (int)doc_len, s.avg_doc_len, s.weight[c]));
+        }
+        ret = __dmul_rn(ret, s.agg_weight);
+        const double score = __dmul_rn((double)doc_score, ret);
+        if (s.scorer == 5) return tanh(__dmul_rn(__ddiv_rn(1.0, (double)s.tanh_factor), score));
+        return score;
+    }
+    case 1: { // BM25 (legacy)      :164-233, slop = 1
+        double ret = 0;
+        for (uint32_t c = 0; c < s.n_children; c++) {
+            const uint32_t f = freqs[c * fstride + o];
+            if (f) ret = __dadd_rn(ret, bm25_leaf(s.idf[c], (double)f, s.avg_doc_len, s.weight[c]));
+        }
+        ret = __dmul_rn(ret, s.agg_weight);
+        const double score = __dmul_rn((double)doc_score, ret);
+        return (score < s.min_score) ? 0.0 : score;
+    }
+    case 2:   // TFIDF              :68-146
+    case 3: { // TFIDF.DOCNORM
+        if (doc_score == 0.0f) return 0.0;
+        const uint32_t norm = (s.scorer == 2) ? (s.max_freq ? s.max_freq[doc] : 1u) : doc_len;
+        if (norm == 0) return 0.0;
+        double raw = 0;
+        for (uint32_t c = 0; c < s.n_children; c++) {
+            const uint32_t f = freqs[c * fstride + o];
+            if (f) raw = __dadd_rn(raw, __dmul_rn(__dmul_rn(s.weight[c], (double)f), s.idf[c]));
+        }
+        raw = __dmul_rn(s.agg_weight, raw);
+        const double tfidf = __ddiv_rn(__dmul_rn((double)doc_score, raw), (double)norm);
+        return (tfidf < s.min_score) ? 0.0 : tfidf;
+    }
+    case 4: return (double)doc_score; // DOCSCORE :366-371
+    case 6: {                         // DISMAX   :378-461: intersection sums, union takes the max
+        double ret = 0;
+        for (uint32_t c = 0; c < s.n_children; c++) {
+            const uint32_t f = freqs[c * fstride + o];
+            if (!f) continue;
+            const double leaf = __dmul_rn(s.weight[c], (double)f);
+            if (s.is_union)
+                ret = (leaf > ret) ? leaf : ret;
+            else
+                ret = __dadd_rn(ret, leaf);
+        }
+        return __dmul_rn(s.agg_weight, ret);
+    }
+    }
+    return 0.0;
+}
+
+// survivors of the intersection -> ordered docIds, per-child freqs
+__global__ void __launch_bounds__(kIIThreads) gather_kernel(const GatherArgs g) {
+    const uint32_t chunk = blockIdx.x;
+    const uint32_t cnt = g.counts[chunk], off = g.offsets[chunk];
+    const uint32_t start = chunk * kIIChunk;
+    for (uint32_t r = threadIdx.x; r < cnt; r += kIIThreads) {
+        const uint32_t idx = g.tmp_idx[start + r];
+        const size_t o = (size_t)off + r;
+        g.out_doc[o] = g.ids0[idx];
+        g.out_freq[o] = g.freqs[0][idx];
+        for (uint32_t j = 1; j < g.n; j++) g.out_freq[(size_t)j * g.fstride + o] = g.freqs[j][g.tmp_pos[(size_t)j * g.stride + idx]];
+    }
+}
+
+__global__ void score_kernel(const ScoreArgs s, const uint32_t *__restrict__ docs, const uint32_t *__restrict__ freqs,
+                             size_t fstride, const uint32_t *__restrict__ d_len, uint32_t cap_len,
+                             double *__restrict__ scores) {
+    const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < m; o += (size_t)gridDim.x * blockDim.x)
+        scores[o] = score_hit(s, docs[o], freqs, fstride, o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// union over a docId bitmap
+// ------------------------------------------------------------------------------------------------
+__global__ void mark_kernel(const uint32_t *__restrict__ ids, uint32_t n, uint32_t *__restrict__ bitmap) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t id = ids[i];
+        atomicOr(&bitmap[id >> 5], 1u << (id & 31));
+    }
+}
+// one warp per 32-word block
+__global__ void popc_kernel(const uint32_t *__restrict__ bitmap, uint32_t nwords, uint32_t *__restrict__ blocksum) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c = (w < nwords) ? __popc(bitmap[w]) : 0;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+    if ((threadIdx.x & 31) == 0) blocksum[w >> 5] = c;
+}
+__global__ void expand_kernel(const uint32_t *__restrict__ bitmap, uint32_t nwords, const uint32_t *__restrict__ blockoff,
+                              uint32_t *__restrict__ wordoff, uint32_t *__restrict__ out_doc) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t bits = (w < nwords) ? bitmap[w] : 0;
+    const uint32_t c = __popc(bits);
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (w >= nwords) return;
+    uint32_t o = blockoff[w >> 5] + incl - c;
+    wordoff[w] = o;
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        out_doc[o++] = (w << 5) + b;
+    }
+}
+__global__ void fill_freq_kernel(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ freqs, uint32_t n,
+                                 const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordoff,
+                                 uint32_t *__restrict__ out_freq) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t id = ids[i], w = id >> 5;
+        const uint32_t rank = wordoff[w] + __popc(bitmap[w] & ((1u << (id & 31)) - 1u));
+        out_freq[rank] = freqs[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// top-N by (score desc, docId asc) — cmpByScore, src/result_processor.c:834-850
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t rank_key(double score) { // smaller key = better rank
+    uint64_t u = (uint64_t)__double_as_longlong(score + 0.0);
+    u = (u >> 63) ? ~u : (u | 0x8000000000000000ull); // ascending-orderable
+    return ~u;                                        // descending score
+}
+struct Cand {
+    uint64_t key;
+    uint32_t id;
+};
+__device__ __forceinline__ bool cand_less(uint64_t ka, uint32_t ia, uint64_t kb, uint32_t ib) {
+    return ka < kb || (ka == kb && ia < ib);
+}
+
+// per-warp lists in smem: keys[k], ids[k]; returns through global lists; final merge by one CTA
+__global__ void __launch_bounds__(256) topn_kernel(const uint32_t *__restrict__ docs, const double *__restrict__ scores,
+                                                   const uint32_t *__restrict__ d_len, uint32_t cap_len, uint32_t k,
+                                                   uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_ids) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem) + (size_t)warp * k;
+    uint32_t *ids = reinterpret_cast<uint32_t *>(reinterpret_cast<uint64_t *>(smem) + (size_t)8 * k) + (size_t)warp * k;
+    for (uint32_t p = lane; p < k; p += 32) {
+        keys[p] = 0xFFFFFFFFFFFFFFFFull;
+        ids[p] = 0xFFFFFFFFu;
+    }
+    __syncwarp();
+    uint64_t wkey = 0xFFFFFFFFFFFFFFFFull; // worst entry of this warp's list (warp-uniform)
+    uint32_t wid = 0xFFFFFFFFu, wpos = 0;
+    const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
+    const uint32_t gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    for (uint64_t base = (uint64_t)gw * 32; base < m; base += (uint64_t)nw * 32) {
+        const uint32_t i = (uint32_t)base + lane;
+        const bool valid = i < m;
+        const uint64_t ck = valid ? rank_key(scores[i]) : 0xFFFFFFFFFFFFFFFFull;
+        const uint32_t ci = valid ? docs[i] : 0xFFFFFFFFu;
+        unsigned pending = __ballot_sync(0xffffffffu, valid && cand_less(ck, ci, wkey, wid));
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const uint64_t k2 = shfl_u64(ck, src);
+            const uint32_t i2 = __shfl_sync(0xffffffffu, ci, src);
+            if (!cand_less(k2, i2, wkey, wid)) continue;
+            if (lane == 0) {
+                keys[wpos] = k2;
+                ids[wpos] = i2;
+            }
+            __syncwarp();
+            uint64_t bk = 0;
+            uint32_t bi = 0, bp = 0;
+            for (uint32_t p = lane; p < k; p += 32) {
+                const uint64_t kk = keys[p];
+                const uint32_t ii = ids[p];
+                if (!cand_less(kk, ii, bk, bi)) {
+                    bk = kk;
+                    bi = ii;
+                    bp = p;
+                }
+            }
+#pragma unroll
+            for (int mm = 16; mm > 0; mm >>= 1) {
+                const uint64_t ok = shfl_xor_u64(bk, mm);
+                const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, mm);
+                const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, mm);
+                if (cand_less(bk, bi, ok, oi) || (ok == bk && oi == bi && op < bp)) {
+                    bk = ok;
+                    bi = oi;
+                    bp = op;
+                }
+            }
+            wkey = bk;
+            wid = bi;
+            wpos = bp;
+        }
+    }
+    __syncwarp();
+    for (uint32_t p = lane; p < k; p += 32) {
+        out_keys[(size_t)gw * k + p] = keys[p];
+        out_ids[(size_t)gw * k + p] = ids[p];
+    }
+}
+
+// ================================================================================================
+// launchers
+// ================================================================================================
+static inline uint32_t grid_for(size_t n, uint32_t threads, uint32_t cap) {
+    const size_t g = (n + threads - 1) / threads;
+    return (uint32_t)std::max<size_t>(1, std::min<size_t>(g, cap));
+}
+
+cudaError_t ii_launch_decode(const uint8_t *d_bytes, const uint64_t *d_byte_off, const uint64_t *d_first_id,
+                             const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint32_t *d_ids, uint32_t *d_freqs,
+                             uint32_t *d_masks, cudaStream_t s) {
+    if (!nblocks) return cudaSuccess;
+    decode_blocks_kernel<<<(nblocks + 127) / 128, 128, 0, s>>>(d_bytes, d_byte_off, d_first_id, d_entry_off, nblocks, codec,
+                                                              d_ids, d_freqs, d_masks);
+    return cudaGetLastError();
+}
+cudaError_t ii_launch_mask_filter(const uint32_t *d_ids, const uint32_t *d_freqs, const uint32_t *d_masks, uint32_t n,
+                                  uint32_t filter, uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_total,
+                                  uint32_t *d_out_ids, uint32_t *d_out_freqs, cudaStream_t s) {
+    if (!n) return cudaMemsetAsync(d_total, 0, 4, s);
+    const uint32_t chunks = (n + 1023) / 1024;
+    mask_flags_kernel<<<chunks, 256, 0, s>>>(d_masks, n, filter, d_counts);
+    scan_kernel<<<1, 1024, 0, s>>>(d_counts, chunks, d_offsets, d_total);
+    mask_compact_kernel<<<chunks, 32, 0, s>>>(d_ids, d_freqs, d_masks, n, filter, d_offsets, d_out_ids, d_out_freqs);
+    return cudaGetLastError();
+}
+
+cudaError_t ii_launch_intersect(const IntersectArgs &a, uint32_t nchunks, uint32_t *d_offsets, uint32_t *d_total,
+                                cudaStream_t s) {
+    intersect_kernel<<<nchunks, kIIThreads, 0, s>>>(a);
+    scan_kernel<<<1, 1024, 0, s>>>(a.counts, nchunks, d_offsets, d_total);
+    return cudaGetLastError();
+}
+cudaError_t ii_launch_gather(const GatherArgs &g, uint32_t nchunks, cudaStream_t s) {
+    gather_kernel<<<nchunks, kIIThreads, 0, s>>>(g);
+    return cudaGetLastError();
+}
+cudaError_t ii_launch_score(const ScoreArgs &sa, const uint32_t *d_docs, const uint32_t *d_freqs, size_t fstride,
+                            const uint32_t *d_len, uint32_t cap_len, double *d_scores, cudaStream_t s) {
+    if (!cap_len) return cudaSuccess;
+    score_kernel<<<grid_for(cap_len, 256, 148 * 8), 256, 0, s>>>(sa, d_docs, d_freqs, fstride, d_len, cap_len, d_scores);
+    return cudaGetLastError();
+}
+cudaError_t ii_launch_union(const uint32_t *const *d_ids, const uint32_t *const *d_freqs, const uint32_t *lens, uint32_t n,
+                            uint32_t nwords, uint32_t *d_bitmap, uint32_t *d_blocksum, uint32_t *d_blockoff,
+                            uint32_t *d_wordoff, uint32_t *d_total, uint32_t *d_out_doc, uint32_t *d_out_freq,
+                            size_t fstride, bool want_freqs, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(d_bitmap, 0, (size_t)nwords * 4, s);
+    if (e != cudaSuccess) return e;
+    for (uint32_t j = 0; j < n; j++)
+        if (lens[j]) mark_kernel<<<grid_for(lens[j], 256, 148 * 8), 256, 0, s>>>(d_ids[j], lens[j], d_bitmap);
+    const uint32_t nblk = (nwords + 31) / 32;
+    popc_kernel<<<nblk, 32, 0, s>>>(d_bitmap, nwords, d_blocksum);
+    scan_kernel<<<1, 1024, 0, s>>>(d_blocksum, nblk, d_blockoff, d_total);
+    expand_kernel<<<nblk, 32, 0, s>>>(d_bitmap, nwords, d_blockoff, d_wordoff, d_out_doc);
+    if (want_freqs)
+        for (uint32_t j = 0; j < n; j++)
+            if (lens[j])
+                fill_freq_kernel<<<grid_for(lens[j], 256, 148 * 8), 256, 0, s>>>(d_ids[j], d_freqs[j], lens[j], d_bitmap, d_wordoff,
+                                                                                d_out_freq + (size_t)j * fstride);
+    return cudaGetLastError();
+}
+uint32_t ii_topn_lists(uint32_t m) { return grid_for(m, 256, 148 * 2) * 8; }
+cudaError_t ii_launch_topn(const uint32_t *d_docs, const double *d_scores, const uint32_t *d_len, uint32_t cap_len, uint32_t k,
+                           uint64_t *d_keys, uint32_t *d_ids, cudaStream_t s) {
+    const uint32_t grid = grid_for(cap_len, 256, 148 * 2);
+    const size_t smem = (size_t)8 * k * 12;
+    topn_kernel<<<grid, 256, smem, s>>>(d_docs, d_scores, d_len, cap_len, k, d_keys, d_ids);
+    return cudaGetLastError();
+}
+
+} // namespace rsb200

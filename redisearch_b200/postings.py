@@ -1,0 +1,273 @@
+"""ctypes face of libii_b200.so (include/ii_b200.h): posting lists in HBM, AND / OR on device, the
+reference's scorers, top-N and the QueryIterator facade.  No compute happens here."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import load_library
+
+CODEC_FULL, CODEC_FREQS_ONLY, CODEC_FREQS_FIELDS, CODEC_FIELDS_ONLY, CODEC_DOCIDS_ONLY, CODEC_RAW_DOCIDS_ONLY = range(6)
+SCORER_BM25STD, SCORER_BM25, SCORER_TFIDF, SCORER_TFIDF_DOCNORM, SCORER_DOCSCORE, SCORER_BM25STD_TANH, SCORER_DISMAX = range(7)
+ITERATOR_OK, ITERATOR_NOTFOUND, ITERATOR_EOF, ITERATOR_TIMEOUT = range(4)
+
+
+class II_BlockView(C.Structure):
+    _fields_ = [("first_doc_id", C.c_uint64), ("last_doc_id", C.c_uint64), ("num_entries", C.c_uint16),
+                ("data", C.POINTER(C.c_uint8)), ("len", C.c_size_t)]
+
+
+class II_TermParams(C.Structure):
+    _fields_ = [("weight", C.c_double), ("idf", C.c_double), ("bm25_idf", C.c_double)]
+
+
+class II_IndexStats(C.Structure):
+    _fields_ = [("numDocs", C.c_size_t), ("numTerms", C.c_size_t), ("avgDocLen", C.c_double)]
+
+
+class II_Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("intersect_device_us", C.c_double), ("score_device_us", C.c_double),
+                ("decode_host_us", C.c_double), ("h2d_us", C.c_double)]
+
+
+class _ResultData(C.Structure):
+    _fields_ = [("tag", C.c_uint8), ("_pad", C.c_uint8 * 7), ("metric", C.c_double), ("_rest", C.c_uint8 * 24)]
+
+
+class II_IndexResult(C.Structure):
+    _fields_ = [("docId", C.c_uint64), ("dmd", C.c_void_p), ("fieldMask_lo", C.c_uint64), ("fieldMask_hi", C.c_uint64),
+                ("freq", C.c_uint32), ("data", _ResultData), ("metrics", C.c_void_p), ("weight", C.c_double),
+                ("hasFieldExpiration", C.c_bool)]
+
+
+class II_QueryIterator(C.Structure):
+    pass
+
+
+_QI = C.POINTER(II_QueryIterator)
+II_QueryIterator._fields_ = [
+    ("type", C.c_uint32), ("atEOF", C.c_bool), ("lastDocId", C.c_uint64), ("current", C.POINTER(II_IndexResult)),
+    ("NumEstimated", C.CFUNCTYPE(C.c_size_t, _QI)), ("Read", C.CFUNCTYPE(C.c_int, _QI)),
+    ("SkipTo", C.CFUNCTYPE(C.c_int, _QI, C.c_uint64)), ("Revalidate", C.CFUNCTYPE(C.c_int, _QI, C.c_void_p)),
+    ("Free", C.CFUNCTYPE(None, _QI)), ("Rewind", C.CFUNCTYPE(None, _QI)), ("ProfileChildren", C.c_void_p),
+    ("PrintProfile", C.c_void_p)]
+
+_P, _SZ = C.c_void_p, C.c_size_t
+SIGNATURES = [
+    ("II_PostingList_FromBlocks", _P, [C.POINTER(II_BlockView), _SZ, C.c_int, C.c_uint32, C.c_int]),
+    ("II_PostingList_FromArrays", _P, [_P, _P, _SZ]),
+    ("II_PostingList_FromDevice", _P, [_P, _P, _SZ]),
+    ("II_PostingList_Len", _SZ, [_P]),
+    ("II_PostingList_NumEstimated", _SZ, [_P]),
+    ("II_PostingList_Free", None, [_P]),
+    ("II_DocTable_New", _P, [_SZ, _P, _P, _P]),
+    ("II_DocTable_FromDevice", _P, [_SZ, _P, _P, _P]),
+    ("II_DocTable_Free", None, [_P]),
+    ("II_Intersect", _P, [_P, _SZ]),
+    ("II_Union", _P, [_P, _SZ, C.c_int]),
+    ("II_ResultSet_Len", _SZ, [_P]),
+    ("II_ResultSet_Free", None, [_P]),
+    ("II_CalculateIDF", C.c_double, [_SZ, _SZ]),
+    ("II_CalculateIDF_BM25", C.c_double, [_SZ, _SZ]),
+    ("II_Score", C.c_int, [_P, C.c_int, C.POINTER(II_TermParams), C.c_double, C.POINTER(II_IndexStats), _P, C.c_double, C.c_uint64]),
+    ("II_ResultSet_Fetch", C.c_int, [_P, _P, _P, _P]),
+    ("II_ResultSet_NumChildren", _SZ, [_P]),
+    ("II_ResultSet_ChildOrder", None, [_P, _P]),
+    ("II_ResultSet_TopN", _SZ, [_P, _SZ, _P, _P]),
+    ("II_ResultSet_DeviceDocIds", _P, [_P]),
+    ("II_ResultSet_DeviceScores", _P, [_P]),
+    ("II_SearchTopN", _SZ, [_P, _SZ, C.c_int, C.c_int, C.POINTER(II_TermParams), C.c_double, C.POINTER(II_IndexStats), _P, _SZ,
+                            _P, _P, C.POINTER(_SZ)]),
+    ("II_NewResultIterator", _QI, [_P, C.c_double]),
+    ("II_GetStats", II_Stats, [C.c_bool]),
+    ("II_Version", C.c_char_p, []),
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        L = load_library("libii_b200.so")
+        for name, res, args in SIGNATURES:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class PostingList:
+    def __init__(self, handle):
+        if not handle:
+            raise RuntimeError("posting list construction failed (no CUDA device, or unrepresentable docIds)")
+        self.h = handle
+        self.L = lib()
+
+    @classmethod
+    def from_arrays(cls, doc_ids, freqs=None):
+        d = np.ascontiguousarray(doc_ids, dtype=np.uint64)
+        f = np.ascontiguousarray(freqs, dtype=np.uint32) if freqs is not None else None
+        return cls(lib().II_PostingList_FromArrays(_ptr(d), _ptr(f), len(d)))
+
+    @classmethod
+    def from_blocks(cls, blocks, codec, field_mask_filter=0, on_device=False):
+        """blocks: list of (first_doc_id, last_doc_id, num_entries, bytes)."""
+        arr = (II_BlockView * max(1, len(blocks)))()
+        keep = []
+        for i, (first, last, n, data) in enumerate(blocks):
+            buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+            keep.append(buf)
+            arr[i] = II_BlockView(first, last, n, C.cast(buf, C.POINTER(C.c_uint8)), len(data))
+        return cls(lib().II_PostingList_FromBlocks(arr, len(blocks), codec, field_mask_filter, int(on_device)))
+
+    def __len__(self):
+        return self.L.II_PostingList_Len(self.h)
+
+    def num_estimated(self):
+        return self.L.II_PostingList_NumEstimated(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.II_PostingList_Free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DocTable:
+    def __init__(self, max_doc_id, doc_len=None, doc_score=None, max_term_freq=None):
+        self.L = lib()
+        dl = np.ascontiguousarray(doc_len, dtype=np.uint32) if doc_len is not None else None
+        ds = np.ascontiguousarray(doc_score, dtype=np.float32) if doc_score is not None else None
+        mf = np.ascontiguousarray(max_term_freq, dtype=np.uint32) if max_term_freq is not None else None
+        self.h = self.L.II_DocTable_New(max_doc_id, _ptr(dl), _ptr(ds), _ptr(mf))
+        if not self.h:
+            raise RuntimeError("II_DocTable_New failed")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.II_DocTable_Free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def _list_array(lists):
+    return (C.c_void_p * len(lists))(*[pl.h for pl in lists])
+
+
+class ResultSet:
+    def __init__(self, handle):
+        if not handle:
+            raise RuntimeError("device iterator evaluation failed")
+        self.h = handle
+        self.L = lib()
+
+    def __len__(self):
+        return self.L.II_ResultSet_Len(self.h)
+
+    def child_order(self):
+        n = self.L.II_ResultSet_NumChildren(self.h)
+        out = np.zeros(n, dtype=np.uint32)
+        self.L.II_ResultSet_ChildOrder(self.h, _ptr(out))
+        return out
+
+    def score(self, scorer, terms, agg_weight, num_docs, avg_doc_len, doc_table=None, min_score=0.0, tanh_factor=4):
+        """terms: list of (weight, idf, bm25_idf) in the ORIGINAL list order."""
+        arr = (II_TermParams * len(terms))(*[II_TermParams(*t) for t in terms])
+        st = II_IndexStats(num_docs, 0, avg_doc_len)
+        rc = self.L.II_Score(self.h, scorer, arr, agg_weight, C.byref(st), doc_table.h if doc_table else None, min_score, tanh_factor)
+        if rc != 0:
+            raise RuntimeError("II_Score failed")
+
+    def fetch(self, want_freqs=True):
+        m = len(self)
+        ids = np.zeros(m, dtype=np.uint64)
+        scores = np.zeros(m, dtype=np.float64)
+        n = self.L.II_ResultSet_NumChildren(self.h)
+        freqs = np.zeros((n, m), dtype=np.uint32) if want_freqs else None
+        rc = self.L.II_ResultSet_Fetch(self.h, _ptr(ids), _ptr(scores), _ptr(freqs) if want_freqs else None)
+        if rc != 0:
+            raise RuntimeError("II_ResultSet_Fetch failed")
+        return ids, scores, freqs
+
+    def topn(self, n):
+        ids = np.zeros(n, dtype=np.uint64)
+        scores = np.zeros(n, dtype=np.float64)
+        got = self.L.II_ResultSet_TopN(self.h, n, _ptr(ids), _ptr(scores))
+        return ids[:got], scores[:got]
+
+    def into_iterator(self, weight=1.0):
+        it = self.L.II_NewResultIterator(self.h, weight)
+        self.h = None  # ownership moved
+        return it
+
+    def close(self):
+        if self.h:
+            self.L.II_ResultSet_Free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def intersect(lists) -> ResultSet:
+    return ResultSet(lib().II_Intersect(_list_array(lists), len(lists)))
+
+
+def union(lists, quick_exit=False) -> ResultSet:
+    return ResultSet(lib().II_Union(_list_array(lists), len(lists), int(quick_exit)))
+
+
+def search_topn(lists, is_union, scorer, terms, agg_weight, num_docs, avg_doc_len, doc_table, top_n):
+    arr = (II_TermParams * len(terms))(*[II_TermParams(*t) for t in terms])
+    st = II_IndexStats(num_docs, 0, avg_doc_len)
+    ids = np.zeros(top_n, dtype=np.uint64)
+    scores = np.zeros(top_n, dtype=np.float64)
+    total = C.c_size_t(0)
+    got = lib().II_SearchTopN(_list_array(lists), len(lists), int(is_union), scorer, arr, agg_weight, C.byref(st),
+                              doc_table.h if doc_table else None, top_n, _ptr(ids), _ptr(scores), C.byref(total))
+    return ids[:got], scores[:got], total.value
+
+
+def stats(reset=False) -> II_Stats:
+    return lib().II_GetStats(reset)
+
+
+def smoke(ol) -> None:
+    """Tiny 3-term AND + BM25STD on cuda:0, checked against the oracle (called by __graft_entry__.smoke)."""
+    rng = np.random.default_rng(5)
+    n_docs = 200_000
+    lists = [np.unique(rng.integers(1, n_docs, m)).astype(np.uint64) for m in (40_000, 90_000, 15_000)]
+    freqs = [rng.integers(1, 9, len(l)).astype(np.uint32) for l in lists]
+    doc_len = rng.integers(50, 500, n_docs + 1).astype(np.uint32)
+    idx = [ol.InvIndex(ol.CODEC_FREQS_ONLY, l, f) for l, f in zip(lists, freqs)]
+    pls = [PostingList.from_blocks(ix.blocks(), CODEC_FREQS_ONLY) for ix in idx]
+    rs = intersect(pls)
+    exp = ol.run_intersect(idx)
+    terms = [(1.0, ol.postings().orc_idf(n_docs, len(l)), ol.postings().orc_idf_bm25(n_docs, len(l))) for l in lists]
+    avg = float(doc_len[1:].mean())
+    rs.score(SCORER_BM25STD, terms, 1.0, n_docs, avg, DocTable(n_docs, doc_len))
+    ids, scores, fr = rs.fetch()
+    assert ids.tolist() == [e[0] for e in exp], "docID sequence differs from the oracle"
+    order = rs.child_order().tolist()
+    for i in range(0, len(exp), max(1, len(exp) // 50)):
+        doc, ch = exp[i]
+        assert [c for c, _ in ch] == order
+        s = ol.oracle_score(ol.SCORER_BM25STD, [f for _, f in ch], [terms[c][1] for c, _ in ch], [terms[c][2] for c, _ in ch],
+                            [1.0] * len(ch), 1.0, int(doc_len[doc]), 1, 1.0, n_docs, avg)
+        assert np.float64(s).tobytes() == np.float64(scores[i]).tobytes(), (s, scores[i])
+    print(f"smoke postings ok: {len(ids)} hits of 3-term AND, BM25STD bit-equal to the oracle")

