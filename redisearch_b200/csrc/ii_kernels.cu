@@ -540,6 +540,10 @@ cudaError_t ii_launch_topn(const uint32_t *d_docs, const double *d_scores, const
                            uint64_t *d_keys, uint32_t *d_ids, cudaStream_t s) {
     const uint32_t grid = grid_for(cap_len, 256, 148 * 2);
     const size_t smem = (size_t)8 * k * 12;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(topn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     topn_kernel<<<grid, 256, smem, s>>>(d_docs, d_scores, d_len, cap_len, k, d_keys, d_ids);
     return cudaGetLastError();
 }
