@@ -155,6 +155,165 @@ def run_reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------
+# second half of the metric: BM25 intersect docs/sec (BASELINE.json configs[3])
+# ------------------------------------------------------------------------------------------------
+POSTING_QUERIES = [(1, 2, 3), (1, 10, 100), (2, 5, 9), (3, 30, 300), (1, 100, 10000), (10, 20, 30), (4, 8, 16), (50, 60, 70)]
+
+
+def cpu_postings_baseline(n_docs, threads):
+    """3-term AND + BM25STD + top-10 on the host with our C restatement of the reference's Rust iterators
+    (kind "port": the reference's posting path cannot be built here — no Rust toolchain)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+
+    import oracle_lib as ol
+
+    L = ol.postings()
+    doc_len = np.zeros(n_docs + 1, dtype=np.uint32)
+    # doc lengths via the same hash (vectorised replica of orc_synth_doclen is not needed for timing: constant cost)
+    doc_len[1:] = 50 + (np.arange(1, n_docs + 1, dtype=np.uint64) * np.uint64(2654435761) % np.uint64(451)).astype(np.uint32)
+    reps = max(1, threads // len(POSTING_QUERIES))
+    terms, keep, postings = [], [], 0
+    for q in POSTING_QUERIES:
+        trio = []
+        for r in q:
+            ix = ol.InvIndex(ol.CODEC_FREQS_ONLY)
+            postings += L.orc_ii_fill_synth(ix.h, n_docs, r)
+            trio.append(ix)
+        keep.append(trio)
+    for _ in range(reps):
+        for trio in keep:
+            terms += [ix.h for ix in trio]
+    nq = len(terms) // 3
+    arr = (C.c_void_p * len(terms))(*terms)
+    ids = np.zeros(nq * 10, dtype=np.uint64)
+    sc = np.zeros(nq * 10, dtype=np.float64)
+    hits = np.zeros(nq, dtype=np.uint64)
+    secs = L.orc_time_search3(arr, nq, ol._p(doc_len), n_docs, float(doc_len[1:].mean()), 10, min(threads, nq), ol._p(ids), ol._p(sc), ol._p(hits))
+    total = postings * reps
+    return {"value": total / secs, "unit": "postings/s", "cores": min(threads, nq), "kind": "port",
+            "sample": f"{nq} queries (the {len(POSTING_QUERIES)} rank triples x {reps}) over a {n_docs}-doc synthetic Zipf index, FreqsOnly blocks, "
+                      f"reader+Intersection::read+BM25STD+top-10 per query, one query per thread; {total} input postings",
+            "sample_seconds": secs}
+
+
+def bench_postings(torch, dev, stream_ptr, n_docs, steps):
+    import numpy as np
+
+    from redisearch_b200 import postings as ps
+    from redisearch_b200._lib import load_library
+
+    S = load_library("libsynth_b200.so")
+    S.Synth_DocFreq.restype = C.c_uint64
+    S.Synth_DocFreq.argtypes = [C.c_uint64, C.c_uint64]
+    S.Synth_Postings.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    S.Synth_DocLens.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p]
+    S.Synth_EncodeFreqsOnlyBlocks.restype = C.c_size_t
+    S.Synth_EncodeFreqsOnlyBlocks.argtypes = [C.c_void_p] * 8 + [C.POINTER(C.c_size_t)]
+    L = ps.lib()
+    chunks = (n_docs + 1023) // 1024
+    scratch = torch.empty(2 * chunks + 16, dtype=torch.int32, device=dev)
+    d_total = torch.zeros(4, dtype=torch.int32, device=dev)
+    h_count = np.zeros(4, dtype=np.uint32)
+    d_len = torch.empty(n_docs + 1, dtype=torch.int32, device=dev)
+    assert S.Synth_DocLens(n_docs, d_len.data_ptr(), stream_ptr) == 0
+    torch.cuda.synchronize()
+    avg_len = float(d_len[1:].double().mean().item())
+    dt = L.II_DocTable_FromDevice(n_docs, d_len.data_ptr(), None, None)
+    assert dt
+    ranks = sorted({r for q in POSTING_QUERIES for r in q})
+    lists, host_lists = {}, {}
+    for r in ranks:
+        cap = int(S.Synth_DocFreq(n_docs, r) * 1.2) + 4096
+        ids = torch.empty(cap, dtype=torch.int32, device=dev)
+        fr = torch.empty(cap, dtype=torch.int32, device=dev)
+        assert S.Synth_Postings(n_docs, r, ids.data_ptr(), fr.data_ptr(), scratch.data_ptr(), d_total.data_ptr(), h_count.ctypes.data, stream_ptr) == 0
+        n = int(h_count[0])
+        lists[r] = L.II_PostingList_FromDevice(ids.data_ptr(), fr.data_ptr(), n)
+        host_lists[r] = (ids[:n].cpu().numpy().view(np.uint32).copy(), fr[:n].cpu().numpy().view(np.uint32).copy())
+        assert lists[r]
+    st = ps.II_IndexStats(n_docs, 0, avg_len)
+
+    def run_query(q, handles):
+        arr = (C.c_void_p * 3)(*handles)
+        terms = (ps.II_TermParams * 3)(*[ps.II_TermParams(1.0, L.II_CalculateIDF(n_docs, len(host_lists[r][0])),
+                                                          L.II_CalculateIDF_BM25(n_docs, len(host_lists[r][0]))) for r in q])
+        ids = np.zeros(10, dtype=np.uint64)
+        sc = np.zeros(10, dtype=np.float64)
+        tot = C.c_size_t(0)
+        got = L.II_SearchTopN(arr, 3, 0, ps.SCORER_BM25STD, terms, 1.0, C.byref(st), dt, 10, ids.ctypes.data, sc.ctypes.data, C.byref(tot))
+        return ids[:got].copy(), sc[:got].copy(), tot.value
+
+    in_postings = sum(len(host_lists[r][0]) for q in POSTING_QUERIES for r in q)
+    for q in POSTING_QUERIES:  # warm-up
+        run_query(q, [lists[r] for r in q])
+    ps.stats(reset=True)
+    dev_us, hits, results = 0.0, 0, {}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for q in POSTING_QUERIES:
+            results[q] = run_query(q, [lists[r] for r in q])
+            s_ = ps.stats(reset=False)
+            dev_us += s_.intersect_device_us + s_.score_device_us
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / steps
+    launches = ps.stats(reset=True).kernel_launches
+    hits = sum(results[q][2] for q in POSTING_QUERIES)
+    dev_s = dev_us * 1e-6 / steps
+    # e2e: encoded IndexBlocks on the host -> decode (all cores) -> H2D -> AND + BM25STD + top-10 -> host
+    enc = {}
+    for r in ranks:
+        ids, fr = host_lists[r]
+        n = len(ids)
+        nb = n // 100 + 2
+        out = np.zeros(n * 9 + 64, dtype=np.uint8)
+        first, last = np.zeros(nb, dtype=np.uint64), np.zeros(nb, dtype=np.uint64)
+        bn, off = np.zeros(nb, dtype=np.uint16), np.zeros(nb + 1, dtype=np.uint64)
+        nblocks = C.c_size_t(0)
+        S.Synth_EncodeFreqsOnlyBlocks(ids.ctypes.data, fr.ctypes.data, n, out.ctypes.data, first.ctypes.data, last.ctypes.data,
+                                      bn.ctypes.data, off.ctypes.data, C.byref(nblocks))
+        views = (ps.II_BlockView * nblocks.value)()
+        base = out.ctypes.data
+        for b in range(nblocks.value):
+            views[b] = ps.II_BlockView(int(first[b]), int(last[b]), int(bn[b]), C.cast(base + int(off[b]), C.POINTER(C.c_uint8)), int(off[b + 1] - off[b]))
+        enc[r] = (views, nblocks.value, out, int(off[nblocks.value]))
+    enc_bytes = sum(enc[r][3] for q in POSTING_QUERIES for r in q)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    decode_us = 0.0
+    for q in POSTING_QUERIES:
+        hs = []
+        for r in q:
+            h = L.II_PostingList_FromBlocks(enc[r][0], enc[r][1], ps.CODEC_FREQS_ONLY, 0, 0)
+            decode_us += ps.stats(reset=False).decode_host_us
+            hs.append(h)
+        e_ids, e_sc, _ = run_query(q, hs)
+        assert e_ids.tolist() == results[q][0].tolist()
+        for h in hs:
+            L.II_PostingList_Free(h)
+    e2e_wall = time.perf_counter() - t0
+    alg_bytes = in_postings * 8 + hits * 16
+    peak, _ = load_peaks()
+    for h in lists.values():
+        L.II_PostingList_Free(h)
+    L.II_DocTable_Free(dt)
+    return {
+        "metric": "BM25 intersect docs/sec", "value": in_postings / wall, "unit": "input postings/s",
+        "matched_docs_per_s": hits / wall, "ms_per_query_set": wall * 1000.0, "gpu_launches": int(launches),
+        "config": {"workload": f"3-term AND + BM25STD + top-10 over a {n_docs}-doc synthetic Zipf index, {len(POSTING_QUERIES)} queries "
+                               f"(rank triples {POSTING_QUERIES}), postings resident in HBM", "input_postings": in_postings, "matched_docs": hits},
+        "e2e": {"value": in_postings / e2e_wall, "unit": "input postings/s", "h2d_bytes_per_step": in_postings * 8,
+                "d2h_bytes_per_step": len(POSTING_QUERIES) * 10 * 16, "encoded_bytes": enc_bytes,
+                "host_decode_ms": decode_us / 1000.0, "ms_per_query_set": e2e_wall * 1000.0,
+                "note": "FreqsOnly IndexBlocks on the host -> II_PostingList_FromBlocks (decode on all cores + H2D) -> II_SearchTopN"},
+        "roofline": {"bound": "hbm", "achieved": alg_bytes / dev_s / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg_bytes / dev_s / 1e9 / peak, "traffic": None, "kernel": "intersect_kernel + gather_kernel + score_kernel",
+                     "device_ms_per_query_set": dev_s * 1000.0, "algorithmic_bytes": alg_bytes},
+    }
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -167,6 +326,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--ref-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-postings", action="store_true")
+    ap.add_argument("--posting-docs", type=int, default=50_000_000)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -344,10 +505,19 @@ def main():
                                           "kernel": "scan_topk_kernel<f32,IP,4,1>", "avg_launch_us": b1_scan_us,
                                           "algorithmic_bytes_per_launch": b1_bytes}},
         }
+        if world == 1 and not args.no_postings:
+            del index
+            torch.cuda.empty_cache()
+            try:
+                line["bm25_intersect"] = bench_postings(torch, dev, sp, args.posting_docs, max(1, min(args.steps, 5)))
+            except Exception as e:
+                line["bm25_intersect"] = {"value": None, "error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 _, info = cpu_reference_qps(args.ref_sample_rows, 2, os.cpu_count() or 1)
                 line["cpu_baseline"] = info
+                if isinstance(line.get("bm25_intersect"), dict) and line["bm25_intersect"].get("value"):
+                    line["bm25_intersect"]["cpu_baseline"] = cpu_postings_baseline(2_000_000, os.cpu_count() or 1)
             except Exception as e:  # the baseline is a reported side number; never fail the bench on it
                 line["cpu_baseline"] = {"value": None, "error": repr(e)}
         print(json.dumps(line))

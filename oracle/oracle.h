@@ -158,6 +158,12 @@ enum { ORC_SCORER_BM25STD = 0, ORC_SCORER_BM25, ORC_SCORER_TFIDF, ORC_SCORER_TFI
 double orc_score(int scorer, const OrcIndexStats *st, const OrcScoreDoc *d, int slop, double min_score,
                  double tanh_factor);
 
+/* Bulk-add every member of vocabulary rank `rank` (synthetic Zipf corpus below); returns the count. */
+size_t orc_ii_fill_synth(OrcInvIndex *ii, uint64_t n_docs, uint64_t rank);
+/* CPU baseline: nq 3-term AND + BM25STD + top-N queries (terms = nq*3 indexes), one query per thread. */
+double orc_time_search3(OrcInvIndex **terms, size_t nq, const uint32_t *doc_len, uint64_t n_docs, double avg_doc_len,
+                        size_t top_n, int nthreads, uint64_t *out_ids, double *out_scores, size_t *out_hits);
+
 /* Synthetic Zipf postings shared with the CUDA path. */
 uint64_t orc_synth_df(uint64_t n_docs, uint64_t rank);
 int orc_synth_member(uint64_t n_docs, uint64_t rank, uint64_t doc, uint32_t *tf);

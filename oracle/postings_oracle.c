@@ -696,3 +696,104 @@ int orc_synth_member(uint64_t n_docs, uint64_t rank, uint64_t doc, uint32_t *tf)
     return 1;
 }
 uint32_t orc_synth_doclen(uint64_t doc) { return 50u + (uint32_t)(orc_mix64(11, doc, 0) % 451u); }
+
+/* ------------------------------------------------------------------ bulk fill + CPU baseline -- */
+size_t orc_ii_fill_synth(OrcInvIndex *ii, uint64_t n_docs, uint64_t rank) {
+    size_t added = 0;
+    for (uint64_t d = 1; d <= n_docs; d++) {
+        uint32_t tf;
+        if (orc_synth_member(n_docs, rank, d, &tf)) {
+            orc_ii_add(ii, d, tf, 1, NULL, 0);
+            added++;
+        }
+    }
+    return added;
+}
+
+#include <pthread.h>
+#include <time.h>
+double orc_score(int scorer, const OrcIndexStats *st, const OrcScoreDoc *d, int slop, double min_score, double tanh_factor);
+
+typedef struct {
+    OrcInvIndex **terms; /* nq * 3 indexes */
+    const uint32_t *doc_len;
+    uint64_t n_docs;
+    double avg_doc_len;
+    size_t nq, top_n;
+    size_t *next;
+    pthread_mutex_t *mu;
+    uint64_t *out_ids;   /* nq * top_n */
+    double *out_scores;
+    size_t *out_hits;
+} SearchWork;
+
+/* One FT.SEARCH "t1 t2 t3" worth of hot path on the CPU: readers over the encoded blocks ->
+ * Intersection::read loop -> BM25STD per hit -> top-N by (score desc, docId asc)
+ * (src/result_processor.c:317-379, 570-603, 752-850). */
+static void search_one(SearchWork *w, size_t q) {
+    OrcReader *r[3];
+    for (int i = 0; i < 3; i++) r[i] = orc_reader_new(w->terms[q * 3 + i], 0);
+    Inter it;
+    inter_init(&it, r, 3);
+    double idf[3], w1[3] = {1.0, 1.0, 1.0}, zero[3] = {0, 0, 0};
+    for (size_t i = 0; i < 3; i++) idf[i] = orc_idf_bm25(w->n_docs, orc_ii_num_docs(it.c[i].r->ii));
+    OrcIndexStats st = {w->n_docs, 0, w->avg_doc_len};
+    uint64_t *ids = w->out_ids + q * w->top_n;
+    double *sc = w->out_scores + q * w->top_n;
+    size_t have = 0, hits = 0;
+    OrcHit h;
+    while (inter_read(&it, &h)) {
+        uint32_t fr[3] = {h.child_freq[0], h.child_freq[1], h.child_freq[2]};
+        OrcScoreDoc d = {3, fr, zero, idf, w1, 1.0, w->doc_len[h.doc_id], 1, 1.0f};
+        double s = orc_score(ORC_SCORER_BM25STD, &st, &d, 1, 0, 0);
+        hits++;
+        /* insertion into a small sorted array = the RPSorter heap for tiny N */
+        size_t pos = have;
+        while (pos > 0 && (sc[pos - 1] < s)) pos--;
+        if (pos < w->top_n) {
+            size_t end = have < w->top_n ? have : w->top_n - 1;
+            for (size_t k = end; k > pos; k--) {
+                sc[k] = sc[k - 1];
+                ids[k] = ids[k - 1];
+            }
+            sc[pos] = s;
+            ids[pos] = h.doc_id;
+            if (have < w->top_n) have++;
+        }
+    }
+    for (size_t k = have; k < w->top_n; k++) {
+        ids[k] = 0;
+        sc[k] = 0;
+    }
+    w->out_hits[q] = hits;
+    free(it.c);
+    for (int i = 0; i < 3; i++) orc_reader_free(r[i]);
+}
+static void *search_worker(void *arg) {
+    SearchWork *w = (SearchWork *)arg;
+    for (;;) {
+        pthread_mutex_lock(w->mu);
+        size_t q = (*w->next)++;
+        pthread_mutex_unlock(w->mu);
+        if (q >= w->nq) break;
+        search_one(w, q);
+    }
+    return NULL;
+}
+/* Wall seconds for nq 3-term AND + BM25STD + top-N queries over `terms` (nq*3 indexes) on nthreads
+ * threads (one query per thread, like the reference's worker pool). */
+double orc_time_search3(OrcInvIndex **terms, size_t nq, const uint32_t *doc_len, uint64_t n_docs, double avg_doc_len,
+                        size_t top_n, int nthreads, uint64_t *out_ids, double *out_scores, size_t *out_hits) {
+    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    size_t next = 0;
+    SearchWork w = {terms, doc_len, n_docs, avg_doc_len, nq, top_n, &next, &mu, out_ids, out_scores, out_hits};
+    if (nthreads < 1) nthreads = 1;
+    pthread_t *th = (pthread_t *)malloc((size_t)nthreads * sizeof(pthread_t));
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, search_worker, &w);
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    free(th);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

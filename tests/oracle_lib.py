@@ -361,6 +361,10 @@ def postings():
         L.orc_synth_member.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, _P]
         L.orc_synth_doclen.restype = C.c_uint32
         L.orc_synth_doclen.argtypes = [C.c_uint64]
+        L.orc_ii_fill_synth.restype = _SZ
+        L.orc_ii_fill_synth.argtypes = [_P, C.c_uint64, C.c_uint64]
+        L.orc_time_search3.restype = C.c_double
+        L.orc_time_search3.argtypes = [_P, _SZ, _P, C.c_uint64, C.c_double, _SZ, C.c_int, _P, _P, _P]
         _post_bound = True
     return L
 
