@@ -517,7 +517,7 @@ def main():
                 _, info = cpu_reference_qps(args.ref_sample_rows, 2, os.cpu_count() or 1)
                 line["cpu_baseline"] = info
                 if isinstance(line.get("bm25_intersect"), dict) and line["bm25_intersect"].get("value"):
-                    line["bm25_intersect"]["cpu_baseline"] = cpu_postings_baseline(2_000_000, os.cpu_count() or 1)
+                    line["bm25_intersect"]["cpu_baseline"] = cpu_postings_baseline(10_000_000, os.cpu_count() or 1)
             except Exception as e:  # the baseline is a reported side number; never fail the bench on it
                 line["cpu_baseline"] = {"value": None, "error": repr(e)}
         print(json.dumps(line))

@@ -20,9 +20,26 @@ namespace {
 struct Ctx { // one stream; calls are serialised (RediSearch runs one iterator tree per worker thread)
     std::mutex mu;
     cudaStream_t stream = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     uint32_t *d_total = nullptr, *h_total = nullptr;
+    uint8_t *h_stage = nullptr; // grow-only pinned staging for decoded postings / top-N lists
+    size_t h_stage_cap = 0;
     II_Stats stats{};
+    uint8_t *stage(size_t bytes) {
+        if (bytes > h_stage_cap) {
+            cudaStreamSynchronize(stream);
+            cudaFreeHost(h_stage);
+            h_stage = nullptr;
+            h_stage_cap = 0;
+            const size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+            if (cudaMallocHost(&h_stage, cap) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            h_stage_cap = cap;
+        }
+        return h_stage;
+    }
     bool ok = false;
     bool init() {
         if (ok) return true;
@@ -35,7 +52,15 @@ struct Ctx { // one stream; calls are serialised (RediSearch runs one iterator t
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
+        cudaEventCreate(&e2);
         if (cudaMalloc(&d_total, 16) != cudaSuccess || cudaMallocHost(&h_total, 16) != cudaSuccess) return false;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX; // never trim: scratch of one query is reused by the next
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
         ok = true;
         return true;
     }
@@ -45,15 +70,26 @@ Ctx &ctx() {
     return c;
 }
 
+// Stream-ordered allocations from the device's default memory pool (kept warm: no cudaMalloc /
+// cudaFree on the query path).  Everything is allocated, used and freed in ctx().stream order.
 template <typename T>
 T *dalloc(size_t n) {
     T *p = nullptr;
     if (n == 0) n = 1;
-    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) {
+    if (cudaMallocAsync(&p, n * sizeof(T), ctx().stream) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
     return p;
+}
+inline void dfree(void *p) {
+    if (p) cudaFreeAsync(p, ctx().stream);
+}
+
+inline cudaError_t copy_sync(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, ctx().stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(ctx().stream);
 }
 
 double now_us() {
@@ -68,8 +104,8 @@ struct II_PostingList {
     size_t estimated = 0; // unfiltered unique docs (num_estimated of the leaf iterator)
     uint32_t last_id = 0;
     ~II_PostingList() {
-        cudaFree(d_ids);
-        cudaFree(d_freqs);
+        dfree(d_ids);
+        dfree(d_freqs);
     }
 };
 
@@ -78,23 +114,25 @@ struct II_DocTable {
     float *d_score = nullptr;
     size_t max_doc = 0;
     ~II_DocTable() {
-        cudaFree(d_len);
-        cudaFree(d_maxf);
-        cudaFree(d_score);
+        dfree(d_len);
+        dfree(d_maxf);
+        dfree(d_score);
     }
 };
 
 struct II_ResultSet {
     uint32_t *d_docs = nullptr, *d_freqs = nullptr; // freqs [n_children][cap]
     double *d_scores = nullptr;
+    uint32_t *d_len = nullptr; // hit count on the device (valid in stream order right after the AND/OR kernels)
     size_t cap = 0, len = 0;
     uint32_t n_children = 0;
     uint32_t child_order[kIIMaxLists] = {0};
     bool is_union = false, has_freqs = true, scored = false;
     ~II_ResultSet() {
-        cudaFree(d_docs);
-        cudaFree(d_freqs);
-        cudaFree(d_scores);
+        dfree(d_docs);
+        dfree(d_freqs);
+        dfree(d_scores);
+        dfree(d_len);
     }
 };
 
@@ -216,14 +254,14 @@ II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nbl
             c.stats.h2d_us = now_us() - t0;
             c.stats.decode_host_us = 0;
             c.stats.kernel_launches += 1;
-            cudaFree(d_bytes);
-            cudaFree(d_boff);
-            cudaFree(d_first);
-            cudaFree(d_eoff);
+            dfree(d_bytes);
+            dfree(d_boff);
+            dfree(d_first);
+            dfree(d_eoff);
         } else {
-            uint32_t *h_ids = nullptr, *h_freqs = nullptr, *h_masks = nullptr;
-            ok = cudaMallocHost(&h_ids, n * 4) == cudaSuccess && cudaMallocHost(&h_freqs, n * 4) == cudaSuccess &&
-                 (!need_mask || cudaMallocHost(&h_masks, n * 4) == cudaSuccess);
+            uint8_t *stg = c.stage(n * 4 * (need_mask ? 3 : 2));
+            uint32_t *h_ids = reinterpret_cast<uint32_t *>(stg), *h_freqs = h_ids + n, *h_masks = need_mask ? h_freqs + n : nullptr;
+            ok = stg != nullptr;
             if (ok) {
                 const double t0 = now_us();
                 unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 64u, (unsigned)(nblocks / 256 + 1)}));
@@ -246,9 +284,6 @@ II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nbl
                 ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
                 c.stats.h2d_us = now_us() - t1;
             }
-            cudaFreeHost(h_ids);
-            cudaFreeHost(h_freqs);
-            cudaFreeHost(h_masks);
         }
     }
     size_t kept = n;
@@ -267,22 +302,22 @@ II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nbl
             std::swap(d_ids, d_ids2);
             std::swap(d_freqs, d_freqs2);
         }
-        cudaFree(d_ids2);
-        cudaFree(d_freqs2);
-        cudaFree(d_counts);
-        cudaFree(d_offs);
+        dfree(d_ids2);
+        dfree(d_freqs2);
+        dfree(d_counts);
+        dfree(d_offs);
     }
-    cudaFree(d_masks);
+    dfree(d_masks);
     if (!ok) {
-        cudaFree(d_ids);
-        cudaFree(d_freqs);
+        dfree(d_ids);
+        dfree(d_freqs);
         delete pl;
         return nullptr;
     }
     pl->d_ids = d_ids;
     pl->d_freqs = d_freqs;
     pl->n = kept;
-    if (kept) cudaMemcpy(&pl->last_id, d_ids + kept - 1, 4, cudaMemcpyDeviceToHost);
+    if (kept) copy_sync(&pl->last_id, d_ids + kept - 1, 4, cudaMemcpyDeviceToHost);
     return pl;
 }
 
@@ -300,8 +335,8 @@ II_PostingList *II_PostingList_FromArrays(const uint64_t *doc_ids, const uint32_
     pl->d_ids = dalloc<uint32_t>(n);
     pl->d_freqs = dalloc<uint32_t>(n);
     if (!pl->d_ids || !pl->d_freqs ||
-        (n && (cudaMemcpy(pl->d_ids, ids32.data(), n * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-               cudaMemcpy(pl->d_freqs, f32.data(), n * 4, cudaMemcpyHostToDevice) != cudaSuccess))) {
+        (n && (copy_sync(pl->d_ids, ids32.data(), n * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+               copy_sync(pl->d_freqs, f32.data(), n * 4, cudaMemcpyHostToDevice) != cudaSuccess))) {
         delete pl;
         return nullptr;
     }
@@ -319,14 +354,14 @@ II_PostingList *II_PostingList_FromDevice(const uint32_t *d_doc_ids, const uint3
     pl->d_freqs = dalloc<uint32_t>(n);
     bool ok = pl->d_ids && pl->d_freqs;
     if (ok && n) {
-        ok = cudaMemcpy(pl->d_ids, d_doc_ids, n * 4, cudaMemcpyDeviceToDevice) == cudaSuccess;
+        ok = copy_sync(pl->d_ids, d_doc_ids, n * 4, cudaMemcpyDeviceToDevice) == cudaSuccess;
         if (d_freqs)
-            ok = ok && cudaMemcpy(pl->d_freqs, d_freqs, n * 4, cudaMemcpyDeviceToDevice) == cudaSuccess;
+            ok = ok && copy_sync(pl->d_freqs, d_freqs, n * 4, cudaMemcpyDeviceToDevice) == cudaSuccess;
         else {
             std::vector<uint32_t> ones(n, 1);
-            ok = ok && cudaMemcpy(pl->d_freqs, ones.data(), n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+            ok = ok && copy_sync(pl->d_freqs, ones.data(), n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
         }
-        ok = ok && cudaMemcpy(&pl->last_id, pl->d_ids + n - 1, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+        ok = ok && copy_sync(&pl->last_id, pl->d_ids + n - 1, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
     }
     if (!ok) {
         delete pl;
@@ -352,15 +387,15 @@ static II_DocTable *doctable_from(size_t max_doc_id, const uint32_t *len, const 
     bool ok = true;
     if (len) {
         dt->d_len = dalloc<uint32_t>(n);
-        ok = ok && dt->d_len && cudaMemcpy(dt->d_len, len, n * 4, kind) == cudaSuccess;
+        ok = ok && dt->d_len && copy_sync(dt->d_len, len, n * 4, kind) == cudaSuccess;
     }
     if (score) {
         dt->d_score = dalloc<float>(n);
-        ok = ok && dt->d_score && cudaMemcpy(dt->d_score, score, n * 4, kind) == cudaSuccess;
+        ok = ok && dt->d_score && copy_sync(dt->d_score, score, n * 4, kind) == cudaSuccess;
     }
     if (maxf) {
         dt->d_maxf = dalloc<uint32_t>(n);
-        ok = ok && dt->d_maxf && cudaMemcpy(dt->d_maxf, maxf, n * 4, kind) == cudaSuccess;
+        ok = ok && dt->d_maxf && copy_sync(dt->d_maxf, maxf, n * 4, kind) == cudaSuccess;
     }
     if (!ok) {
         delete dt;
@@ -378,13 +413,13 @@ II_DocTable *II_DocTable_FromDevice(size_t max_doc_id, const uint32_t *d_doc_len
 void II_DocTable_Free(II_DocTable *dt) { delete dt; }
 
 // ------------------------------------------------------------------------------------------------
-// AND
+// AND / OR: enqueue-only cores (no host synchronisation) + synchronous public wrappers
 // ------------------------------------------------------------------------------------------------
-II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n) {
-    if (n == 0 || n > (size_t)kIIMaxLists) return nullptr;
-    Ctx &c = ctx();
-    std::lock_guard<std::mutex> g(c.mu);
-    if (!c.init()) return nullptr;
+namespace {
+
+// Enqueue the kernels of an intersection on ctx().stream.  On return rs->d_len holds (will hold, in
+// stream order) the number of hits; rs->len is NOT set.  *trivially_empty = an input list is empty.
+bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_ResultSet *rs, bool *trivially_empty) {
     // Intersection::new: stable sort ascending by num_estimated (leaf weight 1.0), intersection.rs:110-145
     std::vector<uint32_t> order(n);
     for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
@@ -395,22 +430,24 @@ II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n) {
     size_t drv = 0;
     for (size_t i = 1; i < n; i++)
         if (lists[order[i]]->n < lists[order[drv]]->n) drv = i;
-    auto *rs = new II_ResultSet();
     rs->n_children = (uint32_t)n;
     for (size_t i = 0; i < n; i++) rs->child_order[i] = order[i];
+    *trivially_empty = false;
+    for (size_t i = 0; i < n; i++) *trivially_empty |= lists[i]->n == 0;
+    if (*trivially_empty) return true;
     const II_PostingList *A = lists[order[drv]];
-    bool empty = false;
-    for (size_t i = 0; i < n; i++) empty |= lists[i]->n == 0;
-    if (empty) return rs;
     const uint32_t nchunks = (uint32_t)((A->n + kIIChunk - 1) / kIIChunk);
     const size_t stride = (size_t)nchunks * kIIChunk;
     rs->cap = A->n;
     rs->d_docs = dalloc<uint32_t>(rs->cap);
     rs->d_freqs = dalloc<uint32_t>(rs->cap * n);
     rs->d_scores = dalloc<double>(rs->cap);
+    rs->d_len = dalloc<uint32_t>(4);
     uint32_t *tmp_idx = dalloc<uint32_t>(stride), *tmp_pos = dalloc<uint32_t>(stride * n);
     uint32_t *counts = dalloc<uint32_t>(nchunks), *offsets = dalloc<uint32_t>(nchunks);
-    bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && tmp_idx && tmp_pos && counts && offsets;
+    uint32_t *scratch = (n > 1) ? dalloc<uint32_t>(rs->cap * n) : nullptr;
+    bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && rs->d_len && tmp_idx && tmp_pos && counts && offsets &&
+              (n == 1 || scratch);
     if (ok) {
         // kernel list order: driver first, then the rest ascending by length (cheap rejections first)
         std::vector<uint32_t> korder;
@@ -418,7 +455,7 @@ II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n) {
         std::vector<uint32_t> rest;
         for (size_t i = 0; i < n; i++)
             if (i != drv) rest.push_back((uint32_t)i);
-        std::stable_sort(rest.begin(), rest.end(), [&](uint32_t a, uint32_t b) { return lists[order[a]]->n < lists[order[b]]->n; });
+        std::stable_sort(rest.begin(), rest.end(), [&](uint32_t x, uint32_t y) { return lists[order[x]]->n < lists[order[y]]->n; });
         korder.insert(korder.end(), rest.begin(), rest.end());
         IntersectArgs a{};
         a.n = (uint32_t)n;
@@ -431,8 +468,7 @@ II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n) {
         a.counts = counts;
         a.stride = stride;
         cudaEventRecord(c.e0, c.stream);
-        ok = ii_launch_intersect(a, nchunks, offsets, c.d_total, c.stream) == cudaSuccess;
-        // gather in AGGREGATE child order: kernel slot k holds aggregate child korder[k]
+        ok = ii_launch_intersect(a, nchunks, offsets, rs->d_len, c.stream) == cudaSuccess;
         GatherArgs ga{};
         ga.ids0 = A->d_ids;
         ga.n = (uint32_t)n;
@@ -443,50 +479,26 @@ II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n) {
         ga.stride = stride;
         ga.out_doc = rs->d_docs;
         ga.fstride = rs->cap;
-        // out_freq row for kernel slot k must land at aggregate row korder[k]: gather writes row j of
-        // its own numbering, so hand it a per-slot base through the freqs/out mapping below
         for (size_t k = 0; k < n; k++) ga.freqs[k] = lists[order[korder[k]]]->d_freqs;
-        // rows are written in kernel-slot order into a scratch, then permuted by row copies
-        uint32_t *scratch = (n > 1) ? dalloc<uint32_t>(rs->cap * n) : rs->d_freqs;
-        ok = ok && scratch;
-        ga.out_freq = scratch;
+        // rows are produced in kernel-slot order, then placed at their aggregate child index
+        ga.out_freq = (n > 1) ? scratch : rs->d_freqs;
         ok = ok && ii_launch_gather(ga, nchunks, c.stream) == cudaSuccess;
         if (ok && n > 1)
             for (size_t k = 0; k < n; k++)
                 ok = ok && cudaMemcpyAsync(rs->d_freqs + (size_t)korder[k] * rs->cap, scratch + k * rs->cap, rs->cap * 4,
                                            cudaMemcpyDeviceToDevice, c.stream) == cudaSuccess;
         cudaEventRecord(c.e1, c.stream);
-        ok = ok && cudaMemcpyAsync(c.h_total, c.d_total, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
-        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
-        if (n > 1) cudaFree(scratch);
-        if (ok) {
-            rs->len = *c.h_total;
-            float ms = 0;
-            cudaEventElapsedTime(&ms, c.e0, c.e1);
-            c.stats.intersect_device_us = ms * 1000.0;
-            c.stats.kernel_launches += 3;
-        }
+        c.stats.kernel_launches += 3;
     }
-    cudaFree(tmp_idx);
-    cudaFree(tmp_pos);
-    cudaFree(counts);
-    cudaFree(offsets);
-    if (!ok) {
-        delete rs;
-        return nullptr;
-    }
-    return rs;
+    dfree(tmp_idx);
+    dfree(tmp_pos);
+    dfree(counts);
+    dfree(offsets);
+    dfree(scratch);
+    return ok;
 }
 
-// ------------------------------------------------------------------------------------------------
-// OR
-// ------------------------------------------------------------------------------------------------
-II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit) {
-    if (n == 0 || n > (size_t)kIIMaxLists) return nullptr;
-    Ctx &c = ctx();
-    std::lock_guard<std::mutex> g(c.mu);
-    if (!c.init()) return nullptr;
-    auto *rs = new II_ResultSet();
+bool union_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int quick_exit, II_ResultSet *rs, bool *trivially_empty) {
     rs->is_union = true;
     rs->n_children = (uint32_t)n;
     rs->has_freqs = !quick_exit;
@@ -497,15 +509,17 @@ II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit) {
         if (lists[i]->n) max_id = std::max(max_id, lists[i]->last_id);
         total_in += lists[i]->n;
     }
-    if (total_in == 0) return rs;
+    *trivially_empty = total_in == 0;
+    if (*trivially_empty) return true;
     const uint32_t nwords = max_id / 32 + 1, nblk = (nwords + 31) / 32;
     rs->cap = std::min<size_t>(total_in, (size_t)max_id + 1);
     rs->d_docs = dalloc<uint32_t>(rs->cap);
     rs->d_freqs = dalloc<uint32_t>(rs->has_freqs ? rs->cap * n : 1);
     rs->d_scores = dalloc<double>(rs->cap);
+    rs->d_len = dalloc<uint32_t>(4);
     uint32_t *bitmap = dalloc<uint32_t>(nwords), *blocksum = dalloc<uint32_t>(nblk), *blockoff = dalloc<uint32_t>(nblk);
     uint32_t *wordoff = dalloc<uint32_t>(nwords);
-    bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && bitmap && blocksum && blockoff && wordoff;
+    bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && rs->d_len && bitmap && blocksum && blockoff && wordoff;
     if (ok) {
         std::vector<const uint32_t *> ids(n), freqs(n);
         std::vector<uint32_t> lens(n);
@@ -517,22 +531,99 @@ II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit) {
         cudaEventRecord(c.e0, c.stream);
         if (rs->has_freqs) ok = cudaMemsetAsync(rs->d_freqs, 0, rs->cap * n * 4, c.stream) == cudaSuccess;
         ok = ok && ii_launch_union(ids.data(), freqs.data(), lens.data(), (uint32_t)n, nwords, bitmap, blocksum, blockoff, wordoff,
-                                   c.d_total, rs->d_docs, rs->d_freqs, rs->cap, rs->has_freqs, c.stream) == cudaSuccess;
+                                   rs->d_len, rs->d_docs, rs->d_freqs, rs->cap, rs->has_freqs, c.stream) == cudaSuccess;
         cudaEventRecord(c.e1, c.stream);
-        ok = ok && cudaMemcpyAsync(c.h_total, c.d_total, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
-        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
-        if (ok) {
-            rs->len = *c.h_total;
-            float ms = 0;
-            cudaEventElapsedTime(&ms, c.e0, c.e1);
-            c.stats.intersect_device_us = ms * 1000.0;
-            c.stats.kernel_launches += 3 + 2 * n;
-        }
+        c.stats.kernel_launches += 3 + 2 * n;
     }
-    cudaFree(bitmap);
-    cudaFree(blocksum);
-    cudaFree(blockoff);
-    cudaFree(wordoff);
+    dfree(bitmap);
+    dfree(blocksum);
+    dfree(blockoff);
+    dfree(wordoff);
+    return ok;
+}
+
+// after the stream has been synchronised
+void finish_len(Ctx &c, II_ResultSet *rs) {
+    rs->len = *c.h_total;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c.e0, c.e1) == cudaSuccess) c.stats.intersect_device_us = ms * 1000.0;
+}
+
+ScoreArgs make_score_args(const II_ResultSet *rs, II_Scorer scorer, const II_TermParams *terms, double agg_weight,
+                          const II_IndexStats *stats, const II_DocTable *docs, double min_score, uint64_t tanh_factor) {
+    ScoreArgs sa{};
+    sa.scorer = (int)scorer;
+    sa.is_union = rs->is_union;
+    sa.n_children = rs->n_children;
+    for (uint32_t i = 0; i < rs->n_children; i++) {
+        const II_TermParams &t = terms[rs->child_order[i]];
+        sa.weight[i] = t.weight;
+        sa.idf[i] = t.idf;
+        sa.bm25_idf[i] = t.bm25_idf;
+    }
+    sa.agg_weight = agg_weight;
+    sa.avg_doc_len = stats ? stats->avgDocLen : 0.0;
+    sa.min_score = min_score;
+    sa.tanh_factor = tanh_factor ? tanh_factor : 1;
+    sa.doc_len = docs ? docs->d_len : nullptr;
+    sa.doc_score = docs ? docs->d_score : nullptr;
+    sa.max_freq = docs ? docs->d_maxf : nullptr;
+    return sa;
+}
+
+// merge the per-warp top-N lists the device selected (<= lists*k survivors)
+size_t merge_topn_lists(const uint64_t *keys, const uint32_t *ids, size_t total, size_t k, uint64_t *doc_ids, double *scores) {
+    std::vector<uint32_t> idx;
+    for (uint32_t i = 0; i < total; i++)
+        if (ids[i] != 0xFFFFFFFFu) idx.push_back(i);
+    const size_t kk = std::min<size_t>(k, idx.size());
+    std::partial_sort(idx.begin(), idx.begin() + kk, idx.end(), [&](uint32_t a, uint32_t b) {
+        return keys[a] < keys[b] || (keys[a] == keys[b] && ids[a] < ids[b]);
+    });
+    for (size_t i = 0; i < kk; i++) {
+        doc_ids[i] = ids[idx[i]];
+        uint64_t u = ~keys[idx[i]];
+        u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+        memcpy(&scores[i], &u, 8);
+    }
+    return kk;
+}
+
+} // namespace
+
+II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n) {
+    if (n == 0 || n > (size_t)kIIMaxLists) return nullptr;
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    auto *rs = new II_ResultSet();
+    bool empty = false;
+    bool ok = intersect_enqueue(c, lists, n, rs, &empty);
+    if (ok && !empty) {
+        ok = cudaMemcpyAsync(c.h_total, rs->d_len, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+        if (ok) finish_len(c, rs);
+    }
+    if (!ok) {
+        delete rs;
+        return nullptr;
+    }
+    return rs;
+}
+
+II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit) {
+    if (n == 0 || n > (size_t)kIIMaxLists) return nullptr;
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    auto *rs = new II_ResultSet();
+    bool empty = false;
+    bool ok = union_enqueue(c, lists, n, quick_exit, rs, &empty);
+    if (ok && !empty) {
+        ok = cudaMemcpyAsync(c.h_total, rs->d_len, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+        if (ok) finish_len(c, rs);
+    }
     if (!ok) {
         delete rs;
         return nullptr;
@@ -575,23 +666,7 @@ int II_Score(II_ResultSet *rs, II_Scorer scorer, const II_TermParams *terms, dou
         return 0;
     }
     if (!rs->has_freqs) return -1;
-    ScoreArgs sa{};
-    sa.scorer = (int)scorer;
-    sa.is_union = rs->is_union;
-    sa.n_children = rs->n_children;
-    for (uint32_t i = 0; i < rs->n_children; i++) {
-        const II_TermParams &t = terms[rs->child_order[i]];
-        sa.weight[i] = t.weight;
-        sa.idf[i] = t.idf;
-        sa.bm25_idf[i] = t.bm25_idf;
-    }
-    sa.agg_weight = agg_weight;
-    sa.avg_doc_len = stats ? stats->avgDocLen : 0.0;
-    sa.min_score = min_score;
-    sa.tanh_factor = tanh_factor ? tanh_factor : 1;
-    sa.doc_len = docs ? docs->d_len : nullptr;
-    sa.doc_score = docs ? docs->d_score : nullptr;
-    sa.max_freq = docs ? docs->d_maxf : nullptr;
+    const ScoreArgs sa = make_score_args(rs, scorer, terms, agg_weight, stats, docs, min_score, tanh_factor);
     cudaEventRecord(c.e0, c.stream);
     bool ok = ii_launch_score(sa, rs->d_docs, rs->d_freqs, rs->cap, nullptr, (uint32_t)rs->len, rs->d_scores, c.stream) == cudaSuccess;
     cudaEventRecord(c.e1, c.stream);
@@ -610,19 +685,21 @@ int II_ResultSet_Fetch(const II_ResultSet *rs, uint64_t *doc_ids, double *scores
     if (m == 0) return 0;
     if (doc_ids) {
         std::vector<uint32_t> tmp(m);
-        if (cudaMemcpy(tmp.data(), rs->d_docs, m * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        if (copy_sync(tmp.data(), rs->d_docs, m * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         for (size_t i = 0; i < m; i++) doc_ids[i] = tmp[i];
     }
     if (scores) {
         if (rs->scored) {
-            if (cudaMemcpy(scores, rs->d_scores, m * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+            if (copy_sync(scores, rs->d_scores, m * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         } else {
             for (size_t i = 0; i < m; i++) scores[i] = 0.0;
         }
     }
     if (child_freqs) {
         if (!rs->has_freqs) return -1;
-        if (cudaMemcpy2D(child_freqs, m * 4, rs->d_freqs, rs->cap * 4, m * 4, rs->n_children, cudaMemcpyDeviceToHost) != cudaSuccess)
+        if (cudaMemcpy2DAsync(child_freqs, m * 4, rs->d_freqs, rs->cap * 4, m * 4, rs->n_children, cudaMemcpyDeviceToHost,
+                              ctx().stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx().stream) != cudaSuccess)
             return -1;
     }
     return 0;
@@ -630,10 +707,11 @@ int II_ResultSet_Fetch(const II_ResultSet *rs, uint64_t *doc_ids, double *scores
 
 size_t II_ResultSet_TopN(const II_ResultSet *rs, size_t n, uint64_t *doc_ids, double *scores) {
     Ctx &c = ctx();
-    std::lock_guard<std::mutex> g(c.mu);
+    std::unique_lock<std::mutex> g(c.mu);
     if (!c.init() || rs->len == 0 || n == 0) return 0;
     const uint32_t k = (uint32_t)std::min<size_t>(n, rs->len);
     if (k > 1024) { // large LIMIT: download and partial-sort (rare; RPSorter heaps are offset+limit wide)
+        g.unlock();
         std::vector<uint64_t> ids(rs->len);
         std::vector<double> sc(rs->len);
         if (II_ResultSet_Fetch(rs, ids.data(), sc.data(), nullptr) != 0) return 0;
@@ -649,46 +727,75 @@ size_t II_ResultSet_TopN(const II_ResultSet *rs, size_t n, uint64_t *doc_ids, do
         return k;
     }
     const uint32_t lists = ii_topn_lists((uint32_t)rs->len);
-    uint64_t *d_keys = dalloc<uint64_t>((size_t)lists * k);
-    uint32_t *d_ids = dalloc<uint32_t>((size_t)lists * k);
-    bool ok = d_keys && d_ids;
+    const size_t total = (size_t)lists * k;
+    uint64_t *d_keys = dalloc<uint64_t>(total);
+    uint32_t *d_ids = dalloc<uint32_t>(total);
+    uint8_t *stg = c.stage(total * 12);
+    bool ok = d_keys && d_ids && stg;
+    uint64_t *h_keys = reinterpret_cast<uint64_t *>(stg);
+    uint32_t *h_ids = reinterpret_cast<uint32_t *>(h_keys + total);
     ok = ok && ii_launch_topn(rs->d_docs, rs->d_scores, nullptr, (uint32_t)rs->len, k, d_keys, d_ids, c.stream) == cudaSuccess;
-    std::vector<uint64_t> keys((size_t)lists * k);
-    std::vector<uint32_t> ids((size_t)lists * k);
-    ok = ok && cudaMemcpyAsync(keys.data(), d_keys, keys.size() * 8, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(ids.data(), d_ids, ids.size() * 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(h_keys, d_keys, total * 8, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(h_ids, d_ids, total * 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    dfree(d_keys);
+    dfree(d_ids);
     ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
-    cudaFree(d_keys);
-    cudaFree(d_ids);
     c.stats.kernel_launches += 1;
     if (!ok) return 0;
-    // merge the per-warp lists (device did the selection; this orders <= lists*k survivors)
-    std::vector<uint32_t> idx;
-    for (uint32_t i = 0; i < keys.size(); i++)
-        if (ids[i] != 0xFFFFFFFFu) idx.push_back(i);
-    const size_t kk = std::min<size_t>(k, idx.size());
-    std::partial_sort(idx.begin(), idx.begin() + kk, idx.end(), [&](uint32_t a, uint32_t b) {
-        return keys[a] < keys[b] || (keys[a] == keys[b] && ids[a] < ids[b]);
-    });
-    for (size_t i = 0; i < kk; i++) {
-        doc_ids[i] = ids[idx[i]];
-        uint64_t u = ~keys[idx[i]];
-        u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
-        memcpy(&scores[i], &u, 8);
-    }
-    return kk;
+    return merge_topn_lists(h_keys, h_ids, total, k, doc_ids, scores);
 }
 
+// AND/OR -> score -> top-N with ONE host synchronisation: the hit count stays on the device, every
+// kernel after the intersection reads it from rs->d_len.
 size_t II_SearchTopN(II_PostingList *const *lists, size_t n, int is_union, II_Scorer scorer, const II_TermParams *terms,
                      double agg_weight, const II_IndexStats *stats, const II_DocTable *docs, size_t top_n, uint64_t *doc_ids,
                      double *scores, size_t *total_hits) {
-    II_ResultSet *rs = is_union ? II_Union(lists, n, 0) : II_Intersect(lists, n);
-    if (!rs) return 0;
-    if (total_hits) *total_hits = rs->len;
-    size_t got = 0;
-    if (II_Score(rs, scorer, terms, agg_weight, stats, docs, 0.0, 4) == 0) got = II_ResultSet_TopN(rs, top_n, doc_ids, scores);
-    II_ResultSet_Free(rs);
-    return got;
+    if (total_hits) *total_hits = 0;
+    if (n == 0 || n > (size_t)kIIMaxLists || top_n == 0) return 0;
+    if (top_n > 1024) { // wide LIMITs take the unfused route
+        II_ResultSet *rs = is_union ? II_Union(lists, n, 0) : II_Intersect(lists, n);
+        if (!rs) return 0;
+        if (total_hits) *total_hits = rs->len;
+        size_t got = 0;
+        if (II_Score(rs, scorer, terms, agg_weight, stats, docs, 0.0, 4) == 0) got = II_ResultSet_TopN(rs, top_n, doc_ids, scores);
+        II_ResultSet_Free(rs);
+        return got;
+    }
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return 0;
+    II_ResultSet rs;
+    bool empty = false;
+    bool ok = is_union ? union_enqueue(c, lists, n, 0, &rs, &empty) : intersect_enqueue(c, lists, n, &rs, &empty);
+    if (!ok || empty) return 0;
+    const uint32_t k = (uint32_t)top_n;
+    const ScoreArgs sa = make_score_args(&rs, scorer, terms, agg_weight, stats, docs, 0.0, 4);
+    cudaEvent_t s0 = c.e1; // score timing starts where the intersection timing stopped
+    (void)s0;
+    ok = ii_launch_score(sa, rs.d_docs, rs.d_freqs, rs.cap, rs.d_len, (uint32_t)rs.cap, rs.d_scores, c.stream) == cudaSuccess;
+    const uint32_t nl = ii_topn_lists((uint32_t)rs.cap);
+    const size_t total = (size_t)nl * k;
+    uint64_t *d_keys = dalloc<uint64_t>(total);
+    uint32_t *d_ids = dalloc<uint32_t>(total);
+    uint8_t *stg = c.stage(total * 12);
+    ok = ok && d_keys && d_ids && stg;
+    uint64_t *h_keys = reinterpret_cast<uint64_t *>(stg);
+    uint32_t *h_ids = reinterpret_cast<uint32_t *>(h_keys + total);
+    ok = ok && ii_launch_topn(rs.d_docs, rs.d_scores, rs.d_len, (uint32_t)rs.cap, k, d_keys, d_ids, c.stream) == cudaSuccess;
+    cudaEventRecord(c.e2, c.stream);
+    ok = ok && cudaMemcpyAsync(h_keys, d_keys, total * 8, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(h_ids, d_ids, total * 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c.h_total, rs.d_len, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    dfree(d_keys);
+    dfree(d_ids);
+    ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+    c.stats.kernel_launches += 2;
+    if (!ok) return 0;
+    finish_len(c, &rs);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c.e1, c.e2) == cudaSuccess) c.stats.score_device_us = ms * 1000.0;
+    if (total_hits) *total_hits = rs.len;
+    return merge_topn_lists(h_keys, h_ids, total, std::min<size_t>(k, rs.len), doc_ids, scores);
 }
 
 // ------------------------------------------------------------------------------------------------
