@@ -260,6 +260,8 @@ int VecSimB200_MergeShardTopK(const float *d_scores, const int64_t *d_labels, si
                ? 0
                : -1;
 }
+void VecSimB200_SetCoarseMode(int mode) { rsb200::set_coarse_mode(mode); }
+int VecSimB200_LastCoarseFlags(VecSimIndex *index, uint32_t *out_ok, size_t nq) { return IX(index)->last_coarse_flags(out_ok, nq); }
 const char *VecSimB200_Version(void) { return "vecsim_b200 0.1 (sm_100a)"; }
 
 } // extern "C"

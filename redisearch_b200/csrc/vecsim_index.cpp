@@ -2,11 +2,13 @@
 #include "vecsim_index.h"
 #include "host_numeric.h"
 #include "topk_common.cuh"
+#include "coarse_tf32.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -619,6 +621,62 @@ VecSimQueryReply *FlatIndex::topk(const void *q, size_t k, VecSimQueryParams *qp
     return rep;
 }
 
+std::atomic<int> g_coarse_mode{-1}; // -1 = from env VECSIM_B200_COARSE (default on), 0 = off, 1 = on
+
+static bool coarse_enabled() {
+    int m = g_coarse_mode.load();
+    if (m < 0) {
+        const char *e = getenv("VECSIM_B200_COARSE");
+        m = (e && e[0] == '0') ? 0 : 1;
+        g_coarse_mode.store(m);
+    }
+    return m != 0;
+}
+
+// Enqueue on `st`: the `ke` best composites of each of `nq` device-resident stored-form queries into
+// d_out [nq][ke].  Cosine fp32 batches take the tensor-core coarse pass + exact rescoring + proof, with
+// the exact scan as an on-device fallback for unverified queries; everything else takes the exact
+// fused scan.  ev_start/ev_stop of `c` bracket the dominant scan kernel.
+bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t nq, uint32_t ke, cudaStream_t st,
+                           LaunchCounters &lc, uint64_t **d_result) {
+    const CorpusView v = view();
+    const ScanPlan sp = plan_scan_topk(v, nq, ke);
+    const bool coarse = coarse_enabled() && metric_ == VecSimMetric_Cosine && !multi_ && coarse_supported(v, nq, ke);
+    last_batch_coarse_ = coarse;
+    if (!coarse) {
+        if (!c.need_cand(sp.cand_elems) || !c.need_out((size_t)nq * ke)) return false;
+        cudaEventRecord(c.ev_start, st);
+        bool ok = launch_scan_topk(v, d_q, qpitch, nq, ke, sp, c.d_cand, st, &lc) == cudaSuccess;
+        cudaEventRecord(c.ev_stop, st);
+        ok = ok && launch_final_select(c.d_cand, nq, sp.lists_per_query * ke, ke, c.d_out, st, &lc) == cudaSuccess;
+        *d_result = c.d_out;
+        return ok;
+    }
+    const CoarsePlan cp = plan_coarse(v, nq);
+    const size_t per_query = (size_t)cp.grid_x * cp.keep;
+    const size_t nA = (size_t)nq * per_query, nO = (size_t)nq * ke;
+    const size_t total = 2 * nA + 2 * nO + sp.cand_elems + (nq + 1) / 2 + 8;
+    if (!c.need_cand(total) || !c.need_out(nO)) return false;
+    uint64_t *coarse_cand = c.d_cand, *exact = coarse_cand + nA, *out1 = exact + nA, *out2 = out1 + nO, *cand2 = out2 + nO;
+    uint32_t *d_ok = reinterpret_cast<uint32_t *>(cand2 + sp.cand_elems);
+    c.d_last_ok = d_ok;
+    c.last_ok_n = nq;
+    cudaEventRecord(c.ev_start, st);
+    bool ok = launch_coarse(v, d_q, qpitch, nq, cp, coarse_cand, st) == cudaSuccess;
+    cudaEventRecord(c.ev_stop, st);
+    ok = ok && launch_rescore(v, d_q, qpitch, nq, (uint32_t)per_query, coarse_cand, exact, st) == cudaSuccess;
+    ok = ok && launch_final_select(exact, nq, (uint32_t)per_query, ke, out1, st, &lc) == cudaSuccess;
+    ok = ok && launch_verify(coarse_cand, out1, nq, cp.grid_x, cp.keep, ke, kCoarseEpsUnit, d_ok, st) == cudaSuccess;
+    // exact fallback, entirely on device: CTAs whose queries are all verified exit at once
+    ok = ok && launch_scan_topk(v, d_q, qpitch, nq, ke, sp, cand2, st, &lc, d_ok) == cudaSuccess;
+    ok = ok && launch_final_select(cand2, nq, sp.lists_per_query * ke, ke, out2, st, &lc) == cudaSuccess;
+    ok = ok && launch_blend(d_ok, out1, out2, nq, ke, c.d_out, st, &lc) == cudaSuccess;
+    lc.launches += 3;
+    coarse_batches_++;
+    *d_result = c.d_out;
+    return ok;
+}
+
 int FlatIndex::topk_batch(const void *qs, size_t qstride, size_t nq, size_t k, VecSimQueryParams *qp, size_t *out_labels,
                           double *out_scores) {
     void *tctx = qp ? qp->timeoutCtx : nullptr;
@@ -651,20 +709,15 @@ int FlatIndex::topk_batch(const void *qs, size_t qstride, size_t nq, size_t k, V
     const size_t qpitch = (stored_bytes_ + 15) & ~(size_t)15;
     const uint32_t ke = (uint32_t)std::min(k, n);
     const CorpusView v = view();
-    const ScanPlan plan = plan_scan_topk(v, (uint32_t)nq, ke);
     LaunchCounters lc;
-    bool ok = c->need_query(qpitch * nq) && c->need_cand(plan.cand_elems) && c->need_out(nq * ke);
+    bool ok = c->need_query(qpitch * nq);
     if (ok) {
         memset(c->h_query, 0, qpitch * nq);
         for (size_t i = 0; i < nq; i++) preprocess_query(static_cast<const uint8_t *>(qs) + i * qstride, c->h_query + i * qpitch);
         ok = cudaMemcpyAsync(c->d_query, c->h_query, qpitch * nq, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
     }
-    if (ok) {
-        cudaEventRecord(c->ev_start, c->stream);
-        ok = launch_scan_topk(v, c->d_query, qpitch, (uint32_t)nq, ke, plan, c->d_cand, c->stream, &lc) == cudaSuccess;
-        cudaEventRecord(c->ev_stop, c->stream);
-    }
-    ok = ok && launch_final_select(c->d_cand, (uint32_t)nq, plan.lists_per_query * ke, ke, c->d_out, c->stream, &lc) == cudaSuccess;
+    uint64_t *d_res = nullptr;
+    ok = ok && batch_scan(*c, c->d_query, qpitch, (uint32_t)nq, ke, c->stream, lc, &d_res);
     ok = ok && cudaMemcpyAsync(c->h_out, c->d_out, nq * ke * 8, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
     launches_total_ += lc.launches;
@@ -718,23 +771,19 @@ int FlatIndex::topk_batch_device(const void *d_q, size_t nq, size_t k, int64_t *
     if (n == 0) {
         ok = cudaMemsetAsync(d_labels, 0xFF, nq * k * 8, st) == cudaSuccess;
     } else {
-        const CorpusView v = view();
-        const ScanPlan plan = plan_scan_topk(v, (uint32_t)nq, ke);
-        ok = c->need_cand(plan.cand_elems) && c->need_out(nq * k);
-        if (ok && ke < k) ok = cudaMemsetAsync(c->d_out, 0xFF, nq * k * 8, st) == cudaSuccess;
-        if (ok) {
-            cudaEventRecord(c->ev_start, st);
-            ok = launch_scan_topk(v, d_q, qpitch, (uint32_t)nq, ke, plan, c->d_cand, st, &lc) == cudaSuccess;
-            cudaEventRecord(c->ev_stop, st);
-        }
-        if (ok && ke == k) {
-            ok = launch_final_select(c->d_cand, (uint32_t)nq, plan.lists_per_query * ke, ke, c->d_out, st, &lc) == cudaSuccess;
-        } else if (ok) {
-            // fewer rows than k: select into a compact [nq][ke] area, then scatter rows
-            ok = c->need_out(nq * k + nq * ke);
-            uint64_t *compact = c->d_out + nq * k;
-            ok = ok && launch_final_select(c->d_cand, (uint32_t)nq, plan.lists_per_query * ke, ke, compact, st, &lc) == cudaSuccess;
-            ok = ok && cudaMemcpy2DAsync(c->d_out, k * 8, compact, ke * 8, ke * 8, nq, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
+        uint64_t *d_res = nullptr;
+        ok = c->need_out(nq * k);
+        if (!ok) {
+        } else if (ke == k) {
+            ok = batch_scan(*c, d_q, qpitch, (uint32_t)nq, ke, st, lc, &d_res);
+        } else {
+            // fewer rows than k: select [nq][ke], then widen the rows to [nq][k] (tail = empty)
+            ok = batch_scan(*c, d_q, qpitch, (uint32_t)nq, ke, st, lc, &d_res);
+            ok = ok && c->need_ids(nq * k * 2);
+            uint64_t *wide = reinterpret_cast<uint64_t *>(c->d_ids);
+            ok = ok && cudaMemsetAsync(wide, 0xFF, nq * k * 8, st) == cudaSuccess;
+            ok = ok && cudaMemcpy2DAsync(wide, k * 8, d_res, ke * 8, ke * 8, nq, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(c->d_out, wide, nq * k * 8, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
         }
         ok = ok && launch_unpack_results(c->d_out, (uint32_t)nq, (uint32_t)k, d_id_to_label_, d_labels, d_scores, st, &lc) == cudaSuccess;
         dev_timing_pending_ = ok;
@@ -1086,6 +1135,15 @@ VecSimDebugInfoIterator *FlatIndex::debug_iterator() const {
     u64("BLOCK_SIZE", block_size_);
     return it;
 }
+
+int FlatIndex::last_coarse_flags(uint32_t *out, size_t n) {
+    std::lock_guard<std::mutex> dg(dev_mu_);
+    if (!dev_ctx_ || !last_batch_coarse_ || !dev_ctx_->d_last_ok || dev_ctx_->last_ok_n < n) return -1;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    return cudaMemcpy(out, dev_ctx_->d_last_ok, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+
+void set_coarse_mode(int mode) { g_coarse_mode.store(mode); }
 
 // dev_mu_ held.  Folds the CUDA-event timing of the last topk_batch_device scan into the stats.
 void FlatIndex::collect_dev_timing_locked() {

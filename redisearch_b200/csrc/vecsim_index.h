@@ -43,6 +43,7 @@ struct Globals {
     VecSimMemoryFunctions mem{};
 };
 Globals &globals();
+void set_coarse_mode(int mode); // -1 env default, 0 exact scans only, 1 tensor-core coarse pass when eligible
 
 // Device + pinned scratch for one in-flight query (or query batch).  Checked out of a pool so
 // that many RediSearch worker threads can query one index concurrently (SURVEY.md §8b threading).
@@ -58,6 +59,8 @@ struct QueryCtx {
     float *d_scores = nullptr; // unfused path: one score per row
     size_t scores_cap = 0;
     uint32_t *d_count = nullptr, *h_count = nullptr;
+    uint32_t *d_last_ok = nullptr; // coarse path: per-query verification flags of the last batch (inside d_cand)
+    uint32_t last_ok_n = 0;
     uint32_t *d_ids = nullptr, *h_ids = nullptr;
     float *d_dist = nullptr, *h_dist = nullptr;
     size_t ids_cap = 0;
@@ -127,6 +130,8 @@ class FlatIndex {
     VecSimDebugInfoIterator *debug_iterator() const;
     void set_last_mode(VecSearchMode m) { last_mode_ = m; }
     VecSimB200_Stats get_stats(bool reset);
+    // debug: verification flags of the last device-batch call (1 = answered by the tensor-core path)
+    int last_coarse_flags(uint32_t *out, size_t n);
     const void *device_rows(size_t *pitch, size_t *rows) {
         flush();
         *pitch = pitch_;
@@ -159,6 +164,8 @@ class FlatIndex {
     // kMaxFusedK; returns the number found or -1.
     long select_from_scores(QueryCtx &c, uint32_t n, bool has_cursor, uint64_t cursor, size_t want);
     bool upload_query(QueryCtx &c, const uint8_t *stored_q, size_t nq);
+    bool batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t nq, uint32_t ke, cudaStream_t st, LaunchCounters &lc,
+                    uint64_t **d_result);
     void finish_reply(VecSimQueryReply *rep, VecSimQueryReply_Order order) const;
 
     DType dtype_;
@@ -188,6 +195,8 @@ class FlatIndex {
     mutable VecSearchMode last_mode_ = EMPTY_MODE;
 
     std::atomic<uint64_t> launches_total_{0};
+    std::atomic<uint64_t> coarse_batches_{0};
+    bool last_batch_coarse_ = false;
     std::unique_ptr<QueryCtx> dev_ctx_; // scratch of topk_batch_device (stream-ordered)
     std::mutex dev_mu_;
     bool dev_timing_pending_ = false;

@@ -86,6 +86,7 @@ struct ScanArgs {
     uint32_t q_smem_pitch; // round16(query blob bytes)
     uint32_t nq, k, wq, lists_per_query;
     uint64_t *cand;
+    const uint32_t *q_ok; // optional: queries already answered (coarse path verified) are skipped
 };
 
 template <int DT, int MT, int RT, int QT, bool QSMEM>
@@ -135,7 +136,15 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
     }
 
     const uint32_t ntiles = (a.n_rows + RT - 1) / RT;
-    if (q0 < a.nq) {
+    bool active = q0 < a.nq;
+    if (active && a.q_ok) { // exact fallback of the tensor-core path: only unverified queries are scanned
+        bool all_ok = true;
+#pragma unroll
+        for (int j = 0; j < QT; j++)
+            if (q0 + j < a.nq && !a.q_ok[q0 + j]) all_ok = false;
+        active = !all_ok;
+    }
+    if (active) {
         for (uint32_t t = blockIdx.x * WR + rg; t < ntiles; t += gridDim.x * WR) {
             const uint32_t r0 = t * RT;
             const uint8_t *rowb[RT];
@@ -467,8 +476,23 @@ static cudaError_t launch_scan_dm(const ScanArgs &a, const ScanPlan &plan, bool 
         break;                                                                                       \
     }
 
+__global__ void blend_kernel(const uint32_t *__restrict__ ok, const uint64_t *__restrict__ a, const uint64_t *__restrict__ b,
+                             uint32_t total, uint32_t k, uint64_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) out[i] = ok[i / k] ? a[i] : b[i];
+}
+cudaError_t launch_blend(const uint32_t *d_ok, const uint64_t *d_a, const uint64_t *d_b, uint32_t nq, uint32_t k, uint64_t *d_out,
+                         cudaStream_t s, LaunchCounters *ctr) {
+    const uint32_t total = nq * k;
+    if (!total) return cudaSuccess;
+    blend_kernel<<<(total + 255) / 256, 256, 0, s>>>(d_ok, d_a, d_b, total, k, d_out);
+    if (ctr) ctr->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scan_topk(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t k,
-                             const ScanPlan &plan, uint64_t *d_cand, cudaStream_t s, LaunchCounters *ctr) {
+                             const ScanPlan &plan, uint64_t *d_cand, cudaStream_t s, LaunchCounters *ctr,
+                             const uint32_t *d_q_ok) {
     if (nq == 0 || k == 0 || k > (uint32_t)kMaxFusedK || c.n_rows == 0) return cudaErrorInvalidValue;
     ScanArgs a{};
     a.rows = static_cast<const uint8_t *>(c.rows);
@@ -483,6 +507,7 @@ cudaError_t launch_scan_topk(const CorpusView &c, const void *d_queries, size_t 
     a.wq = plan.wq;
     a.lists_per_query = plan.lists_per_query;
     a.cand = d_cand;
+    a.q_ok = d_q_ok;
     const bool qsmem = (size_t)plan.wq * plan.qt * a.q_smem_pitch <= kMaxQuerySmem;
     cudaError_t e = cudaErrorInvalidValue;
 #define CALL_SCAN(DT, MT) e = launch_scan_dm<DT, MT>(a, plan, qsmem, s)

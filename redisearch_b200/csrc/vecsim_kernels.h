@@ -39,7 +39,10 @@ ScanPlan plan_scan_topk(const CorpusView &c, uint32_t nq, uint32_t k);
 // d_queries: nq device blobs, qpitch bytes apart, already in stored form (normalised etc.).
 cudaError_t launch_scan_topk(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq,
                              uint32_t k, const ScanPlan &plan, uint64_t *d_cand, cudaStream_t s,
-                             LaunchCounters *ctr);
+                             LaunchCounters *ctr, const uint32_t *d_q_ok = nullptr);
+// out[q] = ok[q] ? a[q] : b[q] for [nq][k] composite arrays
+cudaError_t launch_blend(const uint32_t *d_ok, const uint64_t *d_a, const uint64_t *d_b, uint32_t nq, uint32_t k, uint64_t *d_out,
+                         cudaStream_t s, LaunchCounters *ctr);
 // Reduce m_per_query candidate composites per query to the k smallest, ascending.
 // d_out: [nq][k] composites (kEmptySlot-padded when fewer than k real candidates exist).
 cudaError_t launch_final_select(const uint64_t *d_cand, uint32_t nq, uint32_t m_per_query, uint32_t k,

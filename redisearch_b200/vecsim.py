@@ -131,6 +131,8 @@ SIGNATURES = [
     ("VecSimB200_DeviceRows", _P, [_P, C.POINTER(_SZ), C.POINTER(_SZ)]),
     ("VecSimB200_GetStats", VecSimB200_Stats, [_P, C.c_bool]),
     ("VecSimB200_MergeShardTopK", C.c_int, [_P, _P, _SZ, _SZ, _SZ, _P, _P, _P]),
+    ("VecSimB200_SetCoarseMode", None, [C.c_int]),
+    ("VecSimB200_LastCoarseFlags", C.c_int, [_P, _P, _SZ]),
     ("VecSimB200_Version", C.c_char_p, []),
 ]
 # VecSim_SetMemoryFunctions takes a struct by value; declared in the header, bound lazily.

@@ -1,0 +1,91 @@
+"""GPU: the tensor-core coarse pass (csrc/coarse_tf32.cu) must return EXACTLY what the exact scan returns.
+
+tcgen05 TF32 GEMM + fused candidate lists -> exact rescoring (bit-exact arithmetic) -> per-query
+completeness proof -> on-device fallback.  Whatever the proof decides, ids and scores must equal the
+oracle's bit for bit; the flags tell how many queries were served by the tensor-core path.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_batch(vs, torch, index, qs_norm, k):
+    nq = qs_norm.shape[0]
+    qd = torch.from_numpy(np.ascontiguousarray(qs_norm)).cuda()
+    out_l = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    out_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = vs.lib().VecSimB200_TopKQueryBatchDevice(index.h, qd.data_ptr(), nq, k, out_l.data_ptr(), out_s.data_ptr(), sp)
+    assert rc == 0
+    torch.cuda.synchronize()
+    flags = np.zeros(nq, dtype=np.uint32)
+    frc = vs.lib().VecSimB200_LastCoarseFlags(index.h, flags.ctypes.data, nq)
+    return out_l.cpu().numpy(), out_s.cpu().numpy(), (flags if frc == 0 else None)
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [(70_000, 128, 40, 10), (66_000, 768, 64, 10), (131_072, 96, 17, 16), (80_000, 100, 33, 5)])
+def test_coarse_path_is_exact(n, dim, nq, k):
+    import torch
+
+    from redisearch_b200 import vecsim as vs
+
+    vs.lib().VecSimB200_SetCoarseMode(1)
+    rows = ol.synth_rows(ol.F32, 42, 0, n, dim)
+    g = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, vs.VecSimMetric_Cosine)
+    p = ol.PortIndex(ol.F32, dim, ol.COS, tier=ol.TIER_AVX512)
+    assert g.add_many(rows, label0=1) == n
+    p.add_many(rows, 1)
+    qs = ol.synth_rows(ol.F32, 43, 0, nq, dim)
+    qn = qs.copy()
+    for i in range(nq):
+        ol.port().orc_normalize(ol._p(qn[i]), dim, ol.F32)
+    labels, scores, flags = _device_batch(vs, torch, g, qn, k)
+    assert flags is not None, "the batch did not take the tensor-core path"
+    assert flags.sum() >= nq * 0.9, f"only {int(flags.sum())}/{nq} queries were verified by the coarse path"
+    for i in range(nq):
+        pi, ps = p.topk(qs[i], k)
+        assert labels[i].tolist() == pi.tolist(), (i, flags[i], labels[i], pi)
+        assert scores[i].tobytes() == ps.astype(np.float32).tobytes()
+    # the host-facing batch entry point goes through the same pipeline
+    hl, hs, rc = g.topk_batch(qs, k)
+    assert rc == 0 and (hl.astype(np.int64) == labels).all()
+    # and switching the coarse path off gives the same answer from the exact scan
+    vs.lib().VecSimB200_SetCoarseMode(0)
+    l2, s2, f2 = _device_batch(vs, torch, g, qn, k)
+    assert f2 is None and (l2 == labels).all() and s2.tobytes() == scores.tobytes()
+    vs.lib().VecSimB200_SetCoarseMode(-1)
+
+
+def test_coarse_path_falls_back_when_the_margin_is_too_small():
+    """Many near-duplicates of the query direction: the 24th-best approximate candidate of a row range is
+    within the TF32 error bound of the true k-th distance, so the proof must fail and the exact scan answers."""
+    import torch
+
+    from redisearch_b200 import vecsim as vs
+
+    vs.lib().VecSimB200_SetCoarseMode(1)
+    rng = np.random.default_rng(9)
+    n, dim, nq, k = 70_000, 64, 16, 10
+    base = rng.uniform(-1, 1, dim).astype(np.float32)
+    rows = (base[None, :] + 1e-4 * rng.standard_normal((n, dim))).astype(np.float32)  # all rows almost identical
+    g = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, vs.VecSimMetric_Cosine)
+    p = ol.PortIndex(ol.F32, dim, ol.COS, tier=ol.TIER_AVX512)
+    g.add_many(rows, label0=1)
+    p.add_many(rows, 1)
+    qs = (base[None, :] + 1e-4 * rng.standard_normal((nq, dim))).astype(np.float32)
+    qn = qs.copy()
+    for i in range(nq):
+        ol.port().orc_normalize(ol._p(qn[i]), dim, ol.F32)
+    labels, scores, flags = _device_batch(vs, torch, g, qn, k)
+    assert flags is not None and flags.sum() == 0  # nothing can be proven on this corpus
+    for i in range(nq):
+        pi, ps = p.topk(qs[i], k)
+        assert scores[i].tobytes() == ps.astype(np.float32).tobytes()
+        kth = ps[-1]
+        assert {l for l, s in zip(labels[i].tolist(), scores[i].tolist()) if s < kth} == {l for l, s in zip(pi.tolist(), ps.tolist()) if s < kth}
+    vs.lib().VecSimB200_SetCoarseMode(-1)
