@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace rsb200 {
 
@@ -73,6 +74,30 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
             smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// slice of a tile delivered to the same shared-memory offset of every CTA in `mask`; each destination's
+// mbarrier (same offset) receives the byte count
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
@@ -136,7 +161,8 @@ struct CoarseSmem {
 
 __global__ void __launch_bounds__(kCoarseThreads, 1)
 coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_q, uint32_t n_rows,
-                   uint32_t nq, uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint64_t *__restrict__ cand_out) {
+                   uint32_t nq, uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t csize,
+                   uint64_t *__restrict__ cand_out) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -159,7 +185,7 @@ coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], csize); // one arrival per CTA of the cluster (all read the multicast tile)
         }
         for (int a = 0; a < kAccStages; a++) {
             mbar_init(&tfull[a], 1);
@@ -179,6 +205,12 @@ coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // cluster mode: the csize CTAs that share blockIdx.x (one per query group) read the SAME row tiles;
+    // every CTA fetches 1/csize of each tile from HBM/L2 and multicasts it into all csize shared memories
+    const uint32_t crank = (csize > 1) ? cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+    const uint32_t slice_rows = kTileM / csize;
+    if (csize > 1) cluster_sync_all(); // remote CTAs must see initialised barriers before signalling them
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
@@ -191,7 +223,11 @@ coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], kStageBytes);
-                tma_load_2d(sA + (size_t)s * kStageBytes, &map_a, &full[s], (int)(kb * kBlockK), (int)(tile * kTileM));
+                if (csize > 1)
+                    tma_load_2d_mc(sA + (size_t)s * kStageBytes + (size_t)crank * slice_rows * 128, &map_a, &full[s],
+                                   (int)(kb * kBlockK), (int)(tile * kTileM + crank * slice_rows), cmask);
+                else
+                    tma_load_2d(sA + (size_t)s * kStageBytes, &map_a, &full[s], (int)(kb * kBlockK), (int)(tile * kTileM));
             }
         }
     } else if (warp == 1 && lane == 0) {
@@ -215,7 +251,10 @@ coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     // advance 32 bytes along K inside the swizzled 128-byte row: +2 in 16-byte units
                     umma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0);
                 }
-                umma_commit(&empty[s]); // frees the A stage when these MMAs retire
+                if (csize > 1)
+                    umma_commit_mc(&empty[s], cmask); // this CTA is done with stage s: tell every producer of the cluster
+                else
+                    umma_commit(&empty[s]); // frees the A stage when these MMAs retire
             }
             umma_commit(&tfull[a]); // accumulator of this tile complete
         }
@@ -320,6 +359,7 @@ coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all(); // no CTA may exit while peers can still write its smem / barriers
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 64);
@@ -410,6 +450,8 @@ static bool make_map(CUtensorMap *m, const void *base, uint64_t inner, uint64_t 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+void finalize_coarse_plan(CoarsePlan &p, uint32_t nq);
+
 bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k) {
     if (c.dtype != DT_F32 || c.metric != MT_IP) return false; // cosine on normalised rows (and raw IP, see eps)
     if (c.dim % 4 != 0 || c.dim < 32 || c.dim > 1024) return false;
@@ -427,22 +469,75 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq) {
     const uint32_t sms = (uint32_t)device_sm_count();
     p.grid_x = std::max(1u, std::min(p.tiles, sms / p.grid_y));
     p.keep = kCoarseKeep;
+    p.csize = 1;
     p.cand_elems = (size_t)nq * p.grid_x * p.keep;
     p.smem_bytes = 1024 + (size_t)p.num_kb * kQBlockBytes + (size_t)kStages * kStageBytes + (size_t)kTileN * kListCap * 8 +
                    (2 * kStages + 2 * kAccStages + 1) * 8 + kTileN * 8 + 64;
+    finalize_coarse_plan(p, nq);
     return p;
+}
+
+// Cluster size for the multicast variant: the query groups (grid.y) of one row range form a cluster.
+static uint32_t pick_cluster(uint32_t grid_y) {
+    static int mode = -1; // VECSIM_B200_CLUSTER=0 disables
+    if (mode < 0) {
+        const char *e = getenv("VECSIM_B200_CLUSTER");
+        mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (!mode) return 1;
+    if (grid_y >= 8 && grid_y % 8 == 0) return 8;
+    if (grid_y == 4) return 4;
+    if (grid_y == 2) return 2;
+    return 1;
+}
+
+static void fill_launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *at, const CoarsePlan &p, cudaStream_t s) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3(p.grid_x, p.grid_y, 1);
+    cfg.blockDim = dim3(kCoarseThreads);
+    cfg.dynamicSmemBytes = p.smem_bytes;
+    cfg.stream = s;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = p.csize;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+}
+
+void finalize_coarse_plan(CoarsePlan &p, uint32_t nq) {
+    p.csize = pick_cluster(p.grid_y);
+    if (p.csize > 1) {
+        cudaFuncSetAttribute(coarse_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute at[1];
+        CoarsePlan probe = p;
+        probe.grid_x = 1;
+        fill_launch_cfg(cfg, at, probe, nullptr);
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, coarse_tf32_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+            cudaGetLastError();
+            p.csize = 1;
+        } else {
+            // one wave of co-resident clusters: grid_x row ranges x (grid_y / csize) clusters each
+            const uint32_t per_range = p.grid_y / p.csize;
+            p.grid_x = std::max(1u, std::min(p.tiles, (uint32_t)nclusters / per_range));
+        }
+    }
+    p.cand_elems = (size_t)nq * p.grid_x * p.keep;
 }
 
 cudaError_t launch_coarse(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, const CoarsePlan &p,
                           uint64_t *d_cand, cudaStream_t s) {
     CUtensorMap ma, mq;
-    if (!make_map(&ma, c.rows, c.dim, c.n_rows, c.pitch, kBlockK, kTileM)) return cudaErrorInvalidValue;
+    if (!make_map(&ma, c.rows, c.dim, c.n_rows, c.pitch, kBlockK, kTileM / p.csize)) return cudaErrorInvalidValue;
     if (!make_map(&mq, d_queries, c.dim, nq, qpitch, kBlockK, kTileN)) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(coarse_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
     if (e != cudaSuccess) return e;
-    coarse_tf32_kernel<<<dim3(p.grid_x, p.grid_y), kCoarseThreads, p.smem_bytes, s>>>(ma, mq, c.n_rows, nq, p.num_kb, p.tiles,
-                                                                                      p.keep, d_cand);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[1];
+    fill_launch_cfg(cfg, at, p, s);
+    return cudaLaunchKernelEx(&cfg, coarse_tf32_kernel, ma, mq, c.n_rows, nq, p.num_kb, p.tiles, p.keep, p.csize, d_cand);
 }
 
 cudaError_t launch_rescore(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t per_query,

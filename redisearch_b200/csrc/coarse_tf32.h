@@ -13,6 +13,7 @@ constexpr float kCoarseEpsUnit = 2.5e-3f;
 
 struct CoarsePlan {
     uint32_t grid_x, grid_y, num_kb, tiles, keep;
+    uint32_t csize; // thread-block cluster size along y (1 = no multicast)
     size_t cand_elems; // uint64 per (query, list, keep)
     size_t smem_bytes;
 };

@@ -28,7 +28,8 @@ def _device_batch(vs, torch, index, qs_norm, k):
     return out_l.cpu().numpy(), out_s.cpu().numpy(), (flags if frc == 0 else None)
 
 
-@pytest.mark.parametrize("n,dim,nq,k", [(70_000, 128, 40, 10), (66_000, 768, 64, 10), (131_072, 96, 17, 16), (80_000, 100, 33, 5)])
+@pytest.mark.parametrize("n,dim,nq,k", [(70_000, 128, 40, 10), (66_000, 768, 64, 10), (131_072, 96, 17, 16), (80_000, 100, 33, 5),
+                                        (70_000, 128, 128, 10), (300_000, 64, 256, 10), (66_000, 256, 512, 8)])
 def test_coarse_path_is_exact(n, dim, nq, k):
     import torch
 
