@@ -479,15 +479,14 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq) {
 
 // Cluster size for the multicast variant: the query groups (grid.y) of one row range form a cluster.
 static uint32_t pick_cluster(uint32_t grid_y) {
-    static int mode = -1; // VECSIM_B200_CLUSTER=0 disables
-    if (mode < 0) {
+    static int cap = -1; // VECSIM_B200_CLUSTER = largest cluster size to use (0/1 = no clusters); default 8
+    if (cap < 0) {
         const char *e = getenv("VECSIM_B200_CLUSTER");
-        mode = (e && e[0] == '0') ? 0 : 1;
+        cap = e ? atoi(e) : 8;
+        if (cap < 1) cap = 1;
     }
-    if (!mode) return 1;
-    if (grid_y >= 8 && grid_y % 8 == 0) return 8;
-    if (grid_y == 4) return 4;
-    if (grid_y == 2) return 2;
+    for (uint32_t cs = 8; cs > 1; cs >>= 1)
+        if ((int)cs <= cap && grid_y % cs == 0) return cs;
     return 1;
 }
 
