@@ -99,6 +99,10 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
 }
+// pull a box into L2 ahead of time (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -161,7 +165,7 @@ struct CoarseSmem {
 
 __global__ void __launch_bounds__(kCoarseThreads, 1)
 coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_q, uint32_t n_rows,
-                   uint32_t nq, uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t csize,
+                   uint32_t nq, uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t csize, uint32_t pf_tiles,
                    uint64_t *__restrict__ cand_out) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
@@ -219,6 +223,14 @@ coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         uint32_t it = 0;
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t tile = blockIdx.x + i * gridDim.x;
+            // HBM -> L2 prefetch kPrefetchTiles tiles ahead, so the ring below refills at L2 latency;
+            // the query-group CTAs of a row range share the tiles, one of them (rotating) prefetches
+            if (pf_tiles && i + pf_tiles < my_tiles && (i % gridDim.y) == blockIdx.y) {
+                const uint32_t ptile = blockIdx.x + (i + pf_tiles) * gridDim.x;
+                for (uint32_t kb = 0; kb < num_kb; kb++)
+                    for (uint32_t r = 0; r < csize; r++)
+                        tma_prefetch_2d(&map_a, (int)(kb * kBlockK), (int)(ptile * kTileM + r * slice_rows));
+            }
             for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
@@ -536,7 +548,13 @@ cudaError_t launch_coarse(const CorpusView &c, const void *d_queries, size_t qpi
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
     fill_launch_cfg(cfg, at, p, s);
-    return cudaLaunchKernelEx(&cfg, coarse_tf32_kernel, ma, mq, c.n_rows, nq, p.num_kb, p.tiles, p.keep, p.csize, d_cand);
+    static int pf = -1; // VECSIM_B200_PREFETCH = tiles of L2 prefetch distance (default 4, 0 = off)
+    if (pf < 0) {
+        const char *e = getenv("VECSIM_B200_PREFETCH");
+        pf = e ? atoi(e) : 4;
+    }
+    return cudaLaunchKernelEx(&cfg, coarse_tf32_kernel, ma, mq, c.n_rows, nq, p.num_kb, p.tiles, p.keep, p.csize, (uint32_t)pf,
+                              d_cand);
 }
 
 cudaError_t launch_rescore(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t per_query,
