@@ -418,10 +418,12 @@ VecSimB200_Stats VecSimB200_GetStats(VecSimIndex *index, bool reset);
  * (score,label) pairs, out = [nq][k]. */
 int VecSimB200_MergeShardTopK(const float *d_scores, const int64_t *d_labels, size_t G, size_t nq,
                               size_t k, float *d_out_scores, int64_t *d_out_labels, void *stream);
-/* Batched fp32 cosine queries (nq >= 16, k <= 16, dim % 4 == 0, >= 65536 rows) take a tcgen05 TF32 coarse
- * pass + exact rescoring + a per-query completeness proof, with the exact scan as on-device fallback
- * (csrc/coarse_tf32.cu); results are identical either way.  mode: 0 = exact scans only, 1 = enabled,
- * -1 = environment default (VECSIM_B200_COARSE, on unless "0"). */
+/* Batched fp32 cosine queries (nq >= 16, k <= 16, dim % 8 == 0, >= 65536 rows) take a tcgen05 coarse
+ * pass + exact rescoring from the fp32 rows + a per-query completeness proof, with the exact scan as
+ * on-device fallback (csrc/coarse_tc.cu); results are identical either way.  mode: 0 = exact scans only,
+ * 1 = coarse pass over an fp16 shadow copy of the rows (+50% HBM, built lazily by the first eligible
+ * batch), 2 = TF32 coarse pass over the fp32 rows (no extra memory, ~4x slower than 1),
+ * -1 = environment default (VECSIM_B200_COARSE, 1 unless set). */
 void VecSimB200_SetCoarseMode(int mode);
 /* Debug: after a VecSimB200_TopKQueryBatchDevice call, per-query flags (1 = answered by the tensor-core
  * path, 0 = fell back to the exact scan).  Returns -1 if the last batch did not take the coarse path. */

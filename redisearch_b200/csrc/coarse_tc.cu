@@ -1,28 +1,34 @@
-// Batched fp32 cosine KNN, stage 1: a tcgen05 `kind::tf32` coarse pass over the HBM-resident corpus
-// that keeps, per CTA and per query, the 16 best rows by APPROXIMATE distance.  Stage 2
-// (rescore_kernel) recomputes those candidates with the bit-exact arithmetic of distance_core.cuh and
-// stage 3 (verify) proves per query that no discarded row can belong to the exact top-k — otherwise
-// the query falls back to the exact scan.  Result: the exact answer of BruteForceIndex::topKQuery
+// Batched fp32 cosine KNN, stage 1: a tcgen05 coarse pass over the HBM-resident corpus that keeps, per
+// CTA and per query, the kCoarseKeep best rows by APPROXIMATE distance.  Stage 2 (rescore_kernel)
+// recomputes those candidates from the fp32 rows with the bit-exact arithmetic of distance_core.cuh and
+// stage 3 (verify) proves per query that no discarded row can belong to the exact top-k — otherwise the
+// query falls back to the exact scan.  Result: the exact answer of BruteForceIndex::topKQuery
 // (VS/algorithms/brute_force/brute_force.h:243-291) at tensor-core speed.
 //
 // Why: 256 queries x 10M x 768 fp32 is 3.93 TFLOP per corpus pass — FMA-bound on CUDA cores
-// (DESIGN.md §4); TF32 tensor cores bring the pass back to the HBM/L2 roofline.  TF32 truncates each
-// operand to 10 mantissa bits, so |approx - exact| <= ~2^-9 for unit vectors; that is far too coarse for
-// the reference's 1e-5 parity bar, hence coarse-then-exact instead of trusting the GEMM.
+// (DESIGN.md §4).  On the tensor cores the pass is bound by how many operand bytes each SM has to pull
+// through its L2->shared-memory port (measured ~42 B/clk/SM): every row tile is ingested once per
+// query group, so the two levers are queries per CTA (N) and bytes per element.  Two operand kinds:
+//   CoarseF16   fp16 shadow copy of the corpus (kind::f16, fp32 accumulate), N = 64 queries per CTA:
+//               1/4 of the ingest of the TF32 variant and a TIGHTER error bound (RN to 11 significant
+//               bits vs. TF32's truncation to 11) — the default;
+//   CoarseTF32  the fp32 rows themselves (kind::tf32), N = 32: no shadow memory, 4x the ingest.
+// Neither is precise enough for the reference's 1e-5 parity bar, hence coarse-then-exact.
 //
 // Kernel shape (one CTA per SM, persistent over 128-row tiles of its row range):
-//   warp 0   TMA producer: A tiles [128 rows x 32 floats] (128B swizzle) into a 6-stage ring
-//   warp 1   MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::tf32, M=128 N=32 K=8,
-//            A and B from shared memory, accumulator in TMEM (2 stages x 32 columns)
+//   warp 0   TMA producer: A tiles [128 rows x 128 bytes] (128B swizzle) into an n-stage ring
+//   warp 1   MMA issuer (one elected lane): tcgen05.mma.cta_group::1, M=128, N=32|64, K=32 bytes,
+//            A and B from shared memory, accumulator in TMEM (2 stages x N columns)
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32 (one row x 32 queries per thread), threshold test,
-//            candidate lists in shared memory with lazy compaction
-// The CTA's 32 queries stay resident in shared memory (24 swizzled K-blocks, 96 KB) for the whole pass.
-#include "coarse_tf32.h"
+//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32 (one row x 32 queries per thread and load), threshold
+//            test, candidate lists in shared memory with lazy compaction
+// The CTA's queries stay resident in shared memory (swizzled K-blocks, 96 KB at dim 768).
+#include "coarse_tc.h"
 #include "distance_core.cuh"
 #include "topk_common.cuh"
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -30,15 +36,24 @@
 namespace rsb200 {
 
 constexpr int kTileM = 128;       // rows per tile (UMMA_M)
-constexpr int kTileN = 32;        // queries per CTA (UMMA_N)
-constexpr int kBlockK = 32;       // floats per K block = 128 bytes = one swizzle row
-constexpr int kUmmaK = 8;         // tf32: 32 bytes per instruction
-constexpr int kStages = 6;
+constexpr int kMaxStages = 8;     // ring depth is chosen at plan time from the shared memory left over
 constexpr int kAccStages = 2;
 constexpr int kCoarseThreads = 256;
 constexpr int kListCap = 64;      // per-query candidate buffer in shared memory
-constexpr uint32_t kStageBytes = kTileM * kBlockK * 4; // 16 KB
-constexpr uint32_t kQBlockBytes = kTileN * kBlockK * 4; // 4 KB
+constexpr uint32_t kStageBytes = kTileM * 128; // one K block of a row tile: 128 rows x 128 bytes = 16 KB
+
+struct CfgTF32 {
+    static constexpr int kTileN = 32;   // queries per CTA (UMMA_N)
+    static constexpr int kBlockK = 32;  // elements per K block = 128 bytes = one swizzle row
+    static constexpr int kElem = 4;
+    static constexpr uint32_t kFmt = 2; // UMMA a/b format TF32
+};
+struct CfgF16 {
+    static constexpr int kTileN = 64;
+    static constexpr int kBlockK = 64;
+    static constexpr int kElem = 2;
+    static constexpr uint32_t kFmt = 0; // UMMA a/b format F16
+};
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -75,34 +90,6 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-// slice of a tile delivered to the same shared-memory offset of every CTA in `mask`; each destination's
-// mbarrier (same offset) receives the byte count
-__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(bar)),
-                 "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-}
-// pull a box into L2 ahead of time (no shared-memory destination, no barrier)
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -112,16 +99,28 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+// D[tmem] (+)= A[smem] * B[smem]^T, fp32 accumulate; 32 bytes of K per instruction
+template <class Cfg>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (Cfg::kElem == 4) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -152,32 +151,31 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;           // SWIZZLE_128B
     return d;
 }
-// cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format TF32 (2) [7,10)/[10,13), K-major both,
+// cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format [7,10)/[10,13) (F16 0, TF32 2), K-major both,
 // N>>3 [17,23), M>>4 [24,29)
-__device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__device__ __forceinline__ constexpr uint32_t make_idesc(uint32_t fmt, int m, int n) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
-struct CoarseSmem {
-    // offsets computed at runtime from the 1024-aligned base
-};
-
+template <class Cfg>
 __global__ void __launch_bounds__(kCoarseThreads, 1)
-coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_q, uint32_t n_rows,
-                   uint32_t nq, uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t csize, uint32_t pf_tiles,
-                   uint64_t *__restrict__ cand_out) {
+coarse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_q, uint32_t n_rows, uint32_t nq,
+              uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t nstages, uint64_t *__restrict__ cand_out) {
+    constexpr int kTileN = Cfg::kTileN;
+    constexpr int kHalves = kTileN / 32;
+    constexpr uint32_t kQBlockBytes = kTileN * 128;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *sQ = smem;                                   // num_kb x [32 x 128B]
-    uint8_t *sA = sQ + (size_t)num_kb * kQBlockBytes;     // kStages x [128 x 128B]
-    uint64_t *lists = reinterpret_cast<uint64_t *>(sA + (size_t)kStages * kStageBytes); // [32][kListCap]
+    uint8_t *sQ = smem;                                   // num_kb x [kTileN x 128B]
+    uint8_t *sA = sQ + (size_t)num_kb * kQBlockBytes;     // nstages x [128 x 128B]
+    uint64_t *lists = reinterpret_cast<uint64_t *>(sA + (size_t)nstages * kStageBytes); // [kTileN][kListCap]
     uint64_t *bars = lists + kTileN * kListCap;
-    uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = tfull + kAccStages;
+    uint64_t *full = bars, *empty = bars + kMaxStages, *tfull = bars + 2 * kMaxStages, *tempty = tfull + kAccStages;
     uint64_t *qbar = tempty + kAccStages;
-    uint32_t *counts = reinterpret_cast<uint32_t *>(qbar + 1); // [32]
-    uint32_t *thresh = counts + kTileN;                        // [32] orderable keys
+    uint32_t *counts = reinterpret_cast<uint32_t *>(qbar + 1); // [kTileN]
+    uint32_t *thresh = counts + kTileN;                        // [kTileN] orderable keys
     uint32_t *tmem_slot = thresh + kTileN;
     uint32_t *pending_flag = tmem_slot + 1;
 
@@ -187,9 +185,9 @@ coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t my_tiles = (tiles_total > blockIdx.x) ? (tiles_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (uint32_t s = 0; s < nstages; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], csize); // one arrival per CTA of the cluster (all read the multicast tile)
+            mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < kAccStages; a++) {
             mbar_init(&tfull[a], 1);
@@ -204,69 +202,49 @@ coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         counts[threadIdx.x] = 0;
         thresh[threadIdx.x] = 0xFFFFFFFFu;
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 64);
+    if (warp == 2) tmem_alloc(tmem_slot, kAccStages * kTileN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // cluster mode: the csize CTAs that share blockIdx.x (one per query group) read the SAME row tiles;
-    // every CTA fetches 1/csize of each tile from HBM/L2 and multicasts it into all csize shared memories
-    const uint32_t crank = (csize > 1) ? cluster_ctarank() : 0;
-    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
-    const uint32_t slice_rows = kTileM / csize;
-    if (csize > 1) cluster_sync_all(); // remote CTAs must see initialised barriers before signalling them
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         mbar_expect_tx(qbar, num_kb * kQBlockBytes);
-        for (uint32_t kb = 0; kb < num_kb; kb++) tma_load_2d(sQ + (size_t)kb * kQBlockBytes, &map_q, qbar, (int)(kb * kBlockK), (int)q_base);
-        uint32_t it = 0;
+        for (uint32_t kb = 0; kb < num_kb; kb++)
+            tma_load_2d(sQ + (size_t)kb * kQBlockBytes, &map_q, qbar, (int)(kb * Cfg::kBlockK), (int)q_base);
+        uint32_t s = 0, ph = 0;
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t tile = blockIdx.x + i * gridDim.x;
-            // HBM -> L2 prefetch kPrefetchTiles tiles ahead, so the ring below refills at L2 latency;
-            // the query-group CTAs of a row range share the tiles, one of them (rotating) prefetches
-            if (pf_tiles && i + pf_tiles < my_tiles && (i % gridDim.y) == blockIdx.y) {
-                const uint32_t ptile = blockIdx.x + (i + pf_tiles) * gridDim.x;
-                for (uint32_t kb = 0; kb < num_kb; kb++)
-                    for (uint32_t r = 0; r < csize; r++)
-                        tma_prefetch_2d(&map_a, (int)(kb * kBlockK), (int)(ptile * kTileM + r * slice_rows));
-            }
-            for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
-                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            for (uint32_t kb = 0; kb < num_kb; kb++) {
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], kStageBytes);
-                if (csize > 1)
-                    tma_load_2d_mc(sA + (size_t)s * kStageBytes + (size_t)crank * slice_rows * 128, &map_a, &full[s],
-                                   (int)(kb * kBlockK), (int)(tile * kTileM + crank * slice_rows), cmask);
-                else
-                    tma_load_2d(sA + (size_t)s * kStageBytes, &map_a, &full[s], (int)(kb * kBlockK), (int)(tile * kTileM));
+                tma_load_2d(sA + (size_t)s * kStageBytes, &map_a, &full[s], (int)(kb * Cfg::kBlockK), (int)(tile * kTileM));
+                if (++s == nstages) s = 0, ph ^= 1;
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = make_idesc_tf32(kTileM, kTileN);
+        constexpr uint32_t idesc = make_idesc(Cfg::kFmt, kTileM, kTileN);
         mbar_wait(qbar, 0);
-        uint32_t it = 0;
+        uint32_t s = 0, ph = 0;
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t a = i % kAccStages, aph = (i / kAccStages) & 1;
             mbar_wait(&tempty[a], aph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + a * kTileN;
-            for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
-                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            for (uint32_t kb = 0; kb < num_kb; kb++) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)s * kStageBytes));
                 const uint64_t bdesc = make_smem_desc(smem_u32(sQ + (size_t)kb * kQBlockBytes));
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; k++) {
+                for (int k = 0; k < 4; k++) {
                     // advance 32 bytes along K inside the swizzled 128-byte row: +2 in 16-byte units
-                    umma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0);
+                    umma_ss<Cfg>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0);
                 }
-                if (csize > 1)
-                    umma_commit_mc(&empty[s], cmask); // this CTA is done with stage s: tell every producer of the cluster
-                else
-                    umma_commit(&empty[s]); // frees the A stage when these MMAs retire
+                umma_commit(&empty[s]); // frees the A stage when these MMAs retire
+                if (++s == nstages) s = 0, ph ^= 1;
             }
             umma_commit(&tfull[a]); // accumulator of this tile complete
         }
@@ -279,40 +257,51 @@ coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const uint32_t a = i % kAccStages, aph = (i / kAccStages) & 1;
             mbar_wait(&tfull[a], aph);
             tc_fence_after();
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + a * kTileN, v);
+            uint32_t v[kHalves][32];
+#pragma unroll
+            for (int h = 0; h < kHalves; h++) tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + a * kTileN + h * 32, v[h]);
             tc_fence_before();
             mbar_arrive(&tempty[a]); // accumulator stage may be overwritten
             const uint32_t row = tile * kTileM + ew * 32 + lane;
-            uint32_t pend = 0; // bit j: candidate for query j still to be stored
-            if (row < n_rows) {
+            uint32_t pend[kHalves]; // bit j: candidate for query h*32+j still to be stored
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const float d = 1.0f - __uint_as_float(v[j]);
-                    v[j] = orderable_key(d);
-                    if (v[j] < thresh[j]) pend |= 1u << j;
+            for (int h = 0; h < kHalves; h++) {
+                pend[h] = 0;
+                if (row < n_rows) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float d = 1.0f - __uint_as_float(v[h][j]);
+                        v[h][j] = orderable_key(d);
+                        if (v[h][j] < thresh[h * 32 + j]) pend[h] |= 1u << j;
+                    }
                 }
             }
             // insert with retry: lists are compacted (keep best `keep`) whenever they run full
             for (;;) {
-                uint32_t still = 0;
-                uint32_t p = pend;
-                while (p) {
-                    const int j = __ffs(p) - 1;
-                    p &= p - 1;
-                    uint32_t key = 0;
+                uint32_t any_left = 0;
 #pragma unroll
-                    for (int jj = 0; jj < 32; jj++)
-                        if (jj == j) key = v[jj];
-                    if (key >= thresh[j]) continue; // threshold tightened meanwhile
-                    const uint32_t slot = atomicAdd(&counts[j], 1u);
-                    if (slot < (uint32_t)kListCap)
-                        lists[j * kListCap + slot] = ((uint64_t)key << 32) | row;
-                    else
-                        still |= 1u << j;
+                for (int h = 0; h < kHalves; h++) {
+                    uint32_t still = 0;
+                    uint32_t p = pend[h];
+                    while (p) {
+                        const int jj = __ffs(p) - 1;
+                        p &= p - 1;
+                        uint32_t key = 0;
+#pragma unroll
+                        for (int x = 0; x < 32; x++)
+                            if (x == jj) key = v[h][x];
+                        const int j = h * 32 + jj;
+                        if (key >= thresh[j]) continue; // threshold tightened meanwhile
+                        const uint32_t slot = atomicAdd(&counts[j], 1u);
+                        if (slot < (uint32_t)kListCap)
+                            lists[j * kListCap + slot] = ((uint64_t)key << 32) | row;
+                        else
+                            still |= 1u << jj;
+                    }
+                    pend[h] = still;
+                    any_left |= still;
                 }
-                pend = still;
-                if (pend) *pending_flag = 1;
+                if (any_left) *pending_flag = 1;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 // compaction: warp ew handles queries j = ew, ew+4, ...
                 const uint32_t any_pending = *pending_flag;
@@ -371,10 +360,29 @@ coarse_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (csize > 1) cluster_sync_all(); // no CTA may exit while peers can still write its smem / barriers
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 64);
+        tmem_dealloc(tmem_base, kAccStages * kTileN);
+    }
+}
+
+// fp32 rows -> fp16 (round to nearest even) shadow rows; 8 elements per thread, dim % 8 == 0
+__global__ void __launch_bounds__(256) to_f16_kernel(const uint8_t *__restrict__ src, size_t spitch, uint32_t dim, uint32_t first,
+                                                     uint32_t n, uint8_t *__restrict__ dst, size_t dpitch) {
+    const uint32_t per_row = dim / 8;
+    const size_t total = (size_t)n * per_row;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = first + (uint32_t)(i / per_row), c = (uint32_t)(i % per_row);
+        const float4 *p = reinterpret_cast<const float4 *>(src + (size_t)r * spitch) + 2 * c;
+        const float4 x = p[0], y = p[1];
+        __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+        __half2 h2 = __floats2half2_rn(y.x, y.y), h3 = __floats2half2_rn(y.z, y.w);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t *>(&h0);
+        o.y = *reinterpret_cast<uint32_t *>(&h1);
+        o.z = *reinterpret_cast<uint32_t *>(&h2);
+        o.w = *reinterpret_cast<uint32_t *>(&h3);
+        reinterpret_cast<uint4 *>(dst + (size_t)r * dpitch)[c] = o;
     }
 }
 
@@ -449,112 +457,82 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static bool make_map(CUtensorMap *m, const void *base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner,
-                     uint32_t box_outer) {
+static bool make_map(CUtensorMap *m, CUtensorMapDataType dt, const void *base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                     uint32_t box_inner, uint32_t box_outer) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {pitch_bytes};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return fn(m, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-void finalize_coarse_plan(CoarsePlan &p, uint32_t nq);
+static constexpr size_t kSmemLimit = 232448; // 227 KB opt-in maximum per CTA on sm_100
 
-bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k) {
-    if (c.dtype != DT_F32 || c.metric != MT_IP) return false; // cosine on normalised rows (and raw IP, see eps)
-    if (c.dim % 4 != 0 || c.dim < 32 || c.dim > 1024) return false;
+static size_t fixed_smem(CoarseKind kind, uint32_t num_kb) {
+    const uint32_t tn = kind == CoarseF16 ? CfgF16::kTileN : CfgTF32::kTileN;
+    return 1024 + (size_t)num_kb * tn * 128 + (size_t)tn * kListCap * 8 + (2 * kMaxStages + 2 * kAccStages + 1) * 8 + tn * 8 + 64;
+}
+
+bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind kind) {
+    if (c.dtype != DT_F32 || c.metric != MT_IP) return false; // cosine on normalised rows only (eps assumes unit vectors)
+    if (c.dim % 8 != 0 || c.dim < 32 || c.dim > 1024) return false;
     if (c.pitch % 16 != 0) return false;
     if (k > kCoarseMaxK || nq < 16) return false;
     if (c.n_rows < 65536) return false; // tiny corpora: the exact kernel is already fast
+    const uint32_t bk = kind == CoarseF16 ? CfgF16::kBlockK : CfgTF32::kBlockK;
+    if (fixed_smem(kind, (c.dim + bk - 1) / bk) + 3 * kStageBytes > kSmemLimit) return false;
     return encode_fn() != nullptr;
 }
 
-CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq) {
+CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind) {
     CoarsePlan p{};
-    p.num_kb = (c.dim + kBlockK - 1) / kBlockK;
+    p.kind = kind;
+    const uint32_t bk = kind == CoarseF16 ? CfgF16::kBlockK : CfgTF32::kBlockK;
+    const uint32_t tn = kind == CoarseF16 ? CfgF16::kTileN : CfgTF32::kTileN;
+    p.num_kb = (c.dim + bk - 1) / bk;
     p.tiles = (c.n_rows + kTileM - 1) / kTileM;
-    p.grid_y = (nq + kTileN - 1) / kTileN;
+    p.grid_y = (nq + tn - 1) / tn;
     const uint32_t sms = (uint32_t)device_sm_count();
     p.grid_x = std::max(1u, std::min(p.tiles, sms / p.grid_y));
     p.keep = kCoarseKeep;
-    p.csize = 1;
+    const size_t fixed = fixed_smem(kind, p.num_kb);
+    p.stages = (uint32_t)std::min<size_t>(kMaxStages, (kSmemLimit - fixed) / kStageBytes);
     p.cand_elems = (size_t)nq * p.grid_x * p.keep;
-    p.smem_bytes = 1024 + (size_t)p.num_kb * kQBlockBytes + (size_t)kStages * kStageBytes + (size_t)kTileN * kListCap * 8 +
-                   (2 * kStages + 2 * kAccStages + 1) * 8 + kTileN * 8 + 64;
-    finalize_coarse_plan(p, nq);
+    p.smem_bytes = fixed + (size_t)p.stages * kStageBytes;
     return p;
 }
 
-// Cluster size for the multicast variant: the query groups (grid.y) of one row range form a cluster.
-static uint32_t pick_cluster(uint32_t grid_y) {
-    static int cap = -1; // VECSIM_B200_CLUSTER = largest cluster size to use (0/1 = no clusters); default 8
-    if (cap < 0) {
-        const char *e = getenv("VECSIM_B200_CLUSTER");
-        cap = e ? atoi(e) : 8;
-        if (cap < 1) cap = 1;
-    }
-    for (uint32_t cs = 8; cs > 1; cs >>= 1)
-        if ((int)cs <= cap && grid_y % cs == 0) return cs;
-    return 1;
-}
-
-static void fill_launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *at, const CoarsePlan &p, cudaStream_t s) {
-    cfg = cudaLaunchConfig_t{};
-    cfg.gridDim = dim3(p.grid_x, p.grid_y, 1);
-    cfg.blockDim = dim3(kCoarseThreads);
-    cfg.dynamicSmemBytes = p.smem_bytes;
-    cfg.stream = s;
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 1;
-    at[0].val.clusterDim.y = p.csize;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-}
-
-void finalize_coarse_plan(CoarsePlan &p, uint32_t nq) {
-    p.csize = pick_cluster(p.grid_y);
-    if (p.csize > 1) {
-        cudaFuncSetAttribute(coarse_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
-        cudaLaunchConfig_t cfg;
-        cudaLaunchAttribute at[1];
-        CoarsePlan probe = p;
-        probe.grid_x = 1;
-        fill_launch_cfg(cfg, at, probe, nullptr);
-        int nclusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&nclusters, coarse_tf32_kernel, &cfg) != cudaSuccess || nclusters < 1) {
-            cudaGetLastError();
-            p.csize = 1;
-        } else {
-            // one wave of co-resident clusters: grid_x row ranges x (grid_y / csize) clusters each
-            const uint32_t per_range = p.grid_y / p.csize;
-            p.grid_x = std::max(1u, std::min(p.tiles, (uint32_t)nclusters / per_range));
-        }
-    }
-    p.cand_elems = (size_t)nq * p.grid_x * p.keep;
-}
-
-cudaError_t launch_coarse(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, const CoarsePlan &p,
-                          uint64_t *d_cand, cudaStream_t s) {
+template <class Cfg>
+static cudaError_t launch_coarse_t(const void *rows, size_t pitch, uint32_t n_rows, uint32_t dim, const void *d_queries, size_t qpitch,
+                                   uint32_t nq, const CoarsePlan &p, uint64_t *d_cand, cudaStream_t s) {
+    const CUtensorMapDataType dt = Cfg::kElem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap ma, mq;
-    if (!make_map(&ma, c.rows, c.dim, c.n_rows, c.pitch, kBlockK, kTileM / p.csize)) return cudaErrorInvalidValue;
-    if (!make_map(&mq, d_queries, c.dim, nq, qpitch, kBlockK, kTileN)) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(coarse_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+    if (!make_map(&ma, dt, rows, dim, n_rows, pitch, Cfg::kBlockK, kTileM)) return cudaErrorInvalidValue;
+    if (!make_map(&mq, dt, d_queries, dim, nq, qpitch, Cfg::kBlockK, Cfg::kTileN)) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(coarse_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
     if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute at[1];
-    fill_launch_cfg(cfg, at, p, s);
-    static int pf = -1; // VECSIM_B200_PREFETCH = tiles of L2 prefetch distance (default 4, 0 = off)
-    if (pf < 0) {
-        const char *e = getenv("VECSIM_B200_PREFETCH");
-        pf = e ? atoi(e) : 4;
-    }
-    return cudaLaunchKernelEx(&cfg, coarse_tf32_kernel, ma, mq, c.n_rows, nq, p.num_kb, p.tiles, p.keep, p.csize, (uint32_t)pf,
-                              d_cand);
+    coarse_kernel<Cfg><<<dim3(p.grid_x, p.grid_y), kCoarseThreads, p.smem_bytes, s>>>(ma, mq, n_rows, nq, p.num_kb, p.tiles, p.keep,
+                                                                                     p.stages, d_cand);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
+                          cudaStream_t s) {
+    if (p.kind == CoarseF16)
+        return launch_coarse_t<CfgF16>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);
+    return launch_coarse_t<CfgTF32>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);
+}
+
+cudaError_t launch_to_f16(const void *src, size_t spitch, uint32_t dim, uint32_t first, uint32_t n, void *dst, size_t dpitch,
+                          cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const size_t total = (size_t)n * (dim / 8);
+    const uint32_t grid = (uint32_t)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)device_sm_count() * 16));
+    to_f16_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(src), spitch, dim, first, n, static_cast<uint8_t *>(dst), dpitch);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_rescore(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t per_query,

@@ -1,0 +1,49 @@
+// Launchers of the tensor-core coarse pass (coarse_tc.cu): tcgen05 GEMM (fp16 shadow rows or TF32 on the
+// fp32 rows) with fused candidate selection, exact rescoring, and the completeness proof.  See the header
+// comment of coarse_tc.cu.
+#pragma once
+#include "vecsim_kernels.h"
+
+namespace rsb200 {
+
+constexpr uint32_t kCoarseKeep = 24;   // candidates kept per (CTA row range, query)
+constexpr uint32_t kCoarseMaxK = 16;   // largest k served by the coarse path
+// |approx - exact| bounds for unit vectors (Cauchy-Schwarz over the dot product: sum |a_i b_i| <= 1):
+//  TF32: each operand truncated to 11 significant bits -> 2 * 2^-10 relative per product, + accumulation slack;
+//  F16 : each operand rounded to nearest, 11 significant bits -> 2 * 2^-11 = 9.8e-4 per product; elements below
+//        the fp16 normal range (6.1e-5) add at most 2^-25 * sum|b_i| <= 2^-25 * sqrt(dim) <= 1e-6; fp32
+//        accumulation of <= 1024 terms adds < 1.3e-4.
+constexpr float kCoarseEpsTF32 = 2.5e-3f;
+constexpr float kCoarseEpsF16 = 1.2e-3f;
+
+enum CoarseKind : int { CoarseTF32 = 0, CoarseF16 = 1 };
+inline float coarse_eps(CoarseKind k) { return k == CoarseF16 ? kCoarseEpsF16 : kCoarseEpsTF32; }
+
+struct CoarsePlan {
+    CoarseKind kind;
+    uint32_t grid_x, grid_y, num_kb, tiles, keep;
+    uint32_t stages; // depth of the row-tile ring in shared memory
+    size_t cand_elems; // uint64 per (query, list, keep)
+    size_t smem_bytes;
+};
+
+// operands of the coarse GEMM in the element type of `kind`: corpus rows and the query batch
+struct CoarseOperands {
+    const void *rows;
+    size_t pitch;
+    const void *queries;
+    size_t qpitch;
+};
+bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind kind);
+CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind);
+cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
+                          cudaStream_t s);
+// fp32 rows [first, first+n) -> fp16 rows of the shadow copy (dim % 8 == 0)
+cudaError_t launch_to_f16(const void *src, size_t spitch, uint32_t dim, uint32_t first, uint32_t n, void *dst, size_t dpitch,
+                          cudaStream_t s);
+cudaError_t launch_rescore(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t per_query,
+                           const uint64_t *d_cand, uint64_t *d_exact, cudaStream_t s);
+cudaError_t launch_verify(const uint64_t *d_cand, const uint64_t *d_topk, uint32_t nq, uint32_t lists_per_query, uint32_t keep,
+                          uint32_t k, float eps, uint32_t *d_ok, cudaStream_t s);
+
+} // namespace rsb200

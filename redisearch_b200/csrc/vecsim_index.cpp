@@ -2,7 +2,7 @@
 #include "vecsim_index.h"
 #include "host_numeric.h"
 #include "topk_common.cuh"
-#include "coarse_tf32.h"
+#include "coarse_tc.h"
 
 #include <algorithm>
 #include <cmath>
@@ -205,6 +205,7 @@ FlatIndex::~FlatIndex() {
         cudaStreamDestroy(copy_stream_);
     }
     cudaFree(d_rows_);
+    cudaFree(d_shadow_);
     cudaFree(d_id_to_label_);
     cudaFreeHost(h_stage_);
 }
@@ -333,6 +334,7 @@ int FlatIndex::add(const void *blob, size_t label) {
             } else {
                 if (cudaMemcpy(d_rows_ + (size_t)id * pitch_, tmp.data(), pitch_, cudaMemcpyHostToDevice) != cudaSuccess)
                     return 0;
+                if (d_shadow_) shadow_dirty_.push_back(id);
             }
             return 0;
         }
@@ -411,6 +413,7 @@ int FlatIndex::remove(size_t label) {
             const size_t last_label = id_to_label_[last];
             cudaMemcpyAsync(d_rows_ + (size_t)id * pitch_, d_rows_ + (size_t)last * pitch_, pitch_,
                             cudaMemcpyDeviceToDevice, copy_stream_);
+            if (d_shadow_) shadow_dirty_.push_back(id);
             id_to_label_[id] = last_label;
             if (multi_) {
                 auto &v = label_to_ids_[last_label];
@@ -621,16 +624,62 @@ VecSimQueryReply *FlatIndex::topk(const void *q, size_t k, VecSimQueryParams *qp
     return rep;
 }
 
-std::atomic<int> g_coarse_mode{-1}; // -1 = from env VECSIM_B200_COARSE (default on), 0 = off, 1 = on
+// -1 = from env VECSIM_B200_COARSE (default 1), 0 = exact scans only, 1 = fp16 shadow rows, 2 = TF32 on the fp32 rows
+std::atomic<int> g_coarse_mode{-1};
 
-static bool coarse_enabled() {
+static int coarse_mode() {
     int m = g_coarse_mode.load();
     if (m < 0) {
         const char *e = getenv("VECSIM_B200_COARSE");
-        m = (e && e[0] == '0') ? 0 : 1;
+        m = e ? atoi(e) : 1;
+        if (m < 0 || m > 2) m = 1;
         g_coarse_mode.store(m);
     }
-    return m != 0;
+    return m;
+}
+
+// Bring the fp16 shadow copy of the rows up to date on `st` (rows appended, overwritten or moved by a
+// swap-delete since the last coarse batch).  Returns false if HBM for the shadow cannot be had; the
+// caller then runs the TF32 variant on the fp32 rows.
+bool FlatIndex::ensure_shadow(cudaStream_t st) {
+    std::lock_guard<std::mutex> g(mu_);
+    const size_t sp = (dim_ * 2 + 15) & ~(size_t)15;
+    if (shadow_cap_ < count_ || !d_shadow_) {
+        const size_t cap = std::max(capacity_, count_);
+        uint8_t *nu = nullptr;
+        if (cudaMalloc(&nu, cap * sp) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        cudaFree(d_shadow_); // rows are re-converted below; converting 10M x 768 takes ~7 ms
+        d_shadow_ = nu;
+        shadow_cap_ = cap;
+        shadow_pitch_ = sp;
+        shadow_rows_ = 0;
+        shadow_dirty_.clear();
+    }
+    if (shadow_rows_ > count_) shadow_rows_ = count_;
+    bool launched = false;
+    if (shadow_dirty_.size() > 256) {
+        shadow_rows_ = 0;
+        shadow_dirty_.clear();
+    }
+    for (idType id : shadow_dirty_)
+        if (id < shadow_rows_) {
+            if (launch_to_f16(d_rows_, pitch_, (uint32_t)dim_, id, 1, d_shadow_, shadow_pitch_, st) != cudaSuccess) return false;
+            launched = true;
+        }
+    shadow_dirty_.clear();
+    if (shadow_rows_ < count_) {
+        if (launch_to_f16(d_rows_, pitch_, (uint32_t)dim_, (uint32_t)shadow_rows_, (uint32_t)(count_ - shadow_rows_), d_shadow_,
+                          shadow_pitch_, st) != cudaSuccess)
+            return false;
+        shadow_rows_ = count_;
+        launched = true;
+    }
+    // other query streams may read the shadow as soon as the lock is released
+    if (launched && cudaStreamSynchronize(st) != cudaSuccess) return false;
+    return true;
 }
 
 // Enqueue on `st`: the `ke` best composites of each of `nq` device-resident stored-form queries into
@@ -641,7 +690,13 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
                            LaunchCounters &lc, uint64_t **d_result) {
     const CorpusView v = view();
     const ScanPlan sp = plan_scan_topk(v, nq, ke);
-    const bool coarse = coarse_enabled() && metric_ == VecSimMetric_Cosine && !multi_ && coarse_supported(v, nq, ke);
+    const int cmode = coarse_mode();
+    CoarseKind kind = cmode == 2 ? CoarseTF32 : CoarseF16;
+    bool coarse = cmode != 0 && metric_ == VecSimMetric_Cosine && !multi_ && coarse_supported(v, nq, ke, kind);
+    if (coarse && kind == CoarseF16 && !ensure_shadow(st)) {
+        kind = CoarseTF32;
+        coarse = coarse_supported(v, nq, ke, kind);
+    }
     last_batch_coarse_ = coarse;
     if (!coarse) {
         if (!c.need_cand(sp.cand_elems) || !c.need_out((size_t)nq * ke)) return false;
@@ -652,21 +707,31 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         *d_result = c.d_out;
         return ok;
     }
-    const CoarsePlan cp = plan_coarse(v, nq);
+    const CoarsePlan cp = plan_coarse(v, nq, kind);
     const size_t per_query = (size_t)cp.grid_x * cp.keep;
     const size_t nA = (size_t)nq * per_query, nO = (size_t)nq * ke;
-    const size_t total = 2 * nA + 2 * nO + sp.cand_elems + (nq + 1) / 2 + 8;
+    const size_t q16_pitch = (dim_ * 2 + 15) & ~(size_t)15;
+    const size_t q16_elems = kind == CoarseF16 ? ((size_t)nq * q16_pitch + 7) / 8 : 0;
+    const size_t total = 2 * nA + 2 * nO + sp.cand_elems + q16_elems + (nq + 1) / 2 + 8;
     if (!c.need_cand(total) || !c.need_out(nO)) return false;
     uint64_t *coarse_cand = c.d_cand, *exact = coarse_cand + nA, *out1 = exact + nA, *out2 = out1 + nO, *cand2 = out2 + nO;
-    uint32_t *d_ok = reinterpret_cast<uint32_t *>(cand2 + sp.cand_elems);
+    uint64_t *q16 = cand2 + sp.cand_elems;
+    uint32_t *d_ok = reinterpret_cast<uint32_t *>(q16 + q16_elems);
     c.d_last_ok = d_ok;
     c.last_ok_n = nq;
+    CoarseOperands ops{v.rows, v.pitch, d_q, qpitch};
+    bool ok = true;
+    if (kind == CoarseF16) {
+        ok = launch_to_f16(d_q, qpitch, (uint32_t)dim_, 0, nq, q16, q16_pitch, st) == cudaSuccess;
+        ops = CoarseOperands{d_shadow_, shadow_pitch_, q16, q16_pitch};
+        lc.launches++;
+    }
     cudaEventRecord(c.ev_start, st);
-    bool ok = launch_coarse(v, d_q, qpitch, nq, cp, coarse_cand, st) == cudaSuccess;
+    ok = ok && launch_coarse(ops, v.n_rows, v.dim, nq, cp, coarse_cand, st) == cudaSuccess;
     cudaEventRecord(c.ev_stop, st);
     ok = ok && launch_rescore(v, d_q, qpitch, nq, (uint32_t)per_query, coarse_cand, exact, st) == cudaSuccess;
     ok = ok && launch_final_select(exact, nq, (uint32_t)per_query, ke, out1, st, &lc) == cudaSuccess;
-    ok = ok && launch_verify(coarse_cand, out1, nq, cp.grid_x, cp.keep, ke, kCoarseEpsUnit, d_ok, st) == cudaSuccess;
+    ok = ok && launch_verify(coarse_cand, out1, nq, cp.grid_x, cp.keep, ke, coarse_eps(kind), d_ok, st) == cudaSuccess;
     // exact fallback, entirely on device: CTAs whose queries are all verified exit at once
     ok = ok && launch_scan_topk(v, d_q, qpitch, nq, ke, sp, cand2, st, &lc, d_ok) == cudaSuccess;
     ok = ok && launch_final_select(cand2, nq, sp.lists_per_query * ke, ke, out2, st, &lc) == cudaSuccess;

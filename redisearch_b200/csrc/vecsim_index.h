@@ -43,7 +43,7 @@ struct Globals {
     VecSimMemoryFunctions mem{};
 };
 Globals &globals();
-void set_coarse_mode(int mode); // -1 env default, 0 exact scans only, 1 tensor-core coarse pass when eligible
+void set_coarse_mode(int mode); // -1 env default, 0 exact scans only, 1 coarse pass on fp16 shadow rows, 2 TF32 coarse pass
 
 // Device + pinned scratch for one in-flight query (or query batch).  Checked out of a pool so
 // that many RediSearch worker threads can query one index concurrently (SURVEY.md §8b threading).
@@ -175,6 +175,12 @@ class FlatIndex {
     size_t pitch_ = 0;        // HBM row pitch (>= stored_bytes_)
 
     uint8_t *d_rows_ = nullptr;
+    // fp16 copy of the fp32 rows for the tensor-core coarse pass (coarse_tc.cu); built lazily by the first
+    // eligible batch, rows [0, shadow_rows_) valid except shadow_dirty_
+    uint8_t *d_shadow_ = nullptr;
+    size_t shadow_pitch_ = 0, shadow_cap_ = 0, shadow_rows_ = 0;
+    std::vector<idType> shadow_dirty_;
+    bool ensure_shadow(cudaStream_t st);
     size_t capacity_ = 0; // rows of HBM allocated
     size_t count_ = 0;    // rows in the index (incl. staged)
     size_t resident_ = 0; // rows already copied to HBM

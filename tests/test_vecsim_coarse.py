@@ -1,6 +1,6 @@
-"""GPU: the tensor-core coarse pass (csrc/coarse_tf32.cu) must return EXACTLY what the exact scan returns.
+"""GPU: the tensor-core coarse pass (csrc/coarse_tc.cu) must return EXACTLY what the exact scan returns.
 
-tcgen05 TF32 GEMM + fused candidate lists -> exact rescoring (bit-exact arithmetic) -> per-query
+tcgen05 GEMM (mode 1: fp16 shadow rows, mode 2: TF32 on the fp32 rows) + fused candidate lists -> exact rescoring (bit-exact arithmetic) -> per-query
 completeness proof -> on-device fallback.  Whatever the proof decides, ids and scores must equal the
 oracle's bit for bit; the flags tell how many queries were served by the tensor-core path.
 """
@@ -28,14 +28,16 @@ def _device_batch(vs, torch, index, qs_norm, k):
     return out_l.cpu().numpy(), out_s.cpu().numpy(), (flags if frc == 0 else None)
 
 
-@pytest.mark.parametrize("n,dim,nq,k", [(70_000, 128, 40, 10), (66_000, 768, 64, 10), (131_072, 96, 17, 16), (80_000, 100, 33, 5),
-                                        (70_000, 128, 128, 10), (300_000, 64, 256, 10), (66_000, 256, 512, 8)])
-def test_coarse_path_is_exact(n, dim, nq, k):
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("n,dim,nq,k", [(70_000, 128, 40, 10), (66_000, 768, 64, 10), (131_072, 96, 17, 16), (80_000, 104, 33, 5),
+                                        (70_000, 128, 128, 10), (300_000, 64, 256, 10), (66_000, 256, 512, 8),
+                                        (66_000, 1024, 70, 10)])
+def test_coarse_path_is_exact(n, dim, nq, k, mode):
     import torch
 
     from redisearch_b200 import vecsim as vs
 
-    vs.lib().VecSimB200_SetCoarseMode(1)
+    vs.lib().VecSimB200_SetCoarseMode(mode)
     rows = ol.synth_rows(ol.F32, 42, 0, n, dim)
     g = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, vs.VecSimMetric_Cosine)
     p = ol.PortIndex(ol.F32, dim, ol.COS, tier=ol.TIER_AVX512)
@@ -62,9 +64,55 @@ def test_coarse_path_is_exact(n, dim, nq, k):
     vs.lib().VecSimB200_SetCoarseMode(-1)
 
 
+def test_shadow_rows_follow_updates_and_deletes():
+    """mode 1 keeps an fp16 copy of the rows: appended rows, overwritten labels and rows moved by a
+    swap-delete (brute_force.h:196-224) must reach it before the next coarse batch."""
+    import torch
+
+    from redisearch_b200 import vecsim as vs
+
+    vs.lib().VecSimB200_SetCoarseMode(1)
+    n, dim, nq, k = 70_000, 64, 32, 10
+    rows = ol.synth_rows(ol.F32, 7, 0, n + 2000, dim)
+    g = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, vs.VecSimMetric_Cosine)
+    p = ol.PortIndex(ol.F32, dim, ol.COS, tier=ol.TIER_AVX512)
+    g.add_many(rows[:n], label0=1)
+    p.add_many(rows[:n], 1)
+    qs = ol.synth_rows(ol.F32, 8, 0, nq, dim)
+    qn = qs.copy()
+    for i in range(nq):
+        ol.port().orc_normalize(ol._p(qn[i]), dim, ol.F32)
+
+    def check():
+        labels, scores, flags = _device_batch(vs, torch, g, qn, k)
+        assert flags is not None and flags.sum() >= nq * 0.9
+        for i in range(nq):
+            pi, ps = p.topk(qs[i], k)
+            assert labels[i].tolist() == pi.tolist(), (i, labels[i], pi)
+            assert scores[i].tobytes() == ps.astype(np.float32).tobytes()
+        return labels
+
+    first = check()  # builds the shadow
+    # delete the current best hit of every query (swap-delete moves the last rows into the holes) ...
+    for lab in sorted({int(x) for x in first[:, 0]}):
+        assert g.delete(lab) == 1
+        p.delete(lab)
+    # ... overwrite some labels with the query vectors themselves (they become the new best hits) ...
+    for i in range(0, nq, 4):
+        g.add(qs[i], 1000 + i)
+        p.add(qs[i], 1000 + i)
+    # ... and append fresh rows
+    g.add_many(rows[n:], label0=n + 1)
+    p.add_many(rows[n:], n + 1)
+    second = check()
+    for i in range(0, nq, 4):
+        assert second[i, 0] == 1000 + i
+    vs.lib().VecSimB200_SetCoarseMode(-1)
+
+
 def test_coarse_path_falls_back_when_the_margin_is_too_small():
     """Many near-duplicates of the query direction: the 24th-best approximate candidate of a row range is
-    within the TF32 error bound of the true k-th distance, so the proof must fail and the exact scan answers."""
+    within the coarse error bound of the true k-th distance, so the proof must fail and the exact scan answers."""
     import torch
 
     from redisearch_b200 import vecsim as vs
