@@ -8,7 +8,7 @@ A "step" is one pass of the KNN hot path over one batch of 256 synthetic queries
           timed with CUDA events on the launching stream, max over ranks.
   e2e     the same through the host-facing C-ABI (VecSimB200_TopKQueryBatch): host query blobs in,
           host labels/scores out, H2D + D2H inside the timed region.
-  roofline  the dominant kernel (scan_topk_kernel) against measured HBM bandwidth
+  roofline  the dominant kernel (coarse_kernel / scan_topk_kernel) against measured HBM bandwidth
             (MEASURED_PEAKS.json): algorithmic bytes = N*D*4 per launch / its CUDA-event duration.
   cpu_baseline  the reference's own brute-force code (oracle/_ref, built from /root/reference) or,
             if that library is absent, our C restatement, on a bounded sample.
@@ -358,8 +358,11 @@ def main():
     S = load_library("libsynth_b200.so")
     S.Synth_FillRows.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
     S.Synth_NormalizeRowsF32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_void_p]
-    stream = torch.cuda.current_stream()
+    # an explicit stream: a NULL handle would mean CUDA's legacy default stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
+    assert sp.value
 
     # ---- build the shard in HBM: generate + normalise on device, ingest device-to-device
     index = vs.VecSimIndex(vs.VecSimType_FLOAT32, DIM, vs.VecSimMetric_Cosine)
@@ -469,13 +472,23 @@ def main():
     b1_scan_us = st1.scan_device_us / max(1, st1.scan_launches)
     b1_bytes = rows * DIM * 4 + DIM * 4 + K * 12
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline of the dominant kernel: the library brackets it with CUDA events on the launch stream
+    # (VecSimB200_GetStats); one launch per synchronised call so that every interval is one kernel
     peak, peak_src = load_peaks()
-    scan_us = st.scan_device_us / max(1, st.scan_launches) if st.scan_device_us > 0 else None
-    st2 = index.stats(reset=True)  # e2e arm: scan launches timed with CUDA events inside the library
-    if st2.scan_launches:
-        scan_us = st2.scan_device_us / st2.scan_launches
-    alg_bytes = rows * DIM * 4 + nq * DIM * 4 + nq * K * 12
+    index.stats(reset=True)
+    per_launch = []
+    for _ in range(max(3, min(args.steps, 10))):
+        step_device()
+        torch.cuda.synchronize()
+        s_i = index.stats(reset=True)
+        if s_i.scan_launches:
+            per_launch.append(s_i.scan_device_us / s_i.scan_launches)
+    scan_us = float(np.mean(per_launch)) if per_launch else None
+    coarse_mode = int(os.environ.get("VECSIM_B200_COARSE", "1"))
+    dom_kernel = {0: "scan_topk_kernel<f32,IP,4,8>", 1: "coarse_kernel<CfgF16> (tcgen05 kind::f16, fp16 shadow rows)",
+                  2: "coarse_kernel<CfgTF32> (tcgen05 kind::tf32)"}.get(coarse_mode, "?")
+    alg_bytes = rows * DIM * 4 + nq * DIM * 4 + nq * K * 12  # N*D*s per corpus pass
+    read_bytes = rows * DIM * (2 if coarse_mode == 1 else 4)   # what this kernel has to pull from HBM once
     achieved = alg_bytes / (scan_us * 1e-6) / 1e9 if scan_us else None
 
     if rank == 0:
@@ -494,8 +507,11 @@ def main():
             "gpu_launches": int(st.kernel_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "kernel": "scan_topk_kernel<f32,IP,4,8>", "avg_launch_us": scan_us,
-                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+                         "kernel": dom_kernel, "avg_launch_us": scan_us, "launch_us_samples": per_launch,
+                         "algorithmic_bytes_per_launch": alg_bytes, "hbm_bytes_read_per_launch": read_bytes,
+                         "frac_on_bytes_read": (read_bytes / (scan_us * 1e-6) / 1e9 / peak) if scan_us else None,
+                         "share_of_step": (scan_us / 1000.0 / ms_step) if scan_us else None,
+                         "peak_source": peak_src},
             "clocks": clocks.summary(),
             "single_query": {"api": "VecSimIndex_TopKQuery (host blob in, reply out)", "value": 1.0 / b1_s,
                              "unit": "queries/s", "ms_per_query": b1_s * 1000.0,

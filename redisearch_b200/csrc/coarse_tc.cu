@@ -9,20 +9,21 @@
 // (DESIGN.md §4).  On the tensor cores the pass is bound by how many operand bytes each SM has to pull
 // through its L2->shared-memory port (measured ~42 B/clk/SM): every row tile is ingested once per
 // query group, so the two levers are queries per CTA (N) and bytes per element.  Two operand kinds:
-//   CoarseF16   fp16 shadow copy of the corpus (kind::f16, fp32 accumulate), N = 64 queries per CTA:
-//               1/4 of the ingest of the TF32 variant and a TIGHTER error bound (RN to 11 significant
-//               bits vs. TF32's truncation to 11) — the default;
-//   CoarseTF32  the fp32 rows themselves (kind::tf32), N = 32: no shadow memory, 4x the ingest.
+//   CoarseF16   fp16 shadow copy of the corpus (kind::f16, fp32 accumulate), 128 queries per CTA held in
+//               TENSOR MEMORY (coarse_qtmem_kernel): 1/8 of the ingest of the TF32 variant, no query
+//               re-reads from shared memory, and a TIGHTER error bound (RN to 11 significant bits vs.
+//               TF32's truncation to 11) — the default, dim <= 768;
+//   CoarseTF32  the fp32 rows themselves (kind::tf32, coarse_kernel), 32 queries per CTA in shared
+//               memory: no shadow memory, dim <= 1024.
 // Neither is precise enough for the reference's 1e-5 parity bar, hence coarse-then-exact.
 //
-// Kernel shape (one CTA per SM, persistent over 128-row tiles of its row range):
-//   warp 0   TMA producer: A tiles [128 rows x 128 bytes] (128B swizzle) into an n-stage ring
-//   warp 1   MMA issuer (one elected lane): tcgen05.mma.cta_group::1, M=128, N=32|64, K=32 bytes,
-//            A and B from shared memory, accumulator in TMEM (2 stages x N columns)
+// Kernel shape, both variants (one CTA per SM, persistent over the row tiles of its row range):
+//   warp 0   TMA producer: row tiles [rows x 128 bytes] (128B swizzle) into an n-stage ring
+//   warp 1   MMA issuer (one elected lane): tcgen05.mma.cta_group::1, K = 32 bytes per instruction,
+//            accumulator in TMEM (2 stages)
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32 (one row x 32 queries per thread and load), threshold
-//            test, candidate lists in shared memory with lazy compaction
-// The CTA's queries stay resident in shared memory (swizzled K-blocks, 96 KB at dim 768).
+//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32, threshold test, candidate lists in shared memory with
+//            lazy compaction
 #include "coarse_tc.h"
 #include "distance_core.cuh"
 #include "topk_common.cuh"
@@ -47,12 +48,6 @@ struct CfgTF32 {
     static constexpr int kBlockK = 32;  // elements per K block = 128 bytes = one swizzle row
     static constexpr int kElem = 4;
     static constexpr uint32_t kFmt = 2; // UMMA a/b format TF32
-};
-struct CfgF16 {
-    static constexpr int kTileN = 64;
-    static constexpr int kBlockK = 64;
-    static constexpr int kElem = 2;
-    static constexpr uint32_t kFmt = 0; // UMMA a/b format F16
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -122,6 +117,30 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_
             : "memory");
     }
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: A (the resident queries) is read from tensor memory, only B streams
+// through shared memory
+__device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+        "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -366,6 +385,202 @@ coarse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp16 variant with the QUERIES resident in tensor memory (roles swapped: M = 128 queries, N = 64 rows).
+// Measured on the SS kernel above: with both operands in shared memory every MMA re-reads its query
+// block, and the pass is bound by shared-memory operand bandwidth (skipping the MMAs halves the time
+// while the tensor pipe is 12% busy).  Here the 128 queries of a CTA are written once into TMEM
+// (lane = query, 2 fp16 per 32-bit column, 384 columns at dim 768) and the MMA reads them from there;
+// shared memory only carries the streaming row tiles (2 KB per MMA instead of 6), a CTA serves 128
+// queries instead of 64 (half the L2->SM ingest), and in the epilogue a thread owns one QUERY: its
+// threshold lives in a register and its candidate list needs no atomics.
+//   TMEM columns: [0,128) two accumulator stages of 64 rows; [128, 128 + dim/2) the queries.
+// ------------------------------------------------------------------------------------------------
+constexpr int kQM = 128;            // queries per CTA
+constexpr int kQN = 64;             // rows per tile
+constexpr int kQMaxStages = 16;
+constexpr int kQListCap = 96;       // per-query candidate slots
+constexpr int kQTrigger = 64;       // compact a list when it holds more than this after a half tile
+constexpr int kQListStride = 129;   // lists[slot * stride + query]: conflict-free appends
+constexpr uint32_t kQStageBytes = kQN * 128; // one K block of a row tile: 64 rows x 128 bytes
+constexpr uint32_t kQAccCols = 2 * kQN;
+
+// keep the `keep` smallest of list `q` (c entries, c <= 96), ascending, in slots [0, keep); returns the last kept
+__device__ __forceinline__ uint64_t compact_list(uint64_t *lists, int q, uint32_t c, uint32_t keep, int lane) {
+    uint64_t e0 = (lane < (int)c) ? lists[lane * kQListStride + q] : kEmptySlot;
+    uint64_t e1 = (lane + 32 < (int)c) ? lists[(lane + 32) * kQListStride + q] : kEmptySlot;
+    uint64_t e2 = (lane + 64 < (int)c) ? lists[(lane + 64) * kQListStride + q] : kEmptySlot;
+    __syncwarp();
+    uint64_t last = kEmptySlot;
+    for (uint32_t r = 0; r < keep; r++) {
+        uint64_t m = e0 < e1 ? e0 : e1;
+        m = e2 < m ? e2 : m;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            const uint64_t o = shfl_xor_u64(m, sft);
+            m = o < m ? o : m;
+        }
+        // composites are unique (row id in the low word) unless empty
+        if (e0 == m) e0 = kEmptySlot; else if (e1 == m) e1 = kEmptySlot; else if (e2 == m) e2 = kEmptySlot;
+        if (lane == 0) lists[r * kQListStride + q] = m;
+        last = m;
+    }
+    __syncwarp();
+    return last;
+}
+
+__global__ void __launch_bounds__(kCoarseThreads, 1)
+coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t *__restrict__ q16, size_t q16_pitch, uint32_t n_rows,
+                    uint32_t nq, uint32_t dim, uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t nstages,
+                    uint64_t *__restrict__ cand_out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sB = smem;                                                                   // nstages x [64 x 128B]
+    uint64_t *lists = reinterpret_cast<uint64_t *>(sB + (size_t)nstages * kQStageBytes); // [kQListCap][kQListStride]
+    uint64_t *bars = lists + kQListCap * kQListStride;
+    uint64_t *full = bars, *empty = bars + kQMaxStages, *tfull = bars + 2 * kQMaxStages, *tempty = tfull + kAccStages;
+    uint64_t *qbar = tempty + kAccStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(qbar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t q_base = blockIdx.y * kQM;
+    const uint32_t my_tiles = (tiles_total > blockIdx.x) ? (tiles_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < nstages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < kAccStages; a++) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 128);
+        }
+        mbar_init(qbar, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_q = tmem_base + kQAccCols;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer: row tiles [64 rows x 64 halves], one K block per stage =====
+        uint32_t s = 0, ph = 0;
+        for (uint32_t i = 0; i < my_tiles; i++) {
+            const uint32_t tile = blockIdx.x + i * gridDim.x;
+            for (uint32_t kb = 0; kb < num_kb; kb++) {
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], kQStageBytes);
+                tma_load_2d(sB + (size_t)s * kQStageBytes, &map_rows, &full[s], (int)(kb * 64), (int)(tile * kQN));
+                if (++s == nstages) s = 0, ph ^= 1;
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer: D[128 queries x 64 rows] += Q[tmem] * rows[smem]^T =====
+        constexpr uint32_t idesc = make_idesc(0, kQM, kQN);
+        mbar_wait(qbar, 0);
+        tc_fence_after();
+        uint32_t s = 0, ph = 0;
+        for (uint32_t i = 0; i < my_tiles; i++) {
+            const uint32_t a = i % kAccStages, aph = (i / kAccStages) & 1;
+            mbar_wait(&tempty[a], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + a * kQN;
+            for (uint32_t kb = 0; kb < num_kb; kb++) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)s * kQStageBytes));
+#pragma unroll
+                for (int k = 0; k < 4; k++) // 16 halves per instruction = 8 TMEM columns of Q, 32 bytes of the swizzled row
+                    umma_ts_f16(d_tmem, tmem_q + kb * 32 + k * 8, bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0);
+                umma_commit(&empty[s]);
+                if (++s == nstages) s = 0, ph ^= 1;
+            }
+            umma_commit(&tfull[a]);
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;          // TMEM lane quadrant
+        const int et = threadIdx.x - 128; // 0..127 = query slot = TMEM lane
+        const uint32_t q = q_base + et;
+        const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+        // ===== queries -> TMEM (zero padded to num_kb * 64 halves and to 128 queries) =====
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(q16 + (size_t)q * q16_pitch);
+            for (uint32_t kb = 0; kb < num_kb; kb++) {
+                uint32_t w[32];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    uint4 x = make_uint4(0, 0, 0, 0);
+                    if (q < nq && kb * 64 + u * 8 < dim) x = src[kb * 8 + u];
+                    w[u * 4 + 0] = x.x, w[u * 4 + 1] = x.y, w[u * 4 + 2] = x.z, w[u * 4 + 3] = x.w;
+                }
+                tmem_st32(tmem_q + lane_addr + kb * 32, w);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(qbar);
+        }
+        // ===== epilogue: this thread's query against 64 rows per tile =====
+        uint32_t thr = 0xFFFFFFFFu, cnt = 0;
+        for (uint32_t i = 0; i < my_tiles; i++) {
+            const uint32_t tile = blockIdx.x + i * gridDim.x;
+            const uint32_t a = i % kAccStages, aph = (i / kAccStages) & 1;
+            mbar_wait(&tfull[a], aph);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_addr + a * kQN + h * 32, v);
+                if (h == 1) {
+                    tc_fence_before();
+                    mbar_arrive(&tempty[a]); // accumulator stage may be overwritten
+                }
+                const uint32_t row0 = tile * kQN + h * 32;
+                const uint32_t lim = n_rows > row0 ? n_rows - row0 : 0; // rows past the end are TMA zero fill
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t key = orderable_key(1.0f - __uint_as_float(v[j]));
+                    if (key < thr && (uint32_t)j < lim) {
+                        lists[cnt * kQListStride + et] = ((uint64_t)key << 32) | (row0 + j);
+                        cnt++;
+                    }
+                }
+                // lists that ran past the trigger are cut back to the best `keep` by the whole warp
+                uint32_t m = __ballot_sync(0xFFFFFFFFu, cnt > (uint32_t)kQTrigger);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t c = __shfl_sync(0xFFFFFFFFu, cnt, src);
+                    const uint64_t last = compact_list(lists, ew * 32 + src, c, keep, lane);
+                    if (lane == src) {
+                        cnt = keep;
+                        thr = (uint32_t)(last >> 32);
+                    }
+                }
+            }
+        }
+        // publish: cand_out[q][blockIdx.x][keep], ascending, kEmptySlot padded
+        __syncwarp();
+        for (int src = 0; src < 32; src++) {
+            const uint32_t c = __shfl_sync(0xFFFFFFFFu, cnt, src);
+            const uint32_t qq = q_base + ew * 32 + src;
+            compact_list(lists, ew * 32 + src, c, keep, lane);
+            if (qq < nq)
+                for (uint32_t r = lane; r < keep; r += 32)
+                    cand_out[((size_t)qq * gridDim.x + blockIdx.x) * keep + r] = lists[r * kQListStride + ew * 32 + src];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // fp32 rows -> fp16 (round to nearest even) shadow rows; 8 elements per thread, dim % 8 == 0
 __global__ void __launch_bounds__(256) to_f16_kernel(const uint8_t *__restrict__ src, size_t spitch, uint32_t dim, uint32_t first,
                                                      uint32_t n, uint8_t *__restrict__ dst, size_t dpitch) {
@@ -471,8 +686,14 @@ static bool make_map(CUtensorMap *m, CUtensorMapDataType dt, const void *base, u
 
 static constexpr size_t kSmemLimit = 232448; // 227 KB opt-in maximum per CTA on sm_100
 
-static size_t fixed_smem(CoarseKind kind, uint32_t num_kb) {
-    const uint32_t tn = kind == CoarseF16 ? CfgF16::kTileN : CfgTF32::kTileN;
+static size_t qtmem_fixed_smem() {
+    return 1024 + (size_t)kQListCap * kQListStride * 8 + (2 * kQMaxStages + 2 * kAccStages + 1) * 8 + 64;
+}
+// fp16 with the queries in tensor memory: 128 accumulator columns + dim/2 query columns must fit 512
+static bool qtmem_fits(uint32_t dim) { return kQAccCols + ((dim + 63) / 64) * 32 <= 512; }
+
+static size_t fixed_smem(uint32_t num_kb) {
+    const uint32_t tn = CfgTF32::kTileN;
     return 1024 + (size_t)num_kb * tn * 128 + (size_t)tn * kListCap * 8 + (2 * kMaxStages + 2 * kAccStages + 1) * 8 + tn * 8 + 64;
 }
 
@@ -482,23 +703,34 @@ bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind k
     if (c.pitch % 16 != 0) return false;
     if (k > kCoarseMaxK || nq < 16) return false;
     if (c.n_rows < 65536) return false; // tiny corpora: the exact kernel is already fast
-    const uint32_t bk = kind == CoarseF16 ? CfgF16::kBlockK : CfgTF32::kBlockK;
-    if (fixed_smem(kind, (c.dim + bk - 1) / bk) + 3 * kStageBytes > kSmemLimit) return false;
+    if (kind == CoarseF16 && !qtmem_fits(c.dim)) return false; // wider rows: the TF32 variant (queries in shared memory)
+    if (kind == CoarseTF32 && fixed_smem((c.dim + CfgTF32::kBlockK - 1) / CfgTF32::kBlockK) + 3 * kStageBytes > kSmemLimit) return false;
     return encode_fn() != nullptr;
 }
 
 CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind) {
     CoarsePlan p{};
     p.kind = kind;
-    const uint32_t bk = kind == CoarseF16 ? CfgF16::kBlockK : CfgTF32::kBlockK;
-    const uint32_t tn = kind == CoarseF16 ? CfgF16::kTileN : CfgTF32::kTileN;
+    if (kind == CoarseF16) {
+        p.num_kb = (c.dim + 63) / 64;
+        p.tiles = (c.n_rows + kQN - 1) / kQN;
+        p.grid_y = (nq + kQM - 1) / kQM;
+        const uint32_t sms = (uint32_t)device_sm_count();
+        p.grid_x = std::max(1u, std::min(p.tiles, sms / p.grid_y));
+        p.keep = kCoarseKeep;
+        p.stages = (uint32_t)std::min<size_t>(kQMaxStages, (kSmemLimit - qtmem_fixed_smem()) / kQStageBytes);
+        p.cand_elems = (size_t)nq * p.grid_x * p.keep;
+        p.smem_bytes = qtmem_fixed_smem() + (size_t)p.stages * kQStageBytes;
+        return p;
+    }
+    const uint32_t bk = CfgTF32::kBlockK, tn = CfgTF32::kTileN;
     p.num_kb = (c.dim + bk - 1) / bk;
     p.tiles = (c.n_rows + kTileM - 1) / kTileM;
     p.grid_y = (nq + tn - 1) / tn;
     const uint32_t sms = (uint32_t)device_sm_count();
     p.grid_x = std::max(1u, std::min(p.tiles, sms / p.grid_y));
     p.keep = kCoarseKeep;
-    const size_t fixed = fixed_smem(kind, p.num_kb);
+    const size_t fixed = fixed_smem(p.num_kb);
     p.stages = (uint32_t)std::min<size_t>(kMaxStages, (kSmemLimit - fixed) / kStageBytes);
     p.cand_elems = (size_t)nq * p.grid_x * p.keep;
     p.smem_bytes = fixed + (size_t)p.stages * kStageBytes;
@@ -521,8 +753,15 @@ static cudaError_t launch_coarse_t(const void *rows, size_t pitch, uint32_t n_ro
 
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
                           cudaStream_t s) {
-    if (p.kind == CoarseF16)
-        return launch_coarse_t<CfgF16>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);
+    if (p.kind == CoarseF16) {
+        CUtensorMap mr;
+        if (!make_map(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, o.rows, dim, n_rows, o.pitch, 64, kQN)) return cudaErrorInvalidValue;
+        cudaError_t e = cudaFuncSetAttribute(coarse_qtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+        if (e != cudaSuccess) return e;
+        coarse_qtmem_kernel<<<dim3(p.grid_x, p.grid_y), kCoarseThreads, p.smem_bytes, s>>>(
+            mr, static_cast<const uint8_t *>(o.queries), o.qpitch, n_rows, nq, dim, p.num_kb, p.tiles, p.keep, p.stages, d_cand);
+        return cudaGetLastError();
+    }
     return launch_coarse_t<CfgTF32>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);
 }
 

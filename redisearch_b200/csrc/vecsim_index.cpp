@@ -692,8 +692,9 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     const ScanPlan sp = plan_scan_topk(v, nq, ke);
     const int cmode = coarse_mode();
     CoarseKind kind = cmode == 2 ? CoarseTF32 : CoarseF16;
-    bool coarse = cmode != 0 && metric_ == VecSimMetric_Cosine && !multi_ && coarse_supported(v, nq, ke, kind);
-    if (coarse && kind == CoarseF16 && !ensure_shadow(st)) {
+    const bool eligible = cmode != 0 && metric_ == VecSimMetric_Cosine && !multi_;
+    bool coarse = eligible && coarse_supported(v, nq, ke, kind);
+    if (eligible && kind == CoarseF16 && (!coarse || !ensure_shadow(st))) { // rows too wide for TMEM, or no HBM for the shadow
         kind = CoarseTF32;
         coarse = coarse_supported(v, nq, ke, kind);
     }
@@ -830,7 +831,7 @@ int FlatIndex::topk_batch_device(const void *d_q, size_t nq, size_t k, int64_t *
     collect_dev_timing_locked(); // the previous call's scan events (stream-ordered before this call)
     const size_t qpitch = (stored_bytes_ + 15) & ~(size_t)15;
     const uint32_t ke = (uint32_t)std::min(k, std::max<size_t>(n, 1));
-    cudaStream_t st = s ? s : c->stream;
+    cudaStream_t st = s ? s : cudaStreamLegacy; // NULL = the legacy default stream, as everywhere in CUDA
     LaunchCounters lc;
     bool ok = true;
     if (n == 0) {
