@@ -55,6 +55,20 @@ struct CfgTF32 {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a converged warp; keeps the surrounding code warp-uniform so that descriptors and barrier
+// addresses stay in uniform registers (a `lane == 0` branch makes the compiler re-broadcast them per MMA,
+// which left the issuing thread — not the tensor pipe — as the bottleneck: ~57 clk per instruction)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -227,22 +241,28 @@ coarse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
         // ===== TMA producer =====
-        mbar_expect_tx(qbar, num_kb * kQBlockBytes);
-        for (uint32_t kb = 0; kb < num_kb; kb++)
-            tma_load_2d(sQ + (size_t)kb * kQBlockBytes, &map_q, qbar, (int)(kb * Cfg::kBlockK), (int)q_base);
+        if (elect_one_sync()) {
+            mbar_expect_tx(qbar, num_kb * kQBlockBytes);
+            for (uint32_t kb = 0; kb < num_kb; kb++)
+                tma_load_2d(sQ + (size_t)kb * kQBlockBytes, &map_q, qbar, (int)(kb * Cfg::kBlockK), (int)q_base);
+        }
+        __syncwarp();
         uint32_t s = 0, ph = 0;
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t tile = blockIdx.x + i * gridDim.x;
             for (uint32_t kb = 0; kb < num_kb; kb++) {
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], kStageBytes);
-                tma_load_2d(sA + (size_t)s * kStageBytes, &map_a, &full[s], (int)(kb * Cfg::kBlockK), (int)(tile * kTileM));
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&full[s], kStageBytes);
+                    tma_load_2d(sA + (size_t)s * kStageBytes, &map_a, &full[s], (int)(kb * Cfg::kBlockK), (int)(tile * kTileM));
+                }
+                __syncwarp();
                 if (++s == nstages) s = 0, ph ^= 1;
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc(Cfg::kFmt, kTileM, kTileN);
         mbar_wait(qbar, 0);
@@ -257,15 +277,19 @@ coarse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 tc_fence_after();
                 const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)s * kStageBytes));
                 const uint64_t bdesc = make_smem_desc(smem_u32(sQ + (size_t)kb * kQBlockBytes));
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
+                if (elect_one_sync()) {
                     // advance 32 bytes along K inside the swizzled 128-byte row: +2 in 16-byte units
-                    umma_ss<Cfg>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0);
+                    umma_ss<Cfg>(d_tmem, adesc, bdesc, idesc, kb != 0);
+                    umma_ss<Cfg>(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                    umma_ss<Cfg>(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                    umma_ss<Cfg>(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                    umma_commit(&empty[s]); // frees the A stage when these MMAs retire
                 }
-                umma_commit(&empty[s]); // frees the A stage when these MMAs retire
+                __syncwarp();
                 if (++s == nstages) s = 0, ph ^= 1;
             }
-            umma_commit(&tfull[a]); // accumulator of this tile complete
+            if (elect_one_sync()) umma_commit(&tfull[a]); // accumulator of this tile complete
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> candidate lists =====
@@ -466,19 +490,22 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_q = tmem_base + kQAccCols;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
         // ===== TMA producer: row tiles [64 rows x 64 halves], one K block per stage =====
         uint32_t s = 0, ph = 0;
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t tile = blockIdx.x + i * gridDim.x;
             for (uint32_t kb = 0; kb < num_kb; kb++) {
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], kQStageBytes);
-                tma_load_2d(sB + (size_t)s * kQStageBytes, &map_rows, &full[s], (int)(kb * 64), (int)(tile * kQN));
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&full[s], kQStageBytes);
+                    tma_load_2d(sB + (size_t)s * kQStageBytes, &map_rows, &full[s], (int)(kb * 64), (int)(tile * kQN));
+                }
+                __syncwarp();
                 if (++s == nstages) s = 0, ph ^= 1;
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===== MMA issuer: D[128 queries x 64 rows] += Q[tmem] * rows[smem]^T =====
         constexpr uint32_t idesc = make_idesc(0, kQM, kQN);
         mbar_wait(qbar, 0);
@@ -493,13 +520,20 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)s * kQStageBytes));
-#pragma unroll
-                for (int k = 0; k < 4; k++) // 16 halves per instruction = 8 TMEM columns of Q, 32 bytes of the swizzled row
-                    umma_ts_f16(d_tmem, tmem_q + kb * 32 + k * 8, bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0);
-                umma_commit(&empty[s]);
+                const uint32_t a_tmem = tmem_q + kb * 32;
+                if (elect_one_sync()) {
+                    // 16 halves per instruction = 8 TMEM columns of Q, 32 bytes of the swizzled row
+                    umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, kb != 0);
+                    umma_ts_f16(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
+                    umma_ts_f16(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
+                    umma_ts_f16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
+                    umma_commit(&empty[s]);
+                }
+                __syncwarp();
                 if (++s == nstages) s = 0, ph ^= 1;
             }
-            umma_commit(&tfull[a]);
+            if (elect_one_sync()) umma_commit(&tfull[a]);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;          // TMEM lane quadrant
