@@ -422,11 +422,13 @@ coarse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 constexpr int kQM = 128;            // queries per CTA
 constexpr int kQN = 64;             // rows per tile
-constexpr int kQMaxStages = 16;
+constexpr int kQMaxStages = 8;
+constexpr int kQKbPerStage = 4;     // K blocks per pipeline stage: amortises the barrier round trip over 16 MMAs
 constexpr int kQListCap = 96;       // per-query candidate slots
 constexpr int kQTrigger = 64;       // compact a list when it holds more than this after a half tile
 constexpr int kQListStride = 129;   // lists[slot * stride + query]: conflict-free appends
-constexpr uint32_t kQStageBytes = kQN * 128; // one K block of a row tile: 64 rows x 128 bytes
+constexpr uint32_t kQBlockBytes = kQN * 128;                    // one K block of a row tile: 64 rows x 128 bytes
+constexpr uint32_t kQStageBytes = kQKbPerStage * kQBlockBytes; // 32 KB
 constexpr uint32_t kQAccCols = 2 * kQN;
 
 // keep the `keep` smallest of list `q` (c entries, c <= 96), ascending, in slots [0, keep); returns the last kept
@@ -491,15 +493,18 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
     const uint32_t tmem_q = tmem_base + kQAccCols;
 
     if (warp == 0) {
-        // ===== TMA producer: row tiles [64 rows x 64 halves], one K block per stage =====
+        // ===== TMA producer: row tiles [64 rows x 64 halves], kQKbPerStage K blocks per stage =====
         uint32_t s = 0, ph = 0;
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t tile = blockIdx.x + i * gridDim.x;
-            for (uint32_t kb = 0; kb < num_kb; kb++) {
+            for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kQKbPerStage) {
+                const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
                 mbar_wait(&empty[s], ph ^ 1);
                 if (elect_one_sync()) {
-                    mbar_expect_tx(&full[s], kQStageBytes);
-                    tma_load_2d(sB + (size_t)s * kQStageBytes, &map_rows, &full[s], (int)(kb * 64), (int)(tile * kQN));
+                    mbar_expect_tx(&full[s], kbn * kQBlockBytes);
+                    for (uint32_t j = 0; j < kbn; j++)
+                        tma_load_2d(sB + (size_t)s * kQStageBytes + j * kQBlockBytes, &map_rows, &full[s], (int)((kb0 + j) * 64),
+                                    (int)(tile * kQN));
                 }
                 __syncwarp();
                 if (++s == nstages) s = 0, ph ^= 1;
@@ -516,17 +521,25 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
             mbar_wait(&tempty[a], aph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + a * kQN;
-            for (uint32_t kb = 0; kb < num_kb; kb++) {
+            for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kQKbPerStage) {
+                const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)s * kQStageBytes));
-                const uint32_t a_tmem = tmem_q + kb * 32;
+                const uint64_t bdesc0 = make_smem_desc(smem_u32(sB + (size_t)s * kQStageBytes));
+                const uint32_t a_tmem0 = tmem_q + kb0 * 32;
                 if (elect_one_sync()) {
-                    // 16 halves per instruction = 8 TMEM columns of Q, 32 bytes of the swizzled row
-                    umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, kb != 0);
-                    umma_ts_f16(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
-                    umma_ts_f16(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
-                    umma_ts_f16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
+#pragma unroll
+                    for (uint32_t j = 0; j < (uint32_t)kQKbPerStage; j++) {
+                        if (j < kbn) {
+                            // 16 halves per instruction = 8 TMEM columns of Q, 32 bytes of the swizzled row
+                            const uint64_t bdesc = bdesc0 + (uint64_t)(j * (kQBlockBytes >> 4));
+                            const uint32_t a_tmem = a_tmem0 + j * 32;
+                            umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, (kb0 | j) != 0);
+                            umma_ts_f16(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
+                            umma_ts_f16(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
+                            umma_ts_f16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
+                        }
+                    }
                     umma_commit(&empty[s]);
                 }
                 __syncwarp();
@@ -564,19 +577,20 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
             const uint32_t a = i % kAccStages, aph = (i / kAccStages) & 1;
             mbar_wait(&tfull[a], aph);
             tc_fence_after();
+            // drain both halves to registers and hand the accumulator back at once: the MMAs of tile i+2
+            // overlap the selection below
+            uint32_t v[2][32];
+            tmem_ld32(tmem_base + lane_addr + a * kQN, v[0]);
+            tmem_ld32(tmem_base + lane_addr + a * kQN + 32, v[1]);
+            tc_fence_before();
+            mbar_arrive(&tempty[a]);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_addr + a * kQN + h * 32, v);
-                if (h == 1) {
-                    tc_fence_before();
-                    mbar_arrive(&tempty[a]); // accumulator stage may be overwritten
-                }
                 const uint32_t row0 = tile * kQN + h * 32;
                 const uint32_t lim = n_rows > row0 ? n_rows - row0 : 0; // rows past the end are TMA zero fill
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    const uint32_t key = orderable_key(1.0f - __uint_as_float(v[j]));
+                    const uint32_t key = orderable_key(1.0f - __uint_as_float(v[h][j]));
                     if (key < thr && (uint32_t)j < lim) {
                         lists[cnt * kQListStride + et] = ((uint64_t)key << 32) | (row0 + j);
                         cnt++;
