@@ -99,6 +99,12 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// contiguous global -> shared copy through the TMA engine (no tensor map), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -456,7 +462,7 @@ __device__ __forceinline__ uint64_t compact_list(uint64_t *lists, int q, uint32_
 }
 
 __global__ void __launch_bounds__(kCoarseThreads, 1)
-coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t *__restrict__ q16, size_t q16_pitch, uint32_t n_rows,
+coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restrict__ q16, size_t q16_pitch, uint32_t n_rows,
                     uint32_t nq, uint32_t dim, uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t nstages,
                     uint64_t *__restrict__ cand_out) {
     extern __shared__ uint8_t smem_raw[];
@@ -493,7 +499,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
     const uint32_t tmem_q = tmem_base + kQAccCols;
 
     if (warp == 0) {
-        // ===== TMA producer: row tiles [64 rows x 64 halves], kQKbPerStage K blocks per stage =====
+        // ===== producer: row tiles [64 rows x 64 halves] per K block, kQKbPerStage K blocks per stage =====
         uint32_t s = 0, ph = 0;
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t tile = blockIdx.x + i * gridDim.x;
@@ -501,10 +507,11 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                 const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
                 mbar_wait(&empty[s], ph ^ 1);
                 if (elect_one_sync()) {
+                    // the shadow copy is stored tile by tile in the swizzled shared-memory image (to_f16_tiled_kernel):
+                    // the K blocks of a stage are one contiguous run in HBM
                     mbar_expect_tx(&full[s], kbn * kQBlockBytes);
-                    for (uint32_t j = 0; j < kbn; j++)
-                        tma_load_2d(sB + (size_t)s * kQStageBytes + j * kQBlockBytes, &map_rows, &full[s], (int)((kb0 + j) * 64),
-                                    (int)(tile * kQN));
+                    bulk_load_1d(sB + (size_t)s * kQStageBytes, shadow + ((size_t)tile * num_kb + kb0) * kQBlockBytes, kbn * kQBlockBytes,
+                                 &full[s]);
                 }
                 __syncwarp();
                 if (++s == nstages) s = 0, ph ^= 1;
@@ -572,6 +579,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         }
         // ===== epilogue: this thread's query against 64 rows per tile =====
         uint32_t thr = 0xFFFFFFFFu, cnt = 0;
+        float thr_dot = -__int_as_float(0x7f800000); // -inf: everything passes until the first compaction
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t tile = blockIdx.x + i * gridDim.x;
             const uint32_t a = i % kAccStages, aph = (i / kAccStages) & 1;
@@ -587,11 +595,22 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const uint32_t row0 = tile * kQN + h * 32;
-                const uint32_t lim = n_rows > row0 ? n_rows - row0 : 0; // rows past the end are TMA zero fill
+                // pre-test on the raw dot product against a slightly loose bound (2 instructions per value);
+                // the few survivors take the exact key comparison below
+                uint32_t pass = 0;
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const uint32_t key = orderable_key(1.0f - __uint_as_float(v[h][j]));
-                    if (key < thr && (uint32_t)j < lim) {
+                for (int j = 0; j < 32; j++)
+                    if (__uint_as_float(v[h][j]) > thr_dot) pass |= 1u << j;
+                if (row0 + 32 > n_rows) pass &= (n_rows > row0) ? ((1u << (n_rows - row0)) - 1u) : 0u; // TMA zero fill past the end
+                while (pass) {
+                    const int j = __ffs(pass) - 1;
+                    pass &= pass - 1;
+                    uint32_t raw = 0;
+#pragma unroll
+                    for (int x = 0; x < 32; x++)
+                        if (x == j) raw = v[h][x];
+                    const uint32_t key = orderable_key(1.0f - __uint_as_float(raw));
+                    if (key < thr) {
                         lists[cnt * kQListStride + et] = ((uint64_t)key << 32) | (row0 + j);
                         cnt++;
                     }
@@ -606,6 +625,8 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                     if (lane == src) {
                         cnt = keep;
                         thr = (uint32_t)(last >> 32);
+                        // d = 1 - dot < d_thr needs dot > 1 - d_thr; the slack covers the rounding of both subtractions
+                        thr_dot = (1.0f - key_to_float(thr)) - 4e-7f;
                     }
                 }
             }
@@ -802,15 +823,54 @@ static cudaError_t launch_coarse_t(const void *rows, size_t pitch, uint32_t n_ro
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
                           cudaStream_t s) {
     if (p.kind == CoarseF16) {
-        CUtensorMap mr;
-        if (!make_map(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, o.rows, dim, n_rows, o.pitch, 64, kQN)) return cudaErrorInvalidValue;
         cudaError_t e = cudaFuncSetAttribute(coarse_qtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
         if (e != cudaSuccess) return e;
         coarse_qtmem_kernel<<<dim3(p.grid_x, p.grid_y), kCoarseThreads, p.smem_bytes, s>>>(
-            mr, static_cast<const uint8_t *>(o.queries), o.qpitch, n_rows, nq, dim, p.num_kb, p.tiles, p.keep, p.stages, d_cand);
+            static_cast<const uint8_t *>(o.rows), static_cast<const uint8_t *>(o.queries), o.qpitch, n_rows, nq, dim, p.num_kb, p.tiles,
+            p.keep, p.stages, d_cand);
         return cudaGetLastError();
     }
     return launch_coarse_t<CfgTF32>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);
+}
+
+// fp32 rows -> the tiled fp16 shadow: [tile of 64 rows][K block of 64 halves][64 rows x 128 B, 128B-swizzled],
+// i.e. exactly the bytes a SWIZZLE_128B tensor-map load would have produced in shared memory, so that
+// coarse_qtmem_kernel can stream it with contiguous bulk copies.  One 16-byte chunk (8 halves) per thread;
+// chunks past `dim` are zero.
+__global__ void __launch_bounds__(256) to_f16_tiled_kernel(const uint8_t *__restrict__ src, size_t spitch, uint32_t dim, uint32_t first,
+                                                           uint32_t n, uint8_t *__restrict__ dst, uint32_t num_kb) {
+    const uint32_t per_row = num_kb * 8;
+    const size_t total = (size_t)n * per_row;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = first + (uint32_t)(i / per_row), ci = (uint32_t)(i % per_row);
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (ci * 8 < dim) {
+            const float4 *p = reinterpret_cast<const float4 *>(src + (size_t)r * spitch) + 2 * ci;
+            const float4 x = p[0], y = p[1];
+            __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+            __half2 h2 = __floats2half2_rn(y.x, y.y), h3 = __floats2half2_rn(y.z, y.w);
+            o.x = *reinterpret_cast<uint32_t *>(&h0);
+            o.y = *reinterpret_cast<uint32_t *>(&h1);
+            o.z = *reinterpret_cast<uint32_t *>(&h2);
+            o.w = *reinterpret_cast<uint32_t *>(&h3);
+        }
+        const uint32_t tile = r / kQN, rr = r % kQN, kb = ci / 8, c = ci % 8;
+        uint8_t *blk = dst + ((size_t)tile * num_kb + kb) * kQBlockBytes;
+        *reinterpret_cast<uint4 *>(blk + rr * 128 + ((c ^ (rr & 7)) * 16)) = o;
+    }
+}
+
+size_t coarse_shadow_bytes(uint32_t rows, uint32_t dim) {
+    return (size_t)((rows + kQN - 1) / kQN) * ((dim + 63) / 64) * kQBlockBytes;
+}
+
+cudaError_t launch_to_f16_tiled(const void *src, size_t spitch, uint32_t dim, uint32_t first, uint32_t n, void *dst, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t num_kb = (dim + 63) / 64;
+    const size_t total = (size_t)n * num_kb * 8;
+    const uint32_t grid = (uint32_t)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)device_sm_count() * 16));
+    to_f16_tiled_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(src), spitch, dim, first, n, static_cast<uint8_t *>(dst), num_kb);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_to_f16(const void *src, size_t spitch, uint32_t dim, uint32_t first, uint32_t n, void *dst, size_t dpitch,

@@ -38,7 +38,11 @@ bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind k
 CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind);
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
                           cudaStream_t s);
-// fp32 rows [first, first+n) -> fp16 rows of the shadow copy (dim % 8 == 0)
+// fp32 rows [first, first+n) -> the tiled fp16 shadow copy read by the CoarseF16 kernel (layout in coarse_tc.cu);
+// the buffer holds coarse_shadow_bytes(capacity_rows, dim) bytes
+size_t coarse_shadow_bytes(uint32_t rows, uint32_t dim);
+cudaError_t launch_to_f16_tiled(const void *src, size_t spitch, uint32_t dim, uint32_t first, uint32_t n, void *dst, cudaStream_t s);
+// fp32 rows [first, first+n) -> row-major fp16 rows (the query batch; dim % 8 == 0)
 cudaError_t launch_to_f16(const void *src, size_t spitch, uint32_t dim, uint32_t first, uint32_t n, void *dst, size_t dpitch,
                           cudaStream_t s);
 cudaError_t launch_rescore(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t per_query,

@@ -643,18 +643,16 @@ static int coarse_mode() {
 // caller then runs the TF32 variant on the fp32 rows.
 bool FlatIndex::ensure_shadow(cudaStream_t st) {
     std::lock_guard<std::mutex> g(mu_);
-    const size_t sp = (dim_ * 2 + 15) & ~(size_t)15;
     if (shadow_cap_ < count_ || !d_shadow_) {
         const size_t cap = std::max(capacity_, count_);
         uint8_t *nu = nullptr;
-        if (cudaMalloc(&nu, cap * sp) != cudaSuccess) {
+        if (cudaMalloc(&nu, coarse_shadow_bytes((uint32_t)cap, (uint32_t)dim_)) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
         cudaFree(d_shadow_); // rows are re-converted below; converting 10M x 768 takes ~7 ms
         d_shadow_ = nu;
         shadow_cap_ = cap;
-        shadow_pitch_ = sp;
         shadow_rows_ = 0;
         shadow_dirty_.clear();
     }
@@ -666,13 +664,13 @@ bool FlatIndex::ensure_shadow(cudaStream_t st) {
     }
     for (idType id : shadow_dirty_)
         if (id < shadow_rows_) {
-            if (launch_to_f16(d_rows_, pitch_, (uint32_t)dim_, id, 1, d_shadow_, shadow_pitch_, st) != cudaSuccess) return false;
+            if (launch_to_f16_tiled(d_rows_, pitch_, (uint32_t)dim_, id, 1, d_shadow_, st) != cudaSuccess) return false;
             launched = true;
         }
     shadow_dirty_.clear();
     if (shadow_rows_ < count_) {
-        if (launch_to_f16(d_rows_, pitch_, (uint32_t)dim_, (uint32_t)shadow_rows_, (uint32_t)(count_ - shadow_rows_), d_shadow_,
-                          shadow_pitch_, st) != cudaSuccess)
+        if (launch_to_f16_tiled(d_rows_, pitch_, (uint32_t)dim_, (uint32_t)shadow_rows_, (uint32_t)(count_ - shadow_rows_), d_shadow_,
+                                st) != cudaSuccess)
             return false;
         shadow_rows_ = count_;
         launched = true;
@@ -724,7 +722,7 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     bool ok = true;
     if (kind == CoarseF16) {
         ok = launch_to_f16(d_q, qpitch, (uint32_t)dim_, 0, nq, q16, q16_pitch, st) == cudaSuccess;
-        ops = CoarseOperands{d_shadow_, shadow_pitch_, q16, q16_pitch};
+        ops = CoarseOperands{d_shadow_, 0, q16, q16_pitch};
         lc.launches++;
     }
     cudaEventRecord(c.ev_start, st);

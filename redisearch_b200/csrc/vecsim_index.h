@@ -175,10 +175,11 @@ class FlatIndex {
     size_t pitch_ = 0;        // HBM row pitch (>= stored_bytes_)
 
     uint8_t *d_rows_ = nullptr;
-    // fp16 copy of the fp32 rows for the tensor-core coarse pass (coarse_tc.cu); built lazily by the first
-    // eligible batch, rows [0, shadow_rows_) valid except shadow_dirty_
+    // fp16 copy of the fp32 rows for the tensor-core coarse pass, stored tile by tile in the swizzled layout
+    // the kernel streams (coarse_tc.cu); built lazily by the first eligible batch, rows [0, shadow_rows_)
+    // valid except shadow_dirty_
     uint8_t *d_shadow_ = nullptr;
-    size_t shadow_pitch_ = 0, shadow_cap_ = 0, shadow_rows_ = 0;
+    size_t shadow_cap_ = 0, shadow_rows_ = 0;
     std::vector<idType> shadow_dirty_;
     bool ensure_shadow(cudaStream_t st);
     size_t capacity_ = 0; // rows of HBM allocated
