@@ -105,6 +105,30 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// the same, delivered to the same shared-memory offset of every CTA in `mask`; each destination's mbarrier (same
+// offset) receives the byte count
+__device__ __forceinline__ void bulk_load_1d_mc(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -463,7 +487,7 @@ __device__ __forceinline__ uint64_t compact_list(uint64_t *lists, int q, uint32_
 
 __global__ void __launch_bounds__(kCoarseThreads, 1)
 coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restrict__ q16, size_t q16_pitch, uint32_t n_rows,
-                    uint32_t nq, uint32_t dim, uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t nstages,
+                    uint32_t nq, uint32_t dim, uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t nstages, uint32_t csize,
                     uint64_t *__restrict__ cand_out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -481,7 +505,7 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < nstages; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], csize); // one commit per CTA of the cluster: all of them read the multicast stage
         }
         for (int a = 0; a < kAccStages; a++) {
             mbar_init(&tfull[a], 1);
@@ -497,6 +521,13 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_q = tmem_base + kQAccCols;
+    // cluster mode: the csize CTAs that share blockIdx.x (one per group of 128 queries) walk the SAME row tiles.
+    // Each fetches 1/csize of every stage and multicasts it into all csize shared memories, so a tile leaves
+    // HBM/L2 once per cluster (measured without it: the query groups drift apart and every tile is read from HBM
+    // once per group, L2 hit rate 10%).
+    const uint32_t crank = (csize > 1) ? cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+    if (csize > 1) cluster_sync_all(); // peers must see initialised barriers before anything is signalled remotely
 
     if (warp == 0) {
         // ===== producer: row tiles [64 rows x 64 halves] per K block, kQKbPerStage K blocks per stage =====
@@ -509,9 +540,15 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
                 if (elect_one_sync()) {
                     // the shadow copy is stored tile by tile in the swizzled shared-memory image (to_f16_tiled_kernel):
                     // the K blocks of a stage are one contiguous run in HBM
-                    mbar_expect_tx(&full[s], kbn * kQBlockBytes);
-                    bulk_load_1d(sB + (size_t)s * kQStageBytes, shadow + ((size_t)tile * num_kb + kb0) * kQBlockBytes, kbn * kQBlockBytes,
-                                 &full[s]);
+                    const uint32_t bytes = kbn * kQBlockBytes;
+                    const uint8_t *src = shadow + ((size_t)tile * num_kb + kb0) * kQBlockBytes;
+                    mbar_expect_tx(&full[s], bytes);
+                    if (csize > 1) {
+                        const uint32_t slice = bytes / csize; // multiple of 16
+                        bulk_load_1d_mc(sB + (size_t)s * kQStageBytes + crank * slice, src + crank * slice, slice, &full[s], cmask);
+                    } else {
+                        bulk_load_1d(sB + (size_t)s * kQStageBytes, src, bytes, &full[s]);
+                    }
                 }
                 __syncwarp();
                 if (++s == nstages) s = 0, ph ^= 1;
@@ -547,7 +584,10 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
                             umma_ts_f16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
                         }
                     }
-                    umma_commit(&empty[s]);
+                    if (csize > 1)
+                        umma_commit_mc(&empty[s], cmask); // this CTA is done with stage s: tell every producer of the cluster
+                    else
+                        umma_commit(&empty[s]);
                 }
                 __syncwarp();
                 if (++s == nstages) s = 0, ph ^= 1;
@@ -644,6 +684,7 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
     }
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all(); // no CTA may exit while peers can still write its shared memory / barriers
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -788,8 +829,39 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind) {
         p.grid_x = std::max(1u, std::min(p.tiles, sms / p.grid_y));
         p.keep = kCoarseKeep;
         p.stages = (uint32_t)std::min<size_t>(kQMaxStages, (kSmemLimit - qtmem_fixed_smem()) / kQStageBytes);
-        p.cand_elems = (size_t)nq * p.grid_x * p.keep;
         p.smem_bytes = qtmem_fixed_smem() + (size_t)p.stages * kQStageBytes;
+        // the query groups of a row range form a thread-block cluster (multicast of the row tiles)
+        p.csize = 1;
+        static int ccap = -1; // VECSIM_B200_CLUSTER caps the cluster size (1 = no clusters)
+        if (ccap < 0) {
+            const char *e = getenv("VECSIM_B200_CLUSTER");
+            ccap = e ? std::max(1, atoi(e)) : 4;
+        }
+        for (uint32_t cs = 4; cs > 1; cs >>= 1)
+            if ((int)cs <= ccap && p.grid_y % cs == 0 && (kQStageBytes / kQKbPerStage) % (16 * cs) == 0) {
+                p.csize = cs;
+                break;
+            }
+        if (p.csize > 1) {
+            cudaFuncSetAttribute(coarse_qtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute at[1];
+            cfg.gridDim = dim3(1, p.grid_y, 1);
+            cfg.blockDim = dim3(kCoarseThreads);
+            cfg.dynamicSmemBytes = p.smem_bytes;
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 1, at[0].val.clusterDim.y = p.csize, at[0].val.clusterDim.z = 1;
+            cfg.attrs = at, cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, coarse_qtmem_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                p.csize = 1;
+            } else {
+                // one wave of co-resident clusters: grid_x row ranges x (grid_y / csize) clusters each
+                p.grid_x = std::max(1u, std::min(p.grid_x, (uint32_t)nclusters / (p.grid_y / p.csize)));
+            }
+        }
+        p.cand_elems = (size_t)nq * p.grid_x * p.keep;
         return p;
     }
     const uint32_t bk = CfgTF32::kBlockK, tn = CfgTF32::kTileN;
@@ -825,10 +897,17 @@ cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim
     if (p.kind == CoarseF16) {
         cudaError_t e = cudaFuncSetAttribute(coarse_qtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
         if (e != cudaSuccess) return e;
-        coarse_qtmem_kernel<<<dim3(p.grid_x, p.grid_y), kCoarseThreads, p.smem_bytes, s>>>(
-            static_cast<const uint8_t *>(o.rows), static_cast<const uint8_t *>(o.queries), o.qpitch, n_rows, nq, dim, p.num_kb, p.tiles,
-            p.keep, p.stages, d_cand);
-        return cudaGetLastError();
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute at[1];
+        cfg.gridDim = dim3(p.grid_x, p.grid_y, 1);
+        cfg.blockDim = dim3(kCoarseThreads);
+        cfg.dynamicSmemBytes = p.smem_bytes;
+        cfg.stream = s;
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1, at[0].val.clusterDim.y = p.csize, at[0].val.clusterDim.z = 1;
+        cfg.attrs = at, cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, coarse_qtmem_kernel, static_cast<const uint8_t *>(o.rows), static_cast<const uint8_t *>(o.queries),
+                                  o.qpitch, n_rows, nq, dim, p.num_kb, p.tiles, p.keep, p.stages, p.csize, d_cand);
     }
     return launch_coarse_t<CfgTF32>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);
 }

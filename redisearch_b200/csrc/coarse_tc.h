@@ -23,6 +23,7 @@ struct CoarsePlan {
     CoarseKind kind;
     uint32_t grid_x, grid_y, num_kb, tiles, keep;
     uint32_t stages; // depth of the row-tile ring in shared memory
+    uint32_t csize;  // thread-block cluster size along y (query groups sharing multicast row tiles); 1 = none
     size_t cand_elems; // uint64 per (query, list, keep)
     size_t smem_bytes;
 };
