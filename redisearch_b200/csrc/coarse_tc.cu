@@ -184,6 +184,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -448,18 +460,20 @@ coarse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 // shared memory only carries the streaming row tiles (2 KB per MMA instead of 6), a CTA serves 128
 // queries instead of 64 (half the L2->SM ingest), and in the epilogue a thread owns one QUERY: its
 // threshold lives in a register and its candidate list needs no atomics.
-//   TMEM columns: [0,128) two accumulator stages of 64 rows; [128, 128 + dim/2) the queries.
+//   TMEM columns: [0,128) the accumulator of a 128-row tile; [128, 128 + dim/2) the queries.  There is no room
+//   for a second accumulator, so the epilogue drains the tile to registers (4 x tcgen05.ld) and hands it back
+//   before it looks at a single value; only that drain is not overlapped with the MMAs of the next tile.
 // ------------------------------------------------------------------------------------------------
 constexpr int kQM = 128;            // queries per CTA
-constexpr int kQN = 64;             // rows per tile
+constexpr int kQN = 128;            // rows per tile = N of one MMA (measured: N=64 58 clk, N=128 76 clk per instruction)
 constexpr int kQMaxStages = 8;
-constexpr int kQKbPerStage = 4;     // K blocks per pipeline stage: amortises the barrier round trip over 16 MMAs
+constexpr int kQKbPerStage = 2;     // K blocks per pipeline stage: amortises the barrier round trip over 8 MMAs
 constexpr int kQListCap = 96;       // per-query candidate slots
 constexpr int kQTrigger = 64;       // compact a list when it holds more than this after a half tile
 constexpr int kQListStride = 129;   // lists[slot * stride + query]: conflict-free appends
-constexpr uint32_t kQBlockBytes = kQN * 128;                    // one K block of a row tile: 64 rows x 128 bytes
+constexpr uint32_t kQBlockBytes = kQN * 128;                    // one K block of a row tile: 128 rows x 128 bytes
 constexpr uint32_t kQStageBytes = kQKbPerStage * kQBlockBytes; // 32 KB
-constexpr uint32_t kQAccCols = 2 * kQN;
+constexpr uint32_t kQAccCols = kQN; // ONE accumulator: 128 columns are all that is left beside the queries
 
 // keep the `keep` smallest of list `q` (c entries, c <= 96), ascending, in slots [0, keep); returns the last kept
 __device__ __forceinline__ uint64_t compact_list(uint64_t *lists, int q, uint32_t c, uint32_t keep, int lane) {
@@ -494,7 +508,7 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
     uint8_t *sB = smem;                                                                   // nstages x [64 x 128B]
     uint64_t *lists = reinterpret_cast<uint64_t *>(sB + (size_t)nstages * kQStageBytes); // [kQListCap][kQListStride]
     uint64_t *bars = lists + kQListCap * kQListStride;
-    uint64_t *full = bars, *empty = bars + kQMaxStages, *tfull = bars + 2 * kQMaxStages, *tempty = tfull + kAccStages;
+    uint64_t *full = bars, *empty = bars + kQMaxStages, *tfull = bars + 2 * kQMaxStages, *tempty = tfull + kAccStages; // [0] used
     uint64_t *qbar = tempty + kAccStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(qbar + 1);
 
@@ -555,16 +569,15 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: D[128 queries x 64 rows] += Q[tmem] * rows[smem]^T =====
+        // ===== MMA issuer: D[128 queries x 128 rows] += Q[tmem] * rows[smem]^T =====
         constexpr uint32_t idesc = make_idesc(0, kQM, kQN);
         mbar_wait(qbar, 0);
         tc_fence_after();
         uint32_t s = 0, ph = 0;
         for (uint32_t i = 0; i < my_tiles; i++) {
-            const uint32_t a = i % kAccStages, aph = (i / kAccStages) & 1;
-            mbar_wait(&tempty[a], aph ^ 1);
+            mbar_wait(&tempty[0], (i & 1) ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + a * kQN;
+            const uint32_t d_tmem = tmem_base;
             for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kQKbPerStage) {
                 const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
                 mbar_wait(&full[s], ph);
@@ -592,7 +605,7 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
                 __syncwarp();
                 if (++s == nstages) s = 0, ph ^= 1;
             }
-            if (elect_one_sync()) umma_commit(&tfull[a]);
+            if (elect_one_sync()) umma_commit(&tfull[0]);
             __syncwarp();
         }
     } else if (warp >= 4) {
@@ -622,18 +635,18 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
         float thr_dot = -__int_as_float(0x7f800000); // -inf: everything passes until the first compaction
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t tile = blockIdx.x + i * gridDim.x;
-            const uint32_t a = i % kAccStages, aph = (i / kAccStages) & 1;
-            mbar_wait(&tfull[a], aph);
+            mbar_wait(&tfull[0], i & 1);
             tc_fence_after();
-            // drain both halves to registers and hand the accumulator back at once: the MMAs of tile i+2
+            // drain the whole tile to registers and hand the accumulator back at once: the MMAs of the next tile
             // overlap the selection below
-            uint32_t v[2][32];
-            tmem_ld32(tmem_base + lane_addr + a * kQN, v[0]);
-            tmem_ld32(tmem_base + lane_addr + a * kQN + 32, v[1]);
-            tc_fence_before();
-            mbar_arrive(&tempty[a]);
+            uint32_t v[kQN / 32][32];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int h = 0; h < kQN / 32; h++) tmem_ld32_nowait(tmem_base + lane_addr + h * 32, v[h]);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&tempty[0]);
+#pragma unroll
+            for (int h = 0; h < kQN / 32; h++) {
                 const uint32_t row0 = tile * kQN + h * 32;
                 // pre-test on the raw dot product against a slightly loose bound (2 instructions per value);
                 // the few survivors take the exact key comparison below
@@ -912,7 +925,7 @@ cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim
     return launch_coarse_t<CfgTF32>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);
 }
 
-// fp32 rows -> the tiled fp16 shadow: [tile of 64 rows][K block of 64 halves][64 rows x 128 B, 128B-swizzled],
+// fp32 rows -> the tiled fp16 shadow: [tile of 128 rows][K block of 64 halves][128 rows x 128 B, 128B-swizzled],
 // i.e. exactly the bytes a SWIZZLE_128B tensor-map load would have produced in shared memory, so that
 // coarse_qtmem_kernel can stream it with contiguous bulk copies.  One 16-byte chunk (8 halves) per thread;
 // chunks past `dim` are zero.
