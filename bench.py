@@ -485,8 +485,17 @@ def main():
             per_launch.append(s_i.scan_device_us / s_i.scan_launches)
     scan_us = float(np.mean(per_launch)) if per_launch else None
     coarse_mode = int(os.environ.get("VECSIM_B200_COARSE", "1"))
-    dom_kernel = {0: "scan_topk_kernel<f32,IP,4,8>", 1: "coarse_kernel<CfgF16> (tcgen05 kind::f16, fp16 shadow rows)",
+    dom_kernel = {0: "scan_topk_kernel<f32,IP,4,8>",
+                  1: "coarse_qtmem_kernel (tcgen05 kind::f16 TS-mode, queries in TMEM, fp16 shadow rows)",
                   2: "coarse_kernel<CfgTF32> (tcgen05 kind::tf32)"}.get(coarse_mode, "?")
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f).get(dom_kernel.split(" ")[0].split("<")[0])
+        if t and (t["rows"], t["dim"], t["batch"]) == (rows, DIM, nq):
+            traffic = t["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
     alg_bytes = rows * DIM * 4 + nq * DIM * 4 + nq * K * 12  # N*D*s per corpus pass
     read_bytes = rows * DIM * (2 if coarse_mode == 1 else 4)   # what this kernel has to pull from HBM once
     achieved = alg_bytes / (scan_us * 1e-6) / 1e9 if scan_us else None
@@ -506,7 +515,7 @@ def main():
                     "d2h_bytes_per_step": int(nq * K * 8), "ms_per_step": e2e_s * 1000.0},
             "gpu_launches": int(st.kernel_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "kernel": dom_kernel, "avg_launch_us": scan_us, "launch_us_samples": per_launch,
                          "algorithmic_bytes_per_launch": alg_bytes, "hbm_bytes_read_per_launch": read_bytes,
                          "frac_on_bytes_read": (read_bytes / (scan_us * 1e-6) / 1e9 / peak) if scan_us else None,

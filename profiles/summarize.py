@@ -17,7 +17,12 @@ KEY = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"
        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct",
        "lts__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor",
-       "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
+       "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "sm__cycles_elapsed.avg.per_second",
+       "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+       "dram__bytes_read.sum.per_second", "launch__cluster_size",
+       "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+       "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+       "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
 
 
 def launches(src, dst):
@@ -53,7 +58,7 @@ def full(src, dst):
     with open(dst, "w") as f:
         f.write(f"# ncu --set full capture, source `{src}` (not tracked; regenerate with the command in profiles/README.md)\n\n")
         for r in rows[2:]:
-            if r[idx["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]] in ("", "-nan", "nan"):
+            if r[idx["gpu__time_duration.sum"]] in ("", "-nan", "nan"):
                 continue
             f.write(f"## {r[idx['Kernel Name']]}  (grid {r[idx['launch__grid_size']]})\n\n| metric | value | unit |\n|---|---:|---|\n")
             for k in KEY:
