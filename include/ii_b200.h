@@ -187,7 +187,10 @@ size_t II_ResultSet_TopN(const II_ResultSet *rs, size_t n, uint64_t *doc_ids, do
 const uint32_t *II_ResultSet_DeviceDocIds(const II_ResultSet *rs);
 const double *II_ResultSet_DeviceScores(const II_ResultSet *rs);
 
-/* One call for the common query: AND (or OR) of term lists, score, top-N; host arrays out. */
+/* One call for the common query: AND (or OR) of term lists, score, top-N; host arrays out.
+ * Thread-safe: every calling thread owns a stream inside the library (one iterator tree per RediSearch worker
+ * thread, src/util/workers.c), so concurrent searches over shared posting lists overlap on the device.
+ * II_GetStats reports the calling thread's counters. */
 size_t II_SearchTopN(II_PostingList *const *lists, size_t n, int is_union, II_Scorer scorer,
                      const II_TermParams *terms, double agg_weight, const II_IndexStats *stats,
                      const II_DocTable *docs, size_t top_n, uint64_t *doc_ids, double *scores, size_t *total_hits);

@@ -17,7 +17,8 @@ using namespace rsb200;
 
 namespace {
 
-struct Ctx { // one stream; calls are serialised (RediSearch runs one iterator tree per worker thread)
+struct Ctx { // one per calling thread: own stream, events and pinned staging (RediSearch runs one iterator
+             // tree per worker thread, so concurrent FT.SEARCHes overlap on the device)
     std::mutex mu;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
@@ -41,6 +42,18 @@ struct Ctx { // one stream; calls are serialised (RediSearch runs one iterator t
         return h_stage;
     }
     bool ok = false;
+    ~Ctx() { // worker thread exits; errors after runtime teardown are harmless
+        if (!ok) return;
+        cudaStreamSynchronize(stream);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaEventDestroy(e2);
+        cudaFree(d_total);
+        cudaFreeHost(h_total);
+        cudaFreeHost(h_stage);
+        cudaStreamDestroy(stream);
+        cudaGetLastError();
+    }
     bool init() {
         if (ok) return true;
         int nd = 0;
@@ -66,7 +79,7 @@ struct Ctx { // one stream; calls are serialised (RediSearch runs one iterator t
     }
 };
 Ctx &ctx() {
-    static Ctx c;
+    static thread_local Ctx c;
     return c;
 }
 
@@ -232,27 +245,46 @@ II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nbl
     bool ok = d_ids && d_freqs && (!need_mask || d_masks);
     if (ok && n) {
         if (decode_on_device) {
-            // ship the raw block bytes, decode with one thread per block
-            std::vector<uint8_t> bytes(byte_off[nblocks]);
-            std::vector<uint64_t> first(nblocks);
-            for (size_t b = 0; b < nblocks; b++) {
-                memcpy(bytes.data() + byte_off[b], blocks[b].data, blocks[b].len);
-                first[b] = blocks[b].first_doc_id;
+            // ship the raw block bytes (gathered into pinned staging by all cores), decode with one thread per block
+            const size_t nbytes = byte_off[nblocks];
+            uint8_t *stg = c.stage(nbytes + nblocks * 8 + 16);
+            if (!stg) {
+                dfree(d_ids);
+                dfree(d_freqs);
+                dfree(d_masks);
+                delete pl;
+                return nullptr;
             }
-            uint8_t *d_bytes = dalloc<uint8_t>(bytes.size() + 8);
+            uint8_t *bytes = stg;
+            uint64_t *first = reinterpret_cast<uint64_t *>(stg + ((nbytes + 7) & ~(size_t)7));
+            const double tg = now_us();
+            {
+                unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)(nblocks / 4096 + 1)}));
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < nt; t++)
+                    th.emplace_back([&, t] {
+                        const size_t b0 = nblocks * t / nt, b1 = nblocks * (t + 1) / nt;
+                        for (size_t b = b0; b < b1; b++) {
+                            memcpy(bytes + byte_off[b], blocks[b].data, blocks[b].len);
+                            first[b] = blocks[b].first_doc_id;
+                        }
+                    });
+                for (auto &x : th) x.join();
+            }
+            c.stats.decode_host_us = now_us() - tg; // host share of the device-decode route: the gather
+            uint8_t *d_bytes = dalloc<uint8_t>(nbytes + 8);
             uint64_t *d_boff = dalloc<uint64_t>(nblocks + 1), *d_first = dalloc<uint64_t>(nblocks);
             uint32_t *d_eoff = dalloc<uint32_t>(nblocks + 1);
             ok = d_bytes && d_boff && d_first && d_eoff;
             const double t0 = now_us();
-            ok = ok && cudaMemcpyAsync(d_bytes, bytes.data(), bytes.size(), cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
             ok = ok && cudaMemcpyAsync(d_boff, byte_off.data(), (nblocks + 1) * 8, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
-            ok = ok && cudaMemcpyAsync(d_first, first.data(), nblocks * 8, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(d_first, first, nblocks * 8, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
             ok = ok && cudaMemcpyAsync(d_eoff, entry_off.data(), (nblocks + 1) * 4, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
             ok = ok && ii_launch_decode(d_bytes, d_boff, d_first, d_eoff, (uint32_t)nblocks, (int)codec, d_ids, d_freqs, d_masks,
                                         c.stream) == cudaSuccess;
             ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
             c.stats.h2d_us = now_us() - t0;
-            c.stats.decode_host_us = 0;
             c.stats.kernel_launches += 1;
             dfree(d_bytes);
             dfree(d_boff);

@@ -134,6 +134,26 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t 
     return lo;
 }
 
+// lower_bound by a whole warp: 32 pivots per round instead of one dependent load per bisection step
+// (the probed list has up to 10^7 entries in HBM: 5 rounds of latency instead of 23)
+__device__ __forceinline__ uint32_t warp_lower_bound_u32(const uint32_t *a, uint32_t lo, uint32_t hi, uint32_t key, int lane) {
+    while (hi - lo > 32) {
+        const uint32_t span = hi - lo;
+        // pivots p_i = lo + (i+1)*span/33, i = 0..31 (strictly inside (lo, hi))
+        const uint32_t p = lo + (uint32_t)(((uint64_t)(lane + 1) * span) / 33);
+        const bool less = a[p] < key;
+        const uint32_t m = __ballot_sync(0xffffffffu, less);
+        const int nless = __popc(m); // pivots are ascending, so the set bits are a prefix
+        const uint32_t new_lo = nless ? __shfl_sync(0xffffffffu, p, nless - 1) + 1 : lo;
+        const uint32_t new_hi = nless < 32 ? __shfl_sync(0xffffffffu, p, nless) : hi;
+        lo = new_lo;
+        hi = new_hi;
+    }
+    const uint32_t idx = lo + lane;
+    const bool less = idx < hi && a[idx] < key;
+    return lo + __popc(__ballot_sync(0xffffffffu, less));
+}
+
 __global__ void __launch_bounds__(kIIThreads) intersect_kernel(const IntersectArgs a) {
     __shared__ uint32_t sB[kIISmemElems];
     __shared__ uint32_t s_lo, s_hi;
@@ -153,8 +173,11 @@ __global__ void __launch_bounds__(kIIThreads) intersect_kernel(const IntersectAr
     const uint32_t a_lo = A[start], a_hi = A[end - 1];
     for (uint32_t j = 1; j < a.n; j++) {
         const uint32_t *B = a.ids[j];
-        if (threadIdx.x == 0) s_lo = lower_bound_u32(B, 0, a.len[j], a_lo);
-        if (threadIdx.x == 32) s_hi = lower_bound_u32(B, 0, a.len[j], a_hi + 1u); // a_hi < 2^32-1
+        if (threadIdx.x < 64) { // warp 0 finds the window start, warp 1 its end
+            const bool first = threadIdx.x < 32;
+            const uint32_t r = warp_lower_bound_u32(B, 0, a.len[j], first ? a_lo : a_hi + 1u, threadIdx.x & 31); // a_hi < 2^32-1
+            if ((threadIdx.x & 31) == 0) *(first ? &s_lo : &s_hi) = r;
+        }
         __syncthreads();
         const uint32_t lo = s_lo, hi = s_hi, range = hi - lo;
         uint32_t *posj = a.tmp_pos + (size_t)j * a.stride;

@@ -306,3 +306,38 @@ def test_large_intersection_properties(ps):
     assert ids2.tobytes() == a.tobytes()
     u, _, _ = ps.union([pb, pc], quick_exit=True).fetch(want_freqs=False)
     assert u.tobytes() == np.union1d(b, c).astype(np.uint64).tobytes()
+
+
+def test_concurrent_worker_threads_get_their_own_stream(ps):
+    """RediSearch runs one iterator tree per worker thread; libii_b200 gives every calling thread its own
+    stream and staging.  Eight threads searching shared posting lists concurrently must each get the
+    single-threaded answer (ids, score bits, hit count)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    rng = np.random.default_rng(21)
+    n_docs = 3_000_000
+    sizes = [900_000, 400_000, 150_000, 60_000, 20_000, 5_000]
+    ids = [np.unique(rng.integers(1, n_docs, s)).astype(np.uint64) for s in sizes]
+    freqs = [rng.integers(1, 20, len(x)).astype(np.uint32) for x in ids]
+    pls = [ps.PostingList.from_arrays(x, f) for x, f in zip(ids, freqs)]
+    doc_len = rng.integers(50, 500, n_docs + 1).astype(np.uint32)
+    dt = ps.DocTable(n_docs, doc_len)
+    avg = float(doc_len[1:].mean())
+    queries = [(0, 1, 2), (0, 3), (1, 2, 4), (0, 1), (2, 3, 5), (0, 5), (1, 4), (0, 2, 3)]
+
+    def run(q):
+        terms = [(1.0, ps.lib().II_CalculateIDF(n_docs, len(ids[i])), ps.lib().II_CalculateIDF_BM25(n_docs, len(ids[i]))) for i in q]
+        return ps.search_topn([pls[i] for i in q], False, ps.SCORER_BM25STD, terms, 1.0, n_docs, avg, dt, 10)
+
+    expect = [run(q) for q in queries]
+    with ThreadPoolExecutor(max_workers=len(queries)) as pool:
+        for _ in range(5):
+            got = list(pool.map(run, queries))
+            for (gi, gs, gt), (ei, es, et) in zip(got, expect):
+                assert gi.tolist() == ei.tolist() and gs.tobytes() == es.tobytes() and gt == et
+    # and the sequential answers are the oracle's: hit counts equal numpy's intersection
+    for q, (_, _, tot) in zip(queries, expect):
+        ref = ids[q[0]]
+        for i in q[1:]:
+            ref = np.intersect1d(ref, ids[i])
+        assert tot == len(ref)
