@@ -194,6 +194,14 @@ const double *II_ResultSet_DeviceScores(const II_ResultSet *rs);
 size_t II_SearchTopN(II_PostingList *const *lists, size_t n, int is_union, II_Scorer scorer,
                      const II_TermParams *terms, double agg_weight, const II_IndexStats *stats,
                      const II_DocTable *docs, size_t top_n, uint64_t *doc_ids, double *scores, size_t *total_hits);
+/* `nq` independent searches in one call (the dispatch shim batches concurrent FT.SEARCHes the way
+ * VecSimB200_TopKQueryBatch batches KNN queries).  lists[i] / n_lists[i] / terms[i] describe query i; outputs are
+ * [nq][top_n] row-major, counts[i] = hits written for query i, total_hits[i] (optional) = size of its AND/OR.
+ * The queries are spread over a pool of 8 streams inside the library.  top_n <= 1024.  Returns 0, or -1 on a bad
+ * argument / missing device. */
+int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const size_t *n_lists, int is_union, II_Scorer scorer,
+                       const II_TermParams *const *terms, double agg_weight, const II_IndexStats *stats, const II_DocTable *docs,
+                       size_t top_n, uint64_t *doc_ids, double *scores, size_t *counts, size_t *total_hits);
 
 /* ---- QueryIterator facade ------------------------------------------------------------------------ */
 /* Takes ownership of `rs` (downloads docIds/scores once).  Free through it->Free(it). */

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -78,10 +79,19 @@ struct Ctx { // one per calling thread: own stream, events and pinned staging (R
         return true;
     }
 };
+// II_SearchTopNBatch runs its queries on a pool of contexts of its own; while one of those is current, every
+// helper below (dalloc / dfree / copy_sync, result-set destructors) uses its stream
+static thread_local Ctx *tl_ctx_override = nullptr;
 Ctx &ctx() {
+    if (tl_ctx_override) return *tl_ctx_override;
     static thread_local Ctx c;
     return c;
 }
+struct CtxScope {
+    Ctx *prev;
+    explicit CtxScope(Ctx *c) : prev(tl_ctx_override) { tl_ctx_override = c; }
+    ~CtxScope() { tl_ctx_override = prev; }
+};
 
 // Stream-ordered allocations from the device's default memory pool (kept warm: no cudaMalloc /
 // cudaFree on the query path).  Everything is allocated, used and freed in ctx().stream order.
@@ -621,6 +631,76 @@ size_t merge_topn_lists(const uint64_t *keys, const uint32_t *ids, size_t total,
     return kk;
 }
 
+// One fused search in flight on a context: everything enqueued, nothing waited for.
+struct PendingSearch {
+    bool active = false;
+    std::unique_ptr<II_ResultSet> rs;
+    uint64_t *h_keys = nullptr;
+    uint32_t *h_ids = nullptr;
+    size_t total = 0;
+    uint32_t k = 0;
+};
+
+// AND/OR -> score -> per-warp top-N lists -> D2H, all on c.stream; false (and nothing pending) if the answer is
+// trivially empty or a launch failed
+bool search_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int is_union, II_Scorer scorer, const II_TermParams *terms,
+                    double agg_weight, const II_IndexStats *stats, const II_DocTable *docs, size_t top_n, PendingSearch &p) {
+    p.active = false;
+    p.rs.reset(new II_ResultSet());
+    II_ResultSet &rs = *p.rs;
+    bool empty = false;
+    bool ok = is_union ? union_enqueue(c, lists, n, 0, &rs, &empty) : intersect_enqueue(c, lists, n, &rs, &empty);
+    if (!ok || empty) {
+        p.rs.reset();
+        return false;
+    }
+    const uint32_t k = (uint32_t)top_n;
+    const ScoreArgs sa = make_score_args(&rs, scorer, terms, agg_weight, stats, docs, 0.0, 4);
+    ok = ii_launch_score(sa, rs.d_docs, rs.d_freqs, rs.cap, rs.d_len, (uint32_t)rs.cap, rs.d_scores, c.stream) == cudaSuccess;
+    const uint32_t nl = ii_topn_lists((uint32_t)rs.cap);
+    const size_t total = (size_t)nl * k;
+    uint64_t *d_keys = dalloc<uint64_t>(total);
+    uint32_t *d_ids = dalloc<uint32_t>(total);
+    uint8_t *stg = c.stage(total * 12);
+    ok = ok && d_keys && d_ids && stg;
+    p.h_keys = reinterpret_cast<uint64_t *>(stg);
+    p.h_ids = reinterpret_cast<uint32_t *>(p.h_keys + total);
+    ok = ok && ii_launch_topn(rs.d_docs, rs.d_scores, rs.d_len, (uint32_t)rs.cap, k, d_keys, d_ids, c.stream) == cudaSuccess;
+    cudaEventRecord(c.e2, c.stream);
+    ok = ok && cudaMemcpyAsync(p.h_keys, d_keys, total * 8, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(p.h_ids, d_ids, total * 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c.h_total, rs.d_len, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    dfree(d_keys);
+    dfree(d_ids);
+    c.stats.kernel_launches += 2;
+    if (!ok) {
+        cudaStreamSynchronize(c.stream);
+        p.rs.reset();
+        return false;
+    }
+    p.total = total;
+    p.k = k;
+    p.active = true;
+    return true;
+}
+
+// wait for the context's stream and merge the per-warp lists on the host; must run with `c` current
+size_t search_finish(Ctx &c, PendingSearch &p, uint64_t *doc_ids, double *scores, size_t *total_hits) {
+    p.active = false;
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess) {
+        p.rs.reset();
+        return 0;
+    }
+    finish_len(c, p.rs.get());
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c.e1, c.e2) == cudaSuccess) c.stats.score_device_us = ms * 1000.0;
+    const size_t len = p.rs->len;
+    if (total_hits) *total_hits = len;
+    const size_t got = merge_topn_lists(p.h_keys, p.h_ids, p.total, std::min<size_t>(p.k, len), doc_ids, scores);
+    p.rs.reset(); // stream-ordered frees on c.stream
+    return got;
+}
+
 } // namespace
 
 II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n) {
@@ -796,38 +876,48 @@ size_t II_SearchTopN(II_PostingList *const *lists, size_t n, int is_union, II_Sc
     Ctx &c = ctx();
     std::lock_guard<std::mutex> g(c.mu);
     if (!c.init()) return 0;
-    II_ResultSet rs;
-    bool empty = false;
-    bool ok = is_union ? union_enqueue(c, lists, n, 0, &rs, &empty) : intersect_enqueue(c, lists, n, &rs, &empty);
-    if (!ok || empty) return 0;
-    const uint32_t k = (uint32_t)top_n;
-    const ScoreArgs sa = make_score_args(&rs, scorer, terms, agg_weight, stats, docs, 0.0, 4);
-    cudaEvent_t s0 = c.e1; // score timing starts where the intersection timing stopped
-    (void)s0;
-    ok = ii_launch_score(sa, rs.d_docs, rs.d_freqs, rs.cap, rs.d_len, (uint32_t)rs.cap, rs.d_scores, c.stream) == cudaSuccess;
-    const uint32_t nl = ii_topn_lists((uint32_t)rs.cap);
-    const size_t total = (size_t)nl * k;
-    uint64_t *d_keys = dalloc<uint64_t>(total);
-    uint32_t *d_ids = dalloc<uint32_t>(total);
-    uint8_t *stg = c.stage(total * 12);
-    ok = ok && d_keys && d_ids && stg;
-    uint64_t *h_keys = reinterpret_cast<uint64_t *>(stg);
-    uint32_t *h_ids = reinterpret_cast<uint32_t *>(h_keys + total);
-    ok = ok && ii_launch_topn(rs.d_docs, rs.d_scores, rs.d_len, (uint32_t)rs.cap, k, d_keys, d_ids, c.stream) == cudaSuccess;
-    cudaEventRecord(c.e2, c.stream);
-    ok = ok && cudaMemcpyAsync(h_keys, d_keys, total * 8, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(h_ids, d_ids, total * 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(c.h_total, rs.d_len, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
-    dfree(d_keys);
-    dfree(d_ids);
-    ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
-    c.stats.kernel_launches += 2;
-    if (!ok) return 0;
-    finish_len(c, &rs);
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, c.e1, c.e2) == cudaSuccess) c.stats.score_device_us = ms * 1000.0;
-    if (total_hits) *total_hits = rs.len;
-    return merge_topn_lists(h_keys, h_ids, total, std::min<size_t>(k, rs.len), doc_ids, scores);
+    PendingSearch p;
+    if (!search_enqueue(c, lists, n, is_union, scorer, terms, agg_weight, stats, docs, top_n, p)) return 0;
+    return search_finish(c, p, doc_ids, scores, total_hits);
+}
+
+// The same for `nq` independent queries (one FT.SEARCH each), with their kernels spread over a pool of streams:
+// query i+1 is enqueued while query i runs, and a slot is only synchronised when it is needed again — the
+// device sees up to kBatchSlots searches at once and the host pays one wait per slot, not one per kernel chain.
+int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const size_t *n_lists, int is_union, II_Scorer scorer,
+                       const II_TermParams *const *terms, double agg_weight, const II_IndexStats *stats, const II_DocTable *docs,
+                       size_t top_n, uint64_t *doc_ids, double *scores, size_t *counts, size_t *total_hits) {
+    constexpr size_t kBatchSlots = 8;
+    struct Pool {
+        std::mutex mu;
+        Ctx slot[kBatchSlots];
+    };
+    static Pool pool;
+    if (top_n == 0 || top_n > 1024) return -1;
+    std::lock_guard<std::mutex> g(pool.mu);
+    PendingSearch pend[kBatchSlots];
+    size_t owner[kBatchSlots];
+    auto finish = [&](size_t sl) {
+        CtxScope scope(&pool.slot[sl]);
+        const size_t qi = owner[sl];
+        size_t tot = 0;
+        counts[qi] = search_finish(pool.slot[sl], pend[sl], doc_ids + qi * top_n, scores + qi * top_n, &tot);
+        if (total_hits) total_hits[qi] = tot;
+    };
+    for (size_t i = 0; i < nq; i++) {
+        const size_t sl = i % kBatchSlots;
+        if (pend[sl].active) finish(sl);
+        counts[i] = 0;
+        if (total_hits) total_hits[i] = 0;
+        if (n_lists[i] == 0 || n_lists[i] > (size_t)kIIMaxLists) continue;
+        CtxScope scope(&pool.slot[sl]);
+        if (!pool.slot[sl].init()) return -1;
+        owner[sl] = i;
+        search_enqueue(pool.slot[sl], lists[i], n_lists[i], is_union, scorer, terms[i], agg_weight, stats, docs, top_n, pend[sl]);
+    }
+    for (size_t sl = 0; sl < kBatchSlots; sl++)
+        if (pend[sl].active) finish(sl);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -77,6 +77,7 @@ SIGNATURES = [
     ("II_ResultSet_DeviceScores", _P, [_P]),
     ("II_SearchTopN", _SZ, [_P, _SZ, C.c_int, C.c_int, C.POINTER(II_TermParams), C.c_double, C.POINTER(II_IndexStats), _P, _SZ,
                             _P, _P, C.POINTER(_SZ)]),
+    ("II_SearchTopNBatch", C.c_int, [_SZ, _P, _P, C.c_int, C.c_int, _P, C.c_double, C.POINTER(II_IndexStats), _P, _SZ, _P, _P, _P, _P]),
     ("II_NewResultIterator", _QI, [_P, C.c_double]),
     ("II_GetStats", II_Stats, [C.c_bool]),
     ("II_Version", C.c_char_p, []),
@@ -241,6 +242,38 @@ def search_topn(lists, is_union, scorer, terms, agg_weight, num_docs, avg_doc_le
     got = lib().II_SearchTopN(_list_array(lists), len(lists), int(is_union), scorer, arr, agg_weight, C.byref(st),
                               doc_table.h if doc_table else None, top_n, _ptr(ids), _ptr(scores), C.byref(total))
     return ids[:got], scores[:got], total.value
+
+
+class SearchBatch:
+    """Argument block of II_SearchTopNBatch, built once and reusable: queries = [(lists, terms), ...]."""
+
+    def __init__(self, queries, top_n):
+        self.nq, self.top_n = len(queries), top_n
+        self._keep = []
+        self.lists = (C.c_void_p * self.nq)()
+        self.terms = (C.c_void_p * self.nq)()
+        self.n_lists = (C.c_size_t * self.nq)()
+        for i, (lists, terms) in enumerate(queries):
+            la = _list_array(lists)
+            ta = (II_TermParams * len(terms))(*[II_TermParams(*t) for t in terms])
+            self._keep += [la, ta, lists]
+            self.lists[i] = C.cast(la, C.c_void_p)
+            self.terms[i] = C.cast(ta, C.c_void_p)
+            self.n_lists[i] = len(lists)
+        self.ids = np.zeros((self.nq, top_n), dtype=np.uint64)
+        self.scores = np.zeros((self.nq, top_n), dtype=np.float64)
+        self.counts = np.zeros(self.nq, dtype=np.uint64)
+        self.totals = np.zeros(self.nq, dtype=np.uint64)
+
+    def run(self, is_union, scorer, agg_weight, num_docs, avg_doc_len, doc_table):
+        st = II_IndexStats(num_docs, 0, avg_doc_len)
+        rc = lib().II_SearchTopNBatch(self.nq, self.lists, self.n_lists, int(is_union), scorer, self.terms, agg_weight, C.byref(st),
+                                      doc_table.h if hasattr(doc_table, "h") else doc_table, self.top_n, _ptr(self.ids),
+                                      _ptr(self.scores), _ptr(self.counts), _ptr(self.totals))
+        if rc != 0:
+            raise RuntimeError("II_SearchTopNBatch failed")
+        return [(self.ids[i, :int(self.counts[i])].copy(), self.scores[i, :int(self.counts[i])].copy(), int(self.totals[i]))
+                for i in range(self.nq)]
 
 
 def stats(reset=False) -> II_Stats:

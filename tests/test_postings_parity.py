@@ -335,6 +335,14 @@ def test_concurrent_worker_threads_get_their_own_stream(ps):
             got = list(pool.map(run, queries))
             for (gi, gs, gt), (ei, es, et) in zip(got, expect):
                 assert gi.tolist() == ei.tolist() and gs.tobytes() == es.tobytes() and gt == et
+    # the batch entry point (pool of streams inside the library) returns the same rows
+    batch = ps.SearchBatch([([pls[i] for i in q],
+                             [(1.0, ps.lib().II_CalculateIDF(n_docs, len(ids[i])), ps.lib().II_CalculateIDF_BM25(n_docs, len(ids[i]))) for i in q])
+                            for q in queries * 3], 10)
+    for _ in range(3):
+        got = batch.run(False, ps.SCORER_BM25STD, 1.0, n_docs, avg, dt)
+        for (gi, gs, gt), (ei, es, et) in zip(got, expect * 3):
+            assert gi.tolist() == ei.tolist() and gs.tobytes() == es.tobytes() and gt == et
     # and the sequential answers are the oracle's: hit counts equal numpy's intersection
     for q, (_, _, tot) in zip(queries, expect):
         ref = ids[q[0]]
