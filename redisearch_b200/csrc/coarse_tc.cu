@@ -78,17 +78,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
+// expires) instead of spinning — the pass runs at the 1000 W power cap, so idle polling costs clock
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done;
     do {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
             : "memory");
     } while (!done);
 }
@@ -171,6 +173,16 @@ __device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ss_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -460,9 +472,12 @@ coarse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 // shared memory only carries the streaming row tiles (2 KB per MMA instead of 6), a CTA serves 128
 // queries instead of 64 (half the L2->SM ingest), and in the epilogue a thread owns one QUERY: its
 // threshold lives in a register and its candidate list needs no atomics.
-//   TMEM columns: [0,128) the accumulator of a 128-row tile; [128, 128 + dim/2) the queries.  There is no room
-//   for a second accumulator, so the epilogue drains the tile to registers (4 x tcgen05.ld) and hands it back
-//   before it looks at a single value; only that drain is not overlapped with the MMAs of the next tile.
+//   TMEM columns: [0,256) two accumulator stages of a 128-row tile; [256,512) the first 8 K blocks (512 dims) of
+//   the queries.  K blocks beyond that live in shared memory (swizzled like the row tiles) and are multiplied in
+//   SS mode — 107 instead of 76 clk per MMA, but with a single accumulator the tensor pipe idled a third of the
+//   time while the epilogue drained it (ncu: 33% of the issuer's samples on the tempty barrier).
+//   The candidate lists live in global memory (L2): appends are rare once the thresholds have settled, and shared
+//   memory goes to the row-tile ring.
 // ------------------------------------------------------------------------------------------------
 constexpr int kQM = 128;            // queries per CTA
 constexpr int kQN = 128;            // rows per tile = N of one MMA (measured: N=64 58 clk, N=128 76 clk per instruction)
@@ -474,7 +489,8 @@ constexpr int kQListStride = 129;   // lists[slot * stride + query]: conflict-fr
 static_assert(kCoarseKeep <= 32, "publish_sorted ranks one kept entry per lane");
 constexpr uint32_t kQBlockBytes = kQN * 128;                    // one K block of a row tile: 128 rows x 128 bytes
 constexpr uint32_t kQStageBytes = kQKbPerStage * kQBlockBytes; // 32 KB
-constexpr uint32_t kQAccCols = kQN; // ONE accumulator: 128 columns are all that is left beside the queries
+constexpr uint32_t kQAccCols = 2 * kQN; // two accumulator stages
+constexpr uint32_t kQTmemKb = (512 - kQAccCols) / 32; // K blocks of the queries that fit in tensor memory (8 = 512 dims)
 
 // Cut list `q` (c entries, keep < c <= 96) back to its `keep` smallest, unordered, in slots [0, keep); returns the
 // key of the worst kept entry (the new admission threshold).  Warp-wide radix select on the 32-bit key — 32 rounds
@@ -482,6 +498,7 @@ constexpr uint32_t kQAccCols = kQN; // ONE accumulator: 128 columns are all that
 // epilogue's time and, worse, a stall of the accumulator hand-back).  Entries tied with the threshold key are
 // kept in slot order; the completeness proof only needs "every dropped key >= the returned key".
 __device__ __forceinline__ uint32_t select_keep(uint64_t *lists, int q, uint32_t c, uint32_t keep, int lane) {
+    __syncwarp(); // the list was appended to by one lane: order its (global-memory) writes before the warp's reads
     uint64_t e[3];
     uint32_t k[3];
     bool v[3];
@@ -551,13 +568,17 @@ __device__ __forceinline__ void publish_sorted(const uint64_t *lists, int q, uin
 __global__ void __launch_bounds__(kCoarseThreads, 1)
 coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restrict__ q16, size_t q16_pitch, uint32_t n_rows,
                     uint32_t nq, uint32_t dim, uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t nstages, uint32_t csize,
-                    uint64_t *__restrict__ cand_out) {
+                    uint32_t nacc, uint64_t *__restrict__ list_scratch, uint64_t *__restrict__ cand_out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *sB = smem;                                                                   // nstages x [64 x 128B]
-    uint64_t *lists = reinterpret_cast<uint64_t *>(sB + (size_t)nstages * kQStageBytes); // [kQListCap][kQListStride]
-    uint64_t *bars = lists + kQListCap * kQListStride;
-    uint64_t *full = bars, *empty = bars + kQMaxStages, *tfull = bars + 2 * kQMaxStages, *tempty = tfull + kAccStages; // [0] used
+    // K blocks of the queries in tensor memory (all 512 columns minus the nacc accumulator stages); the rest in sQ
+    const uint32_t kb_tmem = min(num_kb, (512u - nacc * kQN) / 32u);
+    uint8_t *sB = smem;                                            // nstages x kQKbPerStage x [128 x 128B]
+    uint8_t *sQ = sB + (size_t)nstages * kQStageBytes;             // (num_kb - kb_tmem) x [128 queries x 128B], swizzled
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sQ + (size_t)(num_kb - kb_tmem) * kQBlockBytes);
+    uint64_t *full = bars, *empty = bars + kQMaxStages, *tfull = bars + 2 * kQMaxStages, *tempty = tfull + kAccStages;
+    // this CTA's candidate lists [kQListCap][kQListStride]
+    uint64_t *lists = list_scratch + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (kQListCap * kQListStride);
     uint64_t *qbar = tempty + kAccStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(qbar + 1);
 
@@ -583,7 +604,7 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_q = tmem_base + kQAccCols;
+    const uint32_t tmem_q = tmem_base + nacc * kQN;
     // cluster mode: the csize CTAs that share blockIdx.x (one per group of 128 queries) walk the SAME row tiles.
     // Each fetches 1/csize of every stage and multicasts it into all csize shared memories, so a tile leaves
     // HBM/L2 once per cluster (measured without it: the query groups drift apart and every tile is read from HBM
@@ -624,26 +645,35 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
         tc_fence_after();
         uint32_t s = 0, ph = 0;
         for (uint32_t i = 0; i < my_tiles; i++) {
-            mbar_wait(&tempty[0], (i & 1) ^ 1);
+            const uint32_t a = i % nacc, aph = (i / nacc) & 1;
+            mbar_wait(&tempty[a], aph ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base;
+            const uint32_t d_tmem = tmem_base + a * kQN;
             for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kQKbPerStage) {
                 const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint64_t bdesc0 = make_smem_desc(smem_u32(sB + (size_t)s * kQStageBytes));
-                const uint32_t a_tmem0 = tmem_q + kb0 * 32;
                 if (elect_one_sync()) {
 #pragma unroll
                     for (uint32_t j = 0; j < (uint32_t)kQKbPerStage; j++) {
                         if (j < kbn) {
-                            // 16 halves per instruction = 8 TMEM columns of Q, 32 bytes of the swizzled row
+                            const uint32_t kb = kb0 + j;
+                            // 16 halves per instruction: 32 bytes of the swizzled row tile
                             const uint64_t bdesc = bdesc0 + (uint64_t)(j * (kQBlockBytes >> 4));
-                            const uint32_t a_tmem = a_tmem0 + j * 32;
-                            umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, (kb0 | j) != 0);
-                            umma_ts_f16(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
-                            umma_ts_f16(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
-                            umma_ts_f16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
+                            if (kb < kb_tmem) { // queries from tensor memory: 8 columns per instruction
+                                const uint32_t a_tmem = tmem_q + kb * 32;
+                                umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, kb != 0);
+                                umma_ts_f16(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
+                                umma_ts_f16(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
+                                umma_ts_f16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
+                            } else { // queries from shared memory
+                                const uint64_t adesc = make_smem_desc(smem_u32(sQ + (size_t)(kb - kb_tmem) * kQBlockBytes));
+                                umma_ss_f16(d_tmem, adesc, bdesc, idesc, 1);
+                                umma_ss_f16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                                umma_ss_f16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                                umma_ss_f16(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                            }
                         }
                     }
                     if (csize > 1)
@@ -654,7 +684,7 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
                 __syncwarp();
                 if (++s == nstages) s = 0, ph ^= 1;
             }
-            if (elect_one_sync()) umma_commit(&tfull[0]);
+            if (elect_one_sync()) umma_commit(&tfull[a]);
             __syncwarp();
         }
     } else if (warp >= 4) {
@@ -666,15 +696,24 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
         {
             const uint4 *src = reinterpret_cast<const uint4 *>(q16 + (size_t)q * q16_pitch);
             for (uint32_t kb = 0; kb < num_kb; kb++) {
-                uint32_t w[32];
+                uint4 x[8];
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
-                    uint4 x = make_uint4(0, 0, 0, 0);
-                    if (q < nq && kb * 64 + u * 8 < dim) x = src[kb * 8 + u];
-                    w[u * 4 + 0] = x.x, w[u * 4 + 1] = x.y, w[u * 4 + 2] = x.z, w[u * 4 + 3] = x.w;
+                    x[u] = make_uint4(0, 0, 0, 0);
+                    if (q < nq && kb * 64 + u * 8 < dim) x[u] = src[kb * 8 + u];
                 }
-                tmem_st32(tmem_q + lane_addr + kb * 32, w);
+                if (kb < kb_tmem) {
+                    uint32_t w[32];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) w[u * 4 + 0] = x[u].x, w[u * 4 + 1] = x[u].y, w[u * 4 + 2] = x[u].z, w[u * 4 + 3] = x[u].w;
+                    tmem_st32(tmem_q + lane_addr + kb * 32, w);
+                } else { // row `et` of a K-major 128B-swizzled operand tile: chunk c at et*128 + ((c ^ (et & 7)) * 16)
+                    uint8_t *row = sQ + (size_t)(kb - kb_tmem) * kQBlockBytes + et * 128;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) *reinterpret_cast<uint4 *>(row + ((u ^ (et & 7)) * 16)) = x[u];
+                }
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes of sQ -> tensor-core reads
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(qbar);
@@ -684,16 +723,16 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
         float thr_dot = -__int_as_float(0x7f800000); // -inf: everything passes until the first compaction
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t tile = blockIdx.x + i * gridDim.x;
-            mbar_wait(&tfull[0], i & 1);
+            const uint32_t a = i % nacc, aph = (i / nacc) & 1;
+            mbar_wait(&tfull[a], aph);
             tc_fence_after();
-            // drain the whole tile to registers and hand the accumulator back at once: the MMAs of the next tile
-            // overlap the selection below
+            // drain the whole tile to registers and hand the accumulator stage back before looking at a value
             uint32_t v[kQN / 32][32];
 #pragma unroll
-            for (int h = 0; h < kQN / 32; h++) tmem_ld32_nowait(tmem_base + lane_addr + h * 32, v[h]);
+            for (int h = 0; h < kQN / 32; h++) tmem_ld32_nowait(tmem_base + lane_addr + a * kQN + h * 32, v[h]);
             tmem_wait_ld();
             tc_fence_before();
-            mbar_arrive(&tempty[0]);
+            mbar_arrive(&tempty[a]);
 #pragma unroll
             for (int h = 0; h < kQN / 32; h++) {
                 const uint32_t row0 = tile * kQN + h * 32;
@@ -857,13 +896,26 @@ static bool make_map(CUtensorMap *m, CUtensorMapDataType dt, const void *base, u
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+
 static constexpr size_t kSmemLimit = 232448; // 227 KB opt-in maximum per CTA on sm_100
 
-static size_t qtmem_fixed_smem() {
-    return 1024 + (size_t)kQListCap * kQListStride * 8 + (2 * kQMaxStages + 2 * kAccStages + 1) * 8 + 64;
+// accumulator stages: 2 (default) leaves 8 query K blocks in tensor memory and puts the rest in shared memory
+// (SS-mode MMAs); 1 keeps up to 12 there but serialises the accumulator drain.  VECSIM_B200_ACC overrides.
+static uint32_t qtmem_nacc() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("VECSIM_B200_ACC");
+        v = (e && atoi(e) == 1) ? 1 : 2;
+    }
+    return (uint32_t)v;
 }
-// fp16 with the queries in tensor memory: 128 accumulator columns + dim/2 query columns must fit 512
-static bool qtmem_fits(uint32_t dim) { return kQAccCols + ((dim + 63) / 64) * 32 <= 512; }
+static size_t qtmem_fixed_smem(uint32_t num_kb) {
+    const uint32_t kb_t = (512u - qtmem_nacc() * kQN) / 32u;
+    const uint32_t kb_smem = num_kb > kb_t ? num_kb - kb_t : 0; // query K blocks that do not fit tensor memory
+    return 1024 + (size_t)kb_smem * kQBlockBytes + (2 * kQMaxStages + 2 * kAccStages + 1) * 8 + 64;
+}
+// fp16 with the queries in tensor memory (first 512 dims) + shared memory (the rest): keep >= 4 ring stages
+static bool qtmem_fits(uint32_t dim) { return qtmem_fixed_smem((dim + 63) / 64) + 4 * (size_t)kQStageBytes <= kSmemLimit; }
 
 static size_t fixed_smem(uint32_t num_kb) {
     const uint32_t tn = CfgTF32::kTileN;
@@ -891,8 +943,8 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind) {
         const uint32_t sms = (uint32_t)device_sm_count();
         p.grid_x = std::max(1u, std::min(p.tiles, sms / p.grid_y));
         p.keep = kCoarseKeep;
-        p.stages = (uint32_t)std::min<size_t>(kQMaxStages, (kSmemLimit - qtmem_fixed_smem()) / kQStageBytes);
-        p.smem_bytes = qtmem_fixed_smem() + (size_t)p.stages * kQStageBytes;
+        p.stages = (uint32_t)std::min<size_t>(kQMaxStages, (kSmemLimit - qtmem_fixed_smem(p.num_kb)) / kQStageBytes);
+        p.smem_bytes = qtmem_fixed_smem(p.num_kb) + (size_t)p.stages * kQStageBytes;
         // the query groups of a row range form a thread-block cluster (multicast of the row tiles)
         p.csize = 1;
         static int ccap = -1; // VECSIM_B200_CLUSTER caps the cluster size (1 = no clusters)
@@ -925,6 +977,7 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind) {
             }
         }
         p.cand_elems = (size_t)nq * p.grid_x * p.keep;
+        p.scratch_elems = (size_t)p.grid_x * p.grid_y * kQListCap * kQListStride;
         return p;
     }
     const uint32_t bk = CfgTF32::kBlockK, tn = CfgTF32::kTileN;
@@ -956,7 +1009,7 @@ static cudaError_t launch_coarse_t(const void *rows, size_t pitch, uint32_t n_ro
 }
 
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
-                          cudaStream_t s) {
+                          uint64_t *d_scratch, cudaStream_t s) {
     if (p.kind == CoarseF16) {
         cudaError_t e = cudaFuncSetAttribute(coarse_qtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
         if (e != cudaSuccess) return e;
@@ -970,7 +1023,7 @@ cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim
         at[0].val.clusterDim.x = 1, at[0].val.clusterDim.y = p.csize, at[0].val.clusterDim.z = 1;
         cfg.attrs = at, cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, coarse_qtmem_kernel, static_cast<const uint8_t *>(o.rows), static_cast<const uint8_t *>(o.queries),
-                                  o.qpitch, n_rows, nq, dim, p.num_kb, p.tiles, p.keep, p.stages, p.csize, d_cand);
+                                  o.qpitch, n_rows, nq, dim, p.num_kb, p.tiles, p.keep, p.stages, p.csize, qtmem_nacc(), d_scratch, d_cand);
     }
     return launch_coarse_t<CfgTF32>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);
 }

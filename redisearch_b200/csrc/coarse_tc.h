@@ -25,6 +25,7 @@ struct CoarsePlan {
     uint32_t stages; // depth of the row-tile ring in shared memory
     uint32_t csize;  // thread-block cluster size along y (query groups sharing multicast row tiles); 1 = none
     size_t cand_elems; // uint64 per (query, list, keep)
+    size_t scratch_elems; // uint64 of per-CTA candidate-list scratch (CoarseF16), 0 otherwise
     size_t smem_bytes;
 };
 
@@ -38,7 +39,7 @@ struct CoarseOperands {
 bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind kind);
 CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind);
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
-                          cudaStream_t s);
+                          uint64_t *d_scratch, cudaStream_t s);
 // fp32 rows [first, first+n) -> the tiled fp16 shadow copy read by the CoarseF16 kernel (layout in coarse_tc.cu);
 // the buffer holds coarse_shadow_bytes(capacity_rows, dim) bytes
 size_t coarse_shadow_bytes(uint32_t rows, uint32_t dim);

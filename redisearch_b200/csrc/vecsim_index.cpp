@@ -711,11 +711,12 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     const size_t nA = (size_t)nq * per_query, nO = (size_t)nq * ke;
     const size_t q16_pitch = (dim_ * 2 + 15) & ~(size_t)15;
     const size_t q16_elems = kind == CoarseF16 ? ((size_t)nq * q16_pitch + 7) / 8 : 0;
-    const size_t total = 2 * nA + 2 * nO + sp.cand_elems + q16_elems + (nq + 1) / 2 + 8;
+    const size_t total = 2 * nA + 2 * nO + sp.cand_elems + q16_elems + cp.scratch_elems + (nq + 1) / 2 + 8;
     if (!c.need_cand(total) || !c.need_out(nO)) return false;
     uint64_t *coarse_cand = c.d_cand, *exact = coarse_cand + nA, *out1 = exact + nA, *out2 = out1 + nO, *cand2 = out2 + nO;
     uint64_t *q16 = cand2 + sp.cand_elems;
-    uint32_t *d_ok = reinterpret_cast<uint32_t *>(q16 + q16_elems);
+    uint64_t *list_scratch = q16 + q16_elems;
+    uint32_t *d_ok = reinterpret_cast<uint32_t *>(list_scratch + cp.scratch_elems);
     c.d_last_ok = d_ok;
     c.last_ok_n = nq;
     CoarseOperands ops{v.rows, v.pitch, d_q, qpitch};
@@ -726,7 +727,7 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         lc.launches++;
     }
     cudaEventRecord(c.ev_start, st);
-    ok = ok && launch_coarse(ops, v.n_rows, v.dim, nq, cp, coarse_cand, st) == cudaSuccess;
+    ok = ok && launch_coarse(ops, v.n_rows, v.dim, nq, cp, coarse_cand, list_scratch, st) == cudaSuccess;
     cudaEventRecord(c.ev_stop, st);
     ok = ok && launch_rescore(v, d_q, qpitch, nq, (uint32_t)per_query, coarse_cand, exact, st) == cudaSuccess;
     ok = ok && launch_final_select(exact, nq, (uint32_t)per_query, ke, out1, st, &lc) == cudaSuccess;
