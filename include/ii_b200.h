@@ -203,6 +203,13 @@ int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const siz
                        const II_TermParams *const *terms, double agg_weight, const II_IndexStats *stats, const II_DocTable *docs,
                        size_t top_n, uint64_t *doc_ids, double *scores, size_t *counts, size_t *total_hits);
 
+/* Multi-GPU: postings are sharded by docId range with the same boundaries as the vector rows; every
+ * shard runs II_SearchTopN on its slice with the GLOBAL statistics (numDocs, avgDocLen, per-term idf), and the
+ * coordinator merges the per-shard lists — what src/module.c:3139-3176 does with per-shard replies.  scores / doc_ids
+ * are [num_shards][per_shard], counts[g] entries valid; writes the best n by (score desc, docId asc), returns how many. */
+size_t II_MergeShardTopN(const double *scores, const uint64_t *doc_ids, const size_t *counts, size_t num_shards, size_t per_shard,
+                         size_t n, uint64_t *out_ids, double *out_scores);
+
 /* ---- QueryIterator facade ------------------------------------------------------------------------ */
 /* Takes ownership of `rs` (downloads docIds/scores once).  Free through it->Free(it). */
 II_QueryIterator *II_NewResultIterator(II_ResultSet *rs, double weight);

@@ -1019,6 +1019,24 @@ II_Stats II_GetStats(bool reset) {
     if (reset) c.stats = II_Stats{};
     return s;
 }
+// Coordinator-side merge of per-shard top-N lists (postings sharded by docId range): the shards'
+// lists are disjoint in docId, so the global top-N by cmpByScore (score desc, docId asc —
+// src/result_processor.c:834-850) is the top-N of their union.  Host code, no device needed.
+size_t II_MergeShardTopN(const double *scores, const uint64_t *doc_ids, const size_t *counts, size_t num_shards, size_t per_shard,
+                         size_t n, uint64_t *out_ids, double *out_scores) {
+    std::vector<std::pair<double, uint64_t>> all;
+    for (size_t g = 0; g < num_shards; g++)
+        for (size_t i = 0; i < std::min(counts[g], per_shard); i++) all.emplace_back(scores[g * per_shard + i], doc_ids[g * per_shard + i]);
+    const size_t k = std::min(n, all.size());
+    std::partial_sort(all.begin(), all.begin() + k, all.end(), [](const std::pair<double, uint64_t> &a, const std::pair<double, uint64_t> &b) {
+        return a.first > b.first || (a.first == b.first && a.second < b.second);
+    });
+    for (size_t i = 0; i < k; i++) {
+        out_scores[i] = all[i].first;
+        out_ids[i] = all[i].second;
+    }
+    return k;
+}
 const char *II_Version(void) { return "ii_b200 0.1 (sm_100a)"; }
 
 } // extern "C"

@@ -78,6 +78,7 @@ SIGNATURES = [
     ("II_SearchTopN", _SZ, [_P, _SZ, C.c_int, C.c_int, C.POINTER(II_TermParams), C.c_double, C.POINTER(II_IndexStats), _P, _SZ,
                             _P, _P, C.POINTER(_SZ)]),
     ("II_SearchTopNBatch", C.c_int, [_SZ, _P, _P, C.c_int, C.c_int, _P, C.c_double, C.POINTER(II_IndexStats), _P, _SZ, _P, _P, _P, _P]),
+    ("II_MergeShardTopN", _SZ, [_P, _P, _P, _SZ, _SZ, _SZ, _P, _P]),
     ("II_NewResultIterator", _QI, [_P, C.c_double]),
     ("II_GetStats", II_Stats, [C.c_bool]),
     ("II_Version", C.c_char_p, []),

@@ -6,6 +6,11 @@ rows), scans its shard, and the per-shard top-k lists are exchanged with ONE all
 VS/utils/query_result_utils.h:19-23).  Exactness: the global top-k is a subset of the union of the local
 top-k lists.  torch.distributed is plumbing only; the merge itself is a CUDA kernel
 (VecSimB200_MergeShardTopK).
+
+Posting lists shard by docId range with the same boundaries: shard g owns docIds
+(g*N/G, (g+1)*N/G]; every list is cut at the boundaries, each rank evaluates AND/OR + scorer + top-N on its slice
+with the GLOBAL statistics, and the per-shard top-N lists are exchanged with one all-gather and merged by
+`(score desc, docId asc)` (II_MergeShardTopN).
 """
 import ctypes as C
 
@@ -52,3 +57,52 @@ def merge_topk_device(gath_scores, gath_labels, stream_ptr=None):
     if rc != 0:
         raise RuntimeError("VecSimB200_MergeShardTopK failed")
     return out_s, out_l
+
+
+# ------------------------------------------------------------------------------------------------
+# postings
+# ------------------------------------------------------------------------------------------------
+def doc_range(n_docs: int, world: int, rank: int):
+    """docIds are 1..n_docs; shard g owns (lo, hi] with the row-shard boundaries."""
+    return shard_range(n_docs, world, rank)
+
+
+def split_posting_list(doc_ids, freqs, lo: int, hi: int):
+    """Slice of an ascending docId array (and its freqs) inside (lo, hi] — binary search on the boundaries."""
+    import numpy as np
+
+    a = int(np.searchsorted(doc_ids, lo, side="right"))
+    b = int(np.searchsorted(doc_ids, hi, side="right"))
+    return doc_ids[a:b], (freqs[a:b] if freqs is not None else None)
+
+
+def allgather_topn(scores, doc_ids, count: int, group=None):
+    """This rank's top-N (scores f64 [n], docIds i64 [n], `count` valid) -> ([G,n], [G,n], [G]) on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    cnt = torch.tensor([count], dtype=torch.int64, device=scores.device)
+    ls = [torch.empty_like(scores) for _ in range(world)]
+    li = [torch.empty_like(doc_ids) for _ in range(world)]
+    lc = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(ls, scores.contiguous(), group=group)
+    dist.all_gather(li, doc_ids.contiguous(), group=group)
+    dist.all_gather(lc, cnt, group=group)
+    return torch.stack(ls), torch.stack(li), torch.cat(lc)
+
+
+def merge_topn(gath_scores, gath_ids, counts, n: int):
+    """[G,per] gathered per-shard lists -> global top-n (ids uint64, scores f64) with II_MergeShardTopN."""
+    import numpy as np
+
+    from . import postings
+
+    sc = np.ascontiguousarray(gath_scores.cpu().numpy(), dtype=np.float64)
+    ids = np.ascontiguousarray(gath_ids.cpu().numpy()).astype(np.uint64)
+    cn = np.ascontiguousarray(counts.cpu().numpy()).astype(np.uint64)
+    out_i = np.zeros(n, dtype=np.uint64)
+    out_s = np.zeros(n, dtype=np.float64)
+    got = postings.lib().II_MergeShardTopN(sc.ctypes.data, ids.ctypes.data, cn.ctypes.data, sc.shape[0], sc.shape[1], n,
+                                           out_i.ctypes.data, out_s.ctypes.data)
+    return out_i[:got], out_s[:got]

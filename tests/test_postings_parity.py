@@ -349,3 +349,38 @@ def test_concurrent_worker_threads_get_their_own_stream(ps):
         for i in q[1:]:
             ref = np.intersect1d(ref, ids[i])
         assert tot == len(ref)
+
+
+def test_docid_range_shards_merge_to_the_unsharded_topn(ps):
+    """SURVEY.md §8e on one GPU: cut every list at the shard boundaries, search each slice with the global
+    statistics, merge with II_MergeShardTopN — identical to searching the whole lists."""
+    from redisearch_b200 import sharding
+
+    rng = np.random.default_rng(31)
+    n_docs, top = 2_000_000, 25
+    lists = [np.unique(rng.integers(1, n_docs + 1, m)).astype(np.uint64) for m in (700_000, 250_000, 1_100_000)]
+    freqs = [rng.integers(1, 12, len(l)).astype(np.uint32) for l in lists]
+    doc_len = rng.integers(50, 500, n_docs + 1).astype(np.uint32)
+    avg = float(doc_len[1:].mean())
+    dt = ps.DocTable(n_docs, doc_len)
+    terms = [(1.0, ps.lib().II_CalculateIDF(n_docs, len(l)), ps.lib().II_CalculateIDF_BM25(n_docs, len(l))) for l in lists]
+    whole = [ps.PostingList.from_arrays(l, f) for l, f in zip(lists, freqs)]
+    e_ids, e_sc, e_tot = ps.search_topn(whole, False, ps.SCORER_BM25STD, terms, 1.0, n_docs, avg, dt, top)
+    for world in (2, 3, 8):
+        sc = np.full((world, top), np.nan)
+        ids = np.zeros((world, top), dtype=np.uint64)
+        cnt = np.zeros(world, dtype=np.uint64)
+        total = 0
+        for g in range(world):
+            lo, hi = sharding.doc_range(n_docs, world, g)
+            sl = [sharding.split_posting_list(l, f, lo, hi) for l, f in zip(lists, freqs)]
+            pls = [ps.PostingList.from_arrays(l, f) for l, f in sl]
+            gi, gs, gt = ps.search_topn(pls, False, ps.SCORER_BM25STD, terms, 1.0, n_docs, avg, dt, top)
+            ids[g, :len(gi)], sc[g, :len(gi)], cnt[g] = gi, gs, len(gi)
+            total += gt
+        out_i = np.zeros(top, dtype=np.uint64)
+        out_s = np.zeros(top, dtype=np.float64)
+        got = ps.lib().II_MergeShardTopN(sc.ctypes.data, ids.ctypes.data, cnt.ctypes.data, world, top, top, out_i.ctypes.data,
+                                         out_s.ctypes.data)
+        assert total == e_tot and got == len(e_ids)
+        assert out_i[:got].tolist() == e_ids.tolist() and out_s[:got].tobytes() == e_sc.tobytes()

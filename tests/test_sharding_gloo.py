@@ -70,6 +70,70 @@ def test_two_rank_gloo_exchange_and_merge(tmp_path):
     assert "SHARDING-OK" in r.stdout
 
 
+POSTINGS_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+import oracle_lib as ol
+from redisearch_b200 import sharding
+
+def local_topn(lists, freqs, terms, doc_len, n_docs, avg, n):
+    """AND + BM25STD + top-n of this shard's slices, on the CPU oracle (the GPU does this step in production)."""
+    idx = [ol.InvIndex(ol.CODEC_FREQS_ONLY, l, f) for l, f in zip(lists, freqs)]
+    hits = ol.run_intersect(idx) if all(len(l) for l in lists) else []
+    scored = []
+    for doc, ch in hits:
+        s = ol.oracle_score(ol.SCORER_BM25STD, [f for _, f in ch], [terms[c][1] for c, _ in ch], [terms[c][2] for c, _ in ch],
+                            [1.0] * len(ch), 1.0, int(doc_len[doc]), 1, 1.0, n_docs, avg)
+        scored.append((-s, doc))
+    scored.sort()
+    return [(d, -s) for s, d in scored[:n]], len(hits)
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(3)                      # same stream on every rank: the GLOBAL index
+n_docs, TOP = 60_000, 10
+lists = [np.unique(rng.integers(1, n_docs + 1, m)).astype(np.uint64) for m in (30_000, 12_000, 20_000)]
+freqs = [rng.integers(1, 9, len(l)).astype(np.uint32) for l in lists]
+doc_len = rng.integers(50, 500, n_docs + 1).astype(np.uint32)
+avg = float(doc_len[1:].mean())
+# statistics are global: idf from the full lists, avgDocLen over all documents
+terms = [(1.0, ol.postings().orc_idf(n_docs, len(l)), ol.postings().orc_idf_bm25(n_docs, len(l))) for l in lists]
+lo, hi = sharding.doc_range(n_docs, world, rank)
+mine = [sharding.split_posting_list(l, f, lo, hi) for l, f in zip(lists, freqs)]
+assert all((len(l) == 0 or (l[0] > lo and l[-1] <= hi)) for l, _ in mine)
+top, nhits = local_topn([l for l, _ in mine], [f for _, f in mine], terms, doc_len, n_docs, avg, TOP)
+sc = torch.full((TOP,), float("nan"), dtype=torch.float64); ids = torch.full((TOP,), -1, dtype=torch.int64)
+for i, (d, s) in enumerate(top):
+    sc[i], ids[i] = s, d
+gs, gi, gc = sharding.allgather_topn(sc, ids, len(top))
+m_ids, m_sc = sharding.merge_topn(gs, gi, gc, TOP)
+tot = torch.tensor([nhits]); dist.all_reduce(tot)
+if rank == 0:
+    full, full_hits = local_topn(lists, freqs, terms, doc_len, n_docs, avg, TOP)
+    assert int(tot.item()) == full_hits
+    assert m_ids.tolist() == [d for d, _ in full], (m_ids, full)
+    assert m_sc.tobytes() == np.array([s for _, s in full], dtype=np.float64).tobytes()
+    print("POSTINGS-SHARDING-OK")
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_posting_shards(tmp_path):
+    """Postings sharded by docId range (SURVEY.md §8e): per-shard AND + BM25STD + top-N with global statistics,
+    one all-gather, II_MergeShardTopN — must equal the unsharded answer (ids and score bits)."""
+    script = tmp_path / "pworker.py"
+    script.write_text(f"ROOT = {ROOT!r}\n" + POSTINGS_WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "POSTINGS-SHARDING-OK" in r.stdout
+
+
 def test_shard_ranges_partition_exactly():
     sys.path.insert(0, ROOT)
     from redisearch_b200 import sharding
