@@ -418,6 +418,15 @@ VecSimB200_Stats VecSimB200_GetStats(VecSimIndex *index, bool reset);
  * (score,label) pairs, out = [nq][k]. */
 int VecSimB200_MergeShardTopK(const float *d_scores, const int64_t *d_labels, size_t G, size_t nq,
                               size_t k, float *d_out_scores, int64_t *d_out_labels, void *stream);
+/* Hybrid "filter AND KNN" in ad-hoc mode, fused: what HybridIterator does in HYBRID_ADHOC_BF mode
+ * (src/iterators/hybrid_reader.c:289-335: read the child iterator's docIds in ascending order, GetDistanceFrom each,
+ * keep the k best in a heap with strict `<` admission, skip NaN = deleted) — in one call.  doc_ids: the filter's
+ * ascending docIds (= vector labels), on the host or on the device (ids_on_device != 0, e.g.
+ * II_ResultSet_DeviceDocIds of the filter's AND/OR).  Writes up to k (label, distance) pairs ordered by
+ * (distance asc, docId asc) and their number.  Returns 0; -2 if the index cannot serve it (multi-value index, or
+ * labels too sparse for the dense docId -> row table) — the caller then stays on VecSimIndex_GetDistanceFrom_Unsafe. */
+int VecSimB200_TopKFiltered(VecSimIndex *index, const void *queryBlob, size_t k, const uint32_t *doc_ids, size_t n, int ids_on_device,
+                            size_t *out_labels, double *out_scores, size_t *out_count);
 /* Batched fp32 cosine queries (nq >= 16, k <= 16, dim % 8 == 0, >= 65536 rows) take a tcgen05 coarse
  * pass + exact rescoring from the fp32 rows + a per-query completeness proof, with the exact scan as
  * on-device fallback (csrc/coarse_tc.cu); results are identical either way.  mode: 0 = exact scans only,

@@ -206,6 +206,7 @@ FlatIndex::~FlatIndex() {
     }
     cudaFree(d_rows_);
     cudaFree(d_shadow_);
+    cudaFree(d_label_to_id_);
     cudaFree(d_id_to_label_);
     cudaFreeHost(h_stage_);
 }
@@ -354,6 +355,7 @@ int FlatIndex::add(const void *blob, size_t label) {
     else
         label_to_id_[label] = id;
     labels_dirty_ = true;
+    l2i_dirty_ = true;
     return 1;
 }
 
@@ -385,6 +387,7 @@ int FlatIndex::add_bulk_device(const void *d_src, size_t n, size_t label0) {
     count_ += n;
     resident_ = count_;
     labels_dirty_ = true;
+    l2i_dirty_ = true;
     return (int)n;
 }
 
@@ -430,6 +433,7 @@ int FlatIndex::remove(size_t label) {
     cudaStreamSynchronize(copy_stream_);
     resident_ = count_;
     labels_dirty_ = true;
+    l2i_dirty_ = true;
     return removed;
 }
 
@@ -1123,6 +1127,92 @@ void FlatIndex::adhoc_distances(AdhocCtx *a, const size_t *labels, double *out, 
         double &o = out[owner[i]];
         if (std::isnan(o) || d < o) o = d;
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// fused hybrid ad-hoc query (HybridIterator in HYBRID_ADHOC_BF mode, src/iterators/hybrid_reader.c:289-335:
+// child docIds in ascending order -> GetDistanceFrom each -> heap of the k best, strict `<` admission, NaN = deleted)
+// ------------------------------------------------------------------------------------------------
+bool FlatIndex::sync_label_table() {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!l2i_dirty_ && d_label_to_id_) return true;
+    size_t max_label = 0;
+    for (size_t i = 0; i < count_; i++) max_label = std::max(max_label, id_to_label_[i]);
+    if (max_label > 4 * count_ + (1u << 24) || max_label >= 0xFFFFFFFFull) return false; // sparse labels: no dense table
+    const size_t size = max_label + 1;
+    std::vector<uint32_t> tab(size, 0xFFFFFFFFu);
+    for (size_t i = 0; i < count_; i++) tab[id_to_label_[i]] = (uint32_t)i;
+    if (size > l2i_cap_) {
+        cudaFree(d_label_to_id_);
+        d_label_to_id_ = nullptr;
+        const size_t cap = size + size / 4 + 1024;
+        CU_OK(cudaMalloc(&d_label_to_id_, cap * 4));
+        l2i_cap_ = cap;
+    }
+    CU_OK(cudaMemcpy(d_label_to_id_, tab.data(), size * 4, cudaMemcpyHostToDevice));
+    l2i_size_ = size;
+    l2i_dirty_ = false;
+    return true;
+}
+
+int FlatIndex::topk_filtered(const void *q, size_t k, const uint32_t *doc_ids, size_t n, bool ids_on_device, size_t *out_labels,
+                             double *out_scores, size_t *out_count) {
+    *out_count = 0;
+    last_mode_ = HYBRID_ADHOC_BF;
+    if (k == 0 || n == 0) return 0;
+    if (multi_ || n > 0xFFFFFFF0ull) return -2;
+    if (!flush()) return -1;
+    if (count_ == 0) return 0;
+    if (!sync_label_table()) return -2;
+    auto c = checkout();
+    if (!c) return -1;
+    const size_t qpitch = (stored_bytes_ + 15) & ~(size_t)15;
+    LaunchCounters lc;
+    bool ok = c->need_query(qpitch) && c->need_ids(2 * n + 256) && c->need_scores(n);
+    if (ok) {
+        memset(c->h_query, 0, qpitch);
+        preprocess_query(q, c->h_query);
+        ok = upload_query(*c, c->h_query, 1);
+    }
+    // d_ids: [0,n) row ids, [n,2n) the labels when they arrive from the host
+    const uint32_t *d_labels = doc_ids;
+    if (ok && !ids_on_device) {
+        ok = cudaMemcpyAsync(c->d_ids + n, doc_ids, n * 4, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+        d_labels = c->d_ids + n;
+    }
+    ok = ok && launch_map_labels(d_labels, (uint32_t)n, d_label_to_id_, (uint32_t)l2i_size_, c->d_ids, c->stream, &lc) == cudaSuccess;
+    ok = ok && launch_gather_distances(view(), c->d_query, c->d_ids, (uint32_t)n, c->d_scores, c->stream, &lc) == cudaSuccess;
+    launches_total_ += lc.launches;
+    if (!ok) {
+        checkin(std::move(c));
+        return -1;
+    }
+    // k best positions by (distance asc, position asc) = (distance, docId): NaN (deleted docs) sort last and are dropped
+    const size_t want = std::min(k, n);
+    const long got = select_from_scores(*c, (uint32_t)n, false, 0, want);
+    if (got < 0) {
+        checkin(std::move(c));
+        return -1;
+    }
+    LaunchCounters lc2;
+    uint32_t *d_sel = c->d_ids; // row ids are no longer needed
+    ok = launch_pick_labels(c->d_out, (uint32_t)got, d_labels, d_sel, c->stream, &lc2) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->h_ids, d_sel, (size_t)got * 4, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    launches_total_ += lc2.launches;
+    size_t w = 0;
+    if (ok)
+        for (long i = 0; i < got; i++) {
+            const float d = key_to_float((uint32_t)(c->h_out[i] >> 32));
+            if (std::isnan(d)) continue;
+            out_labels[w] = c->h_ids[i];
+            out_scores[w] = (double)d;
+            w++;
+        }
+    *out_count = w;
+    checkin(std::move(c));
+    return ok ? 0 : -1;
 }
 
 // ------------------------------------------------------------------------------------------------

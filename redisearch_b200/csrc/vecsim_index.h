@@ -124,6 +124,9 @@ class FlatIndex {
 
     AdhocCtx *adhoc_new(const void *q);
     void adhoc_distances(AdhocCtx *c, const size_t *labels, double *out, size_t n);
+    // fused hybrid ad-hoc query: k nearest among the rows whose labels are listed (ascending) in doc_ids
+    int topk_filtered(const void *q, size_t k, const uint32_t *doc_ids, size_t n, bool ids_on_device, size_t *out_labels,
+                      double *out_scores, size_t *out_count);
 
     VecSimIndexBasicInfo basic_info() const;
     VecSimIndexStatsInfo stats_info() const;
@@ -195,6 +198,11 @@ class FlatIndex {
     uint64_t *d_id_to_label_ = nullptr;
     size_t d_labels_cap_ = 0;
     bool labels_dirty_ = true;
+    // dense label -> row id table on the device (labels are RediSearch docIds: small integers), for topk_filtered
+    uint32_t *d_label_to_id_ = nullptr;
+    size_t l2i_size_ = 0, l2i_cap_ = 0;
+    bool l2i_dirty_ = true;
+    bool sync_label_table();
 
     mutable std::mutex mu_;      // guards mutation + staging
     std::mutex pool_mu_;

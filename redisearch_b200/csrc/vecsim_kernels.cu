@@ -591,6 +591,35 @@ static cudaError_t launch_gather_inst(const CorpusView &c, const void *d_query, 
     return cudaGetLastError();
 }
 
+// labels (docIds) -> internal row ids through a dense device table; absent / out of range -> 0xFFFFFFFF (-> NaN distance)
+__global__ void __launch_bounds__(256) map_labels_kernel(const uint32_t *__restrict__ labels, uint32_t n, const uint32_t *__restrict__ table,
+                                                         uint32_t table_size, uint32_t *__restrict__ ids) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t l = labels[i];
+        ids[i] = l < table_size ? table[l] : 0xFFFFFFFFu;
+    }
+}
+cudaError_t launch_map_labels(const uint32_t *d_labels, uint32_t n, const uint32_t *d_table, uint32_t table_size, uint32_t *d_ids,
+                              cudaStream_t s, LaunchCounters *ctr) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t grid = std::min<uint32_t>((n + 255) / 256, (uint32_t)device_sm_count() * 8);
+    map_labels_kernel<<<grid, 256, 0, s>>>(d_labels, n, d_table, table_size, d_ids);
+    if (ctr) ctr->launches++;
+    return cudaGetLastError();
+}
+// out_labels[i] = labels[index part of comp[i]] (0 for empty slots)
+__global__ void pick_labels_kernel(const uint64_t *__restrict__ comp, uint32_t k, const uint32_t *__restrict__ labels, uint32_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) out[i] = comp[i] == kEmptySlot ? 0u : labels[(uint32_t)comp[i]];
+}
+cudaError_t launch_pick_labels(const uint64_t *d_comp, uint32_t k, const uint32_t *d_labels, uint32_t *d_out, cudaStream_t s,
+                               LaunchCounters *ctr) {
+    if (k == 0) return cudaSuccess;
+    pick_labels_kernel<<<(k + 127) / 128, 128, 0, s>>>(d_comp, k, d_labels, d_out);
+    if (ctr) ctr->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gather_distances(const CorpusView &c, const void *d_query, const uint32_t *d_ids, uint32_t count,
                                     float *d_out, cudaStream_t s, LaunchCounters *ctr) {
     if (count == 0) return cudaSuccess;

@@ -66,6 +66,12 @@ cudaError_t launch_range_compact(const float *d_scores, uint32_t n, float radius
 cudaError_t launch_gather_distances(const CorpusView &c, const void *d_query, const uint32_t *d_ids,
                                     uint32_t count, float *d_out, cudaStream_t s, LaunchCounters *ctr);
 
+// filter-set plumbing of the fused hybrid query: docId -> row id through a dense table; selected positions -> docIds
+cudaError_t launch_map_labels(const uint32_t *d_labels, uint32_t n, const uint32_t *d_table, uint32_t table_size, uint32_t *d_ids,
+                              cudaStream_t s, LaunchCounters *ctr);
+cudaError_t launch_pick_labels(const uint64_t *d_comp, uint32_t k, const uint32_t *d_labels, uint32_t *d_out, cudaStream_t s,
+                               LaunchCounters *ctr);
+
 // ---- result unpacking / shard merge -------------------------------------------------------------
 // composites [nq][k] + id->label table -> labels (int64, -1 for empty) and float scores.
 cudaError_t launch_unpack_results(const uint64_t *d_comp, uint32_t nq, uint32_t k,

@@ -131,6 +131,7 @@ SIGNATURES = [
     ("VecSimB200_DeviceRows", _P, [_P, C.POINTER(_SZ), C.POINTER(_SZ)]),
     ("VecSimB200_GetStats", VecSimB200_Stats, [_P, C.c_bool]),
     ("VecSimB200_MergeShardTopK", C.c_int, [_P, _P, _SZ, _SZ, _SZ, _P, _P, _P]),
+    ("VecSimB200_TopKFiltered", C.c_int, [_P, _P, _SZ, _P, _SZ, C.c_int, _P, _P, C.POINTER(_SZ)]),
     ("VecSimB200_SetCoarseMode", None, [C.c_int]),
     ("VecSimB200_LastCoarseFlags", C.c_int, [_P, _P, _SZ]),
     ("VecSimB200_Version", C.c_char_p, []),
@@ -237,6 +238,19 @@ class VecSimIndex:
         scores = np.empty((nq, k), dtype=np.float64)
         rc = self.L.VecSimB200_TopKQueryBatch(self.h, _ptr(qs), qs.strides[0], nq, k, params, _ptr(labels), _ptr(scores))
         return labels, scores, rc
+
+    def topk_filtered(self, q: np.ndarray, k: int, doc_ids, n=None):
+        """k nearest among the listed labels.  doc_ids: ascending uint32 numpy array, or a device pointer (int) with n."""
+        q = np.ascontiguousarray(q)
+        labels = np.zeros(k, dtype=np.uint64)
+        scores = np.zeros(k, dtype=np.float64)
+        cnt = C.c_size_t(0)
+        if isinstance(doc_ids, np.ndarray):
+            ids = np.ascontiguousarray(doc_ids, dtype=np.uint32)
+            rc = self.L.VecSimB200_TopKFiltered(self.h, _ptr(q), k, _ptr(ids), len(ids), 0, _ptr(labels), _ptr(scores), C.byref(cnt))
+        else:
+            rc = self.L.VecSimB200_TopKFiltered(self.h, _ptr(q), k, C.c_void_p(int(doc_ids)), n, 1, _ptr(labels), _ptr(scores), C.byref(cnt))
+        return labels[:cnt.value], scores[:cnt.value], rc
 
     def distance_from(self, label: int, blob: np.ndarray) -> float:
         blob = np.ascontiguousarray(blob)
