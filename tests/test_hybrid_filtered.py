@@ -41,11 +41,18 @@ def test_topk_filtered_matches_adhoc_loop(vtype, metric):
         g.delete(int(lab))
         p.delete(int(lab))
     q = ol.synth_rows(vtype, 43, 0, 1, dim)[0]
+    # the reference's loop hands GetDistanceFrom_Unsafe a query it normalised itself (hybrid_reader.c:296-305)
+    vtype_code = {ol.F32: vs.VecSimType_FLOAT32, ol.I8: vs.VecSimType_INT8, ol.F16: vs.VecSimType_FLOAT16}[vtype]
+    mcode = {ol.COS: vs.VecSimMetric_Cosine, ol.L2: vs.VecSimMetric_L2, ol.IP: vs.VecSimMetric_IP}[metric]
+    qb = np.zeros(g.L.VecSimParams_GetQueryBlobSize(vtype_code, dim, mcode), dtype=np.uint8)
+    qb[: q.nbytes] = q.view(np.uint8)
+    if metric == ol.COS:
+        vs.normalize(qb, dim, vtype_code)
     for m in (3, 500, 6000):
         doc_ids = np.sort(rng.choice(np.arange(1, n + 400), m, replace=False)).astype(np.uint32)  # some ids beyond the index
         labels, scores, rc = g.topk_filtered(q, k, doc_ids)
         assert rc == 0
-        exp = _oracle_adhoc(p, q, doc_ids, k)
+        exp = _oracle_adhoc(p, qb, doc_ids, k)
         assert labels.tolist() == [d for _, d in exp], (m, labels, exp)
         tol = 0 if vtype in (ol.F32, ol.I8) else 1e-2
         for s, (es, _) in zip(scores, exp):
@@ -73,9 +80,11 @@ def test_filter_from_device_intersection_feeds_the_knn():
     filt = np.intersect1d(a, b)
     assert len(rs) == len(filt)
     q = ol.synth_rows(ol.F32, 43, 0, 1, dim)[0]
+    qn = q.copy()
+    ol.port().orc_normalize(ol._p(qn), dim, ol.F32)
     d_ptr = ps.lib().II_ResultSet_DeviceDocIds(rs.h)
     labels, scores, rc = g.topk_filtered(q, k, d_ptr, n=len(filt))
     assert rc == 0
-    exp = _oracle_adhoc(p, q, filt, k)
+    exp = _oracle_adhoc(p, qn, filt, k)
     assert labels.tolist() == [d for _, d in exp]
     assert np.asarray(scores, dtype=np.float32).tobytes() == np.array([s for s, _ in exp], dtype=np.float32).tobytes()
