@@ -437,6 +437,10 @@ void VecSimB200_SetCoarseMode(int mode);
 /* Debug: after a VecSimB200_TopKQueryBatchDevice call, per-query flags (1 = answered by the tensor-core
  * path, 0 = fell back to the exact scan).  Returns -1 if the last batch did not take the coarse path. */
 int VecSimB200_LastCoarseFlags(VecSimIndex *index, uint32_t *out_ok, size_t nq);
+/* Debug: which route the last batched query took: 0 = exact CUDA-core scan, 1 = tensor-core coarse pass + exact
+ * rescoring + proof (fp32 cosine), 2 = tensor-core direct (fp16 / bf16 corpora, inner product or cosine, k <= 128:
+ * the fp32-accumulated products of the stored 16-bit values are the distances — csrc/coarse_tc.cu). */
+int VecSimB200_LastBatchPath(VecSimIndex *index);
 /* Library/ABI version and the SM arch the kernels were compiled for ("sm_100a"). */
 const char *VecSimB200_Version(void);
 

@@ -101,6 +101,14 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// slice of a tile delivered to the same shared-memory offset of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
 // contiguous global -> shared copy through the TMA engine (no tensor map), completion on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -483,8 +491,9 @@ constexpr int kQM = 128;            // queries per CTA
 constexpr int kQN = 128;            // rows per tile = N of one MMA (measured: N=64 58 clk, N=128 76 clk per instruction)
 constexpr int kQMaxStages = 8;
 constexpr int kQKbPerStage = 2;     // K blocks per pipeline stage: amortises the barrier round trip over 8 MMAs
-constexpr int kQListCap = 96;       // per-query candidate slots
-constexpr int kQTrigger = 64;       // compact a list when it holds more than this after a half tile
+// candidate lists: kEpl entries per lane of the compacting warp -> kEpl*32 slots per query; a list is cut back to
+// `keep` when it holds more than (slots - 32) entries after a 32-row chunk.  kEpl = 3 (96 slots) serves keep <= 32,
+// kEpl = 8 (256 slots) keep <= 128.
 constexpr int kQListStride = 129;   // lists[slot * stride + query]: conflict-free appends
 static_assert(kCoarseKeep <= 32, "publish_sorted ranks one kept entry per lane");
 constexpr uint32_t kQBlockBytes = kQN * 128;                    // one K block of a row tile: 128 rows x 128 bytes
@@ -492,18 +501,19 @@ constexpr uint32_t kQStageBytes = kQKbPerStage * kQBlockBytes; // 32 KB
 constexpr uint32_t kQAccCols = 2 * kQN; // two accumulator stages
 constexpr uint32_t kQTmemKb = (512 - kQAccCols) / 32; // K blocks of the queries that fit in tensor memory (8 = 512 dims)
 
-// Cut list `q` (c entries, keep < c <= 96) back to its `keep` smallest, unordered, in slots [0, keep); returns the
+// Cut list `q` (c entries, keep < c <= 32 * kEpl) back to its `keep` smallest, unordered, in slots [0, keep); returns the
 // key of the worst kept entry (the new admission threshold).  Warp-wide radix select on the 32-bit key — 32 rounds
 // of ballots — instead of `keep` rounds of warp-min extraction (measured: 21K clk per call, a third of the
 // epilogue's time and, worse, a stall of the accumulator hand-back).  Entries tied with the threshold key are
 // kept in slot order; the completeness proof only needs "every dropped key >= the returned key".
+template <int kEpl>
 __device__ __forceinline__ uint32_t select_keep(uint64_t *lists, int q, uint32_t c, uint32_t keep, int lane) {
     __syncwarp(); // the list was appended to by one lane: order its (global-memory) writes before the warp's reads
-    uint64_t e[3];
-    uint32_t k[3];
-    bool v[3];
+    uint64_t e[kEpl];
+    uint32_t k[kEpl];
+    bool v[kEpl];
 #pragma unroll
-    for (int t = 0; t < 3; t++) {
+    for (int t = 0; t < kEpl; t++) {
         const uint32_t idx = lane + 32 * t;
         v[t] = idx < c;
         e[t] = v[t] ? lists[idx * kQListStride + q] : kEmptySlot;
@@ -516,7 +526,7 @@ __device__ __forceinline__ uint32_t select_keep(uint64_t *lists, int q, uint32_t
         const uint32_t hi_mask = bit == 31 ? 0u : ~((2u << bit) - 1u); // the bits already decided
         uint32_t zeros = 0;
 #pragma unroll
-        for (int t = 0; t < 3; t++) {
+        for (int t = 0; t < kEpl; t++) {
             const bool z = v[t] && ((k[t] ^ prefix) & hi_mask) == 0 && !((k[t] >> bit) & 1u);
             zeros += __popc(__ballot_sync(0xFFFFFFFFu, z));
         }
@@ -529,7 +539,7 @@ __device__ __forceinline__ uint32_t select_keep(uint64_t *lists, int q, uint32_t
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t base = 0;
 #pragma unroll
-    for (int t = 0; t < 3; t++) {
+    for (int t = 0; t < kEpl; t++) {
         const bool less = v[t] && k[t] < prefix;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, less);
         if (less) lists[(base + __popc(m & lt)) * kQListStride + q] = e[t];
@@ -537,7 +547,7 @@ __device__ __forceinline__ uint32_t select_keep(uint64_t *lists, int q, uint32_t
     }
     uint32_t need = remaining;
 #pragma unroll
-    for (int t = 0; t < 3; t++) {
+    for (int t = 0; t < kEpl; t++) {
         const bool eq = v[t] && k[t] == prefix;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, eq);
         const uint32_t r = __popc(m & lt);
@@ -565,10 +575,20 @@ __device__ __forceinline__ void publish_sorted(const uint64_t *lists, int q, uin
         dst[lane] = kEmptySlot;
 }
 
+// kDirect = false: fp32 corpus, rows come from the tiled fp16 shadow (bulk copies), output = sorted candidate lists for
+//                  the exact rescoring + proof.
+// kDirect = true : fp16 / bf16 corpus, rows come straight from the row-major corpus through a 128B-swizzle tensor
+//                  map; the fp32-accumulated products of the stored 16-bit values ARE the distances (the reference's
+//                  own tiers differ by more: SURVEY.md finding 5, bar 1e-2), so each CTA keeps its exact top-`keep`
+//                  and the lists go to final_select unsorted.
+template <bool kDirect, int kEpl>
 __global__ void __launch_bounds__(kCoarseThreads, 1)
-coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restrict__ q16, size_t q16_pitch, uint32_t n_rows,
-                    uint32_t nq, uint32_t dim, uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t nstages, uint32_t csize,
-                    uint32_t nacc, uint64_t *__restrict__ list_scratch, uint64_t *__restrict__ cand_out) {
+coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t *__restrict__ shadow, const uint8_t *__restrict__ q16,
+                    size_t q16_pitch, uint32_t n_rows, uint32_t nq, uint32_t dim, uint32_t num_kb, uint32_t tiles_total, uint32_t keep,
+                    uint32_t nstages, uint32_t csize, uint32_t nacc, uint32_t idesc, uint64_t *__restrict__ list_scratch,
+                    uint64_t *__restrict__ cand_out) {
+    constexpr int kQListCap = kEpl * 32;
+    constexpr uint32_t kQTrigger = kQListCap - 32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     // K blocks of the queries in tensor memory (all 512 columns minus the nacc accumulator stages); the rest in sQ
@@ -622,16 +642,29 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
                 const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
                 mbar_wait(&empty[s], ph ^ 1);
                 if (elect_one_sync()) {
-                    // the shadow copy is stored tile by tile in the swizzled shared-memory image (to_f16_tiled_kernel):
-                    // the K blocks of a stage are one contiguous run in HBM
                     const uint32_t bytes = kbn * kQBlockBytes;
-                    const uint8_t *src = shadow + ((size_t)tile * num_kb + kb0) * kQBlockBytes;
                     mbar_expect_tx(&full[s], bytes);
-                    if (csize > 1) {
-                        const uint32_t slice = bytes / csize; // multiple of 16
-                        bulk_load_1d_mc(sB + (size_t)s * kQStageBytes + crank * slice, src + crank * slice, slice, &full[s], cmask);
+                    if constexpr (kDirect) {
+                        // row-major 16-bit corpus: one 128B-swizzle box of (128 / csize) rows x 64 elements per K block
+                        const uint32_t slice_rows = kQN / csize;
+                        for (uint32_t j = 0; j < kbn; j++) {
+                            uint8_t *dst = sB + (size_t)s * kQStageBytes + j * kQBlockBytes + crank * slice_rows * 128;
+                            const int c0 = (int)((kb0 + j) * 64), c1 = (int)(tile * kQN + crank * slice_rows);
+                            if (csize > 1)
+                                tma_load_2d_mc(dst, &map_rows, &full[s], c0, c1, cmask);
+                            else
+                                tma_load_2d(dst, &map_rows, &full[s], c0, c1);
+                        }
                     } else {
-                        bulk_load_1d(sB + (size_t)s * kQStageBytes, src, bytes, &full[s]);
+                        // the shadow copy is stored tile by tile in the swizzled shared-memory image (to_f16_tiled_kernel):
+                        // the K blocks of a stage are one contiguous run in HBM
+                        const uint8_t *src = shadow + ((size_t)tile * num_kb + kb0) * kQBlockBytes;
+                        if (csize > 1) {
+                            const uint32_t slice = bytes / csize; // multiple of 16
+                            bulk_load_1d_mc(sB + (size_t)s * kQStageBytes + crank * slice, src + crank * slice, slice, &full[s], cmask);
+                        } else {
+                            bulk_load_1d(sB + (size_t)s * kQStageBytes, src, bytes, &full[s]);
+                        }
                     }
                 }
                 __syncwarp();
@@ -640,7 +673,6 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
         }
     } else if (warp == 1) {
         // ===== MMA issuer: D[128 queries x 128 rows] += Q[tmem] * rows[smem]^T =====
-        constexpr uint32_t idesc = make_idesc(0, kQM, kQN);
         mbar_wait(qbar, 0);
         tc_fence_after();
         uint32_t s = 0, ph = 0;
@@ -757,12 +789,12 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
                     }
                 }
                 // lists that ran past the trigger are cut back to the best `keep` by the whole warp
-                uint32_t m = __ballot_sync(0xFFFFFFFFu, cnt > (uint32_t)kQTrigger);
+                uint32_t m = __ballot_sync(0xFFFFFFFFu, cnt > kQTrigger);
                 while (m) {
                     const int src = __ffs(m) - 1;
                     m &= m - 1;
                     const uint32_t c = __shfl_sync(0xFFFFFFFFu, cnt, src);
-                    const uint32_t worst = select_keep(lists, ew * 32 + src, c, keep, lane);
+                    const uint32_t worst = select_keep<kEpl>(lists, ew * 32 + src, c, keep, lane);
                     if (lane == src) {
                         cnt = keep;
                         thr = worst;
@@ -778,10 +810,18 @@ coarse_qtmem_kernel(const uint8_t *__restrict__ shadow, const uint8_t *__restric
             uint32_t c = __shfl_sync(0xFFFFFFFFu, cnt, src);
             const uint32_t qq = q_base + ew * 32 + src;
             if (c > keep) {
-                select_keep(lists, ew * 32 + src, c, keep, lane);
+                select_keep<kEpl>(lists, ew * 32 + src, c, keep, lane);
                 c = keep;
             }
-            if (qq < nq) publish_sorted(lists, ew * 32 + src, c, keep, lane, cand_out + ((size_t)qq * gridDim.x + blockIdx.x) * keep);
+            if (qq < nq) {
+                uint64_t *dst = cand_out + ((size_t)qq * gridDim.x + blockIdx.x) * keep;
+                if constexpr (kDirect) { // final_select takes them in any order
+                    __syncwarp();
+                    for (uint32_t r = lane; r < keep; r += 32) dst[r] = r < c ? lists[r * kQListStride + ew * 32 + src] : kEmptySlot;
+                } else {
+                    publish_sorted(lists, ew * 32 + src, c, keep, lane, dst);
+                }
+            }
         }
     }
     tc_fence_before();
@@ -909,6 +949,10 @@ static uint32_t qtmem_nacc() {
     }
     return (uint32_t)v;
 }
+static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl) {
+    if (kind == CoarseDirect16) return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3> : (const void *)coarse_qtmem_kernel<true, 8>;
+    return (const void *)coarse_qtmem_kernel<false, 3>;
+}
 static size_t qtmem_fixed_smem(uint32_t num_kb) {
     const uint32_t kb_t = (512u - qtmem_nacc() * kQN) / 32u;
     const uint32_t kb_smem = num_kb > kb_t ? num_kb - kb_t : 0; // query K blocks that do not fit tensor memory
@@ -923,6 +967,12 @@ static size_t fixed_smem(uint32_t num_kb) {
 }
 
 bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind kind) {
+    if (kind == CoarseDirect16) { // fp16 / bf16 corpora, inner product or cosine (normalised rows): tensor-core results are final
+        if ((c.dtype != DT_F16 && c.dtype != DT_BF16) || c.metric != MT_IP) return false;
+        if (c.dim % 8 != 0 || c.dim < 32 || c.pitch % 16 != 0 || !qtmem_fits(c.dim)) return false;
+        if (k > 128 || nq < 16 || c.n_rows < 65536) return false;
+        return encode_fn() != nullptr;
+    }
     if (c.dtype != DT_F32 || c.metric != MT_IP) return false; // cosine on normalised rows only (eps assumes unit vectors)
     if (c.dim % 8 != 0 || c.dim < 32 || c.dim > 1024) return false;
     if (c.pitch % 16 != 0) return false;
@@ -933,16 +983,17 @@ bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind k
     return encode_fn() != nullptr;
 }
 
-CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind) {
+CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32_t k) {
     CoarsePlan p{};
     p.kind = kind;
-    if (kind == CoarseF16) {
+    if (kind == CoarseF16 || kind == CoarseDirect16) {
         p.num_kb = (c.dim + 63) / 64;
         p.tiles = (c.n_rows + kQN - 1) / kQN;
         p.grid_y = (nq + kQM - 1) / kQM;
         const uint32_t sms = (uint32_t)device_sm_count();
         p.grid_x = std::max(1u, std::min(p.tiles, sms / p.grid_y));
-        p.keep = kCoarseKeep;
+        p.keep = kind == CoarseF16 ? kCoarseKeep : (k <= 32 ? 32u : 128u); // direct: the CTA's exact top-k of its rows
+        p.epl = p.keep <= 32 ? 3 : 8;
         p.stages = (uint32_t)std::min<size_t>(kQMaxStages, (kSmemLimit - qtmem_fixed_smem(p.num_kb)) / kQStageBytes);
         p.smem_bytes = qtmem_fixed_smem(p.num_kb) + (size_t)p.stages * kQStageBytes;
         // the query groups of a row range form a thread-block cluster (multicast of the row tiles)
@@ -957,8 +1008,9 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind) {
                 p.csize = cs;
                 break;
             }
+        const void *kfn = qtmem_kernel_fn(kind, p.epl);
         if (p.csize > 1) {
-            cudaFuncSetAttribute(coarse_qtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
             cudaLaunchConfig_t cfg{};
             cudaLaunchAttribute at[1];
             cfg.gridDim = dim3(1, p.grid_y, 1);
@@ -968,7 +1020,7 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind) {
             at[0].val.clusterDim.x = 1, at[0].val.clusterDim.y = p.csize, at[0].val.clusterDim.z = 1;
             cfg.attrs = at, cfg.numAttrs = 1;
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, coarse_qtmem_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kfn, &cfg) != cudaSuccess || nclusters < 1) {
                 cudaGetLastError();
                 p.csize = 1;
             } else {
@@ -977,7 +1029,7 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind) {
             }
         }
         p.cand_elems = (size_t)nq * p.grid_x * p.keep;
-        p.scratch_elems = (size_t)p.grid_x * p.grid_y * kQListCap * kQListStride;
+        p.scratch_elems = (size_t)p.grid_x * p.grid_y * (p.epl * 32) * kQListStride;
         return p;
     }
     const uint32_t bk = CfgTF32::kBlockK, tn = CfgTF32::kTileN;
@@ -1010,9 +1062,20 @@ static cudaError_t launch_coarse_t(const void *rows, size_t pitch, uint32_t n_ro
 
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
                           uint64_t *d_scratch, cudaStream_t s) {
-    if (p.kind == CoarseF16) {
-        cudaError_t e = cudaFuncSetAttribute(coarse_qtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+    if (p.kind == CoarseF16 || p.kind == CoarseDirect16) {
+        const void *kfn = qtmem_kernel_fn(p.kind, p.epl);
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
         if (e != cudaSuccess) return e;
+        CUtensorMap mr{};
+        uint32_t fmt = 0; // UMMA a/b format: F16 = 0, BF16 = 1
+        if (p.kind == CoarseDirect16) {
+            const bool bf = o.bf16 != 0;
+            fmt = bf ? 1u : 0u;
+            if (!make_map(&mr, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, o.rows, dim, n_rows, o.pitch, 64,
+                          kQN / p.csize))
+                return cudaErrorInvalidValue;
+        }
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kQN >> 3) << 17) | ((uint32_t)(kQM >> 4) << 24);
         cudaLaunchConfig_t cfg{};
         cudaLaunchAttribute at[1];
         cfg.gridDim = dim3(p.grid_x, p.grid_y, 1);
@@ -1022,8 +1085,12 @@ cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 1, at[0].val.clusterDim.y = p.csize, at[0].val.clusterDim.z = 1;
         cfg.attrs = at, cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, coarse_qtmem_kernel, static_cast<const uint8_t *>(o.rows), static_cast<const uint8_t *>(o.queries),
-                                  o.qpitch, n_rows, nq, dim, p.num_kb, p.tiles, p.keep, p.stages, p.csize, qtmem_nacc(), d_scratch, d_cand);
+        const uint8_t *rows = static_cast<const uint8_t *>(o.rows), *qs = static_cast<const uint8_t *>(o.queries);
+        size_t qp = o.qpitch;
+        uint32_t a_nrows = n_rows, a_nq = nq, a_dim = dim, a_kb = p.num_kb, a_tiles = p.tiles, a_keep = p.keep, a_st = p.stages, a_cs = p.csize,
+                 a_nacc = qtmem_nacc(), a_idesc = idesc;
+        void *args[] = {&mr, &rows, &qs, &qp, &a_nrows, &a_nq, &a_dim, &a_kb, &a_tiles, &a_keep, &a_st, &a_cs, &a_nacc, &a_idesc, &d_scratch, &d_cand};
+        return cudaLaunchKernelExC(&cfg, kfn, args);
     }
     return launch_coarse_t<CfgTF32>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);
 }

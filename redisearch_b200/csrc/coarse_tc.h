@@ -16,13 +16,14 @@ constexpr uint32_t kCoarseMaxK = 16;   // largest k served by the coarse path
 constexpr float kCoarseEpsTF32 = 2.5e-3f;
 constexpr float kCoarseEpsF16 = 1.2e-3f;
 
-enum CoarseKind : int { CoarseTF32 = 0, CoarseF16 = 1 };
+enum CoarseKind : int { CoarseTF32 = 0, CoarseF16 = 1, CoarseDirect16 = 2 };
 inline float coarse_eps(CoarseKind k) { return k == CoarseF16 ? kCoarseEpsF16 : kCoarseEpsTF32; }
 
 struct CoarsePlan {
     CoarseKind kind;
     uint32_t grid_x, grid_y, num_kb, tiles, keep;
     uint32_t stages; // depth of the row-tile ring in shared memory
+    uint32_t epl;    // candidate-list entries per lane of the compacting warp (3 or 8)
     uint32_t csize;  // thread-block cluster size along y (query groups sharing multicast row tiles); 1 = none
     size_t cand_elems; // uint64 per (query, list, keep)
     size_t scratch_elems; // uint64 of per-CTA candidate-list scratch (CoarseF16), 0 otherwise
@@ -35,9 +36,10 @@ struct CoarseOperands {
     size_t pitch;
     const void *queries;
     size_t qpitch;
+    int bf16; // CoarseDirect16: elements are bfloat16 (else IEEE half)
 };
 bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind kind);
-CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind);
+CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32_t k);
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
                           uint64_t *d_scratch, cudaStream_t s);
 // fp32 rows [first, first+n) -> the tiled fp16 shadow copy read by the CoarseF16 kernel (layout in coarse_tc.cu);

@@ -265,6 +265,7 @@ int VecSimB200_TopKFiltered(VecSimIndex *index, const void *queryBlob, size_t k,
     size_t dummy = 0;
     return IX(index)->topk_filtered(queryBlob, k, doc_ids, n, ids_on_device != 0, out_labels, out_scores, out_count ? out_count : &dummy);
 }
+int VecSimB200_LastBatchPath(VecSimIndex *index) { return IX(index)->last_batch_path(); }
 void VecSimB200_SetCoarseMode(int mode) { rsb200::set_coarse_mode(mode); }
 int VecSimB200_LastCoarseFlags(VecSimIndex *index, uint32_t *out_ok, size_t nq) { return IX(index)->last_coarse_flags(out_ok, nq); }
 const char *VecSimB200_Version(void) { return "vecsim_b200 0.1 (sm_100a)"; }

@@ -693,6 +693,26 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     const CorpusView v = view();
     const ScanPlan sp = plan_scan_topk(v, nq, ke);
     const int cmode = coarse_mode();
+    // fp16 / bf16 corpora: the tensor-core GEMM with fp32 accumulation IS the distance (within the 1e-2 bar by four
+    // orders of magnitude), so the batch is one kernel + the usual final selection — no shadow, no rescoring
+    if (cmode != 0 && !multi_ && (dtype_ == DT_F16 || dtype_ == DT_BF16) && coarse_supported(v, nq, ke, CoarseDirect16)) {
+        const CoarsePlan cp = plan_coarse(v, nq, CoarseDirect16, ke);
+        const size_t nA = (size_t)nq * cp.grid_x * cp.keep;
+        if (!c.need_cand(nA + cp.scratch_elems) || !c.need_out((size_t)nq * ke)) return false;
+        last_batch_coarse_ = true;
+        last_batch_path_ = 2;
+        c.d_last_ok = nullptr;
+        c.last_ok_n = 0;
+        const CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, dtype_ == DT_BF16 ? 1 : 0};
+        cudaEventRecord(c.ev_start, st);
+        bool ok = launch_coarse(ops, v.n_rows, v.dim, nq, cp, c.d_cand, c.d_cand + nA, st) == cudaSuccess;
+        cudaEventRecord(c.ev_stop, st);
+        ok = ok && launch_final_select(c.d_cand, nq, (uint32_t)(cp.grid_x * cp.keep), ke, c.d_out, st, &lc) == cudaSuccess;
+        lc.launches++;
+        coarse_batches_++;
+        *d_result = c.d_out;
+        return ok;
+    }
     CoarseKind kind = cmode == 2 ? CoarseTF32 : CoarseF16;
     const bool eligible = cmode != 0 && metric_ == VecSimMetric_Cosine && !multi_;
     bool coarse = eligible && coarse_supported(v, nq, ke, kind);
@@ -701,6 +721,7 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         coarse = coarse_supported(v, nq, ke, kind);
     }
     last_batch_coarse_ = coarse;
+    last_batch_path_ = coarse ? 1 : 0;
     if (!coarse) {
         if (!c.need_cand(sp.cand_elems) || !c.need_out((size_t)nq * ke)) return false;
         cudaEventRecord(c.ev_start, st);
@@ -710,7 +731,7 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         *d_result = c.d_out;
         return ok;
     }
-    const CoarsePlan cp = plan_coarse(v, nq, kind);
+    const CoarsePlan cp = plan_coarse(v, nq, kind, ke);
     const size_t per_query = (size_t)cp.grid_x * cp.keep;
     const size_t nA = (size_t)nq * per_query, nO = (size_t)nq * ke;
     const size_t q16_pitch = (dim_ * 2 + 15) & ~(size_t)15;
@@ -723,11 +744,11 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     uint32_t *d_ok = reinterpret_cast<uint32_t *>(list_scratch + cp.scratch_elems);
     c.d_last_ok = d_ok;
     c.last_ok_n = nq;
-    CoarseOperands ops{v.rows, v.pitch, d_q, qpitch};
+    CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, 0};
     bool ok = true;
     if (kind == CoarseF16) {
         ok = launch_to_f16(d_q, qpitch, (uint32_t)dim_, 0, nq, q16, q16_pitch, st) == cudaSuccess;
-        ops = CoarseOperands{d_shadow_, 0, q16, q16_pitch};
+        ops = CoarseOperands{d_shadow_, 0, q16, q16_pitch, 0};
         lc.launches++;
     }
     cudaEventRecord(c.ev_start, st);

@@ -212,6 +212,10 @@ class FlatIndex {
     std::atomic<uint64_t> launches_total_{0};
     std::atomic<uint64_t> coarse_batches_{0};
     bool last_batch_coarse_ = false;
+    int last_batch_path_ = 0; // 0 exact scan, 1 tensor-core coarse pass + proof, 2 tensor-core direct (16-bit corpora)
+  public:
+    int last_batch_path() const { return last_batch_path_; }
+  private:
     std::unique_ptr<QueryCtx> dev_ctx_; // scratch of topk_batch_device (stream-ordered)
     std::mutex dev_mu_;
     bool dev_timing_pending_ = false;

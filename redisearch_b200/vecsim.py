@@ -132,6 +132,7 @@ SIGNATURES = [
     ("VecSimB200_GetStats", VecSimB200_Stats, [_P, C.c_bool]),
     ("VecSimB200_MergeShardTopK", C.c_int, [_P, _P, _SZ, _SZ, _SZ, _P, _P, _P]),
     ("VecSimB200_TopKFiltered", C.c_int, [_P, _P, _SZ, _P, _SZ, C.c_int, _P, _P, C.POINTER(_SZ)]),
+    ("VecSimB200_LastBatchPath", C.c_int, [_P]),
     ("VecSimB200_SetCoarseMode", None, [C.c_int]),
     ("VecSimB200_LastCoarseFlags", C.c_int, [_P, _P, _SZ]),
     ("VecSimB200_Version", C.c_char_p, []),
