@@ -193,6 +193,27 @@ __device__ __forceinline__ void umma_ss_f16(uint32_t d_tmem, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// 8-bit integer operands (kind::i8: 32 elements per instruction, int32 accumulate) — exact dot products
+__device__ __forceinline__ void umma_ts_i8(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ss_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -504,8 +525,8 @@ constexpr uint32_t kQTmemKb = (512 - kQAccCols) / 32; // K blocks of the queries
 // Cut list `q` (c entries, keep < c <= 32 * kEpl) back to its `keep` smallest, unordered, in slots [0, keep); returns the
 // key of the worst kept entry (the new admission threshold).  Warp-wide radix select on the 32-bit key — 32 rounds
 // of ballots — instead of `keep` rounds of warp-min extraction (measured: 21K clk per call, a third of the
-// epilogue's time and, worse, a stall of the accumulator hand-back).  Entries tied with the threshold key are
-// kept in slot order; the completeness proof only needs "every dropped key >= the returned key".
+// epilogue's time and, worse, a stall of the accumulator hand-back).  Among entries tied with the threshold key the
+// lowest row ids are kept, so the kept set is exactly the `keep` smallest composites (key, row).
 template <int kEpl>
 __device__ __forceinline__ uint32_t select_keep(uint64_t *lists, int q, uint32_t c, uint32_t keep, int lane) {
     __syncwarp(); // the list was appended to by one lane: order its (global-memory) writes before the warp's reads
@@ -545,16 +566,37 @@ __device__ __forceinline__ uint32_t select_keep(uint64_t *lists, int q, uint32_t
         if (less) lists[(base + __popc(m & lt)) * kQListStride + q] = e[t];
         base += __popc(m);
     }
-    uint32_t need = remaining;
+    // entries tied with the threshold key: the `remaining` LOWEST row ids stay (the exact scan admits rows in id order
+    // with a strict `<`), found by a second radix select on the low word when there are more ties than places
+    uint32_t n_eq = 0;
+#pragma unroll
+    for (int t = 0; t < kEpl; t++) n_eq += __popc(__ballot_sync(0xFFFFFFFFu, v[t] && k[t] == prefix));
+    uint32_t row_cut = 0xFFFFFFFFu; // keep tied entries with row <= row_cut
+    if (n_eq > remaining) {
+        uint32_t rp = 0, rem = remaining;
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; bit--) {
+            const uint32_t hi_mask = bit == 31 ? 0u : ~((2u << bit) - 1u);
+            uint32_t zeros = 0;
+#pragma unroll
+            for (int t = 0; t < kEpl; t++) {
+                const uint32_t row = (uint32_t)e[t];
+                const bool z = v[t] && k[t] == prefix && ((row ^ rp) & hi_mask) == 0 && !((row >> bit) & 1u);
+                zeros += __popc(__ballot_sync(0xFFFFFFFFu, z));
+            }
+            if (zeros < rem) {
+                rem -= zeros;
+                rp |= 1u << bit;
+            }
+        }
+        row_cut = rp; // row ids are unique: exactly `remaining` tied entries have row <= rp
+    }
 #pragma unroll
     for (int t = 0; t < kEpl; t++) {
-        const bool eq = v[t] && k[t] == prefix;
+        const bool eq = v[t] && k[t] == prefix && (uint32_t)e[t] <= row_cut;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, eq);
-        const uint32_t r = __popc(m & lt);
-        if (eq && r < need) lists[(base + r) * kQListStride + q] = e[t];
-        const uint32_t taken = min((uint32_t)__popc(m), need);
-        base += taken;
-        need -= taken;
+        if (eq) lists[(base + __popc(m & lt)) * kQListStride + q] = e[t];
+        base += __popc(m);
     }
     __syncwarp();
     return prefix;
@@ -581,12 +623,16 @@ __device__ __forceinline__ void publish_sorted(const uint64_t *lists, int q, uin
 //                  map; the fp32-accumulated products of the stored 16-bit values ARE the distances (the reference's
 //                  own tiers differ by more: SURVEY.md finding 5, bar 1e-2), so each CTA keeps its exact top-`keep`
 //                  and the lists go to final_select unsorted.
-template <bool kDirect, int kEpl>
+//   kOp = 0  16-bit float operands, fp32 accumulators: distance 1 - dot
+//   kOp = 1  int8 / uint8 operands (kind::i8), int32 accumulators, inner product: (float)(1 - dot)  (IP.cpp:248-252)
+//   kOp = 2  the same, cosine: 1 - (float)dot / (norm_row * norm_query), norms = the fp32 stored after the payload
+//            (IP.cpp:264-271).  The integer dot products are exact, so kOp 1/2 reproduce the reference bit for bit.
+template <bool kDirect, int kEpl, int kOp>
 __global__ void __launch_bounds__(kCoarseThreads, 1)
-coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t *__restrict__ shadow, const uint8_t *__restrict__ q16,
-                    size_t q16_pitch, uint32_t n_rows, uint32_t nq, uint32_t dim, uint32_t num_kb, uint32_t tiles_total, uint32_t keep,
-                    uint32_t nstages, uint32_t csize, uint32_t nacc, uint32_t idesc, uint64_t *__restrict__ list_scratch,
-                    uint64_t *__restrict__ cand_out) {
+coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t *__restrict__ shadow, size_t row_pitch,
+                    const uint8_t *__restrict__ q16, size_t q16_pitch, uint32_t n_rows, uint32_t nq, uint32_t dim, uint32_t row_bytes,
+                    uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t nstages, uint32_t csize, uint32_t nacc, uint32_t idesc,
+                    uint64_t *__restrict__ list_scratch, uint64_t *__restrict__ cand_out) {
     constexpr int kQListCap = kEpl * 32;
     constexpr uint32_t kQTrigger = kQListCap - 32;
     extern __shared__ uint8_t smem_raw[];
@@ -649,7 +695,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                         const uint32_t slice_rows = kQN / csize;
                         for (uint32_t j = 0; j < kbn; j++) {
                             uint8_t *dst = sB + (size_t)s * kQStageBytes + j * kQBlockBytes + crank * slice_rows * 128;
-                            const int c0 = (int)((kb0 + j) * 64), c1 = (int)(tile * kQN + crank * slice_rows);
+                            const int c0 = (int)((kb0 + j) * (kOp == 0 ? 64 : 128)), c1 = (int)(tile * kQN + crank * slice_rows);
                             if (csize > 1)
                                 tma_load_2d_mc(dst, &map_rows, &full[s], c0, c1, cmask);
                             else
@@ -695,16 +741,30 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                             const uint64_t bdesc = bdesc0 + (uint64_t)(j * (kQBlockBytes >> 4));
                             if (kb < kb_tmem) { // queries from tensor memory: 8 columns per instruction
                                 const uint32_t a_tmem = tmem_q + kb * 32;
-                                umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, kb != 0);
-                                umma_ts_f16(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
-                                umma_ts_f16(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
-                                umma_ts_f16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
+                                if constexpr (kOp == 0) {
+                                    umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, kb != 0);
+                                    umma_ts_f16(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
+                                    umma_ts_f16(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
+                                    umma_ts_f16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
+                                } else {
+                                    umma_ts_i8(d_tmem, a_tmem, bdesc, idesc, kb != 0);
+                                    umma_ts_i8(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
+                                    umma_ts_i8(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
+                                    umma_ts_i8(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
+                                }
                             } else { // queries from shared memory
                                 const uint64_t adesc = make_smem_desc(smem_u32(sQ + (size_t)(kb - kb_tmem) * kQBlockBytes));
-                                umma_ss_f16(d_tmem, adesc, bdesc, idesc, 1);
-                                umma_ss_f16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
-                                umma_ss_f16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
-                                umma_ss_f16(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                                if constexpr (kOp == 0) {
+                                    umma_ss_f16(d_tmem, adesc, bdesc, idesc, 1);
+                                    umma_ss_f16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                                    umma_ss_f16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                                    umma_ss_f16(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                                } else {
+                                    umma_ss_i8(d_tmem, adesc, bdesc, idesc, 1);
+                                    umma_ss_i8(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                                    umma_ss_i8(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                                    umma_ss_i8(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                                }
                             }
                         }
                     }
@@ -732,7 +792,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     x[u] = make_uint4(0, 0, 0, 0);
-                    if (q < nq && kb * 64 + u * 8 < dim) x[u] = src[kb * 8 + u];
+                    if (q < nq && kb * 128 + u * 16 < row_bytes) x[u] = src[kb * 8 + u];
                 }
                 if (kb < kb_tmem) {
                     uint32_t w[32];
@@ -752,10 +812,21 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         }
         // ===== epilogue: this thread's query against 64 rows per tile =====
         uint32_t thr = 0xFFFFFFFFu, cnt = 0;
-        float thr_dot = -__int_as_float(0x7f800000); // -inf: everything passes until the first compaction
+        // pre-test bound in the raw accumulator domain; -inf: everything passes until the first compaction
+        float thr_dot = -__int_as_float(0x7f800000);
+        float nq_norm = 1.0f;
+        if constexpr (kOp == 2) nq_norm = q < nq ? *reinterpret_cast<const float *>(q16 + (size_t)q * q16_pitch + dim) : 1.0f;
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t tile = blockIdx.x + i * gridDim.x;
             const uint32_t a = i % nacc, aph = (i / nacc) & 1;
+            float nrm[kQN / 32]; // kOp 2: lane l holds the norms of rows h*32 + l of the tile
+            if constexpr (kOp == 2) {
+#pragma unroll
+                for (int h = 0; h < kQN / 32; h++) {
+                    const uint32_t r = tile * kQN + h * 32 + lane;
+                    nrm[h] = r < n_rows ? __ldg(reinterpret_cast<const float *>(shadow + (size_t)r * row_pitch + dim)) : 1.0f;
+                }
+            }
             mbar_wait(&tfull[a], aph);
             tc_fence_after();
             // drain the whole tile to registers and hand the accumulator stage back before looking at a value
@@ -768,12 +839,20 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
 #pragma unroll
             for (int h = 0; h < kQN / 32; h++) {
                 const uint32_t row0 = tile * kQN + h * 32;
-                // pre-test on the raw dot product against a slightly loose bound (2 instructions per value);
-                // the few survivors take the exact key comparison below
+                // pre-test on the raw dot product against a slightly loose bound (a few instructions per value);
+                // the few survivors take the exact distance and key comparison below
                 uint32_t pass = 0;
 #pragma unroll
-                for (int j = 0; j < 32; j++)
-                    if (__uint_as_float(v[h][j]) > thr_dot) pass |= 1u << j;
+                for (int j = 0; j < 32; j++) {
+                    bool p;
+                    if constexpr (kOp == 0)
+                        p = __uint_as_float(v[h][j]) > thr_dot;
+                    else if constexpr (kOp == 1)
+                        p = (float)(int)v[h][j] > thr_dot;
+                    else
+                        p = (float)(int)v[h][j] > __shfl_sync(0xFFFFFFFFu, nrm[h], j) * thr_dot - 0.01f;
+                    if (p) pass |= 1u << j;
+                }
                 if (row0 + 32 > n_rows) pass &= (n_rows > row0) ? ((1u << (n_rows - row0)) - 1u) : 0u; // TMA zero fill past the end
                 while (pass) {
                     const int j = __ffs(pass) - 1;
@@ -782,7 +861,17 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
 #pragma unroll
                     for (int x = 0; x < 32; x++)
                         if (x == j) raw = v[h][x];
-                    const uint32_t key = orderable_key(1.0f - __uint_as_float(raw));
+                    float d;
+                    if constexpr (kOp == 0)
+                        d = 1.0f - __uint_as_float(raw);
+                    else if constexpr (kOp == 1)
+                        d = (float)(1 - (int)raw);
+                    else {
+                        const uint32_t r = row0 + j; // rare path: re-read the norm (L1/L2 hit) instead of a divergent shuffle
+                        const float nr = __ldg(reinterpret_cast<const float *>(shadow + (size_t)r * row_pitch + dim));
+                        d = __fsub_rn(1.0f, __fdiv_rn((float)(int)raw, __fmul_rn(nr, nq_norm)));
+                    }
+                    const uint32_t key = orderable_key(d);
                     if (key < thr) {
                         lists[cnt * kQListStride + et] = ((uint64_t)key << 32) | (row0 + j);
                         cnt++;
@@ -798,8 +887,17 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                     if (lane == src) {
                         cnt = keep;
                         thr = worst;
-                        // d = 1 - dot < d_thr needs dot > 1 - d_thr; the slack covers the rounding of both subtractions
-                        thr_dot = (1.0f - key_to_float(thr)) - 4e-7f;
+                        // d < d_thr needs dot > t = 1 - d_thr (times the norms for the integer cosine); the slack covers
+                        // the rounding of the subtractions, of int -> float and of the norm product
+                        const float t = 1.0f - key_to_float(thr);
+                        if constexpr (kOp == 0)
+                            thr_dot = t - 4e-7f;
+                        else if constexpr (kOp == 1)
+                            thr_dot = t - (fabsf(t) * 1e-6f + 2.0f);
+                        else {
+                            const float tq = t * nq_norm;
+                            thr_dot = tq - fabsf(tq) * 4e-6f;
+                        }
                     }
                 }
             }
@@ -949,9 +1047,13 @@ static uint32_t qtmem_nacc() {
     }
     return (uint32_t)v;
 }
-static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl) {
-    if (kind == CoarseDirect16) return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3> : (const void *)coarse_qtmem_kernel<true, 8>;
-    return (const void *)coarse_qtmem_kernel<false, 3>;
+static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl, bool int_cos) {
+    if (kind == CoarseDirect16) return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 0> : (const void *)coarse_qtmem_kernel<true, 8, 0>;
+    if (kind == CoarseDirect8) {
+        if (int_cos) return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 2> : (const void *)coarse_qtmem_kernel<true, 8, 2>;
+        return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 1> : (const void *)coarse_qtmem_kernel<true, 8, 1>;
+    }
+    return (const void *)coarse_qtmem_kernel<false, 3, 0>;
 }
 static size_t qtmem_fixed_smem(uint32_t num_kb) {
     const uint32_t kb_t = (512u - qtmem_nacc() * kQN) / 32u;
@@ -959,7 +1061,8 @@ static size_t qtmem_fixed_smem(uint32_t num_kb) {
     return 1024 + (size_t)kb_smem * kQBlockBytes + (2 * kQMaxStages + 2 * kAccStages + 1) * 8 + 64;
 }
 // fp16 with the queries in tensor memory (first 512 dims) + shared memory (the rest): keep >= 4 ring stages
-static bool qtmem_fits(uint32_t dim) { return qtmem_fixed_smem((dim + 63) / 64) + 4 * (size_t)kQStageBytes <= kSmemLimit; }
+static bool qtmem_fits_bytes(uint32_t row_bytes) { return qtmem_fixed_smem((row_bytes + 127) / 128) + 4 * (size_t)kQStageBytes <= kSmemLimit; }
+static bool qtmem_fits(uint32_t dim) { return qtmem_fits_bytes(dim * 2); }
 
 static size_t fixed_smem(uint32_t num_kb) {
     const uint32_t tn = CfgTF32::kTileN;
@@ -970,6 +1073,12 @@ bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind k
     if (kind == CoarseDirect16) { // fp16 / bf16 corpora, inner product or cosine (normalised rows): tensor-core results are final
         if ((c.dtype != DT_F16 && c.dtype != DT_BF16) || c.metric != MT_IP) return false;
         if (c.dim % 8 != 0 || c.dim < 32 || c.pitch % 16 != 0 || !qtmem_fits(c.dim)) return false;
+        if (k > 128 || nq < 16 || c.n_rows < 65536) return false;
+        return encode_fn() != nullptr;
+    }
+    if (kind == CoarseDirect8) { // int8 / uint8 corpora, inner product or cosine: exact integer dot products on kind::i8
+        if ((c.dtype != DT_I8 && c.dtype != DT_U8) || (c.metric != MT_IP && c.metric != MT_COS)) return false;
+        if (c.dim % 16 != 0 || c.dim < 32 || c.pitch % 16 != 0 || !qtmem_fits_bytes(c.dim)) return false;
         if (k > 128 || nq < 16 || c.n_rows < 65536) return false;
         return encode_fn() != nullptr;
     }
@@ -986,8 +1095,8 @@ bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind k
 CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32_t k) {
     CoarsePlan p{};
     p.kind = kind;
-    if (kind == CoarseF16 || kind == CoarseDirect16) {
-        p.num_kb = (c.dim + 63) / 64;
+    if (kind == CoarseF16 || kind == CoarseDirect16 || kind == CoarseDirect8) {
+        p.num_kb = kind == CoarseDirect8 ? (c.dim + 127) / 128 : (c.dim + 63) / 64;
         p.tiles = (c.n_rows + kQN - 1) / kQN;
         p.grid_y = (nq + kQM - 1) / kQM;
         const uint32_t sms = (uint32_t)device_sm_count();
@@ -1008,7 +1117,7 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32
                 p.csize = cs;
                 break;
             }
-        const void *kfn = qtmem_kernel_fn(kind, p.epl);
+        const void *kfn = qtmem_kernel_fn(kind, p.epl, c.metric == MT_COS);
         if (p.csize > 1) {
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
             cudaLaunchConfig_t cfg{};
@@ -1062,20 +1171,26 @@ static cudaError_t launch_coarse_t(const void *rows, size_t pitch, uint32_t n_ro
 
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
                           uint64_t *d_scratch, cudaStream_t s) {
-    if (p.kind == CoarseF16 || p.kind == CoarseDirect16) {
-        const void *kfn = qtmem_kernel_fn(p.kind, p.epl);
+    if (p.kind == CoarseF16 || p.kind == CoarseDirect16 || p.kind == CoarseDirect8) {
+        const void *kfn = qtmem_kernel_fn(p.kind, p.epl, o.int_cosine != 0);
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
         if (e != cudaSuccess) return e;
         CUtensorMap mr{};
-        uint32_t fmt = 0; // UMMA a/b format: F16 = 0, BF16 = 1
+        // UMMA instruction descriptor: c_format [4,6) (F32 = 1, S32 = 2), a/b format [7,10)/[10,13), N>>3 [17,23), M>>4 [24,29)
+        uint32_t cfmt = 1, fmt = 0; // kind::f16: F16 = 0, BF16 = 1; kind::i8: UINT8 = 0, INT8 = 1
+        uint32_t row_bytes = dim * 2;
         if (p.kind == CoarseDirect16) {
-            const bool bf = o.bf16 != 0;
-            fmt = bf ? 1u : 0u;
-            if (!make_map(&mr, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, o.rows, dim, n_rows, o.pitch, 64,
+            fmt = o.elem_variant ? 1u : 0u;
+            if (!make_map(&mr, fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, o.rows, dim, n_rows, o.pitch, 64,
                           kQN / p.csize))
                 return cudaErrorInvalidValue;
+        } else if (p.kind == CoarseDirect8) {
+            cfmt = 2;
+            fmt = o.elem_variant ? 1u : 0u; // signed?
+            row_bytes = dim;
+            if (!make_map(&mr, CU_TENSOR_MAP_DATA_TYPE_UINT8, o.rows, dim, n_rows, o.pitch, 128, kQN / p.csize)) return cudaErrorInvalidValue;
         }
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kQN >> 3) << 17) | ((uint32_t)(kQM >> 4) << 24);
+        const uint32_t idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kQN >> 3) << 17) | ((uint32_t)(kQM >> 4) << 24);
         cudaLaunchConfig_t cfg{};
         cudaLaunchAttribute at[1];
         cfg.gridDim = dim3(p.grid_x, p.grid_y, 1);
@@ -1086,10 +1201,11 @@ cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim
         at[0].val.clusterDim.x = 1, at[0].val.clusterDim.y = p.csize, at[0].val.clusterDim.z = 1;
         cfg.attrs = at, cfg.numAttrs = 1;
         const uint8_t *rows = static_cast<const uint8_t *>(o.rows), *qs = static_cast<const uint8_t *>(o.queries);
-        size_t qp = o.qpitch;
-        uint32_t a_nrows = n_rows, a_nq = nq, a_dim = dim, a_kb = p.num_kb, a_tiles = p.tiles, a_keep = p.keep, a_st = p.stages, a_cs = p.csize,
-                 a_nacc = qtmem_nacc(), a_idesc = idesc;
-        void *args[] = {&mr, &rows, &qs, &qp, &a_nrows, &a_nq, &a_dim, &a_kb, &a_tiles, &a_keep, &a_st, &a_cs, &a_nacc, &a_idesc, &d_scratch, &d_cand};
+        size_t rp = o.pitch, qp = o.qpitch;
+        uint32_t a_nrows = n_rows, a_nq = nq, a_dim = dim, a_rb = row_bytes, a_kb = p.num_kb, a_tiles = p.tiles, a_keep = p.keep,
+                 a_st = p.stages, a_cs = p.csize, a_nacc = qtmem_nacc(), a_idesc = idesc;
+        void *args[] = {&mr,    &rows,   &rp,   &qs,   &qp,     &a_nrows, &a_nq,      &a_dim, &a_rb,
+                        &a_kb,  &a_tiles, &a_keep, &a_st, &a_cs, &a_nacc,  &a_idesc, &d_scratch, &d_cand};
         return cudaLaunchKernelExC(&cfg, kfn, args);
     }
     return launch_coarse_t<CfgTF32>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);

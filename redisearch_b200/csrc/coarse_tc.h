@@ -16,7 +16,7 @@ constexpr uint32_t kCoarseMaxK = 16;   // largest k served by the coarse path
 constexpr float kCoarseEpsTF32 = 2.5e-3f;
 constexpr float kCoarseEpsF16 = 1.2e-3f;
 
-enum CoarseKind : int { CoarseTF32 = 0, CoarseF16 = 1, CoarseDirect16 = 2 };
+enum CoarseKind : int { CoarseTF32 = 0, CoarseF16 = 1, CoarseDirect16 = 2, CoarseDirect8 = 3 };
 inline float coarse_eps(CoarseKind k) { return k == CoarseF16 ? kCoarseEpsF16 : kCoarseEpsTF32; }
 
 struct CoarsePlan {
@@ -36,7 +36,8 @@ struct CoarseOperands {
     size_t pitch;
     const void *queries;
     size_t qpitch;
-    int bf16; // CoarseDirect16: elements are bfloat16 (else IEEE half)
+    int elem_variant; // CoarseDirect16: 1 = bfloat16 (else IEEE half); CoarseDirect8: 1 = int8 (else uint8)
+    int int_cosine;   // CoarseDirect8: cosine (rows carry their fp32 norm after the payload) instead of inner product
 };
 bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind kind);
 CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32_t k);

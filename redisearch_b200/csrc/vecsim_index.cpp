@@ -695,15 +695,19 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     const int cmode = coarse_mode();
     // fp16 / bf16 corpora: the tensor-core GEMM with fp32 accumulation IS the distance (within the 1e-2 bar by four
     // orders of magnitude), so the batch is one kernel + the usual final selection — no shadow, no rescoring
-    if (cmode != 0 && !multi_ && (dtype_ == DT_F16 || dtype_ == DT_BF16) && coarse_supported(v, nq, ke, CoarseDirect16)) {
-        const CoarsePlan cp = plan_coarse(v, nq, CoarseDirect16, ke);
+    const bool is16 = dtype_ == DT_F16 || dtype_ == DT_BF16, is8 = dtype_ == DT_I8 || dtype_ == DT_U8;
+    const CoarseKind dkind = is16 ? CoarseDirect16 : CoarseDirect8;
+    if (cmode != 0 && !multi_ && (is16 || is8) && coarse_supported(v, nq, ke, dkind)) {
+        // int8 / uint8: kind::i8 dot products are exact integers and the epilogue applies the reference's own
+        // float expression, so that route is bit-exact
+        const CoarsePlan cp = plan_coarse(v, nq, dkind, ke);
         const size_t nA = (size_t)nq * cp.grid_x * cp.keep;
         if (!c.need_cand(nA + cp.scratch_elems) || !c.need_out((size_t)nq * ke)) return false;
         last_batch_coarse_ = true;
         last_batch_path_ = 2;
         c.d_last_ok = nullptr;
         c.last_ok_n = 0;
-        const CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, dtype_ == DT_BF16 ? 1 : 0};
+        const CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, (dtype_ == DT_BF16 || dtype_ == DT_I8) ? 1 : 0, mkind_ == MT_COS ? 1 : 0};
         cudaEventRecord(c.ev_start, st);
         bool ok = launch_coarse(ops, v.n_rows, v.dim, nq, cp, c.d_cand, c.d_cand + nA, st) == cudaSuccess;
         cudaEventRecord(c.ev_stop, st);
@@ -744,11 +748,11 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     uint32_t *d_ok = reinterpret_cast<uint32_t *>(list_scratch + cp.scratch_elems);
     c.d_last_ok = d_ok;
     c.last_ok_n = nq;
-    CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, 0};
+    CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, 0, 0};
     bool ok = true;
     if (kind == CoarseF16) {
         ok = launch_to_f16(d_q, qpitch, (uint32_t)dim_, 0, nq, q16, q16_pitch, st) == cudaSuccess;
-        ops = CoarseOperands{d_shadow_, 0, q16, q16_pitch, 0};
+        ops = CoarseOperands{d_shadow_, 0, q16, q16_pitch, 0, 0};
         lc.launches++;
     }
     cudaEventRecord(c.ev_start, st);

@@ -181,3 +181,31 @@ def test_16bit_corpora_take_the_tensor_core_route(vtype, metric, n, dim, nq, k):
     assert rc == 0 and vs.lib().VecSimB200_LastBatchPath(g.h) == 0
     assert np.abs(s2 - scores).max() <= 1e-4
     vs.lib().VecSimB200_SetCoarseMode(-1)
+
+
+@pytest.mark.parametrize("vtype,metric,n,dim,nq,k", [(ol.I8, ol.COS, 70_000, 128, 40, 10), (ol.I8, ol.IP, 66_000, 768, 130, 100),
+                                                     (ol.U8, ol.COS, 140_000, 96, 300, 32), (ol.U8, ol.IP, 70_000, 256, 17, 128),
+                                                     (ol.I8, ol.COS, 66_000, 1024, 64, 10)])
+def test_8bit_corpora_take_the_integer_tensor_core_route_bit_exact(vtype, metric, n, dim, nq, k):
+    """int8 / uint8 corpora: tcgen05 kind::i8 dot products are exact int32 sums and the epilogue applies the reference's
+    float expression (IP.cpp:248-285), so ids AND score bits must equal the oracle's — including tie order by id."""
+    from redisearch_b200 import vecsim as vs
+
+    vs.lib().VecSimB200_SetCoarseMode(1)
+    vt = {ol.I8: vs.VecSimType_INT8, ol.U8: vs.VecSimType_UINT8}[vtype]
+    mt = {ol.IP: vs.VecSimMetric_IP, ol.COS: vs.VecSimMetric_Cosine}[metric]
+    rows = ol.synth_rows(vtype, 42, 0, n, dim)
+    rows[5000:5040] = rows[4000:4040]  # exact duplicates: ties that must resolve to the lower id
+    g = vs.VecSimIndex(vt, dim, mt)
+    p = ol.PortIndex(vtype, dim, metric, tier=ol.TIER_AVX512)
+    assert g.add_many(rows, label0=1) == n
+    p.add_many(rows, 1)
+    qs = ol.synth_rows(vtype, 43, 0, nq, dim)
+    qs[1] = rows[4003]  # a query whose best hits are a tied pair
+    labels, scores, rc = g.topk_batch(qs, k)
+    assert rc == 0 and vs.lib().VecSimB200_LastBatchPath(g.h) == 2
+    for i in range(nq):
+        pi, ps = p.topk(qs[i], k)
+        assert labels[i].astype(np.int64).tolist() == pi.tolist(), (i, labels[i][:12], pi[:12])
+        assert scores[i].astype(np.float32).tobytes() == ps.astype(np.float32).tobytes()
+    vs.lib().VecSimB200_SetCoarseMode(-1)
