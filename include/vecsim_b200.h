@@ -438,8 +438,10 @@ void VecSimB200_SetCoarseMode(int mode);
  * path, 0 = fell back to the exact scan).  Returns -1 if the last batch did not take the coarse path. */
 int VecSimB200_LastCoarseFlags(VecSimIndex *index, uint32_t *out_ok, size_t nq);
 /* Debug: which route the last batched query took: 0 = exact CUDA-core scan, 1 = tensor-core coarse pass + exact
- * rescoring + proof (fp32 cosine), 2 = tensor-core direct (fp16 / bf16 corpora, inner product or cosine, k <= 128:
- * the fp32-accumulated products of the stored 16-bit values are the distances — csrc/coarse_tc.cu). */
+ * rescoring + proof (fp32 cosine), 2 = tensor-core direct, k <= 128 (csrc/coarse_tc.cu): fp16 / bf16 corpora, inner
+ * product or cosine — the fp32-accumulated products of the stored 16-bit values are the distances; int8 / uint8 corpora,
+ * inner product or cosine — kind::i8 integer dot products are exact and the reference's float expression is applied
+ * to them, bit-exact. */
 int VecSimB200_LastBatchPath(VecSimIndex *index);
 /* Library/ABI version and the SM arch the kernels were compiled for ("sm_100a"). */
 const char *VecSimB200_Version(void);
