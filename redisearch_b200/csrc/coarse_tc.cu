@@ -1073,19 +1073,19 @@ bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind k
     if (kind == CoarseDirect16) { // fp16 / bf16 corpora, inner product or cosine (normalised rows): tensor-core results are final
         if ((c.dtype != DT_F16 && c.dtype != DT_BF16) || c.metric != MT_IP) return false;
         if (c.dim % 8 != 0 || c.dim < 32 || c.pitch % 16 != 0 || !qtmem_fits(c.dim)) return false;
-        if (k > 128 || nq < 16 || c.n_rows < 65536) return false;
+        if (k > 128 || nq < 1 || c.n_rows < 65536) return false;
         return encode_fn() != nullptr;
     }
     if (kind == CoarseDirect8) { // int8 / uint8 corpora, inner product or cosine: exact integer dot products on kind::i8
         if ((c.dtype != DT_I8 && c.dtype != DT_U8) || (c.metric != MT_IP && c.metric != MT_COS)) return false;
         if (c.dim % 16 != 0 || c.dim < 32 || c.pitch % 16 != 0 || !qtmem_fits_bytes(c.dim)) return false;
-        if (k > 128 || nq < 16 || c.n_rows < 65536) return false;
+        if (k > 128 || nq < 1 || c.n_rows < 65536) return false;
         return encode_fn() != nullptr;
     }
     if (c.dtype != DT_F32 || c.metric != MT_IP) return false; // cosine on normalised rows only (eps assumes unit vectors)
     if (c.dim % 8 != 0 || c.dim < 32 || c.dim > 1024) return false;
     if (c.pitch % 16 != 0) return false;
-    if (k > kCoarseMaxK || nq < 16) return false;
+    if (k > kCoarseMaxK || nq < 1) return false; // batch_scan decides whether a small batch is worth the route
     if (c.n_rows < 65536) return false; // tiny corpora: the exact kernel is already fast
     if (kind == CoarseF16 && !qtmem_fits(c.dim)) return false; // wider rows: the TF32 variant (queries in shared memory)
     if (kind == CoarseTF32 && fixed_smem((c.dim + CfgTF32::kBlockK - 1) / CfgTF32::kBlockK) + 3 * kStageBytes > kSmemLimit) return false;

@@ -547,15 +547,25 @@ VecSimQueryReply *FlatIndex::topk(const void *q, size_t k, VecSimQueryParams *qp
     LaunchCounters lc;
     if (ok && !multi_ && std::min(k, n) <= (size_t)kMaxFusedK) {
         const uint32_t ke = (uint32_t)std::min(k, n);
-        const ScanPlan plan = plan_scan_topk(v, 1, ke);
-        ok = c->need_cand(plan.cand_elems) && c->need_out(ke);
-        if (ok) {
-            cudaEventRecord(c->ev_start, c->stream);
-            ok = launch_scan_topk(v, c->d_query, qpitch, 1, ke, plan, c->d_cand, c->stream, &lc) == cudaSuccess;
-            cudaEventRecord(c->ev_stop, c->stream);
+        const uint64_t *d_res = nullptr;
+        if (single_query_takes_coarse(ke)) {
+            // an up-to-date fp16 shadow exists (a batch built it): one pass over 15 GB of it + exact rescoring + proof
+            // beats the 31 GB exact scan; same answer
+            uint64_t *r = nullptr;
+            ok = batch_scan(*c, c->d_query, qpitch, 1, ke, c->stream, lc, &r);
+            d_res = r;
+        } else {
+            const ScanPlan plan = plan_scan_topk(v, 1, ke);
+            ok = c->need_cand(plan.cand_elems) && c->need_out(ke);
+            if (ok) {
+                cudaEventRecord(c->ev_start, c->stream);
+                ok = launch_scan_topk(v, c->d_query, qpitch, 1, ke, plan, c->d_cand, c->stream, &lc) == cudaSuccess;
+                cudaEventRecord(c->ev_stop, c->stream);
+            }
+            ok = ok && launch_final_select(c->d_cand, 1, plan.lists_per_query * ke, ke, c->d_out, c->stream, &lc) == cudaSuccess;
+            d_res = c->d_out;
         }
-        ok = ok && launch_final_select(c->d_cand, 1, plan.lists_per_query * ke, ke, c->d_out, c->stream, &lc) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(c->h_out, c->d_out, ke * 8, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(c->h_out, d_res, ke * 8, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
         ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
         if (ok) {
             float ms = 0;
@@ -642,6 +652,17 @@ static int coarse_mode() {
     return m;
 }
 
+// Single queries (and batches below 16) take the tensor-core route only if that costs nothing extra: mode 1, an fp16
+// shadow that is already complete, fp32 cosine, k within the coarse lists.
+bool FlatIndex::single_query_takes_coarse(uint32_t ke) {
+    if (coarse_mode() != 1 || multi_ || metric_ != VecSimMetric_Cosine || dtype_ != DT_F32) return false;
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        if (!d_shadow_ || shadow_rows_ != count_ || !shadow_dirty_.empty() || shadow_cap_ < count_) return false;
+    }
+    return coarse_supported(view(), 1, ke, CoarseF16);
+}
+
 // Bring the fp16 shadow copy of the rows up to date on `st` (rows appended, overwritten or moved by a
 // swap-delete since the last coarse batch).  Returns false if HBM for the shadow cannot be had; the
 // caller then runs the TF32 variant on the fp32 rows.
@@ -697,7 +718,7 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     // orders of magnitude), so the batch is one kernel + the usual final selection — no shadow, no rescoring
     const bool is16 = dtype_ == DT_F16 || dtype_ == DT_BF16, is8 = dtype_ == DT_I8 || dtype_ == DT_U8;
     const CoarseKind dkind = is16 ? CoarseDirect16 : CoarseDirect8;
-    if (cmode != 0 && !multi_ && (is16 || is8) && coarse_supported(v, nq, ke, dkind)) {
+    if (cmode != 0 && !multi_ && nq >= 16 && (is16 || is8) && coarse_supported(v, nq, ke, dkind)) {
         // int8 / uint8: kind::i8 dot products are exact integers and the epilogue applies the reference's own
         // float expression, so that route is bit-exact
         const CoarsePlan cp = plan_coarse(v, nq, dkind, ke);
@@ -718,7 +739,7 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         return ok;
     }
     CoarseKind kind = cmode == 2 ? CoarseTF32 : CoarseF16;
-    const bool eligible = cmode != 0 && metric_ == VecSimMetric_Cosine && !multi_;
+    const bool eligible = cmode != 0 && metric_ == VecSimMetric_Cosine && !multi_ && (nq >= 16 || single_query_takes_coarse(ke));
     bool coarse = eligible && coarse_supported(v, nq, ke, kind);
     if (eligible && kind == CoarseF16 && (!coarse || !ensure_shadow(st))) { // rows too wide for TMEM, or no HBM for the shadow
         kind = CoarseTF32;

@@ -185,6 +185,7 @@ class FlatIndex {
     size_t shadow_cap_ = 0, shadow_rows_ = 0;
     std::vector<idType> shadow_dirty_;
     bool ensure_shadow(cudaStream_t st);
+    bool single_query_takes_coarse(uint32_t ke);
     size_t capacity_ = 0; // rows of HBM allocated
     size_t count_ = 0;    // rows in the index (incl. staged)
     size_t resident_ = 0; // rows already copied to HBM

@@ -209,3 +209,38 @@ def test_8bit_corpora_take_the_integer_tensor_core_route_bit_exact(vtype, metric
         assert labels[i].astype(np.int64).tolist() == pi.tolist(), (i, labels[i][:12], pi[:12])
         assert scores[i].astype(np.float32).tobytes() == ps.astype(np.float32).tobytes()
     vs.lib().VecSimB200_SetCoarseMode(-1)
+
+
+def test_single_queries_ride_the_shadow_once_a_batch_built_it():
+    """VecSimIndex_TopKQuery (one query) takes the coarse route only when an up-to-date fp16 shadow already exists;
+    the answer is the exact scan's either way, and a mutation sends single queries back to the exact scan until the
+    next batch refreshes the shadow."""
+    from redisearch_b200 import vecsim as vs
+
+    vs.lib().VecSimB200_SetCoarseMode(1)
+    n, dim, k = 70_000, 128, 10
+    rows = ol.synth_rows(ol.F32, 42, 0, n + 10, dim)
+    g = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, vs.VecSimMetric_Cosine)
+    p = ol.PortIndex(ol.F32, dim, ol.COS, tier=ol.TIER_AVX512)
+    g.add_many(rows[:n], label0=1)
+    p.add_many(rows[:n], 1)
+    qs = ol.synth_rows(ol.F32, 43, 0, 20, dim)
+
+    def check_single(expect_path):
+        for q in qs[:6]:
+            gi, gs, code = g.topk(q, k)
+            pi, ps = p.topk(q, k)
+            assert code == 0 and gi.tolist() == pi.tolist()
+            assert gs.astype(np.float32).tobytes() == ps.astype(np.float32).tobytes()
+            assert vs.lib().VecSimB200_LastBatchPath(g.h) == expect_path
+
+    check_single(0)                     # no shadow yet: exact scan
+    g.topk_batch(qs, k)                 # a batch builds it
+    assert vs.lib().VecSimB200_LastBatchPath(g.h) == 1
+    check_single(1)
+    g.add(rows[n], n + 1)               # stale shadow: single queries do not pay for the refresh
+    p.add(rows[n], n + 1)
+    check_single(0)
+    g.topk_batch(qs, k)
+    check_single(1)
+    vs.lib().VecSimB200_SetCoarseMode(-1)
