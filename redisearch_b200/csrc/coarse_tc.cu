@@ -814,6 +814,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         uint32_t thr = 0xFFFFFFFFu, cnt = 0;
         // pre-test bound in the raw accumulator domain; -inf: everything passes until the first compaction
         float thr_dot = -__int_as_float(0x7f800000);
+        if (q >= nq) thr_dot = __int_as_float(0x7f800000); // padding lanes of a partial query group: nothing ever passes
         float nq_norm = 1.0f;
         if constexpr (kOp == 2) nq_norm = q < nq ? *reinterpret_cast<const float *>(q16 + (size_t)q * q16_pitch + dim) : 1.0f;
         for (uint32_t i = 0; i < my_tiles; i++) {

@@ -555,6 +555,7 @@ VecSimQueryReply *FlatIndex::topk(const void *q, size_t k, VecSimQueryParams *qp
             ok = batch_scan(*c, c->d_query, qpitch, 1, ke, c->stream, lc, &r);
             d_res = r;
         } else {
+            last_batch_path_ = 0;
             const ScanPlan plan = plan_scan_topk(v, 1, ke);
             ok = c->need_cand(plan.cand_elems) && c->need_out(ke);
             if (ok) {
