@@ -107,3 +107,25 @@ def test_ii_header_abi_layout_matches_reference_golden(tmp_path):
     subprocess.run(["gcc", f'-DHDR="{hdr}"', os.path.join(ROOT, "tests", "abi", "ii_abi_probe.c"), "-o", str(exe)], check=True)
     mine = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert mine == open(os.path.join(ROOT, "tests", "golden", "ii_abi_layout.txt")).read()
+
+
+def test_merge_shard_topn_is_host_code_with_cmpbyscore_order():
+    """II_MergeShardTopN is the coordinator-side reducer (no device needed): score desc, docId asc on ties
+    (cmpByScore, src/result_processor.c:834-850), padding beyond counts[g] ignored."""
+    import numpy as np
+
+    from redisearch_b200 import postings
+
+    L = postings.lib()
+    G, per, n = 3, 4, 6
+    scores = np.array([[5.0, 3.0, 3.0, 99.0], [5.0, 4.0, 0.0, 0.0], [3.0, 2.5, 1.0, 0.5]], dtype=np.float64)
+    ids = np.array([[10, 7, 9, 1], [4, 20, 0, 0], [8, 30, 31, 32]], dtype=np.uint64)
+    counts = np.array([3, 2, 4], dtype=np.uint64)  # shard 0's 4th and shard 1's 3rd/4th entries are padding
+    out_i = np.zeros(n, dtype=np.uint64)
+    out_s = np.zeros(n, dtype=np.float64)
+    got = L.II_MergeShardTopN(scores.ctypes.data, ids.ctypes.data, counts.ctypes.data, G, per, n, out_i.ctypes.data, out_s.ctypes.data)
+    assert got == 6
+    assert out_i.tolist() == [4, 10, 20, 7, 8, 9] and out_s.tolist() == [5.0, 5.0, 4.0, 3.0, 3.0, 3.0]
+    got = L.II_MergeShardTopN(scores.ctypes.data, ids.ctypes.data, counts.ctypes.data, G, per, 50, np.zeros(50, dtype=np.uint64).ctypes.data,
+                              np.zeros(50).ctypes.data)
+    assert got == 9
