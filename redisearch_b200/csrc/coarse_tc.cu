@@ -1,29 +1,29 @@
-// Batched fp32 cosine KNN, stage 1: a tcgen05 coarse pass over the HBM-resident corpus that keeps, per
-// CTA and per query, the kCoarseKeep best rows by APPROXIMATE distance.  Stage 2 (rescore_kernel)
-// recomputes those candidates from the fp32 rows with the bit-exact arithmetic of distance_core.cuh and
-// stage 3 (verify) proves per query that no discarded row can belong to the exact top-k — otherwise the
-// query falls back to the exact scan.  Result: the exact answer of BruteForceIndex::topKQuery
-// (VS/algorithms/brute_force/brute_force.h:243-291) at tensor-core speed.
+// Batched KNN on the tensor cores (tcgen05, sm_100a).  Replaces, for query batches, the B independent passes of
+// BruteForceIndex::topKQuery (VS/algorithms/brute_force/brute_force.h:243-291) + the distance kernels of VS/spaces/.
 //
-// Why: 256 queries x 10M x 768 fp32 is 3.93 TFLOP per corpus pass — FMA-bound on CUDA cores
-// (DESIGN.md §4).  On the tensor cores the pass is bound by how many operand bytes each SM has to pull
-// through its L2->shared-memory port (measured ~42 B/clk/SM): every row tile is ingested once per
-// query group, so the two levers are queries per CTA (N) and bytes per element.  Two operand kinds:
-//   CoarseF16   fp16 shadow copy of the corpus (kind::f16, fp32 accumulate), 128 queries per CTA held in
-//               TENSOR MEMORY (coarse_qtmem_kernel): 1/8 of the ingest of the TF32 variant, no query
-//               re-reads from shared memory, and a TIGHTER error bound (RN to 11 significant bits vs.
-//               TF32's truncation to 11) — the default, dim <= 768;
-//   CoarseTF32  the fp32 rows themselves (kind::tf32, coarse_kernel), 32 queries per CTA in shared
-//               memory: no shadow memory, dim <= 1024.
-// Neither is precise enough for the reference's 1e-5 parity bar, hence coarse-then-exact.
+// fp32 cosine corpora — coarse-then-exact: 256 queries x 10M x 768 is 3.93 TFLOP per corpus pass,
+// FMA-bound on CUDA cores, and no tensor-core operand type reproduces the reference's fp32 bits.  So
+//   stage 1  a tcgen05 GEMM with APPROXIMATE distances keeps, per CTA row range and query, the kCoarseKeep best rows
+//            (coarse_qtmem_kernel<false,...> over an fp16 shadow copy, or coarse_kernel<CfgTF32> over the fp32 rows);
+//   stage 2  rescore_kernel recomputes those candidates from the fp32 rows with the bit-exact arithmetic of
+//            distance_core.cuh;
+//   stage 3  verify_kernel proves per query that no discarded row can belong to the exact top-k — otherwise the query
+//            falls back to the exact scan, on the device.
+// fp16 / bf16 corpora (coarse_qtmem_kernel<true,*,0>) and int8 / uint8 corpora (<true,*,1|2>, kind::i8): the
+// tensor-core result IS the distance (16-bit: fp32-accumulated exact products, bar 1e-2; 8-bit: exact integer dot
+// products + the reference's float expression, bit-exact), each CTA keeps its exact top-k.
 //
-// Kernel shape, both variants (one CTA per SM, persistent over the row tiles of its row range):
-//   warp 0   TMA producer: row tiles [rows x 128 bytes] (128B swizzle) into an n-stage ring
-//   warp 1   MMA issuer (one elected lane): tcgen05.mma.cta_group::1, K = 32 bytes per instruction,
-//            accumulator in TMEM (2 stages)
-//   warp 2   TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32, threshold test, candidate lists in shared memory with
-//            lazy compaction
+// coarse_qtmem_kernel (one CTA per SM, persistent over the 128-row tiles of its row range):
+//   warp 0    producer: row tiles into an n-stage shared-memory ring (contiguous bulk copies from the tiled shadow, or
+//             128B-swizzle tensor-map boxes from a row-major 16/8-bit corpus), multicast across the query-group cluster
+//   warp 1    MMA issuer (elect.sync lane): tcgen05.mma.cta_group::1, M = 128 queries, N = 128 rows, 32 bytes of K per
+//             instruction; the queries are the A operand from TENSOR MEMORY (first 8 K blocks) / shared memory (rest)
+//   warp 2    TMEM allocator
+//   warps 4-7 epilogue: a thread owns one query; tcgen05.ld drains an accumulator stage to registers, raw dot products
+//             are tested against a register threshold, survivors go to a per-query list in global memory that a
+//             warp-wide radix select cuts back to the best `keep`
+// coarse_kernel<CfgTF32>: the earlier SS-mode shape (32 queries per CTA in shared memory, rows = A operand), kept for
+// fp32 corpora without shadow memory (mode 2) and rows wider than 896.
 #include "coarse_tc.h"
 #include "distance_core.cuh"
 #include "topk_common.cuh"
