@@ -627,10 +627,13 @@ __device__ __forceinline__ void publish_sorted(const uint64_t *lists, int q, uin
 //   kOp = 1  int8 / uint8 operands (kind::i8), int32 accumulators, inner product: (float)(1 - dot)  (IP.cpp:248-252)
 //   kOp = 2  the same, cosine: 1 - (float)dot / (norm_row * norm_query), norms = the fp32 stored after the payload
 //            (IP.cpp:264-271).  The integer dot products are exact, so kOp 1/2 reproduce the reference bit for bit.
+//   kOp = 3  16-bit float operands, squared L2 from the GEMM: (|q|^2 + |row|^2) - 2 dot, with the squared norms of
+//            the fp32 rows / queries in row_norm2 / q_norm2 (coarse stage of the fp32 L2 route)
 template <bool kDirect, int kEpl, int kOp>
 __global__ void __launch_bounds__(kCoarseThreads, 1)
 coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t *__restrict__ shadow, size_t row_pitch,
-                    const uint8_t *__restrict__ q16, size_t q16_pitch, uint32_t n_rows, uint32_t nq, uint32_t dim, uint32_t row_bytes,
+                    const uint8_t *__restrict__ q16, size_t q16_pitch, const float *__restrict__ row_norm2,
+                    const float *__restrict__ q_norm2, uint32_t n_rows, uint32_t nq, uint32_t dim, uint32_t row_bytes,
                     uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t nstages, uint32_t csize, uint32_t nacc, uint32_t idesc,
                     uint64_t *__restrict__ list_scratch, uint64_t *__restrict__ cand_out) {
     constexpr int kQListCap = kEpl * 32;
@@ -695,7 +698,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                         const uint32_t slice_rows = kQN / csize;
                         for (uint32_t j = 0; j < kbn; j++) {
                             uint8_t *dst = sB + (size_t)s * kQStageBytes + j * kQBlockBytes + crank * slice_rows * 128;
-                            const int c0 = (int)((kb0 + j) * (kOp == 0 ? 64 : 128)), c1 = (int)(tile * kQN + crank * slice_rows);
+                            const int c0 = (int)((kb0 + j) * ((kOp == 0 || kOp == 3) ? 64 : 128)), c1 = (int)(tile * kQN + crank * slice_rows);
                             if (csize > 1)
                                 tma_load_2d_mc(dst, &map_rows, &full[s], c0, c1, cmask);
                             else
@@ -741,7 +744,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                             const uint64_t bdesc = bdesc0 + (uint64_t)(j * (kQBlockBytes >> 4));
                             if (kb < kb_tmem) { // queries from tensor memory: 8 columns per instruction
                                 const uint32_t a_tmem = tmem_q + kb * 32;
-                                if constexpr (kOp == 0) {
+                                if constexpr (kOp == 0 || kOp == 3) {
                                     umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, kb != 0);
                                     umma_ts_f16(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
                                     umma_ts_f16(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
@@ -754,7 +757,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                                 }
                             } else { // queries from shared memory
                                 const uint64_t adesc = make_smem_desc(smem_u32(sQ + (size_t)(kb - kb_tmem) * kQBlockBytes));
-                                if constexpr (kOp == 0) {
+                                if constexpr (kOp == 0 || kOp == 3) {
                                     umma_ss_f16(d_tmem, adesc, bdesc, idesc, 1);
                                     umma_ss_f16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
                                     umma_ss_f16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
@@ -817,10 +820,18 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         if (q >= nq) thr_dot = __int_as_float(0x7f800000); // padding lanes of a partial query group: nothing ever passes
         float nq_norm = 1.0f;
         if constexpr (kOp == 2) nq_norm = q < nq ? *reinterpret_cast<const float *>(q16 + (size_t)q * q16_pitch + dim) : 1.0f;
+        if constexpr (kOp == 3) nq_norm = q < nq ? q_norm2[q] : 0.0f; // |q|^2
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t tile = blockIdx.x + i * gridDim.x;
             const uint32_t a = i % nacc, aph = (i / nacc) & 1;
-            float nrm[kQN / 32]; // kOp 2: lane l holds the norms of rows h*32 + l of the tile
+            float nrm[kQN / 32]; // kOp 2 / 3: lane l holds the norm / squared norm of rows h*32 + l of the tile
+            if constexpr (kOp == 3) {
+#pragma unroll
+                for (int h = 0; h < kQN / 32; h++) {
+                    const uint32_t r = tile * kQN + h * 32 + lane;
+                    nrm[h] = r < n_rows ? __ldg(row_norm2 + r) : 0.0f;
+                }
+            }
             if constexpr (kOp == 2) {
 #pragma unroll
                 for (int h = 0; h < kQN / 32; h++) {
@@ -850,8 +861,10 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                         p = __uint_as_float(v[h][j]) > thr_dot;
                     else if constexpr (kOp == 1)
                         p = (float)(int)v[h][j] > thr_dot;
-                    else
+                    else if constexpr (kOp == 2)
                         p = (float)(int)v[h][j] > __shfl_sync(0xFFFFFFFFu, nrm[h], j) * thr_dot - 0.01f;
+                    else // d < d_thr  <=>  dot > |row|^2 / 2 + (|q|^2 - d_thr) / 2, loosened for the rounding of both sides
+                        p = __uint_as_float(v[h][j]) > fmaf(__shfl_sync(0xFFFFFFFFu, nrm[h], j), 0.499999f, thr_dot);
                     if (p) pass |= 1u << j;
                 }
                 if (row0 + 32 > n_rows) pass &= (n_rows > row0) ? ((1u << (n_rows - row0)) - 1u) : 0u; // TMA zero fill past the end
@@ -867,10 +880,12 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                         d = 1.0f - __uint_as_float(raw);
                     else if constexpr (kOp == 1)
                         d = (float)(1 - (int)raw);
-                    else {
+                    else if constexpr (kOp == 2) {
                         const uint32_t r = row0 + j; // rare path: re-read the norm (L1/L2 hit) instead of a divergent shuffle
                         const float nr = __ldg(reinterpret_cast<const float *>(shadow + (size_t)r * row_pitch + dim));
                         d = __fsub_rn(1.0f, __fdiv_rn((float)(int)raw, __fmul_rn(nr, nq_norm)));
+                    } else {
+                        d = __fsub_rn(__fadd_rn(nq_norm, __ldg(row_norm2 + row0 + j)), __fmul_rn(2.0f, __uint_as_float(raw)));
                     }
                     const uint32_t key = orderable_key(d);
                     if (key < thr) {
@@ -895,9 +910,12 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                             thr_dot = t - 4e-7f;
                         else if constexpr (kOp == 1)
                             thr_dot = t - (fabsf(t) * 1e-6f + 2.0f);
-                        else {
+                        else if constexpr (kOp == 2) {
                             const float tq = t * nq_norm;
                             thr_dot = tq - fabsf(tq) * 4e-6f;
+                        } else {
+                            const float dthr = key_to_float(thr);
+                            thr_dot = 0.5f * (nq_norm - dthr) - 2e-6f * (fabsf(nq_norm) + fabsf(dthr));
                         }
                     }
                 }
@@ -955,10 +973,11 @@ __global__ void __launch_bounds__(256) to_f16_kernel(const uint8_t *__restrict__
 // ------------------------------------------------------------------------------------------------
 // stage 2: exact rescoring of the candidates (bit-exact arithmetic of distance_core.cuh)
 // ------------------------------------------------------------------------------------------------
+template <int MT>
 __global__ void __launch_bounds__(256) rescore_kernel(const uint8_t *rows, size_t pitch, uint32_t dim, const uint8_t *queries,
                                                       size_t qpitch, uint32_t nq, uint32_t per_query,
                                                       const uint64_t *__restrict__ cand, uint64_t *__restrict__ exact) {
-    using Tile = DistTile<DT_F32, MT_IP, 1, 1>;
+    using Tile = DistTile<DT_F32, MT, 1, 1>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t total = (size_t)nq * per_query;
     for (size_t w = (size_t)blockIdx.x * 8 + warp; w < total; w += (size_t)gridDim.x * 8) {
@@ -980,10 +999,21 @@ __global__ void __launch_bounds__(256) rescore_kernel(const uint8_t *rows, size_
 // stage 3: per query, is the exact top-k provably complete?  A row that is NOT among the candidates of
 // its list has approx >= the list's worst kept approx a_w, hence exact >= a_w - eps.  If
 // a_w - eps > e_k (the k-th best exact distance found) for every FULL list, nothing was missed.
+// eps: |approx - exact| bound.  Unit vectors (cosine): the constant `eps`.  Otherwise (q_norm2 != NULL) it scales with the
+// norms — fp16 RN operands give |dot error| <= eps * |a| |q| (Cauchy-Schwarz; `eps` already holds the accumulation
+// slack) + 2^-24 sqrt(D) (|a| + |q|) for elements below the fp16 normal range; |a| <= max_norm for every row.  L2:
+// twice that (the -2 dot term) + the fp32 rounding of the squared norms, (D + 4) 2^-23 (max_norm^2 + |q|^2).
 __global__ void verify_kernel(const uint64_t *__restrict__ cand, const uint64_t *__restrict__ topk, uint32_t nq,
-                              uint32_t lists_per_query, uint32_t keep, uint32_t k, float eps, uint32_t *__restrict__ ok) {
+                              uint32_t lists_per_query, uint32_t keep, uint32_t k, float eps, const float *__restrict__ q_norm2,
+                              float max_norm, int l2, uint32_t dim, uint32_t *__restrict__ ok) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
+    if (q_norm2) {
+        const float qn2 = q_norm2[q], qn = sqrtf(qn2);
+        float e = eps * max_norm * qn + 5.97e-8f * sqrtf((float)dim) * (max_norm + qn);
+        if (l2) e = 2.0f * e + (float)(dim + 4) * 1.2e-7f * (max_norm * max_norm + qn2);
+        eps = e * 1.0001f;
+    }
     const uint64_t kth = topk[(size_t)q * k + (k - 1)];
     bool good = true;
     if (kth == kEmptySlot) {
@@ -1054,7 +1084,7 @@ static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl, bool int_cos) 
         if (int_cos) return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 2> : (const void *)coarse_qtmem_kernel<true, 8, 2>;
         return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 1> : (const void *)coarse_qtmem_kernel<true, 8, 1>;
     }
-    return (const void *)coarse_qtmem_kernel<false, 3, 0>;
+    return int_cos ? (const void *)coarse_qtmem_kernel<false, 3, 3> : (const void *)coarse_qtmem_kernel<false, 3, 0>; // fp32 route: L2 ? 
 }
 static size_t qtmem_fixed_smem(uint32_t num_kb) {
     const uint32_t kb_t = (512u - qtmem_nacc() * kQN) / 32u;
@@ -1083,7 +1113,9 @@ bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind k
         if (k > 128 || nq < 1 || c.n_rows < 65536) return false;
         return encode_fn() != nullptr;
     }
-    if (c.dtype != DT_F32 || c.metric != MT_IP) return false; // cosine on normalised rows only (eps assumes unit vectors)
+    // fp32: cosine / inner product (distance 1 - dot) or squared L2; the caller supplies the error bound (unit vectors or norms)
+    if (c.dtype != DT_F32 || (c.metric != MT_IP && c.metric != MT_L2)) return false;
+    if (kind == CoarseTF32 && c.metric != MT_IP) return false;
     if (c.dim % 8 != 0 || c.dim < 32 || c.dim > 1024) return false;
     if (c.pitch % 16 != 0) return false;
     if (k > kCoarseMaxK || nq < 1) return false; // batch_scan decides whether a small batch is worth the route
@@ -1118,7 +1150,7 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32
                 p.csize = cs;
                 break;
             }
-        const void *kfn = qtmem_kernel_fn(kind, p.epl, c.metric == MT_COS);
+        const void *kfn = qtmem_kernel_fn(kind, p.epl, kind == CoarseF16 ? c.metric == MT_L2 : c.metric == MT_COS);
         if (p.csize > 1) {
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
             cudaLaunchConfig_t cfg{};
@@ -1173,7 +1205,7 @@ static cudaError_t launch_coarse_t(const void *rows, size_t pitch, uint32_t n_ro
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
                           uint64_t *d_scratch, cudaStream_t s) {
     if (p.kind == CoarseF16 || p.kind == CoarseDirect16 || p.kind == CoarseDirect8) {
-        const void *kfn = qtmem_kernel_fn(p.kind, p.epl, o.int_cosine != 0);
+        const void *kfn = qtmem_kernel_fn(p.kind, p.epl, o.int_cosine != 0); // (CoarseF16: the flag selects the L2 epilogue)
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
         if (e != cudaSuccess) return e;
         CUtensorMap mr{};
@@ -1203,9 +1235,10 @@ cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim
         cfg.attrs = at, cfg.numAttrs = 1;
         const uint8_t *rows = static_cast<const uint8_t *>(o.rows), *qs = static_cast<const uint8_t *>(o.queries);
         size_t rp = o.pitch, qp = o.qpitch;
+        const float *rn2 = o.row_norm2, *qn2 = o.q_norm2;
         uint32_t a_nrows = n_rows, a_nq = nq, a_dim = dim, a_rb = row_bytes, a_kb = p.num_kb, a_tiles = p.tiles, a_keep = p.keep,
                  a_st = p.stages, a_cs = p.csize, a_nacc = qtmem_nacc(), a_idesc = idesc;
-        void *args[] = {&mr,    &rows,   &rp,   &qs,   &qp,     &a_nrows, &a_nq,      &a_dim, &a_rb,
+        void *args[] = {&mr,    &rows,   &rp,   &qs,   &qp,     &rn2, &qn2, &a_nrows, &a_nq,      &a_dim, &a_rb,
                         &a_kb,  &a_tiles, &a_keep, &a_st, &a_cs, &a_nacc,  &a_idesc, &d_scratch, &d_cand};
         return cudaLaunchKernelExC(&cfg, kfn, args);
     }
@@ -1252,6 +1285,42 @@ cudaError_t launch_to_f16_tiled(const void *src, size_t spitch, uint32_t dim, ui
     return cudaGetLastError();
 }
 
+// squared norm of fp32 rows [first, first+n) -> norm2[first + r]; running maxima (as float bits: the values are >= 0,
+// a NaN compares as huge and disables the route) of the squared norm and of |x| into stats[0], stats[1]
+__global__ void __launch_bounds__(256) row_stats_kernel(const uint8_t *__restrict__ rows, size_t pitch, uint32_t dim, uint32_t first,
+                                                        uint32_t n, float *__restrict__ norm2, uint32_t *__restrict__ stats) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t r = blockIdx.x * 8 + warp; r < n; r += gridDim.x * 8) {
+        const float *x = reinterpret_cast<const float *>(rows + (size_t)(first + r) * pitch);
+        float s = 0.0f, m = 0.0f;
+        for (uint32_t i = lane; i < dim; i += 32) {
+            const float v = x[i];
+            s = fmaf(v, v, s);
+            m = fmaxf(m, fabsf(v));
+            if (v != v) m = __int_as_float(0x7f800000);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+            m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        }
+        if (lane == 0) {
+            norm2[first + r] = s;
+            if (stats) {
+                atomicMax(&stats[0], __float_as_uint(s));
+                atomicMax(&stats[1], __float_as_uint(m));
+            }
+        }
+    }
+}
+cudaError_t launch_row_stats(const void *rows, size_t pitch, uint32_t dim, uint32_t first, uint32_t n, float *d_norm2, uint32_t *d_stats,
+                             cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t grid = std::max(1u, std::min((n + 7) / 8, (uint32_t)device_sm_count() * 8));
+    row_stats_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(rows), pitch, dim, first, n, d_norm2, d_stats);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_to_f16(const void *src, size_t spitch, uint32_t dim, uint32_t first, uint32_t n, void *dst, size_t dpitch,
                           cudaStream_t s) {
     if (n == 0) return cudaSuccess;
@@ -1265,14 +1334,19 @@ cudaError_t launch_rescore(const CorpusView &c, const void *d_queries, size_t qp
                            const uint64_t *d_cand, uint64_t *d_exact, cudaStream_t s) {
     const size_t total = (size_t)nq * per_query;
     const uint32_t grid = (uint32_t)std::max<size_t>(1, std::min<size_t>((total + 7) / 8, (size_t)device_sm_count() * 8));
-    rescore_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(c.rows), c.pitch, c.dim, static_cast<const uint8_t *>(d_queries),
-                                        qpitch, nq, per_query, d_cand, d_exact);
+    if (c.metric == MT_L2)
+        rescore_kernel<MT_L2><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(c.rows), c.pitch, c.dim,
+                                                   static_cast<const uint8_t *>(d_queries), qpitch, nq, per_query, d_cand, d_exact);
+    else
+        rescore_kernel<MT_IP><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(c.rows), c.pitch, c.dim,
+                                                   static_cast<const uint8_t *>(d_queries), qpitch, nq, per_query, d_cand, d_exact);
     return cudaGetLastError();
 }
 
 cudaError_t launch_verify(const uint64_t *d_cand, const uint64_t *d_topk, uint32_t nq, uint32_t lists_per_query, uint32_t keep,
-                          uint32_t k, float eps, uint32_t *d_ok, cudaStream_t s) {
-    verify_kernel<<<(nq + 127) / 128, 128, 0, s>>>(d_cand, d_topk, nq, lists_per_query, keep, k, eps, d_ok);
+                          uint32_t k, float eps, const float *d_q_norm2, float max_norm, int l2, uint32_t dim, uint32_t *d_ok,
+                          cudaStream_t s) {
+    verify_kernel<<<(nq + 127) / 128, 128, 0, s>>>(d_cand, d_topk, nq, lists_per_query, keep, k, eps, d_q_norm2, max_norm, l2, dim, d_ok);
     return cudaGetLastError();
 }
 

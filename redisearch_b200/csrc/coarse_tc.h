@@ -37,7 +37,10 @@ struct CoarseOperands {
     const void *queries;
     size_t qpitch;
     int elem_variant; // CoarseDirect16: 1 = bfloat16 (else IEEE half); CoarseDirect8: 1 = int8 (else uint8)
-    int int_cosine;   // CoarseDirect8: cosine (rows carry their fp32 norm after the payload) instead of inner product
+    int int_cosine;   // CoarseDirect8: cosine (rows carry their fp32 norm after the payload) instead of inner product;
+                      // CoarseF16: squared-L2 epilogue (needs the two arrays below)
+    const float *row_norm2; // CoarseF16 / L2: |row|^2 per row (fp32 rows)
+    const float *q_norm2;   //                 |q|^2 per query
 };
 bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind kind);
 CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32_t k);
@@ -52,7 +55,13 @@ cudaError_t launch_to_f16(const void *src, size_t spitch, uint32_t dim, uint32_t
                           cudaStream_t s);
 cudaError_t launch_rescore(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t per_query,
                            const uint64_t *d_cand, uint64_t *d_exact, cudaStream_t s);
+// q_norm2 == NULL: unit vectors, |approx - exact| <= eps.  Otherwise the bound scales with max_norm (over all rows) and
+// |q| (see verify_kernel); l2 != 0: distances are squared L2 instead of 1 - dot.
 cudaError_t launch_verify(const uint64_t *d_cand, const uint64_t *d_topk, uint32_t nq, uint32_t lists_per_query, uint32_t keep,
-                          uint32_t k, float eps, uint32_t *d_ok, cudaStream_t s);
+                          uint32_t k, float eps, const float *d_q_norm2, float max_norm, int l2, uint32_t dim, uint32_t *d_ok,
+                          cudaStream_t s);
+// |row|^2 of fp32 rows [first, first+n) into d_norm2[first..]; d_stats (nullable) = {max |row|^2, max |x|} as float bits
+cudaError_t launch_row_stats(const void *rows, size_t pitch, uint32_t dim, uint32_t first, uint32_t n, float *d_norm2, uint32_t *d_stats,
+                             cudaStream_t s);
 
 } // namespace rsb200

@@ -206,6 +206,8 @@ FlatIndex::~FlatIndex() {
     }
     cudaFree(d_rows_);
     cudaFree(d_shadow_);
+    cudaFree(d_norm2_);
+    cudaFree(d_stats_);
     cudaFree(d_label_to_id_);
     cudaFree(d_id_to_label_);
     cudaFreeHost(h_stage_);
@@ -656,7 +658,8 @@ static int coarse_mode() {
 // Single queries (and batches below 16) take the tensor-core route only if that costs nothing extra: mode 1, an fp16
 // shadow that is already complete, fp32 cosine, k within the coarse lists.
 bool FlatIndex::single_query_takes_coarse(uint32_t ke) {
-    if (coarse_mode() != 1 || multi_ || metric_ != VecSimMetric_Cosine || dtype_ != DT_F32) return false;
+    if (coarse_mode() != 1 || multi_ || dtype_ != DT_F32) return false;
+    if (metric_ != VecSimMetric_Cosine && !(shadow_max_abs_ <= 60000.0f)) return false; // fp16 range (also false before the first build)
     {
         std::lock_guard<std::mutex> g(mu_);
         if (!d_shadow_ || shadow_rows_ != count_ || !shadow_dirty_.empty() || shadow_cap_ < count_) return false;
@@ -678,6 +681,18 @@ bool FlatIndex::ensure_shadow(cudaStream_t st) {
         }
         cudaFree(d_shadow_); // rows are re-converted below; converting 10M x 768 takes ~7 ms
         d_shadow_ = nu;
+        if (metric_ != VecSimMetric_Cosine) { // L2 / raw inner product: the error bound and the L2 epilogue need |row|^2
+            cudaFree(d_norm2_);
+            d_norm2_ = nullptr;
+            if (!d_stats_ && (cudaMalloc(&d_stats_, 8) != cudaSuccess || cudaMemset(d_stats_, 0, 8) != cudaSuccess)) {
+                cudaGetLastError();
+                return false;
+            }
+            if (cudaMalloc(&d_norm2_, cap * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+        }
         shadow_cap_ = cap;
         shadow_rows_ = 0;
         shadow_dirty_.clear();
@@ -691,6 +706,7 @@ bool FlatIndex::ensure_shadow(cudaStream_t st) {
     for (idType id : shadow_dirty_)
         if (id < shadow_rows_) {
             if (launch_to_f16_tiled(d_rows_, pitch_, (uint32_t)dim_, id, 1, d_shadow_, st) != cudaSuccess) return false;
+            if (d_norm2_ && launch_row_stats(d_rows_, pitch_, (uint32_t)dim_, id, 1, d_norm2_, d_stats_, st) != cudaSuccess) return false;
             launched = true;
         }
     shadow_dirty_.clear();
@@ -698,11 +714,25 @@ bool FlatIndex::ensure_shadow(cudaStream_t st) {
         if (launch_to_f16_tiled(d_rows_, pitch_, (uint32_t)dim_, (uint32_t)shadow_rows_, (uint32_t)(count_ - shadow_rows_), d_shadow_,
                                 st) != cudaSuccess)
             return false;
+        if (d_norm2_ && launch_row_stats(d_rows_, pitch_, (uint32_t)dim_, (uint32_t)shadow_rows_, (uint32_t)(count_ - shadow_rows_), d_norm2_,
+                                         d_stats_, st) != cudaSuccess)
+            return false;
         shadow_rows_ = count_;
         launched = true;
     }
     // other query streams may read the shadow as soon as the lock is released
-    if (launched && cudaStreamSynchronize(st) != cudaSuccess) return false;
+    if (launched) {
+        uint32_t h[2] = {0, 0};
+        if (d_norm2_ && cudaMemcpyAsync(h, d_stats_, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return false;
+        if (d_norm2_) { // running maxima over every row ever converted (deletes do not lower them: conservative)
+            float n2, ma;
+            memcpy(&n2, &h[0], 4);
+            memcpy(&ma, &h[1], 4);
+            shadow_max_norm_ = std::sqrt(n2);
+            shadow_max_abs_ = ma;
+        }
+    }
     return true;
 }
 
@@ -729,7 +759,7 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         last_batch_path_ = 2;
         c.d_last_ok = nullptr;
         c.last_ok_n = 0;
-        const CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, (dtype_ == DT_BF16 || dtype_ == DT_I8) ? 1 : 0, mkind_ == MT_COS ? 1 : 0};
+        const CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, (dtype_ == DT_BF16 || dtype_ == DT_I8) ? 1 : 0, mkind_ == MT_COS ? 1 : 0, nullptr, nullptr};
         cudaEventRecord(c.ev_start, st);
         bool ok = launch_coarse(ops, v.n_rows, v.dim, nq, cp, c.d_cand, c.d_cand + nA, st) == cudaSuccess;
         cudaEventRecord(c.ev_stop, st);
@@ -740,12 +770,16 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         return ok;
     }
     CoarseKind kind = cmode == 2 ? CoarseTF32 : CoarseF16;
-    const bool eligible = cmode != 0 && metric_ == VecSimMetric_Cosine && !multi_ && (nq >= 16 || single_query_takes_coarse(ke));
+    // cosine: unit vectors, constant error bound, either operand kind.  L2 / raw inner product (fp32): the fp16 route only,
+    // error bound from the row and query norms
+    const bool unit = metric_ == VecSimMetric_Cosine;
+    const bool eligible = cmode != 0 && !multi_ && dtype_ == DT_F32 && (unit || cmode == 1) && (nq >= 16 || single_query_takes_coarse(ke));
     bool coarse = eligible && coarse_supported(v, nq, ke, kind);
     if (eligible && kind == CoarseF16 && (!coarse || !ensure_shadow(st))) { // rows too wide for TMEM, or no HBM for the shadow
         kind = CoarseTF32;
-        coarse = coarse_supported(v, nq, ke, kind);
+        coarse = unit && coarse_supported(v, nq, ke, kind);
     }
+    if (coarse && !unit && !(shadow_max_abs_ <= 60000.0f)) coarse = false; // values outside the fp16 range (or NaN): exact scan
     last_batch_coarse_ = coarse;
     last_batch_path_ = coarse ? 1 : 0;
     if (!coarse) {
@@ -762,27 +796,31 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     const size_t nA = (size_t)nq * per_query, nO = (size_t)nq * ke;
     const size_t q16_pitch = (dim_ * 2 + 15) & ~(size_t)15;
     const size_t q16_elems = kind == CoarseF16 ? ((size_t)nq * q16_pitch + 7) / 8 : 0;
-    const size_t total = 2 * nA + 2 * nO + sp.cand_elems + q16_elems + cp.scratch_elems + (nq + 1) / 2 + 8;
+    const size_t qn_elems = unit ? 0 : (nq + 1) / 2 + 1; // |q|^2 per query (floats)
+    const size_t total = 2 * nA + 2 * nO + sp.cand_elems + q16_elems + cp.scratch_elems + qn_elems + (nq + 1) / 2 + 8;
     if (!c.need_cand(total) || !c.need_out(nO)) return false;
     uint64_t *coarse_cand = c.d_cand, *exact = coarse_cand + nA, *out1 = exact + nA, *out2 = out1 + nO, *cand2 = out2 + nO;
     uint64_t *q16 = cand2 + sp.cand_elems;
     uint64_t *list_scratch = q16 + q16_elems;
-    uint32_t *d_ok = reinterpret_cast<uint32_t *>(list_scratch + cp.scratch_elems);
+    float *d_qn2 = unit ? nullptr : reinterpret_cast<float *>(list_scratch + cp.scratch_elems);
+    uint32_t *d_ok = reinterpret_cast<uint32_t *>(list_scratch + cp.scratch_elems + qn_elems);
     c.d_last_ok = d_ok;
     c.last_ok_n = nq;
-    CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, 0, 0};
+    CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, 0, 0, nullptr, nullptr};
     bool ok = true;
     if (kind == CoarseF16) {
         ok = launch_to_f16(d_q, qpitch, (uint32_t)dim_, 0, nq, q16, q16_pitch, st) == cudaSuccess;
-        ops = CoarseOperands{d_shadow_, 0, q16, q16_pitch, 0, 0};
-        lc.launches++;
+        ops = CoarseOperands{d_shadow_, 0, q16, q16_pitch, 0, mkind_ == MT_L2 ? 1 : 0, d_norm2_, d_qn2};
+        if (!unit) ok = ok && launch_row_stats(d_q, qpitch, (uint32_t)dim_, 0, nq, d_qn2, nullptr, st) == cudaSuccess;
+        lc.launches += unit ? 1 : 2;
     }
     cudaEventRecord(c.ev_start, st);
     ok = ok && launch_coarse(ops, v.n_rows, v.dim, nq, cp, coarse_cand, list_scratch, st) == cudaSuccess;
     cudaEventRecord(c.ev_stop, st);
     ok = ok && launch_rescore(v, d_q, qpitch, nq, (uint32_t)per_query, coarse_cand, exact, st) == cudaSuccess;
     ok = ok && launch_final_select(exact, nq, (uint32_t)per_query, ke, out1, st, &lc) == cudaSuccess;
-    ok = ok && launch_verify(coarse_cand, out1, nq, cp.grid_x, cp.keep, ke, coarse_eps(kind), d_ok, st) == cudaSuccess;
+    ok = ok && launch_verify(coarse_cand, out1, nq, cp.grid_x, cp.keep, ke, coarse_eps(kind), d_qn2, shadow_max_norm_, mkind_ == MT_L2 ? 1 : 0,
+                             (uint32_t)dim_, d_ok, st) == cudaSuccess;
     // exact fallback, entirely on device: CTAs whose queries are all verified exit at once
     ok = ok && launch_scan_topk(v, d_q, qpitch, nq, ke, sp, cand2, st, &lc, d_ok) == cudaSuccess;
     ok = ok && launch_final_select(cand2, nq, sp.lists_per_query * ke, ke, out2, st, &lc) == cudaSuccess;

@@ -10,6 +10,7 @@
 #include "vecsim_kernels.h"
 
 #include <atomic>
+#include <limits>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -183,6 +184,10 @@ class FlatIndex {
     // valid except shadow_dirty_
     uint8_t *d_shadow_ = nullptr;
     size_t shadow_cap_ = 0, shadow_rows_ = 0;
+    // L2 / raw inner-product indexes: |row|^2 per row and the running maxima the error bound needs
+    float *d_norm2_ = nullptr;
+    uint32_t *d_stats_ = nullptr;
+    float shadow_max_norm_ = 0.0f, shadow_max_abs_ = std::numeric_limits<float>::infinity();
     std::vector<idType> shadow_dirty_;
     bool ensure_shadow(cudaStream_t st);
     bool single_query_takes_coarse(uint32_t ke);

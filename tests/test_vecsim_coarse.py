@@ -244,3 +244,58 @@ def test_single_queries_ride_the_shadow_once_a_batch_built_it():
     g.topk_batch(qs, k)
     check_single(1)
     vs.lib().VecSimB200_SetCoarseMode(-1)
+
+
+@pytest.mark.parametrize("metric,n,dim,nq,k", [(ol.L2, 70_000, 128, 40, 10), (ol.IP, 66_000, 768, 130, 10), (ol.L2, 140_000, 96, 300, 16),
+                                               (ol.L2, 66_000, 768, 64, 10)])
+def test_fp32_l2_and_raw_ip_batches_take_the_coarse_route_exactly(metric, n, dim, nq, k):
+    """fp32 L2 / raw inner product: same coarse-then-exact pipeline, the GEMM runs on the fp16 shadow of the raw rows, squared
+    L2 is assembled from the dot product and the squared norms, and the proof's error bound scales with the row / query
+    norms.  ids and score bits must equal the oracle's exact scan."""
+    import torch
+
+    from redisearch_b200 import vecsim as vs
+
+    vs.lib().VecSimB200_SetCoarseMode(1)
+    mt = {ol.L2: vs.VecSimMetric_L2, ol.IP: vs.VecSimMetric_IP}[metric]
+    rows = ol.synth_rows(ol.F32, 42, 0, n, dim)
+    g = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, mt)
+    p = ol.PortIndex(ol.F32, dim, metric, tier=ol.TIER_AVX512)
+    assert g.add_many(rows, label0=1) == n
+    p.add_many(rows, 1)
+    qs = ol.synth_rows(ol.F32, 43, 0, nq, dim)
+    labels, scores, flags = _device_batch(vs, torch, g, qs, k)
+    assert vs.lib().VecSimB200_LastBatchPath(g.h) == 1 and flags is not None
+    assert flags.sum() >= nq * 0.9, f"only {int(flags.sum())}/{nq} queries were verified by the coarse path"
+    for i in range(nq):
+        pi, ps = p.topk(qs[i], k)
+        assert labels[i].tolist() == pi.tolist(), (i, flags[i], labels[i], pi)
+        assert scores[i].tobytes() == ps.astype(np.float32).tobytes()
+    # a single query rides the same shadow
+    gi, gs, code = g.topk(qs[0], k)
+    pi, ps = p.topk(qs[0], k)
+    assert code == 0 and gi.tolist() == pi.tolist() and gs.astype(np.float32).tobytes() == ps.astype(np.float32).tobytes()
+    assert vs.lib().VecSimB200_LastBatchPath(g.h) == 1
+    vs.lib().VecSimB200_SetCoarseMode(-1)
+
+
+def test_values_outside_the_fp16_range_keep_l2_batches_on_the_exact_scan():
+    import torch
+
+    from redisearch_b200 import vecsim as vs
+
+    vs.lib().VecSimB200_SetCoarseMode(1)
+    n, dim, nq, k = 70_000, 64, 32, 10
+    rows = ol.synth_rows(ol.F32, 42, 0, n, dim)
+    rows[123, 5] = 1.0e5  # does not fit an IEEE half
+    g = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, vs.VecSimMetric_L2)
+    p = ol.PortIndex(ol.F32, dim, ol.L2, tier=ol.TIER_AVX512)
+    g.add_many(rows, label0=1)
+    p.add_many(rows, 1)
+    qs = ol.synth_rows(ol.F32, 43, 0, nq, dim)
+    labels, scores, flags = _device_batch(vs, torch, g, qs, k)
+    assert vs.lib().VecSimB200_LastBatchPath(g.h) == 0 and flags is None
+    for i in range(nq):
+        pi, ps = p.topk(qs[i], k)
+        assert labels[i].tolist() == pi.tolist() and scores[i].tobytes() == ps.astype(np.float32).tobytes()
+    vs.lib().VecSimB200_SetCoarseMode(-1)
