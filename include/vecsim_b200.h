@@ -427,7 +427,8 @@ int VecSimB200_MergeShardTopK(const float *d_scores, const int64_t *d_labels, si
  * labels too sparse for the dense docId -> row table) — the caller then stays on VecSimIndex_GetDistanceFrom_Unsafe. */
 int VecSimB200_TopKFiltered(VecSimIndex *index, const void *queryBlob, size_t k, const uint32_t *doc_ids, size_t n, int ids_on_device,
                             size_t *out_labels, double *out_scores, size_t *out_count);
-/* Batched fp32 cosine queries (nq >= 16, k <= 16, dim % 8 == 0, >= 65536 rows) take a tcgen05 coarse
+/* Batched fp32 queries (cosine, and in mode 1 also L2 and raw inner product; nq >= 16, k <= 16, dim % 8 == 0,
+ * >= 65536 rows) take a tcgen05 coarse
  * pass + exact rescoring from the fp32 rows + a per-query completeness proof, with the exact scan as
  * on-device fallback (csrc/coarse_tc.cu); results are identical either way.  mode: 0 = exact scans only,
  * 1 = coarse pass over an fp16 shadow copy of the rows (+50% HBM, built lazily by the first eligible
