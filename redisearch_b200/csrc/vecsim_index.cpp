@@ -658,7 +658,7 @@ static int coarse_mode() {
 // Single queries (and batches below 16) take the tensor-core route only if that costs nothing extra: mode 1, an fp16
 // shadow that is already complete, fp32 cosine, k within the coarse lists.
 bool FlatIndex::single_query_takes_coarse(uint32_t ke) {
-    if (coarse_mode() != 1 || multi_ || dtype_ != DT_F32) return false;
+    if (coarse_mode() != 1 || multi_ || coarse_disabled_ || dtype_ != DT_F32) return false;
     if (metric_ != VecSimMetric_Cosine && !(shadow_max_abs_ <= 60000.0f)) return false; // fp16 range (also false before the first build)
     {
         std::lock_guard<std::mutex> g(mu_);
@@ -773,13 +773,25 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     // cosine: unit vectors, constant error bound, either operand kind.  L2 / raw inner product (fp32): the fp16 route only,
     // error bound from the row and query norms
     const bool unit = metric_ == VecSimMetric_Cosine;
-    const bool eligible = cmode != 0 && !multi_ && dtype_ == DT_F32 && (unit || cmode == 1) && (nq >= 16 || single_query_takes_coarse(ke));
+    const bool eligible = cmode != 0 && !multi_ && !coarse_disabled_ && dtype_ == DT_F32 && (unit || cmode == 1) &&
+                          (nq >= 16 || single_query_takes_coarse(ke));
     bool coarse = eligible && coarse_supported(v, nq, ke, kind);
     if (eligible && kind == CoarseF16 && (!coarse || !ensure_shadow(st))) { // rows too wide for TMEM, or no HBM for the shadow
         kind = CoarseTF32;
         coarse = unit && coarse_supported(v, nq, ke, kind);
     }
-    if (coarse && !unit && !(shadow_max_abs_ <= 60000.0f)) coarse = false; // values outside the fp16 range (or NaN): exact scan
+    if (coarse && !unit && !(shadow_max_abs_ <= 60000.0f)) {
+        // values outside the fp16 range (or NaN): this index stays on the exact scan; give the shadow's HBM back
+        coarse = false;
+        std::lock_guard<std::mutex> g(mu_);
+        coarse_disabled_ = true;
+        cudaFree(d_shadow_);
+        cudaFree(d_norm2_);
+        d_shadow_ = nullptr;
+        d_norm2_ = nullptr;
+        shadow_cap_ = shadow_rows_ = 0;
+        shadow_dirty_.clear();
+    }
     last_batch_coarse_ = coarse;
     last_batch_path_ = coarse ? 1 : 0;
     if (!coarse) {

@@ -188,6 +188,7 @@ class FlatIndex {
     float *d_norm2_ = nullptr;
     uint32_t *d_stats_ = nullptr;
     float shadow_max_norm_ = 0.0f, shadow_max_abs_ = std::numeric_limits<float>::infinity();
+    std::atomic<bool> coarse_disabled_{false}; // L2 / IP index with values outside the fp16 range: exact scans only
     std::vector<idType> shadow_dirty_;
     bool ensure_shadow(cudaStream_t st);
     bool single_query_takes_coarse(uint32_t ke);
