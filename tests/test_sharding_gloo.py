@@ -145,3 +145,26 @@ def test_shard_ranges_partition_exactly():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_posting_lists_split_exactly_at_the_docid_boundaries():
+    sys.path.insert(0, ROOT)
+    from redisearch_b200 import sharding
+
+    rng = np.random.default_rng(0)
+    n_docs = 100_003
+    ids = np.unique(rng.integers(1, n_docs + 1, 40_000)).astype(np.uint64)
+    fr = rng.integers(1, 9, len(ids)).astype(np.uint32)
+    for world in (1, 2, 3, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = sharding.doc_range(n_docs, world, r)
+            a, f = sharding.split_posting_list(ids, fr, lo, hi)
+            assert len(a) == len(f) and (len(a) == 0 or (a[0] > lo and a[-1] <= hi))
+            parts.append((a, f))
+        assert np.concatenate([a for a, _ in parts]).tolist() == ids.tolist()   # disjoint, ordered, complete
+        assert np.concatenate([f for _, f in parts]).tolist() == fr.tolist()
+    # a docId equal to a boundary belongs to the lower shard: ranges are (lo, hi]
+    lo, hi = sharding.doc_range(10, 2, 0)
+    a, _ = sharding.split_posting_list(np.array([hi, hi + 1], dtype=np.uint64), None, lo, hi)
+    assert a.tolist() == [hi]
