@@ -288,3 +288,29 @@ def test_reference_scorers_reproduce_their_own_golden():
     for doc_len, total, _ in g["cases"]:
         s = ol.reference_score(ol.SCORER_BM25STD, [10, 10], [0, 0], [idf, idf], [1.0, 1.0], 1.0, doc_len, 10, 1.0, 3, g["avg_doc_len"])
         assert f"{s:.2f}" == f"{total:.2f}"
+
+
+def test_union_reference_edge_cases(L):
+    """rqe_iterators/tests/integration/union_common.rs:243-452 — the reference's own known answers."""
+    E = G["union_edge_cases"]
+
+    def run(children, **kw):
+        idx = [ol.InvIndex(ol.CODEC_DOCIDS_ONLY, np.array(c, dtype=np.uint64)) for c in children]
+        return idx, [h[0] for h in ol.run_intersect(idx, union=True, **kw)]
+
+    for name in ("disjoint", "overlapping", "empty_mixed", "all_empty"):
+        for quick in (False, True):
+            _, got = run(E[name]["children"], quick=quick)
+            assert got == E[name]["expected"], (name, quick, got)
+    for name in ("skip_exact", "skip_not_found", "skip_past_eof"):
+        idx = [ol.InvIndex(ol.CODEC_DOCIDS_ONLY, np.array(c, dtype=np.uint64)) for c in E[name]["children"]]
+        readers = [ix.reader() for ix in idx]
+        arr = (C.c_void_p * len(readers))(*readers)
+        t = (C.c_uint64 * 1)(*E[name]["targets"])
+        st, landed = (C.c_int * 1)(), (C.c_uint64 * 1)()
+        L.orc_union_skipto(arr, len(readers), t, 1, st, landed)
+        assert list(st) == E[name]["status"], name
+        if "landed" in E[name]:
+            assert list(landed) == E[name]["landed"], name
+        for r in readers:
+            L.orc_reader_free(r)

@@ -384,3 +384,38 @@ def test_docid_range_shards_merge_to_the_unsharded_topn(ps):
                                          out_s.ctypes.data)
         assert total == e_tot and got == len(e_ids)
         assert out_i[:got].tolist() == e_ids.tolist() and out_s[:got].tobytes() == e_sc.tobytes()
+
+
+def test_union_reference_edge_cases_through_the_iterator(ps):
+    """rqe_iterators/tests/integration/union_common.rs:243-452 — the reference's known answers for Union (disjoint,
+    overlapping, empty children, skip_to exact / not found / past EOF + rewind, interleaved read and skip_to), through
+    II_Union and the QueryIterator facade."""
+    E = G["union_edge_cases"]
+
+    def lists_of(children):
+        return [ps.PostingList.from_arrays(np.array(c, dtype=np.uint64)) for c in children]
+
+    for name in ("disjoint", "overlapping", "empty_mixed", "all_empty"):
+        for quick in (False, True):
+            ids, _, _ = ps.union(lists_of(E[name]["children"]), quick_exit=quick).fetch(want_freqs=False)
+            assert ids.tolist() == E[name]["expected"], (name, quick, ids)
+    it = ps.union(lists_of(E["skip_exact"]["children"])).into_iterator()
+    q = it.contents
+    assert q.SkipTo(it, 30) == ps.ITERATOR_OK and q.lastDocId == 30
+    q.Rewind(it)
+    assert q.SkipTo(it, 22) == ps.ITERATOR_NOTFOUND and q.lastDocId == 25
+    q.Free(it)
+    it = ps.union(lists_of(E["skip_past_eof"]["children"])).into_iterator()
+    q = it.contents
+    assert q.SkipTo(it, 100) == ps.ITERATOR_EOF and q.atEOF
+    q.Rewind(it)
+    assert not q.atEOF and q.Read(it) == ps.ITERATOR_OK and q.lastDocId == 10
+    q.Free(it)
+    # union_common.rs:331-352
+    it = ps.union(lists_of([[10, 20, 30, 40, 50, 60, 70, 80], [15, 25, 35, 45, 55, 65, 75, 85]])).into_iterator()
+    q = it.contents
+    assert q.Read(it) == ps.ITERATOR_OK and q.lastDocId == 10
+    assert q.SkipTo(it, 35) == ps.ITERATOR_OK and q.lastDocId == 35
+    assert q.Read(it) == ps.ITERATOR_OK and q.lastDocId == 40
+    assert q.SkipTo(it, 70) == ps.ITERATOR_OK and q.lastDocId == 70
+    q.Free(it)
