@@ -314,3 +314,25 @@ def test_union_reference_edge_cases(L):
             assert list(landed) == E[name]["landed"], name
         for r in readers:
             L.orc_reader_free(r)
+
+
+def test_intersection_reference_edge_cases(L):
+    """rqe_iterators/tests/integration/intersection.rs:325-521, 876-931 — the reference's own known answers."""
+    E = G["intersection_edge_cases"]
+    for name, case in E.items():
+        if name.startswith("_"):
+            continue
+        idx = [ol.InvIndex(ol.CODEC_DOCIDS_ONLY, np.array(c, dtype=np.uint64)) for c in case["children"]]
+        if "expected" in case:
+            assert [h[0] for h in ol.run_intersect(idx)] == case["expected"], name
+        for target, status, landed in case.get("skips", []):  # each skip on a fresh (rewound) iterator
+            readers = [ix.reader() for ix in idx]
+            arr = (C.c_void_p * len(readers))(*readers)
+            t = (C.c_uint64 * 1)(target)
+            st, ld = (C.c_int * 1)(), (C.c_uint64 * 1)()
+            L.orc_intersect_skipto(arr, len(readers), t, 1, st, ld)
+            assert st[0] == status, (name, target, st[0])
+            if status != 2:
+                assert ld[0] == landed, (name, target, ld[0])
+            for r in readers:
+                L.orc_reader_free(r)

@@ -419,3 +419,46 @@ def test_union_reference_edge_cases_through_the_iterator(ps):
     assert q.Read(it) == ps.ITERATOR_OK and q.lastDocId == 40
     assert q.SkipTo(it, 70) == ps.ITERATOR_OK and q.lastDocId == 70
     q.Free(it)
+
+
+def test_intersection_reference_edge_cases_through_the_iterator(ps):
+    """rqe_iterators/tests/integration/intersection.rs:325-521, 876-931 through II_Intersect and the QueryIterator
+    facade: empty / single-element / single-child / overlapping result sets, 10^7 docId gaps, skip_to exact / not found /
+    past EOF (then Read and SkipTo stay at EOF until Rewind), sequential and interleaved skip_to."""
+    E = G["intersection_edge_cases"]
+
+    def lists_of(children):
+        return [ps.PostingList.from_arrays(np.array(c, dtype=np.uint64)) for c in children]
+
+    status = {0: ps.ITERATOR_OK, 1: ps.ITERATOR_NOTFOUND, 2: ps.ITERATOR_EOF}
+    for name, case in E.items():
+        if name.startswith("_"):
+            continue
+        if "expected" in case:
+            ids, _, _ = ps.intersect(lists_of(case["children"])).fetch(want_freqs=False)
+            assert ids.tolist() == case["expected"], name
+        if "skips" in case:
+            it = ps.intersect(lists_of(case["children"])).into_iterator()
+            q = it.contents
+            for target, st, landed in case["skips"]:
+                q.Rewind(it)
+                assert q.SkipTo(it, target) == status[st], (name, target)
+                if st != 2:
+                    assert q.lastDocId == landed
+                else:
+                    assert q.atEOF and q.Read(it) == ps.ITERATOR_EOF and q.SkipTo(it, 10) == ps.ITERATOR_EOF
+            q.Free(it)
+    ids10 = list(range(10, 101, 10))
+    it = ps.intersect(lists_of([ids10, ids10])).into_iterator()
+    q = it.contents
+    for i in ids10[:5]:  # skip_to_sequential
+        assert q.SkipTo(it, i) == ps.ITERATOR_OK and q.lastDocId == i
+    q.Rewind(it)         # interleaved_read_and_skip_to
+    assert q.Read(it) == ps.ITERATOR_OK and q.lastDocId == 10
+    assert q.SkipTo(it, 40) == ps.ITERATOR_OK and q.lastDocId == 40
+    assert q.Read(it) == ps.ITERATOR_OK and q.lastDocId == 50
+    assert q.SkipTo(it, 80) == ps.ITERATOR_OK and q.lastDocId == 80
+    assert q.Read(it) == ps.ITERATOR_OK and q.lastDocId == 90
+    assert q.Read(it) == ps.ITERATOR_OK and q.lastDocId == 100
+    assert q.Read(it) == ps.ITERATOR_EOF
+    q.Free(it)
