@@ -70,6 +70,7 @@ size_t VecSimIndex_IndexSize(VecSimIndex *index) { return IX(index)->size(); }
 // ---------------------------------------------------------------------------------- queries
 VecSimQueryReply *VecSimIndex_TopKQuery(VecSimIndex *index, const void *queryBlob, size_t k,
                                         VecSimQueryParams *queryParams, VecSimQueryReply_Order order) {
+    if (rsb200::FlatIndex::microbatch_window_us() > 0) return IX(index)->topk_combined(queryBlob, k, queryParams, order);
     return IX(index)->topk(queryBlob, k, queryParams, order);
 }
 

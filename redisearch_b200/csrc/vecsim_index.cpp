@@ -3,6 +3,7 @@
 #include "host_numeric.h"
 #include "topk_common.cuh"
 #include "coarse_tc.h"
+#include "micro_batcher.h"
 
 #include <algorithm>
 #include <cmath>
@@ -1310,6 +1311,80 @@ int FlatIndex::topk_filtered(const void *q, size_t k, const uint32_t *doc_ids, s
     *out_count = w;
     checkin(std::move(c));
     return ok ? 0 : -1;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// request combiner for the stock single-query entry point (opt-in)
+// ------------------------------------------------------------------------------------------------
+struct FlatIndex::TopkReq {
+    const void *blob;
+    std::vector<size_t> labels;
+    std::vector<double> scores;
+    int code = VecSim_QueryReply_OK;
+};
+
+int FlatIndex::microbatch_window_us() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("VECSIM_B200_MICROBATCH_US");
+        v = e ? std::max(0, atoi(e)) : 0;
+    }
+    return v;
+}
+
+VecSimQueryReply *FlatIndex::topk_combined(const void *q, size_t k, VecSimQueryParams *qp, VecSimQueryReply_Order order) {
+    const int window = microbatch_window_us();
+    // only what the batched entry point serves in one pass; everything else keeps the direct route
+    if (window <= 0 || multi_ || k == 0 || k > (size_t)kMaxFusedK || count_ < 65536) return topk(q, k, qp, order);
+    void *tctx = qp ? qp->timeoutCtx : nullptr;
+    auto *rep = new VecSimQueryReply();
+    last_mode_ = STANDARD_KNN;
+    if (timed_out(tctx)) {
+        rep->code = VecSim_QueryReply_TimedOut;
+        return rep;
+    }
+    using Batcher = MicroBatcher<TopkReq>;
+    std::shared_ptr<void> holder;
+    {
+        std::lock_guard<std::mutex> g(mb_mu_);
+        auto &slot = batchers_[k];
+        if (!slot) {
+            const size_t blob_bytes = dim_ * elem_bytes_;
+            slot = std::shared_ptr<void>(
+                new Batcher(256, std::chrono::microseconds(window),
+                            [this, k, blob_bytes](std::vector<TopkReq *> &reqs) {
+                                const size_t nq = reqs.size();
+                                std::vector<uint8_t> blobs(nq * blob_bytes);
+                                for (size_t i = 0; i < nq; i++) memcpy(blobs.data() + i * blob_bytes, reqs[i]->blob, blob_bytes);
+                                std::vector<size_t> labels(nq * k);
+                                std::vector<double> scores(nq * k);
+                                const int code = topk_batch(blobs.data(), blob_bytes, nq, k, nullptr, labels.data(), scores.data());
+                                for (size_t i = 0; i < nq; i++) {
+                                    reqs[i]->code = code;
+                                    reqs[i]->labels.assign(labels.begin() + i * k, labels.begin() + (i + 1) * k);
+                                    reqs[i]->scores.assign(scores.begin() + i * k, scores.begin() + (i + 1) * k);
+                                }
+                            }),
+                [](void *p) { delete static_cast<Batcher *>(p); });
+        }
+        holder = slot;
+    }
+    TopkReq r;
+    r.blob = q;
+    static_cast<Batcher *>(holder.get())->submit(r);
+    if (r.code == VecSim_QueryReply_TimedOut || timed_out(tctx)) {
+        rep->code = VecSim_QueryReply_TimedOut;
+        return rep;
+    }
+    if (r.code != VecSim_QueryReply_OK) {
+        log("warning", "vecsim_b200: combined top-k query failed on device");
+        return rep;
+    }
+    for (size_t j = 0; j < k && j < r.labels.size(); j++)
+        if (r.labels[j] != SIZE_MAX) rep->results.push_back({r.labels[j], r.scores[j]});
+    finish_reply(rep, order);
+    return rep;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -10,6 +10,8 @@
 #include "vecsim_kernels.h"
 
 #include <atomic>
+#include <map>
+#include <memory>
 #include <limits>
 #include <memory>
 #include <mutex>
@@ -113,6 +115,10 @@ class FlatIndex {
     bool flush();
 
     VecSimQueryReply *topk(const void *q, size_t k, VecSimQueryParams *qp, VecSimQueryReply_Order order);
+    // the same through the request combiner (micro_batcher.h): concurrent callers share one corpus pass.  Opt-in:
+    // VECSIM_B200_MICROBATCH_US=<collection window in microseconds> (default 0 = off).
+    VecSimQueryReply *topk_combined(const void *q, size_t k, VecSimQueryParams *qp, VecSimQueryReply_Order order);
+    static int microbatch_window_us();
     int topk_batch(const void *qs, size_t qstride, size_t nq, size_t k, VecSimQueryParams *qp, size_t *out_labels,
                    double *out_scores);
     int topk_batch_device(const void *d_q, size_t nq, size_t k, int64_t *d_labels, float *d_scores, cudaStream_t s);
@@ -232,6 +238,9 @@ class FlatIndex {
     std::atomic<uint64_t> scan_bytes_{0};
     double scan_us_ = 0;
     std::mutex stats_mu_;
+    struct TopkReq;
+    std::mutex mb_mu_;
+    std::map<size_t, std::shared_ptr<void>> batchers_; // one MicroBatcher<TopkReq> per k
     friend struct BatchIter;
 };
 
