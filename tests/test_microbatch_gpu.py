@@ -46,5 +46,5 @@ def test_concurrent_single_queries_are_combined(tmp_path):
     script = tmp_path / "mb.py"
     script.write_text(f"ROOT = {ROOT!r}\n" + SCRIPT)
     env = dict(os.environ, VECSIM_B200_MICROBATCH_US="3000")
-    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900, env=env)
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0 and "MICROBATCH-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
