@@ -20,8 +20,8 @@ class MicroBatcher {
   public:
     using BatchFn = std::function<void(std::vector<Req *> &)>;
 
-    MicroBatcher(size_t max_batch, std::chrono::microseconds window, BatchFn fn)
-        : max_batch_(max_batch ? max_batch : 1), window_(window), fn_(std::move(fn)) {}
+    MicroBatcher(size_t max_batch, std::chrono::microseconds window, BatchFn fn, std::function<void(Req &)> on_error = nullptr)
+        : max_batch_(max_batch ? max_batch : 1), window_(window), fn_(std::move(fn)), on_error_(std::move(on_error)) {}
 
     // Blocks until `r` has been processed by some batch (possibly one this thread led).
     void submit(Req &r) {
@@ -53,8 +53,15 @@ class MicroBatcher {
             std::vector<Req *> reqs;
             reqs.reserve(batch.size());
             for (Ticket *b : batch) reqs.push_back(b->req);
-            fn_(reqs);
+            bool threw = false;
+            try {
+                fn_(reqs);
+            } catch (...) { // followers must never be left waiting: mark the batch done, report through on_error
+                threw = true;
+            }
             lk.lock();
+            if (threw && on_error_)
+                for (Ticket *b : batch) on_error_(*b->req);
             for (Ticket *b : batch) b->done = true;
             batches_++;
             requests_ += batch.size();
@@ -77,6 +84,7 @@ class MicroBatcher {
     const size_t max_batch_;
     const std::chrono::microseconds window_;
     BatchFn fn_;
+    std::function<void(Req &)> on_error_; // called (under the lock) for every request of a batch whose fn_ threw
     std::mutex mu_;
     std::condition_variable arrivals_, done_;
     std::vector<Ticket *> pending_;

@@ -340,6 +340,13 @@ int FlatIndex::add(const void *blob, size_t label) {
                     return 0;
                 if (d_shadow_) shadow_dirty_.push_back(id);
             }
+            // the overwritten row is the caller's RAW blob: a cosine index may now hold a non-unit row, so the coarse
+            // proof must stop assuming unit vectors (it switches to the norm-scaled bound of the inner-product route)
+            if (metric_ == VecSimMetric_Cosine && dtype_ == DT_F32 && !raw_rows_) {
+                raw_rows_ = true;
+                shadow_rows_ = 0; // |row|^2 and the running maxima have to be built for every row
+                shadow_dirty_.clear();
+            }
             return 0;
         }
     }
@@ -433,6 +440,8 @@ int FlatIndex::remove(size_t label) {
         count_--;
         removed++;
     }
+    // row ids >= count_ will be re-used by later appends: the shadow copy (and |row|^2) of those ids is stale
+    shadow_rows_ = std::min(shadow_rows_, count_);
     cudaStreamSynchronize(copy_stream_);
     resident_ = count_;
     labels_dirty_ = true;
@@ -660,7 +669,7 @@ static int coarse_mode() {
 // shadow that is already complete, fp32 cosine, k within the coarse lists.
 bool FlatIndex::single_query_takes_coarse(uint32_t ke) {
     if (coarse_mode() != 1 || multi_ || coarse_disabled_ || dtype_ != DT_F32) return false;
-    if (metric_ != VecSimMetric_Cosine && !(shadow_max_abs_ <= 60000.0f)) return false; // fp16 range (also false before the first build)
+    if (!unit_rows() && !(shadow_max_abs_ <= 60000.0f)) return false; // fp16 range (also false before the first build)
     {
         std::lock_guard<std::mutex> g(mu_);
         if (!d_shadow_ || shadow_rows_ != count_ || !shadow_dirty_.empty() || shadow_cap_ < count_) return false;
@@ -682,19 +691,22 @@ bool FlatIndex::ensure_shadow(cudaStream_t st) {
         }
         cudaFree(d_shadow_); // rows are re-converted below; converting 10M x 768 takes ~7 ms
         d_shadow_ = nu;
-        if (metric_ != VecSimMetric_Cosine) { // L2 / raw inner product: the error bound and the L2 epilogue need |row|^2
-            cudaFree(d_norm2_);
-            d_norm2_ = nullptr;
-            if (!d_stats_ && (cudaMalloc(&d_stats_, 8) != cudaSuccess || cudaMemset(d_stats_, 0, 8) != cudaSuccess)) {
-                cudaGetLastError();
-                return false;
-            }
-            if (cudaMalloc(&d_norm2_, cap * sizeof(float)) != cudaSuccess) {
-                cudaGetLastError();
-                return false;
-            }
-        }
+        cudaFree(d_norm2_);
+        d_norm2_ = nullptr;
         shadow_cap_ = cap;
+        shadow_rows_ = 0;
+        shadow_dirty_.clear();
+    }
+    if (!unit_rows() && !d_norm2_) { // L2 / raw inner product / cosine after a raw overwrite: the error bound (and the L2
+                                     // epilogue) need |row|^2 of every row
+        if (!d_stats_ && (cudaMalloc(&d_stats_, 8) != cudaSuccess || cudaMemset(d_stats_, 0, 8) != cudaSuccess)) {
+            cudaGetLastError();
+            return false;
+        }
+        if (cudaMalloc(&d_norm2_, shadow_cap_ * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
         shadow_rows_ = 0;
         shadow_dirty_.clear();
     }
@@ -773,7 +785,7 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     CoarseKind kind = cmode == 2 ? CoarseTF32 : CoarseF16;
     // cosine: unit vectors, constant error bound, either operand kind.  L2 / raw inner product (fp32): the fp16 route only,
     // error bound from the row and query norms
-    const bool unit = metric_ == VecSimMetric_Cosine;
+    const bool unit = unit_rows();
     const bool eligible = cmode != 0 && !multi_ && !coarse_disabled_ && dtype_ == DT_F32 && (unit || cmode == 1) &&
                           (nq >= 16 || single_query_takes_coarse(ke));
     bool coarse = eligible && coarse_supported(v, nq, ke, kind);
@@ -1337,6 +1349,9 @@ VecSimQueryReply *FlatIndex::topk_combined(const void *q, size_t k, VecSimQueryP
     const int window = microbatch_window_us();
     // only what the batched entry point serves in one pass; everything else keeps the direct route
     if (window <= 0 || multi_ || k == 0 || k > (size_t)kMaxFusedK || count_ < 65536) return topk(q, k, qp, order);
+    // fp16 / bf16 corpora: a combined batch >= 16 would ride the tensor-core direct route, whose scores are within the 1e-2
+    // bar but not bit-identical with the single-query scan — the answer would depend on how many callers were concurrent
+    if (dtype_ == DT_F16 || dtype_ == DT_BF16) return topk(q, k, qp, order);
     void *tctx = qp ? qp->timeoutCtx : nullptr;
     auto *rep = new VecSimQueryReply();
     last_mode_ = STANDARD_KNN;
@@ -1365,7 +1380,8 @@ VecSimQueryReply *FlatIndex::topk_combined(const void *q, size_t k, VecSimQueryP
                                     reqs[i]->labels.assign(labels.begin() + i * k, labels.begin() + (i + 1) * k);
                                     reqs[i]->scores.assign(scores.begin() + i * k, scores.begin() + (i + 1) * k);
                                 }
-                            }),
+                            },
+                            [](TopkReq &r) { r.code = -1; }),
                 [](void *p) { delete static_cast<Batcher *>(p); });
         }
         holder = slot;

@@ -195,6 +195,10 @@ class FlatIndex {
     uint32_t *d_stats_ = nullptr;
     float shadow_max_norm_ = 0.0f, shadow_max_abs_ = std::numeric_limits<float>::infinity();
     std::atomic<bool> coarse_disabled_{false}; // L2 / IP index with values outside the fp16 range: exact scans only
+    // cosine index that took an in-place update (brute_force_single.h:139-144 stores the caller's RAW blob): its rows are
+    // no longer all unit vectors, the coarse proof uses the norm-scaled bound from then on
+    std::atomic<bool> raw_rows_{false};
+    bool unit_rows() const { return metric_ == VecSimMetric_Cosine && !raw_rows_; }
     std::vector<idType> shadow_dirty_;
     bool ensure_shadow(cudaStream_t st);
     bool single_query_takes_coarse(uint32_t ke);

@@ -1,16 +1,15 @@
 """GPU: the opt-in request combiner behind the stock VecSimIndex_TopKQuery (VECSIM_B200_MICROBATCH_US > 0): many
 threads issuing single queries must each get the exact answer, while the library serves them with shared corpus passes.
 
-The combiner itself is unit-tested on the host (tests/test_micro_batcher.py).  Its wiring into the C API was written
-after this round's GPU budget was spent and has not yet run on a GPU box, hence the non-strict xfail: a pass is
-reported as XPASS, a failure does not break the suite, and the feature is off unless the variable is set."""
+The combiner itself is unit-tested on the host (tests/test_micro_batcher.py); the feature is off unless the variable
+is set."""
 import os
 import subprocess
 import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="combiner wiring not yet verified on a GPU box", strict=False)]
+pytestmark = [pytest.mark.gpu]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SCRIPT = r'''

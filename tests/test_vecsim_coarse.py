@@ -110,6 +110,104 @@ def test_shadow_rows_follow_updates_and_deletes():
     vs.lib().VecSimB200_SetCoarseMode(-1)
 
 
+def _checker(metric_code):
+    """The reference's own compiled code when oracle/_ref is present, else the C restatement (pinned to it)."""
+    def make(dim):
+        if ol.ref_vecsim() is not None:
+            return ol.RefIndex(ol.F32, dim, metric_code)
+        return ol.PortIndex(ol.F32, dim, metric_code, tier=ol.TIER_AVX512)
+    return make
+
+
+def test_deleted_then_reused_row_ids_do_not_keep_stale_shadow_rows():
+    """Delete the LAST rows (no swap, nothing marked dirty), then append rows that are the exact nearest neighbours of
+    the queries: they land on the re-used row ids.  A shadow that still held the deleted rows would score those ids
+    against the wrong vectors and the proof would pass on a wrong answer (round-1 advisor finding)."""
+    import torch
+
+    from redisearch_b200 import vecsim as vs
+
+    vs.lib().VecSimB200_SetCoarseMode(1)
+    n, dim, nq, k = 70_000, 64, 32, 10
+    rows = ol.synth_rows(ol.F32, 17, 0, n, dim)
+    g = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, vs.VecSimMetric_Cosine)
+    p = _checker(ol.COS)(dim)
+    g.add_many(rows, label0=1)
+    p.add_many(rows, 1)
+    qs = ol.synth_rows(ol.F32, 18, 0, nq, dim)
+    qn = qs.copy()
+    for i in range(nq):
+        ol.port().orc_normalize(ol._p(qn[i]), dim, ol.F32)
+    labels, _, flags = _device_batch(vs, torch, g, qn, k)  # builds the shadow over all n rows
+    assert flags is not None
+    for lab in range(n, n - nq, -1):  # always the last row: removeVector does not move anything
+        assert g.delete(lab) == 1
+        p.delete(lab)
+    for i in range(nq):  # the new rows ARE the queries: distance ~0, on the row ids just vacated
+        assert g.add(qs[i], 5_000_000 + i) == 1
+        p.add(qs[i], 5_000_000 + i)
+    labels, scores, flags = _device_batch(vs, torch, g, qn, k)
+    assert flags is not None and vs.lib().VecSimB200_LastBatchPath(g.h) == 1
+    for i in range(nq):
+        pi, ps = p.topk(qs[i], k)
+        assert labels[i, 0] == 5_000_000 + i, (i, labels[i], pi)
+        assert labels[i].tolist() == pi.tolist(), (i, flags[i], labels[i], pi)
+        assert scores[i].tobytes() == ps.astype(np.float32).tobytes()
+    vs.lib().VecSimB200_SetCoarseMode(-1)
+
+
+def test_cosine_raw_overwrite_near_the_kth_boundary_keeps_the_proof_sound():
+    """brute_force_single.h:139-144 overwrites an existing label with the caller's RAW blob, so a cosine index can hold
+    non-unit rows.  Rows of norm ~16 are planted right at the k-th boundary of each query (on both sides of it): their
+    fp16 error is ~16x the unit-vector bound, so a proof that assumed unit vectors could pass on a wrong answer.  ids and
+    score bits must still equal the reference's."""
+    import torch
+
+    from redisearch_b200 import vecsim as vs
+
+    vs.lib().VecSimB200_SetCoarseMode(1)
+    n, dim, nq, k = 70_000, 128, 32, 10
+    rows = ol.synth_rows(ol.F32, 27, 0, n, dim)
+    g = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, vs.VecSimMetric_Cosine)
+    p = _checker(ol.COS)(dim)
+    g.add_many(rows, label0=1)
+    p.add_many(rows, 1)
+    qs = ol.synth_rows(ol.F32, 28, 0, nq, dim)
+    qn = qs.copy()
+    for i in range(nq):
+        ol.port().orc_normalize(ol._p(qn[i]), dim, ol.F32)
+    _device_batch(vs, torch, g, qn, k)  # shadow built while every row is still a unit vector
+    rng = np.random.default_rng(5)
+    scale = 16.0
+    victim = 100
+    for i in range(nq):
+        pi, ps = p.topk(qs[i], k)
+        d_k = float(ps[-1])
+        for delta in (-3e-4, -2e-5, 2e-5, 3e-4):  # just inside / just outside the current k-th distance
+            want = d_k + delta  # 1 - scale * c = want
+            c = (1.0 - want) / scale
+            q = qn[i].astype(np.float64)
+            u = rng.standard_normal(dim)
+            u -= u.dot(q) * q
+            u /= np.linalg.norm(u)
+            blob = (scale * (c * q + np.sqrt(max(0.0, 1.0 - c * c)) * u)).astype(np.float32)
+            victim += 1
+            assert g.add(blob, victim) == 0  # label exists: in-place overwrite with the raw blob
+            p.add(blob, victim)
+    labels, scores, flags = _device_batch(vs, torch, g, qn, k)
+    assert flags is not None and vs.lib().VecSimB200_LastBatchPath(g.h) == 1
+    planted = 0
+    for i in range(nq):
+        pi, ps = p.topk(qs[i], k)
+        planted += int(((pi > 100) & (pi <= victim)).sum())
+        assert labels[i].tolist() == pi.tolist(), (i, flags[i], labels[i], pi)
+        assert scores[i].tobytes() == ps.astype(np.float32).tobytes()
+    assert planted >= nq, "the planted rows did not reach the top-k: the test is not exercising the boundary"
+    hl, hs, rc = g.topk_batch(qs, k)
+    assert rc == 0 and (hl.astype(np.int64) == labels).all()
+    vs.lib().VecSimB200_SetCoarseMode(-1)
+
+
 def test_coarse_path_falls_back_when_the_margin_is_too_small():
     """Many near-duplicates of the query direction: the 24th-best approximate candidate of a row range is
     within the coarse error bound of the true k-th distance, so the proof must fail and the exact scan answers."""
