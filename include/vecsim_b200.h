@@ -418,6 +418,32 @@ VecSimB200_Stats VecSimB200_GetStats(VecSimIndex *index, bool reset);
  * (score,label) pairs, out = [nq][k]. */
 int VecSimB200_MergeShardTopK(const float *d_scores, const int64_t *d_labels, size_t G, size_t nq,
                               size_t k, float *d_out_scores, int64_t *d_out_labels, void *stream);
+/* ---- sharded KNN across GPUs, the exchange inside the library -------------------------------------------
+ * One process per GPU, every process holds one row shard in its own VecSimIndex.  A query batch is answered by: local scan
+ * of the shard -> ONE ncclAllGather of the packed per-shard top-k (labels + scores of a rank in one block) over NVLink ->
+ * G-way merge on device by (score, label) — the coordinator's knnPostProcess, src/module.c:3139-3176, comparator
+ * VS/utils/query_result_utils.h:19-23.  NCCL is bound at run time (dlopen "libnccl.so.2", or VECSIM_B200_NCCL_LIB), so
+ * single-GPU users never load it.  Bootstrap like any NCCL program: rank 0 calls _UniqueId, ships the 128 bytes to the
+ * other ranks over whatever control channel the host has (RediSearch: the cluster bus), every rank calls _New. */
+typedef struct VecSimB200_ShardGroup VecSimB200_ShardGroup;
+/* The exchange block of one shard: [labels int64 x nq*k][scores float x nq*k] padded to 16 bytes; and the merge of G such
+ * blocks laid out rank-major (what an all-gather leaves) — for hosts that move the blocks with their own transport. */
+size_t VecSimB200_ShardBlockBytes(size_t nq, size_t k);
+int VecSimB200_MergeShardBlocks(const void *d_blocks, size_t G, size_t nq, size_t k, float *d_out_scores, int64_t *d_out_labels,
+                                void *stream);
+int VecSimB200_ShardGroup_UniqueId(void *out128);                                        /* 0 = ok */
+VecSimB200_ShardGroup *VecSimB200_ShardGroup_New(const void *id128, int rank, int world); /* collective; NULL on error */
+void VecSimB200_ShardGroup_Free(VecSimB200_ShardGroup *g);
+int VecSimB200_ShardGroup_Rank(const VecSimB200_ShardGroup *g);
+int VecSimB200_ShardGroup_Size(const VecSimB200_ShardGroup *g);
+/* Collective, enqueued on `stream`, nothing synchronised: d_queries = nq stored-form (normalised) query blobs on this
+ * rank's device; every rank receives the merged [nq][k] labels (int64, -1 = empty) and distances. */
+int VecSimB200_ShardGroup_TopKBatchDevice(VecSimB200_ShardGroup *g, VecSimIndex *shard, const void *d_queries, size_t nq, size_t k,
+                                          int64_t *d_out_labels, float *d_out_scores, void *stream);
+/* Collective, host buffers end to end (raw query blobs in as for VecSimIndex_TopKQuery; H2D, shard scan, all-gather,
+ * merge, D2H inside the call).  Empty slots: label SIZE_MAX, score NaN.  Returns 0 / -1. */
+int VecSimB200_ShardGroup_TopKBatch(VecSimB200_ShardGroup *g, VecSimIndex *shard, const void *queryBlobs, size_t qstride, size_t nq,
+                                    size_t k, size_t *out_labels, double *out_scores);
 /* Hybrid "filter AND KNN" in ad-hoc mode, fused: what HybridIterator does in HYBRID_ADHOC_BF mode
  * (src/iterators/hybrid_reader.c:289-335: read the child iterator's docIds in ascending order, GetDistanceFrom each,
  * keep the k best in a heap with strict `<` admission, skip NaN = deleted) — in one call.  doc_ids: the filter's
@@ -436,8 +462,9 @@ int VecSimB200_TopKFiltered(VecSimIndex *index, const void *queryBlob, size_t k,
  * 10M x 768), 2 = TF32 coarse pass over the fp32 rows (no extra memory, ~4x slower than 1),
  * -1 = environment default (VECSIM_B200_COARSE, 1 unless set). */
 void VecSimB200_SetCoarseMode(int mode);
-/* Debug: after a VecSimB200_TopKQueryBatchDevice call, per-query flags (1 = answered by the tensor-core
- * path, 0 = fell back to the exact scan).  Returns -1 if the last batch did not take the coarse path. */
+/* Debug: after a VecSimB200_TopKQueryBatchDevice call, per-query flags (1 = answered by the tensor-core path on the first
+ * tier's 24-entry candidate lists, 2 = by the second tier's 128-entry lists, 0 = fell back to the exact scan).  Returns -1
+ * if the last batch did not take the coarse path. */
 int VecSimB200_LastCoarseFlags(VecSimIndex *index, uint32_t *out_ok, size_t nq);
 /* Debug: which route the last top-k query (single or batched) took: 0 = exact CUDA-core scan, 1 = tensor-core coarse pass + exact
  * rescoring + proof (fp32 cosine), 2 = tensor-core direct, k <= 128 (csrc/coarse_tc.cu): fp16 / bf16 corpora, inner

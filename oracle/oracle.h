@@ -63,6 +63,10 @@ size_t orc_index_all_sorted(const OrcIndex *ix, const void *query, size_t *label
  * reference). */
 double orc_index_time_topk(const OrcIndex *ix, const void *queries, size_t qstride, size_t nq, size_t k,
                            int nthreads, size_t *labels, double *scores);
+/* streaming top-k over a flat chunk of stored-form rows (state carried between chunks); see vecsim_oracle.c */
+void orc_scan_topk_chunk(int type, int metric, int tier, size_t dim, const void *rows, size_t stride, size_t n, size_t label0,
+                         const void *queries, size_t qstride, size_t nq, size_t k, int nthreads, size_t *labels, float *scores,
+                         size_t *counts);
 
 /* Counter-based synthetic data shared with the CUDA generator: element (row,col)
  * of stream `seed` is U(-1,1) from a 64-bit mix; bit-identical on host and device. */

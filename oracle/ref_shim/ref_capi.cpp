@@ -190,4 +190,58 @@ double Ref_TimeTopK(void *idx, const void *queries, size_t qstride, size_t nq, s
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// Streaming form of BruteForceIndex::topKQuery (brute_force.h:243-291) over a FLAT array of stored-form rows that
+// the caller hands over chunk by chunk (bench.py copies the device's own corpus back 1M rows at a time): the
+// reference's dispatched distance kernel (spaces::GetDistFunc, same call as calcDistance) and the reference's heap
+// class with its admission rule, per query, `nthreads` queries at a time.  The heap state travels between chunks in
+// ids/scores/counts (counts[i] entries valid, any order); labels are label0 + row index.  `queries` are stored-form
+// (already normalised for cosine).  After the last chunk the caller sorts by (score, label).
+void Ref_ScanTopKChunk(int type, int metric, size_t dim, const void *rows, size_t stride, size_t n, size_t label0,
+                       const void *queries, size_t qstride, size_t nq, size_t k, int nthreads, size_t *ids,
+                       float *scores, size_t *counts) {
+    using namespace spaces;
+    unsigned char al = 0;
+    auto m = (VecSimMetric)metric;
+    dist_func_t<float> fn = nullptr;
+    switch ((VecSimType)type) {
+    case VecSimType_FLOAT32: fn = GetDistFunc<float, float>(m, dim, &al); break;
+    case VecSimType_FLOAT16: fn = GetDistFunc<vecsim_types::float16, float>(m, dim, &al); break;
+    case VecSimType_BFLOAT16: fn = GetDistFunc<vecsim_types::bfloat16, float>(m, dim, &al); break;
+    case VecSimType_INT8: fn = GetDistFunc<int8_t, float>(m, dim, &al); break;
+    case VecSimType_UINT8: fn = GetDistFunc<uint8_t, float>(m, dim, &al); break;
+    default: return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < (nthreads < 1 ? 1 : nthreads); t++)
+        th.emplace_back([&] {
+            auto alloc = VecSimAllocator::newVecsimAllocator();
+            for (;;) {
+                const size_t qi = next.fetch_add(1);
+                if (qi >= nq) break;
+                const void *q = (const char *)queries + qi * qstride;
+                vecsim_stl::max_priority_queue<float, labelType> heap(alloc);
+                for (size_t j = 0; j < counts[qi]; j++) heap.emplace(scores[qi * k + j], ids[qi * k + j]);
+                float upperBound = heap.size() ? heap.top().first : std::numeric_limits<float>::lowest();
+                for (size_t r = 0; r < n; r++) {
+                    const float score = fn((const char *)rows + r * stride, q, dim);
+                    if (score < upperBound || heap.size() < k) { // brute_force.h:271-278
+                        heap.emplace(score, (labelType)(label0 + r));
+                        if (heap.size() > k) heap.pop();
+                        upperBound = heap.top().first;
+                    }
+                }
+                size_t c = 0;
+                while (!heap.empty()) {
+                    scores[qi * k + c] = heap.top().first;
+                    ids[qi * k + c] = heap.top().second;
+                    heap.pop();
+                    c++;
+                }
+                counts[qi] = c;
+            }
+        });
+    for (auto &t : th) t.join();
+}
+
 } // extern "C"

@@ -14,6 +14,7 @@
  */
 #include "oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
@@ -639,6 +640,68 @@ double orc_index_time_topk(const OrcIndex *ix, const void *queries, size_t qstri
     clock_gettime(CLOCK_MONOTONIC, &t1);
     free(th);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+/* Streaming form of orc_index_topk over a flat array of stored-form rows handed over chunk by chunk (the fallback of
+ * oracle/ref_shim/ref_capi.cpp Ref_ScanTopKChunk when oracle/_ref is not built): brute_force.h:262-281 admission rule on
+ * the same heap, state carried in labels/scores/counts between chunks, labels = label0 + row index. */
+typedef struct {
+    int type, metric, tier;
+    size_t dim, stride, n, label0, qstride, nq, k;
+    const uint8_t *rows, *queries;
+    size_t *labels, *counts;
+    float *scores;
+    size_t *next;
+    pthread_mutex_t *mu;
+} ScanWork;
+static void *scan_worker(void *arg) {
+    ScanWork *w = (ScanWork *)arg;
+    Pair *heap = (Pair *)malloc((w->k + 1) * sizeof(Pair));
+    for (;;) {
+        pthread_mutex_lock(w->mu);
+        size_t qi = (*w->next)++;
+        pthread_mutex_unlock(w->mu);
+        if (qi >= w->nq) break;
+        const void *q = w->queries + qi * w->qstride;
+        size_t hn = 0;
+        for (size_t j = 0; j < w->counts[qi]; j++) {
+            Pair v = {w->scores[qi * w->k + j], w->labels[qi * w->k + j]};
+            heap_push(heap, &hn, v);
+        }
+        float upper = hn ? heap[0].score : -FLT_MAX;
+        for (size_t r = 0; r < w->n; r++) {
+            float sc = orc_distance(w->type, w->metric, w->dim, w->rows + r * w->stride, q, w->tier);
+            if (sc < upper || hn < w->k) {
+                Pair v = {sc, w->label0 + r};
+                heap_push(heap, &hn, v);
+                if (hn > w->k) heap_pop(heap, &hn);
+                upper = heap[0].score;
+            }
+        }
+        size_t c = 0;
+        while (hn) {
+            w->scores[qi * w->k + c] = heap[0].score;
+            w->labels[qi * w->k + c] = heap[0].label;
+            heap_pop(heap, &hn);
+            c++;
+        }
+        w->counts[qi] = c;
+    }
+    free(heap);
+    return NULL;
+}
+void orc_scan_topk_chunk(int type, int metric, int tier, size_t dim, const void *rows, size_t stride, size_t n, size_t label0,
+                         const void *queries, size_t qstride, size_t nq, size_t k, int nthreads, size_t *labels, float *scores,
+                         size_t *counts) {
+    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    size_t next = 0;
+    ScanWork w = {type, metric, tier, dim, stride, n, label0, qstride, nq, k, (const uint8_t *)rows, (const uint8_t *)queries,
+                  labels, counts, scores, &next, &mu};
+    if (nthreads < 1) nthreads = 1;
+    pthread_t *th = (pthread_t *)malloc((size_t)nthreads * sizeof(pthread_t));
+    for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, scan_worker, &w);
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th);
 }
 
 /* ------------------------------------------------------------------ synthetic data ---------- */

@@ -94,6 +94,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// pure spin (no suspend hint): for the two single-warp roles whose wake-up latency is on the critical path (the
+// producer and the MMA issuer) — a sleeping try_wait is resumed through NANOSLEEP.SYNCS and adds to every stage hand-over
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -213,6 +229,20 @@ __device__ __forceinline__ void umma_ss_i8(uint32_t d_tmem, uint64_t adesc, uint
         "}\n" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+template <int kOp>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (kOp == 0 || kOp == 3)
+        umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, accumulate);
+    else
+        umma_ts_i8(d_tmem, a_tmem, bdesc, idesc, accumulate);
+}
+template <int kOp>
+__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (kOp == 0 || kOp == 3)
+        umma_ss_f16(d_tmem, adesc, bdesc, idesc, accumulate);
+    else
+        umma_ss_i8(d_tmem, adesc, bdesc, idesc, accumulate);
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(
@@ -516,7 +546,6 @@ constexpr int kQKbPerStage = 2;     // K blocks per pipeline stage: amortises th
 // `keep` when it holds more than (slots - 32) entries after a 32-row chunk.  kEpl = 3 (96 slots) serves keep <= 32,
 // kEpl = 8 (256 slots) keep <= 128.
 constexpr int kQListStride = 129;   // lists[slot * stride + query]: conflict-free appends
-static_assert(kCoarseKeep <= 32, "publish_sorted ranks one kept entry per lane");
 constexpr uint32_t kQBlockBytes = kQN * 128;                    // one K block of a row tile: 128 rows x 128 bytes
 constexpr uint32_t kQStageBytes = kQKbPerStage * kQBlockBytes; // 32 KB
 constexpr uint32_t kQAccCols = 2 * kQN; // two accumulator stages
@@ -602,21 +631,6 @@ __device__ __forceinline__ uint32_t select_keep(uint64_t *lists, int q, uint32_t
     return prefix;
 }
 
-// list `q` (c <= 32 entries) -> dst[0, keep): ascending, kEmptySlot padded.  Rank by counting.
-__device__ __forceinline__ void publish_sorted(const uint64_t *lists, int q, uint32_t c, uint32_t keep, int lane, uint64_t *dst) {
-    const uint64_t mine = (uint32_t)lane < c ? lists[lane * kQListStride + q] : kEmptySlot;
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < c; j++) {
-        const uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)mine, j), hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(mine >> 32), j);
-        const uint64_t o = ((uint64_t)hi << 32) | lo;
-        rank += o < mine; // composites are unique (row id in the low word)
-    }
-    if ((uint32_t)lane < c)
-        dst[rank] = mine;
-    else if ((uint32_t)lane < keep)
-        dst[lane] = kEmptySlot;
-}
-
 // kDirect = false: fp32 corpus, rows come from the tiled fp16 shadow (bulk copies), output = sorted candidate lists for
 //                  the exact rescoring + proof.
 // kDirect = true : fp16 / bf16 corpus, rows come straight from the row-major corpus through a 128B-swizzle tensor
@@ -629,14 +643,24 @@ __device__ __forceinline__ void publish_sorted(const uint64_t *lists, int q, uin
 //            (IP.cpp:264-271).  The integer dot products are exact, so kOp 1/2 reproduce the reference bit for bit.
 //   kOp = 3  16-bit float operands, squared L2 from the GEMM: (|q|^2 + |row|^2) - 2 dot, with the squared norms of
 //            the fp32 rows / queries in row_norm2 / q_norm2 (coarse stage of the fp32 L2 route)
-template <bool kDirect, int kEpl, int kOp>
+//   kFixed   the admission threshold of every query is FIXED for the whole pass (thr_fixed[q], a distance, from the sample
+//            pass): every row with approximate distance < thr_fixed[q] is kept — no running threshold, no list compaction;
+//            a list that runs full sets overflow[q] (the query goes to the next tier).  fp32 route only (kOp 0 / 3).
+//   tile_stride > 1: only every tile_stride-th row tile is visited (the sample pass)
+template <bool kDirect, int kEpl, int kOp, bool kFixed>
 __global__ void __launch_bounds__(kCoarseThreads, 1)
 coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t *__restrict__ shadow, size_t row_pitch,
                     const uint8_t *__restrict__ q16, size_t q16_pitch, const float *__restrict__ row_norm2,
                     const float *__restrict__ q_norm2, uint32_t n_rows, uint32_t nq, uint32_t dim, uint32_t row_bytes,
                     uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t nstages, uint32_t csize, uint32_t nacc, uint32_t idesc,
-                    uint64_t *__restrict__ list_scratch, uint64_t *__restrict__ cand_out) {
+                    uint64_t *__restrict__ list_scratch, uint64_t *__restrict__ cand_out, const uint32_t *__restrict__ nq_dev,
+                    uint32_t tile_stride, const float *__restrict__ thr_fixed, uint32_t *__restrict__ overflow) {
+    static_assert(!kFixed || (!kDirect && (kOp == 0 || kOp == 3)), "fixed thresholds: fp32 route only");
     constexpr int kQListCap = kEpl * 32;
+    if (nq_dev) { // second tier: the number of live queries is only known on the device; nothing to do = every CTA leaves
+        nq = min(nq, *nq_dev);
+        if (nq == 0) return;
+    }
     constexpr uint32_t kQTrigger = kQListCap - 32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -685,11 +709,12 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
     if (warp == 0) {
         // ===== producer: row tiles [64 rows x 64 halves] per K block, kQKbPerStage K blocks per stage =====
         uint32_t s = 0, ph = 0;
+        const uint32_t slice_full = kQStageBytes / csize, slice_tail = ((num_kb % kQKbPerStage) * kQBlockBytes) / csize;
         for (uint32_t i = 0; i < my_tiles; i++) {
-            const uint32_t tile = blockIdx.x + i * gridDim.x;
+            const uint32_t tile = (blockIdx.x + i * gridDim.x) * tile_stride;
             for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kQKbPerStage) {
                 const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
-                mbar_wait(&empty[s], ph ^ 1);
+                mbar_wait_spin(&empty[s], ph ^ 1);
                 if (elect_one_sync()) {
                     const uint32_t bytes = kbn * kQBlockBytes;
                     mbar_expect_tx(&full[s], bytes);
@@ -709,7 +734,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                         // the K blocks of a stage are one contiguous run in HBM
                         const uint8_t *src = shadow + ((size_t)tile * num_kb + kb0) * kQBlockBytes;
                         if (csize > 1) {
-                            const uint32_t slice = bytes / csize; // multiple of 16
+                            const uint32_t slice = kbn == (uint32_t)kQKbPerStage ? slice_full : slice_tail; // bytes / csize, multiple of 16
                             bulk_load_1d_mc(sB + (size_t)s * kQStageBytes + crank * slice, src + crank * slice, slice, &full[s], cmask);
                         } else {
                             bulk_load_1d(sB + (size_t)s * kQStageBytes, src, bytes, &full[s]);
@@ -722,62 +747,78 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         }
     } else if (warp == 1) {
         // ===== MMA issuer: D[128 queries x 128 rows] += Q[tmem] * rows[smem]^T =====
+        // Everything that does not change from stage to stage is hoisted, and a stage takes one of two branch-free
+        // bodies (all K blocks from tensor memory / all from shared memory): ncu showed this thread spending half its
+        // time on descriptor arithmetic and per-MMA branches while the tensor pipe sat at 53 %.
         mbar_wait(qbar, 0);
         tc_fence_after();
         uint32_t s = 0, ph = 0;
+        const uint64_t bdesc_first = make_smem_desc(smem_u32(sB));
+        const uint64_t adesc_first = make_smem_desc(smem_u32(sQ));
+        constexpr uint64_t kStageStep = kQStageBytes >> 4, kBlockStep = kQBlockBytes >> 4;
+        uint64_t bdesc_s = bdesc_first; // descriptor of ring stage s
+        const bool multi = csize > 1;
         for (uint32_t i = 0; i < my_tiles; i++) {
-            const uint32_t a = i % nacc, aph = (i / nacc) & 1;
-            mbar_wait(&tempty[a], aph ^ 1);
+            const uint32_t a = (nacc == 2) ? (i & 1u) : 0u, aph = (nacc == 2) ? ((i >> 1) & 1u) : (i & 1u);
+            mbar_wait_spin(&tempty[a], aph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + a * kQN;
             for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kQKbPerStage) {
-                const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
-                mbar_wait(&full[s], ph);
+                mbar_wait_spin(&full[s], ph);
                 tc_fence_after();
-                const uint64_t bdesc0 = make_smem_desc(smem_u32(sB + (size_t)s * kQStageBytes));
                 if (elect_one_sync()) {
-#pragma unroll
-                    for (uint32_t j = 0; j < (uint32_t)kQKbPerStage; j++) {
-                        if (j < kbn) {
+                    if (kb0 + kQKbPerStage <= kb_tmem) {
+                        // both K blocks of the stage: queries from tensor memory (8 columns per instruction), 16 halves
+                        // (32 bytes of the swizzled row tile) per instruction
+                        const uint32_t at = tmem_q + kb0 * 32;
+                        umma_ts<kOp>(d_tmem, at, bdesc_s, idesc, kb0 != 0);
+                        umma_ts<kOp>(d_tmem, at + 8, bdesc_s + 2, idesc, 1);
+                        umma_ts<kOp>(d_tmem, at + 16, bdesc_s + 4, idesc, 1);
+                        umma_ts<kOp>(d_tmem, at + 24, bdesc_s + 6, idesc, 1);
+                        umma_ts<kOp>(d_tmem, at + 32, bdesc_s + kBlockStep, idesc, 1);
+                        umma_ts<kOp>(d_tmem, at + 40, bdesc_s + kBlockStep + 2, idesc, 1);
+                        umma_ts<kOp>(d_tmem, at + 48, bdesc_s + kBlockStep + 4, idesc, 1);
+                        umma_ts<kOp>(d_tmem, at + 56, bdesc_s + kBlockStep + 6, idesc, 1);
+                    } else if (kb0 >= kb_tmem && kb0 + kQKbPerStage <= num_kb) {
+                        // both K blocks: queries from shared memory
+                        const uint64_t ad = adesc_first + (uint64_t)(kb0 - kb_tmem) * kBlockStep;
+                        umma_ss2<kOp>(d_tmem, ad, bdesc_s, idesc, kb0 != 0);
+                        umma_ss2<kOp>(d_tmem, ad + 2, bdesc_s + 2, idesc, 1);
+                        umma_ss2<kOp>(d_tmem, ad + 4, bdesc_s + 4, idesc, 1);
+                        umma_ss2<kOp>(d_tmem, ad + 6, bdesc_s + 6, idesc, 1);
+                        umma_ss2<kOp>(d_tmem, ad + kBlockStep, bdesc_s + kBlockStep, idesc, 1);
+                        umma_ss2<kOp>(d_tmem, ad + kBlockStep + 2, bdesc_s + kBlockStep + 2, idesc, 1);
+                        umma_ss2<kOp>(d_tmem, ad + kBlockStep + 4, bdesc_s + kBlockStep + 4, idesc, 1);
+                        umma_ss2<kOp>(d_tmem, ad + kBlockStep + 6, bdesc_s + kBlockStep + 6, idesc, 1);
+                    } else {
+                        // a stage that straddles the tensor-memory / shared-memory split, or the odd last K block
+                        const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
+                        for (uint32_t j = 0; j < kbn; j++) {
                             const uint32_t kb = kb0 + j;
-                            // 16 halves per instruction: 32 bytes of the swizzled row tile
-                            const uint64_t bdesc = bdesc0 + (uint64_t)(j * (kQBlockBytes >> 4));
-                            if (kb < kb_tmem) { // queries from tensor memory: 8 columns per instruction
-                                const uint32_t a_tmem = tmem_q + kb * 32;
-                                if constexpr (kOp == 0 || kOp == 3) {
-                                    umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, kb != 0);
-                                    umma_ts_f16(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
-                                    umma_ts_f16(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
-                                    umma_ts_f16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
-                                } else {
-                                    umma_ts_i8(d_tmem, a_tmem, bdesc, idesc, kb != 0);
-                                    umma_ts_i8(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
-                                    umma_ts_i8(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
-                                    umma_ts_i8(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
-                                }
-                            } else { // queries from shared memory
-                                const uint64_t adesc = make_smem_desc(smem_u32(sQ + (size_t)(kb - kb_tmem) * kQBlockBytes));
-                                if constexpr (kOp == 0 || kOp == 3) {
-                                    umma_ss_f16(d_tmem, adesc, bdesc, idesc, 1);
-                                    umma_ss_f16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
-                                    umma_ss_f16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
-                                    umma_ss_f16(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
-                                } else {
-                                    umma_ss_i8(d_tmem, adesc, bdesc, idesc, 1);
-                                    umma_ss_i8(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
-                                    umma_ss_i8(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
-                                    umma_ss_i8(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
-                                }
+                            const uint64_t bd = bdesc_s + (uint64_t)j * kBlockStep;
+                            if (kb < kb_tmem) {
+                                const uint32_t at = tmem_q + kb * 32;
+                                umma_ts<kOp>(d_tmem, at, bd, idesc, kb != 0);
+                                umma_ts<kOp>(d_tmem, at + 8, bd + 2, idesc, 1);
+                                umma_ts<kOp>(d_tmem, at + 16, bd + 4, idesc, 1);
+                                umma_ts<kOp>(d_tmem, at + 24, bd + 6, idesc, 1);
+                            } else {
+                                const uint64_t ad = adesc_first + (uint64_t)(kb - kb_tmem) * kBlockStep;
+                                umma_ss2<kOp>(d_tmem, ad, bd, idesc, kb != 0);
+                                umma_ss2<kOp>(d_tmem, ad + 2, bd + 2, idesc, 1);
+                                umma_ss2<kOp>(d_tmem, ad + 4, bd + 4, idesc, 1);
+                                umma_ss2<kOp>(d_tmem, ad + 6, bd + 6, idesc, 1);
                             }
                         }
                     }
-                    if (csize > 1)
+                    if (multi)
                         umma_commit_mc(&empty[s], cmask); // this CTA is done with stage s: tell every producer of the cluster
                     else
                         umma_commit(&empty[s]);
                 }
                 __syncwarp();
-                if (++s == nstages) s = 0, ph ^= 1;
+                bdesc_s += kStageStep;
+                if (++s == nstages) s = 0, ph ^= 1, bdesc_s = bdesc_first;
             }
             if (elect_one_sync()) umma_commit(&tfull[a]);
             __syncwarp();
@@ -813,17 +854,30 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
             tc_fence_before();
             mbar_arrive(qbar);
         }
-        // ===== epilogue: this thread's query against 64 rows per tile =====
+        // ===== epilogue: this thread's query against 128 rows per tile =====
         uint32_t thr = 0xFFFFFFFFu, cnt = 0;
         // pre-test bound in the raw accumulator domain; -inf: everything passes until the first compaction
         float thr_dot = -__int_as_float(0x7f800000);
-        if (q >= nq) thr_dot = __int_as_float(0x7f800000); // padding lanes of a partial query group: nothing ever passes
         float nq_norm = 1.0f;
         if constexpr (kOp == 2) nq_norm = q < nq ? *reinterpret_cast<const float *>(q16 + (size_t)q * q16_pitch + dim) : 1.0f;
         if constexpr (kOp == 3) nq_norm = q < nq ? q_norm2[q] : 0.0f; // |q|^2
+        bool ovf = false;
+        if constexpr (kFixed) {
+            // fixed admission bound (a distance): keep every row with approximate distance < T
+            const float T = q < nq ? thr_fixed[q] : -__int_as_float(0x7f800000);
+            thr = orderable_key(T);
+            if constexpr (kOp == 0) { // d < T  <=>  dot > 1 - T; slack: the rounding of the two subtractions
+                const float t = 1.0f - T;
+                thr_dot = t - (4e-7f + 2.4e-7f * fabsf(t));
+            } else {
+                thr_dot = 0.5f * (nq_norm - T) - 2e-6f * (fabsf(nq_norm) + fabsf(T));
+            }
+            if (!(T == T)) thr_dot = -__int_as_float(0x7f800000), thr = 0xFFFFFFFFu; // NaN bound: keep everything (-> overflow -> next tier)
+        }
+        if (q >= nq) thr_dot = __int_as_float(0x7f800000); // padding lanes of a partial query group: nothing ever passes
         for (uint32_t i = 0; i < my_tiles; i++) {
-            const uint32_t tile = blockIdx.x + i * gridDim.x;
-            const uint32_t a = i % nacc, aph = (i / nacc) & 1;
+            const uint32_t tile = (blockIdx.x + i * gridDim.x) * tile_stride;
+            const uint32_t a = (nacc == 2) ? (i & 1u) : 0u, aph = (nacc == 2) ? ((i >> 1) & 1u) : (i & 1u);
             float nrm[kQN / 32]; // kOp 2 / 3: lane l holds the norm / squared norm of rows h*32 + l of the tile
             if constexpr (kOp == 3) {
 #pragma unroll
@@ -851,11 +905,32 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
 #pragma unroll
             for (int h = 0; h < kQN / 32; h++) {
                 const uint32_t row0 = tile * kQN + h * 32;
+                uint32_t pass_pre = 0;
+                if constexpr (kFixed) {
+                    // With a fixed bound only ~k * (rows / sample rows) rows of the whole corpus pass: one 3-input max tree
+                    // over the 32 values (16 instructions) and ONE compare decide the common case
+                    if constexpr (kOp == 0) {
+                        float mx;
+                        float m8[8];
+#pragma unroll
+                        for (int g = 0; g < 8; g++)
+                            m8[g] = fmaxf(fmaxf(__uint_as_float(v[h][4 * g]), __uint_as_float(v[h][4 * g + 1])),
+                                          fmaxf(__uint_as_float(v[h][4 * g + 2]), __uint_as_float(v[h][4 * g + 3])));
+                        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+                        if (!(mx > thr_dot)) continue;
+                    } else { // squared L2: the bound depends on the row; the shuffles need the whole warp, so the pass mask
+                             // itself is built here, before the lanes diverge
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (__uint_as_float(v[h][j]) > fmaf(__shfl_sync(0xFFFFFFFFu, nrm[h], j), 0.499999f, thr_dot)) pass_pre |= 1u << j;
+                        if (pass_pre == 0) continue;
+                    }
+                }
                 // pre-test on the raw dot product against a slightly loose bound (a few instructions per value);
                 // the few survivors take the exact distance and key comparison below
-                uint32_t pass = 0;
+                uint32_t pass = pass_pre;
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
+                for (int j = 0; j < ((kFixed && kOp == 3) ? 0 : 32); j++) {
                     bool p;
                     if constexpr (kOp == 0)
                         p = __uint_as_float(v[h][j]) > thr_dot;
@@ -889,10 +964,20 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                     }
                     const uint32_t key = orderable_key(d);
                     if (key < thr) {
-                        lists[cnt * kQListStride + et] = ((uint64_t)key << 32) | (row0 + j);
-                        cnt++;
+                        if constexpr (kFixed) {
+                            if (cnt < (uint32_t)kQListCap) {
+                                lists[cnt * kQListStride + et] = ((uint64_t)key << 32) | (row0 + j);
+                                cnt++;
+                            } else {
+                                ovf = true; // more rows below the bound than the list holds: the query goes to the next tier
+                            }
+                        } else {
+                            lists[cnt * kQListStride + et] = ((uint64_t)key << 32) | (row0 + j);
+                            cnt++;
+                        }
                     }
                 }
+                if constexpr (kFixed) continue;
                 // lists that ran past the trigger are cut back to the best `keep` by the whole warp
                 uint32_t m = __ballot_sync(0xFFFFFFFFu, cnt > kQTrigger);
                 while (m) {
@@ -921,8 +1006,11 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                 }
             }
         }
-        // publish: cand_out[q][blockIdx.x][keep], ascending, kEmptySlot padded
+        // publish: cand_out[q][blockIdx.x][keep], kEmptySlot padded
         __syncwarp();
+        if constexpr (kFixed) {
+            if (ovf && q < nq) overflow[q] = 1u;
+        }
         for (int src = 0; src < 32; src++) {
             uint32_t c = __shfl_sync(0xFFFFFFFFu, cnt, src);
             const uint32_t qq = q_base + ew * 32 + src;
@@ -931,13 +1019,10 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                 c = keep;
             }
             if (qq < nq) {
+                // unordered: final_select (direct routes) and refine_kernel (fp32 route) take the lists in any order
                 uint64_t *dst = cand_out + ((size_t)qq * gridDim.x + blockIdx.x) * keep;
-                if constexpr (kDirect) { // final_select takes them in any order
-                    __syncwarp();
-                    for (uint32_t r = lane; r < keep; r += 32) dst[r] = r < c ? lists[r * kQListStride + ew * 32 + src] : kEmptySlot;
-                } else {
-                    publish_sorted(lists, ew * 32 + src, c, keep, lane, dst);
-                }
+                __syncwarp();
+                for (uint32_t r = lane; r < keep; r += 32) dst[r] = r < c ? lists[r * kQListStride + ew * 32 + src] : kEmptySlot;
             }
         }
     }
@@ -971,65 +1056,214 @@ __global__ void __launch_bounds__(256) to_f16_kernel(const uint8_t *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage 2: exact rescoring of the candidates (bit-exact arithmetic of distance_core.cuh)
+// stages 2 + 3 in one kernel, one CTA per query: exact rescoring of the candidates that can still matter, the exact
+// top-k, and the completeness proof.
+//
+//   * a_k = the k-th smallest APPROXIMATE distance over all candidate lists of the query (radix select on the keys).
+//     With |approx - exact| <= eps, the k best-approx candidates all have exact <= a_k + eps, so the k-th exact distance
+//     e_k <= a_k + eps; a candidate with approx > a_k + 2 eps has exact > a_k + eps >= e_k and cannot be among the k
+//     best: only candidates with approx <= a_k + 2 eps are re-read from the fp32 corpus (a few dozen rows instead of
+//     lists x keep = 1,776) and scored with the bit-exact arithmetic of distance_core.cuh.
+//   * proof (as before): a row that is NOT among the candidates of its list has approx >= the list's worst kept
+//     approx a_w, hence exact >= a_w - eps.  If a_w - eps > e_k for every FULL list, nothing was missed.
+//   eps: unit vectors (cosine): the constant `eps`.  Otherwise (q_norm2 != NULL) it scales with the norms — fp16 RN
+//   operands give |dot error| <= eps |a| |q| (Cauchy-Schwarz; `eps` already holds the accumulation slack)
+//   + 2^-24 sqrt(D) (|a| + |q|) for elements below the fp16 normal range; |a| <= max_norm for every row.  L2: twice
+//   that (the -2 dot term) + the fp32 rounding of the squared norms, (D + 4) 2^-23 (max_norm^2 + |q|^2).
+//   q_index (nullable): second tier — CTA i works on query q_index[i] of the original batch (its lists are stored at
+//   position i); nq_dev (nullable) = number of live CTAs.
 // ------------------------------------------------------------------------------------------------
-template <int MT>
-__global__ void __launch_bounds__(256) rescore_kernel(const uint8_t *rows, size_t pitch, uint32_t dim, const uint8_t *queries,
-                                                      size_t qpitch, uint32_t nq, uint32_t per_query,
-                                                      const uint64_t *__restrict__ cand, uint64_t *__restrict__ exact) {
-    using Tile = DistTile<DT_F32, MT, 1, 1>;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t total = (size_t)nq * per_query;
-    for (size_t w = (size_t)blockIdx.x * 8 + warp; w < total; w += (size_t)gridDim.x * 8) {
-        const uint64_t c = cand[w];
-        if (c == kEmptySlot) {
-            if (lane == 0) exact[w] = kEmptySlot;
-            continue;
+constexpr uint32_t kRefineMaxSurv = 2048;
+
+// |approx - exact| bound of one query (see above); q_norm2 == NULL: unit vectors
+__device__ __forceinline__ float query_eps(float eps, const float *q_norm2, uint32_t pos, float max_norm, uint32_t dim, bool l2) {
+    if (!q_norm2) return eps;
+    const float qn2 = q_norm2[pos], qn = sqrtf(qn2);
+    float e = eps * max_norm * qn + 5.97e-8f * sqrtf((float)dim) * (max_norm + qn);
+    if (l2) e = 2.0f * e + (float)(dim + 4) * 1.2e-7f * (max_norm * max_norm + qn2);
+    return e * 1.0001f;
+}
+// k-th smallest key (high word) among the non-empty composites of mine[0, total) — block-wide radix select, 8 bits per
+// pass; 0xFFFFFFFF when there are fewer than k.  256 threads; hist[256] and ctl[4] in shared memory.
+__device__ __forceinline__ uint32_t block_kth_key(const uint64_t *mine, uint32_t total, uint32_t k, uint32_t *hist, uint32_t *ctl) {
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) ctl[0] = 0, ctl[1] = k, ctl[2] = 0;
+    __syncthreads();
+    uint32_t cnt = 0;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) cnt += mine[i] != kEmptySlot;
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if (lane == 0 && cnt) atomicAdd(&ctl[2], cnt);
+    __syncthreads();
+    if (ctl[2] < k) return 0xFFFFFFFFu;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t prefix = ctl[0];
+        const uint32_t hi_mask = shift == 24 ? 0u : ~((1u << (shift + 8)) - 1u);
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            const uint64_t c = mine[i];
+            if (c == kEmptySlot) continue;
+            const uint32_t key = (uint32_t)(c >> 32);
+            if (((key ^ prefix) & hi_mask) == 0) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
-        const uint32_t row = (uint32_t)c;
-        const uint32_t q = (uint32_t)(w / per_query);
-        const uint8_t *rowb[1] = {rows + (size_t)row * pitch};
-        const uint8_t *qb[1] = {queries + (size_t)q * qpitch};
-        float d[1];
-        Tile::run(rowb, qb, dim, lane, d);
-        if (lane == 0) exact[w] = make_composite(d[0], row);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t rem = ctl[1], b = 0;
+            for (; b < 255; b++) {
+                if (hist[b] >= rem) break;
+                rem -= hist[b];
+            }
+            ctl[0] = prefix | (b << shift);
+            ctl[1] = rem;
+        }
+        __syncthreads();
+    }
+    return ctl[0];
+}
+
+// Admission bound of the main pass from the SAMPLE pass (every tile_stride-th row tile): T[q] = (k-th smallest approximate
+// distance among the sample's candidates) + 2 eps.  The k-th exact distance over the whole corpus e_k is at most the
+// sample's, which is <= a_k + eps, so T - eps > e_k: a row the main pass drops (approx >= T) has exact >= T - eps > e_k.
+// Also clears the overflow flags.  One CTA per query.
+__global__ void __launch_bounds__(256) threshold_kernel(const uint64_t *__restrict__ cand, uint32_t nq, uint32_t lists_per_query,
+                                                        uint32_t keep, uint32_t k, float eps, const float *__restrict__ q_norm2,
+                                                        float max_norm, uint32_t dim, int l2, float *__restrict__ thr_out,
+                                                        uint32_t *__restrict__ overflow) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t ctl[4];
+    const uint32_t q = blockIdx.x;
+    if (q >= nq) return;
+    const uint32_t ak = block_kth_key(cand + (size_t)q * lists_per_query * keep, lists_per_query * keep, k, hist, ctl);
+    if (threadIdx.x == 0) {
+        const float e = query_eps(eps, q_norm2, q, max_norm, dim, l2 != 0);
+        thr_out[q] = ak == 0xFFFFFFFFu ? __int_as_float(0x7f800000) : key_to_float(ak) + (2.0f * e) * 1.001f + 1e-30f;
+        overflow[q] = 0;
     }
 }
 
-// stage 3: per query, is the exact top-k provably complete?  A row that is NOT among the candidates of
-// its list has approx >= the list's worst kept approx a_w, hence exact >= a_w - eps.  If
-// a_w - eps > e_k (the k-th best exact distance found) for every FULL list, nothing was missed.
-// eps: |approx - exact| bound.  Unit vectors (cosine): the constant `eps`.  Otherwise (q_norm2 != NULL) it scales with the
-// norms — fp16 RN operands give |dot error| <= eps * |a| |q| (Cauchy-Schwarz; `eps` already holds the accumulation
-// slack) + 2^-24 sqrt(D) (|a| + |q|) for elements below the fp16 normal range; |a| <= max_norm for every row.  L2:
-// twice that (the -2 dot term) + the fp32 rounding of the squared norms, (D + 4) 2^-23 (max_norm^2 + |q|^2).
-__global__ void verify_kernel(const uint64_t *__restrict__ cand, const uint64_t *__restrict__ topk, uint32_t nq,
-                              uint32_t lists_per_query, uint32_t keep, uint32_t k, float eps, const float *__restrict__ q_norm2,
-                              float max_norm, int l2, uint32_t dim, uint32_t *__restrict__ ok) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    if (q_norm2) {
-        const float qn2 = q_norm2[q], qn = sqrtf(qn2);
-        float e = eps * max_norm * qn + 5.97e-8f * sqrtf((float)dim) * (max_norm + qn);
-        if (l2) e = 2.0f * e + (float)(dim + 4) * 1.2e-7f * (max_norm * max_norm + qn2);
-        eps = e * 1.0001f;
-    }
-    const uint64_t kth = topk[(size_t)q * k + (k - 1)];
-    bool good = true;
-    if (kth == kEmptySlot) {
-        // fewer than k rows found: complete only if no list was truncated
-        for (uint32_t l = 0; l < lists_per_query; l++)
-            if (cand[((size_t)q * lists_per_query + l) * keep + (keep - 1)] != kEmptySlot) good = false;
-    } else {
-        const float ek = key_to_float((uint32_t)(kth >> 32));
-        for (uint32_t l = 0; l < lists_per_query; l++) {
-            const uint64_t worst = cand[((size_t)q * lists_per_query + l) * keep + (keep - 1)];
-            if (worst == kEmptySlot) continue; // list not full: it holds every row of its range that passed
-            const float aw = key_to_float((uint32_t)(worst >> 32));
-            if (!(aw - eps > ek)) good = false;
+// thr_T == NULL: adaptive lists (a full list's worst kept approximate distance bounds what its row range dropped).
+// thr_T != NULL: lists of the fixed-bound pass — every list holds ALL rows of its range with approx < thr_T[pos] unless
+//                overflow[pos] is set; what was dropped has approx >= thr_T[pos].
+template <int MT>
+__global__ void __launch_bounds__(256) refine_kernel(const uint8_t *rows, size_t pitch, uint32_t dim, const uint8_t *queries,
+                                                     size_t qpitch, uint32_t nq, uint32_t lists_per_query, uint32_t keep, uint32_t k,
+                                                     const uint64_t *__restrict__ cand, float eps, const float *__restrict__ q_norm2,
+                                                     float max_norm, uint32_t *__restrict__ ok, uint32_t ok_value, uint64_t *__restrict__ out,
+                                                     const uint32_t *__restrict__ q_index, const uint32_t *__restrict__ nq_dev,
+                                                     const float *__restrict__ thr_T, const uint32_t *__restrict__ overflow) {
+    using Tile = DistTile<DT_F32, MT, 1, 1>;
+    __shared__ uint64_t surv[kRefineMaxSurv];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t ctl[4];
+    __shared__ uint32_t s_nsurv, s_bad;
+    if (nq_dev) nq = min(nq, *nq_dev);
+    if (blockIdx.x >= nq) return;
+    const uint32_t q = q_index ? q_index[blockIdx.x] : blockIdx.x; // query of the original batch
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t *mine = cand + (size_t)blockIdx.x * lists_per_query * keep;
+    const uint32_t total = lists_per_query * keep;
+    eps = query_eps(eps, q_norm2, blockIdx.x, max_norm, dim, MT == MT_L2);
+    if (threadIdx.x == 0) s_nsurv = 0, s_bad = 0;
+    // a_k: k-th smallest approximate key; fewer than k candidates: everything survives
+    const uint32_t ak_key = block_kth_key(mine, total, k, hist, ctl);
+    // survivors: approx <= a_k + 2 eps (rounded up)
+    const float cut = ak_key == 0xFFFFFFFFu ? __int_as_float(0x7f800000) : key_to_float(ak_key) + (2.0f * eps) * 1.001f + 1e-30f;
+    for (uint32_t i0 = 0; i0 < total; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint64_t c = i < total ? mine[i] : kEmptySlot;
+        const bool take = c != kEmptySlot && (ak_key == 0xFFFFFFFFu || key_to_float((uint32_t)(c >> 32)) <= cut);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, take);
+        uint32_t base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_nsurv, (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (take) {
+            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < kRefineMaxSurv) surv[pos] = c;
         }
     }
-    ok[q] = good ? 1u : 0u;
+    __syncthreads();
+    const uint32_t n_all = s_nsurv, n_surv = min(n_all, kRefineMaxSurv);
+    // exact distances of the survivors (one warp per row)
+    const uint8_t *qb[1] = {queries + (size_t)q * qpitch};
+    for (uint32_t i = warp; i < n_surv; i += 8) {
+        const uint32_t row = (uint32_t)surv[i];
+        const uint8_t *rowb[1] = {rows + (size_t)row * pitch};
+        float d[1];
+        Tile::run(rowb, qb, dim, lane, d);
+        __syncwarp();
+        if (lane == 0) surv[i] = make_composite(d[0], row);
+    }
+    const uint32_t n_sort = max(32u, next_pow2(n_surv));
+    __syncthreads();
+    for (uint32_t i = n_surv + threadIdx.x; i < n_sort; i += blockDim.x) surv[i] = kEmptySlot;
+    bitonic_sort_smem(surv, n_sort);
+    for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) out[(size_t)q * k + i] = i < n_surv ? surv[i] : kEmptySlot;
+    // proof
+    bool bad = n_all > kRefineMaxSurv; // more candidates within 2 eps of the k-th than the buffer holds: the next tier answers
+    const bool have_k = n_surv >= k;
+    const float ek = have_k ? key_to_float((uint32_t)(surv[k - 1] >> 32)) : 0.0f;
+    if (thr_T) {
+        if (threadIdx.x == 0 && (overflow[blockIdx.x] != 0 || !have_k || !(thr_T[blockIdx.x] - eps > ek))) bad = true;
+    } else {
+        for (uint32_t l = threadIdx.x; l < lists_per_query; l += blockDim.x) {
+            const uint64_t *lst = mine + (size_t)l * keep;
+            uint32_t worst = 0;
+            bool full = true;
+            for (uint32_t j = 0; j < keep; j++) {
+                const uint64_t c = lst[j];
+                if (c == kEmptySlot)
+                    full = false;
+                else
+                    worst = max(worst, (uint32_t)(c >> 32));
+            }
+            if (!full) continue; // the list holds every row of its range that passed the kernel's threshold
+            if (!have_k)
+                bad = true; // fewer than k rows found although a list was truncated
+            else if (!(key_to_float(worst) - eps > ek))
+                bad = true;
+        }
+    }
+    if (bad) atomicOr(&s_bad, 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) ok[q] = s_bad ? 0u : ok_value; // 1 = first tier, 2 = second tier (any non-zero = proven)
+}
+
+// indices of the queries the first tier left unproven, densely packed: idx[0, *count)
+__global__ void compact_unproven_kernel(const uint32_t *__restrict__ ok, uint32_t nq, uint32_t *__restrict__ idx,
+                                        uint32_t *__restrict__ count) {
+    __shared__ uint32_t n;
+    if (threadIdx.x == 0) n = 0;
+    __syncthreads();
+    for (uint32_t q0 = 0; q0 < nq; q0 += blockDim.x) { // one CTA, ascending order kept chunk by chunk
+        const uint32_t q = q0 + threadIdx.x;
+        const bool un = q < nq && ok[q] == 0;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, un);
+        __shared__ uint32_t wbase[32];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) wbase[warp] = __popc(m);
+        __syncthreads();
+        uint32_t before = 0;
+        for (int w = 0; w < warp; w++) before += wbase[w];
+        uint32_t all = 0;
+        for (uint32_t w = 0; w < blockDim.x / 32; w++) all += wbase[w];
+        if (un) idx[n + before + __popc(m & ((1u << lane) - 1u))] = q;
+        __syncthreads();
+        if (threadIdx.x == 0) n += all;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = n;
+}
+// dst row i = src row idx[i] for i < *count (fp16 query rows and, optionally, their squared norms)
+__global__ void gather_queries_kernel(const uint8_t *__restrict__ src, size_t pitch, const float *__restrict__ src_n2,
+                                      const uint32_t *__restrict__ idx, const uint32_t *__restrict__ count,
+                                      uint8_t *__restrict__ dst, float *__restrict__ dst_n2) {
+    const uint32_t n = *count;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src + (size_t)idx[i] * pitch);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst + (size_t)i * pitch);
+        for (uint32_t c = threadIdx.x; c < pitch / 16; c += blockDim.x) d4[c] = s4[c];
+        if (src_n2 && threadIdx.x == 0) dst_n2[i] = src_n2[idx[i]];
+    }
 }
 
 // ================================================================================================
@@ -1078,13 +1312,18 @@ static uint32_t qtmem_nacc() {
     }
     return (uint32_t)v;
 }
-static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl, bool int_cos) {
-    if (kind == CoarseDirect16) return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 0> : (const void *)coarse_qtmem_kernel<true, 8, 0>;
+static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl, bool int_cos, bool fixed = false) {
+    if (kind == CoarseDirect16)
+        return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 0, false> : (const void *)coarse_qtmem_kernel<true, 8, 0, false>;
     if (kind == CoarseDirect8) {
-        if (int_cos) return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 2> : (const void *)coarse_qtmem_kernel<true, 8, 2>;
-        return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 1> : (const void *)coarse_qtmem_kernel<true, 8, 1>;
+        if (int_cos) return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 2, false> : (const void *)coarse_qtmem_kernel<true, 8, 2, false>;
+        return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 1, false> : (const void *)coarse_qtmem_kernel<true, 8, 1, false>;
     }
-    return int_cos ? (const void *)coarse_qtmem_kernel<false, 3, 3> : (const void *)coarse_qtmem_kernel<false, 3, 0>; // fp32 route: L2 ? 
+    // fp32 route (shadow rows): the flag selects the squared-L2 epilogue; epl 8 = lists of up to 128 (second tier, k > 16);
+    // fixed = admission bound from the sample pass, lists of 96 without compaction
+    if (fixed) return int_cos ? (const void *)coarse_qtmem_kernel<false, 3, 3, true> : (const void *)coarse_qtmem_kernel<false, 3, 0, true>;
+    if (int_cos) return epl == 3 ? (const void *)coarse_qtmem_kernel<false, 3, 3, false> : (const void *)coarse_qtmem_kernel<false, 8, 3, false>;
+    return epl == 3 ? (const void *)coarse_qtmem_kernel<false, 3, 0, false> : (const void *)coarse_qtmem_kernel<false, 8, 0, false>;
 }
 static size_t qtmem_fixed_smem(uint32_t num_kb) {
     const uint32_t kb_t = (512u - qtmem_nacc() * kQN) / 32u;
@@ -1125,17 +1364,24 @@ bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind k
     return encode_fn() != nullptr;
 }
 
-CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32_t k) {
+CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32_t k, uint32_t keep_override, uint32_t tile_stride,
+                       bool fixed) {
     CoarsePlan p{};
     p.kind = kind;
+    p.tile_stride = std::max(1u, tile_stride);
+    p.fixed = fixed && kind == CoarseF16;
     if (kind == CoarseF16 || kind == CoarseDirect16 || kind == CoarseDirect8) {
         p.num_kb = kind == CoarseDirect8 ? (c.dim + 127) / 128 : (c.dim + 63) / 64;
-        p.tiles = (c.n_rows + kQN - 1) / kQN;
+        p.tiles = ((c.n_rows + kQN - 1) / kQN + p.tile_stride - 1) / p.tile_stride; // row tiles this pass visits
         p.grid_y = (nq + kQM - 1) / kQM;
         const uint32_t sms = (uint32_t)device_sm_count();
         p.grid_x = std::max(1u, std::min(p.tiles, sms / p.grid_y));
-        p.keep = kind == CoarseF16 ? kCoarseKeep : (k <= 32 ? 32u : 128u); // direct: the CTA's exact top-k of its rows
+        // direct routes: the CTA's exact top-k of its rows.  fp32 route: candidates per (row range, query) — kCoarseKeep
+        // for k <= 16, 128 for larger k and for the second tier
+        p.keep = kind == CoarseF16 ? (keep_override ? keep_override : (k <= kCoarseTier1MaxK ? kCoarseKeep : kCoarseKeepWide))
+                                   : (k <= 32 ? 32u : 128u);
         p.epl = p.keep <= 32 ? 3 : 8;
+        if (p.fixed) p.keep = kCoarseFixedCap, p.epl = 3; // every row below the bound, up to the list capacity
         p.stages = (uint32_t)std::min<size_t>(kQMaxStages, (kSmemLimit - qtmem_fixed_smem(p.num_kb)) / kQStageBytes);
         p.smem_bytes = qtmem_fixed_smem(p.num_kb) + (size_t)p.stages * kQStageBytes;
         // the query groups of a row range form a thread-block cluster (multicast of the row tiles)
@@ -1150,7 +1396,7 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32
                 p.csize = cs;
                 break;
             }
-        const void *kfn = qtmem_kernel_fn(kind, p.epl, kind == CoarseF16 ? c.metric == MT_L2 : c.metric == MT_COS);
+        const void *kfn = qtmem_kernel_fn(kind, p.epl, kind == CoarseF16 ? c.metric == MT_L2 : c.metric == MT_COS, p.fixed);
         if (p.csize > 1) {
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
             cudaLaunchConfig_t cfg{};
@@ -1181,10 +1427,10 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32
     const uint32_t sms = (uint32_t)device_sm_count();
     p.grid_x = std::max(1u, std::min(p.tiles, sms / p.grid_y));
     p.keep = kCoarseKeep;
-    const size_t fixed = fixed_smem(p.num_kb);
-    p.stages = (uint32_t)std::min<size_t>(kMaxStages, (kSmemLimit - fixed) / kStageBytes);
+    const size_t fixed_bytes = fixed_smem(p.num_kb);
+    p.stages = (uint32_t)std::min<size_t>(kMaxStages, (kSmemLimit - fixed_bytes) / kStageBytes);
     p.cand_elems = (size_t)nq * p.grid_x * p.keep;
-    p.smem_bytes = fixed + (size_t)p.stages * kStageBytes;
+    p.smem_bytes = fixed_bytes + (size_t)p.stages * kStageBytes;
     return p;
 }
 
@@ -1203,9 +1449,10 @@ static cudaError_t launch_coarse_t(const void *rows, size_t pitch, uint32_t n_ro
 }
 
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
-                          uint64_t *d_scratch, cudaStream_t s) {
+                          uint64_t *d_scratch, cudaStream_t s, const uint32_t *d_nq_dev, const float *d_thr_fixed, uint32_t *d_overflow) {
     if (p.kind == CoarseF16 || p.kind == CoarseDirect16 || p.kind == CoarseDirect8) {
-        const void *kfn = qtmem_kernel_fn(p.kind, p.epl, o.int_cosine != 0); // (CoarseF16: the flag selects the L2 epilogue)
+        if (p.fixed && (!d_thr_fixed || !d_overflow)) return cudaErrorInvalidValue;
+        const void *kfn = qtmem_kernel_fn(p.kind, p.epl, o.int_cosine != 0, p.fixed); // (CoarseF16: the flag selects the L2 epilogue)
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
         if (e != cudaSuccess) return e;
         CUtensorMap mr{};
@@ -1237,9 +1484,10 @@ cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim
         size_t rp = o.pitch, qp = o.qpitch;
         const float *rn2 = o.row_norm2, *qn2 = o.q_norm2;
         uint32_t a_nrows = n_rows, a_nq = nq, a_dim = dim, a_rb = row_bytes, a_kb = p.num_kb, a_tiles = p.tiles, a_keep = p.keep,
-                 a_st = p.stages, a_cs = p.csize, a_nacc = qtmem_nacc(), a_idesc = idesc;
+                 a_st = p.stages, a_cs = p.csize, a_nacc = qtmem_nacc(), a_idesc = idesc, a_stride = p.tile_stride;
         void *args[] = {&mr,    &rows,   &rp,   &qs,   &qp,     &rn2, &qn2, &a_nrows, &a_nq,      &a_dim, &a_rb,
-                        &a_kb,  &a_tiles, &a_keep, &a_st, &a_cs, &a_nacc,  &a_idesc, &d_scratch, &d_cand};
+                        &a_kb,  &a_tiles, &a_keep, &a_st, &a_cs, &a_nacc,  &a_idesc, &d_scratch, &d_cand, &d_nq_dev,
+                        &a_stride, &d_thr_fixed, &d_overflow};
         return cudaLaunchKernelExC(&cfg, kfn, args);
     }
     return launch_coarse_t<CfgTF32>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);
@@ -1330,23 +1578,38 @@ cudaError_t launch_to_f16(const void *src, size_t spitch, uint32_t dim, uint32_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_rescore(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t per_query,
-                           const uint64_t *d_cand, uint64_t *d_exact, cudaStream_t s) {
-    const size_t total = (size_t)nq * per_query;
-    const uint32_t grid = (uint32_t)std::max<size_t>(1, std::min<size_t>((total + 7) / 8, (size_t)device_sm_count() * 8));
+cudaError_t launch_refine(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t lists_per_query, uint32_t keep,
+                          uint32_t k, const uint64_t *d_cand, float eps, const float *d_q_norm2, float max_norm, uint32_t *d_ok,
+                          uint64_t *d_out, const uint32_t *d_q_index, const uint32_t *d_nq_dev, cudaStream_t s, const float *d_thr_T,
+                          const uint32_t *d_overflow) {
+    if (nq == 0) return cudaSuccess;
+    const uint32_t okv = d_q_index ? 2u : 1u;
+    const uint8_t *rows = static_cast<const uint8_t *>(c.rows), *qs = static_cast<const uint8_t *>(d_queries);
     if (c.metric == MT_L2)
-        rescore_kernel<MT_L2><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(c.rows), c.pitch, c.dim,
-                                                   static_cast<const uint8_t *>(d_queries), qpitch, nq, per_query, d_cand, d_exact);
+        refine_kernel<MT_L2><<<nq, 256, 0, s>>>(rows, c.pitch, c.dim, qs, qpitch, nq, lists_per_query, keep, k, d_cand, eps, d_q_norm2,
+                                                max_norm, d_ok, okv, d_out, d_q_index, d_nq_dev, d_thr_T, d_overflow);
     else
-        rescore_kernel<MT_IP><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(c.rows), c.pitch, c.dim,
-                                                   static_cast<const uint8_t *>(d_queries), qpitch, nq, per_query, d_cand, d_exact);
+        refine_kernel<MT_IP><<<nq, 256, 0, s>>>(rows, c.pitch, c.dim, qs, qpitch, nq, lists_per_query, keep, k, d_cand, eps, d_q_norm2,
+                                                max_norm, d_ok, okv, d_out, d_q_index, d_nq_dev, d_thr_T, d_overflow);
     return cudaGetLastError();
 }
 
-cudaError_t launch_verify(const uint64_t *d_cand, const uint64_t *d_topk, uint32_t nq, uint32_t lists_per_query, uint32_t keep,
-                          uint32_t k, float eps, const float *d_q_norm2, float max_norm, int l2, uint32_t dim, uint32_t *d_ok,
-                          cudaStream_t s) {
-    verify_kernel<<<(nq + 127) / 128, 128, 0, s>>>(d_cand, d_topk, nq, lists_per_query, keep, k, eps, d_q_norm2, max_norm, l2, dim, d_ok);
+cudaError_t launch_threshold(const uint64_t *d_cand, uint32_t nq, uint32_t lists_per_query, uint32_t keep, uint32_t k, float eps,
+                             const float *d_q_norm2, float max_norm, uint32_t dim, int l2, float *d_thr, uint32_t *d_overflow, cudaStream_t s) {
+    if (nq == 0) return cudaSuccess;
+    threshold_kernel<<<nq, 256, 0, s>>>(d_cand, nq, lists_per_query, keep, k, eps, d_q_norm2, max_norm, dim, l2, d_thr, d_overflow);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact_unproven(const uint32_t *d_ok, uint32_t nq, uint32_t *d_idx, uint32_t *d_count, cudaStream_t s) {
+    compact_unproven_kernel<<<1, 256, 0, s>>>(d_ok, nq, d_idx, d_count);
+    return cudaGetLastError();
+}
+cudaError_t launch_gather_queries(const void *d_src, size_t pitch, const float *d_src_n2, const uint32_t *d_idx, const uint32_t *d_count,
+                                  uint32_t max_n, void *d_dst, float *d_dst_n2, cudaStream_t s) {
+    if (max_n == 0) return cudaSuccess;
+    gather_queries_kernel<<<std::min(max_n, 256u), 128, 0, s>>>(static_cast<const uint8_t *>(d_src), pitch, d_src_n2, d_idx, d_count,
+                                                               static_cast<uint8_t *>(d_dst), d_dst_n2);
     return cudaGetLastError();
 }
 

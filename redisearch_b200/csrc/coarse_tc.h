@@ -6,8 +6,11 @@
 
 namespace rsb200 {
 
-constexpr uint32_t kCoarseKeep = 24;   // candidates kept per (CTA row range, query)
-constexpr uint32_t kCoarseMaxK = 16;   // largest k served by the coarse path
+constexpr uint32_t kCoarseKeep = 24;       // candidates kept per (CTA row range, query), first tier
+constexpr uint32_t kCoarseKeepWide = 128;  // second tier (queries the first proof left open) and first tier of k > 16
+constexpr uint32_t kCoarseTier1MaxK = 16;  // largest k the 24-entry lists serve
+constexpr uint32_t kCoarseMaxK = 128;      // largest k served by the coarse path
+constexpr uint32_t kCoarseFixedCap = 96;   // list capacity of the fixed-bound main pass (rows below the bound per row range)
 // |approx - exact| bounds for unit vectors (Cauchy-Schwarz over the dot product: sum |a_i b_i| <= 1):
 //  TF32: each operand truncated to 11 significant bits -> 2 * 2^-10 relative per product, + accumulation slack;
 //  F16 : each operand rounded to nearest, 11 significant bits -> 2 * 2^-11 = 9.8e-4 per product; elements below
@@ -24,6 +27,8 @@ struct CoarsePlan {
     uint32_t grid_x, grid_y, num_kb, tiles, keep;
     uint32_t stages; // depth of the row-tile ring in shared memory
     uint32_t epl;    // candidate-list entries per lane of the compacting warp (3 or 8)
+    uint32_t tile_stride; // 1 = every row tile; n = every n-th (the sample pass)
+    bool fixed;      // fixed admission bound per query (CoarseF16 main pass) instead of adaptive top-`keep` lists
     uint32_t csize;  // thread-block cluster size along y (query groups sharing multicast row tiles); 1 = none
     size_t cand_elems; // uint64 per (query, list, keep)
     size_t scratch_elems; // uint64 of per-CTA candidate-list scratch (CoarseF16), 0 otherwise
@@ -43,9 +48,17 @@ struct CoarseOperands {
     const float *q_norm2;   //                 |q|^2 per query
 };
 bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind kind);
-CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32_t k);
+// keep_override != 0 (CoarseF16 only): candidates per list instead of the default for k
+CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32_t k, uint32_t keep_override = 0, uint32_t tile_stride = 1,
+                       bool fixed = false);
+// d_nq_dev (nullable): the number of live queries is read from device memory (min with nq); 0 = the kernel exits at once
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
-                          uint64_t *d_scratch, cudaStream_t s);
+                          uint64_t *d_scratch, cudaStream_t s, const uint32_t *d_nq_dev = nullptr, const float *d_thr_fixed = nullptr,
+                          uint32_t *d_overflow = nullptr);
+// bound of the fixed pass from the sample pass's candidate lists: d_thr[q] = k-th smallest approximate distance + 2 eps;
+// clears d_overflow[q]
+cudaError_t launch_threshold(const uint64_t *d_cand, uint32_t nq, uint32_t lists_per_query, uint32_t keep, uint32_t k, float eps,
+                             const float *d_q_norm2, float max_norm, uint32_t dim, int l2, float *d_thr, uint32_t *d_overflow, cudaStream_t s);
 // fp32 rows [first, first+n) -> the tiled fp16 shadow copy read by the CoarseF16 kernel (layout in coarse_tc.cu);
 // the buffer holds coarse_shadow_bytes(capacity_rows, dim) bytes
 size_t coarse_shadow_bytes(uint32_t rows, uint32_t dim);
@@ -53,13 +66,20 @@ cudaError_t launch_to_f16_tiled(const void *src, size_t spitch, uint32_t dim, ui
 // fp32 rows [first, first+n) -> row-major fp16 rows (the query batch; dim % 8 == 0)
 cudaError_t launch_to_f16(const void *src, size_t spitch, uint32_t dim, uint32_t first, uint32_t n, void *dst, size_t dpitch,
                           cudaStream_t s);
-cudaError_t launch_rescore(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t per_query,
-                           const uint64_t *d_cand, uint64_t *d_exact, cudaStream_t s);
-// q_norm2 == NULL: unit vectors, |approx - exact| <= eps.  Otherwise the bound scales with max_norm (over all rows) and
-// |q| (see verify_kernel); l2 != 0: distances are squared L2 instead of 1 - dot.
-cudaError_t launch_verify(const uint64_t *d_cand, const uint64_t *d_topk, uint32_t nq, uint32_t lists_per_query, uint32_t keep,
-                          uint32_t k, float eps, const float *d_q_norm2, float max_norm, int l2, uint32_t dim, uint32_t *d_ok,
-                          cudaStream_t s);
+// One CTA per query: exact rescoring of the candidates within 2 eps of the k-th best approximate distance, exact top-k
+// (d_out[q][k], ascending, kEmptySlot padded) and the completeness proof (d_ok[q]).  d_q_norm2 == NULL: unit vectors,
+// |approx - exact| <= eps; otherwise the bound scales with max_norm (over all rows) and |q| (refine_kernel).  Second tier:
+// d_q_index[i] = query of the original batch whose lists sit at position i (d_q_norm2 is indexed by position), *d_nq_dev
+// live positions.
+cudaError_t launch_refine(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t lists_per_query, uint32_t keep,
+                          uint32_t k, const uint64_t *d_cand, float eps, const float *d_q_norm2, float max_norm, uint32_t *d_ok,
+                          uint64_t *d_out, const uint32_t *d_q_index, const uint32_t *d_nq_dev, cudaStream_t s,
+                          const float *d_thr_T = nullptr, const uint32_t *d_overflow = nullptr);
+// d_idx[0, *d_count) = the queries with d_ok == 0, ascending
+cudaError_t launch_compact_unproven(const uint32_t *d_ok, uint32_t nq, uint32_t *d_idx, uint32_t *d_count, cudaStream_t s);
+// row i of dst = row d_idx[i] of src (pitch % 16 == 0), squared norms likewise (nullable), for i < *d_count
+cudaError_t launch_gather_queries(const void *d_src, size_t pitch, const float *d_src_n2, const uint32_t *d_idx, const uint32_t *d_count,
+                                  uint32_t max_n, void *d_dst, float *d_dst_n2, cudaStream_t s);
 // |row|^2 of fp32 rows [first, first+n) into d_norm2[first..]; d_stats (nullable) = {max |row|^2, max |x|} as float bits
 cudaError_t launch_row_stats(const void *rows, size_t pitch, uint32_t dim, uint32_t first, uint32_t n, float *d_norm2, uint32_t *d_stats,
                              cudaStream_t s);

@@ -654,6 +654,27 @@ VecSimQueryReply *FlatIndex::topk(const void *q, size_t k, VecSimQueryParams *qp
 // -1 = from env VECSIM_B200_COARSE (default 1), 0 = exact scans only, 1 = fp16 shadow rows, 2 = TF32 on the fp32 rows
 std::atomic<int> g_coarse_mode{-1};
 
+// second tier of the coarse route (lists of 128 for the queries the first proof left open); VECSIM_B200_TIER2=0 turns it off
+static bool coarse_tier2_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("VECSIM_B200_TIER2");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
+
+// two-pass first tier of the fp16 route (sample pass -> fixed admission bound -> main pass); VECSIM_B200_FIXED=0 falls back
+// to the single pass with adaptive lists
+static bool coarse_fixed_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("VECSIM_B200_FIXED");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
+
 static int coarse_mode() {
     int m = g_coarse_mode.load();
     if (m < 0) {
@@ -816,19 +837,56 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         *d_result = c.d_out;
         return ok;
     }
-    const CoarsePlan cp = plan_coarse(v, nq, kind, ke);
+    // fp16 route, first tier in two passes over the shadow rows:
+    //   sample pass   every `stride`-th row tile with adaptive top-`keep` lists -> per query the bound
+    //                 T = (k-th best approximate distance of the sample) + 2 eps
+    //   main pass     all row tiles, every row with approximate distance < T is kept (fixed bound: no running thresholds,
+    //                 no list compaction — ncu had the epilogue warps busy 62 % of the pass with exactly that)
+    // TF32 route: one pass with adaptive lists, as before.
+    const bool two_pass = kind == CoarseF16 && coarse_fixed_enabled();
+    CoarsePlan cp = plan_coarse(v, nq, kind, ke); // TF32 / single-pass: the adaptive lists ARE the first tier
+    CoarsePlan cps{};                             // sample pass
+    if (two_pass) {
+        // expected rows below T per (query, row range) = k / (sample fraction * ranges): aim at 24 of the 96 slots
+        const CoarsePlan probe = plan_coarse(v, nq, kind, ke, 0, 1, true);
+        double f = (double)ke / (24.0 * probe.grid_x);
+        f = std::min(0.25, std::max(0.01, f));
+        const uint32_t stride = (uint32_t)std::max(1.0, std::floor(1.0 / f));
+        cps = plan_coarse(v, nq, kind, ke, 0, stride, false);
+        cp = probe;
+    }
     const size_t per_query = (size_t)cp.grid_x * cp.keep;
+    // second tier (fp16 route): the queries whose first-tier proof failed (a list of the main pass overflowed: more than 96
+    // rows of one range within the bound — clustered corpora) are packed to the front and run once more with adaptive
+    // lists of 128 per row range.  Nothing is known on the host: the tier's kernels read the count of open queries from
+    // device memory and leave at once when it is zero.
+    const bool tier2 = kind == CoarseF16 && coarse_tier2_enabled();
+    CoarsePlan cp2{};
+    if (tier2) cp2 = plan_coarse(v, nq, kind, ke, kCoarseKeepWide);
     const size_t nA = (size_t)nq * per_query, nO = (size_t)nq * ke;
+    const size_t nS = two_pass ? (size_t)nq * cps.grid_x * cps.keep : 0;
+    const size_t nA2 = tier2 ? (size_t)nq * cp2.grid_x * cp2.keep : 0;
     const size_t q16_pitch = (dim_ * 2 + 15) & ~(size_t)15;
     const size_t q16_elems = kind == CoarseF16 ? ((size_t)nq * q16_pitch + 7) / 8 : 0;
     const size_t qn_elems = unit ? 0 : (nq + 1) / 2 + 1; // |q|^2 per query (floats)
-    const size_t total = 2 * nA + 2 * nO + sp.cand_elems + q16_elems + cp.scratch_elems + qn_elems + (nq + 1) / 2 + 8;
+    const size_t scratch = std::max(std::max(cp.scratch_elems, two_pass ? cps.scratch_elems : 0), tier2 ? cp2.scratch_elems : 0);
+    const size_t flag_elems = (nq + 1) / 2 + 1; // nq uint32 / float values
+    const size_t total = nA + nS + nA2 + 2 * nO + sp.cand_elems + (tier2 ? 2 : 1) * (q16_elems + qn_elems) + scratch + 5 * flag_elems + 16;
     if (!c.need_cand(total) || !c.need_out(nO)) return false;
-    uint64_t *coarse_cand = c.d_cand, *exact = coarse_cand + nA, *out1 = exact + nA, *out2 = out1 + nO, *cand2 = out2 + nO;
+    uint64_t *coarse_cand = c.d_cand, *cand_s = coarse_cand + nA, *cand_t2 = cand_s + nS, *out1 = cand_t2 + nA2, *out2 = out1 + nO,
+             *cand2 = out2 + nO;
     uint64_t *q16 = cand2 + sp.cand_elems;
-    uint64_t *list_scratch = q16 + q16_elems;
-    float *d_qn2 = unit ? nullptr : reinterpret_cast<float *>(list_scratch + cp.scratch_elems);
-    uint32_t *d_ok = reinterpret_cast<uint32_t *>(list_scratch + cp.scratch_elems + qn_elems);
+    uint64_t *q16_t2 = q16 + q16_elems;
+    uint64_t *list_scratch = q16_t2 + (tier2 ? q16_elems : 0);
+    uint64_t *tail = list_scratch + scratch;
+    float *d_qn2 = unit ? nullptr : reinterpret_cast<float *>(tail);
+    float *d_qn2_t2 = (unit || !tier2) ? nullptr : reinterpret_cast<float *>(tail + qn_elems);
+    tail += (tier2 ? 2 : 1) * qn_elems;
+    uint32_t *d_ok = reinterpret_cast<uint32_t *>(tail);
+    uint32_t *d_idx = reinterpret_cast<uint32_t *>(tail + flag_elems); // tier 2: indices of the open queries
+    uint32_t *d_n2 = reinterpret_cast<uint32_t *>(tail + 2 * flag_elems); //         and their count
+    float *d_thr = reinterpret_cast<float *>(tail + 3 * flag_elems);       // fixed bound per query
+    uint32_t *d_ovf = reinterpret_cast<uint32_t *>(tail + 4 * flag_elems); // a list of the main pass ran full
     c.d_last_ok = d_ok;
     c.last_ok_n = nq;
     CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, 0, 0, nullptr, nullptr};
@@ -839,18 +897,36 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         if (!unit) ok = ok && launch_row_stats(d_q, qpitch, (uint32_t)dim_, 0, nq, d_qn2, nullptr, st) == cudaSuccess;
         lc.launches += unit ? 1 : 2;
     }
+    const float eps = coarse_eps(kind);
+    if (two_pass) {
+        ok = ok && launch_coarse(ops, v.n_rows, v.dim, nq, cps, cand_s, list_scratch, st) == cudaSuccess;
+        ok = ok && launch_threshold(cand_s, nq, cps.grid_x, cps.keep, ke, eps, d_qn2, shadow_max_norm_, (uint32_t)dim_, mkind_ == MT_L2 ? 1 : 0, d_thr,
+                                    d_ovf, st) == cudaSuccess;
+        lc.launches += 2;
+    }
     cudaEventRecord(c.ev_start, st);
-    ok = ok && launch_coarse(ops, v.n_rows, v.dim, nq, cp, coarse_cand, list_scratch, st) == cudaSuccess;
+    ok = ok && launch_coarse(ops, v.n_rows, v.dim, nq, cp, coarse_cand, list_scratch, st, nullptr, two_pass ? d_thr : nullptr,
+                             two_pass ? d_ovf : nullptr) == cudaSuccess;
     cudaEventRecord(c.ev_stop, st);
-    ok = ok && launch_rescore(v, d_q, qpitch, nq, (uint32_t)per_query, coarse_cand, exact, st) == cudaSuccess;
-    ok = ok && launch_final_select(exact, nq, (uint32_t)per_query, ke, out1, st, &lc) == cudaSuccess;
-    ok = ok && launch_verify(coarse_cand, out1, nq, cp.grid_x, cp.keep, ke, coarse_eps(kind), d_qn2, shadow_max_norm_, mkind_ == MT_L2 ? 1 : 0,
-                             (uint32_t)dim_, d_ok, st) == cudaSuccess;
+    // exact rescoring of the few candidates that can still matter + exact top-k + proof, one CTA per query
+    ok = ok && launch_refine(v, d_q, qpitch, nq, cp.grid_x, cp.keep, ke, coarse_cand, eps, d_qn2, shadow_max_norm_, d_ok, out1, nullptr, nullptr,
+                             st, two_pass ? d_thr : nullptr, two_pass ? d_ovf : nullptr) == cudaSuccess;
+    lc.launches += 2;
+    if (tier2) {
+        ok = ok && launch_compact_unproven(d_ok, nq, d_idx, d_n2, st) == cudaSuccess;
+        ok = ok && launch_gather_queries(q16, q16_pitch, d_qn2, d_idx, d_n2, nq, q16_t2, d_qn2_t2, st) == cudaSuccess;
+        CoarseOperands ops2 = ops;
+        ops2.queries = q16_t2;
+        ops2.q_norm2 = d_qn2_t2;
+        ok = ok && launch_coarse(ops2, v.n_rows, v.dim, nq, cp2, cand_t2, list_scratch, st, d_n2) == cudaSuccess;
+        ok = ok && launch_refine(v, d_q, qpitch, nq, cp2.grid_x, cp2.keep, ke, cand_t2, eps, d_qn2_t2, shadow_max_norm_, d_ok, out1, d_idx, d_n2,
+                                 st) == cudaSuccess;
+        lc.launches += 4;
+    }
     // exact fallback, entirely on device: CTAs whose queries are all verified exit at once
     ok = ok && launch_scan_topk(v, d_q, qpitch, nq, ke, sp, cand2, st, &lc, d_ok) == cudaSuccess;
     ok = ok && launch_final_select(cand2, nq, sp.lists_per_query * ke, ke, out2, st, &lc) == cudaSuccess;
     ok = ok && launch_blend(d_ok, out1, out2, nq, ke, c.d_out, st, &lc) == cudaSuccess;
-    lc.launches += 3;
     coarse_batches_++;
     *d_result = c.d_out;
     return ok;

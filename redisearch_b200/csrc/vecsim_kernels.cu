@@ -346,19 +346,21 @@ __global__ void unpack_results_kernel(const uint64_t *__restrict__ comp, uint32_
 }
 
 // One CTA per query, rank sort of G*k (score,label) pairs; empty entries have label < 0.
+// Shard g's arrays start score_stride floats / label_stride int64s after shard g-1's ([G][nq][k] arrays: nq*k; the
+// packed exchange buffer of the shard group: one block of labels + scores per shard).
 __global__ void merge_shards_kernel(const float *__restrict__ scores, const int64_t *__restrict__ labels, uint32_t G,
-                                    uint32_t nq, uint32_t k, float *__restrict__ out_scores,
-                                    int64_t *__restrict__ out_labels) {
+                                    uint32_t nq, uint32_t k, size_t score_stride, size_t label_stride,
+                                    float *__restrict__ out_scores, int64_t *__restrict__ out_labels) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t q = blockIdx.x, n = G * k;
     uint32_t *keys = reinterpret_cast<uint32_t *>(smem);
     int64_t *labs = reinterpret_cast<int64_t *>(smem + (((size_t)n * 4 + 15) & ~(size_t)15));
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t g = i / k, p = i - g * k;
-        const size_t src = ((size_t)g * nq + q) * k + p;
-        const int64_t l = labels[src];
+        const size_t src = (size_t)q * k + p;
+        const int64_t l = labels[(size_t)g * label_stride + src];
         labs[i] = l;
-        keys[i] = (l < 0) ? 0xFFFFFFFFu : orderable_key(scores[src]);
+        keys[i] = (l < 0) ? 0xFFFFFFFFu : orderable_key(scores[(size_t)g * score_stride + src]);
     }
     for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
         out_labels[(size_t)q * k + i] = -1;
@@ -641,14 +643,17 @@ cudaError_t launch_unpack_results(const uint64_t *d_comp, uint32_t nq, uint32_t 
 }
 
 cudaError_t launch_merge_shards(const float *d_scores, const int64_t *d_labels, uint32_t G, uint32_t nq, uint32_t k,
-                                float *d_out_scores, int64_t *d_out_labels, cudaStream_t s, LaunchCounters *ctr) {
+                                float *d_out_scores, int64_t *d_out_labels, cudaStream_t s, LaunchCounters *ctr,
+                                size_t score_stride, size_t label_stride) {
+    if (score_stride == 0) score_stride = (size_t)nq * k;
+    if (label_stride == 0) label_stride = (size_t)nq * k;
     if (nq == 0 || k == 0 || G == 0) return cudaSuccess;
     const size_t n = (size_t)G * k;
     const size_t smem = ((n * 4 + 15) & ~(size_t)15) + n * 8;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = ensure_smem(merge_shards_kernel, smem);
     if (e != cudaSuccess) return e;
-    merge_shards_kernel<<<nq, 256, smem, s>>>(d_scores, d_labels, G, nq, k, d_out_scores, d_out_labels);
+    merge_shards_kernel<<<nq, 256, smem, s>>>(d_scores, d_labels, G, nq, k, score_stride, label_stride, d_out_scores, d_out_labels);
     if (ctr) ctr->launches++;
     return cudaGetLastError();
 }

@@ -78,8 +78,9 @@ cudaError_t launch_unpack_results(const uint64_t *d_comp, uint32_t nq, uint32_t 
                                   const uint64_t *d_id_to_label, int64_t *d_labels, float *d_scores,
                                   cudaStream_t s, LaunchCounters *ctr);
 // [G][nq][k] (score,label) -> [nq][k] by (score asc, label asc); label -1 = empty.
+// score_stride / label_stride: elements between consecutive shards' arrays (0 = nq*k, i.e. dense [G][nq][k]).
 cudaError_t launch_merge_shards(const float *d_scores, const int64_t *d_labels, uint32_t G, uint32_t nq,
                                 uint32_t k, float *d_out_scores, int64_t *d_out_labels, cudaStream_t s,
-                                LaunchCounters *ctr);
+                                LaunchCounters *ctr, size_t score_stride = 0, size_t label_stride = 0);
 
 } // namespace rsb200

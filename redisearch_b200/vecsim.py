@@ -136,6 +136,15 @@ SIGNATURES = [
     ("VecSimB200_SetCoarseMode", None, [C.c_int]),
     ("VecSimB200_LastCoarseFlags", C.c_int, [_P, _P, _SZ]),
     ("VecSimB200_Version", C.c_char_p, []),
+    ("VecSimB200_ShardBlockBytes", _SZ, [_SZ, _SZ]),
+    ("VecSimB200_MergeShardBlocks", C.c_int, [_P, _SZ, _SZ, _SZ, _P, _P, _P]),
+    ("VecSimB200_ShardGroup_UniqueId", C.c_int, [_P]),
+    ("VecSimB200_ShardGroup_New", _P, [_P, C.c_int, C.c_int]),
+    ("VecSimB200_ShardGroup_Free", None, [_P]),
+    ("VecSimB200_ShardGroup_Rank", C.c_int, [_P]),
+    ("VecSimB200_ShardGroup_Size", C.c_int, [_P]),
+    ("VecSimB200_ShardGroup_TopKBatchDevice", C.c_int, [_P, _P, _P, _SZ, _SZ, _P, _P, _P]),
+    ("VecSimB200_ShardGroup_TopKBatch", C.c_int, [_P, _P, _P, _SZ, _SZ, _SZ, _P, _P]),
 ]
 # VecSim_SetMemoryFunctions takes a struct by value; declared in the header, bound lazily.
 EXTRA_SYMBOLS = ["VecSim_SetMemoryFunctions"]

@@ -71,6 +71,7 @@ def port():
         L.orc_index_all_sorted.argtypes = [_P, _P, _P, _P]
         L.orc_index_time_topk.restype = C.c_double
         L.orc_index_time_topk.argtypes = [_P, _P, _SZ, _SZ, _SZ, C.c_int, _P, _P]
+        L.orc_scan_topk_chunk.argtypes = [C.c_int, C.c_int, C.c_int, _SZ, _P, _SZ, _SZ, _SZ, _P, _SZ, _SZ, _SZ, C.c_int, _P, _P, _P]
         L.orc_mix64.restype = C.c_uint64
         L.orc_mix64.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
         L.orc_synth_f32.restype = C.c_float
@@ -118,6 +119,7 @@ def ref_vecsim():
         L.Ref_Distance.argtypes = [C.c_int, C.c_int, _SZ, _P, _P]
         L.Ref_Distances.argtypes = [C.c_int, C.c_int, _SZ, _P, _SZ, _SZ, _P, _P]
         L.Ref_Normalize.argtypes = [_P, _SZ, C.c_int]
+        L.Ref_ScanTopKChunk.argtypes = [C.c_int, C.c_int, _SZ, _P, _SZ, _SZ, _SZ, _P, _SZ, _SZ, _SZ, C.c_int, _P, _P, _P]
         L.Ref_TimeTopK.restype = C.c_double
         L.Ref_TimeTopK.argtypes = [_P, _P, _SZ, _SZ, _SZ, C.c_int, _P, _P]
         _ref = L
@@ -258,6 +260,38 @@ class RefIndex:
                 break
         self.L.Ref_BatchFree(it)
         return out
+
+
+class StreamingTopK:
+    """k nearest rows of a corpus that is handed over chunk by chunk (stored-form rows, e.g. copied back from the device):
+    the reference's own distance kernels + heap when oracle/_ref is built (Ref_ScanTopKChunk), else the C restatement."""
+
+    def __init__(self, vtype, metric, dim, queries_stored_form, k, threads):
+        self.vtype, self.metric, self.dim, self.k, self.threads = vtype, metric, dim, k, max(1, threads)
+        self.q = np.ascontiguousarray(queries_stored_form)
+        nq = self.q.shape[0]
+        self.ids = np.zeros((nq, k), dtype=np.uint64)
+        self.scores = np.zeros((nq, k), dtype=np.float32)
+        self.counts = np.zeros(nq, dtype=np.uint64)
+        self.kind = "reference" if ref_vecsim() is not None else "port"
+
+    def feed(self, rows, label0):
+        rows = np.ascontiguousarray(rows)
+        nq = self.q.shape[0]
+        if self.kind == "reference":
+            ref_vecsim().Ref_ScanTopKChunk(self.vtype, self.metric, self.dim, _p(rows), rows.strides[0], rows.shape[0], label0,
+                                           _p(self.q), self.q.strides[0], nq, self.k, self.threads, _p(self.ids), _p(self.scores),
+                                           _p(self.counts))
+        else:
+            port().orc_scan_topk_chunk(self.vtype, self.metric, TIER_AVX512, self.dim, _p(rows), rows.strides[0], rows.shape[0], label0,
+                                       _p(self.q), self.q.strides[0], nq, self.k, self.threads, _p(self.ids), _p(self.scores),
+                                       _p(self.counts))
+
+    def result(self, i):
+        """(labels, scores) of query i ordered by (score, label) like a drained reference heap."""
+        c = int(self.counts[i])
+        order = np.lexsort((self.ids[i, :c], self.scores[i, :c]))
+        return self.ids[i, :c][order].astype(np.int64), self.scores[i, :c][order]
 
 
 def synth_rows(vtype, seed, row0, nrows, dim):

@@ -236,3 +236,31 @@ def test_known_answers_spaces(oracle):
     ai = np.array([1, 2, 3, 4, 5], dtype=np.int8)
     assert oracle.orc_distance(I8, L2, dim, ol._p(ai), ol._p(ai), 0) == 0.0
     assert oracle.orc_distance(I8, IP, dim, ol._p(ai), ol._p(ai), 0) == 1.0 - 55.0
+
+
+def test_streaming_topk_equals_the_reference_index():
+    """bench.py's parity check at the full 10M x 768 size feeds the device's own rows back chunk by chunk to
+    ol.StreamingTopK (the reference's distance kernels + heap over a flat array): it must answer exactly like the
+    reference's BruteForceIndex::topKQuery over the same rows, ties at the boundary included."""
+    n, dim, k = 30_000, 96, 10
+    rows = ol.synth_rows(ol.F32, 1, 0, n, dim)
+    rows[5000:5010] = rows[100]  # exact duplicates: score ties resolved like the heap does
+    for r in rows:
+        ol.port().orc_normalize(ol._p(r), dim, ol.F32)
+    qs = ol.synth_rows(ol.F32, 2, 0, 4, dim)
+    qs[3] = rows[100]
+    for r in qs:
+        ol.port().orc_normalize(ol._p(r), dim, ol.F32)
+    ix = ol.PortIndex(ol.F32, dim, ol.IP, tier=ol.TIER_AVX512)
+    ix.add_many(rows, 1)
+    kinds = ["port"] + (["reference"] if ol.ref_vecsim() is not None else [])
+    for kind in kinds:
+        st = ol.StreamingTopK(ol.F32, ol.COS, dim, qs, k, 3)
+        st.kind = kind
+        for c in range(0, n, 7000):
+            st.feed(rows[c:c + 7000], 1 + c)
+        for i in range(len(qs)):
+            a, b = ix.topk(qs[i], k)
+            l, s = st.result(i)
+            assert a.tolist() == l.tolist(), (kind, i)
+            assert b.astype(np.float32).tobytes() == s.tobytes()

@@ -135,3 +135,113 @@ def test_config5_shape_hybrid_filter_sharded():
     exp = sorted((np.float32(full.distance_from(int(d), qn)), int(d)) for d in filt.tolist())[:K]
     assert ml[0].cpu().numpy().tolist() == [d for _, d in exp]
     assert ms[0].cpu().numpy().tobytes() == np.array([s for s, _ in exp], dtype=np.float32).tobytes()
+
+
+@pytest.mark.parametrize("G,B,k", [(2, 5, 10), (8, 33, 10), (4, 3, 100), (3, 7, 1)])
+def test_packed_exchange_blocks_merge_like_the_dense_arrays(G, B, k):
+    """The shard group's exchange format — one block [labels int64 x B*k][scores float x B*k] per rank, padded to 16
+    bytes, rank-major after the single all-gather — merges to the same answer as the dense [G][B][k] arrays."""
+    import ctypes as C
+
+    import torch
+
+    from redisearch_b200 import vecsim as vs
+
+    L = vs.lib()
+    rng = np.random.default_rng(G * 7 + k)
+    gs = np.sort(rng.random((G, B, k)).astype(np.float32), axis=2)
+    gl = rng.permutation(G * B * k).reshape(G, B, k).astype(np.int64)
+    gl[rng.random((G, B, k)) < 0.2] = -1
+    block = int(L.VecSimB200_ShardBlockBytes(B, k))
+    assert block % 16 == 0 and block >= B * k * 12
+    buf = np.zeros(G * block, dtype=np.uint8)
+    for g in range(G):
+        buf[g * block:g * block + B * k * 8] = gl[g].reshape(-1).view(np.uint8)
+        buf[g * block + B * k * 8:g * block + B * k * 12] = gs[g].reshape(-1).view(np.uint8)
+    d = torch.from_numpy(buf).cuda()
+    out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+    out_l = torch.empty((B, k), dtype=torch.int64, device="cuda")
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert L.VecSimB200_MergeShardBlocks(d.data_ptr(), G, B, k, out_s.data_ptr(), out_l.data_ptr(), sp) == 0
+    torch.cuda.synchronize()
+    rs, rl = _merge_reference(gs, gl, k)
+    assert out_l.cpu().numpy().tolist() == rl.tolist()
+    a = out_s.cpu().numpy()
+    assert ((a == rs) | (np.isnan(a) & np.isnan(rs))).all()
+
+
+def test_shard_group_of_one_answers_like_the_index():
+    """world = 1: the collective entry points degenerate to the local scan (no NCCL is loaded)."""
+    from redisearch_b200 import vecsim as vs
+
+    L = vs.lib()
+    n, dim, k, nq = 30_000, 64, 10, 12
+    rows = ol.synth_rows(ol.F32, 42, 0, n, dim)
+    qs = ol.synth_rows(ol.F32, 43, 0, nq, dim)
+    ix = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, vs.VecSimMetric_Cosine)
+    ix.add_many(rows, label0=1)
+    g = L.VecSimB200_ShardGroup_New(None, 0, 1)
+    assert g and L.VecSimB200_ShardGroup_Size(g) == 1 and L.VecSimB200_ShardGroup_Rank(g) == 0
+    labels = np.zeros((nq, k), dtype=np.uint64)
+    scores = np.zeros((nq, k), dtype=np.float64)
+    assert L.VecSimB200_ShardGroup_TopKBatch(g, ix.h, qs.ctypes.data, qs.strides[0], nq, k, labels.ctypes.data, scores.ctypes.data) == 0
+    el, es, rc = ix.topk_batch(qs, k)
+    assert rc == 0 and (labels == el).all() and (scores.astype(np.float32) == es.astype(np.float32)).all()
+    L.VecSimB200_ShardGroup_Free(g)
+
+
+NCCL_SCRIPT = r'''
+import os, sys, ctypes as C
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as ol
+from redisearch_b200 import vecsim as vs, sharding
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo")          # control plane only: ships the 128-byte NCCL id
+L = vs.lib()
+idbuf = np.zeros(128, dtype=np.uint8)
+if rank == 0:
+    assert L.VecSimB200_ShardGroup_UniqueId(idbuf.ctypes.data) == 0
+t = torch.from_numpy(idbuf); dist.broadcast(t, 0)
+g = L.VecSimB200_ShardGroup_New(idbuf.ctypes.data, rank, world)
+assert g, "ncclCommInitRank failed"
+N, DIM, K, B = 200_000, 96, 10, 40
+lo, hi = sharding.shard_range(N, world, rank)
+rows = ol.synth_rows(ol.F32, 42, lo, hi - lo, DIM)
+qs = ol.synth_rows(ol.F32, 43, 0, B, DIM)
+ix = vs.VecSimIndex(vs.VecSimType_FLOAT32, DIM, vs.VecSimMetric_Cosine)
+ix.add_many(rows, label0=lo + 1)
+labels = np.zeros((B, K), dtype=np.uint64); scores = np.zeros((B, K), dtype=np.float64)
+for rep in range(3):
+    assert L.VecSimB200_ShardGroup_TopKBatch(g, ix.h, qs.ctypes.data, qs.strides[0], B, K, labels.ctypes.data, scores.ctypes.data) == 0
+# every rank checks the merged answer against the oracle over the whole corpus
+full = ol.PortIndex(ol.F32, DIM, ol.COS, tier=ol.TIER_AVX512)
+full.add_many(ol.synth_rows(ol.F32, 42, 0, N, DIM), 1)
+for i in range(B):
+    pi, ps = full.topk(qs[i], K)
+    assert labels[i].astype(np.int64).tolist() == pi.tolist(), (rank, i)
+    assert scores[i].astype(np.float32).tobytes() == ps.astype(np.float32).tobytes()
+L.VecSimB200_ShardGroup_Free(g)
+dist.barrier()
+if rank == 0: print("SHARDGROUP-NCCL-OK")
+'''
+
+
+def test_shard_group_over_nccl_two_ranks(tmp_path):
+    """Two processes, two GPUs: local scans, ONE ncclAllGather of the packed blocks inside the library, device merge;
+    every rank's merged answer equals the oracle's over the unsharded corpus.  Skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "sg.py"
+    script.write_text(f"ROOT = {root!r}\n" + NCCL_SCRIPT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDGROUP-NCCL-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
