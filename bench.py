@@ -1,26 +1,32 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the hot path (contract in the task statement).
 
-Workload (BASELINE.json configs[1]): FLAT 10M x 768 fp32, cosine, k=10, batch=256 queries, 1 x B200.
+Default workload (BASELINE.json configs[1]): FLAT 10M x 768 fp32, cosine, k=10, batch=256 queries.
 A "step" is one pass of the KNN hot path over one batch of 256 synthetic queries.
 
-  value   queries/s with queries and corpus already resident in HBM (VecSimB200_TopKQueryBatchDevice),
-          timed with CUDA events on the launching stream, max over ranks.
-  e2e     the same through the host-facing C-ABI (VecSimB200_TopKQueryBatch): host query blobs in,
-          host labels/scores out, H2D + D2H inside the timed region.
-  roofline  the dominant kernel, timed with CUDA events inside the library.  The batched pass is tensor-bound
-            (2*B*N*D flop against the measured dense bf16 peak in MEASURED_PEAKS.json); the HBM view
-            (algorithmic bytes = N*D*4 per launch, and the bytes the fp16 shadow actually costs) sits beside it
-            under roofline.hbm.  The single-query leg is HBM-bound.
-  cpu_baseline  the reference's own brute-force code (oracle/_ref, built from /root/reference) or,
-            if that library is absent, our C restatement, on a bounded sample.
+  value   true queries/s on the WHOLE corpus with queries and corpus resident in HBM, timed with CUDA events on the
+          launching stream, max over ranks.
+  e2e     the same through the host-facing C-ABI with HOST buffers: VecSimB200_TopKQueryBatch (N = 1) /
+          VecSimB200_ShardGroup_TopKBatch (N > 1: H2D, shard scan, the ONE ncclAllGather, device merge, D2H — all inside).
+  roofline  the dominant kernel (main pass of the tcgen05 coarse scan), timed with CUDA events inside the library.  The
+            batched pass is tensor-bound (2*B*N*D flop against the measured dense bf16 peak of MEASURED_PEAKS.json); the
+            HBM view sits beside it under roofline.hbm.  The single-query leg is HBM-bound.
+  parity_at_config  after the timed region, 16+ of the 256 queries are checked at the FULL size against the reference's
+            own distance kernels + heap (oracle/_ref) run over the device's corpus copied back to the host:
+            ids and score bits.
+  cpu_baseline  that same CPU scan, timed (one query per host thread over the full 10M x 768 corpus).
 
-N > 1 (torchrun): every rank owns its own 10M-row shard of an (N x 10M)-row corpus (weak scaling);
-a step scans the local shard for the same 256 queries, all-gathers the per-shard top-k over NCCL and
-merges on device (VecSimB200_MergeShardTopK).  value = N*256 / step time = throughput in units of
-"query x 10M-row shard".
+N > 1 (torchrun), --scaling strong (default): the 10M-row corpus of BASELINE configs[1] is row-sharded over the N GPUs
+(10M / N rows each); a step = local scan + one all-gather of the packed per-shard top-k + device merge, all inside
+VecSimB200_ShardGroup_TopKBatchDevice.  value = 256 / step time = QPS on exactly the BASELINE corpus at every N.
+--scaling weak: every GPU holds its own 10M rows (corpus = N x 10M); value is still true QPS (on the N x 10M corpus),
+`shard_query_rate` carries the additive figure (queries x 10M-row shards per second).
 
---impl reference: times the reference CPU implementation on the host cores (rank 0 only).
+--config 3 | 5: BASELINE configs[2] (50M x 768 fp16, IP, k=100, batch 1024, sharded) and configs[4] (hybrid filtered
+KNN: 10M x 768 fp32 pre-filtered by a 2-term posting-list intersection, k=10), same contract.
+
+--impl reference: the reference's own BruteForceIndex::topKQuery (oracle/_ref, compiled from /root/reference) on the host
+cores over the FULL 10M x 768 corpus (rank 0 only).
 """
 import argparse
 import ctypes as C
@@ -38,6 +44,22 @@ sys.path.insert(0, ROOT)
 METRIC = "KNN QPS @k=10 on 10M x 768 fp32 (cosine, batch=256)"
 N_ROWS, DIM, K, BATCH = 10_000_000, 768, 10, 256
 SEED_ROWS, SEED_QUERIES = 42, 43
+
+
+def usable_cores():
+    """Threads this process may really use: scheduler affinity, capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
 
 
 def load_peaks():
@@ -82,7 +104,7 @@ class ClockSampler:
                     self.samples.append(parts)
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1)
 
     def __enter__(self):
         self.t.start()
@@ -97,71 +119,106 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi samples"]}
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
         reasons = set()
         for s in self.samples:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def knn_config(rows_total, nq, k, world, scaling, dtype="fp32", metric="cosine"):
+    """The `config` object: identical for our arm and the reference arm (nothing run-dependent in here)."""
+    rows_gpu = rows_total // world if scaling == "strong" else rows_total
+    corpus = rows_total if scaling == "strong" else rows_total * world
+    shard = "" if world == 1 else f", row-sharded over {world} GPUs ({rows_gpu} rows each): one NCCL all-gather of per-shard top-k + device merge"
+    return {"workload": f"FLAT {corpus} x {DIM} {dtype} {metric} k={k} batch={nq}{shard}", "corpus_rows": corpus, "rows_per_gpu": rows_gpu,
+            "dim": DIM, "k": k, "batch": nq, "scaling": scaling,
+            "l2_policy": "the corpus (GBs per GPU) is far larger than the 126 MB L2: every step re-reads it from HBM, no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's own CPU code on the host cores
+# reference arm: the reference's own CPU code on the host cores, FULL corpus
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_qps(sample_rows, queries_per_thread, threads):
-    """Times BruteForceIndex::topKQuery (oracle/_ref = the reference's sources) — or our C restatement
-    if that library was not built — on `sample_rows` x 768 cosine rows; scales QPS linearly to 10M rows
-    (the scan is a streaming pass).  Returns (qps_at_10M, info)."""
+def build_reference_index(ol, rows_total, threads, log):
+    """10M x 768 fp32 cosine rows into the reference's BruteForceIndex.  Rows are generated by `threads` workers (the
+    generator call releases the GIL) and added 250K at a time; blockSize 65536 (a BFParams knob of the reference) keeps
+    brute_force.h's per-block resize of idToLabelMapping from going quadratic at 10M rows."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+
+    ix = ol.RefIndex(ol.F32, DIM, ol.COS, block_size=65536) if ol.ref_vecsim() is not None else None
+    kind = "reference"
+    if ix is None:
+        kind = "port"
+        ix = ol.PortIndex(ol.F32, DIM, ol.COS, tier=ol.TIER_AVX512)
+    chunk = 250_000
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        done = 0
+        while done < rows_total:
+            n = min(chunk, rows_total - done)
+            buf = np.empty((n, DIM), dtype=np.float32)
+            parts = max(1, min(threads, n // 4096))
+            bounds = [(done + n * i // parts, done + n * (i + 1) // parts) for i in range(parts)]
+            list(ex.map(lambda b: ol.port().orc_synth_rows(ol.F32, SEED_ROWS, b[0], b[1] - b[0], DIM, ol._p(buf[b[0] - done:b[1] - done])), bounds))
+            ix.add_many(buf, done + 1)
+            done += n
+    log["build_seconds"] = round(time.perf_counter() - t0, 1)
+    return ix, kind
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
 
     import oracle_lib as ol
 
-    rows = ol.synth_rows(ol.F32, SEED_ROWS, 0, sample_rows, DIM)
-    nq = queries_per_thread * threads
-    qs = ol.synth_rows(ol.F32, SEED_QUERIES, 0, nq, DIM)
-    ref = ol.ref_vecsim()
-    if ref is not None:
-        kind = "reference"
-        ix = ol.RefIndex(ol.F32, DIM, ol.COS)
-        ix.add_many(rows, 1)
-        secs = ref.Ref_TimeTopK(ix.h, ol._p(qs), qs.strides[0], nq, K, threads, None, None)
-    else:
-        kind = "port"
-        ix = ol.PortIndex(ol.F32, DIM, ol.COS, tier=ol.TIER_AVX512)
-        ix.add_many(rows, 1)
-        secs = ol.port().orc_index_time_topk(ix.h, ol._p(qs), qs.strides[0], nq, K, threads, None, None)
-    qps_sample = nq / secs
-    qps_full = qps_sample * sample_rows / N_ROWS
-    info = {"value": qps_full, "unit": "queries/s", "cores": threads, "kind": kind,
-            "sample": f"{nq} queries x {sample_rows} rows x {DIM} fp32 cosine, {threads} threads, one query per "
-                      f"thread (brute_force.h:243-291); QPS scaled x{sample_rows}/{N_ROWS} to 10M rows",
-            "sample_seconds": secs}
-    del ix
-    return qps_full, info
+    threads = usable_cores()
+    rows_total = args.rows if args.scaling == "strong" else args.rows * world
+    log = {}
+    t_all = time.perf_counter()
+    ix, kind = build_reference_index(ol, rows_total, threads, log)
+    qs_all = ol.synth_rows(ol.F32, SEED_QUERIES, 0, args.batch, DIM)
 
+    def run(nq_step, first):
+        qs = np.ascontiguousarray(qs_all[[(first + i) % args.batch for i in range(nq_step)]])
+        th = min(threads, nq_step)
+        if kind == "reference":
+            return ol.ref_vecsim().Ref_TimeTopK(ix.h, ol._p(qs), qs.strides[0], nq_step, K, th, None, None)
+        return ol.port().orc_index_time_topk(ix.h, ol._p(qs), qs.strides[0], nq_step, K, th, None, None)
 
-def run_reference_arm(args, rank):
-    if rank != 0:
-        return
-    threads = os.cpu_count() or 1
-    steps = []
-    info = None
-    total = args.warmup + args.steps
-    for i in range(total):
-        t0 = time.perf_counter()
-        qps, info = cpu_reference_qps(args.ref_sample_rows, 1, threads)
-        if i >= args.warmup:
-            steps.append((qps, time.perf_counter() - t0))
-        if time.perf_counter() - t0 > 120:
+    # a step = nq_step queries, one per host thread (brute_force.h:243-291 is one thread per query), sized from a
+    # calibration pass so that a step takes ~8 s; every step scans the full corpus
+    cal_n = min(threads, 16)
+    cal_s = run(cal_n, 0)
+    nq_step = int(max(4, min(4 * threads, round(cal_n / cal_s * 8.0))))
+    budget_s = 150.0
+    warm = max(1, min(args.warmup, 2))
+    for w in range(warm):
+        run(nq_step, w * nq_step)
+    times = []
+    for i in range(args.steps):
+        times.append(run(nq_step, (warm + i) * nq_step))
+        if sum(times) > budget_s:
             break
-    qps = statistics.mean(s[0] for s in steps)
+    secs = sum(times)
+    qps = nq_step * len(times) / secs
+    cfg = knn_config(args.rows, args.batch, K, world, args.scaling)
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-            "steps": len(steps), "warmup": args.warmup, "ms_per_step": 1000.0 * BATCH / qps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "FLAT 10M x 768 fp32 cosine k=10 batch=256 (reference CPU path, bounded sample)"},
-            "cpu_baseline": info,
+            "steps": len(times), "warmup": warm, "ms_per_step": 1000.0 * secs / len(times),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": min(threads, nq_step), "kind": kind,
+                             "sample": f"{len(times)} steps x {nq_step} queries over the FULL {rows_total} x {DIM} fp32 cosine corpus in the "
+                                       f"reference's BruteForceIndex (blockSize 65536), one query per thread, {min(threads, nq_step)} threads "
+                                       f"(usable cores: {threads}, os.cpu_count {os.cpu_count()}); a step is a bounded sample of the batch-{args.batch} workload",
+                             "sample_seconds": secs, "queries_per_step": nq_step, "index_build_seconds": log.get("build_seconds"),
+                             "wall_seconds": round(time.perf_counter() - t_all, 1)},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -169,359 +226,295 @@ def run_reference_arm(args, rank):
 # ------------------------------------------------------------------------------------------------
 # second half of the metric: BM25 intersect docs/sec (BASELINE.json configs[3])
 # ------------------------------------------------------------------------------------------------
-POSTING_QUERIES = [(1, 2, 3), (1, 10, 100), (2, 5, 9), (3, 30, 300), (1, 100, 10000), (10, 20, 30), (4, 8, 16), (50, 60, 70)]
+from bench_postings import bench_postings, cpu_postings_baseline  # noqa: E402
 
 
-def cpu_postings_baseline(n_docs, threads):
-    """3-term AND + BM25STD + top-10 on the host with our C restatement of the reference's Rust iterators
-    (kind "port": the reference's posting path cannot be built here — no Rust toolchain)."""
+# ------------------------------------------------------------------------------------------------
+# helpers of our arm
+# ------------------------------------------------------------------------------------------------
+class Env:
+    """torch / NCCL plumbing + the library handles for one rank."""
+
+    def __init__(self):
+        import torch
+
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        from redisearch_b200 import vecsim as vs
+        from redisearch_b200._lib import load_library
+
+        self.vs = vs
+        self.L = vs.lib()
+        S = load_library("libsynth_b200.so")
+        S.Synth_FillRows.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
+        S.Synth_NormalizeRowsF32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_void_p]
+        self.S = S
+        # an explicit stream: a NULL handle would mean CUDA's legacy default stream
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.stream)
+        self.sp = C.c_void_p(self.stream.cuda_stream)
+        self.group = None
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def shard_group(self):
+        """The library's own NCCL communicator: rank 0 draws the id, torch.distributed (plumbing) ships the 128 bytes."""
+        if self.group is None:
+            import numpy as np
+
+            idbuf = np.zeros(128, dtype=np.uint8)
+            if self.world > 1:
+                if self.rank == 0:
+                    assert self.L.VecSimB200_ShardGroup_UniqueId(idbuf.ctypes.data) == 0, "cannot load NCCL"
+                t = self.torch.from_numpy(idbuf).to(self.dev)
+                self.dist.broadcast(t, 0)
+                idbuf = t.cpu().numpy()
+            self.group = self.L.VecSimB200_ShardGroup_New(idbuf.ctypes.data, self.rank, self.world)
+            assert self.group, "VecSimB200_ShardGroup_New failed"
+        return self.group
+
+    def close(self):
+        if self.group:
+            self.L.VecSimB200_ShardGroup_Free(self.group)
+            self.group = None
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def build_shard(env, vtype, metric, rows, row0_global, dim=DIM, normalize=True):
+    """Generate + (cosine fp32) normalise on device, ingest device-to-device.  Labels = global row + 1."""
+    vs, L, S, torch = env.vs, env.L, env.S, env.torch
+    index = vs.VecSimIndex(vtype, dim, metric)
+    assert L.VecSimB200_Reserve(index.h, rows) == 0, "cannot reserve HBM for the corpus"
+    es = {vs.VecSimType_FLOAT32: 4, vs.VecSimType_FLOAT16: 2, vs.VecSimType_BFLOAT16: 2}[vtype]
+    tdt = {4: torch.float32, 2: torch.float16}[es]
+    chunk = min(rows, 1_000_000)
+    buf = torch.empty((chunk, dim), dtype=tdt, device=env.dev)
+    t0 = time.perf_counter()
+    done = 0
+    while done < rows:
+        n = min(chunk, rows - done)
+        assert S.Synth_FillRows(buf.data_ptr(), dim * es, vtype, SEED_ROWS, row0_global + done, n, dim, env.sp) == 0
+        if normalize and vtype == vs.VecSimType_FLOAT32 and metric == vs.VecSimMetric_Cosine:
+            assert S.Synth_NormalizeRowsF32(buf.data_ptr(), dim * 4, n, dim, env.sp) == 0
+        torch.cuda.synchronize()
+        assert L.VecSimB200_AddVectorsDevice(index.h, buf.data_ptr(), n, row0_global + done + 1) == n
+        done += n
+    del buf
+    return index, time.perf_counter() - t0
+
+
+def reference_scan_of_device_rows(env, index, rows, row0_global, q_stored, k, vtype_code, metric_code, threads):
+    """The parity checker at full size: copy this rank's stored rows back from HBM 500K at a time and feed them to the
+    reference's own distance kernels + heap (tests/oracle_lib.StreamingTopK -> oracle/_ref Ref_ScanTopKChunk).  Returns
+    (checker, cpu seconds spent in the scan, checker kind)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
 
     import oracle_lib as ol
 
-    L = ol.postings()
-    doc_len = np.zeros(n_docs + 1, dtype=np.uint32)
-    # doc lengths via the same hash (vectorised replica of orc_synth_doclen is not needed for timing: constant cost)
-    doc_len[1:] = 50 + (np.arange(1, n_docs + 1, dtype=np.uint64) * np.uint64(2654435761) % np.uint64(451)).astype(np.uint32)
-    reps = max(1, threads // len(POSTING_QUERIES))
-    terms, keep, postings = [], [], 0
-    for q in POSTING_QUERIES:
-        trio = []
-        for r in q:
-            ix = ol.InvIndex(ol.CODEC_FREQS_ONLY)
-            postings += L.orc_ii_fill_synth(ix.h, n_docs, r)
-            trio.append(ix)
-        keep.append(trio)
-    for _ in range(reps):
-        for trio in keep:
-            terms += [ix.h for ix in trio]
-    nq = len(terms) // 3
-    arr = (C.c_void_p * len(terms))(*terms)
-    ids = np.zeros(nq * 10, dtype=np.uint64)
-    sc = np.zeros(nq * 10, dtype=np.float64)
-    hits = np.zeros(nq, dtype=np.uint64)
-    secs = L.orc_time_search3(arr, nq, ol._p(doc_len), n_docs, float(doc_len[1:].mean()), 10, min(threads, nq), ol._p(ids), ol._p(sc), ol._p(hits))
-    total = postings * reps
-    return {"value": total / secs, "unit": "postings/s", "cores": min(threads, nq), "kind": "port",
-            "sample": f"{nq} queries (the {len(POSTING_QUERIES)} rank triples x {reps}) over a {n_docs}-doc synthetic Zipf index, FreqsOnly blocks, "
-                      f"reader+Intersection::read+BM25STD+top-10 per query, one query per thread; {total} input postings",
-            "sample_seconds": secs}
-
-
-def bench_postings(torch, dev, stream_ptr, n_docs, steps):
-    import numpy as np
-
-    from redisearch_b200 import postings as ps
-    from redisearch_b200._lib import load_library
-
-    S = load_library("libsynth_b200.so")
-    S.Synth_DocFreq.restype = C.c_uint64
-    S.Synth_DocFreq.argtypes = [C.c_uint64, C.c_uint64]
-    S.Synth_Postings.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    S.Synth_DocLens.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p]
-    S.Synth_EncodeFreqsOnlyBlocks.restype = C.c_size_t
-    S.Synth_EncodeFreqsOnlyBlocks.argtypes = [C.c_void_p] * 8 + [C.POINTER(C.c_size_t)]
-    L = ps.lib()
-    chunks = (n_docs + 1023) // 1024
-    scratch = torch.empty(2 * chunks + 16, dtype=torch.int32, device=dev)
-    d_total = torch.zeros(4, dtype=torch.int32, device=dev)
-    h_count = np.zeros(4, dtype=np.uint32)
-    d_len = torch.empty(n_docs + 1, dtype=torch.int32, device=dev)
-    assert S.Synth_DocLens(n_docs, d_len.data_ptr(), stream_ptr) == 0
-    torch.cuda.synchronize()
-    avg_len = float(d_len[1:].double().mean().item())
-    dt = L.II_DocTable_FromDevice(n_docs, d_len.data_ptr(), None, None)
-    assert dt
-    ranks = sorted({r for q in POSTING_QUERIES for r in q})
-    lists, host_lists = {}, {}
-    for r in ranks:
-        cap = int(S.Synth_DocFreq(n_docs, r) * 1.2) + 4096
-        ids = torch.empty(cap, dtype=torch.int32, device=dev)
-        fr = torch.empty(cap, dtype=torch.int32, device=dev)
-        assert S.Synth_Postings(n_docs, r, ids.data_ptr(), fr.data_ptr(), scratch.data_ptr(), d_total.data_ptr(), h_count.ctypes.data, stream_ptr) == 0
-        n = int(h_count[0])
-        lists[r] = L.II_PostingList_FromDevice(ids.data_ptr(), fr.data_ptr(), n)
-        host_lists[r] = (ids[:n].cpu().numpy().view(np.uint32).copy(), fr[:n].cpu().numpy().view(np.uint32).copy())
-        assert lists[r]
-    st = ps.II_IndexStats(n_docs, 0, avg_len)
-
-    def run_query(q, handles):
-        arr = (C.c_void_p * 3)(*handles)
-        terms = (ps.II_TermParams * 3)(*[ps.II_TermParams(1.0, L.II_CalculateIDF(n_docs, len(host_lists[r][0])),
-                                                          L.II_CalculateIDF_BM25(n_docs, len(host_lists[r][0]))) for r in q])
-        ids = np.zeros(10, dtype=np.uint64)
-        sc = np.zeros(10, dtype=np.float64)
-        tot = C.c_size_t(0)
-        got = L.II_SearchTopN(arr, 3, 0, ps.SCORER_BM25STD, terms, 1.0, C.byref(st), dt, 10, ids.ctypes.data, sc.ctypes.data, C.byref(tot))
-        return ids[:got].copy(), sc[:got].copy(), tot.value
-
-    in_postings = sum(len(host_lists[r][0]) for q in POSTING_QUERIES for r in q)
-    for q in POSTING_QUERIES:  # warm-up
-        run_query(q, [lists[r] for r in q])
-    ps.stats(reset=True)
-    dev_us, hits, results = 0.0, 0, {}
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        for q in POSTING_QUERIES:
-            results[q] = run_query(q, [lists[r] for r in q])
-            s_ = ps.stats(reset=False)
-            dev_us += s_.intersect_device_us + s_.score_device_us
-    torch.cuda.synchronize()
-    wall_seq = (time.perf_counter() - t0) / steps
-    launches = ps.stats(reset=True).kernel_launches
-    hits = sum(results[q][2] for q in POSTING_QUERIES)
-    dev_s = dev_us * 1e-6 / steps
-    # the same query set through the batch entry point: the 8 searches are spread over a pool of streams inside
-    # the library (what a dispatch shim does with concurrent FT.SEARCHes)
-    def term_params(q):
-        return [(1.0, L.II_CalculateIDF(n_docs, len(host_lists[r][0])), L.II_CalculateIDF_BM25(n_docs, len(host_lists[r][0]))) for r in q]
-
-    class _H:  # SearchBatch wants objects with a .h handle
-        def __init__(self, h):
-            self.h = h
-
-    batch = ps.SearchBatch([([_H(lists[r]) for r in q], term_params(q)) for q in POSTING_QUERIES], 10)
-    for _ in range(3):
-        conc = batch.run(False, ps.SCORER_BM25STD, 1.0, n_docs, avg_len, dt)
-    reps = max(steps, 5) * 4
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        conc = batch.run(False, ps.SCORER_BM25STD, 1.0, n_docs, avg_len, dt)
-    wall = (time.perf_counter() - t0) / reps
-    for q, r_ in zip(POSTING_QUERIES, conc):
-        assert r_[0].tolist() == results[q][0].tolist() and r_[2] == results[q][2]
-    # e2e: encoded IndexBlocks on the host -> decode (all cores) -> H2D -> AND + BM25STD + top-10 -> host
-    enc = {}
-    for r in ranks:
-        ids, fr = host_lists[r]
-        n = len(ids)
-        nb = n // 100 + 2
-        out = np.zeros(n * 9 + 64, dtype=np.uint8)
-        first, last = np.zeros(nb, dtype=np.uint64), np.zeros(nb, dtype=np.uint64)
-        bn, off = np.zeros(nb, dtype=np.uint16), np.zeros(nb + 1, dtype=np.uint64)
-        nblocks = C.c_size_t(0)
-        S.Synth_EncodeFreqsOnlyBlocks(ids.ctypes.data, fr.ctypes.data, n, out.ctypes.data, first.ctypes.data, last.ctypes.data,
-                                      bn.ctypes.data, off.ctypes.data, C.byref(nblocks))
-        views = (ps.II_BlockView * nblocks.value)()
-        base = out.ctypes.data
-        for b in range(nblocks.value):
-            views[b] = ps.II_BlockView(int(first[b]), int(last[b]), int(bn[b]), C.cast(base + int(off[b]), C.POINTER(C.c_uint8)), int(off[b + 1] - off[b]))
-        enc[r] = (views, nblocks.value, out, int(off[nblocks.value]))
-    enc_bytes = sum(enc[r][3] for q in POSTING_QUERIES for r in q)
-    def e2e_pass(on_device):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        dec_us = 0.0
-        for q in POSTING_QUERIES:
-            hs = []
-            for r in q:
-                h = L.II_PostingList_FromBlocks(enc[r][0], enc[r][1], ps.CODEC_FREQS_ONLY, 0, on_device)
-                dec_us += ps.stats(reset=False).decode_host_us
-                hs.append(h)
-            e_ids, e_sc, _ = run_query(q, hs)
-            assert e_ids.tolist() == results[q][0].tolist()
-            for h in hs:
-                L.II_PostingList_Free(h)
-        return time.perf_counter() - t0, dec_us
-
-    e2e_pass(1)  # warm the pinned staging
-    e2e_wall, decode_us = e2e_pass(1)
-    e2e_wall_host, decode_us_host = e2e_pass(0)
-    alg_bytes = in_postings * 8 + hits * 16
-    peak, _ = load_peaks()
-    for h in lists.values():
-        L.II_PostingList_Free(h)
-    L.II_DocTable_Free(dt)
-    return {
-        "metric": "BM25 intersect docs/sec", "value": in_postings / wall, "unit": "input postings/s",
-        "matched_docs_per_s": hits / wall, "ms_per_query_set": wall * 1000.0, "gpu_launches": int(launches),
-        "api": "II_SearchTopNBatch (8 queries per call, pool of 8 streams)",
-        "sequential": {"value": in_postings / wall_seq, "ms_per_query_set": wall_seq * 1000.0,
-                       "note": "II_SearchTopN, one query at a time"},
-        "config": {"workload": f"3-term AND + BM25STD + top-10 over a {n_docs}-doc synthetic Zipf index, {len(POSTING_QUERIES)} queries "
-                               f"(rank triples {POSTING_QUERIES}), postings resident in HBM, one II_SearchTopNBatch call per set", "input_postings": in_postings,
-                   "matched_docs": hits},
-        "e2e": {"value": in_postings / e2e_wall, "unit": "input postings/s", "h2d_bytes_per_step": in_postings * 8,
-                "d2h_bytes_per_step": len(POSTING_QUERIES) * 10 * 16, "encoded_bytes": enc_bytes,
-                "host_gather_ms": decode_us / 1000.0, "ms_per_query_set": e2e_wall * 1000.0,
-                "note": "FreqsOnly IndexBlocks on the host -> II_PostingList_FromBlocks (gather to pinned, H2D of the encoded bytes, "
-                        "decode_blocks_kernel) -> II_SearchTopN, one query at a time",
-                "host_decode_variant": {"value": in_postings / e2e_wall_host, "ms_per_query_set": e2e_wall_host * 1000.0,
-                                        "host_decode_ms": decode_us_host / 1000.0}},
-        "roofline": {"bound": "hbm", "achieved": alg_bytes / dev_s / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": alg_bytes / dev_s / 1e9 / peak, "traffic": None, "kernel": "intersect_kernel + gather_kernel + score_kernel",
-                     "device_ms_per_query_set": dev_s * 1000.0, "algorithmic_bytes": alg_bytes},
-    }
-
-
-# ------------------------------------------------------------------------------------------------
-# our arm
-# ------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows", type=int, default=N_ROWS, help="rows per GPU (default = the BASELINE workload)")
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--ref-sample-rows", type=int, default=1_000_000)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-postings", action="store_true")
-    ap.add_argument("--posting-docs", type=int, default=50_000_000)
-    args = ap.parse_args()
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-
-    if args.impl == "reference":
-        run_reference_arm(args, rank)
-        return
-
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    from redisearch_b200 import vecsim as vs
-    from redisearch_b200._lib import load_library
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    warmup = max(3, args.warmup)
-    rows, nq = args.rows, args.batch
-
-    L = vs.lib()
-    S = load_library("libsynth_b200.so")
-    S.Synth_FillRows.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
-    S.Synth_NormalizeRowsF32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_void_p]
-    # an explicit stream: a NULL handle would mean CUDA's legacy default stream
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    sp = C.c_void_p(stream.cuda_stream)
-    assert sp.value
-
-    # ---- build the shard in HBM: generate + normalise on device, ingest device-to-device
-    index = vs.VecSimIndex(vs.VecSimType_FLOAT32, DIM, vs.VecSimMetric_Cosine)
-    assert L.VecSimB200_Reserve(index.h, rows) == 0, "cannot reserve HBM for the corpus"
-    chunk = min(rows, 1_000_000)
-    buf = torch.empty((chunk, DIM), dtype=torch.float32, device=dev)
-    row0_global = rank * rows
-    t_build = time.perf_counter()
-    done = 0
+    st = ol.StreamingTopK(vtype_code, metric_code, DIM, q_stored, k, threads)
+    es = q_stored.dtype.itemsize
+    chunk = 500_000
+    host = np.empty((chunk, DIM), dtype=q_stored.dtype)
+    secs, done = 0.0, 0
     while done < rows:
         n = min(chunk, rows - done)
-        assert S.Synth_FillRows(buf.data_ptr(), DIM * 4, 0, SEED_ROWS, row0_global + done, n, DIM, sp) == 0
-        assert S.Synth_NormalizeRowsF32(buf.data_ptr(), DIM * 4, n, DIM, sp) == 0
-        torch.cuda.synchronize()
-        assert L.VecSimB200_AddVectorsDevice(index.h, buf.data_ptr(), n, row0_global + done + 1) == n
+        assert env.L.VecSimB200_ReadRows(index.h, done, n, host.ctypes.data) == 0
+        t0 = time.perf_counter()
+        st.feed(host[:n], row0_global + done + 1)
+        secs += time.perf_counter() - t0
         done += n
-    del buf
-    build_s = time.perf_counter() - t_build
+    assert es * DIM == host.strides[0]
+    return st, secs, st.kind
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm, config 2 (default): FLAT 10M x 768 fp32 cosine k=10 batch=256
+# ------------------------------------------------------------------------------------------------
+def run_knn(args):
+    import numpy as np
+
+    env = Env()
+    torch, L, vs, S = env.torch, env.L, env.vs, env.S
+    rank, world, dev, sp = env.rank, env.world, env.dev, env.sp
+    warmup = max(3, args.warmup)
+    nq = args.batch
+    if args.scaling == "strong":
+        lo = (args.rows * rank) // world
+        hi = (args.rows * (rank + 1)) // world
+        rows, row0 = hi - lo, lo
+        corpus_rows = args.rows
+    else:
+        rows, row0 = args.rows, rank * args.rows
+        corpus_rows = args.rows * world
+    index, build_s = build_shard(env, vs.VecSimType_FLOAT32, vs.VecSimMetric_Cosine, rows, row0)
+    group = env.shard_group()
 
     # ---- queries: same generator, normalised like VecSimIndex_TopKQuery would (preprocessors.h:121-131)
     qdev = torch.empty((nq, DIM), dtype=torch.float32, device=dev)
     assert S.Synth_FillRows(qdev.data_ptr(), DIM * 4, 0, SEED_QUERIES, 0, nq, DIM, sp) == 0
     q_host_raw = qdev.cpu().numpy().copy()  # raw (un-normalised) host blobs for the e2e arm
     assert S.Synth_NormalizeRowsF32(qdev.data_ptr(), DIM * 4, nq, DIM, sp) == 0
+    torch.cuda.synchronize()
+    q_stored = qdev.cpu().numpy().copy()
     out_labels = torch.empty((nq, K), dtype=torch.int64, device=dev)
     out_scores = torch.empty((nq, K), dtype=torch.float32, device=dev)
-    if world > 1:
-        gath_s = torch.empty((world, nq, K), dtype=torch.float32, device=dev)
-        gath_l = torch.empty((world, nq, K), dtype=torch.int64, device=dev)
-        fin_s = torch.empty((nq, K), dtype=torch.float32, device=dev)
-        fin_l = torch.empty((nq, K), dtype=torch.int64, device=dev)
 
-    def step_device():
-        rc = L.VecSimB200_TopKQueryBatchDevice(index.h, qdev.data_ptr(), nq, K, out_labels.data_ptr(),
-                                               out_scores.data_ptr(), sp)
-        assert rc == 0
-        if world > 1:  # the one exchange step: per-shard top-k -> all ranks -> G-way merge on device
-            dist.all_gather_into_tensor(gath_s, out_scores)
-            dist.all_gather_into_tensor(gath_l, out_labels)
-            assert L.VecSimB200_MergeShardTopK(gath_s.data_ptr(), gath_l.data_ptr(), world, nq, K, fin_s.data_ptr(),
-                                               fin_l.data_ptr(), sp) == 0
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def step_device():  # world > 1: local scan -> ONE all-gather of the packed per-shard top-k -> device merge, inside the library
+        assert L.VecSimB200_ShardGroup_TopKBatchDevice(group, index.h, qdev.data_ptr(), nq, K, out_labels.data_ptr(),
+                                                       out_scores.data_ptr(), sp) == 0
 
     for _ in range(warmup):
         step_device()
-    barrier()
+    env.barrier()
     index.stats(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        ev0.record(stream)
+    with ClockSampler(env.local_rank) as clocks:
+        env.barrier()
+        ev0.record(env.stream)
         for _ in range(args.steps):
             step_device()
-        ev1.record(stream)
-        barrier()
-    ms_total = ev0.elapsed_time(ev1)
+        ev1.record(env.stream)
+        env.barrier()
     st = index.stats(reset=True)
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * nq / (ms_step / 1000.0)
+    ms_step = env.max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    value = nq / (ms_step / 1000.0)  # true QPS: every step answers nq queries over the whole corpus
 
-    # ---- e2e through the host-facing C-ABI: host blobs in, host results out
+    # ---- sustained: the same loop for >= 3 s (the short timed region above is a burst; the pass draws ~1 kW)
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_long = max(args.steps, int(args.sustained_seconds * 1000.0 / ms_step))
+        with ClockSampler(env.local_rank) as clocks_long:
+            env.barrier()
+            ev0.record(env.stream)
+            for _ in range(n_long):
+                step_device()
+            ev1.record(env.stream)
+            env.barrier()
+        ms_long = env.max_over_ranks(ev0.elapsed_time(ev1)) / n_long
+        sustained = {"steps": n_long, "ms_per_step": ms_long, "value": nq / (ms_long / 1000.0), "clocks": clocks_long.summary()}
+        index.stats(reset=True)
+
+    # ---- e2e through the host-facing C-ABI: host blobs in, host results out (all ranks: it is a collective)
     h_labels = np.empty((nq, K), dtype=np.uint64)
     h_scores = np.empty((nq, K), dtype=np.float64)
     qh = np.ascontiguousarray(q_host_raw)
-    for _ in range(2):
-        assert L.VecSimB200_TopKQueryBatch(index.h, qh.ctypes.data, qh.strides[0], nq, K, None, h_labels.ctypes.data,
-                                           h_scores.ctypes.data) == 0
-    e2e_steps = max(3, min(args.steps, 10))
-    barrier()
+
+    def step_e2e():
+        if world == 1:
+            assert L.VecSimB200_TopKQueryBatch(index.h, qh.ctypes.data, qh.strides[0], nq, K, None, h_labels.ctypes.data, h_scores.ctypes.data) == 0
+        else:
+            assert L.VecSimB200_ShardGroup_TopKBatch(group, index.h, qh.ctypes.data, qh.strides[0], nq, K, h_labels.ctypes.data,
+                                                     h_scores.ctypes.data) == 0
+
+    for _ in range(3):
+        step_e2e()
+    e2e_steps = max(3, min(args.steps, 20))
+    env.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        assert L.VecSimB200_TopKQueryBatch(index.h, qh.ctypes.data, qh.strides[0], nq, K, None, h_labels.ctypes.data,
-                                           h_scores.ctypes.data) == 0
+        step_e2e()
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * nq / e2e_s
-    # host-path and device-path answers must agree (same kernels)
-    dl = out_labels.cpu().numpy()
+    e2e_s = env.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e_value = nq / e2e_s
+    dl, ds = out_labels.cpu().numpy(), out_scores.cpu().numpy()
     agree = bool((dl == h_labels.astype(np.int64)).all())
 
-    # ---- B=1 through the stock VecSimIndex_TopKQuery (what hybrid_reader.c:374 calls).  Two legs: as served (the fp16
-    # shadow built by the batches above is current, so a single query rides the tensor-core route too) and the exact
-    # HBM-bound scan alone (coarse mode off) — the north_star's ">= 10x CPU at >= 70% of HBM roofline" figure
-    def single_query_leg():
-        index.stats(reset=True)
-        q1 = np.ascontiguousarray(q_host_raw[0])
-        for _ in range(3):
-            index.topk(q1, K)
-        index.stats(reset=True)
-        n1 = 20
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(n1):
-            index.topk(np.ascontiguousarray(q_host_raw[i % nq]), K)
-        dt = (time.perf_counter() - t0) / n1
-        st1 = index.stats(reset=True)
-        return dt, st1.scan_device_us / max(1, st1.scan_launches), int(L.VecSimB200_LastBatchPath(index.h))
+    # ---- proof statistics of the last device batch (tier 1 = sample pass + fixed bound, tier 2 = lists of 128, 0 = exact scan)
+    step_device()
+    torch.cuda.synchronize()
+    flags = np.zeros(nq, dtype=np.uint32)
+    tiers = None
+    if world == 1 and L.VecSimB200_LastCoarseFlags(index.h, flags.ctypes.data, nq) == 0:
+        tiers = {"tier1": int((flags == 1).sum()), "tier2": int((flags == 2).sum()), "exact_scan": int((flags == 0).sum())}
 
-    b1s_s, b1s_scan_us, b1s_path = single_query_leg()
-    L.VecSimB200_SetCoarseMode(0)
-    b1_s, b1_scan_us, _ = single_query_leg()
-    L.VecSimB200_SetCoarseMode(-1)
-    b1_bytes = rows * DIM * 4 + DIM * 4 + K * 12
+    # ---- parity at the quoted size + the CPU baseline: the reference's distance kernels + heap over the device's rows
+    parity, cpu_base = None, None
+    if not args.no_parity:
+        threads = usable_cores()
+        n_check = max(16, min(threads, 64, nq)) if world == 1 else 16
+        pick = [(i * nq) // n_check for i in range(n_check)]
+        chk, scan_s, chk_kind = reference_scan_of_device_rows(env, index, rows, row0, np.ascontiguousarray(q_stored[pick]), K, 0, 2, threads)
+        local = [chk.result(i) for i in range(n_check)]
+        if world > 1:  # merge the per-shard reference answers by (score, label) like the coordinator
+            gathered = [None] * world
+            env.dist.all_gather_object(gathered, local)
+            local = []
+            for i in range(n_check):
+                ids = np.concatenate([g[i][0] for g in gathered])
+                sc = np.concatenate([g[i][1] for g in gathered])
+                order = np.lexsort((ids, sc))[:K]
+                local.append((ids[order], sc[order]))
+        ids_equal = all(dl[q].tolist() == local[i][0].tolist() for i, q in enumerate(pick))
+        bits_equal = all(ds[q].tobytes() == local[i][1].astype(np.float32).tobytes() for i, q in enumerate(pick))
+        parity = {"queries": n_check, "ids_equal": bool(ids_equal), "score_bits_equal": bool(bits_equal), "rows": corpus_rows,
+                  "checker": f"{chk_kind}: the reference's dispatched distance kernel + its heap (oracle/_ref Ref_ScanTopKChunk) over the "
+                             f"device's own stored rows copied back from HBM" + ("; per-shard answers merged by (score, label)" if world > 1 else ""),
+                  "proven_by_tier": tiers}
+        if world == 1:
+            cpu_base = {"value": n_check / scan_s, "unit": "queries/s", "cores": min(threads, n_check), "kind": chk_kind,
+                        "sample": f"{n_check} of the {nq} queries, one per host thread, each scanning the FULL {rows} x {DIM} fp32 corpus with the "
+                                  f"reference's distance kernel + heap (the loop of brute_force.h:262-281 over flat 500K-row chunks); "
+                                  f"usable cores {threads}",
+                        "sample_seconds": scan_s}
+
+    # ---- B=1 through the stock VecSimIndex_TopKQuery (what hybrid_reader.c:374 calls), N = 1 only.  Two legs: as served
+    # (the fp16 shadow built by the batches above is current, so a single query rides the tensor-core route too) and the
+    # exact HBM-bound scan alone (coarse mode off) — the north_star's ">= 10x CPU at >= 70% of HBM roofline" figure
+    single = {}
+    if world == 1:
+        def single_query_leg():
+            index.stats(reset=True)
+            q1 = np.ascontiguousarray(q_host_raw[0])
+            for _ in range(3):
+                index.topk(q1, K)
+            index.stats(reset=True)
+            n1 = 20
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(n1):
+                index.topk(np.ascontiguousarray(q_host_raw[i % nq]), K)
+            dt = (time.perf_counter() - t0) / n1
+            st1 = index.stats(reset=True)
+            return dt, st1.scan_device_us / max(1, st1.scan_launches), int(L.VecSimB200_LastBatchPath(index.h))
+
+        b1s_s, b1s_scan_us, b1s_path = single_query_leg()
+        L.VecSimB200_SetCoarseMode(0)
+        b1_s, b1_scan_us, _ = single_query_leg()
+        L.VecSimB200_SetCoarseMode(-1)
+        b1_bytes = rows * DIM * 4 + DIM * 4 + K * 12
+        peak, _ = load_peaks()
+        single = {"single_query_as_served": {"api": "VecSimIndex_TopKQuery with the fp16 shadow current", "value": 1.0 / b1s_s,
+                                             "unit": "queries/s", "ms_per_query": b1s_s * 1000.0, "route": b1s_path,
+                                             "dominant_kernel_us": b1s_scan_us},
+                  "single_query": {"api": "VecSimIndex_TopKQuery (host blob in, reply out), exact scan only", "value": 1.0 / b1_s,
+                                   "unit": "queries/s", "ms_per_query": b1_s * 1000.0,
+                                   "roofline": {"bound": "hbm", "achieved": b1_bytes / (b1_scan_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                                                "frac": b1_bytes / (b1_scan_us * 1e-6) / 1e9 / peak, "kernel": "scan_topk_kernel<f32,IP,4,1>",
+                                                "avg_launch_us": b1_scan_us, "algorithmic_bytes_per_launch": b1_bytes}}}
 
     # ---- roofline of the dominant kernel: the library brackets it with CUDA events on the launch stream
     # (VecSimB200_GetStats); one launch per synchronised call so that every interval is one kernel
@@ -537,11 +530,11 @@ def main():
     scan_us = float(np.mean(per_launch)) if per_launch else None
     coarse_mode = int(os.environ.get("VECSIM_B200_COARSE", "1"))
     dom_kernel = {0: "scan_topk_kernel<f32,IP,4,8>",
-                  1: "coarse_qtmem_kernel (tcgen05 kind::f16 TS-mode, queries in TMEM, fp16 shadow rows)",
+                  1: "coarse_qtmem_kernel<fixed bound> (tcgen05 kind::f16 TS-mode, queries in TMEM, fp16 shadow rows; main pass)",
                   2: "coarse_kernel<CfgTF32> (tcgen05 kind::tf32)"}.get(coarse_mode, "?")
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             t = json.load(f).get(dom_kernel.split(" ")[0].split("<")[0])
         if t and (t["rows"], t["dim"], t["batch"]) == (rows, DIM, nq):
             traffic = t["dram_bytes_per_launch"]
@@ -550,7 +543,6 @@ def main():
     alg_bytes = rows * DIM * 4 + nq * DIM * 4 + nq * K * 12  # N*D*s per corpus pass
     read_bytes = rows * DIM * (2 if coarse_mode == 1 else 4)   # what this kernel has to pull from HBM once
     achieved = alg_bytes / (scan_us * 1e-6) / 1e9 if scan_us else None
-
     hbm_view = {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "hbm_bytes_read_per_launch": read_bytes,
                 "frac_on_bytes_read": (read_bytes / (scan_us * 1e-6) / 1e9 / peak) if scan_us else None}
@@ -566,55 +558,187 @@ def main():
         roofline = dict(common, bound="tensor", achieved=tf, peak=tpeak, unit="TFLOP/s", frac=tf / tpeak,
                         flops_per_launch=flops, peak_source=tsrc + " — burst dense bf16 (cuBLAS), kernel timed alone",
                         peak_sustained=tsust, hbm=dict(hbm_view, peak_source=peak_src),
-                        note="sustained runs sit at the 1000 W board power cap (clocks.reasons)")
+                        note="per GPU; long runs sit at the 1000 W board power cap (see `sustained`)")
     else:
         roofline = dict(common, bound="hbm", peak_source=peak_src, **hbm_view)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"FLAT {rows} x {DIM} fp32 cosine k={K} batch={nq} per GPU"
-                                   + (f"; corpus = {world} shards, NCCL all-gather of per-shard top-k + device merge" if world > 1 else ""),
-                       "rows_per_gpu": rows, "dim": DIM, "k": K, "batch": nq,
-                       "l2_policy": "corpus (30.7 GB) >> 126 MB L2, no flush needed",
-                       "value_unit_note": "queries x 10M-row shards per second" if world > 1 else "queries per second",
-                       "build_seconds": round(build_s, 2), "host_device_results_agree": agree},
+            "config": knn_config(args.rows, nq, K, world, args.scaling),
+            "run_info": {"build_seconds": round(build_s, 2), "host_device_results_agree": agree,
+                         "exchange": None if world == 1 else "VecSimB200_ShardGroup (library-owned NCCL communicator): one ncclAllGather of "
+                                                             f"{L.VecSimB200_ShardBlockBytes(nq, K)} B per rank + merge_shards_kernel"},
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(nq * DIM * 4),
-                    "d2h_bytes_per_step": int(nq * K * 8), "ms_per_step": e2e_s * 1000.0},
+                    "d2h_bytes_per_step": int(nq * K * 12), "ms_per_step": e2e_s * 1000.0,
+                    "api": "VecSimB200_TopKQueryBatch" if world == 1 else "VecSimB200_ShardGroup_TopKBatch (includes the all-gather and the merge)"},
             "gpu_launches": int(st.kernel_launches),
             "roofline": roofline,
             "clocks": clocks.summary(),
-            "single_query_as_served": {"api": "VecSimIndex_TopKQuery with the fp16 shadow current", "value": 1.0 / b1s_s,
-                                       "unit": "queries/s", "ms_per_query": b1s_s * 1000.0, "route": b1s_path,
-                                       "dominant_kernel_us": b1s_scan_us},
-            "single_query": {"api": "VecSimIndex_TopKQuery (host blob in, reply out), exact scan only", "value": 1.0 / b1_s,
-                             "unit": "queries/s", "ms_per_query": b1_s * 1000.0,
-                             "roofline": {"bound": "hbm", "achieved": b1_bytes / (b1_scan_us * 1e-6) / 1e9,
-                                          "peak": peak, "unit": "GB/s",
-                                          "frac": b1_bytes / (b1_scan_us * 1e-6) / 1e9 / peak,
-                                          "kernel": "scan_topk_kernel<f32,IP,4,1>", "avg_launch_us": b1_scan_us,
-                                          "algorithmic_bytes_per_launch": b1_bytes}},
+            "sustained": sustained,
+            "parity_at_config": parity,
         }
+        if args.scaling == "weak" and world > 1:
+            line["shard_query_rate"] = {"value": world * value, "unit": "queries x 10M-row shards / s"}
+        line.update(single)
         if world == 1 and not args.no_postings:
             del index
             torch.cuda.empty_cache()
             try:
-                line["bm25_intersect"] = bench_postings(torch, dev, sp, args.posting_docs, max(1, min(args.steps, 5)))
+                line["bm25_intersect"] = bench_postings(torch, dev, sp, args.posting_docs, max(1, min(args.steps, 5)), load_peaks()[0],
+                                                        check=not args.no_parity)
             except Exception as e:
                 line["bm25_intersect"] = {"value": None, "error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_base if cpu_base else {"value": None, "error": "parity scan skipped (--no-parity)"}
             try:
-                _, info = cpu_reference_qps(args.ref_sample_rows, 2, os.cpu_count() or 1)
-                line["cpu_baseline"] = info
                 if isinstance(line.get("bm25_intersect"), dict) and line["bm25_intersect"].get("value"):
-                    line["bm25_intersect"]["cpu_baseline"] = cpu_postings_baseline(10_000_000, os.cpu_count() or 1)
+                    line["bm25_intersect"]["cpu_baseline"] = cpu_postings_baseline(args.posting_docs, usable_cores())
             except Exception as e:  # the baseline is a reported side number; never fail the bench on it
-                line["cpu_baseline"] = {"value": None, "error": repr(e)}
+                line["bm25_intersect"]["cpu_baseline"] = {"value": None, "error": repr(e)}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    env.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# config 3: FLAT 50M x 768 fp16, IP, k=100, batch=1024, row-sharded over the GPUs (BASELINE configs[2])
+# ------------------------------------------------------------------------------------------------
+def run_config3(args):
+    import numpy as np
+
+    env = Env()
+    torch, L, vs, S = env.torch, env.L, env.vs, env.S
+    rank, world, dev, sp = env.rank, env.world, env.dev, env.sp
+    total, k, nq = args.rows3, 100, 1024
+    lo, hi = (total * rank) // world, (total * (rank + 1)) // world
+    rows = hi - lo
+    index, build_s = build_shard(env, vs.VecSimType_FLOAT16, vs.VecSimMetric_IP, rows, lo)
+    group = env.shard_group()
+    qdev = torch.empty((nq, DIM), dtype=torch.float16, device=dev)
+    assert S.Synth_FillRows(qdev.data_ptr(), DIM * 2, vs.VecSimType_FLOAT16, SEED_QUERIES, 0, nq, DIM, sp) == 0
+    torch.cuda.synchronize()
+    q_host = qdev.cpu().numpy().copy()
+    out_labels = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+
+    def step_device():
+        assert L.VecSimB200_ShardGroup_TopKBatchDevice(group, index.h, qdev.data_ptr(), nq, k, out_labels.data_ptr(), out_scores.data_ptr(), sp) == 0
+
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
+        step_device()
+    env.barrier()
+    assert L.VecSimB200_LastBatchPath(index.h) == 2, "the batch did not take the tensor-core direct route"
+    index.stats(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(env.local_rank) as clocks:
+        env.barrier()
+        ev0.record(env.stream)
+        for _ in range(args.steps):
+            step_device()
+        ev1.record(env.stream)
+        env.barrier()
+    st = index.stats(reset=True)
+    ms_step = env.max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    scan_us = st.scan_device_us / max(1, st.scan_launches)
+    h_labels = np.empty((nq, k), dtype=np.uint64)
+    h_scores = np.empty((nq, k), dtype=np.float64)
+    for _ in range(2):
+        assert L.VecSimB200_ShardGroup_TopKBatch(group, index.h, q_host.ctypes.data, q_host.strides[0], nq, k, h_labels.ctypes.data, h_scores.ctypes.data) == 0
+    e2e_steps = max(3, min(args.steps, 10))
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        assert L.VecSimB200_ShardGroup_TopKBatch(group, index.h, q_host.ctypes.data, q_host.strides[0], nq, k, h_labels.ctypes.data, h_scores.ctypes.data) == 0
+    torch.cuda.synchronize()
+    e2e_s = env.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    # parity at the quoted size: 8 queries against the reference's fp16 kernels over the device's rows (bar 1e-2)
+    parity = None
+    if not args.no_parity:
+        threads = usable_cores()
+        pick = [(i * nq) // 8 for i in range(8)]
+        chk, scan_s, chk_kind = reference_scan_of_device_rows(env, index, rows, lo, np.ascontiguousarray(q_host[pick]), k, 3, 1, threads)
+        local = [chk.result(i) for i in range(8)]
+        if world > 1:
+            gathered = [None] * world
+            env.dist.all_gather_object(gathered, local)
+            local = []
+            for i in range(8):
+                ids = np.concatenate([g[i][0] for g in gathered])
+                sc = np.concatenate([g[i][1] for g in gathered])
+                order = np.lexsort((ids, sc))[:k]
+                local.append((ids[order], sc[order]))
+        dl, ds = out_labels.cpu().numpy(), out_scores.cpu().numpy()
+        worst, id_overlap = 0.0, 1.0
+        for i, q in enumerate(pick):
+            worst = max(worst, float(np.abs(ds[q] - local[i][1].astype(np.float32)).max()))
+            id_overlap = min(id_overlap, len(set(dl[q].tolist()) & set(local[i][0].tolist())) / k)
+        parity = {"queries": 8, "max_abs_score_diff": worst, "tolerance": 1e-2, "within_tolerance": worst <= 1e-2, "min_id_overlap": id_overlap,
+                  "checker": f"{chk_kind}: reference fp16 distance kernel (the CPU's own tier) + heap over the device's rows"}
+    tpeak, tsust, tsrc = load_tensor_peak()
+    flops = 2.0 * nq * rows * DIM
+    tf = flops / (scan_us * 1e-6) / 1e12
+    if rank == 0:
+        print(json.dumps({
+            "metric": "KNN QPS @k=100 on 50M x 768 fp16 (IP, batch=1024)", "value": nq / (ms_step / 1000.0), "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"FLAT {total} x {DIM} fp16 IP k={k} batch={nq}, row-sharded over {world} GPU(s) ({rows} rows each), one NCCL "
+                                   f"all-gather of per-shard top-k + device merge", "corpus_rows": total, "rows_per_gpu": rows, "dim": DIM, "k": k, "batch": nq},
+            "run_info": {"build_seconds": round(build_s, 2)},
+            "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * DIM * 2), "d2h_bytes_per_step": int(nq * k * 12),
+                    "ms_per_step": e2e_s * 1000.0, "api": "VecSimB200_ShardGroup_TopKBatch"},
+            "gpu_launches": int(st.kernel_launches),
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "peak_sustained": tsust,
+                         "peak_source": tsrc, "kernel": "coarse_qtmem_kernel<direct 16-bit> (tcgen05 kind::f16, rows through a 128B-swizzle tensor map)",
+                         "avg_launch_us": scan_us, "flops_per_launch": flops, "share_of_step": scan_us / 1000.0 / ms_step, "traffic": None,
+                         "hbm": {"algorithmic_bytes_per_launch": rows * DIM * 2, "achieved": rows * DIM * 2 / (scan_us * 1e-6) / 1e9,
+                                 "peak": load_peaks()[0], "unit": "GB/s"}},
+            "clocks": clocks.summary(), "parity_at_config": parity}))
+    env.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# config 5: hybrid filtered KNN — 10M x 768 fp32 FLAT scan pre-filtered by a 2-term posting intersection, k=10
+# ------------------------------------------------------------------------------------------------
+from bench_postings import run_config5  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5], help="2 = BASELINE configs[1] (default, the metric), 3 = configs[2], 5 = configs[4]")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--rows", type=int, default=N_ROWS, help="corpus rows (strong scaling: total; weak: per GPU)")
+    ap.add_argument("--rows3", type=int, default=50_000_000, help="config 3 corpus rows")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--sustained-seconds", type=float, default=3.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-postings", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--posting-docs", type=int, default=50_000_000)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if args.config != 2:
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": f"the reference arm covers the metric's config only (config 2); config {args.config} has its CPU leg inside the line"}))
+            return
+        run_reference_arm(args, rank, world)
+        return
+    if args.config == 3:
+        run_config3(args)
+    elif args.config == 5:
+        run_config5(args, Env, build_shard, ClockSampler, load_peaks, usable_cores)
+    else:
+        run_knn(args)
 
 
 if __name__ == "__main__":

@@ -413,6 +413,10 @@ typedef struct {
     uint64_t scan_bytes; /* algorithmic bytes the timed scan launches covered */
 } VecSimB200_Stats;
 VecSimB200_Stats VecSimB200_GetStats(VecSimIndex *index, bool reset);
+/* Copy stored-form rows [first_row, first_row + n_rows) (internal row order, after the storage preprocessor: what
+ * DataBlocksContainer holds in the reference) from HBM into a tightly packed host buffer of n_rows * stored-size bytes.
+ * For persistence (RDB save) and for checking the device's corpus against a CPU scan.  0 / -1. */
+int VecSimB200_ReadRows(VecSimIndex *index, size_t first_row, size_t n_rows, void *host_dst);
 /* G-way merge of per-shard top-k lists (the coordinator's knnPostProcess, src/module.c:3139-3176,
  * comparator VecSim utils/query_result_utils.h:19-23), on device: in = [G][nq][k] gathered
  * (score,label) pairs, out = [nq][k]. */

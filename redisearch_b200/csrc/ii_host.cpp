@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -881,9 +882,151 @@ size_t II_SearchTopN(II_PostingList *const *lists, size_t n, int is_union, II_Sc
     return search_finish(c, p, doc_ids, scores, total_hits);
 }
 
-// The same for `nq` independent queries (one FT.SEARCH each), with their kernels spread over a pool of streams:
-// query i+1 is enqueued while query i runs, and a slot is only synchronised when it is needed again — the
-// device sees up to kBatchSlots searches at once and the host pays one wait per slot, not one per kernel chain.
+// `nq` independent queries (one FT.SEARCH each) in one call.  AND queries with <= 8 terms and top_n <= 128 — the BASELINE
+// shape — run FUSED: the whole batch is two kernel launches (membership + scorer + per-chunk top-N, then per-query top-N),
+// one descriptor upload, one result download, one synchronisation.  Everything else (unions, wide ANDs, wide LIMITs) takes
+// the per-query kernel chains, spread over a pool of streams.
+namespace {
+struct FusedScratch { // grow-only, owned by the batch entry point (serialised by its mutex)
+    FusedQuery *h_q = nullptr, *d_q = nullptr;
+    size_t q_cap = 0;
+    uint64_t *d_cand_keys = nullptr, *d_out_keys = nullptr, *h_out_keys = nullptr;
+    uint32_t *d_cand_ids = nullptr, *d_out_ids = nullptr, *h_out_ids = nullptr, *d_hits = nullptr, *h_hits = nullptr;
+    size_t cand_cap = 0, out_cap = 0;
+    bool need(size_t nq, size_t cand, size_t out) {
+        if (nq > q_cap) {
+            cudaFreeHost(h_q);
+            cudaFree(d_q);
+            cudaFree(d_hits);
+            cudaFreeHost(h_hits);
+            h_q = d_q = nullptr;
+            d_hits = h_hits = nullptr;
+            q_cap = 0;
+            const size_t cap = std::max<size_t>(nq, 1024);
+            if (cudaMallocHost(&h_q, cap * sizeof(FusedQuery)) != cudaSuccess || cudaMalloc(&d_q, cap * sizeof(FusedQuery)) != cudaSuccess ||
+                cudaMalloc(&d_hits, cap * 4) != cudaSuccess || cudaMallocHost(&h_hits, cap * 4) != cudaSuccess)
+                return false;
+            q_cap = cap;
+        }
+        if (cand > cand_cap) {
+            cudaFree(d_cand_keys);
+            cudaFree(d_cand_ids);
+            d_cand_keys = nullptr;
+            d_cand_ids = nullptr;
+            cand_cap = 0;
+            const size_t cap = cand + cand / 4 + 4096;
+            if (cudaMalloc(&d_cand_keys, cap * 8) != cudaSuccess || cudaMalloc(&d_cand_ids, cap * 4) != cudaSuccess) return false;
+            cand_cap = cap;
+        }
+        if (out > out_cap) {
+            cudaFree(d_out_keys);
+            cudaFree(d_out_ids);
+            cudaFreeHost(h_out_keys);
+            cudaFreeHost(h_out_ids);
+            d_out_keys = h_out_keys = nullptr;
+            d_out_ids = h_out_ids = nullptr;
+            out_cap = 0;
+            const size_t cap = out + out / 4 + 4096;
+            if (cudaMalloc(&d_out_keys, cap * 8) != cudaSuccess || cudaMalloc(&d_out_ids, cap * 4) != cudaSuccess ||
+                cudaMallocHost(&h_out_keys, cap * 8) != cudaSuccess || cudaMallocHost(&h_out_ids, cap * 4) != cudaSuccess)
+                return false;
+            out_cap = cap;
+        }
+        return true;
+    }
+};
+
+// Run the fusable queries idx[0..m) of the batch; false = nothing was written (the caller falls back to the chains)
+bool fused_batch(Ctx &c, FusedScratch &fs, const std::vector<size_t> &idx, II_PostingList *const *const *lists, const size_t *n_lists,
+                 II_Scorer scorer, const II_TermParams *const *terms, double agg_weight, const II_IndexStats *stats, const II_DocTable *docs,
+                 size_t top_n, uint64_t *doc_ids, double *scores, size_t *counts, size_t *total_hits) {
+    constexpr size_t kMaxCand = (size_t)96 << 20; // candidate slots per launch (x 12 B): larger batches are cut into several launches
+    size_t done = 0;
+    while (done < idx.size()) {
+        // sub-batch [done, stop): as many queries as fit the candidate budget
+        size_t stop = done, items = 0;
+        std::vector<uint32_t> order;
+        while (stop < idx.size()) {
+            const size_t qi = idx[stop];
+            size_t shortest = SIZE_MAX;
+            for (size_t t = 0; t < n_lists[qi]; t++) shortest = std::min(shortest, lists[qi][t]->n);
+            const size_t ch = (shortest + kIIChunk - 1) / kIIChunk;
+            if (stop > done && (items + ch) * top_n > kMaxCand) break;
+            items += ch;
+            stop++;
+        }
+        const size_t m = stop - done;
+        if (!fs.need(m, items * top_n, m * top_n)) return false;
+        uint32_t item0 = 0;
+        for (size_t k = 0; k < m; k++) {
+            const size_t qi = idx[done + k];
+            const size_t n = n_lists[qi];
+            FusedQuery &fq = fs.h_q[k];
+            memset(&fq, 0, sizeof(fq));
+            // aggregate child order: stable sort ascending by num_estimated (intersection.rs:110-145); the kernel drives with
+            // child 0, so put the list with the fewest ACTUAL entries first only when the estimates tie the order anyway
+            order.resize(n);
+            for (size_t t = 0; t < n; t++) order[t] = (uint32_t)t;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return lists[qi][a]->estimated < lists[qi][b]->estimated; });
+            for (size_t t = 0; t < n; t++) {
+                const II_PostingList *pl = lists[qi][order[t]];
+                fq.ids[t] = pl->d_ids;
+                fq.freqs[t] = pl->d_freqs;
+                fq.len[t] = (uint32_t)pl->n;
+                fq.weight[t] = terms[qi][order[t]].weight;
+                fq.idf[t] = terms[qi][order[t]].idf;
+                fq.bm25_idf[t] = terms[qi][order[t]].bm25_idf;
+            }
+            fq.n = (uint32_t)n;
+            fq.item0 = item0;
+            fq.nchunks = (uint32_t)((fq.len[0] + kIIChunk - 1) / kIIChunk);
+            item0 += fq.nchunks;
+        }
+        FusedCommon fc{};
+        fc.scorer = (int)scorer;
+        fc.agg_weight = agg_weight;
+        fc.avg_doc_len = stats ? stats->avgDocLen : 0.0;
+        fc.tanh_factor = 4;
+        fc.doc_len = docs ? docs->d_len : nullptr;
+        fc.doc_score = docs ? docs->d_score : nullptr;
+        fc.max_freq = docs ? docs->d_maxf : nullptr;
+        bool ok = cudaMemcpyAsync(fs.d_q, fs.h_q, m * sizeof(FusedQuery), cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+        cudaEventRecord(c.e0, c.stream);
+        ok = ok && ii_launch_fused_search(fs.d_q, (uint32_t)m, item0, fc, (uint32_t)top_n, fs.d_cand_keys, fs.d_cand_ids, fs.d_hits,
+                                          fs.d_out_keys, fs.d_out_ids, c.stream) == cudaSuccess;
+        cudaEventRecord(c.e1, c.stream);
+        ok = ok && cudaMemcpyAsync(fs.h_out_keys, fs.d_out_keys, m * top_n * 8, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(fs.h_out_ids, fs.d_out_ids, m * top_n * 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(fs.h_hits, fs.d_hits, m * 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            return false;
+        }
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c.e0, c.e1) == cudaSuccess) c.stats.intersect_device_us += ms * 1000.0;
+        c.stats.kernel_launches += 2;
+        for (size_t k = 0; k < m; k++) {
+            const size_t qi = idx[done + k];
+            size_t w = 0;
+            for (size_t t = 0; t < top_n; t++) {
+                const uint32_t id = fs.h_out_ids[k * top_n + t];
+                if (id == 0xFFFFFFFFu) break;
+                doc_ids[qi * top_n + w] = id;
+                uint64_t u = ~fs.h_out_keys[k * top_n + t];
+                u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+                memcpy(&scores[qi * top_n + w], &u, 8);
+                w++;
+            }
+            counts[qi] = w;
+            if (total_hits) total_hits[qi] = fs.h_hits[k];
+        }
+        done = stop;
+    }
+    return true;
+}
+} // namespace
+
 int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const size_t *n_lists, int is_union, II_Scorer scorer,
                        const II_TermParams *const *terms, double agg_weight, const II_IndexStats *stats, const II_DocTable *docs,
                        size_t top_n, uint64_t *doc_ids, double *scores, size_t *counts, size_t *total_hits) {
@@ -891,10 +1034,52 @@ int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const siz
     struct Pool {
         std::mutex mu;
         Ctx slot[kBatchSlots];
+        FusedScratch fused;
     };
     static Pool pool;
     if (top_n == 0 || top_n > 1024) return -1;
     std::lock_guard<std::mutex> g(pool.mu);
+    for (size_t i = 0; i < nq; i++) {
+        counts[i] = 0;
+        if (total_hits) total_hits[i] = 0;
+    }
+    // ---- fused path
+    static const bool fused_on = [] {
+        const char *e = getenv("II_B200_FUSED");
+        return !(e && atoi(e) == 0);
+    }();
+    std::vector<size_t> fusable, rest;
+    for (size_t i = 0; i < nq; i++) {
+        if (n_lists[i] == 0 || n_lists[i] > (size_t)kIIMaxLists) continue;
+        bool empty = false;
+        for (size_t t = 0; t < n_lists[i]; t++) empty |= lists[i][t]->n == 0;
+        if (!is_union && empty) continue; // an empty child: the AND is empty (intersection.rs:363-417)
+        if (fused_on && !is_union && n_lists[i] <= (size_t)kFusedMaxLists && top_n <= (size_t)kFusedMaxTopN)
+            fusable.push_back(i);
+        else
+            rest.push_back(i);
+    }
+    if (!fusable.empty()) {
+        double dev_us = 0;
+        uint64_t launches = 0;
+        {
+            CtxScope scope(&pool.slot[0]);
+            if (!pool.slot[0].init()) return -1;
+            pool.slot[0].stats.intersect_device_us = 0;
+            const uint64_t l0 = pool.slot[0].stats.kernel_launches;
+            if (!fused_batch(pool.slot[0], pool.fused, fusable, lists, n_lists, scorer, terms, agg_weight, stats, docs, top_n, doc_ids, scores,
+                             counts, total_hits))
+                rest.insert(rest.end(), fusable.begin(), fusable.end());
+            dev_us = pool.slot[0].stats.intersect_device_us;
+            launches = pool.slot[0].stats.kernel_launches - l0;
+        }
+        // II_GetStats reports the calling thread's counters: device time of the fused launches (membership + scorer + top-N)
+        ctx().stats.intersect_device_us = dev_us;
+        ctx().stats.score_device_us = 0;
+        ctx().stats.kernel_launches += launches;
+    }
+    // ---- per-query kernel chains on the stream pool: query i+1 is enqueued while query i runs, a slot is only
+    // synchronised when it is needed again
     PendingSearch pend[kBatchSlots];
     size_t owner[kBatchSlots];
     auto finish = [&](size_t sl) {
@@ -904,20 +1089,22 @@ int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const siz
         counts[qi] = search_finish(pool.slot[sl], pend[sl], doc_ids + qi * top_n, scores + qi * top_n, &tot);
         if (total_hits) total_hits[qi] = tot;
     };
-    for (size_t i = 0; i < nq; i++) {
-        const size_t sl = i % kBatchSlots;
+    int rc = 0;
+    for (size_t r = 0; r < rest.size(); r++) {
+        const size_t i = rest[r];
+        const size_t sl = r % kBatchSlots;
         if (pend[sl].active) finish(sl);
-        counts[i] = 0;
-        if (total_hits) total_hits[i] = 0;
-        if (n_lists[i] == 0 || n_lists[i] > (size_t)kIIMaxLists) continue;
         CtxScope scope(&pool.slot[sl]);
-        if (!pool.slot[sl].init()) return -1;
+        if (!pool.slot[sl].init()) {
+            rc = -1; // drain what is in flight before reporting the error: its buffers are freed in stream order
+            break;
+        }
         owner[sl] = i;
         search_enqueue(pool.slot[sl], lists[i], n_lists[i], is_union, scorer, terms[i], agg_weight, stats, docs, top_n, pend[sl]);
     }
     for (size_t sl = 0; sl < kBatchSlots; sl++)
         if (pend[sl].active) finish(sl);
-    return 0;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -45,6 +45,37 @@ struct ScoreArgs {
     const uint32_t *max_freq;  // by docId, may be NULL
 };
 
+// ---- fused batch search: AND + scorer + top-N of MANY queries in two launches --------------------------------------
+constexpr int kFusedMaxLists = 8;   // more children: the per-query kernel chain
+constexpr int kFusedMaxTopN = 128;
+// One query of the batch.  Children are in the reference's aggregate order (ascending num_estimated, stable:
+// RS/rqe_iterators/src/intersection.rs:110-145), which for the fused path is also ascending ACTUAL length, so child 0 drives.
+struct FusedQuery {
+    const uint32_t *ids[kFusedMaxLists];
+    const uint32_t *freqs[kFusedMaxLists];
+    uint32_t len[kFusedMaxLists];
+    double weight[kFusedMaxLists], idf[kFusedMaxLists], bm25_idf[kFusedMaxLists];
+    uint32_t n;       // children (1..kFusedMaxLists)
+    uint32_t item0;   // first work item (1024-entry chunk of child 0) of this query in the batch
+    uint32_t nchunks; // work items of this query
+    uint32_t _pad;
+};
+struct FusedCommon {
+    int scorer;
+    double agg_weight, avg_doc_len;
+    uint64_t tanh_factor;
+    const uint32_t *doc_len;
+    const float *doc_score;
+    const uint32_t *max_freq;
+};
+// Launch 1: one CTA per work item — membership of the chunk's docIds in every other child (window located by two warp-wide
+// searches, staged in shared memory), freqs of the matches, the scorer, and the CTA's best `top_n` hits into
+// cand_keys / cand_ids [item][top_n] (padded with ~0); hits[q] += survivors.  Launch 2: one CTA per query selects the best
+// top_n by (score desc, docId asc) over its items' candidates into out_keys / out_ids [nq][top_n].
+cudaError_t ii_launch_fused_search(const FusedQuery *d_queries, uint32_t nq, uint32_t total_items, const FusedCommon &fc, uint32_t top_n,
+                                   uint64_t *d_cand_keys, uint32_t *d_cand_ids, uint32_t *d_hits, uint64_t *d_out_keys,
+                                   uint32_t *d_out_ids, cudaStream_t s);
+
 cudaError_t ii_launch_decode(const uint8_t *d_bytes, const uint64_t *d_byte_off, const uint64_t *d_first_id,
                              const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint32_t *d_ids, uint32_t *d_freqs,
                              uint32_t *d_masks, cudaStream_t s);

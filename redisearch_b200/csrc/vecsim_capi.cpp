@@ -253,6 +253,9 @@ const void *VecSimB200_DeviceRows(VecSimIndex *index, size_t *row_pitch_bytes, s
     if (rows) *rows = r;
     return d;
 }
+int VecSimB200_ReadRows(VecSimIndex *index, size_t first_row, size_t n_rows, void *host_dst) {
+    return IX(index)->read_rows(first_row, n_rows, host_dst) ? 0 : -1;
+}
 VecSimB200_Stats VecSimB200_GetStats(VecSimIndex *index, bool reset) { return IX(index)->get_stats(reset); }
 int VecSimB200_MergeShardTopK(const float *d_scores, const int64_t *d_labels, size_t G, size_t nq, size_t k,
                               float *d_out_scores, int64_t *d_out_labels, void *stream) {

@@ -449,6 +449,13 @@ int FlatIndex::remove(size_t label) {
     return removed;
 }
 
+bool FlatIndex::read_rows(size_t first, size_t n, void *host_dst) {
+    if (!flush()) return false;
+    if (first + n > count_ || !host_dst) return false;
+    if (n == 0) return true;
+    return cudaMemcpy2D(host_dst, stored_bytes_, d_rows_ + first * pitch_, pitch_, stored_bytes_, n, cudaMemcpyDeviceToHost) == cudaSuccess;
+}
+
 bool FlatIndex::sync_labels_to_device() {
     std::lock_guard<std::mutex> g(mu_);
     if (!labels_dirty_ && d_id_to_label_) return true;

@@ -149,6 +149,8 @@ class FlatIndex {
         return d_rows_;
     }
 
+    // stored-form rows [first, first + n) -> tightly packed host buffer (stored_bytes_ per row); false if out of range
+    bool read_rows(size_t first, size_t n, void *host_dst);
     size_t query_blob_bytes() const { return stored_bytes_; } // VecSimParams_GetQueryBlobSize
     void preprocess_query(const void *blob, uint8_t *dst) const;   // -> stored form
     void preprocess_storage(const void *blob, uint8_t *dst) const; // -> stored form

@@ -130,6 +130,7 @@ SIGNATURES = [
     ("VecSimB200_Flush", C.c_int, [_P]),
     ("VecSimB200_DeviceRows", _P, [_P, C.POINTER(_SZ), C.POINTER(_SZ)]),
     ("VecSimB200_GetStats", VecSimB200_Stats, [_P, C.c_bool]),
+    ("VecSimB200_ReadRows", C.c_int, [_P, _SZ, _SZ, _P]),
     ("VecSimB200_MergeShardTopK", C.c_int, [_P, _P, _SZ, _SZ, _SZ, _P, _P, _P]),
     ("VecSimB200_TopKFiltered", C.c_int, [_P, _P, _SZ, _P, _SZ, C.c_int, _P, _P, C.POINTER(_SZ)]),
     ("VecSimB200_LastBatchPath", C.c_int, [_P]),

@@ -462,3 +462,57 @@ def test_intersection_reference_edge_cases_through_the_iterator(ps):
     assert q.Read(it) == ps.ITERATOR_OK and q.lastDocId == 100
     assert q.Read(it) == ps.ITERATOR_EOF
     q.Free(it)
+
+
+@pytest.mark.parametrize("scorer", [0, 1, 2, 3, 4, 5, 6])
+def test_fused_batch_search_equals_the_per_query_chains(ps, scorer):
+    """II_SearchTopNBatch runs AND queries with <= 8 terms and top_n <= 128 FUSED (two launches for the whole batch:
+    membership + scorer + per-chunk top-N, then per-query top-N).  Every query's rows must be the rows of II_SearchTopN
+    (the per-query kernel chain, itself pinned to the oracle by the tests above): docIds, score bits, hit counts — for
+    every scorer, 1..8 terms, ties in the score (DOCSCORE: all equal -> docId order), empty children and top_n 1 / 10 / 128;
+    a 9-term query in the same batch takes the chain path."""
+    rng = np.random.default_rng(100 + scorer)
+    n_docs = 400_000
+    sizes = [150_000, 90_000, 60_000, 30_000, 12_000, 5_000, 2_500, 900, 300, 1]
+    ids = [np.unique(rng.integers(1, n_docs, s)).astype(np.uint64) for s in sizes]
+    ids[3] = np.union1d(ids[3], ids[4][:4000])  # make the deeper ANDs non-empty
+    for j in range(5, 9):
+        ids[j] = np.union1d(ids[j], ids[4][:300])
+    freqs = [rng.integers(1, 30, len(x)).astype(np.uint32) for x in ids]
+    pls = [ps.PostingList.from_arrays(x, f) for x, f in zip(ids, freqs)]
+    empty = ps.PostingList.from_arrays(np.zeros(0, dtype=np.uint64))
+    doc_len = rng.integers(50, 500, n_docs + 1).astype(np.uint32)
+    doc_score = (rng.integers(1, 4, n_docs + 1) / 2.0).astype(np.float32)
+    max_freq = rng.integers(1, 40, n_docs + 1).astype(np.uint32)
+    dt = ps.DocTable(n_docs, doc_len, doc_score, max_freq)
+    avg = float(doc_len[1:].mean())
+    L = ps.lib()
+
+    def terms_of(q):
+        return [(1.0 + 0.25 * (i % 3), L.II_CalculateIDF(n_docs, max(1, len(ids[i]) if i >= 0 else 1)),
+                 L.II_CalculateIDF_BM25(n_docs, max(1, len(ids[i]) if i >= 0 else 1))) for i in q]
+
+    queries = [(0, 1), (0, 1, 2), (2, 1, 0), (3, 4), (0,), (9,), (4, 3, 2, 1, 0), (0, 1, 2, 3, 4, 5, 6, 7), (8, 7, 6, 5), (0, 9),
+               (1, 2, 3, 4, 5, 6, 7, 8, 0), (5, 6), (0, 1, 4), (2, 3)]
+    for top_n in (1, 10, 128):
+        qs = []
+        for q in queries:
+            qs.append(([pls[i] for i in q], terms_of(q)))
+        qs.append(([pls[0], empty, pls[1]], terms_of((0, -1, 1))))  # an empty child: the AND is empty
+        batch = ps.SearchBatch(qs, top_n)
+        got = batch.run(False, scorer, 1.5, n_docs, avg, dt)
+        for (lists, terms), (gi, gs, gt) in zip(qs, got):
+            ei, es, et = ps.search_topn(lists, False, scorer, terms, 1.5, n_docs, avg, dt, top_n)
+            assert gt == et, (scorer, top_n, gt, et)
+            assert gi.tolist() == ei.tolist(), (scorer, top_n, len(lists))
+            assert gs.tobytes() == es.tobytes()
+    # a few hundred random queries in one call
+    many = []
+    for _ in range(300):
+        k = int(rng.integers(1, 5))
+        q = tuple(int(x) for x in rng.choice(9, k, replace=False))
+        many.append(([pls[i] for i in q], terms_of(q)))
+    got = ps.SearchBatch(many, 10).run(False, scorer, 1.0, n_docs, avg, dt)
+    for (lists, terms), (gi, gs, gt) in list(zip(many, got))[::7]:
+        ei, es, et = ps.search_topn(lists, False, scorer, terms, 1.0, n_docs, avg, dt, 10)
+        assert gt == et and gi.tolist() == ei.tolist() and gs.tobytes() == es.tobytes()
