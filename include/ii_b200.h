@@ -115,6 +115,12 @@ typedef struct II_PostingList II_PostingList; /* (docId u32, freq u32) arrays re
  * decode in a kernel (one thread per block). */
 II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nblocks, II_Codec codec,
                                           uint32_t field_mask_filter, int decode_on_device);
+/* The same for MANY lists in one call (the terms of a batch of queries): one gather of all block bytes and block tables
+ * into pinned staging, one H2D copy, one decode launch, one synchronisation; the lists share their device arrays.
+ * blocks[i] / nblocks[i] describe list i, out[i] receives its handle (NULL if it could not be built).  Returns the number
+ * of lists built. */
+size_t II_PostingList_FromBlocksBatch(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec,
+                                      II_PostingList **out);
 /* From already-decoded host arrays (freqs may be NULL = all 1).  docIds strictly ascending. */
 II_PostingList *II_PostingList_FromArrays(const uint64_t *doc_ids, const uint32_t *freqs, size_t n);
 /* Adopt COPIES of device arrays (docIds u32 ascending, freqs u32). */
@@ -209,6 +215,28 @@ int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const siz
  * are [num_shards][per_shard], counts[g] entries valid; writes the best n by (score desc, docId asc), returns how many. */
 size_t II_MergeShardTopN(const double *scores, const uint64_t *doc_ids, const size_t *counts, size_t num_shards, size_t per_shard,
                          size_t n, uint64_t *out_ids, double *out_scores);
+
+/* ---- term -> device posting list cache ------------------------------------------------------------------------------
+ * Hot terms stay decoded in HBM between queries; the host decode / H2D leaves the query path.
+ * keys[i] identifies a term's inverted index (e.g. the InvertedIndex pointer), versions[i] must change whenever that index
+ * is written or garbage-collected — e.g. (gc_marker << 32) | num_entries: the gc_marker is what the reference's readers
+ * compare in needs_revalidation (RS/inverted_index/src/reader/core.rs:372-374, bumped by the GC at index/core.rs:436), the
+ * entry count moves with every append.  Acquire returns resident lists for (key, version) hits WITHOUT touching the blocks
+ * and decodes all misses together in one II_PostingList_FromBlocksBatch; a stale version is dropped and rebuilt.  The
+ * returned handles are pinned (never evicted, never freed) until II_TermCache_Release; they must not be passed to
+ * II_PostingList_Free.  Eviction is LRU over unpinned lists once resident_bytes exceeds max_device_bytes.  Thread-safe. */
+typedef struct II_TermCache II_TermCache;
+typedef struct {
+    size_t hits, misses, evictions, resident_bytes, resident_lists;
+} II_TermCacheStats;
+II_TermCache *II_TermCache_New(size_t max_device_bytes);
+void II_TermCache_Free(II_TermCache *cache);
+/* Returns how many of the n lists are available in out[] (NULL = could not be built). */
+size_t II_TermCache_Acquire(II_TermCache *cache, size_t n, const uint64_t *keys, const uint64_t *versions,
+                            const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec, II_PostingList **out);
+void II_TermCache_Release(II_TermCache *cache, size_t n, II_PostingList *const *lists);
+void II_TermCache_Invalidate(II_TermCache *cache, uint64_t key); /* from the index writer / GC, when it is cheaper than versions */
+II_TermCacheStats II_TermCache_GetStats(II_TermCache *cache);
 
 /* ---- QueryIterator facade ------------------------------------------------------------------------ */
 /* Takes ownership of `rs` (downloads docIds/scores once).  Free through it->Free(it). */

@@ -13,6 +13,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 using namespace rsb200;
@@ -122,14 +123,23 @@ double now_us() {
 
 } // namespace
 
+// device memory shared by the posting lists of one batch decode (freed when the last of them goes)
+struct SharedDeviceBlock {
+    void *p = nullptr;
+    ~SharedDeviceBlock() { dfree(p); }
+};
+
 struct II_PostingList {
     uint32_t *d_ids = nullptr, *d_freqs = nullptr;
     size_t n = 0;
     size_t estimated = 0; // unfiltered unique docs (num_estimated of the leaf iterator)
     uint32_t last_id = 0;
+    std::shared_ptr<SharedDeviceBlock> owner; // set: d_ids / d_freqs are slices of owner->p
     ~II_PostingList() {
-        dfree(d_ids);
-        dfree(d_freqs);
+        if (!owner) {
+            dfree(d_ids);
+            dfree(d_freqs);
+        }
     }
 };
 
@@ -235,8 +245,136 @@ bool decode_block(const II_BlockView &b, II_Codec codec, uint32_t *ids, uint32_t
 
 extern "C" {
 
+// Decode MANY posting lists in one go: ONE gather of all block bytes + block tables into pinned staging, ONE H2D copy,
+// ONE decode launch (decode_blocks_staged_kernel), ONE synchronisation.  The lists share two device arrays (ids, freqs).
+size_t II_PostingList_FromBlocksBatch(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec,
+                                      II_PostingList **out) {
+    for (size_t i = 0; i < n_lists; i++) out[i] = nullptr;
+    if (n_lists == 0) return 0;
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return 0;
+    size_t built = 0, first_list = 0;
+    while (first_list < n_lists) {
+        // sub-batch: < 4 GB of bytes and < 2^32 entries (32-bit tables)
+        size_t stop = first_list, B = 0, nbytes = 0, n = 0;
+        bool bad_ids = false;
+        while (stop < n_lists) {
+            size_t lb = 0, le = 0;
+            for (size_t b = 0; b < nblocks[stop]; b++) {
+                lb += blocks[stop][b].len;
+                le += blocks[stop][b].num_entries;
+                bad_ids |= blocks[stop][b].last_doc_id > 0xFFFFFFFEull;
+            }
+            if (stop > first_list && (nbytes + lb > ((size_t)3 << 30) || n + le > ((size_t)1 << 31))) break;
+            nbytes += lb;
+            n += le;
+            B += nblocks[stop];
+            stop++;
+        }
+        if (bad_ids || nbytes > ((size_t)4 << 30) - 64 || n >= ((size_t)1 << 32)) return built; // not representable on the device
+        const size_t bytes_pad = (nbytes + 15 + 16) & ~(size_t)15; // the kernel copies whole 16-byte chunks
+        const size_t stage_bytes = bytes_pad + (3 * B + 2) * 4;
+        uint8_t *stg = c.stage(stage_bytes);
+        if (!stg) return built;
+        uint32_t *first = reinterpret_cast<uint32_t *>(stg + bytes_pad), *boff = first + B, *eoff = boff + B + 1;
+        // tables (serial: cheap), then the byte gather on as many threads as the volume is worth
+        std::vector<size_t> list_b0(stop - first_list + 1, 0), list_e0(stop - first_list + 1, 0);
+        {
+            size_t bi = 0, bo = 0, eo = 0;
+            for (size_t l = first_list; l < stop; l++) {
+                list_b0[l - first_list] = bi;
+                list_e0[l - first_list] = eo;
+                for (size_t b = 0; b < nblocks[l]; b++, bi++) {
+                    first[bi] = (uint32_t)blocks[l][b].first_doc_id;
+                    boff[bi] = (uint32_t)bo;
+                    eoff[bi] = (uint32_t)eo;
+                    bo += blocks[l][b].len;
+                    eo += blocks[l][b].num_entries;
+                }
+            }
+            boff[B] = (uint32_t)bo;
+            eoff[B] = (uint32_t)eo;
+            list_b0.back() = bi;
+            list_e0.back() = eo;
+        }
+        const double tg = now_us();
+        {
+            const unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)(nbytes >> 22) + 1u}));
+            auto work = [&](unsigned t) {
+                const size_t l0 = first_list + (stop - first_list) * t / nt, l1 = first_list + (stop - first_list) * (t + 1) / nt;
+                for (size_t l = l0; l < l1; l++) {
+                    size_t bi = list_b0[l - first_list];
+                    for (size_t b = 0; b < nblocks[l]; b++, bi++) memcpy(stg + boff[bi], blocks[l][b].data, blocks[l][b].len);
+                }
+            };
+            if (nt == 1 || stop - first_list < 2 * (size_t)nt) {
+                // few lists: split by blocks instead
+                const unsigned nb_t = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)(nbytes >> 22) + 1u}));
+                if (nb_t == 1) {
+                    for (unsigned t = 0; t < nt; t++) work(t);
+                } else {
+                    std::vector<const II_BlockView *> flat(B);
+                    size_t bi = 0;
+                    for (size_t l = first_list; l < stop; l++)
+                        for (size_t b = 0; b < nblocks[l]; b++) flat[bi++] = &blocks[l][b];
+                    std::vector<std::thread> th;
+                    for (unsigned t = 0; t < nb_t; t++)
+                        th.emplace_back([&, t] {
+                            for (size_t x = B * t / nb_t; x < B * (t + 1) / nb_t; x++) memcpy(stg + boff[x], flat[x]->data, flat[x]->len);
+                        });
+                    for (auto &x : th) x.join();
+                }
+            } else {
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+                for (auto &x : th) x.join();
+            }
+            memset(stg + nbytes, 0, bytes_pad - nbytes);
+        }
+        c.stats.decode_host_us = now_us() - tg;
+        const double t0 = now_us();
+        auto blockmem = std::make_shared<SharedDeviceBlock>();
+        blockmem->p = dalloc<uint8_t>((n ? n : 1) * 8);
+        uint8_t *d_stage = dalloc<uint8_t>(stage_bytes);
+        bool ok = blockmem->p && d_stage;
+        uint32_t *d_ids = reinterpret_cast<uint32_t *>(blockmem->p), *d_freqs = d_ids + n;
+        ok = ok && cudaMemcpyAsync(d_stage, stg, stage_bytes, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+        const uint32_t *d_first = reinterpret_cast<const uint32_t *>(d_stage + bytes_pad), *d_boff = d_first + B, *d_eoff = d_boff + B + 1;
+        ok = ok && ii_launch_decode_staged(d_stage, d_boff, d_first, d_eoff, (uint32_t)B, (int)codec, d_ids, d_freqs, nullptr, c.stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+        c.stats.h2d_us = now_us() - t0;
+        c.stats.kernel_launches += 1;
+        dfree(d_stage);
+        if (!ok) {
+            cudaGetLastError();
+            return built;
+        }
+        for (size_t l = first_list; l < stop; l++) {
+            auto *pl = new II_PostingList();
+            const size_t e0 = list_e0[l - first_list], e1 = (l + 1 < stop) ? list_e0[l + 1 - first_list] : n;
+            pl->owner = blockmem;
+            pl->d_ids = d_ids + e0;
+            pl->d_freqs = d_freqs + e0;
+            pl->n = pl->estimated = e1 - e0;
+            pl->last_id = nblocks[l] ? (uint32_t)blocks[l][nblocks[l] - 1].last_doc_id : 0;
+            out[l] = pl;
+            built++;
+        }
+        first_list = stop;
+    }
+    return built;
+}
+
 II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nblocks, II_Codec codec,
                                           uint32_t field_mask_filter, int decode_on_device) {
+    if (decode_on_device && field_mask_filter == 0) { // the common case rides the batch decoder (one copy, one launch, one sync)
+        II_PostingList *one = nullptr;
+        const II_BlockView *bl[1] = {blocks};
+        const size_t nb[1] = {nblocks};
+        II_PostingList_FromBlocksBatch(1, bl, nb, codec, &one);
+        return one;
+    }
     Ctx &c = ctx();
     std::lock_guard<std::mutex> g(c.mu);
     if (!c.init()) return nullptr;
@@ -1105,6 +1243,164 @@ int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const siz
     for (size_t sl = 0; sl < kBatchSlots; sl++)
         if (pend[sl].active) finish(sl);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// term -> device posting list cache
+// ------------------------------------------------------------------------------------------------
+struct II_TermCache {
+    struct Entry {
+        uint64_t version = 0;
+        II_PostingList *pl = nullptr;
+        size_t refs = 0, bytes = 0;
+        uint64_t tick = 0;
+    };
+    std::mutex mu;
+    std::unordered_map<uint64_t, Entry> live;
+    std::unordered_map<II_PostingList *, uint64_t> key_of;       // resident lists -> key
+    std::unordered_map<II_PostingList *, size_t> zombies;        // replaced / invalidated while pinned: list -> refs left
+    size_t max_bytes = 0, resident_bytes = 0;
+    uint64_t tick = 0;
+    II_TermCacheStats st{};
+    void evict_locked() {
+        while (resident_bytes > max_bytes) {
+            uint64_t victim = 0, best = UINT64_MAX;
+            bool found = false;
+            for (auto &kv : live)
+                if (kv.second.refs == 0 && kv.second.tick < best) {
+                    best = kv.second.tick;
+                    victim = kv.first;
+                    found = true;
+                }
+            if (!found) break;
+            Entry &e = live[victim];
+            resident_bytes -= e.bytes;
+            key_of.erase(e.pl);
+            delete e.pl;
+            live.erase(victim);
+            st.evictions++;
+        }
+    }
+    void drop_locked(uint64_t key) {
+        auto it = live.find(key);
+        if (it == live.end()) return;
+        Entry &e = it->second;
+        resident_bytes -= e.bytes;
+        key_of.erase(e.pl);
+        if (e.refs)
+            zombies[e.pl] = e.refs; // still pinned by a running query: freed by the last Release
+        else
+            delete e.pl;
+        live.erase(it);
+    }
+};
+
+II_TermCache *II_TermCache_New(size_t max_device_bytes) {
+    auto *c = new II_TermCache();
+    c->max_bytes = max_device_bytes;
+    return c;
+}
+void II_TermCache_Free(II_TermCache *c) {
+    if (!c) return;
+    for (auto &kv : c->live) delete kv.second.pl;
+    for (auto &kv : c->zombies) delete kv.first;
+    delete c;
+}
+void II_TermCache_Invalidate(II_TermCache *c, uint64_t key) {
+    std::lock_guard<std::mutex> g(c->mu);
+    c->drop_locked(key);
+}
+II_TermCacheStats II_TermCache_GetStats(II_TermCache *c) {
+    std::lock_guard<std::mutex> g(c->mu);
+    II_TermCacheStats s = c->st;
+    s.resident_bytes = c->resident_bytes;
+    s.resident_lists = c->live.size();
+    return s;
+}
+
+size_t II_TermCache_Acquire(II_TermCache *c, size_t n, const uint64_t *keys, const uint64_t *versions, const II_BlockView *const *blocks,
+                            const size_t *nblocks, II_Codec codec, II_PostingList **out) {
+    std::vector<size_t> miss;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        for (size_t i = 0; i < n; i++) {
+            out[i] = nullptr;
+            auto it = c->live.find(keys[i]);
+            if (it != c->live.end() && it->second.version != versions[i]) { // the index was written / collected since
+                c->drop_locked(keys[i]);
+                it = c->live.end();
+            }
+            if (it != c->live.end()) {
+                it->second.refs++;
+                it->second.tick = ++c->tick;
+                out[i] = it->second.pl;
+                c->st.hits++;
+            } else {
+                miss.push_back(i);
+            }
+        }
+    }
+    if (!miss.empty()) {
+        // the same key may appear twice among the misses (two queries of a batch sharing a term): decode it once
+        std::vector<size_t> uniq;
+        std::unordered_map<uint64_t, size_t> first_of;
+        for (size_t i : miss)
+            if (first_of.emplace(keys[i], uniq.size()).second) uniq.push_back(i);
+        std::vector<const II_BlockView *> b(uniq.size());
+        std::vector<size_t> nb(uniq.size());
+        std::vector<II_PostingList *> built(uniq.size(), nullptr);
+        for (size_t k = 0; k < uniq.size(); k++) {
+            b[k] = blocks[uniq[k]];
+            nb[k] = nblocks[uniq[k]];
+        }
+        II_PostingList_FromBlocksBatch(uniq.size(), b.data(), nb.data(), codec, built.data());
+        std::lock_guard<std::mutex> g(c->mu);
+        for (size_t k = 0; k < uniq.size(); k++) {
+            if (!built[k]) continue;
+            const uint64_t key = keys[uniq[k]];
+            c->drop_locked(key); // another thread may have inserted it meanwhile: ours replaces it
+            II_TermCache::Entry e;
+            e.version = versions[uniq[k]];
+            e.pl = built[k];
+            e.bytes = built[k]->n * 8;
+            e.tick = ++c->tick;
+            c->live[key] = e;
+            c->key_of[built[k]] = key;
+            c->resident_bytes += e.bytes;
+            c->st.misses++;
+        }
+        for (size_t i : miss) {
+            auto it = c->live.find(keys[i]);
+            if (it == c->live.end()) continue;
+            it->second.refs++;
+            out[i] = it->second.pl;
+        }
+        c->evict_locked();
+    }
+    size_t got = 0;
+    for (size_t i = 0; i < n; i++) got += out[i] != nullptr;
+    return got;
+}
+
+void II_TermCache_Release(II_TermCache *c, size_t n, II_PostingList *const *lists) {
+    std::lock_guard<std::mutex> g(c->mu);
+    for (size_t i = 0; i < n; i++) {
+        II_PostingList *pl = lists[i];
+        if (!pl) continue;
+        auto z = c->zombies.find(pl);
+        if (z != c->zombies.end()) {
+            if (--z->second == 0) {
+                delete pl;
+                c->zombies.erase(z);
+            }
+            continue;
+        }
+        auto k = c->key_of.find(pl);
+        if (k == c->key_of.end()) continue;
+        auto it = c->live.find(k->second);
+        if (it != c->live.end() && it->second.refs) it->second.refs--;
+    }
+    c->evict_locked();
 }
 
 // ------------------------------------------------------------------------------------------------

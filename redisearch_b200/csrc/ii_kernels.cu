@@ -89,6 +89,85 @@ __global__ void decode_blocks_kernel(const uint8_t *__restrict__ bytes, const ui
     }
 }
 
+// The same, for a whole batch of posting lists at once, with the block bytes staged in shared memory: a CTA of 128 threads
+// owns 128 consecutive blocks of the gathered byte stream (contiguous in HBM), copies their bytes into shared memory with
+// coalesced 16-byte loads and then every thread walks its own block there — the qint / varint records of a block are a
+// dependent chain (the lead byte of record e+1 is only known after record e), so the parallelism is across blocks, and
+// what the one-thread-per-block kernel above loses is byte-granular global loads.  Tables are 32-bit (a batch is < 4 GB).
+// out_masks may be NULL.  Blocks whose bytes do not fit the staging area are read from global memory.
+constexpr int kDecodeThreads = 128;
+constexpr uint32_t kDecodeSmem = 96 * 1024;
+__global__ void __launch_bounds__(kDecodeThreads) decode_blocks_staged_kernel(const uint8_t *__restrict__ bytes, const uint32_t *__restrict__ byte_off,
+                                                                              const uint32_t *__restrict__ first_id,
+                                                                              const uint32_t *__restrict__ entry_off, uint32_t nblocks, int codec,
+                                                                              uint32_t *__restrict__ out_ids, uint32_t *__restrict__ out_freqs,
+                                                                              uint32_t *__restrict__ out_masks) {
+    extern __shared__ __align__(16) uint8_t s_bytes[];
+    const uint32_t b0 = blockIdx.x * kDecodeThreads;
+    const uint32_t b1 = min(b0 + (uint32_t)kDecodeThreads, nblocks);
+    const uint32_t lo = byte_off[b0] & ~15u, hi = byte_off[b1]; // 16-byte aligned start: the gathered stream is 16-byte aligned
+    const bool staged = hi - lo <= kDecodeSmem;
+    if (staged) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(bytes + lo);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_bytes);
+        const uint32_t n16 = (hi - lo + 15) / 16;
+        for (uint32_t t = threadIdx.x; t < n16; t += kDecodeThreads) dst[t] = src[t]; // the stream is padded to 16 bytes
+        __syncthreads();
+    }
+    const uint32_t b = b0 + threadIdx.x;
+    if (b >= b1) return;
+    const uint8_t *p = staged ? s_bytes + (byte_off[b] - lo) : bytes + byte_off[b];
+    const uint32_t n = entry_off[b + 1] - entry_off[b];
+    uint32_t o = entry_off[b];
+    const uint32_t base0 = first_id[b];
+    uint32_t last = base0; // the reader resets the delta base to first_doc_id on block entry (reader/core.rs:430-440)
+    for (uint32_t e = 0; e < n; e++, o++) {
+        uint32_t freq = 1, mask = 0xFFFFFFFFu, id;
+        if (codec == 5) { // raw doc ids: u32 delta from the block's first id
+            id = base0 + qint_value(p, 4);
+            p += 4;
+        } else if (codec == 4) { // varint delta (RS/varint/src/lib.rs read_as_varint)
+            uint8_t c = *p++;
+            uint32_t val = c & 0x7f;
+            while (c & 0x80) {
+                val += 1;
+                c = *p++;
+                val = (val << 7) | (c & 0x7f);
+            }
+            id = last + val;
+        } else {
+            const uint8_t lead = *p++;
+            const int nvals = (codec == 0) ? 4 : (codec == 2) ? 3 : 2;
+            uint32_t v[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (i < nvals) {
+                    const int nb = ((lead >> (2 * i)) & 3) + 1;
+                    v[i] = qint_value(p, nb);
+                    p += nb;
+                }
+            }
+            id = last + v[0];
+            if (codec == 0) { // Full: delta, freq, fieldMask, offsetsLen + offsets bytes
+                freq = v[1];
+                mask = v[2];
+                p += v[3];
+            } else if (codec == 1) { // FreqsOnly
+                freq = v[1];
+            } else if (codec == 2) { // FreqsFields
+                freq = v[1];
+                mask = v[2];
+            } else { // FieldsOnly
+                mask = v[1];
+            }
+        }
+        last = id;
+        out_ids[o] = id;
+        out_freqs[o] = freq;
+        if (out_masks) out_masks[o] = mask;
+    }
+}
+
 // keep records with (mask & filter) != 0, in order: flags -> scan done by the caller (scan_kernel)
 __global__ void mask_flags_kernel(const uint32_t *__restrict__ masks, uint32_t n, uint32_t filter,
                                   uint32_t *__restrict__ chunk_counts) {
@@ -760,6 +839,20 @@ cudaError_t ii_launch_decode(const uint8_t *d_bytes, const uint64_t *d_byte_off,
     if (!nblocks) return cudaSuccess;
     decode_blocks_kernel<<<(nblocks + 127) / 128, 128, 0, s>>>(d_bytes, d_byte_off, d_first_id, d_entry_off, nblocks, codec,
                                                               d_ids, d_freqs, d_masks);
+    return cudaGetLastError();
+}
+cudaError_t ii_launch_decode_staged(const uint8_t *d_bytes, const uint32_t *d_byte_off, const uint32_t *d_first_id,
+                                    const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint32_t *d_ids, uint32_t *d_freqs,
+                                    uint32_t *d_masks, cudaStream_t s) {
+    if (!nblocks) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(decode_blocks_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    decode_blocks_staged_kernel<<<(nblocks + kDecodeThreads - 1) / kDecodeThreads, kDecodeThreads, kDecodeSmem, s>>>(
+        d_bytes, d_byte_off, d_first_id, d_entry_off, nblocks, codec, d_ids, d_freqs, d_masks);
     return cudaGetLastError();
 }
 cudaError_t ii_launch_mask_filter(const uint32_t *d_ids, const uint32_t *d_freqs, const uint32_t *d_masks, uint32_t n,

@@ -79,6 +79,11 @@ cudaError_t ii_launch_fused_search(const FusedQuery *d_queries, uint32_t nq, uin
 cudaError_t ii_launch_decode(const uint8_t *d_bytes, const uint64_t *d_byte_off, const uint64_t *d_first_id,
                              const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint32_t *d_ids, uint32_t *d_freqs,
                              uint32_t *d_masks, cudaStream_t s);
+// batch decode: 32-bit tables (byte_off[nblocks+1] into the 16-byte-aligned, 16-byte-padded gathered stream, first_id[nblocks],
+// entry_off[nblocks+1] into the output arrays), blocks of MANY lists back to back
+cudaError_t ii_launch_decode_staged(const uint8_t *d_bytes, const uint32_t *d_byte_off, const uint32_t *d_first_id,
+                                    const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint32_t *d_ids, uint32_t *d_freqs,
+                                    uint32_t *d_masks, cudaStream_t s);
 cudaError_t ii_launch_mask_filter(const uint32_t *d_ids, const uint32_t *d_freqs, const uint32_t *d_masks, uint32_t n,
                                   uint32_t filter, uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_total,
                                   uint32_t *d_out_ids, uint32_t *d_out_freqs, cudaStream_t s);

@@ -29,6 +29,11 @@ class II_Stats(C.Structure):
                 ("decode_host_us", C.c_double), ("h2d_us", C.c_double)]
 
 
+class II_TermCacheStats(C.Structure):
+    _fields_ = [("hits", C.c_size_t), ("misses", C.c_size_t), ("evictions", C.c_size_t), ("resident_bytes", C.c_size_t),
+                ("resident_lists", C.c_size_t)]
+
+
 class _ResultData(C.Structure):
     _fields_ = [("tag", C.c_uint8), ("_pad", C.c_uint8 * 7), ("metric", C.c_double), ("_rest", C.c_uint8 * 24)]
 
@@ -54,6 +59,7 @@ II_QueryIterator._fields_ = [
 _P, _SZ = C.c_void_p, C.c_size_t
 SIGNATURES = [
     ("II_PostingList_FromBlocks", _P, [C.POINTER(II_BlockView), _SZ, C.c_int, C.c_uint32, C.c_int]),
+    ("II_PostingList_FromBlocksBatch", _SZ, [_SZ, _P, _P, C.c_int, _P]),
     ("II_PostingList_FromArrays", _P, [_P, _P, _SZ]),
     ("II_PostingList_FromDevice", _P, [_P, _P, _SZ]),
     ("II_PostingList_Len", _SZ, [_P]),
@@ -80,6 +86,12 @@ SIGNATURES = [
     ("II_SearchTopNBatch", C.c_int, [_SZ, _P, _P, C.c_int, C.c_int, _P, C.c_double, C.POINTER(II_IndexStats), _P, _SZ, _P, _P, _P, _P]),
     ("II_MergeShardTopN", _SZ, [_P, _P, _P, _SZ, _SZ, _SZ, _P, _P]),
     ("II_NewResultIterator", _QI, [_P, C.c_double]),
+    ("II_TermCache_New", _P, [_SZ]),
+    ("II_TermCache_Free", None, [_P]),
+    ("II_TermCache_Acquire", _SZ, [_P, _SZ, _P, _P, _P, _P, C.c_int, _P]),
+    ("II_TermCache_Release", None, [_P, _SZ, _P]),
+    ("II_TermCache_Invalidate", None, [_P, C.c_uint64]),
+    ("II_TermCache_GetStats", II_TermCacheStats, [_P]),
     ("II_GetStats", II_Stats, [C.c_bool]),
     ("II_Version", C.c_char_p, []),
 ]

@@ -516,3 +516,117 @@ def test_fused_batch_search_equals_the_per_query_chains(ps, scorer):
     for (lists, terms), (gi, gs, gt) in list(zip(many, got))[::7]:
         ei, es, et = ps.search_topn(lists, False, scorer, terms, 1.0, n_docs, avg, dt, 10)
         assert gt == et and gi.tolist() == ei.tolist() and gs.tobytes() == es.tobytes()
+
+
+def _block_views(ps, blocks):
+    """list of (first, last, n, bytes) -> (II_BlockView array, keep-alive buffers)"""
+    arr = (ps.II_BlockView * max(1, len(blocks)))()
+    keep = []
+    for i, (first, last, n, data) in enumerate(blocks):
+        buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+        keep.append(buf)
+        arr[i] = ps.II_BlockView(first, last, n, C.cast(buf, C.POINTER(C.c_uint8)), len(data))
+    return arr, keep
+
+
+@pytest.mark.parametrize("codec", range(6))
+def test_batch_decode_of_many_lists_matches_the_oracle_reader(ps, codec):
+    """II_PostingList_FromBlocksBatch: the blocks of MANY lists in one gather / one copy / one decode launch (bytes staged in
+    shared memory, one thread per block).  Every list must read back exactly like the oracle reader: long lists, a one-entry
+    list, an empty list, wide deltas (4-byte qint fields) and, for the Full codec, records with offset payloads."""
+    rng = np.random.default_rng(40 + codec)
+    specs = [(7000, 50), (1, 10), (0, 1), (333, 3_000_000), (12_345, 9), (100, 70_000), (2501, 300)]
+    idx, views, keep, nbl = [], [], [], []
+    for n, gap in specs:
+        ix = ol.InvIndex(codec)
+        doc = 0
+        for _ in range(n):
+            doc += int(rng.integers(1, gap + 1))
+            off = bytes(rng.integers(0, 255, int(rng.integers(0, 9))).astype(np.uint8)) if codec == ol.CODEC_FULL else b""
+            ix.add(doc, int(rng.integers(1, 1 << int(rng.integers(1, 31)))), int(rng.integers(1, 1 << 30)), off)
+        bl = ix.blocks()
+        arr, k = _block_views(ps, bl)
+        idx.append(ix)
+        views.append(arr)
+        keep.append(k)
+        nbl.append(len(bl))
+    L = ps.lib()
+    ptrs = (C.c_void_p * len(specs))(*[C.cast(v, C.c_void_p) for v in views])
+    ns = (C.c_size_t * len(specs))(*nbl)
+    out = (C.c_void_p * len(specs))()
+    assert L.II_PostingList_FromBlocksBatch(len(specs), ptrs, ns, codec, out) == len(specs)
+    for ix, h in zip(idx, out):
+        pl = ps.PostingList(h)
+        exp = ix.read_all()
+        assert len(pl) == len(exp)
+        if not exp:
+            continue
+        got_ids, _, got_fr = ps.union([pl]).fetch()
+        assert got_ids.tolist() == [e[0] for e in exp]
+        assert got_fr[0].tolist() == [e[1] for e in exp]
+
+
+def test_term_cache_hits_versions_pins_and_eviction(ps):
+    """II_TermCache: a (key, version) hit returns the resident list without touching the blocks; a new version (the index was
+    written / collected: gc_marker, RS/inverted_index/src/reader/core.rs:372-374) rebuilds it; pinned lists survive
+    replacement until released; LRU eviction keeps the resident bytes under the budget."""
+    L = ps.lib()
+    rng = np.random.default_rng(77)
+
+    def make(n, seed):
+        r = np.random.default_rng(seed)
+        ids = np.cumsum(r.integers(1, 50, n)).astype(np.uint64)
+        ix = ol.InvIndex(ol.CODEC_FREQS_ONLY, ids, r.integers(1, 9, n).tolist())
+        arr, keep = _block_views(ps, ix.blocks())
+        return ix, arr, keep, len(ix.blocks())
+
+    terms = [make(5000 + 1000 * i, i) for i in range(6)]
+    cache = L.II_TermCache_New(8 * (5000 + 6000 + 7000) + 64)  # room for about three of the lists
+
+    def acquire(which, versions):
+        n = len(which)
+        keys = (C.c_uint64 * n)(*[1000 + w for w in which])
+        vers = (C.c_uint64 * n)(*versions)
+        bl = (C.c_void_p * n)(*[C.cast(terms[w][1], C.c_void_p) for w in which])
+        nb = (C.c_size_t * n)(*[terms[w][3] for w in which])
+        out = (C.c_void_p * n)()
+        assert L.II_TermCache_Acquire(cache, n, keys, vers, bl, nb, ol.CODEC_FREQS_ONLY, out) == n
+        return out
+
+    def check(handle, w):
+        h = C.c_void_p(handle)
+        arr = (C.c_void_p * 1)(h)
+        rs = L.II_Union(arr, 1, 0)
+        m = L.II_ResultSet_Len(rs)
+        ids = np.zeros(m, dtype=np.uint64)
+        assert L.II_ResultSet_Fetch(rs, ids.ctypes.data, None, None) == 0
+        L.II_ResultSet_Free(rs)
+        assert ids.tolist() == [e[0] for e in terms[w][0].read_all()]
+
+    a = acquire([0, 1, 0], [1, 1, 1])  # the same term twice in one batch: decoded once
+    assert a[0] == a[2]
+    st = L.II_TermCache_GetStats(cache)
+    assert (st.misses, st.hits, st.resident_lists) == (2, 0, 2)
+    check(a[0], 0)
+    check(a[1], 1)
+    L.II_TermCache_Release(cache, 3, a)
+    b = acquire([0, 1], [1, 1])
+    st = L.II_TermCache_GetStats(cache)
+    assert (st.misses, st.hits) == (2, 2) and b[0] == a[0] and b[1] == a[1]
+    # version bump of term 0 while it is still pinned by `b`: a fresh list is built, the old handle stays valid until released
+    c2 = acquire([0], [2])
+    assert c2[0] != b[0]
+    check(b[0], 0)
+    check(c2[0], 0)
+    L.II_TermCache_Release(cache, 2, b)
+    L.II_TermCache_Release(cache, 1, c2)
+    # fill past the budget: least recently used unpinned lists go
+    for w in (2, 3, 4, 5):
+        h = acquire([w], [1])
+        check(h[0], w)
+        L.II_TermCache_Release(cache, 1, h)
+    st = L.II_TermCache_GetStats(cache)
+    assert st.evictions >= 2 and st.resident_bytes <= 8 * (5000 + 6000 + 7000) + 64
+    L.II_TermCache_Invalidate(cache, 1005)
+    assert L.II_TermCache_GetStats(cache).resident_lists == st.resident_lists - 1
+    L.II_TermCache_Free(cache)
