@@ -591,13 +591,18 @@ def run_knn(args):
                                                         check=not args.no_parity)
             except Exception as e:
                 line["bm25_intersect"] = {"value": None, "error": repr(e)}
+        bm = line.get("bm25_intersect") if isinstance(line.get("bm25_intersect"), dict) else None
+        gpu_rows = bm.pop("_gpu_rows", None) if bm else None
+        doc_len = bm.pop("_doc_len", None) if bm else None
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_base if cpu_base else {"value": None, "error": "parity scan skipped (--no-parity)"}
             try:
-                if isinstance(line.get("bm25_intersect"), dict) and line["bm25_intersect"].get("value"):
-                    line["bm25_intersect"]["cpu_baseline"] = cpu_postings_baseline(args.posting_docs, usable_cores())
+                if bm and bm.get("value"):
+                    cb = cpu_postings_baseline(args.posting_docs, usable_cores(), doc_len=doc_len, gpu_rows=gpu_rows)
+                    bm["parity_at_config"] = cb.pop("parity_at_config", None)
+                    bm["cpu_baseline"] = cb
             except Exception as e:  # the baseline is a reported side number; never fail the bench on it
-                line["bm25_intersect"]["cpu_baseline"] = {"value": None, "error": repr(e)}
+                bm["cpu_baseline"] = {"value": None, "error": repr(e)}
         print(json.dumps(line))
     env.close()
 
