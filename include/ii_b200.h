@@ -151,6 +151,11 @@ II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n);
 /* OR of n (1..16) posting lists — UnionFlat::read_full (RS/rqe_iterators/src/union_flat.rs:324-348)
  * run to EOF; quick_exit != 0 keeps docIds only (quick mode reports a single child, :433-524). */
 II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit);
+/* AND with NOT / OPTIONAL children — the "a -b" / "a ~b" query shapes (RS/rqe_iterators/src/not.rs, optional.rs as children of
+ * an Intersection): modes[i] 0 = required, 1 = NOT (docIds of lists[i] are excluded), 2 = OPTIONAL (never rejects; where
+ * the docId is present its freq is kept).  Excluded / absent children yield the reference's virtual results: freq 0, no
+ * contribution to any scorer (src/ext/default.c:289-297).  At least one child must be required. */
+II_ResultSet *II_IntersectEx(II_PostingList *const *lists, const int *modes, size_t n);
 size_t II_ResultSet_Len(const II_ResultSet *rs);
 void II_ResultSet_Free(II_ResultSet *rs);
 
@@ -241,6 +246,41 @@ II_TermCacheStats II_TermCache_GetStats(II_TermCache *cache);
 /* ---- QueryIterator facade ------------------------------------------------------------------------ */
 /* Takes ownership of `rs` (downloads docIds/scores once).  Free through it->Free(it). */
 II_QueryIterator *II_NewResultIterator(II_ResultSet *rs, double weight);
+
+/* ---- the reference's constructors and scorer extension on top of the device algebra ------------------------------------
+ * NewIntersectionIterator / NewUnionIterator carry the reference's exact signatures (RS/headers/iterators_ffi.h:309,594;
+ * `QueryIterator` == II_QueryIterator, layout-identical) and ownership rules: they take over the `its` array (freed with
+ * RedisModule_Free when the host exports it, else free) and every child.  Children may be B200 iterators (term leaves,
+ * NOT / OPTIONAL wrappers, nested results: they stay on the device) or FOREIGN iterators of the host (numeric, tag, geo ...
+ * leaves: drained once through Read() and uploaded).  The reduction rules of intersection.rs:363-417 / union_reducer.rs:30-66
+ * are applied (no children -> empty, NULL / empty child, wildcard stripping, single survivor returned as is).  The tree is
+ * evaluated on the device at construction; the returned iterator walks the finished result set.  Phrase constraints
+ * (max_slop >= 0, in_order) need term offsets on the device and are not taken: NULL is returned and the caller keeps the
+ * reference's iterator for that node. */
+II_QueryIterator *NewIntersectionIterator(II_QueryIterator **its, size_t num, int32_t max_slop, bool in_order, double weight);
+II_QueryIterator *NewUnionIterator(II_QueryIterator **its, int32_t num, bool quick_exit, double weight, int /* QueryNodeType */ type_,
+                                   const char *q_str, const void /* IteratorsConfig */ *config);
+II_QueryIterator *II_NewEmptyIterator(void);
+/* Term leaf over a device posting list (what NewInvIndIterator_TermQuery, iterators_ffi.h:404, yields): weight = the query
+ * node's weight, idf / bm25_idf = QueryTerm_GetIDF / QueryTerm_GetBM25_IDF of the term. */
+II_QueryIterator *II_NewTermIterator(II_PostingList *pl, int take_ownership, double weight, double idf, double bm25_idf);
+/* The same straight from the host's InvertedIndex*: its block accessors (inverted_index_ffi.h:102-132,286,387,425,444, plus
+ * IndexBlock_DataLen — INTEGRATION.md §2) are resolved in the host process with dlsym.  With a cache the decoded list is
+ * shared across queries, keyed by the index pointer and versioned by (gc_marker, num_entries). */
+II_QueryIterator *II_NewTermIterator_FromIndex(const void *inverted_index, II_Codec codec, double weight, double idf, double bm25_idf,
+                                               II_TermCache *cache);
+/* NOT / OPTIONAL over a B200 term leaf (iterators_ffi.h NewNotIterator / NewOptionalIterator without the QueryEvalCtx): as a
+ * child of NewIntersectionIterator they fuse into the membership kernel (exclusion / optional contribution). */
+II_QueryIterator *II_NewNotIterator(II_QueryIterator *child, t_docId max_doc_id, double weight);
+II_QueryIterator *II_NewOptionalIterator(II_QueryIterator *child, t_docId max_doc_id, double weight);
+/* Per-document metadata the *.B200 scorers read (one table per index spec; the default applies to iterators built afterwards). */
+void II_SetDefaultDocTable(const II_DocTable *docs);
+/* Scorer extension entry point: `redis-server --loadmodule redisearch.so EXTLOAD libii_b200.so` makes Extension_LoadDynamic
+ * (src/extension.c:121-145) dlsym this symbol; it registers BM25STD.B200, BM25.B200, TFIDF.B200, TFIDF.DOCNORM.B200,
+ * DOCSCORE.B200, BM25STD.TANH.B200 and DISMAX.B200 through ctx->RegisterScoringFunction (RSExtensionCtx, src/redisearch.h:282).
+ * Each is an RSScoringFunction (src/redisearch.h:277): called per result with the iterator's `current`, it scores the WHOLE
+ * result set on the device at the first call and returns the stored value afterwards. */
+int RS_ExtensionInit(void *rs_extension_ctx);
 
 /* ---- statistics for bench / roofline ---------------------------------------------------------------- */
 typedef struct {

@@ -646,8 +646,14 @@ __device__ __forceinline__ uint32_t select_keep(uint64_t *lists, int q, uint32_t
 //   kFixed   the admission threshold of every query is FIXED for the whole pass (thr_fixed[q], a distance, from the sample
 //            pass): every row with approximate distance < thr_fixed[q] is kept — no running threshold, no list compaction;
 //            a list that runs full sets overflow[q] (the query goes to the next tier).  fp32 route only (kOp 0 / 3).
+//   kSample  the sample pass: no lists at all — every thread keeps the smallest approximate distance it has seen in each of
+//            8 interleaved slices of its row range (chunk of the tile x tile parity) and publishes those 8 values as
+//            keep = 8 composites per (query, row range).  The k-th smallest of a query's lists x 8 minima is an upper
+//            bound of its k-th best distance over the sample (k distinct rows are at or below it), which is all the
+//            fixed bound needs.  (An earlier version ran the adaptive lists here: with ~10 tiles per CTA they never left
+//            their warm-up — 435 us for 1 % of the rows, ncu launch list profiles/r2c_launches.md.)
 //   tile_stride > 1: only every tile_stride-th row tile is visited (the sample pass)
-template <bool kDirect, int kEpl, int kOp, bool kFixed>
+template <bool kDirect, int kEpl, int kOp, int kMode>
 __global__ void __launch_bounds__(kCoarseThreads, 1)
 coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t *__restrict__ shadow, size_t row_pitch,
                     const uint8_t *__restrict__ q16, size_t q16_pitch, const float *__restrict__ row_norm2,
@@ -655,7 +661,8 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                     uint32_t num_kb, uint32_t tiles_total, uint32_t keep, uint32_t nstages, uint32_t csize, uint32_t nacc, uint32_t idesc,
                     uint64_t *__restrict__ list_scratch, uint64_t *__restrict__ cand_out, const uint32_t *__restrict__ nq_dev,
                     uint32_t tile_stride, const float *__restrict__ thr_fixed, uint32_t *__restrict__ overflow) {
-    static_assert(!kFixed || (!kDirect && (kOp == 0 || kOp == 3)), "fixed thresholds: fp32 route only");
+    constexpr bool kFixed = kMode == 1, kSample = kMode == 2;
+    static_assert(kMode == 0 || (!kDirect && (kOp == 0 || kOp == 3)), "fixed bound / sample pass: fp32 route only");
     constexpr int kQListCap = kEpl * 32;
     if (nq_dev) { // second tier: the number of live queries is only known on the device; nothing to do = every CTA leaves
         nq = min(nq, *nq_dev);
@@ -862,6 +869,11 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         if constexpr (kOp == 2) nq_norm = q < nq ? *reinterpret_cast<const float *>(q16 + (size_t)q * q16_pitch + dim) : 1.0f;
         if constexpr (kOp == 3) nq_norm = q < nq ? q_norm2[q] : 0.0f; // |q|^2
         bool ovf = false;
+        float smax[2][kQN / 32]; // kSample: running maxima of the pre-test value per slice (largest = smallest distance)
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+            for (int h = 0; h < kQN / 32; h++) smax[x][h] = -__int_as_float(0x7f800000);
         if constexpr (kFixed) {
             // fixed admission bound (a distance): keep every row with approximate distance < T
             const float T = q < nq ? thr_fixed[q] : -__int_as_float(0x7f800000);
@@ -906,6 +918,36 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
             for (int h = 0; h < kQN / 32; h++) {
                 const uint32_t row0 = tile * kQN + h * 32;
                 uint32_t pass_pre = 0;
+                if constexpr (kSample) {
+                    // largest dot (cosine / inner product) or largest dot - |row|^2 / 2 (squared L2) of the chunk
+                    float mx = -__int_as_float(0x7f800000);
+                    const bool tail = row0 + 32 > n_rows; // rows past the end (zero fill / stale shadow bytes) must not count
+                    if constexpr (kOp == 0) {
+                        if (!tail) {
+                            float m8[8];
+#pragma unroll
+                            for (int g = 0; g < 8; g++)
+                                m8[g] = fmaxf(fmaxf(__uint_as_float(v[h][4 * g]), __uint_as_float(v[h][4 * g + 1])),
+                                              fmaxf(__uint_as_float(v[h][4 * g + 2]), __uint_as_float(v[h][4 * g + 3])));
+                            mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (row0 + j < n_rows) mx = fmaxf(mx, __uint_as_float(v[h][j]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float u = fmaf(__shfl_sync(0xFFFFFFFFu, nrm[h], j), -0.5f, __uint_as_float(v[h][j]));
+                            if (!tail || row0 + j < n_rows) mx = fmaxf(mx, u);
+                        }
+                    }
+                    if (i & 1u)
+                        smax[1][h] = fmaxf(smax[1][h], mx);
+                    else
+                        smax[0][h] = fmaxf(smax[0][h], mx);
+                    continue;
+                }
                 if constexpr (kFixed) {
                     // With a fixed bound only ~k * (rows / sample rows) rows of the whole corpus pass: one 3-input max tree
                     // over the 32 values (16 instructions) and ONE compare decide the common case
@@ -1011,7 +1053,24 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         if constexpr (kFixed) {
             if (ovf && q < nq) overflow[q] = 1u;
         }
-        for (int src = 0; src < 32; src++) {
+        if constexpr (kSample) { // keep == 8: the slice minima as composites (the row id is not needed by threshold_kernel)
+            if (q < nq) {
+                uint64_t *dst = cand_out + ((size_t)q * gridDim.x + blockIdx.x) * keep;
+#pragma unroll
+                for (int x = 0; x < 2; x++)
+#pragma unroll
+                    for (int h = 0; h < kQN / 32; h++) {
+                        const float m = smax[x][h];
+                        uint64_t c = kEmptySlot;
+                        if (m > -__int_as_float(0x7f800000)) {
+                            const float d = kOp == 0 ? 1.0f - m : __fsub_rn(nq_norm, __fmul_rn(2.0f, m));
+                            c = (uint64_t)orderable_key(d) << 32;
+                        }
+                        if ((uint32_t)(x * (kQN / 32) + h) < keep) dst[x * (kQN / 32) + h] = c;
+                    }
+            }
+        }
+        for (int src = 0; src < (kSample ? 0 : 32); src++) {
             uint32_t c = __shfl_sync(0xFFFFFFFFu, cnt, src);
             const uint32_t qq = q_base + ew * 32 + src;
             if (c > keep) {
@@ -1312,18 +1371,19 @@ static uint32_t qtmem_nacc() {
     }
     return (uint32_t)v;
 }
-static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl, bool int_cos, bool fixed = false) {
+static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl, bool int_cos, int mode = 0) {
     if (kind == CoarseDirect16)
-        return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 0, false> : (const void *)coarse_qtmem_kernel<true, 8, 0, false>;
+        return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 0, 0> : (const void *)coarse_qtmem_kernel<true, 8, 0, 0>;
     if (kind == CoarseDirect8) {
-        if (int_cos) return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 2, false> : (const void *)coarse_qtmem_kernel<true, 8, 2, false>;
-        return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 1, false> : (const void *)coarse_qtmem_kernel<true, 8, 1, false>;
+        if (int_cos) return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 2, 0> : (const void *)coarse_qtmem_kernel<true, 8, 2, 0>;
+        return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 1, 0> : (const void *)coarse_qtmem_kernel<true, 8, 1, 0>;
     }
-    // fp32 route (shadow rows): the flag selects the squared-L2 epilogue; epl 8 = lists of up to 128 (second tier, k > 16);
-    // fixed = admission bound from the sample pass, lists of 96 without compaction
-    if (fixed) return int_cos ? (const void *)coarse_qtmem_kernel<false, 3, 3, true> : (const void *)coarse_qtmem_kernel<false, 3, 0, true>;
-    if (int_cos) return epl == 3 ? (const void *)coarse_qtmem_kernel<false, 3, 3, false> : (const void *)coarse_qtmem_kernel<false, 8, 3, false>;
-    return epl == 3 ? (const void *)coarse_qtmem_kernel<false, 3, 0, false> : (const void *)coarse_qtmem_kernel<false, 8, 0, false>;
+    // fp32 route (shadow rows): the flag selects the squared-L2 epilogue; epl 8 = lists of up to 128 (second tier);
+    // mode 1 = fixed admission bound (lists of 96, no compaction), mode 2 = the sample pass (slice minima only)
+    if (mode == 1) return int_cos ? (const void *)coarse_qtmem_kernel<false, 3, 3, 1> : (const void *)coarse_qtmem_kernel<false, 3, 0, 1>;
+    if (mode == 2) return int_cos ? (const void *)coarse_qtmem_kernel<false, 3, 3, 2> : (const void *)coarse_qtmem_kernel<false, 3, 0, 2>;
+    if (int_cos) return epl == 3 ? (const void *)coarse_qtmem_kernel<false, 3, 3, 0> : (const void *)coarse_qtmem_kernel<false, 8, 3, 0>;
+    return epl == 3 ? (const void *)coarse_qtmem_kernel<false, 3, 0, 0> : (const void *)coarse_qtmem_kernel<false, 8, 0, 0>;
 }
 static size_t qtmem_fixed_smem(uint32_t num_kb) {
     const uint32_t kb_t = (512u - qtmem_nacc() * kQN) / 32u;
@@ -1365,11 +1425,11 @@ bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind k
 }
 
 CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32_t k, uint32_t keep_override, uint32_t tile_stride,
-                       bool fixed) {
+                       int mode) {
     CoarsePlan p{};
     p.kind = kind;
     p.tile_stride = std::max(1u, tile_stride);
-    p.fixed = fixed && kind == CoarseF16;
+    p.mode = kind == CoarseF16 ? mode : 0;
     if (kind == CoarseF16 || kind == CoarseDirect16 || kind == CoarseDirect8) {
         p.num_kb = kind == CoarseDirect8 ? (c.dim + 127) / 128 : (c.dim + 63) / 64;
         p.tiles = ((c.n_rows + kQN - 1) / kQN + p.tile_stride - 1) / p.tile_stride; // row tiles this pass visits
@@ -1381,7 +1441,8 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32
         p.keep = kind == CoarseF16 ? (keep_override ? keep_override : (k <= kCoarseTier1MaxK ? kCoarseKeep : kCoarseKeepWide))
                                    : (k <= 32 ? 32u : 128u);
         p.epl = p.keep <= 32 ? 3 : 8;
-        if (p.fixed) p.keep = kCoarseFixedCap, p.epl = 3; // every row below the bound, up to the list capacity
+        if (p.mode == 1) p.keep = kCoarseFixedCap, p.epl = 3; // every row below the bound, up to the list capacity
+        if (p.mode == 2) p.keep = kCoarseSampleSlices, p.epl = 3; // the slice minima
         p.stages = (uint32_t)std::min<size_t>(kQMaxStages, (kSmemLimit - qtmem_fixed_smem(p.num_kb)) / kQStageBytes);
         p.smem_bytes = qtmem_fixed_smem(p.num_kb) + (size_t)p.stages * kQStageBytes;
         // the query groups of a row range form a thread-block cluster (multicast of the row tiles)
@@ -1396,7 +1457,7 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32
                 p.csize = cs;
                 break;
             }
-        const void *kfn = qtmem_kernel_fn(kind, p.epl, kind == CoarseF16 ? c.metric == MT_L2 : c.metric == MT_COS, p.fixed);
+        const void *kfn = qtmem_kernel_fn(kind, p.epl, kind == CoarseF16 ? c.metric == MT_L2 : c.metric == MT_COS, p.mode);
         if (p.csize > 1) {
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
             cudaLaunchConfig_t cfg{};
@@ -1451,8 +1512,8 @@ static cudaError_t launch_coarse_t(const void *rows, size_t pitch, uint32_t n_ro
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
                           uint64_t *d_scratch, cudaStream_t s, const uint32_t *d_nq_dev, const float *d_thr_fixed, uint32_t *d_overflow) {
     if (p.kind == CoarseF16 || p.kind == CoarseDirect16 || p.kind == CoarseDirect8) {
-        if (p.fixed && (!d_thr_fixed || !d_overflow)) return cudaErrorInvalidValue;
-        const void *kfn = qtmem_kernel_fn(p.kind, p.epl, o.int_cosine != 0, p.fixed); // (CoarseF16: the flag selects the L2 epilogue)
+        if (p.mode == 1 && (!d_thr_fixed || !d_overflow)) return cudaErrorInvalidValue;
+        const void *kfn = qtmem_kernel_fn(p.kind, p.epl, o.int_cosine != 0, p.mode); // (CoarseF16: the flag selects the L2 epilogue)
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
         if (e != cudaSuccess) return e;
         CUtensorMap mr{};

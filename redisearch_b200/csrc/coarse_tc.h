@@ -10,6 +10,7 @@ constexpr uint32_t kCoarseKeep = 24;       // candidates kept per (CTA row range
 constexpr uint32_t kCoarseKeepWide = 128;  // second tier (queries the first proof left open) and first tier of k > 16
 constexpr uint32_t kCoarseTier1MaxK = 16;  // largest k the 24-entry lists serve
 constexpr uint32_t kCoarseMaxK = 128;      // largest k served by the coarse path
+constexpr uint32_t kCoarseSampleSlices = 8; // minima the sample pass publishes per (query, row range)
 constexpr uint32_t kCoarseFixedCap = 96;   // list capacity of the fixed-bound main pass (rows below the bound per row range)
 // |approx - exact| bounds for unit vectors (Cauchy-Schwarz over the dot product: sum |a_i b_i| <= 1):
 //  TF32: each operand truncated to 11 significant bits -> 2 * 2^-10 relative per product, + accumulation slack;
@@ -28,7 +29,7 @@ struct CoarsePlan {
     uint32_t stages; // depth of the row-tile ring in shared memory
     uint32_t epl;    // candidate-list entries per lane of the compacting warp (3 or 8)
     uint32_t tile_stride; // 1 = every row tile; n = every n-th (the sample pass)
-    bool fixed;      // fixed admission bound per query (CoarseF16 main pass) instead of adaptive top-`keep` lists
+    int mode;        // CoarseF16: 0 adaptive top-`keep` lists, 1 fixed admission bound per query (main pass), 2 sample pass (slice minima)
     uint32_t csize;  // thread-block cluster size along y (query groups sharing multicast row tiles); 1 = none
     size_t cand_elems; // uint64 per (query, list, keep)
     size_t scratch_elems; // uint64 of per-CTA candidate-list scratch (CoarseF16), 0 otherwise
@@ -50,7 +51,7 @@ struct CoarseOperands {
 bool coarse_supported(const CorpusView &c, uint32_t nq, uint32_t k, CoarseKind kind);
 // keep_override != 0 (CoarseF16 only): candidates per list instead of the default for k
 CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32_t k, uint32_t keep_override = 0, uint32_t tile_stride = 1,
-                       bool fixed = false);
+                       int mode = 0);
 // d_nq_dev (nullable): the number of live queries is read from device memory (min with nq); 0 = the kernel exits at once
 cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim, uint32_t nq, const CoarsePlan &p, uint64_t *d_cand,
                           uint64_t *d_scratch, cudaStream_t s, const uint32_t *d_nq_dev = nullptr, const float *d_thr_fixed = nullptr,

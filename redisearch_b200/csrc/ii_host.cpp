@@ -3,6 +3,8 @@
 #include "../../include/ii_b200.h"
 #include "ii_kernels.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -600,21 +602,25 @@ namespace {
 
 // Enqueue the kernels of an intersection on ctx().stream.  On return rs->d_len holds (will hold, in
 // stream order) the number of hits; rs->len is NOT set.  *trivially_empty = an input list is empty.
-bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_ResultSet *rs, bool *trivially_empty) {
-    // Intersection::new: stable sort ascending by num_estimated (leaf weight 1.0), intersection.rs:110-145
+// modes (nullable): per list 0 = required, 1 = NOT, 2 = OPTIONAL (IntersectArgs::mode); at least one list is required
+bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_ResultSet *rs, bool *trivially_empty, const int *modes = nullptr) {
+    auto mode_of = [&](size_t i) { return modes ? modes[i] : 0; };
+    // Intersection::new: stable sort ascending by num_estimated (leaf weight 1.0), intersection.rs:110-145; NOT / OPTIONAL
+    // children estimate max_doc_id (not.rs / optional.rs num_estimated): they sort behind every term, in their given order
     std::vector<uint32_t> order(n);
     for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
-    std::stable_sort(order.begin(), order.end(),
-                     [&](uint32_t a, uint32_t b) { return lists[a]->estimated < lists[b]->estimated; });
-    // the kernel is driven by the list with the fewest actual entries (a field-mask filter may make
+    auto est = [&](uint32_t a) { return mode_of(a) ? (size_t)1 << 62 : lists[a]->estimated; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return est(a) < est(b); });
+    // the kernel is driven by the REQUIRED list with the fewest actual entries (a field-mask filter may make
     // that differ from the estimate order); the aggregate child order stays the reference's
-    size_t drv = 0;
-    for (size_t i = 1; i < n; i++)
-        if (lists[order[i]]->n < lists[order[drv]]->n) drv = i;
+    size_t drv = n;
+    for (size_t i = 0; i < n; i++)
+        if (mode_of(order[i]) == 0 && (drv == n || lists[order[i]]->n < lists[order[drv]]->n)) drv = i;
+    if (drv == n) return false;
     rs->n_children = (uint32_t)n;
     for (size_t i = 0; i < n; i++) rs->child_order[i] = order[i];
     *trivially_empty = false;
-    for (size_t i = 0; i < n; i++) *trivially_empty |= lists[i]->n == 0;
+    for (size_t i = 0; i < n; i++) *trivially_empty |= mode_of(i) == 0 && lists[i]->n == 0;
     if (*trivially_empty) return true;
     const II_PostingList *A = lists[order[drv]];
     const uint32_t nchunks = (uint32_t)((A->n + kIIChunk - 1) / kIIChunk);
@@ -643,6 +649,7 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
         for (size_t i = 0; i < n; i++) {
             a.ids[i] = lists[order[korder[i]]]->d_ids;
             a.len[i] = (uint32_t)lists[order[korder[i]]]->n;
+            a.mode[i] = (uint8_t)mode_of(order[korder[i]]);
         }
         a.tmp_idx = tmp_idx;
         a.tmp_pos = tmp_pos;
@@ -660,7 +667,10 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
         ga.stride = stride;
         ga.out_doc = rs->d_docs;
         ga.fstride = rs->cap;
-        for (size_t k = 0; k < n; k++) ga.freqs[k] = lists[order[korder[k]]]->d_freqs;
+        for (size_t k = 0; k < n; k++) {
+            ga.freqs[k] = lists[order[korder[k]]]->d_freqs;
+            ga.mode[k] = (uint8_t)mode_of(order[korder[k]]);
+        }
         // rows are produced in kernel-slot order, then placed at their aggregate child index
         ga.out_freq = (n > 1) ? scratch : rs->d_freqs;
         ok = ok && ii_launch_gather(ga, nchunks, c.stream) == cudaSuccess;
@@ -850,6 +860,28 @@ II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n) {
     auto *rs = new II_ResultSet();
     bool empty = false;
     bool ok = intersect_enqueue(c, lists, n, rs, &empty);
+    if (ok && !empty) {
+        ok = cudaMemcpyAsync(c.h_total, rs->d_len, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+        if (ok) finish_len(c, rs);
+    }
+    if (!ok) {
+        delete rs;
+        return nullptr;
+    }
+    return rs;
+}
+
+// AND with NOT / OPTIONAL children: modes[i] 0 = required, 1 = NOT (docIds of lists[i] are excluded), 2 = OPTIONAL (never
+// rejects; its freq is kept where present).  The excluded / absent children yield virtual results (freq 0, score 0).
+II_ResultSet *II_IntersectEx(II_PostingList *const *lists, const int *modes, size_t n) {
+    if (n == 0 || n > (size_t)kIIMaxLists) return nullptr;
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    auto *rs = new II_ResultSet();
+    bool empty = false;
+    bool ok = intersect_enqueue(c, lists, n, rs, &empty, modes);
     if (ok && !empty) {
         ok = cudaMemcpyAsync(c.h_total, rs->d_len, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
         ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
@@ -1219,7 +1251,7 @@ int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const siz
     // ---- per-query kernel chains on the stream pool: query i+1 is enqueued while query i runs, a slot is only
     // synchronised when it is needed again
     PendingSearch pend[kBatchSlots];
-    size_t owner[kBatchSlots];
+    size_t owner[kBatchSlots] = {0};
     auto finish = [&](size_t sl) {
         CtxScope scope(&pool.slot[sl]);
         const size_t qi = owner[sl];
@@ -1493,6 +1525,508 @@ II_QueryIterator *II_NewResultIterator(II_ResultSet *rs, double weight) {
         return nullptr;
     }
     return &it->base;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The reference's iterator constructors (RS/headers/iterators_ffi.h:309,594) and scorer extension entry point
+// (src/extension.c:121-145, src/redisearch.h:277-287) on top of the device algebra.
+//
+// Children may be (a) our own iterators — term leaves (II_NewTermIterator*), NOT / OPTIONAL wrappers, results of a nested
+// AND / OR built here — which stay on the device, or (b) FOREIGN iterators (anything with the QueryIterator vtable: numeric,
+// tag, geo ... leaves of RediSearch): those are drained through Read() once, their docIds / freqs uploaded, and take part
+// as one more device list.  The iterator tree is evaluated eagerly at construction (a few kernels + one synchronisation);
+// the returned iterator walks the finished result set and carries, in `current`, the back-pointer the registered scoring
+// functions need to return a score computed ON THE DEVICE for the whole result set at the first call.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr uint64_t kNodeMagic = 0xB200D15C0FFEE5ull;
+const II_DocTable *g_default_docs = nullptr;
+
+enum NodeKind { NODE_LEAF = 0, NODE_RESULT = 1, NODE_EMPTY = 2 };
+enum LeafMode { LEAF_REQUIRED = 0, LEAF_NOT = 1, LEAF_OPTIONAL = 2 };
+
+struct NodeIter {
+    II_QueryIterator base; // MUST be first
+    uint64_t magic = kNodeMagic;
+    NodeKind kind = NODE_EMPTY;
+    // leaf
+    II_PostingList *pl = nullptr;
+    bool owns_pl = false;
+    II_TermCache *cache = nullptr; // non-NULL: pl is pinned in this cache (released, not freed)
+    II_TermParams term{1.0, 0.0, 0.0};
+    LeafMode mode = LEAF_REQUIRED;
+    uint64_t max_doc_id = 0; // NOT / OPTIONAL: the universe is 1..max_doc_id
+    // result of an evaluated AND / OR (or a leaf that is read directly)
+    II_ResultSet *rs = nullptr;
+    std::vector<II_TermParams> terms; // per child, in the order of the constructor's `its`
+    double agg_weight = 1.0;
+    int scored_with = -1; // II_Scorer the host score array holds
+    const II_DocTable *docs = nullptr;
+    // host cursor
+    bool host_ready = false;
+    std::vector<uint64_t> ids;
+    std::vector<double> scores;
+    std::vector<uint32_t> freq_sum;
+    size_t pos = 0;
+    II_IndexResult res;
+    ~NodeIter() {
+        if (pl) {
+            if (cache)
+                II_TermCache_Release(cache, 1, &pl);
+            else if (owns_pl)
+                delete pl;
+        }
+        delete rs;
+    }
+};
+inline NodeIter *NI(II_QueryIterator *b) { return reinterpret_cast<NodeIter *>(b); }
+inline bool is_node(const II_QueryIterator *b) { return b && reinterpret_cast<const NodeIter *>(b)->magic == kNodeMagic && b->Free != nullptr; }
+
+void host_free(void *p) { // `its` arrays come from the Redis allocator
+    static void (**rm_free)(void *) = reinterpret_cast<void (**)(void *)>(dlsym(RTLD_DEFAULT, "RedisModule_Free"));
+    if (rm_free && *rm_free)
+        (*rm_free)(p);
+    else
+        free(p);
+}
+
+// a leaf that is read directly (single-term query: the reducers hand the child back) becomes a 1-child result
+bool node_materialise(NodeIter *it) {
+    if (it->kind == NODE_LEAF && !it->rs) {
+        II_PostingList *one[1] = {it->pl};
+        it->rs = II_Union(one, 1, 0);
+        if (!it->rs) return false;
+        it->terms.assign(1, it->term);
+        it->agg_weight = 1.0;
+    }
+    return true;
+}
+bool node_host(NodeIter *it) {
+    if (it->host_ready) return true;
+    if (it->kind == NODE_EMPTY) {
+        it->host_ready = true;
+        return true;
+    }
+    if (!node_materialise(it) || !it->rs) return false;
+    const size_t m = it->rs->len;
+    it->ids.resize(m);
+    it->scores.assign(m, 0.0);
+    if (II_ResultSet_Fetch(it->rs, it->ids.data(), nullptr, nullptr) != 0) return false;
+    if (it->rs->has_freqs && m) {
+        std::vector<uint32_t> fr((size_t)it->rs->n_children * m);
+        if (II_ResultSet_Fetch(it->rs, nullptr, nullptr, fr.data()) != 0) return false;
+        it->freq_sum.assign(m, 0);
+        for (uint32_t ch = 0; ch < it->rs->n_children; ch++)
+            for (size_t i = 0; i < m; i++) it->freq_sum[i] += fr[(size_t)ch * m + i];
+    }
+    it->host_ready = true;
+    return true;
+}
+void node_publish(NodeIter *it, size_t i) {
+    it->res.docId = it->ids[i];
+    it->res.freq = it->freq_sum.empty() ? 1u : it->freq_sum[i];
+    it->res.data.metric = it->scores[i];
+    it->base.lastDocId = it->ids[i];
+    it->base.current = &it->res;
+}
+size_t node_num_estimated(const II_QueryIterator *b) {
+    const NodeIter *it = reinterpret_cast<const NodeIter *>(b);
+    if (it->kind == NODE_EMPTY) return 0;
+    if (it->rs) return it->rs->len;
+    if (it->mode != LEAF_REQUIRED) return (size_t)it->max_doc_id; // not.rs / optional.rs num_estimated = max_doc_id
+    return it->pl ? it->pl->estimated : 0;
+}
+IteratorStatus node_read(II_QueryIterator *b) {
+    NodeIter *it = NI(b);
+    if (!node_host(it) || it->pos >= it->ids.size()) {
+        b->atEOF = true;
+        b->current = nullptr;
+        return ITERATOR_EOF;
+    }
+    node_publish(it, it->pos++);
+    return ITERATOR_OK;
+}
+IteratorStatus node_skip_to(II_QueryIterator *b, t_docId doc) {
+    NodeIter *it = NI(b);
+    if (!node_host(it)) {
+        b->atEOF = true;
+        b->current = nullptr;
+        return ITERATOR_EOF;
+    }
+    auto lb = std::lower_bound(it->ids.begin() + it->pos, it->ids.end(), doc);
+    if (lb == it->ids.end()) {
+        it->pos = it->ids.size();
+        b->atEOF = true;
+        b->current = nullptr;
+        return ITERATOR_EOF;
+    }
+    const size_t i = (size_t)(lb - it->ids.begin());
+    node_publish(it, i);
+    it->pos = i + 1;
+    return *lb == doc ? ITERATOR_OK : ITERATOR_NOTFOUND;
+}
+ValidateStatus node_revalidate(II_QueryIterator *, struct IndexSpec *) { return VALIDATE_OK; } // a snapshot never moves
+void node_rewind(II_QueryIterator *b) {
+    NodeIter *it = NI(b);
+    it->pos = 0;
+    b->atEOF = false;
+    b->lastDocId = 0;
+    b->current = nullptr;
+}
+void node_free(II_QueryIterator *b) { delete NI(b); }
+
+NodeIter *new_node(NodeKind kind, uint32_t type, double weight) {
+    auto *it = new NodeIter();
+    memset(&it->base, 0, sizeof(it->base));
+    memset(&it->res, 0, sizeof(it->res));
+    it->kind = kind;
+    it->base.type = type;
+    it->base.NumEstimated = node_num_estimated;
+    it->base.Read = node_read;
+    it->base.SkipTo = node_skip_to;
+    it->base.Revalidate = node_revalidate;
+    it->base.Free = node_free;
+    it->base.Rewind = node_rewind;
+    it->res.data.tag = II_ResultData_Metric;
+    it->res.weight = weight;
+    it->res.fieldMask = ~(unsigned __int128)0; // RS_FIELDMASK_ALL
+    // back-pointer for the scoring functions: bytes the Metric variant of the reference's result union does not use
+    memcpy(it->res.data._rest, &kNodeMagic, 8);
+    NodeIter *self = it;
+    memcpy(it->res.data._rest + 8, &self, 8);
+    it->docs = g_default_docs;
+    if (kind == NODE_EMPTY) it->base.atEOF = false;
+    return it;
+}
+
+// a FOREIGN iterator -> device posting list (docIds ascending as the contract guarantees; freq = current->freq)
+II_PostingList *drain_foreign(II_QueryIterator *f) {
+    std::vector<uint64_t> ids;
+    std::vector<uint32_t> freqs;
+    if (f->Rewind) f->Rewind(f);
+    while (f->Read(f) == ITERATOR_OK) {
+        ids.push_back(f->lastDocId);
+        freqs.push_back(f->current ? f->current->freq : 1u);
+    }
+    return II_PostingList_FromArrays(ids.data(), freqs.data(), ids.size());
+}
+
+struct ChildView { // what the algebra needs from a child
+    II_PostingList *pl = nullptr;
+    bool temp = false; // built here (foreign / nested result): freed after the evaluation
+    LeafMode mode = LEAF_REQUIRED;
+    II_TermParams term{1.0, 1.0, 1.0};
+};
+bool child_view(II_QueryIterator *c, ChildView &v) {
+    if (is_node(c)) {
+        NodeIter *n = NI(c);
+        if (n->kind == NODE_LEAF) {
+            v.pl = n->pl;
+            v.mode = n->mode;
+            v.term = n->term;
+            return v.pl != nullptr;
+        }
+        if (n->kind == NODE_RESULT && n->rs) { // nested AND / OR: its docIds, freq = sum over its children
+            if (!node_host(n)) return false;
+            std::vector<uint32_t> fr(n->ids.size(), 1u);
+            for (size_t i = 0; i < fr.size() && i < n->freq_sum.size(); i++) fr[i] = n->freq_sum[i];
+            v.pl = II_PostingList_FromArrays(n->ids.data(), fr.data(), n->ids.size());
+            v.temp = true;
+            v.term = II_TermParams{n->agg_weight, 1.0, 1.0};
+            return v.pl != nullptr;
+        }
+        return false;
+    }
+    v.pl = drain_foreign(c);
+    v.temp = true;
+    return v.pl != nullptr;
+}
+bool child_is_empty(const II_QueryIterator *c) {
+    if (!c) return true;
+    if (c->type == II_IteratorType_Empty) return true;
+    if (is_node(c)) {
+        const NodeIter *n = reinterpret_cast<const NodeIter *>(c);
+        if (n->kind == NODE_EMPTY) return true;
+        if (n->kind == NODE_LEAF && n->mode == LEAF_REQUIRED && n->pl && n->pl->n == 0) return true;
+        if (n->kind == NODE_RESULT && n->rs && n->rs->len == 0) return true;
+    }
+    return false;
+}
+} // namespace
+
+void II_SetDefaultDocTable(const II_DocTable *docs) { g_default_docs = docs; }
+
+II_QueryIterator *II_NewEmptyIterator(void) { return &new_node(NODE_EMPTY, II_IteratorType_Empty, 1.0)->base; }
+
+II_QueryIterator *II_NewTermIterator(II_PostingList *pl, int take_ownership, double weight, double idf, double bm25_idf) {
+    if (!pl) return nullptr;
+    NodeIter *it = new_node(NODE_LEAF, 1 /* IteratorType_InvIdxTerm */, weight);
+    it->pl = pl;
+    it->owns_pl = take_ownership != 0;
+    it->term = II_TermParams{weight, idf, bm25_idf};
+    return &it->base;
+}
+
+// Term leaf straight from the host's InvertedIndex: the block accessors of RS/headers/inverted_index_ffi.h:102-132,286,387,425,444
+// are resolved in the host process at first use (+ IndexBlock_DataLen, the one accessor the FFI does not have yet — three lines
+// of Rust).  With a cache the decoded list is shared between queries and revalidated by
+// (gc_marker, num_entries).
+II_QueryIterator *II_NewTermIterator_FromIndex(const void *inverted_index, II_Codec codec, double weight, double idf, double bm25_idf,
+                                               II_TermCache *cache) {
+    struct Api {
+        size_t (*NumBlocks)(const void *) = nullptr;
+        const void *(*BlockRef)(const void *, size_t) = nullptr;
+        const char *(*Data)(const void *) = nullptr;
+        size_t (*DataLen)(const void *) = nullptr;
+        uint64_t (*FirstId)(const void *) = nullptr;
+        uint64_t (*LastId)(const void *) = nullptr;
+        uint16_t (*NumEntries)(const void *) = nullptr;
+        uint32_t (*GcMarker)(const void *) = nullptr;
+        size_t (*IndexEntries)(const void *) = nullptr;
+        bool ok = false;
+    };
+    static Api api = [] {
+        Api a;
+        a.NumBlocks = reinterpret_cast<decltype(a.NumBlocks)>(dlsym(RTLD_DEFAULT, "InvertedIndex_NumBlocks"));
+        a.BlockRef = reinterpret_cast<decltype(a.BlockRef)>(dlsym(RTLD_DEFAULT, "InvertedIndex_BlockRef"));
+        a.Data = reinterpret_cast<decltype(a.Data)>(dlsym(RTLD_DEFAULT, "IndexBlock_Data"));
+        a.DataLen = reinterpret_cast<decltype(a.DataLen)>(dlsym(RTLD_DEFAULT, "IndexBlock_DataLen"));
+        a.FirstId = reinterpret_cast<decltype(a.FirstId)>(dlsym(RTLD_DEFAULT, "IndexBlock_FirstId"));
+        a.LastId = reinterpret_cast<decltype(a.LastId)>(dlsym(RTLD_DEFAULT, "IndexBlock_LastId"));
+        a.NumEntries = reinterpret_cast<decltype(a.NumEntries)>(dlsym(RTLD_DEFAULT, "IndexBlock_NumEntries"));
+        a.GcMarker = reinterpret_cast<decltype(a.GcMarker)>(dlsym(RTLD_DEFAULT, "InvertedIndex_GcMarker"));
+        a.IndexEntries = reinterpret_cast<decltype(a.IndexEntries)>(dlsym(RTLD_DEFAULT, "InvertedIndex_NumEntries"));
+        a.ok = a.NumBlocks && a.BlockRef && a.Data && a.DataLen && a.FirstId && a.LastId && a.NumEntries;
+        return a;
+    }();
+    if (!api.ok || !inverted_index) {
+        fprintf(stderr, "ii_b200: the host process does not export the InvertedIndex block accessors (inverted_index_ffi.h + IndexBlock_DataLen)\n");
+        return nullptr;
+    }
+    const size_t nb = api.NumBlocks(inverted_index);
+    std::vector<II_BlockView> views(nb);
+    for (size_t b = 0; b < nb; b++) {
+        const void *blk = api.BlockRef(inverted_index, b);
+        views[b] = II_BlockView{api.FirstId(blk), api.LastId(blk), api.NumEntries(blk), reinterpret_cast<const uint8_t *>(api.Data(blk)), api.DataLen(blk)};
+    }
+    II_PostingList *pl = nullptr;
+    if (cache) {
+        const uint64_t key = (uint64_t)(uintptr_t)inverted_index;
+        const uint64_t version = ((uint64_t)(api.GcMarker ? api.GcMarker(inverted_index) : 0) << 32) ^ (uint64_t)(api.IndexEntries ? api.IndexEntries(inverted_index) : nb);
+        const II_BlockView *bl[1] = {views.data()};
+        const size_t nbs[1] = {nb};
+        II_TermCache_Acquire(cache, 1, &key, &version, bl, nbs, codec, &pl);
+    } else {
+        pl = II_PostingList_FromBlocks(views.data(), nb, codec, 0, 1);
+    }
+    if (!pl) return nullptr;
+    II_QueryIterator *it = II_NewTermIterator(pl, cache ? 0 : 1, weight, idf, bm25_idf);
+    if (it && cache) NI(it)->cache = cache;
+    return it;
+}
+
+// NOT / OPTIONAL over one of OUR term leaves (RS/rqe_iterators/src/not.rs, optional.rs): inside an AND they become an
+// exclusion / an optional contribution of the membership kernel; read on their own they walk 1..max_doc_id.
+II_QueryIterator *II_NewNotIterator(II_QueryIterator *child, t_docId max_doc_id, double weight) {
+    if (child_is_empty(child)) { // NOT of nothing = every document: needs the universe, which only the host's wildcard iterator has
+        if (child && child->Free) child->Free(child);
+        return nullptr;
+    }
+    if (!is_node(child) || NI(child)->kind != NODE_LEAF || NI(child)->mode != LEAF_REQUIRED) return nullptr;
+    NodeIter *n = NI(child);
+    n->mode = LEAF_NOT;
+    n->max_doc_id = max_doc_id;
+    n->base.type = 8; // IteratorType_Not
+    n->res.weight = weight;
+    n->term.weight = 0.0; // a NOT child contributes a virtual result: nothing to the score (default.c:289-297)
+    return child;
+}
+II_QueryIterator *II_NewOptionalIterator(II_QueryIterator *child, t_docId max_doc_id, double weight) {
+    if (!is_node(child) || NI(child)->kind != NODE_LEAF || NI(child)->mode != LEAF_REQUIRED) return nullptr;
+    NodeIter *n = NI(child);
+    n->mode = LEAF_OPTIONAL;
+    n->max_doc_id = max_doc_id;
+    n->base.type = 10; // IteratorType_Optional
+    n->res.weight = weight;
+    n->term.weight = weight; // optional.rs:260: the weight is applied to real hits only; misses are virtual (score 0)
+    return child;
+}
+
+static II_QueryIterator *build_aggregate(II_QueryIterator **its, size_t num, bool is_union, bool quick_exit, double weight) {
+    auto free_children = [&] {
+        for (size_t i = 0; i < num; i++)
+            if (its[i] && its[i]->Free) its[i]->Free(its[i]);
+        host_free(its);
+    };
+    // reduction rules (intersection.rs:363-417, union_reducer.rs:30-66)
+    std::vector<II_QueryIterator *> kids;
+    for (size_t i = 0; i < num; i++) {
+        II_QueryIterator *c = its[i];
+        const bool wildcard = c && (c->type == 12 /* Wildcard */ || c->type == 2 /* InvIdxWildcard */);
+        if (!is_union) {
+            if (child_is_empty(c)) { // any empty child -> the AND is empty
+                free_children();
+                return II_NewEmptyIterator();
+            }
+            if (wildcard) continue; // stripped (every document matches)
+        } else if (child_is_empty(c)) {
+            continue; // dropped
+        }
+        kids.push_back(c);
+    }
+    if (kids.empty()) {
+        // all wildcards -> the last one is returned (AND); nothing left -> empty (OR)
+        II_QueryIterator *keep = nullptr;
+        if (!is_union)
+            for (size_t i = num; i-- > 0;)
+                if (its[i]) {
+                    keep = its[i];
+                    break;
+                }
+        for (size_t i = 0; i < num; i++)
+            if (its[i] && its[i] != keep && its[i]->Free) its[i]->Free(its[i]);
+        host_free(its);
+        return keep ? keep : II_NewEmptyIterator();
+    }
+    if (kids.size() == 1 && !(is_node(kids[0]) && NI(kids[0])->mode == LEAF_NOT)) { // one survivor -> the child itself
+        II_QueryIterator *keep = kids[0];
+        for (size_t i = 0; i < num; i++)
+            if (its[i] && its[i] != keep && its[i]->Free) its[i]->Free(its[i]);
+        host_free(its);
+        return keep;
+    }
+    if (kids.size() > (size_t)kIIMaxLists) {
+        free_children();
+        return nullptr;
+    }
+    std::vector<ChildView> views(kids.size());
+    bool ok = true;
+    for (size_t i = 0; i < kids.size() && ok; i++) ok = child_view(kids[i], views[i]);
+    NodeIter *out = nullptr;
+    if (ok) {
+        std::vector<II_PostingList *> pls;
+        std::vector<int> modes;
+        std::vector<II_TermParams> terms;
+        for (auto &v : views) {
+            pls.push_back(v.pl);
+            modes.push_back((int)v.mode);
+            terms.push_back(v.term);
+        }
+        bool any_mode = false, any_required = false;
+        for (int m : modes) any_mode |= m != LEAF_REQUIRED, any_required |= m == LEAF_REQUIRED;
+        II_ResultSet *rs = nullptr;
+        if (is_union)
+            rs = any_mode ? nullptr : II_Union(pls.data(), pls.size(), quick_exit ? 1 : 0);
+        else if (!any_mode)
+            rs = II_Intersect(pls.data(), pls.size());
+        else if (any_required)
+            rs = II_IntersectEx(pls.data(), modes.data(), pls.size());
+        if (rs) {
+            out = new_node(NODE_RESULT, is_union ? II_IteratorType_Union : II_IteratorType_Intersect, weight);
+            out->rs = rs;
+            out->terms = terms;
+            out->agg_weight = weight;
+        }
+    }
+    for (auto &v : views)
+        if (v.temp) delete v.pl;
+    free_children();
+    return out ? &out->base : nullptr;
+}
+
+// RS/headers/iterators_ffi.h:309.  max_slop >= 0 / in_order (phrase constraints) need term offsets on the device: not yet —
+// NULL is returned and the caller keeps the reference's own iterator for that node.
+II_QueryIterator *NewIntersectionIterator(II_QueryIterator **its, size_t num, int32_t max_slop, bool in_order, double weight) {
+    if (max_slop >= 0 || in_order) return nullptr;
+    if (!its || num == 0) {
+        if (its) host_free(its);
+        return II_NewEmptyIterator();
+    }
+    return build_aggregate(its, num, false, false, weight);
+}
+// RS/headers/iterators_ffi.h:594 (type_, q_str and config only steer the reference's flat / heap choice and its profile output)
+II_QueryIterator *NewUnionIterator(II_QueryIterator **its, int32_t num, bool quick_exit, double weight, int type_, const char *q_str,
+                                   const void *config) {
+    (void)type_;
+    (void)q_str;
+    (void)config;
+    if (!its || num <= 0) {
+        if (its) host_free(its);
+        return II_NewEmptyIterator();
+    }
+    return build_aggregate(its, (size_t)num, true, quick_exit, weight);
+}
+
+// ---- scorer extension ------------------------------------------------------------------------------
+} // extern "C" (templates below)
+namespace {
+struct RSIndexStatsC { // src/redisearch.h:245-249
+    size_t numDocs, numTerms;
+    double avgDocLen;
+};
+struct ScoringFunctionArgsC { // src/redisearch.h:254-274
+    void *extdata;
+    const void *qdata;
+    size_t qdatalen;
+    RSIndexStatsC indexStats;
+    void *scrExp;
+    int (*GetSlop)(const void *res);
+    uint64_t tanhFactor;
+};
+typedef double (*RSScoringFunctionC)(const ScoringFunctionArgsC *ctx, const void *res, const void *dmd, double minScore);
+struct RSExtensionCtxC { // src/redisearch.h:282-287
+    int (*RegisterScoringFunction)(const char *alias, RSScoringFunctionC func, void (*ff)(void *), void *privdata);
+    int (*RegisterQueryExpander)(const char *alias, void *exp, void (*ff)(void *), void *privdata);
+};
+
+template <int kScorer>
+double b200_scorer(const ScoringFunctionArgsC *args, const void *res_v, const void *dmd, double min_score) {
+    (void)dmd;
+    const II_IndexResult *res = static_cast<const II_IndexResult *>(res_v);
+    uint64_t magic = 0;
+    NodeIter *it = nullptr;
+    if (res && res->data.tag == II_ResultData_Metric) {
+        memcpy(&magic, res->data._rest, 8);
+        memcpy(&it, res->data._rest + 8, 8);
+    }
+    if (magic != kNodeMagic || !it || it->magic != kNodeMagic) {
+        static bool warned = false;
+        if (!warned) fprintf(stderr, "ii_b200: a *.B200 scorer was called on a result that does not come from a B200 iterator; returning 0\n");
+        warned = true;
+        return 0.0;
+    }
+    if (it->scored_with != kScorer) { // first call for this result set: score every hit on the device, once
+        if (!node_materialise(it) || !it->rs || !node_host(it)) return 0.0;
+        II_IndexStats st{args->indexStats.numDocs, args->indexStats.numTerms, args->indexStats.avgDocLen};
+        // terms are stored in the order of the constructor's `its`, which is what II_Score expects
+        if (II_Score(it->rs, (II_Scorer)kScorer, it->terms.data(), it->agg_weight, &st, it->docs, min_score,
+                     args->tanhFactor ? args->tanhFactor : 4) != 0)
+            return 0.0;
+        if (II_ResultSet_Fetch(it->rs, nullptr, it->scores.data(), nullptr) != 0) return 0.0;
+        it->scored_with = kScorer;
+    }
+    // `res` is the iterator's current result: pos points one past it
+    const size_t i = it->pos ? it->pos - 1 : 0;
+    return i < it->scores.size() ? it->scores[i] : 0.0;
+}
+} // namespace
+extern "C" {
+
+// Loaded by Extension_LoadDynamic (dlopen + dlsym "RS_ExtensionInit", src/extension.c:121-145).  Registers the device
+// counterparts of the default scorers under <NAME>.B200; FT.SEARCH ... SCORER BM25STD.B200 then returns, per result, the
+// score computed on the device for the whole result set.  0 = REDISEARCH_OK.
+int RS_ExtensionInit(void *ctx_v) {
+    auto *ctx = static_cast<RSExtensionCtxC *>(ctx_v);
+    if (!ctx || !ctx->RegisterScoringFunction) return 1;
+    int rc = 0;
+    rc |= ctx->RegisterScoringFunction("BM25STD.B200", b200_scorer<II_SCORER_BM25STD>, nullptr, nullptr);
+    rc |= ctx->RegisterScoringFunction("BM25.B200", b200_scorer<II_SCORER_BM25>, nullptr, nullptr);
+    rc |= ctx->RegisterScoringFunction("TFIDF.B200", b200_scorer<II_SCORER_TFIDF>, nullptr, nullptr);
+    rc |= ctx->RegisterScoringFunction("TFIDF.DOCNORM.B200", b200_scorer<II_SCORER_TFIDF_DOCNORM>, nullptr, nullptr);
+    rc |= ctx->RegisterScoringFunction("DOCSCORE.B200", b200_scorer<II_SCORER_DOCSCORE>, nullptr, nullptr);
+    rc |= ctx->RegisterScoringFunction("BM25STD.TANH.B200", b200_scorer<II_SCORER_BM25STD_TANH>, nullptr, nullptr);
+    rc |= ctx->RegisterScoringFunction("DISMAX.B200", b200_scorer<II_SCORER_DISMAX>, nullptr, nullptr);
+    return rc ? 1 : 0;
 }
 
 II_Stats II_GetStats(bool reset) {

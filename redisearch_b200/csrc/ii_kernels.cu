@@ -260,24 +260,32 @@ __global__ void __launch_bounds__(kIIThreads) intersect_kernel(const IntersectAr
         __syncthreads();
         const uint32_t lo = s_lo, hi = s_hi, range = hi - lo;
         uint32_t *posj = a.tmp_pos + (size_t)j * a.stride;
-        if (range <= (uint32_t)kIISmemElems) {
+        const int mode = a.mode[j];
+        const bool staged = range <= (uint32_t)kIISmemElems;
+        if (staged) {
             for (uint32_t t = threadIdx.x; t < range; t += kIIThreads) sB[t] = B[lo + t];
             __syncthreads();
+        }
 #pragma unroll
-            for (int i = 0; i < kIIItems; i++) {
-                if (alive[i]) {
-                    const uint32_t p = lower_bound_u32(sB, 0, range, doc[i]);
-                    alive[i] = (p < range) && sB[p] == doc[i];
-                    if (alive[i]) posj[start + threadIdx.x * kIIItems + i] = lo + p;
+        for (int i = 0; i < kIIItems; i++) {
+            if (alive[i]) {
+                uint32_t p;
+                bool found;
+                if (staged) {
+                    p = lower_bound_u32(sB, 0, range, doc[i]);
+                    found = (p < range) && sB[p] == doc[i];
+                    p += lo;
+                } else {
+                    p = lower_bound_u32(B, lo, hi, doc[i]);
+                    found = (p < hi) && B[p] == doc[i];
                 }
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < kIIItems; i++) {
-                if (alive[i]) {
-                    const uint32_t p = lower_bound_u32(B, lo, hi, doc[i]);
-                    alive[i] = (p < hi) && B[p] == doc[i];
-                    if (alive[i]) posj[start + threadIdx.x * kIIItems + i] = p;
+                if (mode == 0) { // required
+                    alive[i] = found;
+                    if (found) posj[start + threadIdx.x * kIIItems + i] = p;
+                } else if (mode == 1) { // NOT: present = rejected
+                    alive[i] = !found;
+                } else { // OPTIONAL: remembered where present
+                    posj[start + threadIdx.x * kIIItems + i] = found ? p : 0xFFFFFFFFu;
                 }
             }
         }
@@ -431,7 +439,14 @@ __global__ void __launch_bounds__(kIIThreads) gather_kernel(const GatherArgs g) 
         const size_t o = (size_t)off + r;
         g.out_doc[o] = g.ids0[idx];
         g.out_freq[o] = g.freqs[0][idx];
-        for (uint32_t j = 1; j < g.n; j++) g.out_freq[(size_t)j * g.fstride + o] = g.freqs[j][g.tmp_pos[(size_t)j * g.stride + idx]];
+        for (uint32_t j = 1; j < g.n; j++) {
+            uint32_t f = 0; // NOT children and absent OPTIONAL children are virtual results: freq 0
+            if (g.mode[j] != 1) {
+                const uint32_t p = g.tmp_pos[(size_t)j * g.stride + idx];
+                if (g.mode[j] == 0 || p != 0xFFFFFFFFu) f = g.freqs[j][p];
+            }
+            g.out_freq[(size_t)j * g.fstride + o] = f;
+        }
     }
 }
 

@@ -15,6 +15,8 @@ constexpr int kIIMaxLists = 16;
 struct IntersectArgs {
     const uint32_t *ids[kIIMaxLists]; // [0] = the shortest list (drives), others ascending by length
     uint32_t len[kIIMaxLists];
+    uint8_t mode[kIIMaxLists]; // per list (slot 0 = the driver, always required): 0 = required (AND), 1 = NOT (the docId must be
+                               // absent: not.rs as a child of an intersection), 2 = OPTIONAL (never rejects: optional.rs)
     uint32_t n;
     uint32_t *tmp_idx;  // [nchunks*kIIChunk] survivors of chunk c at tmp_idx[c*kIIChunk + r] (index into list 0)
     uint32_t *tmp_pos;  // [n][stride]: position of entry idx of list 0 inside list j (valid for survivors)
@@ -25,6 +27,7 @@ struct IntersectArgs {
 struct GatherArgs {
     const uint32_t *ids0;
     const uint32_t *freqs[kIIMaxLists];
+    uint8_t mode[kIIMaxLists]; // as IntersectArgs: NOT children yield freq 0, OPTIONAL children freq 0 where absent (virtual results)
     uint32_t n;
     const uint32_t *tmp_idx, *tmp_pos, *counts, *offsets;
     size_t stride;   // of tmp_pos

@@ -845,8 +845,9 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         return ok;
     }
     // fp16 route, first tier in two passes over the shadow rows:
-    //   sample pass   every `stride`-th row tile with adaptive top-`keep` lists -> per query the bound
-    //                 T = (k-th best approximate distance of the sample) + 2 eps
+    //   sample pass   every `stride`-th row tile, per (query, row range) the smallest approximate distance of 8 interleaved
+    //                 slices -> per query the bound T = (k-th smallest of its ranges x 8 minima) + 2 eps: k distinct rows
+    //                 lie at or below it, so it bounds the k-th best distance from above
     //   main pass     all row tiles, every row with approximate distance < T is kept (fixed bound: no running thresholds,
     //                 no list compaction — ncu had the epilogue warps busy 62 % of the pass with exactly that)
     // TF32 route: one pass with adaptive lists, as before.
@@ -855,11 +856,11 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     CoarsePlan cps{};                             // sample pass
     if (two_pass) {
         // expected rows below T per (query, row range) = k / (sample fraction * ranges): aim at 24 of the 96 slots
-        const CoarsePlan probe = plan_coarse(v, nq, kind, ke, 0, 1, true);
+        const CoarsePlan probe = plan_coarse(v, nq, kind, ke, 0, 1, 1);
         double f = (double)ke / (24.0 * probe.grid_x);
         f = std::min(0.25, std::max(0.01, f));
         const uint32_t stride = (uint32_t)std::max(1.0, std::floor(1.0 / f));
-        cps = plan_coarse(v, nq, kind, ke, 0, stride, false);
+        cps = plan_coarse(v, nq, kind, ke, 0, stride, 2);
         cp = probe;
     }
     const size_t per_query = (size_t)cp.grid_x * cp.keep;

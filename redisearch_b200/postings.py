@@ -86,6 +86,16 @@ SIGNATURES = [
     ("II_SearchTopNBatch", C.c_int, [_SZ, _P, _P, C.c_int, C.c_int, _P, C.c_double, C.POINTER(II_IndexStats), _P, _SZ, _P, _P, _P, _P]),
     ("II_MergeShardTopN", _SZ, [_P, _P, _P, _SZ, _SZ, _SZ, _P, _P]),
     ("II_NewResultIterator", _QI, [_P, C.c_double]),
+    ("II_IntersectEx", _P, [_P, _P, _SZ]),
+    ("NewIntersectionIterator", _QI, [_P, _SZ, C.c_int32, C.c_bool, C.c_double]),
+    ("NewUnionIterator", _QI, [_P, C.c_int32, C.c_bool, C.c_double, C.c_int, C.c_char_p, _P]),
+    ("II_NewEmptyIterator", _QI, []),
+    ("II_NewTermIterator", _QI, [_P, C.c_int, C.c_double, C.c_double, C.c_double]),
+    ("II_NewTermIterator_FromIndex", _QI, [_P, C.c_int, C.c_double, C.c_double, C.c_double, _P]),
+    ("II_NewNotIterator", _QI, [_QI, C.c_uint64, C.c_double]),
+    ("II_NewOptionalIterator", _QI, [_QI, C.c_uint64, C.c_double]),
+    ("II_SetDefaultDocTable", None, [_P]),
+    ("RS_ExtensionInit", C.c_int, [_P]),
     ("II_TermCache_New", _P, [_SZ]),
     ("II_TermCache_Free", None, [_P]),
     ("II_TermCache_Acquire", _SZ, [_P, _SZ, _P, _P, _P, _P, C.c_int, _P]),

@@ -630,3 +630,54 @@ def test_term_cache_hits_versions_pins_and_eviction(ps):
     L.II_TermCache_Invalidate(cache, 1005)
     assert L.II_TermCache_GetStats(cache).resident_lists == st.resident_lists - 1
     L.II_TermCache_Free(cache)
+
+
+def test_and_with_not_and_optional_children(ps):
+    """"a b -c ~d": required terms intersect, NOT children exclude (not.rs as a child of an intersection), OPTIONAL children never
+    reject (optional.rs) and contribute only where present.  Excluded / absent children are the reference's virtual results:
+    freq 0 and nothing in any scorer (src/ext/default.c:289-297).  DocIds vs numpy set algebra, freqs per child in
+    aggregate order, BM25STD / TFIDF scores bit-equal to the scorer oracle fed with the non-virtual children."""
+    rng = np.random.default_rng(55)
+    n_docs = 500_000
+    ids = [np.unique(rng.integers(1, n_docs, s)).astype(np.uint64) for s in (200_000, 90_000, 150_000, 60_000)]
+    freqs = [rng.integers(1, 30, len(x)).astype(np.uint32) for x in ids]
+    pls = [ps.PostingList.from_arrays(x, f) for x, f in zip(ids, freqs)]
+    doc_len = rng.integers(50, 500, n_docs + 1).astype(np.uint32)
+    dt = ps.DocTable(n_docs, doc_len)
+    avg = float(doc_len[1:].mean())
+    L = ps.lib()
+    P = ol.postings()
+    maps = [dict(zip(x.tolist(), f.tolist())) for x, f in zip(ids, freqs)]
+    for modes in ([0, 0, 1, 2], [0, 1, 0, 0], [2, 0, 0, 1], [0, 2, 2, 2], [0, 1, 1, 1]):
+        arr = (C.c_void_p * 4)(*[p.h for p in pls])
+        marr = (C.c_int * 4)(*modes)
+        rs = ps.ResultSet(L.II_IntersectEx(arr, marr, 4))
+        exp = None
+        for i, m in enumerate(modes):
+            if m == 0:
+                exp = ids[i] if exp is None else np.intersect1d(exp, ids[i])
+        for i, m in enumerate(modes):
+            if m == 1:
+                exp = np.setdiff1d(exp, ids[i])
+        terms = [(1.0 + 0.5 * i, P.orc_idf(n_docs, len(ids[i])), P.orc_idf_bm25(n_docs, len(ids[i]))) for i in range(4)]
+        for scorer in (ps.SCORER_BM25STD, ps.SCORER_TFIDF):
+            rs.score(scorer, terms, 1.25, n_docs, avg, dt)
+            got_ids, got_sc, got_fr = rs.fetch()
+            assert got_ids.tolist() == exp.tolist(), modes
+            order = rs.child_order().tolist()
+            # required children first (ascending estimate), NOT / OPTIONAL children behind in their given order
+            req = sorted([i for i in range(4) if modes[i] == 0], key=lambda i: len(ids[i]))
+            assert order == req + [i for i in range(4) if modes[i] != 0], (modes, order)
+            for j in range(0, len(exp), max(1, len(exp) // 60)):
+                d = int(exp[j])
+                fr, idf, bidf, w = [], [], [], []
+                for slot, c in enumerate(order):
+                    present = modes[c] != 1 and d in maps[c]
+                    assert got_fr[slot][j] == (maps[c][d] if present else 0)
+                    if present:
+                        fr.append(maps[c][d]); idf.append(terms[c][1]); bidf.append(terms[c][2]); w.append(terms[c][0])
+                s = ol.oracle_score(scorer, fr, idf, bidf, w, 1.25, int(doc_len[d]), 1, 1.0, n_docs, avg)
+                assert np.float64(s).tobytes() == np.float64(got_sc[j]).tobytes(), (modes, scorer, d)
+    # no required child: refused
+    arr = (C.c_void_p * 2)(pls[0].h, pls[1].h)
+    assert not L.II_IntersectEx(arr, (C.c_int * 2)(1, 2), 2)
