@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <limits>
+#include <thread>
 
 namespace rsb200 {
 
@@ -227,10 +229,15 @@ CorpusView FlatIndex::view() const {
 
 std::unique_ptr<QueryCtx> FlatIndex::checkout() {
     {
-        std::lock_guard<std::mutex> g(pool_mu_);
+        std::unique_lock<std::mutex> g(pool_mu_);
         if (!pool_.empty()) {
             auto c = std::move(pool_.back());
             pool_.pop_back();
+            g.unlock();
+            if (c->abandoned) { // its last user timed out and left: let that work drain before the buffers are reused
+                cudaStreamSynchronize(c->stream);
+                c->abandoned = false;
+            }
             return c;
         }
     }
@@ -247,6 +254,18 @@ void FlatIndex::checkin(std::unique_ptr<QueryCtx> c) {
 bool FlatIndex::timed_out(void *ctx) const {
     timeoutCallbackFunction cb = globals().timeout_cb.load();
     return cb && cb(ctx) != 0;
+}
+
+int FlatIndex::wait_polling(cudaStream_t s, void *timeout_ctx) const {
+    timeoutCallbackFunction cb = globals().timeout_cb.load();
+    if (!cb) return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -1;
+    for (;;) {
+        const cudaError_t e = cudaStreamQuery(s);
+        if (e == cudaSuccess) return 0;
+        if (e != cudaErrorNotReady) return -1;
+        if (cb(timeout_ctx) != 0) return 1;
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -586,7 +605,17 @@ VecSimQueryReply *FlatIndex::topk(const void *q, size_t k, VecSimQueryParams *qp
             d_res = c->d_out;
         }
         ok = ok && cudaMemcpyAsync(c->h_out, d_res, ke * 8, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
-        ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+        if (ok) {
+            const int w = wait_polling(c->stream, tctx);
+            if (w == 1) { // deadline passed while the scan was running
+                c->abandoned = true;
+                launches_total_ += lc.launches;
+                checkin(std::move(c));
+                rep->code = VecSim_QueryReply_TimedOut;
+                return rep;
+            }
+            ok = w == 0;
+        }
         if (ok) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop) == cudaSuccess) {
@@ -982,8 +1011,16 @@ int FlatIndex::topk_batch(const void *qs, size_t qstride, size_t nq, size_t k, V
     uint64_t *d_res = nullptr;
     ok = ok && batch_scan(*c, c->d_query, qpitch, (uint32_t)nq, ke, c->stream, lc, &d_res);
     ok = ok && cudaMemcpyAsync(c->h_out, c->d_out, nq * ke * 8, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
-    ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
     launches_total_ += lc.launches;
+    if (ok) {
+        const int w = wait_polling(c->stream, tctx); // a 414 ms exact-scan fallback no longer holds a timed-out caller
+        if (w == 1) {
+            c->abandoned = true;
+            checkin(std::move(c));
+            return VecSim_QueryReply_TimedOut;
+        }
+        ok = w == 0;
+    }
     if (ok) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop) == cudaSuccess) {

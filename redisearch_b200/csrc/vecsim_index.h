@@ -67,6 +67,7 @@ struct QueryCtx {
     uint32_t *d_ids = nullptr, *h_ids = nullptr;
     float *d_dist = nullptr, *h_dist = nullptr;
     size_t ids_cap = 0;
+    bool abandoned = false; // a timed-out caller left while kernels were still running on `stream`: synchronise before reuse
     ~QueryCtx();
     bool init();
     bool need_query(size_t bytes);
@@ -172,6 +173,10 @@ class FlatIndex {
     bool grow_to(size_t rows);
     bool sync_labels_to_device();
     bool timed_out(void *ctx) const;
+    // Wait for `s`, polling the timeout callback (VecSim_SetTimeoutCallbackFunction) every ~50 us while kernels run —
+    // the reference checks it per vector (brute_force.h:265-269); a device pass cannot be interrupted, but the caller
+    // is released as soon as the deadline passes.  0 = done, 1 = timed out (the stream is still busy), -1 = CUDA error.
+    int wait_polling(cudaStream_t s, void *timeout_ctx) const;
     // k smallest composites (> cursor) over ctx->d_scores[0..n) into ctx->h_out, chunked by
     // kMaxFusedK; returns the number found or -1.
     long select_from_scores(QueryCtx &c, uint32_t n, bool has_cursor, uint64_t cursor, size_t want);

@@ -471,6 +471,51 @@ def test_timeout_callback(vs):
     assert g.topk(np.zeros(8, dtype=np.float32), 5)[2] == vs.VecSim_QueryReply_OK
 
 
+def test_timeout_fires_while_the_scan_is_running(vs):
+    """The reference polls the timeout per vector (brute_force.h:265-269).  A device pass cannot be interrupted, but the host
+    polls the callback while kernels run: a deadline that passes DURING a long exact scan releases the caller at once with
+    VecSim_QueryReply_TimedOut, and the abandoned scratch is drained before it is reused (the next query is correct)."""
+    import time
+
+    L = vs.lib()
+    L.VecSimB200_SetCoarseMode(0)  # force the slow exact batched scan
+    n, dim, nq, k = 400_000, 256, 256, 10
+    rows = ol.synth_rows(ol.F32, 5, 0, n, dim)
+    g = vs.VecSimIndex(F32, dim, L2)
+    g.add_many(rows, label0=1)
+    qs = ol.synth_rows(ol.F32, 6, 0, nq, dim)
+    labels, scores, rc = g.topk_batch(qs, k)  # warm: allocations, first launch
+    t0 = time.perf_counter()
+    labels, scores, rc = g.topk_batch(qs, k)
+    full_s = time.perf_counter() - t0
+    assert rc == vs.VecSim_QueryReply_OK
+    calls = {"n": 0}
+
+    def fire_after_a_few_polls(ctx):
+        calls["n"] += 1
+        return 1 if calls["n"] > 4 else 0  # the pre-launch check and three polls pass, then the deadline is over
+
+    cb = vs.TIMEOUT_CB(fire_after_a_few_polls)
+    cb_off = vs.TIMEOUT_CB(lambda ctx: 0)
+    _KEEPALIVE.extend([cb, cb_off])
+    qp = vs.VecSimQueryParams()
+    L.VecSim_SetTimeoutCallbackFunction(cb)
+    try:
+        out_l = np.zeros((nq, k), dtype=np.uint64)
+        out_s = np.zeros((nq, k), dtype=np.float64)
+        t0 = time.perf_counter()
+        rc = L.VecSimB200_TopKQueryBatch(g.h, qs.ctypes.data, qs.strides[0], nq, k, C.byref(qp), out_l.ctypes.data, out_s.ctypes.data)
+        early_s = time.perf_counter() - t0
+    finally:
+        L.VecSim_SetTimeoutCallbackFunction(cb_off)
+    assert rc == vs.VecSim_QueryReply_TimedOut
+    if full_s > 0.004:  # only meaningful when the scan is long compared with the polling period
+        assert early_s < 0.6 * full_s, (early_s, full_s)
+    l2, s2, rc2 = g.topk_batch(qs, k)
+    assert rc2 == vs.VecSim_QueryReply_OK and (l2 == labels).all() and s2.tobytes() == scores.tobytes()
+    L.VecSimB200_SetCoarseMode(-1)
+
+
 def test_resolve_params(vs):
     """vec_sim.cpp:270-343 for a FLAT index."""
     L = vs.lib()
