@@ -143,12 +143,13 @@ void II_DocTable_Free(II_DocTable *dt);
 /* ---- iterator algebra on device ---------------------------------------------------------------- */
 typedef struct II_ResultSet II_ResultSet;
 
-/* AND of n (1..16) posting lists: ascending docIds present in all of them — Intersection::read
+/* AND of n (1..32) posting lists: ascending docIds present in all of them — Intersection::read
  * (RS/rqe_iterators/src/intersection.rs:428-452) run to EOF.  Children are ordered by
  * num_estimated ascending, stable, exactly like Intersection::new (:103-169); per-hit child freqs
  * are kept in that order for the scorers. */
 II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n);
-/* OR of n (1..16) posting lists — UnionFlat::read_full (RS/rqe_iterators/src/union_flat.rs:324-348)
+/* OR of n (1..32) posting lists — UnionFlat::read_full (RS/rqe_iterators/src/union_flat.rs:324-348; above
+ * min_union_iter_heap = 20 children the reference picks union_heap.rs: same docIds, same aggregate per docId)
  * run to EOF; quick_exit != 0 keeps docIds only (quick mode reports a single child, :433-524). */
 II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit);
 /* AND with NOT / OPTIONAL children — the "a -b" / "a ~b" query shapes (RS/rqe_iterators/src/not.rs, optional.rs as children of

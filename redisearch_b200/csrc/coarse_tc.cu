@@ -1209,20 +1209,45 @@ __global__ void __launch_bounds__(256) refine_kernel(const uint8_t *rows, size_t
                                                      const uint64_t *__restrict__ cand, float eps, const float *__restrict__ q_norm2,
                                                      float max_norm, uint32_t *__restrict__ ok, uint32_t ok_value, uint64_t *__restrict__ out,
                                                      const uint32_t *__restrict__ q_index, const uint32_t *__restrict__ nq_dev,
-                                                     const float *__restrict__ thr_T, const uint32_t *__restrict__ overflow) {
+                                                     const float *__restrict__ thr_T, const uint32_t *__restrict__ overflow,
+                                                     uint32_t smem_cap) {
     using Tile = DistTile<DT_F32, MT, 1, 1>;
     __shared__ uint64_t surv[kRefineMaxSurv];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t ctl[4];
-    __shared__ uint32_t s_nsurv, s_bad;
+    __shared__ uint32_t s_nsurv, s_bad, s_ncomp;
     if (nq_dev) nq = min(nq, *nq_dev);
     if (blockIdx.x >= nq) return;
     const uint32_t q = q_index ? q_index[blockIdx.x] : blockIdx.x; // query of the original batch
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t *mine = cand + (size_t)blockIdx.x * lists_per_query * keep;
-    const uint32_t total = lists_per_query * keep;
+    uint32_t total = lists_per_query * keep;
     eps = query_eps(eps, q_norm2, blockIdx.x, max_norm, dim, MT == MT_L2);
-    if (threadIdx.x == 0) s_nsurv = 0, s_bad = 0;
+    if (threadIdx.x == 0) s_nsurv = 0, s_bad = 0, s_ncomp = 0;
+    __syncthreads();
+    // the lists are mostly empty slots (fixed-bound pass: ~15 of 96 per list): pack the real candidates into shared memory
+    // once, so that the selection passes below do not re-read 57 KB of global memory five times per query
+    extern __shared__ uint64_t s_cand[];
+    for (uint32_t i0 = 0; i0 < total; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint64_t c = i < total ? mine[i] : kEmptySlot;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, c != kEmptySlot);
+        uint32_t base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_ncomp, (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (c != kEmptySlot) {
+            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < smem_cap) s_cand[pos] = c;
+        }
+    }
+    __syncthreads();
+    const bool packed = s_ncomp <= smem_cap;
+    const uint64_t *mine_all = mine; // the proof of the adaptive tier walks the lists as published
+    const uint32_t total_all = total;
+    if (packed) {
+        mine = s_cand;
+        total = s_ncomp;
+    }
     // a_k: k-th smallest approximate key; fewer than k candidates: everything survives
     const uint32_t ak_key = block_kth_key(mine, total, k, hist, ctl);
     // survivors: approx <= a_k + 2 eps (rounded up)
@@ -1264,8 +1289,9 @@ __global__ void __launch_bounds__(256) refine_kernel(const uint8_t *rows, size_t
     if (thr_T) {
         if (threadIdx.x == 0 && (overflow[blockIdx.x] != 0 || !have_k || !(thr_T[blockIdx.x] - eps > ek))) bad = true;
     } else {
+        (void)total_all;
         for (uint32_t l = threadIdx.x; l < lists_per_query; l += blockDim.x) {
-            const uint64_t *lst = mine + (size_t)l * keep;
+            const uint64_t *lst = mine_all + (size_t)l * keep;
             uint32_t worst = 0;
             bool full = true;
             for (uint32_t j = 0; j < keep; j++) {
@@ -1646,12 +1672,15 @@ cudaError_t launch_refine(const CorpusView &c, const void *d_queries, size_t qpi
     if (nq == 0) return cudaSuccess;
     const uint32_t okv = d_q_index ? 2u : 1u;
     const uint8_t *rows = static_cast<const uint8_t *>(c.rows), *qs = static_cast<const uint8_t *>(d_queries);
+    // candidates packed in shared memory: as many slots as the lists have, up to 20 KB worth
+    const uint32_t smem_cap = std::min<uint32_t>(lists_per_query * keep, 2560);
+    const size_t smem = (size_t)smem_cap * 8;
     if (c.metric == MT_L2)
-        refine_kernel<MT_L2><<<nq, 256, 0, s>>>(rows, c.pitch, c.dim, qs, qpitch, nq, lists_per_query, keep, k, d_cand, eps, d_q_norm2,
-                                                max_norm, d_ok, okv, d_out, d_q_index, d_nq_dev, d_thr_T, d_overflow);
+        refine_kernel<MT_L2><<<nq, 256, smem, s>>>(rows, c.pitch, c.dim, qs, qpitch, nq, lists_per_query, keep, k, d_cand, eps, d_q_norm2,
+                                                   max_norm, d_ok, okv, d_out, d_q_index, d_nq_dev, d_thr_T, d_overflow, smem_cap);
     else
-        refine_kernel<MT_IP><<<nq, 256, 0, s>>>(rows, c.pitch, c.dim, qs, qpitch, nq, lists_per_query, keep, k, d_cand, eps, d_q_norm2,
-                                                max_norm, d_ok, okv, d_out, d_q_index, d_nq_dev, d_thr_T, d_overflow);
+        refine_kernel<MT_IP><<<nq, 256, smem, s>>>(rows, c.pitch, c.dim, qs, qpitch, nq, lists_per_query, keep, k, d_cand, eps, d_q_norm2,
+                                                   max_norm, d_ok, okv, d_out, d_q_index, d_nq_dev, d_thr_T, d_overflow, smem_cap);
     return cudaGetLastError();
 }
 

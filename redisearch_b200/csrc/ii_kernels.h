@@ -10,7 +10,7 @@ constexpr int kIIThreads = 256;
 constexpr int kIIItems = 4;
 constexpr int kIIChunk = kIIThreads * kIIItems; // entries of the driving list per CTA
 constexpr int kIISmemElems = 8192;              // 32 KB window of the probed list staged per CTA
-constexpr int kIIMaxLists = 16;
+constexpr int kIIMaxLists = 32; // children of one AND / OR (the reference switches its union to the heap variant above 20: same docIds)
 
 struct IntersectArgs {
     const uint32_t *ids[kIIMaxLists]; // [0] = the shortest list (drives), others ascending by length

@@ -40,7 +40,7 @@ def test_coarse_path_is_exact(n, dim, nq, k, mode):
     vs.lib().VecSimB200_SetCoarseMode(mode)
     rows = ol.synth_rows(ol.F32, 42, 0, n, dim)
     g = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, vs.VecSimMetric_Cosine)
-    p = ol.PortIndex(ol.F32, dim, ol.COS, tier=ol.TIER_AVX512)
+    p = _checker(ol.COS)(dim)  # the reference's own compiled code when oracle/_ref is present
     assert g.add_many(rows, label0=1) == n
     p.add_many(rows, 1)
     qs = ol.synth_rows(ol.F32, 43, 0, nq, dim)
