@@ -662,7 +662,9 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                     uint64_t *__restrict__ list_scratch, uint64_t *__restrict__ cand_out, const uint32_t *__restrict__ nq_dev,
                     uint32_t tile_stride, const float *__restrict__ thr_fixed, uint32_t *__restrict__ overflow) {
     constexpr bool kFixed = kMode == 1, kSample = kMode == 2;
-    static_assert(kMode == 0 || (!kDirect && (kOp == 0 || kOp == 3)), "fixed bound / sample pass: fp32 route only");
+    static_assert(kMode == 0 || (!kDirect && (kOp == 0 || kOp == 3)) || (kDirect && kOp == 0),
+                  "fixed bound / sample pass: the fp32 route and 16-bit corpora (inner product / cosine)");
+    constexpr int kSliceSets = (int)kCoarseSampleSlices / (kQN / 32); // tiles i, i + kSliceSets, ... share a slice set
     constexpr int kQListCap = kEpl * 32;
     if (nq_dev) { // second tier: the number of live queries is only known on the device; nothing to do = every CTA leaves
         nq = min(nq, *nq_dev);
@@ -869,9 +871,9 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         if constexpr (kOp == 2) nq_norm = q < nq ? *reinterpret_cast<const float *>(q16 + (size_t)q * q16_pitch + dim) : 1.0f;
         if constexpr (kOp == 3) nq_norm = q < nq ? q_norm2[q] : 0.0f; // |q|^2
         bool ovf = false;
-        float smax[2][kQN / 32]; // kSample: running maxima of the pre-test value per slice (largest = smallest distance)
+        float smax[kSample ? kSliceSets : 1][kQN / 32]; // kSample: running maxima of the pre-test value per slice (largest = smallest distance)
 #pragma unroll
-        for (int x = 0; x < 2; x++)
+        for (int x = 0; x < (kSample ? kSliceSets : 1); x++)
 #pragma unroll
             for (int h = 0; h < kQN / 32; h++) smax[x][h] = -__int_as_float(0x7f800000);
         if constexpr (kFixed) {
@@ -942,10 +944,10 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                             if (!tail || row0 + j < n_rows) mx = fmaxf(mx, u);
                         }
                     }
-                    if (i & 1u)
-                        smax[1][h] = fmaxf(smax[1][h], mx);
-                    else
-                        smax[0][h] = fmaxf(smax[0][h], mx);
+                    // slice set = tile counter mod kSliceSets: a uniform switch keeps the register indices static
+#pragma unroll
+                    for (int x = 0; x < kSliceSets; x++)
+                        if ((int)(i % (uint32_t)kSliceSets) == x) smax[kSample ? x : 0][h] = fmaxf(smax[kSample ? x : 0][h], mx);
                     continue;
                 }
                 if constexpr (kFixed) {
@@ -1057,10 +1059,10 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
             if (q < nq) {
                 uint64_t *dst = cand_out + ((size_t)q * gridDim.x + blockIdx.x) * keep;
 #pragma unroll
-                for (int x = 0; x < 2; x++)
+                for (int x = 0; x < kSliceSets; x++)
 #pragma unroll
                     for (int h = 0; h < kQN / 32; h++) {
-                        const float m = smax[x][h];
+                        const float m = smax[kSample ? x : 0][h];
                         uint64_t c = kEmptySlot;
                         if (m > -__int_as_float(0x7f800000)) {
                             const float d = kOp == 0 ? 1.0f - m : __fsub_rn(nq_norm, __fmul_rn(2.0f, m));
@@ -1195,7 +1197,14 @@ __global__ void __launch_bounds__(256) threshold_kernel(const uint64_t *__restri
     const uint32_t ak = block_kth_key(cand + (size_t)q * lists_per_query * keep, lists_per_query * keep, k, hist, ctl);
     if (threadIdx.x == 0) {
         const float e = query_eps(eps, q_norm2, q, max_norm, dim, l2 != 0);
-        thr_out[q] = ak == 0xFFFFFFFFu ? __int_as_float(0x7f800000) : key_to_float(ak) + (2.0f * e) * 1.001f + 1e-30f;
+        float T;
+        if (ak == 0xFFFFFFFFu)
+            T = __int_as_float(0x7f800000);
+        else if (e == 0.0f) // 16-bit corpora: the GEMM result IS the distance — keep d <= a_k (the main pass tests d < T)
+            T = key_to_float(ak + 1u);
+        else
+            T = key_to_float(ak) + (2.0f * e) * 1.001f + 1e-30f;
+        thr_out[q] = T;
         overflow[q] = 0;
     }
 }
@@ -1398,8 +1407,11 @@ static uint32_t qtmem_nacc() {
     return (uint32_t)v;
 }
 static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl, bool int_cos, int mode = 0) {
-    if (kind == CoarseDirect16)
+    if (kind == CoarseDirect16) {
+        if (mode == 1) return (const void *)coarse_qtmem_kernel<true, 8, 0, 1>; // fixed bound, lists of 256
+        if (mode == 2) return (const void *)coarse_qtmem_kernel<true, 3, 0, 2>; // sample pass
         return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 0, 0> : (const void *)coarse_qtmem_kernel<true, 8, 0, 0>;
+    }
     if (kind == CoarseDirect8) {
         if (int_cos) return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 2, 0> : (const void *)coarse_qtmem_kernel<true, 8, 2, 0>;
         return epl == 3 ? (const void *)coarse_qtmem_kernel<true, 3, 1, 0> : (const void *)coarse_qtmem_kernel<true, 8, 1, 0>;
@@ -1455,7 +1467,7 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32
     CoarsePlan p{};
     p.kind = kind;
     p.tile_stride = std::max(1u, tile_stride);
-    p.mode = kind == CoarseF16 ? mode : 0;
+    p.mode = (kind == CoarseF16 || (kind == CoarseDirect16 && c.metric == MT_IP)) ? mode : 0;
     if (kind == CoarseF16 || kind == CoarseDirect16 || kind == CoarseDirect8) {
         p.num_kb = kind == CoarseDirect8 ? (c.dim + 127) / 128 : (c.dim + 63) / 64;
         p.tiles = ((c.n_rows + kQN - 1) / kQN + p.tile_stride - 1) / p.tile_stride; // row tiles this pass visits
@@ -1467,7 +1479,8 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32
         p.keep = kind == CoarseF16 ? (keep_override ? keep_override : (k <= kCoarseTier1MaxK ? kCoarseKeep : kCoarseKeepWide))
                                    : (k <= 32 ? 32u : 128u);
         p.epl = p.keep <= 32 ? 3 : 8;
-        if (p.mode == 1) p.keep = kCoarseFixedCap, p.epl = 3; // every row below the bound, up to the list capacity
+        if (p.mode == 1 && kind == CoarseF16) p.keep = kCoarseFixedCap, p.epl = 3; // every row below the bound, up to the list capacity
+        if (p.mode == 1 && kind == CoarseDirect16) p.keep = kCoarseFixedCapDirect, p.epl = 8;
         if (p.mode == 2) p.keep = kCoarseSampleSlices, p.epl = 3; // the slice minima
         p.stages = (uint32_t)std::min<size_t>(kQMaxStages, (kSmemLimit - qtmem_fixed_smem(p.num_kb)) / kQStageBytes);
         p.smem_bytes = qtmem_fixed_smem(p.num_kb) + (size_t)p.stages * kQStageBytes;
@@ -1688,6 +1701,31 @@ cudaError_t launch_threshold(const uint64_t *d_cand, uint32_t nq, uint32_t lists
                              const float *d_q_norm2, float max_norm, uint32_t dim, int l2, float *d_thr, uint32_t *d_overflow, cudaStream_t s) {
     if (nq == 0) return cudaSuccess;
     threshold_kernel<<<nq, 256, 0, s>>>(d_cand, nq, lists_per_query, keep, k, eps, d_q_norm2, max_norm, dim, l2, d_thr, d_overflow);
+    return cudaGetLastError();
+}
+
+__global__ void flags_from_overflow_kernel(const uint32_t *__restrict__ ovf, uint32_t nq, uint32_t *__restrict__ ok) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) ok[q] = ovf[q] ? 0u : 1u;
+}
+cudaError_t launch_flags_from_overflow(const uint32_t *d_overflow, uint32_t nq, uint32_t *d_ok, cudaStream_t s) {
+    if (nq == 0) return cudaSuccess;
+    flags_from_overflow_kernel<<<(nq + 255) / 256, 256, 0, s>>>(d_overflow, nq, d_ok);
+    return cudaGetLastError();
+}
+__global__ void scatter_rows_kernel(const uint64_t *__restrict__ src, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ count,
+                                    uint32_t k, uint64_t *__restrict__ dst, uint32_t *__restrict__ ok) {
+    const uint32_t n = *count;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t q = idx[i];
+        for (uint32_t t = threadIdx.x; t < k; t += blockDim.x) dst[(size_t)q * k + t] = src[(size_t)i * k + t];
+        if (threadIdx.x == 0) ok[q] = 2u;
+    }
+}
+cudaError_t launch_scatter_rows(const uint64_t *d_src, const uint32_t *d_idx, const uint32_t *d_count, uint32_t max_n, uint32_t k,
+                                uint64_t *d_dst, uint32_t *d_ok, cudaStream_t s) {
+    if (max_n == 0) return cudaSuccess;
+    scatter_rows_kernel<<<std::min(max_n, 256u), 128, 0, s>>>(d_src, d_idx, d_count, k, d_dst, d_ok);
     return cudaGetLastError();
 }
 

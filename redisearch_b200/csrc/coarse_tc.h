@@ -10,7 +10,8 @@ constexpr uint32_t kCoarseKeep = 24;       // candidates kept per (CTA row range
 constexpr uint32_t kCoarseKeepWide = 128;  // second tier (queries the first proof left open) and first tier of k > 16
 constexpr uint32_t kCoarseTier1MaxK = 16;  // largest k the 24-entry lists serve
 constexpr uint32_t kCoarseMaxK = 128;      // largest k served by the coarse path
-constexpr uint32_t kCoarseSampleSlices = 8; // minima the sample pass publishes per (query, row range)
+constexpr uint32_t kCoarseSampleSlices = 32; // minima the sample pass publishes per (query, row range)
+constexpr uint32_t kCoarseFixedCapDirect = 256; // list capacity of the fixed-bound pass on 16-bit corpora (k up to 128)
 constexpr uint32_t kCoarseFixedCap = 96;   // list capacity of the fixed-bound main pass (rows below the bound per row range)
 // |approx - exact| bounds for unit vectors (Cauchy-Schwarz over the dot product: sum |a_i b_i| <= 1):
 //  TF32: each operand truncated to 11 significant bits -> 2 * 2^-10 relative per product, + accumulation slack;
@@ -76,6 +77,11 @@ cudaError_t launch_refine(const CorpusView &c, const void *d_queries, size_t qpi
                           uint32_t k, const uint64_t *d_cand, float eps, const float *d_q_norm2, float max_norm, uint32_t *d_ok,
                           uint64_t *d_out, const uint32_t *d_q_index, const uint32_t *d_nq_dev, cudaStream_t s,
                           const float *d_thr_T = nullptr, const uint32_t *d_overflow = nullptr);
+// direct 16-bit route: d_ok[q] = d_overflow[q] ? 0 : 1
+cudaError_t launch_flags_from_overflow(const uint32_t *d_overflow, uint32_t nq, uint32_t *d_ok, cudaStream_t s);
+// second tier of the direct route: row i of src ([.][k] composites) -> row d_idx[i] of dst, d_ok[d_idx[i]] = 2, for i < *d_count
+cudaError_t launch_scatter_rows(const uint64_t *d_src, const uint32_t *d_idx, const uint32_t *d_count, uint32_t max_n, uint32_t k,
+                                uint64_t *d_dst, uint32_t *d_ok, cudaStream_t s);
 // d_idx[0, *d_count) = the queries with d_ok == 0, ascending
 cudaError_t launch_compact_unproven(const uint32_t *d_ok, uint32_t nq, uint32_t *d_idx, uint32_t *d_count, cudaStream_t s);
 // row i of dst = row d_idx[i] of src (pitch % 16 == 0), squared norms likewise (nullable), for i < *d_count

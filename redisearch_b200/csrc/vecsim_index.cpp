@@ -822,14 +822,60 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     if (cmode != 0 && !multi_ && nq >= 16 && (is16 || is8) && coarse_supported(v, nq, ke, dkind)) {
         // int8 / uint8: kind::i8 dot products are exact integers and the epilogue applies the reference's own
         // float expression, so that route is bit-exact
-        const CoarsePlan cp = plan_coarse(v, nq, dkind, ke);
-        const size_t nA = (size_t)nq * cp.grid_x * cp.keep;
-        if (!c.need_cand(nA + cp.scratch_elems) || !c.need_out((size_t)nq * ke)) return false;
+        const CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, (dtype_ == DT_BF16 || dtype_ == DT_I8) ? 1 : 0, mkind_ == MT_COS ? 1 : 0, nullptr, nullptr};
         last_batch_coarse_ = true;
         last_batch_path_ = 2;
         c.d_last_ok = nullptr;
         c.last_ok_n = 0;
-        const CoarseOperands ops{v.rows, v.pitch, d_q, qpitch, (dtype_ == DT_BF16 || dtype_ == DT_I8) ? 1 : 0, mkind_ == MT_COS ? 1 : 0, nullptr, nullptr};
+        const CoarsePlan cp = plan_coarse(v, nq, dkind, ke);
+        // 16-bit corpora: the fixed-bound scheme of the fp32 route without the error term — the GEMM result IS the distance, so
+        // T = the k-th smallest slice minimum of the sample pass bounds the k-th best distance from above and the main pass
+        // keeps every row with d <= T (no running thresholds, no compaction); a list that runs full sends the query to the
+        // adaptive kernel.  (int8 distances are small integers with massive ties: they stay on the adaptive lists.)
+        const CoarsePlan probe = plan_coarse(v, nq, dkind, ke, 0, 1, 1);
+        if (is16 && probe.mode == 1 && coarse_fixed_enabled()) {
+            double f = (double)ke / (64.0 * probe.grid_x); // aim at 64 of the 256 slots per (query, row range)
+            f = std::min(0.25, std::max(0.01, f));
+            // small corpora: the sample must still hold a few times k slice minima (4 per visited tile)
+            const uint32_t stride = (uint32_t)std::max(1.0, std::min(std::floor(1.0 / f), std::floor(probe.tiles / (2.0 * ke))));
+            const CoarsePlan cps = plan_coarse(v, nq, dkind, ke, 0, stride, 2);
+            const bool tier2 = coarse_tier2_enabled();
+            const size_t nM = (size_t)nq * probe.grid_x * probe.keep, nS = (size_t)nq * cps.grid_x * cps.keep, nO = (size_t)nq * ke;
+            const size_t nA2 = tier2 ? (size_t)nq * cp.grid_x * cp.keep : 0;
+            const size_t scratch = std::max(std::max(probe.scratch_elems, cps.scratch_elems), tier2 ? cp.scratch_elems : 0);
+            const size_t qcopy = tier2 ? ((size_t)nq * qpitch + 7) / 8 : 0, flag_elems = (nq + 1) / 2 + 1;
+            if (!c.need_cand(nM + nS + nA2 + nO + scratch + qcopy + 5 * flag_elems + 16) || !c.need_out(nO)) return false;
+            uint64_t *cand_m = c.d_cand, *cand_s = cand_m + nM, *cand_t2 = cand_s + nS, *out2 = cand_t2 + nA2, *list_scratch = out2 + nO;
+            uint64_t *q_t2 = list_scratch + scratch, *tail = q_t2 + qcopy;
+            uint32_t *d_ok = reinterpret_cast<uint32_t *>(tail), *d_idx = reinterpret_cast<uint32_t *>(tail + flag_elems);
+            uint32_t *d_n2 = reinterpret_cast<uint32_t *>(tail + 2 * flag_elems), *d_ovf = reinterpret_cast<uint32_t *>(tail + 4 * flag_elems);
+            float *d_thr = reinterpret_cast<float *>(tail + 3 * flag_elems);
+            c.d_last_ok = d_ok;
+            c.last_ok_n = nq;
+            bool ok = launch_coarse(ops, v.n_rows, v.dim, nq, cps, cand_s, list_scratch, st) == cudaSuccess;
+            ok = ok && launch_threshold(cand_s, nq, cps.grid_x, cps.keep, ke, 0.0f, nullptr, 0.0f, (uint32_t)dim_, 0, d_thr, d_ovf, st) == cudaSuccess;
+            cudaEventRecord(c.ev_start, st);
+            ok = ok && launch_coarse(ops, v.n_rows, v.dim, nq, probe, cand_m, list_scratch, st, nullptr, d_thr, d_ovf) == cudaSuccess;
+            cudaEventRecord(c.ev_stop, st);
+            ok = ok && launch_final_select(cand_m, nq, (uint32_t)(probe.grid_x * probe.keep), ke, c.d_out, st, &lc) == cudaSuccess;
+            ok = ok && launch_flags_from_overflow(d_ovf, nq, d_ok, st) == cudaSuccess;
+            lc.launches += 4;
+            if (tier2) {
+                ok = ok && launch_compact_unproven(d_ok, nq, d_idx, d_n2, st) == cudaSuccess;
+                ok = ok && launch_gather_queries(d_q, qpitch, nullptr, d_idx, d_n2, nq, q_t2, nullptr, st) == cudaSuccess;
+                CoarseOperands ops2 = ops;
+                ops2.queries = q_t2;
+                ok = ok && launch_coarse(ops2, v.n_rows, v.dim, nq, cp, cand_t2, list_scratch, st, d_n2) == cudaSuccess;
+                ok = ok && launch_final_select(cand_t2, nq, (uint32_t)(cp.grid_x * cp.keep), ke, out2, st, &lc, d_n2) == cudaSuccess;
+                ok = ok && launch_scatter_rows(out2, d_idx, d_n2, nq, ke, c.d_out, d_ok, st) == cudaSuccess;
+                lc.launches += 4;
+            }
+            coarse_batches_++;
+            *d_result = c.d_out;
+            return ok;
+        }
+        const size_t nA = (size_t)nq * cp.grid_x * cp.keep;
+        if (!c.need_cand(nA + cp.scratch_elems) || !c.need_out((size_t)nq * ke)) return false;
         cudaEventRecord(c.ev_start, st);
         bool ok = launch_coarse(ops, v.n_rows, v.dim, nq, cp, c.d_cand, c.d_cand + nA, st) == cudaSuccess;
         cudaEventRecord(c.ev_stop, st);
@@ -888,7 +934,8 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         const CoarsePlan probe = plan_coarse(v, nq, kind, ke, 0, 1, 1);
         double f = (double)ke / (24.0 * probe.grid_x);
         f = std::min(0.25, std::max(0.01, f));
-        const uint32_t stride = (uint32_t)std::max(1.0, std::floor(1.0 / f));
+        // small corpora: the sample must still hold a few times k slice minima (4 per visited tile)
+        const uint32_t stride = (uint32_t)std::max(1.0, std::min(std::floor(1.0 / f), std::floor(probe.tiles / (2.0 * ke))));
         cps = plan_coarse(v, nq, kind, ke, 0, stride, 2);
         cp = probe;
     }

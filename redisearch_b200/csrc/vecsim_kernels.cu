@@ -188,8 +188,10 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
 // candidates -> k smallest per query, ascending
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads) final_select_kernel(const uint64_t *__restrict__ cand, uint32_t m,
-                                                                    uint32_t k, uint64_t *__restrict__ out) {
+                                                                    uint32_t k, uint64_t *__restrict__ out,
+                                                                    const uint32_t *__restrict__ nq_dev) {
     extern __shared__ __align__(16) uint8_t smem[];
+    if (nq_dev && blockIdx.x >= *nq_dev) return; // second tier: only the first *nq_dev positions hold lists
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sortn = next_pow2(kScanWarps * k);
     uint64_t *sortbuf = reinterpret_cast<uint64_t *>(smem); // [sortn]; first 8*k double as the lists
@@ -520,10 +522,10 @@ cudaError_t launch_scan_topk(const CorpusView &c, const void *d_queries, size_t 
 }
 
 cudaError_t launch_final_select(const uint64_t *d_cand, uint32_t nq, uint32_t m_per_query, uint32_t k,
-                                uint64_t *d_out, cudaStream_t s, LaunchCounters *ctr) {
+                                uint64_t *d_out, cudaStream_t s, LaunchCounters *ctr, const uint32_t *d_nq_dev) {
     if (k == 0 || k > (uint32_t)kMaxFusedK) return cudaErrorInvalidValue;
     const size_t smem = (size_t)next_pow2(kScanWarps * k) * 8 + kScanWarps * 12;
-    final_select_kernel<<<nq, kScanThreads, smem, s>>>(d_cand, m_per_query, k, d_out);
+    final_select_kernel<<<nq, kScanThreads, smem, s>>>(d_cand, m_per_query, k, d_out, d_nq_dev);
     if (ctr) ctr->launches++;
     return cudaGetLastError();
 }

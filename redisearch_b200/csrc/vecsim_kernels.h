@@ -45,8 +45,9 @@ cudaError_t launch_blend(const uint32_t *d_ok, const uint64_t *d_a, const uint64
                          cudaStream_t s, LaunchCounters *ctr);
 // Reduce m_per_query candidate composites per query to the k smallest, ascending.
 // d_out: [nq][k] composites (kEmptySlot-padded when fewer than k real candidates exist).
+// d_nq_dev (nullable): only the first *d_nq_dev queries are processed (count known on the device only).
 cudaError_t launch_final_select(const uint64_t *d_cand, uint32_t nq, uint32_t m_per_query, uint32_t k,
-                                uint64_t *d_out, cudaStream_t s, LaunchCounters *ctr);
+                                uint64_t *d_out, cudaStream_t s, LaunchCounters *ctr, const uint32_t *d_nq_dev = nullptr);
 
 // ---- unfused path: all distances of one query, then cursor-select / range-compact ------------
 cudaError_t launch_scan_scores(const CorpusView &c, const void *d_query, float *d_scores,
