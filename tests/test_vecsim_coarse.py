@@ -379,6 +379,51 @@ def test_16bit_corpora_take_the_tensor_core_route(vtype, metric, n, dim, nq, k):
     vs.lib().VecSimB200_SetCoarseMode(-1)
 
 
+def test_16bit_fixed_bound_pass_and_its_second_tier():
+    """fp16 corpora: the batched scan is a sample pass + a fixed-bound main pass (every row with distance <= the bound is kept in
+    lists of 256 per row range, no compaction).  Uniform data stays on that tier (flag 1); 300 near-duplicates of the query
+    direction packed into ONE row range overflow its list and the adaptive kernel answers (flag 2).  Either way the distances
+    are within the 1e-2 bar of the reference tier and every id whose distance is clearly below the k-th is present."""
+    import torch
+
+    from redisearch_b200 import vecsim as vs
+
+    vs.lib().VecSimB200_SetCoarseMode(1)
+    n, dim, nq, k = 140_000, 96, 32, 10
+    rng = np.random.default_rng(3)
+    rows32 = ol.synth_rows(ol.F32, 42, 0, n, dim)
+    base = rng.uniform(-1, 1, dim).astype(np.float32)
+    gx = 148  # nq <= 128: one query group, 148 row ranges; tiles t, t + 148, t + 296 belong to the same range
+    for j, t in enumerate((5, 5 + gx, 5 + 2 * gx)):
+        rows32[t * 128:t * 128 + 100] = 3.0 * base[None, :] + 1e-2 * rng.standard_normal((100, dim)).astype(np.float32)
+    rows = rows32.astype(np.float16).view(np.uint16)  # round-to-nearest-even, like the reference's float16.h conversion
+    g = vs.VecSimIndex(vs.VecSimType_FLOAT16, dim, vs.VecSimMetric_IP)
+    p = ol.PortIndex(ol.F16, dim, ol.IP, tier=ol.TIER_AVX512)
+    assert g.add_many(rows, label0=1) == n
+    p.add_many(rows, 1)
+    uniform_q = ol.synth_rows(ol.F32, 43, 0, nq, dim).astype(np.float16).view(np.uint16)
+    cluster_q = (base[None, :] + 1e-2 * rng.standard_normal((nq, dim))).astype(np.float16).view(np.uint16)
+    for qs, want in ((uniform_q, 1), (cluster_q, 2)):
+        qd = torch.from_numpy(qs.view(np.int16)).cuda()
+        out_l = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        out_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        assert vs.lib().VecSimB200_TopKQueryBatchDevice(g.h, qd.data_ptr(), nq, k, out_l.data_ptr(), out_s.data_ptr(), sp) == 0
+        torch.cuda.synchronize()
+        assert vs.lib().VecSimB200_LastBatchPath(g.h) == 2
+        flags = np.zeros(nq, dtype=np.uint32)
+        assert vs.lib().VecSimB200_LastCoarseFlags(g.h, flags.ctypes.data, nq) == 0
+        assert (flags == want).sum() >= nq * 0.9, (want, np.bincount(flags, minlength=3).tolist())
+        labels, scores = out_l.cpu().numpy(), out_s.cpu().numpy()
+        for i in range(nq):
+            pi, ps = p.topk(qs[i], k)
+            assert np.abs(scores[i] - ps.astype(np.float32)).max() <= 1e-2 * max(1.0, float(np.abs(ps).max()))
+            kth = float(ps[-1])
+            safe = {int(l) for l, s_ in zip(pi.tolist(), ps.tolist()) if s_ < kth - 1e-2 * max(1.0, abs(kth))}
+            assert safe <= set(labels[i].tolist()), (want, i)
+    vs.lib().VecSimB200_SetCoarseMode(-1)
+
+
 @pytest.mark.parametrize("vtype,metric,n,dim,nq,k", [(ol.I8, ol.COS, 70_000, 128, 40, 10), (ol.I8, ol.IP, 66_000, 768, 130, 100),
                                                      (ol.U8, ol.COS, 140_000, 96, 300, 32), (ol.U8, ol.IP, 70_000, 256, 17, 128),
                                                      (ol.I8, ol.COS, 66_000, 1024, 64, 10)])
