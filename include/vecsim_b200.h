@@ -448,6 +448,18 @@ int VecSimB200_ShardGroup_TopKBatchDevice(VecSimB200_ShardGroup *g, VecSimIndex 
  * merge, D2H inside the call).  Empty slots: label SIZE_MAX, score NaN.  Returns 0 / -1. */
 int VecSimB200_ShardGroup_TopKBatch(VecSimB200_ShardGroup *g, VecSimIndex *shard, const void *queryBlobs, size_t qstride, size_t nq,
                                     size_t k, size_t *out_labels, double *out_scores);
+/* The whole HybridIterator state machine of src/iterators/hybrid_reader.c in one call: mode choice (:668-691:
+ * VecSimIndex_PreferAdHocSearch on the child's estimate unless qp->searchMode forces a policy), HYBRID_BATCHES with the
+ * reference's batch-size formula (:400-404), the alternating merge of each BY_ID batch with the child (:140-169) and the
+ * policy review that may restart in ad-hoc mode (:346-370, :430-438), and HYBRID_ADHOC_BF (:289-335) served by ONE fused
+ * device call over the drained child docIds instead of a GetDistanceFrom round trip per document.  child_iterator: any
+ * object with the reference's QueryIterator vtable (iterator_api.h:46-151) — a B200 AND / OR result or a host iterator; it
+ * is NOT freed.  The k best are kept in the reference's heap order (cmpVecSimResByScore :35-44) and written ordered by
+ * (score, docId).  *out_mode = VecSearchMode the query ended in (also VecSimIndex's LAST_SEARCH_MODE), *out_iterations =
+ * batches run.  Returns a VecSimQueryReply_Code, or -1.  Exact score ties at the k-th place in ad-hoc mode resolve towards
+ * the smaller docId (the reference's min-max heap evicts the smaller docId among tied worst entries). */
+int VecSimB200_HybridTopK(VecSimIndex *index, const void *queryBlob, size_t k, void *child_iterator, VecSimQueryParams *queryParams,
+                          size_t *out_labels, double *out_scores, size_t *out_count, int *out_mode, size_t *out_iterations);
 /* Hybrid "filter AND KNN" in ad-hoc mode, fused: what HybridIterator does in HYBRID_ADHOC_BF mode
  * (src/iterators/hybrid_reader.c:289-335: read the child iterator's docIds in ascending order, GetDistanceFrom each,
  * keep the k best in a heap with strict `<` admission, skip NaN = deleted) — in one call.  doc_ids: the filter's

@@ -133,6 +133,7 @@ SIGNATURES = [
     ("VecSimB200_ReadRows", C.c_int, [_P, _SZ, _SZ, _P]),
     ("VecSimB200_MergeShardTopK", C.c_int, [_P, _P, _SZ, _SZ, _SZ, _P, _P, _P]),
     ("VecSimB200_TopKFiltered", C.c_int, [_P, _P, _SZ, _P, _SZ, C.c_int, _P, _P, C.POINTER(_SZ)]),
+    ("VecSimB200_HybridTopK", C.c_int, [_P, _P, _SZ, _P, C.POINTER(VecSimQueryParams), _P, _P, C.POINTER(_SZ), C.POINTER(C.c_int), C.POINTER(_SZ)]),
     ("VecSimB200_LastBatchPath", C.c_int, [_P]),
     ("VecSimB200_SetCoarseMode", None, [C.c_int]),
     ("VecSimB200_LastCoarseFlags", C.c_int, [_P, _P, _SZ]),
