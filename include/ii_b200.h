@@ -121,6 +121,12 @@ II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nbl
  * of lists built. */
 size_t II_PostingList_FromBlocksBatch(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec,
                                       II_PostingList **out);
+/* Same, and the TERM POSITIONS stay on the device (II_CODEC_FULL only; other codecs behave like the call above): the encoded
+ * block bytes are kept resident and every posting records where its offsets payload (varint position deltas,
+ * RS/index_result/src/core/proximity.rs:45-52) sits inside them.  Needed by slop / in-order intersections. */
+size_t II_PostingList_FromBlocksBatchOffsets(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec,
+                                             II_PostingList **out);
+int II_PostingList_HasOffsets(const II_PostingList *pl);
 /* From already-decoded host arrays (freqs may be NULL = all 1).  docIds strictly ascending. */
 II_PostingList *II_PostingList_FromArrays(const uint64_t *doc_ids, const uint32_t *freqs, size_t n);
 /* Adopt COPIES of device arrays (docIds u32 ascending, freqs u32). */
@@ -157,6 +163,15 @@ II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit);
  * the docId is present its freq is kept).  Excluded / absent children yield the reference's virtual results: freq 0, no
  * contribution to any scorer (src/ext/default.c:289-297).  At least one child must be required. */
 II_ResultSet *II_IntersectEx(II_PostingList *const *lists, const int *modes, size_t n);
+/* AND under the reference's proximity constraints — exact phrases and "within N words" (Intersection::relevancy check,
+ * RS/rqe_iterators/src/intersection.rs:201-242, -> RSIndexResult::is_within_range, RS/index_result/src/core/proximity.rs:
+ * within_range_in_order :127-180, within_range_unordered :184-220, is_within_range :262-299).  max_slop < 0 = no limit;
+ * in_order != 0 = the terms must appear in the order of `lists`, which is then also the aggregate child order (the reference
+ * does not sort the children of an in-order intersection, intersection.rs:143).  One thread per candidate hit walks the term
+ * positions of its children on the device; hits out of range are dropped, order and per-child freqs are kept.  modes may be
+ * NULL; NOT children and absent OPTIONAL children are virtual results without positions and are left out of the check, as
+ * in the reference.  Every other list must come from II_PostingList_FromBlocksBatchOffsets; n <= 8. */
+II_ResultSet *II_IntersectPhrase(II_PostingList *const *lists, const int *modes, size_t n, int32_t max_slop, int in_order);
 size_t II_ResultSet_Len(const II_ResultSet *rs);
 void II_ResultSet_Free(II_ResultSet *rs);
 
@@ -242,6 +257,8 @@ size_t II_TermCache_Acquire(II_TermCache *cache, size_t n, const uint64_t *keys,
                             const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec, II_PostingList **out);
 void II_TermCache_Release(II_TermCache *cache, size_t n, II_PostingList *const *lists);
 void II_TermCache_Invalidate(II_TermCache *cache, uint64_t key); /* from the index writer / GC, when it is cheaper than versions */
+/* on: lists decoded from now on keep their term positions (Full codec) so that phrase / slop intersections can use them */
+void II_TermCache_KeepOffsets(II_TermCache *cache, int on);
 II_TermCacheStats II_TermCache_GetStats(II_TermCache *cache);
 
 /* ---- QueryIterator facade ------------------------------------------------------------------------ */
@@ -256,8 +273,9 @@ II_QueryIterator *II_NewResultIterator(II_ResultSet *rs, double weight);
  * leaves: drained once through Read() and uploaded).  The reduction rules of intersection.rs:363-417 / union_reducer.rs:30-66
  * are applied (no children -> empty, NULL / empty child, wildcard stripping, single survivor returned as is).  The tree is
  * evaluated on the device at construction; the returned iterator walks the finished result set.  Phrase constraints
- * (max_slop >= 0, in_order) need term offsets on the device and are not taken: NULL is returned and the caller keeps the
- * reference's iterator for that node. */
+ * (max_slop >= 0, in_order) are evaluated on the device (II_IntersectPhrase) when every child is a B200 term leaf carrying
+ * its term positions and there are at most 8 of them; otherwise NULL is returned with nothing consumed and the caller keeps
+ * the reference's iterator for that node. */
 II_QueryIterator *NewIntersectionIterator(II_QueryIterator **its, size_t num, int32_t max_slop, bool in_order, double weight);
 II_QueryIterator *NewUnionIterator(II_QueryIterator **its, int32_t num, bool quick_exit, double weight, int /* QueryNodeType */ type_,
                                    const char *q_str, const void /* IteratorsConfig */ *config);

@@ -135,6 +135,10 @@ size_t orc_union_skipto(OrcReader **children, size_t n, const uint64_t *targets,
 /* IDF (RS/idf/src/lib.rs:36-110). */
 double orc_idf(uint64_t total_docs, uint64_t term_docs);
 double orc_idf_bm25(uint64_t total_docs, uint64_t term_docs);
+/* proximity.rs is_within_range over term children: offsets[i] / lens[i] = the varint-delta position bytes of child i for the
+ * document (len 0 = the child carries no offsets); has_slop 0 = no slop limit (in-order only) */
+int orc_within_range(size_t n_children, const uint8_t *const *offsets, const size_t *lens, int has_slop, uint32_t max_slop,
+                     int in_order);
 
 /* ---- scorer_oracle.c ------------------------------------------------------------------------ */
 /* One matched document seen by a scorer: a flat intersection/union of term leaves

@@ -797,3 +797,96 @@ double orc_time_search3(OrcInvIndex **terms, size_t nq, const uint32_t *doc_len,
     free(th);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------ proximity (slop / in-order) ----------
+ * RS/index_result/src/core/proximity.rs: OffsetIter::Term (:45-52: varint deltas accumulated into positions),
+ * within_range_in_order (:127-180), within_range_unordered (:184-220), is_within_range (:262-299: children without offsets
+ * are left out, <= 1 stream left is trivially in range).  Term children only (no Merge streams). */
+typedef struct {
+    const uint8_t *p, *end;
+    uint32_t last;
+} OffCursor;
+static int off_next(OffCursor *c, uint32_t *pos) {
+    if (c->p >= c->end) return 0;
+    uint64_t d = 0;
+    /* a truncated varint is an error in the reference (read(...).ok()? -> None): treat as EOF */
+    const uint8_t *q = c->p;
+    uint8_t b = *q++;
+    uint64_t val = b & 0x7f;
+    while (b & 0x80) {
+        if (q >= c->end) return 0;
+        val += 1;
+        b = *q++;
+        val = (val << 7) | (b & 0x7f);
+    }
+    d = val;
+    c->p = q;
+    c->last = c->last + (uint32_t)d; /* wrapping_add */
+    *pos = c->last;
+    return 1;
+}
+int orc_within_range(size_t n_children, const uint8_t *const *offsets, const size_t *lens, int has_slop, uint32_t max_slop_in,
+                     int in_order) {
+    OffCursor it[64];
+    size_t n = 0;
+    for (size_t i = 0; i < n_children && n < 64; i++)
+        if (lens[i]) { /* has_offsets */
+            it[n].p = offsets[i];
+            it[n].end = offsets[i] + lens[i];
+            it[n].last = 0;
+            n++;
+        }
+    if (n_children <= 1 || n <= 1) return 1;
+    const uint32_t max_slop = has_slop ? max_slop_in : 0xFFFFFFFFu;
+    uint32_t positions[64];
+    if (in_order) {
+        for (size_t i = 0; i < n; i++) positions[i] = 0;
+        for (;;) {
+            int32_t span = 0;
+            int over = 0;
+            for (size_t i = 0; i < n; i++) {
+                uint32_t pos;
+                if (i == 0) {
+                    if (!off_next(&it[0], &pos)) return 0;
+                } else {
+                    pos = positions[i];
+                }
+                const uint32_t last_pos = i == 0 ? 0u : positions[i - 1];
+                while (pos < last_pos)
+                    if (!off_next(&it[i], &pos)) return 0;
+                positions[i] = pos;
+                if (i > 0) {
+                    span += (int32_t)pos - (int32_t)last_pos - 1;
+                    if (span > 0 && (uint32_t)span > max_slop) {
+                        over = 1;
+                        break;
+                    }
+                }
+            }
+            if (!over) return 1;
+        }
+    }
+    for (size_t i = 0; i < n; i++)
+        if (!off_next(&it[i], &positions[i])) return 0;
+    uint32_t max_pos = 0;
+    for (size_t i = 0; i < n; i++)
+        if (positions[i] >= max_pos) max_pos = positions[i];
+    for (;;) {
+        uint32_t min_pos = 0xFFFFFFFFu;
+        size_t min_idx = 0;
+        for (size_t i = 0; i < n; i++)
+            if (positions[i] < min_pos) { /* min_by_key: the first minimum */
+                min_pos = positions[i];
+                min_idx = i;
+            }
+        if (min_pos != max_pos) {
+            const int32_t span = (int32_t)max_pos - (int32_t)min_pos - ((int32_t)n - 1);
+            if (span < 0 || (uint32_t)span <= max_slop) return 1;
+        }
+        uint32_t np;
+        if (!off_next(&it[min_idx], &np)) break;
+        positions[min_idx] = np;
+        if (np > max_pos) max_pos = np;
+    }
+    return 0;
+}

@@ -137,6 +137,11 @@ struct II_PostingList {
     size_t estimated = 0; // unfiltered unique docs (num_estimated of the leaf iterator)
     uint32_t last_id = 0;
     std::shared_ptr<SharedDeviceBlock> owner; // set: d_ids / d_freqs are slices of owner->p
+    // term positions (Full codec, kept on request): the encoded block bytes stay on the device and every posting points at
+    // its offsets payload inside them
+    const uint8_t *d_bytes = nullptr;
+    const uint32_t *d_off_pos = nullptr, *d_off_len = nullptr;
+    std::shared_ptr<SharedDeviceBlock> bytes_owner;
     ~II_PostingList() {
         if (!owner) {
             dfree(d_ids);
@@ -245,12 +250,12 @@ bool decode_block(const II_BlockView &b, II_Codec codec, uint32_t *ids, uint32_t
 }
 } // namespace
 
-extern "C" {
-
 // Decode MANY posting lists in one go: ONE gather of all block bytes + block tables into pinned staging, ONE H2D copy,
 // ONE decode launch (decode_blocks_staged_kernel), ONE synchronisation.  The lists share two device arrays (ids, freqs).
-size_t II_PostingList_FromBlocksBatch(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec,
-                                      II_PostingList **out) {
+// keep_offsets (Full codec): the encoded bytes stay resident and every posting records where its term positions are.
+static size_t from_blocks_batch(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec, bool keep_offsets,
+                                II_PostingList **out) {
+    keep_offsets = keep_offsets && codec == II_CODEC_FULL;
     for (size_t i = 0; i < n_lists; i++) out[i] = nullptr;
     if (n_lists == 0) return 0;
     Ctx &c = ctx();
@@ -337,17 +342,24 @@ size_t II_PostingList_FromBlocksBatch(size_t n_lists, const II_BlockView *const 
         c.stats.decode_host_us = now_us() - tg;
         const double t0 = now_us();
         auto blockmem = std::make_shared<SharedDeviceBlock>();
-        blockmem->p = dalloc<uint8_t>((n ? n : 1) * 8);
+        blockmem->p = dalloc<uint8_t>((n ? n : 1) * (keep_offsets ? 16 : 8));
         uint8_t *d_stage = dalloc<uint8_t>(stage_bytes);
         bool ok = blockmem->p && d_stage;
         uint32_t *d_ids = reinterpret_cast<uint32_t *>(blockmem->p), *d_freqs = d_ids + n;
+        uint32_t *d_off_pos = keep_offsets ? d_freqs + n : nullptr, *d_off_len = keep_offsets ? d_off_pos + n : nullptr;
         ok = ok && cudaMemcpyAsync(d_stage, stg, stage_bytes, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
         const uint32_t *d_first = reinterpret_cast<const uint32_t *>(d_stage + bytes_pad), *d_boff = d_first + B, *d_eoff = d_boff + B + 1;
-        ok = ok && ii_launch_decode_staged(d_stage, d_boff, d_first, d_eoff, (uint32_t)B, (int)codec, d_ids, d_freqs, nullptr, c.stream) == cudaSuccess;
+        ok = ok && ii_launch_decode_staged(d_stage, d_boff, d_first, d_eoff, (uint32_t)B, (int)codec, d_ids, d_freqs, nullptr, d_off_pos, d_off_len, c.stream) == cudaSuccess;
         ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
         c.stats.h2d_us = now_us() - t0;
         c.stats.kernel_launches += 1;
-        dfree(d_stage);
+        std::shared_ptr<SharedDeviceBlock> bytesmem;
+        if (keep_offsets && ok) {
+            bytesmem = std::make_shared<SharedDeviceBlock>();
+            bytesmem->p = d_stage;
+        } else {
+            dfree(d_stage);
+        }
         if (!ok) {
             cudaGetLastError();
             return built;
@@ -358,6 +370,12 @@ size_t II_PostingList_FromBlocksBatch(size_t n_lists, const II_BlockView *const 
             pl->owner = blockmem;
             pl->d_ids = d_ids + e0;
             pl->d_freqs = d_freqs + e0;
+            if (keep_offsets) {
+                pl->bytes_owner = bytesmem;
+                pl->d_bytes = d_stage;
+                pl->d_off_pos = d_off_pos + e0;
+                pl->d_off_len = d_off_len + e0;
+            }
             pl->n = pl->estimated = e1 - e0;
             pl->last_id = nblocks[l] ? (uint32_t)blocks[l][nblocks[l] - 1].last_doc_id : 0;
             out[l] = pl;
@@ -367,6 +385,19 @@ size_t II_PostingList_FromBlocksBatch(size_t n_lists, const II_BlockView *const 
     }
     return built;
 }
+
+extern "C" {
+
+size_t II_PostingList_FromBlocksBatch(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec,
+                                      II_PostingList **out) {
+    return from_blocks_batch(n_lists, blocks, nblocks, codec, false, out);
+}
+// same, keeping the term positions of a Full-codec index on the device (needed by slop / in-order intersections)
+size_t II_PostingList_FromBlocksBatchOffsets(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec,
+                                             II_PostingList **out) {
+    return from_blocks_batch(n_lists, blocks, nblocks, codec, true, out);
+}
+int II_PostingList_HasOffsets(const II_PostingList *pl) { return pl->d_off_len != nullptr; }
 
 II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nblocks, II_Codec codec,
                                           uint32_t field_mask_filter, int decode_on_device) {
@@ -603,14 +634,22 @@ namespace {
 // Enqueue the kernels of an intersection on ctx().stream.  On return rs->d_len holds (will hold, in
 // stream order) the number of hits; rs->len is NOT set.  *trivially_empty = an input list is empty.
 // modes (nullable): per list 0 = required, 1 = NOT, 2 = OPTIONAL (IntersectArgs::mode); at least one list is required
-bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_ResultSet *rs, bool *trivially_empty, const int *modes = nullptr) {
+struct PhraseSpec {
+    uint32_t max_slop; // 0xFFFFFFFF: no limit (in-order only)
+    bool in_order;
+};
+bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_ResultSet *rs, bool *trivially_empty, const int *modes = nullptr,
+                       const PhraseSpec *phrase = nullptr) {
     auto mode_of = [&](size_t i) { return modes ? modes[i] : 0; };
+    if (phrase && n > (size_t)kPhraseMaxLists) return false;
     // Intersection::new: stable sort ascending by num_estimated (leaf weight 1.0), intersection.rs:110-145; NOT / OPTIONAL
     // children estimate max_doc_id (not.rs / optional.rs num_estimated): they sort behind every term, in their given order
     std::vector<uint32_t> order(n);
     for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
     auto est = [&](uint32_t a) { return mode_of(a) ? (size_t)1 << 62 : lists[a]->estimated; };
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return est(a) < est(b); });
+    // an in-order intersection keeps the children as given: their order is the order the terms must appear in
+    // (intersection.rs new_sorted_by: `if !in_order { children.sort_by(compare) }`)
+    if (!(phrase && phrase->in_order)) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return est(a) < est(b); });
     // the kernel is driven by the REQUIRED list with the fewest actual entries (a field-mask filter may make
     // that differ from the estimate order); the aggregate child order stays the reference's
     size_t drv = n;
@@ -633,8 +672,13 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
     uint32_t *tmp_idx = dalloc<uint32_t>(stride), *tmp_pos = dalloc<uint32_t>(stride * n);
     uint32_t *counts = dalloc<uint32_t>(nchunks), *offsets = dalloc<uint32_t>(nchunks);
     uint32_t *scratch = (n > 1) ? dalloc<uint32_t>(rs->cap * n) : nullptr;
+    const bool check_phrase = phrase && n > 1;
+    const uint32_t pchunks = (uint32_t)((rs->cap + 1023) / 1024);
+    uint32_t *hit_pos = check_phrase ? dalloc<uint32_t>(rs->cap * n) : nullptr, *flags = check_phrase ? dalloc<uint32_t>(rs->cap) : nullptr;
+    uint32_t *pcounts = check_phrase ? dalloc<uint32_t>(pchunks) : nullptr, *poffsets = check_phrase ? dalloc<uint32_t>(pchunks) : nullptr;
+    uint32_t *pre_docs = check_phrase ? dalloc<uint32_t>(rs->cap) : nullptr, *pre_len = check_phrase ? dalloc<uint32_t>(4) : nullptr;
     bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && rs->d_len && tmp_idx && tmp_pos && counts && offsets &&
-              (n == 1 || scratch);
+              (n == 1 || scratch) && (!check_phrase || (hit_pos && flags && pcounts && poffsets && pre_docs && pre_len));
     if (ok) {
         // kernel list order: driver first, then the rest ascending by length (cheap rejections first)
         std::vector<uint32_t> korder;
@@ -656,7 +700,7 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
         a.counts = counts;
         a.stride = stride;
         cudaEventRecord(c.e0, c.stream);
-        ok = ii_launch_intersect(a, nchunks, offsets, rs->d_len, c.stream) == cudaSuccess;
+        ok = ii_launch_intersect(a, nchunks, offsets, check_phrase ? pre_len : rs->d_len, c.stream) == cudaSuccess;
         GatherArgs ga{};
         ga.ids0 = A->d_ids;
         ga.n = (uint32_t)n;
@@ -665,7 +709,8 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
         ga.counts = counts;
         ga.offsets = offsets;
         ga.stride = stride;
-        ga.out_doc = rs->d_docs;
+        ga.out_doc = check_phrase ? pre_docs : rs->d_docs;
+        ga.out_pos = hit_pos;
         ga.fstride = rs->cap;
         for (size_t k = 0; k < n; k++) {
             ga.freqs[k] = lists[order[korder[k]]]->d_freqs;
@@ -674,13 +719,43 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
         // rows are produced in kernel-slot order, then placed at their aggregate child index
         ga.out_freq = (n > 1) ? scratch : rs->d_freqs;
         ok = ok && ii_launch_gather(ga, nchunks, c.stream) == cudaSuccess;
-        if (ok && n > 1)
+        if (ok && check_phrase) {
+            // slop / in-order: one thread per hit walks the term positions of its children (kept on the device by the
+            // decoder), survivors are compacted in order straight into the aggregate rows
+            PhraseArgs pa{};
+            pa.n = (uint32_t)n;
+            pa.max_slop = phrase->max_slop;
+            pa.in_order = phrase->in_order ? 1 : 0;
+            pa.pos = hit_pos;
+            pa.fstride = rs->cap;
+            for (size_t k = 0; k < n; k++) {
+                const II_PostingList *L = lists[order[korder[k]]];
+                const uint32_t j = korder[k]; // aggregate child index of kernel slot k
+                pa.row[j] = (uint32_t)k;
+                pa.bytes[j] = L->d_bytes;
+                pa.off_pos[j] = L->d_off_pos;
+                pa.off_len[j] = mode_of(order[korder[k]]) == 1 ? nullptr : L->d_off_len;
+            }
+            // compaction writes freq row k (kernel slot) of the survivors; the rows are then placed like the plain path
+            ok = ii_launch_phrase_filter(pa, pre_len, (uint32_t)rs->cap, flags, pcounts, poffsets, rs->d_len, pre_docs, scratch, rs->cap,
+                                         rs->d_docs, hit_pos /* reused: compacted freq rows */, rs->cap, c.stream) == cudaSuccess;
+            for (size_t k = 0; k < n; k++)
+                ok = ok && cudaMemcpyAsync(rs->d_freqs + (size_t)korder[k] * rs->cap, hit_pos + k * rs->cap, rs->cap * 4,
+                                           cudaMemcpyDeviceToDevice, c.stream) == cudaSuccess;
+            c.stats.kernel_launches += 4;
+        } else if (ok && n > 1)
             for (size_t k = 0; k < n; k++)
                 ok = ok && cudaMemcpyAsync(rs->d_freqs + (size_t)korder[k] * rs->cap, scratch + k * rs->cap, rs->cap * 4,
                                            cudaMemcpyDeviceToDevice, c.stream) == cudaSuccess;
         cudaEventRecord(c.e1, c.stream);
         c.stats.kernel_launches += 3;
     }
+    dfree(hit_pos);
+    dfree(flags);
+    dfree(pcounts);
+    dfree(poffsets);
+    dfree(pre_docs);
+    dfree(pre_len);
     dfree(tmp_idx);
     dfree(tmp_pos);
     dfree(counts);
@@ -882,6 +957,33 @@ II_ResultSet *II_IntersectEx(II_PostingList *const *lists, const int *modes, siz
     auto *rs = new II_ResultSet();
     bool empty = false;
     bool ok = intersect_enqueue(c, lists, n, rs, &empty, modes);
+    if (ok && !empty) {
+        ok = cudaMemcpyAsync(c.h_total, rs->d_len, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+        if (ok) finish_len(c, rs);
+    }
+    if (!ok) {
+        delete rs;
+        return nullptr;
+    }
+    return rs;
+}
+
+// AND with the reference's proximity constraints (intersection.rs:201-242 -> index_result proximity.rs): max_slop < 0 = no
+// limit; in_order = the terms must appear in the order of `lists` (which is then also the aggregate child order).  Every
+// required / optional list must carry term positions (II_PostingList_FromBlocksBatchOffsets, Full codec).
+II_ResultSet *II_IntersectPhrase(II_PostingList *const *lists, const int *modes, size_t n, int32_t max_slop, int in_order) {
+    if (n == 0 || n > (size_t)kPhraseMaxLists) return nullptr;
+    for (size_t i = 0; i < n; i++)
+        if ((!modes || modes[i] != 1) && !lists[i]->d_off_len) return nullptr;
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    auto *rs = new II_ResultSet();
+    bool empty = false;
+    const PhraseSpec ph{max_slop < 0 ? 0xFFFFFFFFu : (uint32_t)max_slop, in_order != 0};
+    const bool constrained = max_slop >= 0 || in_order;
+    bool ok = intersect_enqueue(c, lists, n, rs, &empty, modes, constrained ? &ph : nullptr);
     if (ok && !empty) {
         ok = cudaMemcpyAsync(c.h_total, rs->d_len, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
         ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
@@ -1293,6 +1395,7 @@ struct II_TermCache {
     std::unordered_map<II_PostingList *, size_t> zombies;        // replaced / invalidated while pinned: list -> refs left
     size_t max_bytes = 0, resident_bytes = 0;
     uint64_t tick = 0;
+    bool keep_offsets = false; // Full-codec lists keep their term positions on the device (slop / in-order queries)
     II_TermCacheStats st{};
     void evict_locked() {
         while (resident_bytes > max_bytes) {
@@ -1337,6 +1440,10 @@ void II_TermCache_Free(II_TermCache *c) {
     for (auto &kv : c->live) delete kv.second.pl;
     for (auto &kv : c->zombies) delete kv.first;
     delete c;
+}
+void II_TermCache_KeepOffsets(II_TermCache *c, int on) {
+    std::lock_guard<std::mutex> g(c->mu);
+    c->keep_offsets = on != 0;
 }
 void II_TermCache_Invalidate(II_TermCache *c, uint64_t key) {
     std::lock_guard<std::mutex> g(c->mu);
@@ -1385,7 +1492,12 @@ size_t II_TermCache_Acquire(II_TermCache *c, size_t n, const uint64_t *keys, con
             b[k] = blocks[uniq[k]];
             nb[k] = nblocks[uniq[k]];
         }
-        II_PostingList_FromBlocksBatch(uniq.size(), b.data(), nb.data(), codec, built.data());
+        bool keep;
+        {
+            std::lock_guard<std::mutex> g(c->mu);
+            keep = c->keep_offsets;
+        }
+        from_blocks_batch(uniq.size(), b.data(), nb.data(), codec, keep, built.data());
         std::lock_guard<std::mutex> g(c->mu);
         for (size_t k = 0; k < uniq.size(); k++) {
             if (!built[k]) continue;
@@ -1395,6 +1507,10 @@ size_t II_TermCache_Acquire(II_TermCache *c, size_t n, const uint64_t *keys, con
             e.version = versions[uniq[k]];
             e.pl = built[k];
             e.bytes = built[k]->n * 8;
+            if (built[k]->d_off_len) { // + positions index + the encoded bytes that stay resident
+                e.bytes += built[k]->n * 8;
+                for (size_t x = 0; x < nb[k]; x++) e.bytes += b[k][x].len;
+            }
             e.tick = ++c->tick;
             c->live[key] = e;
             c->key_of[built[k]] = key;
@@ -1852,7 +1968,8 @@ II_QueryIterator *II_NewOptionalIterator(II_QueryIterator *child, t_docId max_do
     return child;
 }
 
-static II_QueryIterator *build_aggregate(II_QueryIterator **its, size_t num, bool is_union, bool quick_exit, double weight) {
+static II_QueryIterator *build_aggregate(II_QueryIterator **its, size_t num, bool is_union, bool quick_exit, double weight,
+                                         const PhraseSpec *phrase = nullptr) {
     auto free_children = [&] {
         for (size_t i = 0; i < num; i++)
             if (its[i] && its[i]->Free) its[i]->Free(its[i]);
@@ -1917,6 +2034,10 @@ static II_QueryIterator *build_aggregate(II_QueryIterator **its, size_t num, boo
         II_ResultSet *rs = nullptr;
         if (is_union)
             rs = any_mode ? nullptr : II_Union(pls.data(), pls.size(), quick_exit ? 1 : 0);
+        else if (phrase)
+            rs = any_required ? II_IntersectPhrase(pls.data(), modes.data(), pls.size(),
+                                                   phrase->max_slop == 0xFFFFFFFFu ? -1 : (int32_t)phrase->max_slop, phrase->in_order)
+                              : nullptr;
         else if (!any_mode)
             rs = II_Intersect(pls.data(), pls.size());
         else if (any_required)
@@ -1934,13 +2055,26 @@ static II_QueryIterator *build_aggregate(II_QueryIterator **its, size_t num, boo
     return out ? &out->base : nullptr;
 }
 
-// RS/headers/iterators_ffi.h:309.  max_slop >= 0 / in_order (phrase constraints) need term offsets on the device: not yet —
-// NULL is returned and the caller keeps the reference's own iterator for that node.
+// RS/headers/iterators_ffi.h:309.  max_slop >= 0 / in_order (phrase constraints) are evaluated on the device when every child
+// is one of OUR term leaves carrying its term positions (Full codec decoded with offsets kept, at most kPhraseMaxLists
+// children); for anything else (foreign children, nested unions whose positions the reference merges, leaves without
+// positions) NULL is returned BEFORE anything is consumed and the caller keeps the reference's own iterator for that node.
 II_QueryIterator *NewIntersectionIterator(II_QueryIterator **its, size_t num, int32_t max_slop, bool in_order, double weight) {
-    if (max_slop >= 0 || in_order) return nullptr;
     if (!its || num == 0) {
         if (its) host_free(its);
         return II_NewEmptyIterator();
+    }
+    if (max_slop >= 0 || in_order) {
+        if (num > (size_t)kPhraseMaxLists) return nullptr;
+        for (size_t i = 0; i < num; i++) {
+            II_QueryIterator *c = its[i];
+            if (!c) return nullptr;
+            if (child_is_empty(c)) continue; // reduces the AND to empty whatever the constraint
+            if (!is_node(c) || NI(c)->kind != NODE_LEAF || !NI(c)->pl) return nullptr;
+            if (NI(c)->mode != LEAF_NOT && !NI(c)->pl->d_off_len) return nullptr;
+        }
+        const PhraseSpec ph{max_slop < 0 ? 0xFFFFFFFFu : (uint32_t)max_slop, in_order};
+        return build_aggregate(its, num, false, false, weight, &ph);
     }
     return build_aggregate(its, num, false, false, weight);
 }

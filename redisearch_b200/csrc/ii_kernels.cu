@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_blocks_staged_kernel(co
                                                                               const uint32_t *__restrict__ first_id,
                                                                               const uint32_t *__restrict__ entry_off, uint32_t nblocks, int codec,
                                                                               uint32_t *__restrict__ out_ids, uint32_t *__restrict__ out_freqs,
-                                                                              uint32_t *__restrict__ out_masks) {
+                                                                              uint32_t *__restrict__ out_masks, uint32_t *__restrict__ out_off_pos,
+                                                                              uint32_t *__restrict__ out_off_len) {
     extern __shared__ __align__(16) uint8_t s_bytes[];
     const uint32_t b0 = blockIdx.x * kDecodeThreads;
     const uint32_t b1 = min(b0 + (uint32_t)kDecodeThreads, nblocks);
@@ -117,6 +118,8 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_blocks_staged_kernel(co
     const uint32_t b = b0 + threadIdx.x;
     if (b >= b1) return;
     const uint8_t *p = staged ? s_bytes + (byte_off[b] - lo) : bytes + byte_off[b];
+    const uint8_t *const p0 = p; // position of a byte in the gathered stream = byte_off[b] + (its address - p0)
+    const uint32_t stream0 = byte_off[b];
     const uint32_t n = entry_off[b + 1] - entry_off[b];
     uint32_t o = entry_off[b];
     const uint32_t base0 = first_id[b];
@@ -151,6 +154,10 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_blocks_staged_kernel(co
             if (codec == 0) { // Full: delta, freq, fieldMask, offsetsLen + offsets bytes
                 freq = v[1];
                 mask = v[2];
+                if (out_off_pos) { // the term's position bytes stay where they are, in the gathered stream kept on the device
+                    out_off_pos[o] = stream0 + (uint32_t)(p - p0);
+                    out_off_len[o] = v[3];
+                }
                 p += v[3];
             } else if (codec == 1) { // FreqsOnly
                 freq = v[1];
@@ -439,12 +446,15 @@ __global__ void __launch_bounds__(kIIThreads) gather_kernel(const GatherArgs g) 
         const size_t o = (size_t)off + r;
         g.out_doc[o] = g.ids0[idx];
         g.out_freq[o] = g.freqs[0][idx];
+        if (g.out_pos) g.out_pos[o] = idx;
         for (uint32_t j = 1; j < g.n; j++) {
             uint32_t f = 0; // NOT children and absent OPTIONAL children are virtual results: freq 0
+            uint32_t p = 0xFFFFFFFFu;
             if (g.mode[j] != 1) {
-                const uint32_t p = g.tmp_pos[(size_t)j * g.stride + idx];
+                p = g.tmp_pos[(size_t)j * g.stride + idx];
                 if (g.mode[j] == 0 || p != 0xFFFFFFFFu) f = g.freqs[j][p];
             }
+            if (g.out_pos) g.out_pos[(size_t)j * g.fstride + o] = p;
             g.out_freq[(size_t)j * g.fstride + o] = f;
         }
     }
@@ -840,6 +850,178 @@ cudaError_t ii_launch_fused_search(const FusedQuery *d_queries, uint32_t nq, uin
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// phrase constraints: slop / in-order over the term positions of every hit
+// (RS/index_result/src/core/proximity.rs: OffsetIter::Term :45-52, within_range_in_order :127-180,
+//  within_range_unordered :184-220, is_within_range :262-299; called from intersection.rs:201-242)
+// ------------------------------------------------------------------------------------------------
+struct OffCur {
+    const uint8_t *p, *end;
+    uint32_t last;
+};
+__device__ __forceinline__ bool off_next(OffCur &c, uint32_t &pos) {
+    if (c.p >= c.end) return false;
+    const uint8_t *q = c.p;
+    uint8_t b = *q++;
+    uint32_t val = b & 0x7f;
+    while (b & 0x80) { // RS/varint: 7-bit groups, most significant first, +1 per continuation
+        if (q >= c.end) return false;
+        val += 1;
+        b = *q++;
+        val = (val << 7) | (b & 0x7f);
+    }
+    c.p = q;
+    c.last += val; // wrapping
+    pos = c.last;
+    return true;
+}
+// one thread per hit; children in AGGREGATE order (for in_order queries that is the query order: the reference does not sort
+// the children of an in-order intersection, intersection.rs:110-121)
+__global__ void phrase_filter_kernel(const PhraseArgs a, const uint32_t *__restrict__ d_len, uint32_t cap_len, uint32_t *__restrict__ flags) {
+    const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
+    for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < m; o += gridDim.x * blockDim.x) {
+        OffCur it[kPhraseMaxLists];
+        uint32_t n = 0;
+        for (uint32_t j = 0; j < a.n; j++) {
+            const uint32_t p = a.pos[(size_t)a.row[j] * a.fstride + o];
+            const uint32_t len = (a.off_len[j] && p != 0xFFFFFFFFu) ? a.off_len[j][p] : 0u; // virtual results carry no offsets
+            if (len) { // has_offsets
+                it[n].p = a.bytes[j] + a.off_pos[j][p];
+                it[n].end = it[n].p + len;
+                it[n].last = 0;
+                n++;
+            }
+        }
+        bool ok;
+        if (a.n <= 1 || n <= 1) {
+            ok = true;
+        } else if (a.in_order) {
+            uint32_t positions[kPhraseMaxLists];
+            for (uint32_t i = 0; i < n; i++) positions[i] = 0;
+            ok = false;
+            bool done = false;
+            while (!done) {
+                int32_t span = 0;
+                bool over = false;
+                for (uint32_t i = 0; i < n; i++) {
+                    uint32_t pos;
+                    if (i == 0) {
+                        if (!off_next(it[0], pos)) {
+                            done = true;
+                            break;
+                        }
+                    } else {
+                        pos = positions[i];
+                    }
+                    const uint32_t last_pos = i == 0 ? 0u : positions[i - 1];
+                    bool eof = false;
+                    while (pos < last_pos)
+                        if (!off_next(it[i], pos)) {
+                            eof = true;
+                            break;
+                        }
+                    if (eof) {
+                        done = true;
+                        break;
+                    }
+                    positions[i] = pos;
+                    if (i > 0) {
+                        span += (int32_t)pos - (int32_t)last_pos - 1;
+                        if (span > 0 && (uint32_t)span > a.max_slop) {
+                            over = true;
+                            break;
+                        }
+                    }
+                }
+                if (done) break;
+                if (!over) {
+                    ok = true;
+                    break;
+                }
+            }
+        } else {
+            uint32_t positions[kPhraseMaxLists];
+            ok = false;
+            bool primed = true;
+            for (uint32_t i = 0; i < n; i++) primed = primed && off_next(it[i], positions[i]);
+            if (primed) {
+                uint32_t max_pos = 0;
+                for (uint32_t i = 0; i < n; i++)
+                    if (positions[i] >= max_pos) max_pos = positions[i];
+                for (;;) {
+                    uint32_t min_pos = 0xFFFFFFFFu, min_idx = 0;
+                    for (uint32_t i = 0; i < n; i++)
+                        if (positions[i] < min_pos) {
+                            min_pos = positions[i];
+                            min_idx = i;
+                        }
+                    if (min_pos != max_pos) {
+                        const int32_t span = (int32_t)max_pos - (int32_t)min_pos - ((int32_t)n - 1);
+                        if (span < 0 || (uint32_t)span <= a.max_slop) {
+                            ok = true;
+                            break;
+                        }
+                    }
+                    uint32_t np;
+                    if (!off_next(it[min_idx], np)) break;
+                    positions[min_idx] = np;
+                    if (np > max_pos) max_pos = np;
+                }
+            }
+        }
+        flags[o] = ok ? 1u : 0u;
+    }
+}
+// per 1024-entry chunk: how many flagged
+__global__ void flag_count_kernel(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ d_len, uint32_t cap_len,
+                                  uint32_t *__restrict__ chunk_counts) {
+    __shared__ uint32_t s_cnt;
+    const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * 1024u;
+    uint32_t c = 0;
+    for (uint32_t i = threadIdx.x; i < 1024u; i += blockDim.x)
+        if (base + i < m && flags[base + i]) c++;
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_counts[blockIdx.x] = s_cnt;
+}
+// ordered compaction of docs and the n freq rows (one warp per chunk keeps the order with ballots)
+__global__ void flag_compact_kernel(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ d_len, uint32_t cap_len,
+                                    const uint32_t *__restrict__ chunk_off, const uint32_t *__restrict__ docs,
+                                    const uint32_t *__restrict__ freqs, uint32_t n, size_t fstride, uint32_t *__restrict__ out_docs,
+                                    uint32_t *__restrict__ out_freqs, size_t out_fstride) {
+    const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
+    const uint32_t base = blockIdx.x * 1024u;
+    uint32_t o = chunk_off[blockIdx.x];
+    const int lane = threadIdx.x;
+    for (uint32_t i0 = 0; i0 < 1024u; i0 += 32) {
+        const uint32_t i = base + i0 + lane;
+        const bool keep = i < m && flags[i];
+        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const uint32_t dst = o + __popc(mask & ((1u << lane) - 1u));
+            out_docs[dst] = docs[i];
+            for (uint32_t j = 0; j < n; j++) out_freqs[(size_t)j * out_fstride + dst] = freqs[(size_t)j * fstride + i];
+        }
+        o += __popc(mask);
+    }
+}
+
+cudaError_t ii_launch_phrase_filter(const PhraseArgs &a, const uint32_t *d_len, uint32_t cap_len, uint32_t *d_flags, uint32_t *d_counts,
+                                    uint32_t *d_offsets, uint32_t *d_total, const uint32_t *d_docs, const uint32_t *d_freqs, size_t fstride,
+                                    uint32_t *d_out_docs, uint32_t *d_out_freqs, size_t out_fstride, cudaStream_t s) {
+    if (!cap_len) return cudaMemsetAsync(d_total, 0, 4, s);
+    const uint32_t chunks = (cap_len + 1023) / 1024;
+    phrase_filter_kernel<<<std::max(1u, std::min((cap_len + 127) / 128, 148u * 16)), 128, 0, s>>>(a, d_len, cap_len, d_flags);
+    flag_count_kernel<<<chunks, 256, 0, s>>>(d_flags, d_len, cap_len, d_counts);
+    scan_kernel<<<1, 1024, 0, s>>>(d_counts, chunks, d_offsets, d_total);
+    flag_compact_kernel<<<chunks, 32, 0, s>>>(d_flags, d_len, cap_len, d_offsets, d_docs, d_freqs, a.n, fstride, d_out_docs, d_out_freqs,
+                                              out_fstride);
+    return cudaGetLastError();
+}
+
 // ================================================================================================
 // launchers
 // ================================================================================================
@@ -858,7 +1040,7 @@ cudaError_t ii_launch_decode(const uint8_t *d_bytes, const uint64_t *d_byte_off,
 }
 cudaError_t ii_launch_decode_staged(const uint8_t *d_bytes, const uint32_t *d_byte_off, const uint32_t *d_first_id,
                                     const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint32_t *d_ids, uint32_t *d_freqs,
-                                    uint32_t *d_masks, cudaStream_t s) {
+                                    uint32_t *d_masks, uint32_t *d_off_pos, uint32_t *d_off_len, cudaStream_t s) {
     if (!nblocks) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
@@ -867,7 +1049,7 @@ cudaError_t ii_launch_decode_staged(const uint8_t *d_bytes, const uint32_t *d_by
         attr_set = true;
     }
     decode_blocks_staged_kernel<<<(nblocks + kDecodeThreads - 1) / kDecodeThreads, kDecodeThreads, kDecodeSmem, s>>>(
-        d_bytes, d_byte_off, d_first_id, d_entry_off, nblocks, codec, d_ids, d_freqs, d_masks);
+        d_bytes, d_byte_off, d_first_id, d_entry_off, nblocks, codec, d_ids, d_freqs, d_masks, d_off_pos, d_off_len);
     return cudaGetLastError();
 }
 cudaError_t ii_launch_mask_filter(const uint32_t *d_ids, const uint32_t *d_freqs, const uint32_t *d_masks, uint32_t n,

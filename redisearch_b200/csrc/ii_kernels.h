@@ -33,8 +33,26 @@ struct GatherArgs {
     size_t stride;   // of tmp_pos
     uint32_t *out_doc;
     uint32_t *out_freq; // [n][fstride]
+    uint32_t *out_pos;  // nullable, [n][fstride]: position of the hit inside list j (phrase checks read the term positions there)
     size_t fstride;
 };
+
+// phrase constraints (slop / in-order): the term positions of every hit, children in aggregate order
+constexpr int kPhraseMaxLists = 8;
+struct PhraseArgs {
+    const uint8_t *bytes[kPhraseMaxLists];    // gathered block bytes of list j (the offsets payloads live inside)
+    const uint32_t *off_pos[kPhraseMaxLists]; // per posting: start of its offsets payload in bytes[j]
+    const uint32_t *off_len[kPhraseMaxLists]; // per posting: length (0 / NULL array = the child carries no offsets)
+    const uint32_t *pos;                      // [n][fstride] posting position of hit o, rows in KERNEL-slot order (GatherArgs::out_pos)
+    uint32_t row[kPhraseMaxLists];            // aggregate child j -> its row of pos
+    size_t fstride;
+    uint32_t n;
+    uint32_t max_slop; // 0xFFFFFFFF = no limit
+    int in_order;
+};
+cudaError_t ii_launch_phrase_filter(const PhraseArgs &a, const uint32_t *d_len, uint32_t cap_len, uint32_t *d_flags, uint32_t *d_counts,
+                                    uint32_t *d_offsets, uint32_t *d_total, const uint32_t *d_docs, const uint32_t *d_freqs, size_t fstride,
+                                    uint32_t *d_out_docs, uint32_t *d_out_freqs, size_t out_fstride, cudaStream_t s);
 
 struct ScoreArgs {
     int scorer; // II_Scorer numbering
@@ -86,7 +104,7 @@ cudaError_t ii_launch_decode(const uint8_t *d_bytes, const uint64_t *d_byte_off,
 // entry_off[nblocks+1] into the output arrays), blocks of MANY lists back to back
 cudaError_t ii_launch_decode_staged(const uint8_t *d_bytes, const uint32_t *d_byte_off, const uint32_t *d_first_id,
                                     const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint32_t *d_ids, uint32_t *d_freqs,
-                                    uint32_t *d_masks, cudaStream_t s);
+                                    uint32_t *d_masks, uint32_t *d_off_pos, uint32_t *d_off_len, cudaStream_t s);
 cudaError_t ii_launch_mask_filter(const uint32_t *d_ids, const uint32_t *d_freqs, const uint32_t *d_masks, uint32_t n,
                                   uint32_t filter, uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_total,
                                   uint32_t *d_out_ids, uint32_t *d_out_freqs, cudaStream_t s);

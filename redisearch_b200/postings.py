@@ -60,6 +60,8 @@ _P, _SZ = C.c_void_p, C.c_size_t
 SIGNATURES = [
     ("II_PostingList_FromBlocks", _P, [C.POINTER(II_BlockView), _SZ, C.c_int, C.c_uint32, C.c_int]),
     ("II_PostingList_FromBlocksBatch", _SZ, [_SZ, _P, _P, C.c_int, _P]),
+    ("II_PostingList_FromBlocksBatchOffsets", _SZ, [_SZ, _P, _P, C.c_int, _P]),
+    ("II_PostingList_HasOffsets", C.c_int, [_P]),
     ("II_PostingList_FromArrays", _P, [_P, _P, _SZ]),
     ("II_PostingList_FromDevice", _P, [_P, _P, _SZ]),
     ("II_PostingList_Len", _SZ, [_P]),
@@ -87,6 +89,7 @@ SIGNATURES = [
     ("II_MergeShardTopN", _SZ, [_P, _P, _P, _SZ, _SZ, _SZ, _P, _P]),
     ("II_NewResultIterator", _QI, [_P, C.c_double]),
     ("II_IntersectEx", _P, [_P, _P, _SZ]),
+    ("II_IntersectPhrase", _P, [_P, _P, _SZ, C.c_int32, C.c_int]),
     ("NewIntersectionIterator", _QI, [_P, _SZ, C.c_int32, C.c_bool, C.c_double]),
     ("NewUnionIterator", _QI, [_P, C.c_int32, C.c_bool, C.c_double, C.c_int, C.c_char_p, _P]),
     ("II_NewEmptyIterator", _QI, []),
@@ -101,6 +104,7 @@ SIGNATURES = [
     ("II_TermCache_Acquire", _SZ, [_P, _SZ, _P, _P, _P, _P, C.c_int, _P]),
     ("II_TermCache_Release", None, [_P, _SZ, _P]),
     ("II_TermCache_Invalidate", None, [_P, C.c_uint64]),
+    ("II_TermCache_KeepOffsets", None, [_P, C.c_int]),
     ("II_TermCache_GetStats", II_TermCacheStats, [_P]),
     ("II_GetStats", II_Stats, [C.c_bool]),
     ("II_Version", C.c_char_p, []),
@@ -250,6 +254,32 @@ class ResultSet:
 
 def intersect(lists) -> ResultSet:
     return ResultSet(lib().II_Intersect(_list_array(lists), len(lists)))
+
+
+def postings_with_offsets(block_lists, codec=0):
+    """II_PostingList_FromBlocksBatchOffsets: block_lists[i] = list of (first, last, n, bytes) of term i (Full codec); the term
+    positions stay on the device for II_IntersectPhrase"""
+    views, keep = [], []
+    for blocks in block_lists:
+        arr = (II_BlockView * max(1, len(blocks)))()
+        for i, (first, last, n, data) in enumerate(blocks):
+            buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+            keep.append(buf)
+            arr[i] = II_BlockView(first, last, n, C.cast(buf, C.POINTER(C.c_uint8)), len(data))
+        views.append(arr)
+    n = len(block_lists)
+    ptrs = (C.c_void_p * n)(*[C.cast(v, C.c_void_p) for v in views])
+    ns = (C.c_size_t * n)(*[len(b) for b in block_lists])
+    out = (C.c_void_p * n)()
+    if lib().II_PostingList_FromBlocksBatchOffsets(n, ptrs, ns, codec, out) != n:
+        raise RuntimeError("batch decode failed")
+    return [PostingList(h) for h in out]
+
+
+def intersect_phrase(lists, max_slop, in_order, modes=None) -> ResultSet:
+    """II_IntersectPhrase: max_slop None = no limit"""
+    m = (C.c_int * len(lists))(*modes) if modes is not None else None
+    return ResultSet(lib().II_IntersectPhrase(_list_array(lists), m, len(lists), -1 if max_slop is None else int(max_slop), int(in_order)))
 
 
 def union(lists, quick_exit=False) -> ResultSet:

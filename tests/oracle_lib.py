@@ -397,6 +397,8 @@ def postings():
         L.orc_synth_doclen.argtypes = [C.c_uint64]
         L.orc_ii_fill_synth.restype = _SZ
         L.orc_ii_fill_synth.argtypes = [_P, C.c_uint64, C.c_uint64]
+        L.orc_within_range.restype = C.c_int
+        L.orc_within_range.argtypes = [_SZ, _P, _P, C.c_int, C.c_uint32, C.c_int]
         L.orc_time_search3.restype = C.c_double
         L.orc_time_search3.argtypes = [_P, _SZ, _P, C.c_uint64, C.c_double, _SZ, C.c_int, _P, _P, _P]
         _post_bound = True
@@ -463,6 +465,15 @@ class InvIndex:
             out.append((d.value, f.value, m.value))
         self.L.orc_reader_free(r)
         return out
+
+
+def within_range(offset_bytes, max_slop, in_order):
+    """proximity.rs is_within_range for term children; offset_bytes: list of bytes objects (varint deltas), max_slop None = no limit"""
+    n = len(offset_bytes)
+    bufs = [(C.c_uint8 * max(1, len(b))).from_buffer_copy(b or b"\0") for b in offset_bytes]
+    ptrs = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
+    lens = (C.c_size_t * n)(*[len(b) for b in offset_bytes])
+    return bool(postings().orc_within_range(n, ptrs, lens, 0 if max_slop is None else 1, 0 if max_slop is None else max_slop, int(in_order)))
 
 
 def run_intersect(indexes, union=False, quick=False):

@@ -336,3 +336,29 @@ def test_intersection_reference_edge_cases(L):
                 assert ld[0] == landed, (name, target, ld[0])
             for r in readers:
                 L.orc_reader_free(r)
+
+
+def test_proximity_known_answers_of_the_reference():
+    """RS/index_result/src/core/proximity.rs tests (:318-392): in-order / unordered slop checks over varint-delta offsets."""
+    vw1, vw2 = bytes([1, 8, 4, 3, 6]), bytes([4, 3, 25])  # positions 1,9,13,16,22 and 4,7,32
+    for slop, exp in ((0, False), (1, False), (2, True), (3, True), (4, True), (5, True)):
+        assert ol.within_range([vw1, vw2], slop, True) is exp, ("in_order", slop)
+    for slop, exp in ((0, False), (1, True), (2, True), (3, True), (4, True)):
+        assert ol.within_range([vw1, vw2], slop, False) is exp, ("unordered", slop)
+    assert ol.within_range([bytes([3]), bytes([4])], 0, True)          # in_order_exact_consecutive
+    assert not ol.within_range([bytes([10]), bytes([5])], 100, True)   # in_order_out_of_order_terms
+    assert not ol.within_range([bytes([10]), bytes([5])], 3, False)    # unordered_reversed_order_ok
+    assert ol.within_range([bytes([10]), bytes([5])], 4, False)
+    # a child without offsets is left out of the check; one stream left = trivially in range (is_within_range :282-290)
+    assert ol.within_range([b"", bytes([5])], 0, True) and ol.within_range([bytes([5])], 0, False)
+    # no slop limit, order only
+    assert ol.within_range([bytes([1]), bytes([90])], None, True) and not ol.within_range([bytes([90]), bytes([1])], None, True)
+    # multi-byte varints (the -1 bias per continuation): 300 = [0x81, 0x2c]
+    enc = lambda v: bytes(ol_varint(v))
+    assert ol.within_range([enc(300), enc(302)], 1, True) and not ol.within_range([enc(300), enc(303)], 1, True)
+
+
+def ol_varint(v):
+    out = (C.c_uint8 * 16)()
+    n = ol.postings().orc_varint_encode(v, out)
+    return bytes(out[:n])

@@ -681,3 +681,112 @@ def test_and_with_not_and_optional_children(ps):
     # no required child: refused
     arr = (C.c_void_p * 2)(pls[0].h, pls[1].h)
     assert not L.II_IntersectEx(arr, (C.c_int * 2)(1, 2), 2)
+
+
+def _positions_to_offsets(positions):
+    """term positions (ascending) -> the offsets payload of a Full-codec record: varint deltas"""
+    out, last = b"", 0
+    for p in positions:
+        buf = (C.c_uint8 * 16)()
+        n = ol.postings().orc_varint_encode(int(p) - last, buf)
+        out += bytes(buf[:n])
+        last = int(p)
+    return out
+
+
+def _phrase_corpus(rng, n_docs, n_terms, density, doc_words):
+    """Full-codec indexes of n_terms terms with random term positions; returns (indexes, per term {doc: offsets bytes})"""
+    idx, offs = [], []
+    for t in range(n_terms):
+        ix = ol.InvIndex(ol.CODEC_FULL)
+        docs = np.flatnonzero(rng.random(n_docs) < density[t]) + 1
+        m = {}
+        for d in docs.tolist():
+            k = int(rng.integers(1, 6))
+            pos = np.unique(rng.integers(1, doc_words, k))
+            if rng.random() < 0.02:
+                pos = pos[:0]  # a record without positions: left out of the check by the reference
+            if rng.random() < 0.03:
+                pos = np.unique(np.concatenate([pos, rng.integers(200, 70_000, 2)]))  # multi-byte varints
+            ob = _positions_to_offsets(pos.tolist())
+            m[d] = ob
+            ix.add(d, max(1, len(pos)), int(rng.integers(1, 1 << 20)), ob)
+        idx.append(ix)
+        offs.append(m)
+    return idx, offs
+
+
+@pytest.mark.parametrize("in_order", [False, True])
+@pytest.mark.parametrize("n_terms", [2, 3, 5])
+def test_phrase_intersection_slop_and_order(ps, in_order, n_terms):
+    """Exact phrases / "within N words": II_IntersectPhrase against the oracle's restatement of the reference's proximity check
+    (RS/index_result/src/core/proximity.rs within_range_in_order / within_range_unordered, pinned on the reference's own
+    known answers in test_oracle_postings.py) applied to every hit of the oracle intersection, for several slops incl. none.
+    DocIds, per-child freqs and the aggregate child order (given order when in_order) must be identical."""
+    rng = np.random.default_rng(900 + n_terms + 10 * in_order)
+    n_docs = 60_000
+    density = [0.5, 0.35, 0.6, 0.45, 0.7][:n_terms]
+    idx, offs = _phrase_corpus(rng, n_docs, n_terms, density, 40)
+    pls = ps.postings_with_offsets([ix.blocks() for ix in idx], ol.CODEC_FULL)
+    assert all(ps.lib().II_PostingList_HasOffsets(p.h) for p in pls)
+    hits = ol.run_intersect(idx)
+    freq_of = [dict((d, f) for d, f, _ in ix.read_all()) for ix in idx]
+    sorted_order = [c for c, _ in hits[0][1]] if hits else list(range(n_terms))
+    for slop in (0, 1, 3, 10, None):
+        if slop is None and not in_order:
+            continue
+        rs = ps.intersect_phrase(pls, slop, in_order)
+        order = rs.child_order().tolist()
+        assert order == (list(range(n_terms)) if in_order else sorted_order)
+        exp = [d for d, _ in hits if ol.within_range([offs[c][d] for c in order], slop, in_order)]
+        got_ids, _, got_fr = rs.fetch()
+        assert got_ids.tolist() == exp, (slop, in_order, len(got_ids), len(exp))
+        assert 0 < len(exp) < len(hits) or slop is None or slop >= 10
+        for slot, c in enumerate(order):
+            assert got_fr[slot].tolist() == [freq_of[c][d] for d in exp]
+    # no constraint at all = the plain intersection
+    rs = ps.intersect_phrase(pls, None, False)
+    assert rs.fetch()[0].tolist() == [d for d, _ in hits]
+
+
+def test_phrase_constructor_takes_slop_and_in_order(ps):
+    """NewIntersectionIterator(max_slop >= 0 / in_order) over B200 term leaves that carry positions is evaluated on the device;
+    leaves without positions are refused with nothing consumed (the caller keeps the reference's iterator)."""
+    rng = np.random.default_rng(931)
+    idx, offs = _phrase_corpus(rng, 20_000, 3, [0.5, 0.4, 0.6], 30)
+    L = ps.lib()
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+
+    def its_of(pls):
+        arr = libc.malloc(8 * len(pls))
+        view = (C.c_void_p * len(pls)).from_address(arr)
+        leaves = []
+        for i, p in enumerate(pls):
+            leaf = L.II_NewTermIterator(p.h, 0, 1.0, 1.0, 1.0)
+            view[i] = C.cast(leaf, C.c_void_p).value
+            leaves.append(leaf)
+        return arr, leaves
+
+    hits = ol.run_intersect(idx)
+    pls = ps.postings_with_offsets([ix.blocks() for ix in idx], ol.CODEC_FULL)
+    for slop, in_order in ((0, True), (2, False), (-1, True)):
+        arr, _ = its_of(pls)
+        qi = L.NewIntersectionIterator(arr, 3, slop, in_order, 1.0)
+        assert qi
+        got = []
+        while qi.contents.Read(qi) == 0:
+            got.append(qi.contents.lastDocId)
+        order = list(range(3)) if in_order else [c for c, _ in hits[0][1]]
+        exp = [d for d, _ in hits if ol.within_range([offs[c][d] for c in order], None if slop < 0 else slop, in_order)]
+        assert got == exp and 0 < len(exp) < len(hits)
+        qi.contents.Free(qi)
+    # leaves decoded WITHOUT positions: refused, children untouched
+    plain = [ps.PostingList.from_blocks(ix.blocks(), ol.CODEC_FULL, on_device=True) for ix in idx]
+    arr, leaves = its_of(plain)
+    assert not L.NewIntersectionIterator(arr, 3, 0, True, 1.0)
+    for lf in leaves:
+        lf.contents.Free(lf)
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(arr)
