@@ -145,6 +145,9 @@ II_DocTable *II_DocTable_New(size_t max_doc_id, const uint32_t *doc_len, const f
 II_DocTable *II_DocTable_FromDevice(size_t max_doc_id, const uint32_t *d_doc_len, const float *d_doc_score,
                                     const uint32_t *d_max_term_freq);
 void II_DocTable_Free(II_DocTable *dt);
+/* Document payloads (dmd->payload, src/redisearch.h RSDocumentMetadata) for the HAMMING scorer: the bytes of docId d are
+ * payloads[offsets[d] .. offsets[d + 1]), offsets has max_doc_id + 2 entries; an empty range = the document has no payload. */
+int II_DocTable_SetPayloads(II_DocTable *dt, const uint8_t *payloads, const uint64_t *offsets);
 
 /* ---- iterator algebra on device ---------------------------------------------------------------- */
 typedef struct II_ResultSet II_ResultSet;
@@ -178,12 +181,14 @@ void II_ResultSet_Free(II_ResultSet *rs);
 /* ---- scoring ------------------------------------------------------------------------------------ */
 typedef enum {
     II_SCORER_BM25STD = 0,      /* default scorer; src/ext/default.c:241-316 */
-    II_SCORER_BM25 = 1,         /* legacy; :164-233 (slop taken as 1: offsets are not shipped) */
-    II_SCORER_TFIDF = 2,        /* :68-146 (slop 1) */
+    II_SCORER_BM25 = 1,         /* legacy; :164-233, divided by GetSlop = IndexResult_MinOffsetDelta (src/index_result/index_result.c:51-108)
+                                 * over the term positions of the hit when the lists carry them, else `children - 1` as the reference */
+    II_SCORER_TFIDF = 2,        /* :68-146 (same slop factor) */
     II_SCORER_TFIDF_DOCNORM = 3,/* :148-153 */
     II_SCORER_DOCSCORE = 4,     /* :366-371 */
     II_SCORER_BM25STD_TANH = 5, /* :339-359 */
-    II_SCORER_DISMAX = 6        /* :378-461 */
+    II_SCORER_DISMAX = 6,       /* :378-461 */
+    II_SCORER_HAMMING = 7       /* :475-497: needs the payloads (II_DocTable_SetPayloads) and goes through II_ScoreHamming */
 } II_Scorer;
 
 /* Per query term, in the ORIGINAL order of the `lists` argument. */
@@ -200,6 +205,10 @@ double II_CalculateIDF_BM25(size_t total_docs, size_t term_docs); /* RS/idf/src/
  * Returns 0, or -1 on failure. */
 int II_Score(II_ResultSet *rs, II_Scorer scorer, const II_TermParams *terms, double agg_weight,
              const II_IndexStats *stats, const II_DocTable *docs, double min_score, uint64_t tanh_factor);
+
+/* HAMMING scorer (src/ext/default.c:475-497) over every hit: 1 / (bit distance between the query payload and the document's
+ * payload + 1); 0 for documents without a payload or of another length. */
+int II_ScoreHamming(II_ResultSet *rs, const II_DocTable *docs, const void *qdata, size_t qdatalen);
 
 /* Copy results to the host.  Any output pointer may be NULL.  child_freqs is [n_children][len]
  * (children in aggregate order; 0 = child absent, union only).  scores are 0 before II_Score. */

@@ -166,6 +166,10 @@ enum { ORC_SCORER_BM25STD = 0, ORC_SCORER_BM25, ORC_SCORER_TFIDF, ORC_SCORER_TFI
 double orc_score(int scorer, const OrcIndexStats *st, const OrcScoreDoc *d, int slop, double min_score,
                  double tanh_factor);
 
+/* GetSlop = IndexResult_MinOffsetDelta (src/index_result/index_result.c:51-108) over an aggregate of n term leaves / virtual
+ * results: decoded positions of child i at pos[i*stride .. i*stride + npos[i]). */
+int orc_min_offset_delta(size_t n, const uint32_t *npos, const uint32_t *pos, size_t stride, const int *is_virtual);
+
 /* Bulk-add every member of vocabulary rank `rank` (synthetic Zipf corpus below); returns the count. */
 size_t orc_ii_fill_synth(OrcInvIndex *ii, uint64_t n_docs, uint64_t rank);
 /* CPU baseline: nq 3-term AND + BM25STD + top-N queries (terms = nq*3 indexes), one query per thread. */

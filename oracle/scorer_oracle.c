@@ -88,3 +88,39 @@ double orc_score(int scorer, const OrcIndexStats *st, const OrcScoreDoc *d, int 
     }
     return NAN;
 }
+
+/* GetSlop = IndexResult_MinOffsetDelta (src/index_result/index_result.c:51-108; wired at src/extension.c:159): over the
+ * aggregate's children that carry offsets (term leaves with a non-empty offset vector; virtual results never do, :19-42),
+ * taken as CONSECUTIVE pairs (child i with the next such child, which then opens the following pair), the smallest position
+ * distance a two-pointer walk sees before it drops to <= 1 or either side ends; sqrt of the sum of squares, truncated.
+ * npos[i] = 0: a term without offsets; is_virtual[i]: NOT / absent OPTIONAL child. */
+int orc_min_offset_delta(size_t n, const uint32_t *npos, const uint32_t *pos, size_t stride, const int *is_virtual) {
+    if (n <= 1) return 1;
+#define ORC_HAS(i) (!(is_virtual && is_virtual[i]) && npos[i] > 0)
+#define ORC_NEXT(c, k) ((k) < npos[c] ? pos[(c) * stride + (k)++] : 0xFFFFFFFFu)
+    int dist = 0;
+    size_t i = 0;
+    while (i < n) {
+        while (i < n && !ORC_HAS(i)) i++;
+        if (i == n) break;
+        const size_t a = i++;
+        while (i < n && !ORC_HAS(i)) i++;
+        if (i == n) break;
+        const size_t b = i;
+        uint32_t ka = 0, kb = 0;
+        uint32_t p1 = ORC_NEXT(a, ka), p2 = ORC_NEXT(b, kb);
+        int cd = (int)(p2 > p1 ? p2 - p1 : p1 - p2);
+        while (cd > 1 && p1 != 0xFFFFFFFFu && p2 != 0xFFFFFFFFu) {
+            const uint32_t d = p2 > p1 ? p2 - p1 : p1 - p2;
+            cd = (int)(d < (uint32_t)cd ? d : (uint32_t)cd); /* MIN(unsigned, int) compares as unsigned */
+            if (p2 > p1)
+                p1 = ORC_NEXT(a, ka);
+            else
+                p2 = ORC_NEXT(b, kb);
+        }
+        dist += cd * cd;
+    }
+#undef ORC_HAS
+#undef ORC_NEXT
+    return dist ? (int)sqrt((double)dist) : (int)(n - 1);
+}

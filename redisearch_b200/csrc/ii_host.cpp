@@ -154,10 +154,14 @@ struct II_DocTable {
     uint32_t *d_len = nullptr, *d_maxf = nullptr;
     float *d_score = nullptr;
     size_t max_doc = 0;
+    uint8_t *d_payloads = nullptr;    // dmd->payload bytes of every document back to back (HAMMING scorer)
+    uint64_t *d_payload_off = nullptr; // [max_doc + 2]
     ~II_DocTable() {
         dfree(d_len);
         dfree(d_maxf);
         dfree(d_score);
+        dfree(d_payloads);
+        dfree(d_payload_off);
     }
 };
 
@@ -169,11 +173,24 @@ struct II_ResultSet {
     uint32_t n_children = 0;
     uint32_t child_order[kIIMaxLists] = {0};
     bool is_union = false, has_freqs = true, scored = false;
+    // term positions of the hits, kept when a child list carries them: GetSlop of the legacy scorers walks them
+    // (IndexResult_MinOffsetDelta, src/index_result/index_result.c:51-108) the first time such a scorer is asked for
+    uint32_t *d_hit_pos = nullptr; // [n_children][cap] posting position of the hit inside child j (aggregate order); ~0 = virtual / absent
+    uint32_t *d_slop = nullptr;    // [cap]
+    struct ChildOffsets {
+        const uint8_t *bytes = nullptr;
+        const uint32_t *off_pos = nullptr, *off_len = nullptr;
+        std::shared_ptr<SharedDeviceBlock> keep_tables, keep_bytes; // the lists may be released before the scorer runs
+    } child_off[kIIMaxLists];
+    UnionOrder *d_order = nullptr; // unions: the reference's aggregate child order per docId epoch
     ~II_ResultSet() {
         dfree(d_docs);
         dfree(d_freqs);
         dfree(d_scores);
         dfree(d_len);
+        dfree(d_hit_pos);
+        dfree(d_slop);
+        dfree(d_order);
     }
 };
 
@@ -625,6 +642,30 @@ II_DocTable *II_DocTable_FromDevice(size_t max_doc_id, const uint32_t *d_doc_len
     return doctable_from(max_doc_id, d_doc_len, d_doc_score, d_max_term_freq, cudaMemcpyDeviceToDevice);
 }
 void II_DocTable_Free(II_DocTable *dt) { delete dt; }
+int II_DocTable_SetPayloads(II_DocTable *dt, const uint8_t *payloads, const uint64_t *offsets) {
+    if (!dt || !offsets) return -1;
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return -1;
+    const size_t n = dt->max_doc + 2, bytes = offsets[dt->max_doc + 1];
+    for (size_t d = 0; d + 1 < n; d++)
+        if (offsets[d] > offsets[d + 1]) return -1;
+    dfree(dt->d_payloads);
+    dfree(dt->d_payload_off);
+    dt->d_payloads = dalloc<uint8_t>(bytes ? bytes : 1);
+    dt->d_payload_off = dalloc<uint64_t>(n);
+    bool ok = dt->d_payloads && dt->d_payload_off;
+    ok = ok && copy_sync(dt->d_payload_off, offsets, n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && (!bytes || (payloads && copy_sync(dt->d_payloads, payloads, bytes, cudaMemcpyHostToDevice) == cudaSuccess));
+    if (!ok) {
+        dfree(dt->d_payloads);
+        dfree(dt->d_payload_off);
+        dt->d_payloads = nullptr;
+        dt->d_payload_off = nullptr;
+        return -1;
+    }
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // AND / OR: enqueue-only cores (no host synchronisation) + synchronous public wrappers
@@ -671,14 +712,19 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
     rs->d_len = dalloc<uint32_t>(4);
     uint32_t *tmp_idx = dalloc<uint32_t>(stride), *tmp_pos = dalloc<uint32_t>(stride * n);
     uint32_t *counts = dalloc<uint32_t>(nchunks), *offsets = dalloc<uint32_t>(nchunks);
-    uint32_t *scratch = (n > 1) ? dalloc<uint32_t>(rs->cap * n) : nullptr;
     const bool check_phrase = phrase && n > 1;
+    // keep the hits' posting positions when a child carries term positions: GetSlop needs them later (II_Score)
+    bool keep_pos = false;
+    for (size_t i = 0; i < n && n > 1; i++) keep_pos |= mode_of(i) != 1 && lists[i]->d_off_len != nullptr;
+    if (keep_pos) rs->d_hit_pos = dalloc<uint32_t>(rs->cap * n);
     const uint32_t pchunks = (uint32_t)((rs->cap + 1023) / 1024);
-    uint32_t *hit_pos = check_phrase ? dalloc<uint32_t>(rs->cap * n) : nullptr, *flags = check_phrase ? dalloc<uint32_t>(rs->cap) : nullptr;
+    // phrase path: the gather fills scratch rows, the filter compacts the survivors into the result set
+    uint32_t *pre_freqs = check_phrase ? dalloc<uint32_t>(rs->cap * n) : nullptr, *pre_pos = check_phrase ? dalloc<uint32_t>(rs->cap * n) : nullptr;
+    uint32_t *flags = check_phrase ? dalloc<uint32_t>(rs->cap) : nullptr;
     uint32_t *pcounts = check_phrase ? dalloc<uint32_t>(pchunks) : nullptr, *poffsets = check_phrase ? dalloc<uint32_t>(pchunks) : nullptr;
     uint32_t *pre_docs = check_phrase ? dalloc<uint32_t>(rs->cap) : nullptr, *pre_len = check_phrase ? dalloc<uint32_t>(4) : nullptr;
-    bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && rs->d_len && tmp_idx && tmp_pos && counts && offsets &&
-              (n == 1 || scratch) && (!check_phrase || (hit_pos && flags && pcounts && poffsets && pre_docs && pre_len));
+    bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && rs->d_len && tmp_idx && tmp_pos && counts && offsets && (!keep_pos || rs->d_hit_pos) &&
+              (!check_phrase || (pre_freqs && pre_pos && flags && pcounts && poffsets && pre_docs && pre_len));
     if (ok) {
         // kernel list order: driver first, then the rest ascending by length (cheap rejections first)
         std::vector<uint32_t> korder;
@@ -709,16 +755,27 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
         ga.counts = counts;
         ga.offsets = offsets;
         ga.stride = stride;
-        ga.out_doc = check_phrase ? pre_docs : rs->d_docs;
-        ga.out_pos = hit_pos;
         ga.fstride = rs->cap;
         for (size_t k = 0; k < n; k++) {
             ga.freqs[k] = lists[order[korder[k]]]->d_freqs;
             ga.mode[k] = (uint8_t)mode_of(order[korder[k]]);
+            ga.row[k] = (uint8_t)korder[k]; // kernel slot k holds aggregate child korder[k]
         }
-        // rows are produced in kernel-slot order, then placed at their aggregate child index
-        ga.out_freq = (n > 1) ? scratch : rs->d_freqs;
+        // rows land at their aggregate child index
+        ga.out_doc = check_phrase ? pre_docs : rs->d_docs;
+        ga.out_freq = check_phrase ? pre_freqs : rs->d_freqs;
+        ga.out_pos = check_phrase ? pre_pos : rs->d_hit_pos;
         ok = ok && ii_launch_gather(ga, nchunks, c.stream) == cudaSuccess;
+        for (size_t j = 0; j < n && keep_pos; j++) { // aggregate child j
+            const II_PostingList *L = lists[order[j]];
+            II_ResultSet::ChildOffsets &co = rs->child_off[j];
+            if (mode_of(order[j]) == 1 || !L->d_off_len) continue;
+            co.bytes = L->d_bytes;
+            co.off_pos = L->d_off_pos;
+            co.off_len = L->d_off_len;
+            co.keep_tables = L->owner;
+            co.keep_bytes = L->bytes_owner;
+        }
         if (ok && check_phrase) {
             // slop / in-order: one thread per hit walks the term positions of its children (kept on the device by the
             // decoder), survivors are compacted in order straight into the aggregate rows
@@ -726,31 +783,23 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
             pa.n = (uint32_t)n;
             pa.max_slop = phrase->max_slop;
             pa.in_order = phrase->in_order ? 1 : 0;
-            pa.pos = hit_pos;
+            pa.pos = pre_pos;
             pa.fstride = rs->cap;
-            for (size_t k = 0; k < n; k++) {
-                const II_PostingList *L = lists[order[korder[k]]];
-                const uint32_t j = korder[k]; // aggregate child index of kernel slot k
-                pa.row[j] = (uint32_t)k;
+            for (size_t j = 0; j < n; j++) {
+                const II_PostingList *L = lists[order[j]];
                 pa.bytes[j] = L->d_bytes;
                 pa.off_pos[j] = L->d_off_pos;
-                pa.off_len[j] = mode_of(order[korder[k]]) == 1 ? nullptr : L->d_off_len;
+                pa.off_len[j] = mode_of(order[j]) == 1 ? nullptr : L->d_off_len;
             }
-            // compaction writes freq row k (kernel slot) of the survivors; the rows are then placed like the plain path
-            ok = ii_launch_phrase_filter(pa, pre_len, (uint32_t)rs->cap, flags, pcounts, poffsets, rs->d_len, pre_docs, scratch, rs->cap,
-                                         rs->d_docs, hit_pos /* reused: compacted freq rows */, rs->cap, c.stream) == cudaSuccess;
-            for (size_t k = 0; k < n; k++)
-                ok = ok && cudaMemcpyAsync(rs->d_freqs + (size_t)korder[k] * rs->cap, hit_pos + k * rs->cap, rs->cap * 4,
-                                           cudaMemcpyDeviceToDevice, c.stream) == cudaSuccess;
+            ok = ii_launch_phrase_filter(pa, pre_len, (uint32_t)rs->cap, flags, pcounts, poffsets, rs->d_len, pre_docs, pre_freqs, rs->cap,
+                                         rs->d_docs, rs->d_freqs, rs->d_hit_pos, rs->cap, c.stream) == cudaSuccess;
             c.stats.kernel_launches += 4;
-        } else if (ok && n > 1)
-            for (size_t k = 0; k < n; k++)
-                ok = ok && cudaMemcpyAsync(rs->d_freqs + (size_t)korder[k] * rs->cap, scratch + k * rs->cap, rs->cap * 4,
-                                           cudaMemcpyDeviceToDevice, c.stream) == cudaSuccess;
+        }
         cudaEventRecord(c.e1, c.stream);
         c.stats.kernel_launches += 3;
     }
-    dfree(hit_pos);
+    dfree(pre_freqs);
+    dfree(pre_pos);
     dfree(flags);
     dfree(pcounts);
     dfree(poffsets);
@@ -760,8 +809,27 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
     dfree(tmp_pos);
     dfree(counts);
     dfree(offsets);
-    dfree(scratch);
     return ok;
+}
+
+// GetSlop per hit, once per result set and only when a legacy scorer asks for it.  d_len / cap_len as for the scorer launch.
+bool ensure_slop(Ctx &c, II_ResultSet *rs, const uint32_t *d_len, uint32_t cap_len) {
+    if (!rs->d_hit_pos || rs->d_slop) return true;
+    rs->d_slop = dalloc<uint32_t>(rs->cap);
+    if (!rs->d_slop) return false;
+    SlopArgs sa{};
+    sa.n = rs->n_children;
+    sa.is_union = rs->is_union ? 1 : 0;
+    sa.order = rs->d_order;
+    sa.pos = rs->d_hit_pos;
+    sa.fstride = rs->cap;
+    for (uint32_t j = 0; j < rs->n_children; j++) {
+        sa.bytes[j] = rs->child_off[j].bytes;
+        sa.off_pos[j] = rs->child_off[j].off_pos;
+        sa.off_len[j] = rs->child_off[j].off_len;
+    }
+    c.stats.kernel_launches += 1;
+    return ii_launch_min_offset_delta(sa, rs->d_docs, d_len, cap_len, rs->d_slop, c.stream) == cudaSuccess;
 }
 
 bool union_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int quick_exit, II_ResultSet *rs, bool *trivially_empty) {
@@ -785,7 +853,43 @@ bool union_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int quick_exi
     rs->d_len = dalloc<uint32_t>(4);
     uint32_t *bitmap = dalloc<uint32_t>(nwords), *blocksum = dalloc<uint32_t>(nblk), *blockoff = dalloc<uint32_t>(nblk);
     uint32_t *wordoff = dalloc<uint32_t>(nwords);
-    bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && rs->d_len && bitmap && blocksum && blockoff && wordoff;
+    // the reference's aggregate child order (UnionFlat, full mode, read front to back): children live in an "active" array,
+    // an exhausted child is swap-removed by the pass that follows the document it ended on (advance_and_find_min,
+    // union_flat.rs:218-258; empty children by initialize_children :263-296), positions visited in ascending order and a
+    // swapped-in child examined at once.  (Above min_union_iter_heap = 20 children the reference uses UnionHeap, whose
+    // aggregate order follows its heap array: same docIds and children, sums may differ in the last bit.)
+    UnionOrder uo{};
+    if (rs->has_freqs) {
+        std::vector<uint32_t> active(n);
+        for (size_t i = 0; i < n; i++) active[i] = (uint32_t)i;
+        size_t num_active = n;
+        auto sweep = [&](auto &&exhausted) {
+            for (size_t i = 0; i < num_active;) {
+                if (exhausted(active[i])) {
+                    num_active--;
+                    if (i < num_active) std::swap(active[i], active[num_active]);
+                    continue;
+                }
+                i++;
+            }
+        };
+        sweep([&](uint32_t ch) { return lists[ch]->n == 0; });
+        while (num_active) {
+            uint32_t bound = 0xFFFFFFFFu;
+            for (size_t i = 0; i < num_active; i++) bound = std::min(bound, lists[active[i]]->last_id);
+            const uint32_t e = uo.n_epochs++;
+            uo.bound[e] = bound;
+            uo.n_active[e] = (uint8_t)num_active;
+            for (size_t i = 0; i < num_active; i++) uo.perm[e][i] = (uint8_t)active[i];
+            sweep([&](uint32_t ch) { return lists[ch]->last_id == bound; });
+        }
+        rs->d_order = dalloc<UnionOrder>(1);
+    }
+    bool keep_pos = false;
+    for (size_t i = 0; i < n && n > 1 && rs->has_freqs; i++) keep_pos |= lists[i]->d_off_len != nullptr;
+    if (keep_pos) rs->d_hit_pos = dalloc<uint32_t>(rs->cap * n);
+    bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && rs->d_len && bitmap && blocksum && blockoff && wordoff &&
+              (!rs->has_freqs || rs->d_order) && (!keep_pos || rs->d_hit_pos);
     if (ok) {
         std::vector<const uint32_t *> ids(n), freqs(n);
         std::vector<uint32_t> lens(n);
@@ -796,8 +900,24 @@ bool union_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int quick_exi
         }
         cudaEventRecord(c.e0, c.stream);
         if (rs->has_freqs) ok = cudaMemsetAsync(rs->d_freqs, 0, rs->cap * n * 4, c.stream) == cudaSuccess;
+        if (rs->d_order) { // pageable source: the copy is staged before the call returns
+            ok = ok && cudaMemcpyAsync(rs->d_order, &uo, sizeof(uo), cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+        }
+        if (keep_pos) {
+            ok = ok && cudaMemsetAsync(rs->d_hit_pos, 0xFF, rs->cap * n * 4, c.stream) == cudaSuccess;
+            for (size_t j = 0; j < n; j++) {
+                const II_PostingList *L = lists[j];
+                II_ResultSet::ChildOffsets &co = rs->child_off[j];
+                if (!L->d_off_len) continue;
+                co.bytes = L->d_bytes;
+                co.off_pos = L->d_off_pos;
+                co.off_len = L->d_off_len;
+                co.keep_tables = L->owner;
+                co.keep_bytes = L->bytes_owner;
+            }
+        }
         ok = ok && ii_launch_union(ids.data(), freqs.data(), lens.data(), (uint32_t)n, nwords, bitmap, blocksum, blockoff, wordoff,
-                                   rs->d_len, rs->d_docs, rs->d_freqs, rs->cap, rs->has_freqs, c.stream) == cudaSuccess;
+                                   rs->d_len, rs->d_docs, rs->d_freqs, rs->cap, rs->has_freqs, rs->d_hit_pos, c.stream) == cudaSuccess;
         cudaEventRecord(c.e1, c.stream);
         c.stats.kernel_launches += 3 + 2 * n;
     }
@@ -834,6 +954,8 @@ ScoreArgs make_score_args(const II_ResultSet *rs, II_Scorer scorer, const II_Ter
     sa.doc_len = docs ? docs->d_len : nullptr;
     sa.doc_score = docs ? docs->d_score : nullptr;
     sa.max_freq = docs ? docs->d_maxf : nullptr;
+    sa.slop = rs->d_slop; // NULL: no term positions on the device, the kernel uses `children - 1`
+    sa.order = rs->d_order;
     return sa;
 }
 
@@ -879,8 +1001,10 @@ bool search_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int is_union
         return false;
     }
     const uint32_t k = (uint32_t)top_n;
+    if (scorer == II_SCORER_BM25 || scorer == II_SCORER_TFIDF || scorer == II_SCORER_TFIDF_DOCNORM)
+        ok = ensure_slop(c, &rs, rs.d_len, (uint32_t)rs.cap);
     const ScoreArgs sa = make_score_args(&rs, scorer, terms, agg_weight, stats, docs, 0.0, 4);
-    ok = ii_launch_score(sa, rs.d_docs, rs.d_freqs, rs.cap, rs.d_len, (uint32_t)rs.cap, rs.d_scores, c.stream) == cudaSuccess;
+    ok = ok && ii_launch_score(sa, rs.d_docs, rs.d_freqs, rs.cap, rs.d_len, (uint32_t)rs.cap, rs.d_scores, c.stream) == cudaSuccess;
     const uint32_t nl = ii_topn_lists((uint32_t)rs.cap);
     const size_t total = (size_t)nl * k;
     uint64_t *d_keys = dalloc<uint64_t>(total);
@@ -1051,11 +1175,42 @@ int II_Score(II_ResultSet *rs, II_Scorer scorer, const II_TermParams *terms, dou
         return 0;
     }
     if (!rs->has_freqs) return -1;
-    const ScoreArgs sa = make_score_args(rs, scorer, terms, agg_weight, stats, docs, min_score, tanh_factor);
     cudaEventRecord(c.e0, c.stream);
-    bool ok = ii_launch_score(sa, rs->d_docs, rs->d_freqs, rs->cap, nullptr, (uint32_t)rs->len, rs->d_scores, c.stream) == cudaSuccess;
+    bool ok = true;
+    if (scorer == II_SCORER_BM25 || scorer == II_SCORER_TFIDF || scorer == II_SCORER_TFIDF_DOCNORM)
+        ok = ensure_slop(c, rs, nullptr, (uint32_t)rs->len);
+    const ScoreArgs sa = make_score_args(rs, scorer, terms, agg_weight, stats, docs, min_score, tanh_factor);
+    ok = ok && ii_launch_score(sa, rs->d_docs, rs->d_freqs, rs->cap, nullptr, (uint32_t)rs->len, rs->d_scores, c.stream) == cudaSuccess;
     cudaEventRecord(c.e1, c.stream);
     ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+    if (!ok) return -1;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.e0, c.e1);
+    c.stats.score_device_us = ms * 1000.0;
+    c.stats.kernel_launches += 1;
+    rs->scored = true;
+    return 0;
+}
+
+// HAMMING (src/ext/default.c:475-497): the scorer looks at the query payload and the document payload only
+int II_ScoreHamming(II_ResultSet *rs, const II_DocTable *docs, const void *qdata, size_t qdatalen) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init() || !rs) return -1;
+    if (rs->len == 0) {
+        rs->scored = true;
+        return 0;
+    }
+    if (!docs || !docs->d_payload_off || qdatalen > 0xFFFFFFFFull) return -1;
+    uint8_t *d_q = dalloc<uint8_t>(qdatalen ? qdatalen : 1);
+    bool ok = d_q != nullptr;
+    if (ok && qdatalen) ok = cudaMemcpyAsync(d_q, qdata, qdatalen, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+    cudaEventRecord(c.e0, c.stream);
+    ok = ok && ii_launch_hamming(rs->d_docs, nullptr, (uint32_t)rs->len, docs->d_payloads, docs->d_payload_off, d_q, (uint32_t)qdatalen,
+                                 rs->d_scores, c.stream) == cudaSuccess;
+    cudaEventRecord(c.e1, c.stream);
+    ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess; // also covers the pageable qdata copy
+    dfree(d_q);
     if (!ok) return -1;
     float ms = 0;
     cudaEventElapsedTime(&ms, c.e0, c.e1);
@@ -1164,8 +1319,21 @@ struct FusedScratch { // grow-only, owned by the batch entry point (serialised b
     size_t q_cap = 0;
     uint64_t *d_cand_keys = nullptr, *d_out_keys = nullptr, *h_out_keys = nullptr;
     uint32_t *d_cand_ids = nullptr, *d_out_ids = nullptr, *h_out_ids = nullptr, *d_hits = nullptr, *h_hits = nullptr;
-    size_t cand_cap = 0, out_cap = 0;
-    bool need(size_t nq, size_t cand, size_t out) {
+    uint32_t *d_item_q = nullptr; // work item -> query
+    uint2 *d_win = nullptr;       // [items][kFusedMaxLists - 1] window of every other child per work item
+    size_t cand_cap = 0, out_cap = 0, item_cap = 0;
+    bool need(size_t nq, size_t cand, size_t out, size_t items) {
+        if (items > item_cap) {
+            cudaFree(d_item_q);
+            cudaFree(d_win);
+            d_item_q = nullptr;
+            d_win = nullptr;
+            item_cap = 0;
+            const size_t cap = items + items / 4 + 1024;
+            if (cudaMalloc(&d_item_q, cap * 4) != cudaSuccess || cudaMalloc(&d_win, cap * (kFusedMaxLists - 1) * sizeof(uint2)) != cudaSuccess)
+                return false;
+            item_cap = cap;
+        }
         if (nq > q_cap) {
             cudaFreeHost(h_q);
             cudaFree(d_q);
@@ -1228,8 +1396,8 @@ bool fused_batch(Ctx &c, FusedScratch &fs, const std::vector<size_t> &idx, II_Po
             stop++;
         }
         const size_t m = stop - done;
-        if (!fs.need(m, items * top_n, m * top_n)) return false;
-        uint32_t item0 = 0;
+        if (!fs.need(m, items * top_n, m * top_n, items)) return false;
+        uint32_t item0 = 0, max_children = 1;
         for (size_t k = 0; k < m; k++) {
             const size_t qi = idx[done + k];
             const size_t n = n_lists[qi];
@@ -1250,6 +1418,7 @@ bool fused_batch(Ctx &c, FusedScratch &fs, const std::vector<size_t> &idx, II_Po
                 fq.bm25_idf[t] = terms[qi][order[t]].bm25_idf;
             }
             fq.n = (uint32_t)n;
+            max_children = std::max(max_children, fq.n);
             fq.item0 = item0;
             fq.nchunks = (uint32_t)((fq.len[0] + kIIChunk - 1) / kIIChunk);
             item0 += fq.nchunks;
@@ -1264,8 +1433,8 @@ bool fused_batch(Ctx &c, FusedScratch &fs, const std::vector<size_t> &idx, II_Po
         fc.max_freq = docs ? docs->d_maxf : nullptr;
         bool ok = cudaMemcpyAsync(fs.d_q, fs.h_q, m * sizeof(FusedQuery), cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
         cudaEventRecord(c.e0, c.stream);
-        ok = ok && ii_launch_fused_search(fs.d_q, (uint32_t)m, item0, fc, (uint32_t)top_n, fs.d_cand_keys, fs.d_cand_ids, fs.d_hits,
-                                          fs.d_out_keys, fs.d_out_ids, c.stream) == cudaSuccess;
+        ok = ok && ii_launch_fused_search(fs.d_q, (uint32_t)m, item0, max_children, fc, (uint32_t)top_n, fs.d_item_q, fs.d_win, fs.d_cand_keys,
+                                          fs.d_cand_ids, fs.d_hits, fs.d_out_keys, fs.d_out_ids, c.stream) == cudaSuccess;
         cudaEventRecord(c.e1, c.stream);
         ok = ok && cudaMemcpyAsync(fs.h_out_keys, fs.d_out_keys, m * top_n * 8, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
         ok = ok && cudaMemcpyAsync(fs.h_out_ids, fs.d_out_ids, m * top_n * 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
@@ -1277,7 +1446,7 @@ bool fused_batch(Ctx &c, FusedScratch &fs, const std::vector<size_t> &idx, II_Po
         }
         float ms = 0;
         if (cudaEventElapsedTime(&ms, c.e0, c.e1) == cudaSuccess) c.stats.intersect_device_us += ms * 1000.0;
-        c.stats.kernel_launches += 2;
+        c.stats.kernel_launches += 4;
         for (size_t k = 0; k < m; k++) {
             const size_t qi = idx[done + k];
             size_t w = 0;
@@ -1326,7 +1495,11 @@ int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const siz
         bool empty = false;
         for (size_t t = 0; t < n_lists[i]; t++) empty |= lists[i][t]->n == 0;
         if (!is_union && empty) continue; // an empty child: the AND is empty (intersection.rs:363-417)
-        if (fused_on && !is_union && n_lists[i] <= (size_t)kFusedMaxLists && top_n <= (size_t)kFusedMaxTopN)
+        // the legacy scorers divide by GetSlop, which walks term positions when the lists carry them: the per-query chain does
+        bool wants_positions = false;
+        if (scorer == II_SCORER_BM25 || scorer == II_SCORER_TFIDF || scorer == II_SCORER_TFIDF_DOCNORM)
+            for (size_t t = 0; t < n_lists[i] && n_lists[i] > 1; t++) wants_positions |= lists[i][t]->d_off_len != nullptr;
+        if (fused_on && !is_union && !wants_positions && n_lists[i] <= (size_t)kFusedMaxLists && top_n <= (size_t)kFusedMaxTopN)
             fusable.push_back(i);
         else
             rest.push_back(i);
@@ -2133,8 +2306,10 @@ double b200_scorer(const ScoringFunctionArgsC *args, const void *res_v, const vo
         if (!node_materialise(it) || !it->rs || !node_host(it)) return 0.0;
         II_IndexStats st{args->indexStats.numDocs, args->indexStats.numTerms, args->indexStats.avgDocLen};
         // terms are stored in the order of the constructor's `its`, which is what II_Score expects
-        if (II_Score(it->rs, (II_Scorer)kScorer, it->terms.data(), it->agg_weight, &st, it->docs, min_score,
-                     args->tanhFactor ? args->tanhFactor : 4) != 0)
+        if (kScorer == II_SCORER_HAMMING) {
+            if (II_ScoreHamming(it->rs, it->docs, args->qdata, args->qdatalen) != 0) return 0.0;
+        } else if (II_Score(it->rs, (II_Scorer)kScorer, it->terms.data(), it->agg_weight, &st, it->docs, min_score,
+                            args->tanhFactor ? args->tanhFactor : 4) != 0)
             return 0.0;
         if (II_ResultSet_Fetch(it->rs, nullptr, it->scores.data(), nullptr) != 0) return 0.0;
         it->scored_with = kScorer;
@@ -2160,6 +2335,7 @@ int RS_ExtensionInit(void *ctx_v) {
     rc |= ctx->RegisterScoringFunction("DOCSCORE.B200", b200_scorer<II_SCORER_DOCSCORE>, nullptr, nullptr);
     rc |= ctx->RegisterScoringFunction("BM25STD.TANH.B200", b200_scorer<II_SCORER_BM25STD_TANH>, nullptr, nullptr);
     rc |= ctx->RegisterScoringFunction("DISMAX.B200", b200_scorer<II_SCORER_DISMAX>, nullptr, nullptr);
+    rc |= ctx->RegisterScoringFunction("HAMMING.B200", b200_scorer<II_SCORER_HAMMING>, nullptr, nullptr);
     return rc ? 1 : 0;
 }
 

@@ -378,14 +378,47 @@ __device__ __forceinline__ double bm25_leaf(double idf, double f, double avg, do
     return __ddiv_rn(__dmul_rn(__dmul_rn(weight, idf), f), denom); // :173
 }
 
+// children of the aggregate in the reference's order: intersections keep the constructor's (sorted) order; a union's follows the
+// active array of UnionFlat (UnionOrder: a function of the docId for a union read front to back)
+struct ChildOrder {
+    const uint8_t *perm; // NULL: 0..n-1
+    uint32_t n;
+};
+__device__ __forceinline__ ChildOrder child_order_of(const UnionOrder *order, uint32_t n_children, uint32_t doc) {
+    ChildOrder co{nullptr, n_children};
+    if (order) {
+        uint32_t e = 0;
+        while (e + 1 < order->n_epochs && doc > order->bound[e]) e++;
+        co.perm = order->perm[e];
+        co.n = order->n_active[e];
+    }
+    return co;
+}
+// IndexResult_MinOffsetDelta without any offsets: `dist ? sqrt(dist) : num - 1`, 1 for num <= 1 (index_result.c:57-60,107)
+__device__ __forceinline__ uint32_t slop_without_offsets(uint32_t num) { return num <= 1 ? 1u : num - 1u; }
+
 __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *freqs, size_t fstride, size_t o) {
     const float doc_score = s.doc_score ? s.doc_score[doc] : 1.0f;
     const uint32_t doc_len = s.doc_len ? s.doc_len[doc] : 0u;
+    const ChildOrder co = child_order_of(s.is_union ? s.order : nullptr, s.n_children, doc);
+#define II_FOR_CHILDREN(c) for (uint32_t ci_ = 0, c = 0; ci_ < co.n && ((c = co.perm ? co.perm[ci_] : ci_), true); ci_++)
+    uint32_t slop = 1;
+    if (s.scorer >= 1 && s.scorer <= 3) { // the legacy scorers divide by GetSlop (:130-131, :226-227)
+        if (s.slop) {
+            slop = s.slop[o];
+        } else if (s.is_union) {
+            uint32_t present = 0;
+            for (uint32_t c = 0; c < s.n_children; c++) present += freqs[c * fstride + o] != 0;
+            slop = slop_without_offsets(present);
+        } else {
+            slop = slop_without_offsets(s.n_children);
+        }
+    }
     switch (s.scorer) {
     case 0:   // BM25STD            :253-316
     case 5: { // BM25STD.TANH       :339-359
         double ret = 0;
-        for (uint32_t c = 0; c < s.n_children; c++) {
+        II_FOR_CHILDREN(c) {
             const uint32_t f = freqs[c * fstride + o];
             if (f) ret = __dadd_rn(ret, bm25std_leaf(s.bm25_idf[c], (double)f, (int)doc_len, s.avg_doc_len, s.weight[c]));
         }
@@ -394,15 +427,16 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
         if (s.scorer == 5) return tanh(__dmul_rn(__ddiv_rn(1.0, (double)s.tanh_factor), score));
         return score;
     }
-    case 1: { // BM25 (legacy)      :164-233, slop = 1
+    case 1: { // BM25 (legacy)      :164-233
         double ret = 0;
-        for (uint32_t c = 0; c < s.n_children; c++) {
+        II_FOR_CHILDREN(c) {
             const uint32_t f = freqs[c * fstride + o];
             if (f) ret = __dadd_rn(ret, bm25_leaf(s.idf[c], (double)f, s.avg_doc_len, s.weight[c]));
         }
         ret = __dmul_rn(ret, s.agg_weight);
         const double score = __dmul_rn((double)doc_score, ret);
-        return (score < s.min_score) ? 0.0 : score;
+        if (score < s.min_score) return 0.0;
+        return __ddiv_rn(score, (double)(int)slop); // `score /= slop` with an int slop
     }
     case 2:   // TFIDF              :68-146
     case 3: { // TFIDF.DOCNORM
@@ -410,18 +444,19 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
         const uint32_t norm = (s.scorer == 2) ? (s.max_freq ? s.max_freq[doc] : 1u) : doc_len;
         if (norm == 0) return 0.0;
         double raw = 0;
-        for (uint32_t c = 0; c < s.n_children; c++) {
+        II_FOR_CHILDREN(c) {
             const uint32_t f = freqs[c * fstride + o];
             if (f) raw = __dadd_rn(raw, __dmul_rn(__dmul_rn(s.weight[c], (double)f), s.idf[c]));
         }
         raw = __dmul_rn(s.agg_weight, raw);
         const double tfidf = __ddiv_rn(__dmul_rn((double)doc_score, raw), (double)norm);
-        return (tfidf < s.min_score) ? 0.0 : tfidf;
+        if (tfidf < s.min_score) return 0.0;
+        return __ddiv_rn(tfidf, (double)(int)slop);
     }
     case 4: return (double)doc_score; // DOCSCORE :366-371
     case 6: {                         // DISMAX   :378-461: intersection sums, union takes the max
         double ret = 0;
-        for (uint32_t c = 0; c < s.n_children; c++) {
+        II_FOR_CHILDREN(c) {
             const uint32_t f = freqs[c * fstride + o];
             if (!f) continue;
             const double leaf = __dmul_rn(s.weight[c], (double)f);
@@ -433,6 +468,7 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
         return __dmul_rn(s.agg_weight, ret);
     }
     }
+#undef II_FOR_CHILDREN
     return 0.0;
 }
 
@@ -445,8 +481,8 @@ __global__ void __launch_bounds__(kIIThreads) gather_kernel(const GatherArgs g) 
         const uint32_t idx = g.tmp_idx[start + r];
         const size_t o = (size_t)off + r;
         g.out_doc[o] = g.ids0[idx];
-        g.out_freq[o] = g.freqs[0][idx];
-        if (g.out_pos) g.out_pos[o] = idx;
+        g.out_freq[(size_t)g.row[0] * g.fstride + o] = g.freqs[0][idx];
+        if (g.out_pos) g.out_pos[(size_t)g.row[0] * g.fstride + o] = idx;
         for (uint32_t j = 1; j < g.n; j++) {
             uint32_t f = 0; // NOT children and absent OPTIONAL children are virtual results: freq 0
             uint32_t p = 0xFFFFFFFFu;
@@ -454,8 +490,8 @@ __global__ void __launch_bounds__(kIIThreads) gather_kernel(const GatherArgs g) 
                 p = g.tmp_pos[(size_t)j * g.stride + idx];
                 if (g.mode[j] == 0 || p != 0xFFFFFFFFu) f = g.freqs[j][p];
             }
-            if (g.out_pos) g.out_pos[(size_t)j * g.fstride + o] = p;
-            g.out_freq[(size_t)j * g.fstride + o] = f;
+            if (g.out_pos) g.out_pos[(size_t)g.row[j] * g.fstride + o] = p;
+            g.out_freq[(size_t)g.row[j] * g.fstride + o] = f;
         }
     }
 }
@@ -466,6 +502,25 @@ __global__ void score_kernel(const ScoreArgs s, const uint32_t *__restrict__ doc
     const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < m; o += (size_t)gridDim.x * blockDim.x)
         scores[o] = score_hit(s, docs[o], freqs, fstride, o);
+}
+
+// HAMMING (default.c:475-497): the byte loop of the reference is a popcount per byte; the sum is the same taken 4 bytes at a time
+__global__ void hamming_kernel(const uint32_t *__restrict__ docs, const uint32_t *__restrict__ d_len, uint32_t cap_len,
+                               const uint8_t *__restrict__ payloads, const uint64_t *__restrict__ payload_off,
+                               const uint8_t *__restrict__ qdata, uint32_t qlen, double *__restrict__ scores) {
+    const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < m; o += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t doc = docs[o];
+        const uint64_t b0 = payload_off[doc], b1 = payload_off[doc + 1];
+        double r = 0.0;
+        if (b1 > b0 && b1 - b0 == (uint64_t)qlen) { // hasPayload, len != 0, same length as the query payload
+            const uint8_t *b = payloads + b0;
+            uint64_t bits = 0;
+            for (uint32_t i = 0; i < qlen; i++) bits += __popc((uint32_t)(qdata[i] ^ b[i]));
+            r = __ddiv_rn(1.0, (double)(bits + 1));
+        }
+        scores[o] = r;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -508,11 +563,12 @@ __global__ void expand_kernel(const uint32_t *__restrict__ bitmap, uint32_t nwor
 }
 __global__ void fill_freq_kernel(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ freqs, uint32_t n,
                                  const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wordoff,
-                                 uint32_t *__restrict__ out_freq) {
+                                 uint32_t *__restrict__ out_freq, uint32_t *__restrict__ out_pos) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t id = ids[i], w = id >> 5;
         const uint32_t rank = wordoff[w] + __popc(bitmap[w] & ((1u << (id & 31)) - 1u));
         out_freq[rank] = freqs[i];
+        if (out_pos) out_pos[rank] = i;
     }
 }
 
@@ -591,6 +647,7 @@ __global__ void __launch_bounds__(256) topn_kernel(const uint32_t *__restrict__ 
             wkey = bk;
             wid = bi;
             wpos = bp;
+            __syncwarp(); // every lane has finished reading the list before lane 0 inserts the next candidate
         }
     }
     __syncwarp();
@@ -620,7 +677,9 @@ __device__ __forceinline__ void score_child(const FusedCommon &fc, ScoreAcc &a, 
     default: break;
     }
 }
-__device__ __forceinline__ double score_finish(const FusedCommon &fc, const ScoreAcc &a, uint32_t doc, uint32_t doc_len) {
+// n_children: the fused path carries no term positions, so GetSlop is `children - 1` (1 for a single child); lists that do carry
+// positions take the per-query chain when a legacy scorer is asked for (II_SearchTopNBatch)
+__device__ __forceinline__ double score_finish(const FusedCommon &fc, const ScoreAcc &a, uint32_t doc, uint32_t doc_len, uint32_t n_children) {
     const float doc_score = fc.doc_score ? fc.doc_score[doc] : 1.0f;
     switch (fc.scorer) {
     case 0:
@@ -631,7 +690,7 @@ __device__ __forceinline__ double score_finish(const FusedCommon &fc, const Scor
     }
     case 1: {
         const double score = __dmul_rn((double)doc_score, __dmul_rn(a.ret, fc.agg_weight));
-        return (score < 0.0) ? 0.0 : score; // minScore = 0 on this path
+        return (score < 0.0) ? 0.0 : __ddiv_rn(score, (double)(int)slop_without_offsets(n_children)); // minScore = 0 on this path
     }
     case 2:
     case 3: {
@@ -639,7 +698,7 @@ __device__ __forceinline__ double score_finish(const FusedCommon &fc, const Scor
         const uint32_t norm = (fc.scorer == 2) ? (fc.max_freq ? fc.max_freq[doc] : 1u) : doc_len;
         if (norm == 0) return 0.0;
         const double tfidf = __ddiv_rn(__dmul_rn((double)doc_score, __dmul_rn(fc.agg_weight, a.ret)), (double)norm);
-        return (tfidf < 0.0) ? 0.0 : tfidf;
+        return (tfidf < 0.0) ? 0.0 : __ddiv_rn(tfidf, (double)(int)slop_without_offsets(n_children));
     }
     case 4: return (double)doc_score;
     case 6: return __dmul_rn(fc.agg_weight, a.ret);
@@ -668,29 +727,60 @@ __device__ __forceinline__ void bitonic_sort_pairs(uint64_t *keys, uint32_t *ids
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kIIThreads) fused_and_kernel(const FusedQuery *__restrict__ queries, uint32_t nq, const FusedCommon fc,
-                                                               uint32_t top_n, uint64_t *__restrict__ cand_keys,
-                                                               uint32_t *__restrict__ cand_ids, uint32_t *__restrict__ hits) {
+// Pre-pass of the fused search: which query owns a work item, and for every (item, other child j) the window [lo, hi) of child
+// j that can hold the item's docIds.  Round-2 first version located the windows inside fused_and_kernel with two warp-wide
+// searches per list behind a barrier each: ~5 dependent HBM round trips per list on the critical path of every CTA (ncu:
+// 37 % warps active, long-scoreboard + barrier stalls, 27 us per CTA for 1.8 GB of traffic).  Here every search is one thread
+// and all of them are in flight at once.
+__global__ void fused_itemq_kernel(const FusedQuery *__restrict__ queries, uint32_t nq, uint32_t *__restrict__ item_q) {
+    const uint32_t q = blockIdx.x;
+    if (q >= nq) return;
+    const uint32_t i0 = queries[q].item0, nc = queries[q].nchunks;
+    for (uint32_t t = threadIdx.x; t < nc; t += blockDim.x) item_q[i0 + t] = q;
+}
+__global__ void __launch_bounds__(256) fused_window_kernel(const FusedQuery *__restrict__ queries, const uint32_t *__restrict__ item_q,
+                                                           uint32_t total_items, uint32_t max_others, uint2 *__restrict__ win) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (uint64_t)total_items * max_others) return;
+    const uint32_t item = (uint32_t)(g / max_others), j = (uint32_t)(g % max_others) + 1;
+    const FusedQuery &Q = queries[item_q[item]];
+    if (j >= Q.n) return;
+    const uint32_t start = (item - Q.item0) * kIIChunk;
+    const uint32_t end = min(start + (uint32_t)kIIChunk, Q.len[0]);
+    const uint32_t *A = Q.ids[0], *B = Q.ids[j];
+    const uint32_t k_lo = A[start], k_hi = A[end - 1] + 1u; // docIds are < 2^32 - 1
+    // the two lower bounds advance in lockstep: two independent loads per round
+    uint32_t lo0 = 0, hi0 = Q.len[j], lo1 = 0, hi1 = Q.len[j];
+    while (lo0 < hi0 || lo1 < hi1) {
+        const uint32_t m0 = lo0 + ((hi0 - lo0) >> 1), m1 = lo1 + ((hi1 - lo1) >> 1);
+        const uint32_t v0 = lo0 < hi0 ? B[m0] : 0u, v1 = lo1 < hi1 ? B[m1] : 0u;
+        if (lo0 < hi0) {
+            if (v0 < k_lo)
+                lo0 = m0 + 1;
+            else
+                hi0 = m0;
+        }
+        if (lo1 < hi1) {
+            if (v1 < k_hi)
+                lo1 = m1 + 1;
+            else
+                hi1 = m1;
+        }
+    }
+    win[(size_t)item * (kFusedMaxLists - 1) + (j - 1)] = make_uint2(lo0, lo1);
+}
+
+__global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQuery *__restrict__ queries, const uint32_t *__restrict__ item_q,
+                                                               const uint2 *__restrict__ win, const FusedCommon fc, uint32_t top_n,
+                                                               uint64_t *__restrict__ cand_keys, uint32_t *__restrict__ cand_ids,
+                                                               uint32_t *__restrict__ hits) {
     __shared__ uint32_t sB[kIISmemElems];
     __shared__ uint64_t s_keys[kIIChunk];
     __shared__ uint32_t s_ids[kIIChunk];
-    __shared__ uint32_t s_lo, s_hi, s_q, s_cnt;
     __shared__ uint32_t s_warp[kIIThreads / 32];
     const uint32_t item = blockIdx.x;
-    if (threadIdx.x == 0) { // which query owns this work item: binary search over the queries' first items
-        uint32_t lo = 0, hi = nq;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (queries[mid].item0 <= item)
-                lo = mid;
-            else
-                hi = mid;
-        }
-        s_q = lo;
-        s_cnt = 0;
-    }
-    __syncthreads();
-    const FusedQuery &Q = queries[s_q];
+    const uint32_t q = item_q[item];
+    const FusedQuery &Q = queries[q];
     const uint32_t n = Q.n;
     const uint32_t chunk = item - Q.item0;
     const uint32_t start = chunk * kIIChunk;
@@ -704,44 +794,79 @@ __global__ void __launch_bounds__(kIIThreads) fused_and_kernel(const FusedQuery 
         alive[i] = idx < end;
         doc[i] = alive[i] ? A[idx] : 0xFFFFFFFFu;
     }
-    const uint32_t a_lo = A[start], a_hi = A[end - 1];
-    bool any_alive = true;
+    // the windows of the other children (block-uniform), and where each would sit in shared memory
+    uint32_t w_lo[kFusedMaxLists - 1], w_off[kFusedMaxLists - 1], w_len[kFusedMaxLists - 1];
+    uint32_t total_range = 0;
+    bool all_fit = true;
 #pragma unroll
     for (int j = 1; j < kFusedMaxLists; j++) {
-        if (j >= (int)n || !any_alive) break;
-        const uint32_t *B = Q.ids[j];
-        if (threadIdx.x < 64) { // warp 0 finds the window start, warp 1 its end
-            const bool first = threadIdx.x < 32;
-            const uint32_t r = warp_lower_bound_u32(B, 0, Q.len[j], first ? a_lo : a_hi + 1u, threadIdx.x & 31);
-            if ((threadIdx.x & 31) == 0) *(first ? &s_lo : &s_hi) = r;
+        w_lo[j - 1] = w_off[j - 1] = w_len[j - 1] = 0;
+        if (j < (int)n) {
+            const uint2 w = win[(size_t)item * (kFusedMaxLists - 1) + (j - 1)];
+            w_lo[j - 1] = w.x;
+            w_len[j - 1] = w.y - w.x;
+            w_off[j - 1] = total_range;
+            all_fit = all_fit && w_len[j - 1] <= (uint32_t)kIISmemElems && total_range + w_len[j - 1] <= (uint32_t)kIISmemElems;
+            if (all_fit) total_range += w_len[j - 1];
         }
+    }
+    if (all_fit) {
+        // every window at once: one round of loads, one barrier, then each entry walks the children on its own
+#pragma unroll
+        for (int j = 1; j < kFusedMaxLists; j++)
+            if (j < (int)n) {
+                const uint32_t *B = Q.ids[j] + w_lo[j - 1];
+                for (uint32_t t = threadIdx.x; t < w_len[j - 1]; t += kIIThreads) sB[w_off[j - 1] + t] = B[t];
+            }
         __syncthreads();
-        const uint32_t lo = s_lo, hi = s_hi, range = hi - lo;
-        if (range <= (uint32_t)kIISmemElems) {
-            for (uint32_t t = threadIdx.x; t < range; t += kIIThreads) sB[t] = B[lo + t];
-            __syncthreads();
 #pragma unroll
-            for (int i = 0; i < kIIItems; i++) {
-                if (alive[i]) {
-                    const uint32_t p = lower_bound_u32(sB, 0, range, doc[i]);
-                    alive[i] = (p < range) && sB[p] == doc[i];
-                    pos[j - 1][i] = lo + p;
+        for (int j = 1; j < kFusedMaxLists; j++)
+            if (j < (int)n) {
+                const uint32_t *W = sB + w_off[j - 1];
+                const uint32_t range = w_len[j - 1];
+#pragma unroll
+                for (int i = 0; i < kIIItems; i++)
+                    if (alive[i]) {
+                        const uint32_t p = lower_bound_u32(W, 0, range, doc[i]);
+                        alive[i] = (p < range) && W[p] == doc[i];
+                        pos[j - 1][i] = w_lo[j - 1] + p;
+                    }
+            }
+    } else {
+        // a window larger than the staging buffer (a short list against a much longer one): list by list, large windows
+        // searched in place
+        bool any_alive = true;
+#pragma unroll
+        for (int j = 1; j < kFusedMaxLists; j++) {
+            if (j >= (int)n || !any_alive) break;
+            const uint32_t *B = Q.ids[j];
+            const uint32_t lo = w_lo[j - 1], range = w_len[j - 1], hi = lo + range;
+            if (range <= (uint32_t)kIISmemElems) {
+                for (uint32_t t = threadIdx.x; t < range; t += kIIThreads) sB[t] = B[lo + t];
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < kIIItems; i++) {
+                    if (alive[i]) {
+                        const uint32_t p = lower_bound_u32(sB, 0, range, doc[i]);
+                        alive[i] = (p < range) && sB[p] == doc[i];
+                        pos[j - 1][i] = lo + p;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kIIItems; i++) {
+                    if (alive[i]) {
+                        const uint32_t p = lower_bound_u32(B, lo, hi, doc[i]);
+                        alive[i] = (p < hi) && B[p] == doc[i];
+                        pos[j - 1][i] = p;
+                    }
                 }
             }
-        } else {
+            bool any = false;
 #pragma unroll
-            for (int i = 0; i < kIIItems; i++) {
-                if (alive[i]) {
-                    const uint32_t p = lower_bound_u32(B, lo, hi, doc[i]);
-                    alive[i] = (p < hi) && B[p] == doc[i];
-                    pos[j - 1][i] = p;
-                }
-            }
+            for (int i = 0; i < kIIItems; i++) any |= alive[i];
+            any_alive = __syncthreads_or(any); // also fences sB before the next list reuses it
         }
-        bool any = false;
-#pragma unroll
-        for (int i = 0; i < kIIItems; i++) any |= alive[i];
-        any_alive = __syncthreads_or(any); // also fences sB before the next list reuses it
     }
     // score the survivors, child by child in aggregate order
     uint32_t cnt = 0;
@@ -758,7 +883,7 @@ __global__ void __launch_bounds__(kIIThreads) fused_and_kernel(const FusedQuery 
 #pragma unroll
         for (int j = 1; j < kFusedMaxLists; j++)
             if (j < (int)n) score_child(fc, acc, Q.weight[j], Q.idf[j], Q.bm25_idf[j], Q.freqs[j][pos[j - 1][i]], dl);
-        key[i] = rank_key(score_finish(fc, acc, d, dl));
+        key[i] = rank_key(score_finish(fc, acc, d, dl, n));
     }
     // ordered compaction of (key, docId) into shared memory, then the CTA's best top_n
     uint32_t incl = cnt;
@@ -783,17 +908,18 @@ __global__ void __launch_bounds__(kIIThreads) fused_and_kernel(const FusedQuery 
             s_ids[rank] = doc[i];
             rank++;
         }
-    const uint32_t nsort = max(32u, next_pow2(total));
     __syncthreads();
-    for (uint32_t t = total + threadIdx.x; t < nsort; t += kIIThreads) s_keys[t] = 0xFFFFFFFFFFFFFFFFull, s_ids[t] = 0xFFFFFFFFu;
-    if (total > 1) bitonic_sort_pairs(s_keys, s_ids, nsort); // entry syncs inside
-    else __syncthreads();
+    if (total > top_n) { // more survivors than the query keeps: the CTA's best top_n (the per-query pass takes lists in any order)
+        const uint32_t nsort = max(32u, next_pow2(total));
+        for (uint32_t t = total + threadIdx.x; t < nsort; t += kIIThreads) s_keys[t] = 0xFFFFFFFFFFFFFFFFull, s_ids[t] = 0xFFFFFFFFu;
+        bitonic_sort_pairs(s_keys, s_ids, nsort); // entry syncs inside
+    }
     for (uint32_t t = threadIdx.x; t < top_n; t += kIIThreads) {
         const bool v = t < total;
         cand_keys[(size_t)item * top_n + t] = v ? s_keys[t] : 0xFFFFFFFFFFFFFFFFull;
         cand_ids[(size_t)item * top_n + t] = v ? s_ids[t] : 0xFFFFFFFFu;
     }
-    if (threadIdx.x == 0 && total) atomicAdd(&hits[s_q], total);
+    if (threadIdx.x == 0 && total) atomicAdd(&hits[q], total);
 }
 
 // one CTA per query: best top_n of its items' candidate lists (each ascending, ~0-padded)
@@ -810,6 +936,9 @@ __global__ void __launch_bounds__(256) fused_topn_kernel(const FusedQuery *__res
     for (uint32_t t = threadIdx.x; t < 2 * kTile; t += blockDim.x) s_keys[t] = 0xFFFFFFFFFFFFFFFFull, s_ids[t] = 0xFFFFFFFFu;
     if (threadIdx.x == 0) s_fill = top_n;
     __syncthreads();
+    // the fill level is tracked in registers (block-uniform, from the barrier's own count): reading s_fill for the fold decision
+    // would race with the next round's atomicAdd of a faster warp and could split the CTA across the barriers below
+    uint32_t fill = top_n;
     for (size_t off = 0; off < total; off += blockDim.x) {
         const size_t i = off + threadIdx.x;
         const uint64_t k = i < total ? cand_keys[base + i] : 0xFFFFFFFFFFFFFFFFull;
@@ -823,13 +952,13 @@ __global__ void __launch_bounds__(256) fused_topn_kernel(const FusedQuery *__res
             s_keys[p] = k;
             s_ids[p] = cand_ids[base + i];
         }
-        __syncthreads();
-        if (s_fill + blockDim.x > 2 * kTile || off + blockDim.x >= total) { // buffer (nearly) full, or last round: fold
-            const uint32_t fill = s_fill;
+        fill += (uint32_t)__syncthreads_count(real);
+        if (fill + blockDim.x > 2 * kTile || off + blockDim.x >= total) { // buffer (nearly) full, or last round: fold
             const uint32_t nsort = max(32u, next_pow2(fill));
             for (uint32_t t = fill + threadIdx.x; t < nsort; t += blockDim.x) s_keys[t] = 0xFFFFFFFFFFFFFFFFull, s_ids[t] = 0xFFFFFFFFu;
             bitonic_sort_pairs(s_keys, s_ids, nsort);
             if (threadIdx.x == 0) s_fill = top_n;
+            fill = top_n;
             __syncthreads();
         }
     }
@@ -839,13 +968,21 @@ __global__ void __launch_bounds__(256) fused_topn_kernel(const FusedQuery *__res
     }
 }
 
-cudaError_t ii_launch_fused_search(const FusedQuery *d_queries, uint32_t nq, uint32_t total_items, const FusedCommon &fc, uint32_t top_n,
-                                   uint64_t *d_cand_keys, uint32_t *d_cand_ids, uint32_t *d_hits, uint64_t *d_out_keys,
-                                   uint32_t *d_out_ids, cudaStream_t s) {
-    if (nq == 0 || top_n == 0 || top_n > (uint32_t)kFusedMaxTopN) return cudaErrorInvalidValue;
+cudaError_t ii_launch_fused_search(const FusedQuery *d_queries, uint32_t nq, uint32_t total_items, uint32_t max_children, const FusedCommon &fc,
+                                   uint32_t top_n, uint32_t *d_item_q, uint2 *d_win, uint64_t *d_cand_keys, uint32_t *d_cand_ids,
+                                   uint32_t *d_hits, uint64_t *d_out_keys, uint32_t *d_out_ids, cudaStream_t s) {
+    if (nq == 0 || top_n == 0 || top_n > (uint32_t)kFusedMaxTopN || max_children == 0 || max_children > (uint32_t)kFusedMaxLists)
+        return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(d_hits, 0, (size_t)nq * 4, s);
     if (e != cudaSuccess) return e;
-    if (total_items) fused_and_kernel<<<total_items, kIIThreads, 0, s>>>(d_queries, nq, fc, top_n, d_cand_keys, d_cand_ids, d_hits);
+    if (total_items) {
+        fused_itemq_kernel<<<nq, 128, 0, s>>>(d_queries, nq, d_item_q);
+        if (max_children > 1) {
+            const uint64_t searches = (uint64_t)total_items * (max_children - 1);
+            fused_window_kernel<<<(uint32_t)((searches + 255) / 256), 256, 0, s>>>(d_queries, d_item_q, total_items, max_children - 1, d_win);
+        }
+        fused_and_kernel<<<total_items, kIIThreads, 0, s>>>(d_queries, d_item_q, d_win, fc, top_n, d_cand_keys, d_cand_ids, d_hits);
+    }
     fused_topn_kernel<<<nq, 256, 0, s>>>(d_queries, top_n, d_cand_keys, d_cand_ids, d_out_keys, d_out_ids);
     return cudaGetLastError();
 }
@@ -883,7 +1020,7 @@ __global__ void phrase_filter_kernel(const PhraseArgs a, const uint32_t *__restr
         OffCur it[kPhraseMaxLists];
         uint32_t n = 0;
         for (uint32_t j = 0; j < a.n; j++) {
-            const uint32_t p = a.pos[(size_t)a.row[j] * a.fstride + o];
+            const uint32_t p = a.pos[(size_t)j * a.fstride + o];
             const uint32_t len = (a.off_len[j] && p != 0xFFFFFFFFu) ? a.off_len[j][p] : 0u; // virtual results carry no offsets
             if (len) { // has_offsets
                 it[n].p = a.bytes[j] + a.off_pos[j][p];
@@ -987,11 +1124,13 @@ __global__ void flag_count_kernel(const uint32_t *__restrict__ flags, const uint
     __syncthreads();
     if (threadIdx.x == 0) chunk_counts[blockIdx.x] = s_cnt;
 }
-// ordered compaction of docs and the n freq rows (one warp per chunk keeps the order with ballots)
+// ordered compaction of docs, the n freq rows and (optionally) the n posting-position rows (one warp per chunk keeps the order
+// with ballots)
 __global__ void flag_compact_kernel(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ d_len, uint32_t cap_len,
                                     const uint32_t *__restrict__ chunk_off, const uint32_t *__restrict__ docs,
-                                    const uint32_t *__restrict__ freqs, uint32_t n, size_t fstride, uint32_t *__restrict__ out_docs,
-                                    uint32_t *__restrict__ out_freqs, size_t out_fstride) {
+                                    const uint32_t *__restrict__ freqs, const uint32_t *__restrict__ pos, uint32_t n, size_t fstride,
+                                    uint32_t *__restrict__ out_docs, uint32_t *__restrict__ out_freqs, uint32_t *__restrict__ out_pos,
+                                    size_t out_fstride) {
     const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
     const uint32_t base = blockIdx.x * 1024u;
     uint32_t o = chunk_off[blockIdx.x];
@@ -1003,7 +1142,10 @@ __global__ void flag_compact_kernel(const uint32_t *__restrict__ flags, const ui
         if (keep) {
             const uint32_t dst = o + __popc(mask & ((1u << lane) - 1u));
             out_docs[dst] = docs[i];
-            for (uint32_t j = 0; j < n; j++) out_freqs[(size_t)j * out_fstride + dst] = freqs[(size_t)j * fstride + i];
+            for (uint32_t j = 0; j < n; j++) {
+                out_freqs[(size_t)j * out_fstride + dst] = freqs[(size_t)j * fstride + i];
+                if (out_pos) out_pos[(size_t)j * out_fstride + dst] = pos[(size_t)j * fstride + i];
+            }
         }
         o += __popc(mask);
     }
@@ -1011,14 +1153,74 @@ __global__ void flag_compact_kernel(const uint32_t *__restrict__ flags, const ui
 
 cudaError_t ii_launch_phrase_filter(const PhraseArgs &a, const uint32_t *d_len, uint32_t cap_len, uint32_t *d_flags, uint32_t *d_counts,
                                     uint32_t *d_offsets, uint32_t *d_total, const uint32_t *d_docs, const uint32_t *d_freqs, size_t fstride,
-                                    uint32_t *d_out_docs, uint32_t *d_out_freqs, size_t out_fstride, cudaStream_t s) {
+                                    uint32_t *d_out_docs, uint32_t *d_out_freqs, uint32_t *d_out_pos, size_t out_fstride, cudaStream_t s) {
     if (!cap_len) return cudaMemsetAsync(d_total, 0, 4, s);
     const uint32_t chunks = (cap_len + 1023) / 1024;
     phrase_filter_kernel<<<std::max(1u, std::min((cap_len + 127) / 128, 148u * 16)), 128, 0, s>>>(a, d_len, cap_len, d_flags);
     flag_count_kernel<<<chunks, 256, 0, s>>>(d_flags, d_len, cap_len, d_counts);
     scan_kernel<<<1, 1024, 0, s>>>(d_counts, chunks, d_offsets, d_total);
-    flag_compact_kernel<<<chunks, 32, 0, s>>>(d_flags, d_len, cap_len, d_offsets, d_docs, d_freqs, a.n, fstride, d_out_docs, d_out_freqs,
-                                              out_fstride);
+    flag_compact_kernel<<<chunks, 32, 0, s>>>(d_flags, d_len, cap_len, d_offsets, d_docs, d_freqs, a.pos, a.n, fstride, d_out_docs, d_out_freqs,
+                                              d_out_pos, out_fstride);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// GetSlop: IndexResult_MinOffsetDelta (src/index_result/index_result.c:51-108) per hit
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t off_next_or_eof(OffCur &c) { // RSOffsetIterator::Next: RS_OFFSETVECTOR_EOF at the end
+    uint32_t p;
+    return off_next(c, p) ? p : 0xFFFFFFFFu;
+}
+__global__ void min_offset_delta_kernel(const SlopArgs a, const uint32_t *__restrict__ docs, const uint32_t *__restrict__ d_len,
+                                        uint32_t cap_len, uint32_t *__restrict__ slop) {
+    const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
+    for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < m; o += gridDim.x * blockDim.x) {
+        const ChildOrder co = child_order_of(a.is_union ? a.order : nullptr, a.n, docs[o]);
+        // the aggregate's children: all of them for an intersection (virtual results included), the present ones for a union
+        uint32_t num = 0;
+        int dist = 0;
+        bool have_prev = false;
+        OffCur prev{};
+        for (uint32_t ci = 0; ci < co.n; ci++) {
+            const uint32_t c = co.perm ? co.perm[ci] : ci;
+            const uint32_t p = a.pos[(size_t)c * a.fstride + o];
+            if (a.is_union && p == 0xFFFFFFFFu) continue; // not part of this document's aggregate
+            num++;
+            const uint32_t len = (a.off_len[c] && p != 0xFFFFFFFFu) ? a.off_len[c][p] : 0u;
+            if (!len) continue; // RSIndexResult_HasOffsets :19-42: virtual results / empty offset vectors are skipped
+            OffCur cur;
+            cur.p = a.bytes[c] + a.off_pos[c][p];
+            cur.end = cur.p + len;
+            cur.last = 0;
+            if (have_prev) { // the pair (previous child with offsets, this one); this one then opens the next pair (:63-104)
+                OffCur v1 = prev, v2 = cur;
+                uint32_t p1 = off_next_or_eof(v1), p2 = off_next_or_eof(v2);
+                int cd = (int)(p2 > p1 ? p2 - p1 : p1 - p2);
+                while (cd > 1 && p1 != 0xFFFFFFFFu && p2 != 0xFFFFFFFFu) {
+                    const uint32_t d = p2 > p1 ? p2 - p1 : p1 - p2;
+                    cd = (int)(d < (uint32_t)cd ? d : (uint32_t)cd);
+                    if (p2 > p1)
+                        p1 = off_next_or_eof(v1);
+                    else
+                        p2 = off_next_or_eof(v2);
+                }
+                dist += cd * cd;
+            }
+            prev = cur;
+            have_prev = true;
+        }
+        uint32_t r;
+        if (num <= 1)
+            r = 1;
+        else
+            r = dist ? (uint32_t)(int)sqrt((double)dist) : num - 1;
+        slop[o] = r;
+    }
+}
+cudaError_t ii_launch_min_offset_delta(const SlopArgs &a, const uint32_t *d_docs, const uint32_t *d_len, uint32_t cap_len,
+                                       uint32_t *d_slop, cudaStream_t s) {
+    if (!cap_len) return cudaSuccess;
+    min_offset_delta_kernel<<<std::max(1u, std::min((cap_len + 127) / 128, 148u * 16)), 128, 0, s>>>(a, d_docs, d_len, cap_len, d_slop);
     return cudaGetLastError();
 }
 
@@ -1082,7 +1284,7 @@ cudaError_t ii_launch_score(const ScoreArgs &sa, const uint32_t *d_docs, const u
 cudaError_t ii_launch_union(const uint32_t *const *d_ids, const uint32_t *const *d_freqs, const uint32_t *lens, uint32_t n,
                             uint32_t nwords, uint32_t *d_bitmap, uint32_t *d_blocksum, uint32_t *d_blockoff,
                             uint32_t *d_wordoff, uint32_t *d_total, uint32_t *d_out_doc, uint32_t *d_out_freq,
-                            size_t fstride, bool want_freqs, cudaStream_t s) {
+                            size_t fstride, bool want_freqs, uint32_t *d_out_pos, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(d_bitmap, 0, (size_t)nwords * 4, s);
     if (e != cudaSuccess) return e;
     for (uint32_t j = 0; j < n; j++)
@@ -1095,7 +1297,14 @@ cudaError_t ii_launch_union(const uint32_t *const *d_ids, const uint32_t *const 
         for (uint32_t j = 0; j < n; j++)
             if (lens[j])
                 fill_freq_kernel<<<grid_for(lens[j], 256, 148 * 8), 256, 0, s>>>(d_ids[j], d_freqs[j], lens[j], d_bitmap, d_wordoff,
-                                                                                d_out_freq + (size_t)j * fstride);
+                                                                                d_out_freq + (size_t)j * fstride,
+                                                                                d_out_pos ? d_out_pos + (size_t)j * fstride : nullptr);
+    return cudaGetLastError();
+}
+cudaError_t ii_launch_hamming(const uint32_t *d_docs, const uint32_t *d_len, uint32_t cap_len, const uint8_t *d_payloads,
+                              const uint64_t *d_payload_off, const uint8_t *d_qdata, uint32_t qlen, double *d_scores, cudaStream_t s) {
+    if (!cap_len) return cudaSuccess;
+    hamming_kernel<<<grid_for(cap_len, 256, 148 * 8), 256, 0, s>>>(d_docs, d_len, cap_len, d_payloads, d_payload_off, d_qdata, qlen, d_scores);
     return cudaGetLastError();
 }
 uint32_t ii_topn_lists(uint32_t m) { return grid_for(m, 256, 148 * 2) * 8; }

@@ -32,8 +32,10 @@ struct GatherArgs {
     const uint32_t *tmp_idx, *tmp_pos, *counts, *offsets;
     size_t stride;   // of tmp_pos
     uint32_t *out_doc;
+    uint8_t row[kIIMaxLists]; // kernel slot j -> its row of out_freq / out_pos: the AGGREGATE child index
     uint32_t *out_freq; // [n][fstride]
-    uint32_t *out_pos;  // nullable, [n][fstride]: position of the hit inside list j (phrase checks read the term positions there)
+    uint32_t *out_pos;  // nullable, [n][fstride]: position of the hit inside the child (phrase checks and GetSlop read the term
+                        // positions there); 0xFFFFFFFF = a virtual result (NOT child / absent OPTIONAL child)
     size_t fstride;
 };
 
@@ -43,16 +45,42 @@ struct PhraseArgs {
     const uint8_t *bytes[kPhraseMaxLists];    // gathered block bytes of list j (the offsets payloads live inside)
     const uint32_t *off_pos[kPhraseMaxLists]; // per posting: start of its offsets payload in bytes[j]
     const uint32_t *off_len[kPhraseMaxLists]; // per posting: length (0 / NULL array = the child carries no offsets)
-    const uint32_t *pos;                      // [n][fstride] posting position of hit o, rows in KERNEL-slot order (GatherArgs::out_pos)
-    uint32_t row[kPhraseMaxLists];            // aggregate child j -> its row of pos
+    const uint32_t *pos;                      // [n][fstride] posting position of hit o inside child j (GatherArgs::out_pos)
     size_t fstride;
     uint32_t n;
     uint32_t max_slop; // 0xFFFFFFFF = no limit
     int in_order;
 };
+// survivors are compacted in order: docs, the n freq rows and (when d_out_pos is given) the n rows of a.pos
 cudaError_t ii_launch_phrase_filter(const PhraseArgs &a, const uint32_t *d_len, uint32_t cap_len, uint32_t *d_flags, uint32_t *d_counts,
                                     uint32_t *d_offsets, uint32_t *d_total, const uint32_t *d_docs, const uint32_t *d_freqs, size_t fstride,
-                                    uint32_t *d_out_docs, uint32_t *d_out_freqs, size_t out_fstride, cudaStream_t s);
+                                    uint32_t *d_out_docs, uint32_t *d_out_freqs, uint32_t *d_out_pos, size_t out_fstride, cudaStream_t s);
+
+// GetSlop of the legacy scorers = IndexResult_MinOffsetDelta (src/index_result/index_result.c:51-108), one thread per hit.
+// Rows of `pos` are in AGGREGATE child order: the posting position of the hit inside child j, 0xFFFFFFFF = the child is a
+// virtual result here (NOT / absent OPTIONAL child of an intersection) or, for a union, is not part of the aggregate at all.
+struct SlopArgs {
+    const uint8_t *bytes[kIIMaxLists];
+    const uint32_t *off_pos[kIIMaxLists];
+    const uint32_t *off_len[kIIMaxLists]; // NULL: the child carries no offsets
+    const uint32_t *pos;                  // [n][fstride]
+    const struct UnionOrder *order;       // unions: the children in the reference's active-array order (NULL: index order)
+    size_t fstride;
+    uint32_t n;
+    int is_union;
+};
+cudaError_t ii_launch_min_offset_delta(const SlopArgs &a, const uint32_t *d_docs, const uint32_t *d_len, uint32_t cap_len,
+                                       uint32_t *d_slop, cudaStream_t s);
+
+// UnionFlat keeps its children in an "active" array and swap-removes a child when it is exhausted (union_flat.rs:174-180,
+// advance_and_find_min :218-258): the aggregate's child order for a document is the active array's order at that moment.
+// For a union read front to back that order is a function of the docId alone: epoch e covers docIds in (bound[e-1], bound[e]].
+struct UnionOrder {
+    uint32_t n_epochs;
+    uint32_t bound[kIIMaxLists + 1];
+    uint8_t n_active[kIIMaxLists + 1];
+    uint8_t perm[kIIMaxLists + 1][kIIMaxLists];
+};
 
 struct ScoreArgs {
     int scorer; // II_Scorer numbering
@@ -64,6 +92,10 @@ struct ScoreArgs {
     const uint32_t *doc_len;   // by docId, may be NULL
     const float *doc_score;    // by docId, may be NULL
     const uint32_t *max_freq;  // by docId, may be NULL
+    // GetSlop of the legacy scorers (BM25, TFIDF, TFIDF.DOCNORM divide by it): per hit when term positions are on the device,
+    // else the value IndexResult_MinOffsetDelta returns without offsets: children - 1 (1 for a single child)
+    const uint32_t *slop;      // per hit, may be NULL
+    const UnionOrder *order;   // unions: child order per docId epoch (device memory), may be NULL
 };
 
 // ---- fused batch search: AND + scorer + top-N of MANY queries in two launches --------------------------------------
@@ -89,13 +121,14 @@ struct FusedCommon {
     const float *doc_score;
     const uint32_t *max_freq;
 };
-// Launch 1: one CTA per work item — membership of the chunk's docIds in every other child (window located by two warp-wide
-// searches, staged in shared memory), freqs of the matches, the scorer, and the CTA's best `top_n` hits into
-// cand_keys / cand_ids [item][top_n] (padded with ~0); hits[q] += survivors.  Launch 2: one CTA per query selects the best
-// top_n by (score desc, docId asc) over its items' candidates into out_keys / out_ids [nq][top_n].
-cudaError_t ii_launch_fused_search(const FusedQuery *d_queries, uint32_t nq, uint32_t total_items, const FusedCommon &fc, uint32_t top_n,
-                                   uint64_t *d_cand_keys, uint32_t *d_cand_ids, uint32_t *d_hits, uint64_t *d_out_keys,
-                                   uint32_t *d_out_ids, cudaStream_t s);
+// Launches: (1) item -> query table; (2) one thread per (work item, other child): the window of the child that can hold the
+// item's docIds; (3) one CTA per work item — every window staged in shared memory at once (list by list when they do not fit),
+// membership, freqs of the matches, the scorer, and the CTA's best `top_n` hits into cand_keys / cand_ids [item][top_n] (padded
+// with ~0); hits[q] += survivors; (4) one CTA per query selects the best top_n by (score desc, docId asc) over its items'
+// candidates into out_keys / out_ids [nq][top_n].  d_item_q: [total_items]; d_win: [total_items][kFusedMaxLists - 1].
+cudaError_t ii_launch_fused_search(const FusedQuery *d_queries, uint32_t nq, uint32_t total_items, uint32_t max_children, const FusedCommon &fc,
+                                   uint32_t top_n, uint32_t *d_item_q, uint2 *d_win, uint64_t *d_cand_keys, uint32_t *d_cand_ids,
+                                   uint32_t *d_hits, uint64_t *d_out_keys, uint32_t *d_out_ids, cudaStream_t s);
 
 cudaError_t ii_launch_decode(const uint8_t *d_bytes, const uint64_t *d_byte_off, const uint64_t *d_first_id,
                              const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint32_t *d_ids, uint32_t *d_freqs,
@@ -116,7 +149,11 @@ cudaError_t ii_launch_score(const ScoreArgs &sa, const uint32_t *d_docs, const u
 cudaError_t ii_launch_union(const uint32_t *const *d_ids, const uint32_t *const *d_freqs, const uint32_t *lens, uint32_t n,
                             uint32_t nwords, uint32_t *d_bitmap, uint32_t *d_blocksum, uint32_t *d_blockoff,
                             uint32_t *d_wordoff, uint32_t *d_total, uint32_t *d_out_doc, uint32_t *d_out_freq,
-                            size_t fstride, bool want_freqs, cudaStream_t s);
+                            size_t fstride, bool want_freqs, uint32_t *d_out_pos, cudaStream_t s);
+// HAMMING scorer (src/ext/default.c:475-497): 1 / (popcount(query payload XOR document payload) + 1); 0 when the document has no
+// payload or the lengths differ.  payload_off[d] .. payload_off[d+1] delimit the payload of docId d inside `payloads`.
+cudaError_t ii_launch_hamming(const uint32_t *d_docs, const uint32_t *d_len, uint32_t cap_len, const uint8_t *d_payloads,
+                              const uint64_t *d_payload_off, const uint8_t *d_qdata, uint32_t qlen, double *d_scores, cudaStream_t s);
 uint32_t ii_topn_lists(uint32_t m);
 cudaError_t ii_launch_topn(const uint32_t *d_docs, const double *d_scores, const uint32_t *d_len, uint32_t cap_len, uint32_t k,
                            uint64_t *d_keys, uint32_t *d_ids, cudaStream_t s);

@@ -76,6 +76,8 @@ SIGNATURES = [
     ("II_ResultSet_Free", None, [_P]),
     ("II_CalculateIDF", C.c_double, [_SZ, _SZ]),
     ("II_CalculateIDF_BM25", C.c_double, [_SZ, _SZ]),
+    ("II_ScoreHamming", C.c_int, [_P, _P, _P, _SZ]),
+    ("II_DocTable_SetPayloads", C.c_int, [_P, _P, _P]),
     ("II_Score", C.c_int, [_P, C.c_int, C.POINTER(II_TermParams), C.c_double, C.POINTER(II_IndexStats), _P, C.c_double, C.c_uint64]),
     ("II_ResultSet_Fetch", C.c_int, [_P, _P, _P, _P]),
     ("II_ResultSet_NumChildren", _SZ, [_P]),
@@ -181,6 +183,14 @@ class DocTable:
         if not self.h:
             raise RuntimeError("II_DocTable_New failed")
 
+    def set_payloads(self, payloads):
+        """payloads: list indexed by docId (0..max_doc_id) of bytes / None"""
+        off = np.zeros(len(payloads) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(p) if p else 0 for p in payloads])
+        blob = np.frombuffer(b"".join(p or b"" for p in payloads) or b"\0", dtype=np.uint8)
+        if self.L.II_DocTable_SetPayloads(self.h, _ptr(blob), _ptr(off)) != 0:
+            raise RuntimeError("II_DocTable_SetPayloads failed")
+
     def __del__(self):
         try:
             if self.h:
@@ -218,6 +228,11 @@ class ResultSet:
         if rc != 0:
             raise RuntimeError("II_Score failed")
 
+    def score_hamming(self, doc_table, qdata: bytes):
+        buf = (C.c_uint8 * max(1, len(qdata))).from_buffer_copy(qdata or b"\0")
+        if self.L.II_ScoreHamming(self.h, doc_table.h, buf, len(qdata)) != 0:
+            raise RuntimeError("II_ScoreHamming failed")
+
     def fetch(self, want_freqs=True):
         m = len(self)
         ids = np.zeros(m, dtype=np.uint64)
@@ -254,6 +269,11 @@ class ResultSet:
 
 def intersect(lists) -> ResultSet:
     return ResultSet(lib().II_Intersect(_list_array(lists), len(lists)))
+
+
+def intersect_ex(lists, modes) -> ResultSet:
+    """II_IntersectEx: modes[i] 0 = required, 1 = NOT, 2 = OPTIONAL"""
+    return ResultSet(lib().II_IntersectEx(_list_array(lists), (C.c_int * len(lists))(*modes), len(lists)))
 
 
 def postings_with_offsets(block_lists, codec=0):

@@ -399,6 +399,8 @@ def postings():
         L.orc_ii_fill_synth.argtypes = [_P, C.c_uint64, C.c_uint64]
         L.orc_within_range.restype = C.c_int
         L.orc_within_range.argtypes = [_SZ, _P, _P, C.c_int, C.c_uint32, C.c_int]
+        L.orc_min_offset_delta.restype = C.c_int
+        L.orc_min_offset_delta.argtypes = [_SZ, _P, _P, _SZ, _P]
         L.orc_time_search3.restype = C.c_double
         L.orc_time_search3.argtypes = [_P, _SZ, _P, C.c_uint64, C.c_double, _SZ, C.c_int, _P, _P, _P]
         _post_bound = True
@@ -418,6 +420,10 @@ def ref_scorers():
         L.RefScore.restype = C.c_double
         L.RefScore.argtypes = [C.c_char_p, C.c_int, _SZ, _P, _P, _P, _P, C.c_double, C.c_uint32, C.c_uint32, C.c_float,
                                _SZ, C.c_double, C.c_int, C.c_double, C.c_uint64]
+        L.RefHamming.restype = C.c_double
+        L.RefHamming.argtypes = [C.c_char_p, _SZ, C.c_char_p, _SZ]
+        L.RefMinOffsetDelta.restype = C.c_int
+        L.RefMinOffsetDelta.argtypes = [C.c_int, _SZ, _P, _P, _SZ, _P]
         _ref_scorers = L
     return _ref_scorers
 
@@ -474,6 +480,35 @@ def within_range(offset_bytes, max_slop, in_order):
     ptrs = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
     lens = (C.c_size_t * n)(*[len(b) for b in offset_bytes])
     return bool(postings().orc_within_range(n, ptrs, lens, 0 if max_slop is None else 1, 0 if max_slop is None else max_slop, int(in_order)))
+
+
+def _slop_args(positions, virtual):
+    n = len(positions)
+    stride = max(1, max((len(p) for p in positions), default=1))
+    npos = (C.c_uint32 * n)(*[len(p) for p in positions])
+    flat = (C.c_uint32 * (n * stride))()
+    for i, p in enumerate(positions):
+        for j, v in enumerate(p):
+            flat[i * stride + j] = v
+    virt = (C.c_int * n)(*[int(bool(v)) for v in (virtual or [0] * n)])
+    return n, npos, flat, stride, virt
+
+
+def min_offset_delta(positions, virtual=None):
+    """oracle GetSlop (IndexResult_MinOffsetDelta) over an aggregate of term leaves; positions: list of position lists"""
+    n, npos, flat, stride, virt = _slop_args(positions, virtual)
+    return postings().orc_min_offset_delta(n, npos, flat, stride, virt)
+
+
+def reference_min_offset_delta(positions, virtual=None, is_union=False):
+    """the reference's own src/index_result/index_result.c:51-108 (compiled in place into libscorers_ref.so)"""
+    n, npos, flat, stride, virt = _slop_args(positions, virtual)
+    return ref_scorers().RefMinOffsetDelta(int(is_union), n, npos, flat, stride, virt)
+
+
+def reference_hamming(payload, qdata):
+    """the reference's HammingDistanceScorer (src/ext/default.c:475-497); payload None = the document has no payload"""
+    return ref_scorers().RefHamming(payload, len(payload) if payload else 0, qdata, len(qdata))
 
 
 def run_intersect(indexes, union=False, quick=False):

@@ -28,8 +28,8 @@ def test_extension_init_registers_the_b200_scorers(tmp_path):
     exe = _build(tmp_path)
     r = subprocess.run([str(exe), LIB, str(tmp_path), "10", "1.0", "register-only"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
-    assert r.stdout.strip() == ("registered 7: BM25STD.B200 BM25.B200 TFIDF.B200 TFIDF.DOCNORM.B200 DOCSCORE.B200 BM25STD.TANH.B200 "
-                                "DISMAX.B200")
+    assert r.stdout.strip() == ("registered 8: BM25STD.B200 BM25.B200 TFIDF.B200 TFIDF.DOCNORM.B200 DOCSCORE.B200 BM25STD.TANH.B200 "
+                                "DISMAX.B200 HAMMING.B200")
 
 
 @pytest.mark.gpu

@@ -358,6 +358,27 @@ def test_proximity_known_answers_of_the_reference():
     assert ol.within_range([enc(300), enc(302)], 1, True) and not ol.within_range([enc(300), enc(303)], 1, True)
 
 
+def test_min_offset_delta_equals_the_reference():
+    """GetSlop of the legacy scorers: the restatement against the reference's own index_result.c, and its doc-comment example."""
+    assert ol.min_offset_delta([[2, 4, 8], [0, 5, 12]]) == 1           # index_result.c:47-50: abs(4-5)
+    assert ol.min_offset_delta([[5]]) == 1 and ol.min_offset_delta([[], []]) == 1 and ol.min_offset_delta([[], [], []]) == 2
+    assert ol.min_offset_delta([[1], [10]]) == 9 and ol.min_offset_delta([[1], [4], [8]]) == 5  # sqrt(9 + 16)
+    if ol.ref_scorers() is None:
+        pytest.skip("oracle/_ref/libscorers_ref.so not built")
+    rng = np.random.default_rng(77)
+    for _ in range(3000):
+        n = int(rng.integers(1, 7))
+        positions, virtual = [], []
+        for _i in range(n):
+            kind = rng.integers(0, 8)
+            cnt = 0 if kind == 0 else int(rng.integers(1, 9))
+            positions.append(np.sort(rng.choice(np.arange(1, 60), size=cnt, replace=False)).tolist())
+            virtual.append(kind == 1)
+        a = ol.min_offset_delta(positions, virtual)
+        b = ol.reference_min_offset_delta(positions, virtual)
+        assert a == b, (positions, virtual, a, b)
+
+
 def ol_varint(v):
     out = (C.c_uint8 * 16)()
     n = ol.postings().orc_varint_encode(v, out)

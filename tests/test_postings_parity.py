@@ -235,13 +235,15 @@ def test_scorers_bit_equal_to_oracle(ps, scorer, is_union):
     ids, scores, fr = rs.fetch()
     exp = ol.run_intersect(idx, union=is_union)
     assert ids.tolist() == [e[0] for e in exp]
-    for i in range(0, len(exp), max(1, len(exp) // 300)):
+    # every 300th hit plus the tail, where the union's children run out one after the other and the reference's active array
+    # (hence the order the leaf scores are summed in) is permuted by swap_remove_child (union_flat.rs:174-180)
+    for i in sorted(set(range(0, len(exp), max(1, len(exp) // 300))) | set(range(max(0, len(exp) - 200), len(exp)))):
         doc, ch = exp[i]
-        if is_union:
-            ch = sorted(ch)  # device sums union children in list order (documented; <= 1e-15 relative)
+        # FreqsOnly lists carry no term positions: GetSlop = children - 1 (1 for a single child), index_result.c:57-60,107
+        slop = len(ch) - 1 if len(ch) > 1 else 1
         s = ol.oracle_score(scorer, [f for _, f in ch], [terms[c][1] for c, _ in ch], [terms[c][2] for c, _ in ch],
                             [terms[c][0] for c, _ in ch], aggw, int(doc_len[doc]), int(max_freq[doc]), float(doc_score[doc]),
-                            n_docs, avg, 1, min_score, float(tanh))
+                            n_docs, avg, slop, min_score, float(tanh))
         if scorer == ol.SCORER_DISMAX and is_union:
             s = aggw * max(terms[c][0] * f for c, f in ch)
         if scorer == ol.SCORER_BM25STD_TANH:
@@ -676,7 +678,8 @@ def test_and_with_not_and_optional_children(ps):
                     assert got_fr[slot][j] == (maps[c][d] if present else 0)
                     if present:
                         fr.append(maps[c][d]); idf.append(terms[c][1]); bidf.append(terms[c][2]); w.append(terms[c][0])
-                s = ol.oracle_score(scorer, fr, idf, bidf, w, 1.25, int(doc_len[d]), 1, 1.0, n_docs, avg)
+                # 4 aggregate children (the virtual ones included), no term positions: GetSlop = 4 - 1 (index_result.c:107)
+                s = ol.oracle_score(scorer, fr, idf, bidf, w, 1.25, int(doc_len[d]), 1, 1.0, n_docs, avg, 3)
                 assert np.float64(s).tobytes() == np.float64(got_sc[j]).tobytes(), (modes, scorer, d)
     # no required child: refused
     arr = (C.c_void_p * 2)(pls[0].h, pls[1].h)
@@ -747,6 +750,120 @@ def test_phrase_intersection_slop_and_order(ps, in_order, n_terms):
     # no constraint at all = the plain intersection
     rs = ps.intersect_phrase(pls, None, False)
     assert rs.fetch()[0].tolist() == [d for d, _ in hits]
+
+
+def _decode_offsets(ob):
+    pos, last, i = [], 0, 0
+    while i < len(ob):
+        b = ob[i]
+        i += 1
+        v = b & 0x7F
+        while b & 0x80:
+            b = ob[i]
+            i += 1
+            v = ((v + 1) << 7) | (b & 0x7F)
+        last += v
+        pos.append(last)
+    return pos
+
+
+@pytest.mark.parametrize("scorer", [ol.SCORER_BM25, ol.SCORER_TFIDF, ol.SCORER_TFIDF_DOCNORM])
+@pytest.mark.parametrize("shape", ["and3", "and5", "or3", "and_not_optional", "phrase"])
+def test_legacy_scorers_divide_by_the_slop_of_the_hit(ps, scorer, shape):
+    """BM25 / TFIDF / TFIDF.DOCNORM divide by GetSlop = IndexResult_MinOffsetDelta (src/index_result/index_result.c:51-108) of the
+    hit.  With term positions on the device the kernel walks them pair by pair like the reference; the expected value is the
+    oracle restatement (pinned on the reference's own compiled index_result.c in test_oracle_postings.py) over the decoded
+    positions of the hit's children in aggregate order.  Scores bit-equal."""
+    n_terms = {"and3": 3, "and5": 5, "or3": 3, "and_not_optional": 4, "phrase": 3}[shape]
+    rng = np.random.default_rng(1200 + scorer * 10 + n_terms + len(shape))
+    n_docs = 40_000
+    density = [0.5, 0.35, 0.6, 0.45, 0.7][:n_terms]
+    if shape == "or3":
+        density = [0.02, 0.03, 0.015]
+    idx, offs = _phrase_corpus(rng, n_docs, n_terms, density, 40)
+    pls = ps.postings_with_offsets([ix.blocks() for ix in idx], ol.CODEC_FULL)
+    doc_len = rng.integers(1, 900, n_docs + 1).astype(np.uint32)
+    doc_score = rng.choice(np.array([1.0, 0.5, 0.77], dtype=np.float32), n_docs + 1)
+    max_freq = rng.integers(1, 60, n_docs + 1).astype(np.uint32)
+    dt = ps.DocTable(n_docs, doc_len, doc_score, max_freq)
+    P = ol.postings()
+    weights = rng.choice([1.0, 0.5, 2.0], n_terms).tolist()
+    terms = [(w, P.orc_idf(n_docs, ix.num_docs()), P.orc_idf_bm25(n_docs, ix.num_docs())) for w, ix in zip(weights, idx)]
+    avg, aggw = 222.5, 0.7
+    freq_of = [dict((d, f) for d, f, _ in ix.read_all()) for ix in idx]
+    if shape == "or3":
+        rs = ps.union(pls)
+        exp = ol.run_intersect(idx, union=True)
+        rows = [(d, [(c, f, False) for c, f in ch]) for d, ch in exp]
+    elif shape == "and_not_optional":
+        modes = [0, 0, 1, 2]  # t0 AND t1 AND NOT t2 AND OPTIONAL t3
+        rs = ps.intersect_ex(pls, modes)
+        order = rs.child_order().tolist()
+        members = [set(freq_of[c]) for c in range(4)]
+        docs = sorted((members[0] & members[1]) - members[2])
+        rows = [(d, [(c, freq_of[c].get(d, 0) if modes[c] != 1 else 0, modes[c] == 1 or (modes[c] == 2 and d not in members[c]))
+                     for c in order]) for d in docs]
+    elif shape == "phrase":
+        rs = ps.intersect_phrase(pls, 4, False)
+        order = rs.child_order().tolist()
+        rows = [(d, [(c, freq_of[c][d], False) for c in order]) for d, _ in ol.run_intersect(idx)
+                if ol.within_range([offs[c][d] for c in order], 4, False)]
+    else:
+        rs = ps.intersect(pls)
+        rows = [(d, [(c, f, False) for c, f in ch]) for d, ch in ol.run_intersect(idx)]
+    rs.score(scorer, terms, aggw, n_docs, avg, dt, 0.0, 4)
+    ids, scores, _ = rs.fetch()
+    assert ids.tolist() == [d for d, _ in rows] and len(rows) > 50
+    slops = set()
+    for i in sorted(set(range(0, len(rows), max(1, len(rows) // 400))) | set(range(max(0, len(rows) - 100), len(rows)))):
+        doc, ch = rows[i]
+        positions = [[] if virt else _decode_offsets(offs[c][doc]) for c, _, virt in ch]
+        slop = ol.min_offset_delta(positions, [virt for _, _, virt in ch])
+        slops.add(slop)
+        real = [(c, f) for c, f, virt in ch if f]
+        s = ol.oracle_score(scorer, [f for _, f in real], [terms[c][1] for c, _ in real], [terms[c][2] for c, _ in real],
+                            [terms[c][0] for c, _ in real], aggw, int(doc_len[doc]), int(max_freq[doc]), float(doc_score[doc]),
+                            n_docs, avg, slop, 0.0, 4.0)
+        assert np.float64(s).tobytes() == np.float64(scores[i]).tobytes(), (shape, scorer, doc, slop, s, scores[i])
+    assert len(slops) >= 3, slops  # the data exercises several different slop values
+
+
+def test_hamming_scorer_matches_the_reference(ps):
+    """HAMMING (src/ext/default.c:475-497): 1 / (bit distance of the payloads + 1), 0 without a payload or with another length;
+    checked against the reference's own default.c when oracle/_ref is built, else against the formula."""
+    rng = np.random.default_rng(4711)
+    n_docs = 30_000
+    ids = [np.unique(rng.integers(1, n_docs, s)).astype(np.uint64) for s in (20_000, 9_000)]
+    pls = [ps.PostingList.from_arrays(x, np.ones(len(x), dtype=np.uint32)) for x in ids]
+    payloads = [None] * (n_docs + 1)
+    for d in range(1, n_docs + 1):
+        r = rng.random()
+        if r < 0.7:
+            payloads[d] = rng.integers(0, 256, 16, dtype=np.uint8).tobytes()
+        elif r < 0.8:
+            payloads[d] = rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8).tobytes()
+    dt = ps.DocTable(n_docs)
+    dt.set_payloads(payloads)
+    rs = ps.intersect(pls)
+    q = rng.integers(0, 256, 16, dtype=np.uint8).tobytes()
+    rs.score_hamming(dt, q)
+    got_ids, got, _ = rs.fetch()
+    assert got_ids.tolist() == np.intersect1d(ids[0], ids[1]).tolist() and len(got_ids) > 1000
+    seen = set()
+    for i, d in enumerate(got_ids.tolist()):
+        p = payloads[d]
+        if not p or len(p) != len(q):
+            exp = 0.0
+        else:
+            bits = int(np.unpackbits(np.frombuffer(p, np.uint8) ^ np.frombuffer(q, np.uint8)).sum())
+            exp = 1.0 / (bits + 1)
+        if ol.ref_scorers() is not None and i % 7 == 0:
+            assert ol.reference_hamming(p, q) == exp
+        assert got[i] == exp, (d, got[i], exp)
+        seen.add(exp == 0.0)
+    assert seen == {True, False}
+    rs.score_hamming(dt, b"")  # an empty query payload never matches (payload length 0 is "no payload")
+    assert not rs.fetch()[1].any()
 
 
 def test_phrase_constructor_takes_slop_and_in_order(ps):

@@ -401,7 +401,11 @@ def test_16bit_fixed_bound_pass_and_its_second_tier():
     p = ol.PortIndex(ol.F16, dim, ol.IP, tier=ol.TIER_AVX512)
     assert g.add_many(rows, label0=1) == n
     p.add_many(rows, 1)
-    uniform_q = ol.synth_rows(ol.F32, 43, 0, nq, dim).astype(np.float16).view(np.uint16)
+    # uniform queries, flipped away from the planted direction where needed: a query that happens to point along `base` sees all
+    # 300 planted rows (3x the norm of the rest) at the top, which rightly overflows the range's list like the cluster queries do
+    uniform_q32 = ol.synth_rows(ol.F32, 43, 0, nq, dim)
+    uniform_q32[(uniform_q32 @ base) > 0] *= -1.0
+    uniform_q = uniform_q32.astype(np.float16).view(np.uint16)
     cluster_q = (base[None, :] + 1e-2 * rng.standard_normal((nq, dim))).astype(np.float16).view(np.uint16)
     for qs, want in ((uniform_q, 1), (cluster_q, 2)):
         qd = torch.from_numpy(qs.view(np.int16)).cuda()
