@@ -94,7 +94,15 @@ typedef enum {
     II_CODEC_FREQS_FIELDS = 2,/* qint3[delta,freq,fieldMask]                     codec/freqs_fields.rs:43 */
     II_CODEC_FIELDS_ONLY = 3, /* qint2[delta,fieldMask]                          codec/fields_only.rs:43 */
     II_CODEC_DOCIDS_ONLY = 4, /* varint(delta)                                   codec/doc_ids_only.rs:33 */
-    II_CODEC_RAW_DOCIDS_ONLY = 5 /* u32 (docId - block.first_doc_id)             codec/raw_doc_ids_only.rs:31-37 */
+    II_CODEC_RAW_DOCIDS_ONLY = 5, /* u32 (docId - block.first_doc_id)            codec/raw_doc_ids_only.rs:31-37 */
+    II_CODEC_FREQS_OFFSETS = 6,   /* qint3[delta,freq,offsetsLen]+offsets            codec/freqs_offsets.rs:32-64 */
+    II_CODEC_OFFSETS_ONLY = 7,    /* qint2[delta,offsetsLen]+offsets (freq 1)        codec/offsets_only.rs:31-62 */
+    II_CODEC_FIELDS_OFFSETS = 8,  /* qint3[delta,fieldMask,offsetsLen]+offsets       codec/fields_offsets.rs:36-84 */
+    /* u128 field masks (more than 32 fields), the mask as a varint after the qint group: */
+    II_CODEC_FULL_WIDE = 9,           /* qint3[delta,freq,offsetsLen]+varint(mask)+offsets   codec/full.rs:197-232 */
+    II_CODEC_FREQS_FIELDS_WIDE = 10,  /* qint2[delta,freq]+varint(mask)                      codec/freqs_fields.rs:114-145 */
+    II_CODEC_FIELDS_ONLY_WIDE = 11,   /* varint(delta)+varint(mask)                          codec/fields_only.rs:109-137 */
+    II_CODEC_FIELDS_OFFSETS_WIDE = 12 /* qint2[delta,offsetsLen]+varint(mask)+offsets        codec/fields_offsets.rs:138-185 */
 } II_Codec;
 
 /* One IndexBlock as the reference exposes it (RS/inverted_index/src/index/core.rs:76-94). */
@@ -115,13 +123,18 @@ typedef struct II_PostingList II_PostingList; /* (docId u32, freq u32) arrays re
  * decode in a kernel (one thread per block). */
 II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nblocks, II_Codec codec,
                                           uint32_t field_mask_filter, int decode_on_device);
+/* The same with a 128-bit field-mask filter {low 64 bits, high 64 bits} for the *Wide codecs (t_fieldMask is u128 on 64-bit
+ * builds of the reference); NULL or all zero = no filter.  A filter with bits above 31 on a 32-bit-mask codec is refused. */
+II_PostingList *II_PostingList_FromBlocksWideMask(const II_BlockView *blocks, size_t nblocks, II_Codec codec, const uint64_t filter128[2],
+                                                  int decode_on_device);
 /* The same for MANY lists in one call (the terms of a batch of queries): one gather of all block bytes and block tables
  * into pinned staging, one H2D copy, one decode launch, one synchronisation; the lists share their device arrays.
  * blocks[i] / nblocks[i] describe list i, out[i] receives its handle (NULL if it could not be built).  Returns the number
  * of lists built. */
 size_t II_PostingList_FromBlocksBatch(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec,
                                       II_PostingList **out);
-/* Same, and the TERM POSITIONS stay on the device (II_CODEC_FULL only; other codecs behave like the call above): the encoded
+/* Same, and the TERM POSITIONS stay on the device (the codecs that store them: FULL, FREQS_OFFSETS, OFFSETS_ONLY, FIELDS_OFFSETS and
+ * the wide variants; other codecs behave like the call above): the encoded
  * block bytes are kept resident and every posting records where its offsets payload (varint position deltas,
  * RS/index_result/src/core/proximity.rs:45-52) sits inside them.  Needed by slop / in-order intersections. */
 size_t II_PostingList_FromBlocksBatchOffsets(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec,

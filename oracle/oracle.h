@@ -89,7 +89,14 @@ enum {
     ORC_CODEC_FREQS_FIELDS,   /* qint3[delta,freq,fieldMask]                        codec/freqs_fields.rs:43 */
     ORC_CODEC_FIELDS_ONLY,    /* qint2[delta,fieldMask]                             codec/fields_only.rs:43 */
     ORC_CODEC_DOCIDS_ONLY,    /* varint(delta)                                      codec/doc_ids_only.rs:33 */
-    ORC_CODEC_RAW_DOCIDS_ONLY /* u32 LE (docId - block.first_doc_id)                codec/raw_doc_ids_only.rs:31-37 */
+    ORC_CODEC_RAW_DOCIDS_ONLY,/* u32 LE (docId - block.first_doc_id)                codec/raw_doc_ids_only.rs:31-37 */
+    ORC_CODEC_FREQS_OFFSETS,  /* qint3[delta,freq,offsetsLen] + offsets             codec/freqs_offsets.rs:32-50 */
+    ORC_CODEC_OFFSETS_ONLY,   /* qint2[delta,offsetsLen] + offsets (freq 1)         codec/offsets_only.rs:31-48 */
+    ORC_CODEC_FIELDS_OFFSETS, /* qint3[delta,fieldMask,offsetsLen] + offsets        codec/fields_offsets.rs:36-60 */
+    ORC_CODEC_FULL_WIDE,      /* qint3[delta,freq,offsetsLen] + varint(mask u128) + offsets   codec/full.rs:197-217 */
+    ORC_CODEC_FREQS_FIELDS_WIDE, /* qint2[delta,freq] + varint(mask u128)           codec/freqs_fields.rs:114-126 */
+    ORC_CODEC_FIELDS_ONLY_WIDE,  /* varint(delta) + varint(mask u128)               codec/fields_only.rs:109-121 */
+    ORC_CODEC_FIELDS_OFFSETS_WIDE /* qint2[delta,offsetsLen] + varint(mask u128) + offsets    codec/fields_offsets.rs:138-160 */
 };
 typedef struct OrcInvIndex OrcInvIndex;
 OrcInvIndex *orc_ii_new(int codec);
@@ -105,6 +112,11 @@ void orc_ii_block(const OrcInvIndex *ii, size_t b, uint64_t *first_id, uint64_t 
 
 typedef struct OrcReader OrcReader; /* IndexReaderCore: next_record / seek_record / skip_to */
 OrcReader *orc_reader_new(const OrcInvIndex *ii, uint32_t field_mask_filter /* 0 = no filter */);
+/* u128 field masks (the *Wide codecs): mask / filter as (lo, hi) 64-bit halves */
+OrcReader *orc_reader_new_wide(const OrcInvIndex *ii, uint64_t filter_lo, uint64_t filter_hi);
+size_t orc_ii_add_wide(OrcInvIndex *ii, uint64_t doc_id, uint32_t freq, uint64_t mask_lo, uint64_t mask_hi, const uint8_t *offsets,
+                       uint32_t offsets_len);
+int orc_reader_next_wide(OrcReader *r, uint64_t *doc_id, uint32_t *freq, uint64_t *mask_lo, uint64_t *mask_hi);
 void orc_reader_free(OrcReader *r);
 void orc_reader_rewind(OrcReader *r);
 /* 1 = record produced, 0 = EOF.  (reader/core.rs:245-277) */

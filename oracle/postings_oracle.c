@@ -8,7 +8,8 @@
  *   qint      src/redisearch_rs/qint/src/lib.rs:149-286            (tests: qint/tests/qint.rs)
  *   varint    src/redisearch_rs/varint/src/lib.rs                   (tests: varint/tests/varint.rs)
  *   codecs    src/redisearch_rs/inverted_index/src/codec/{full,freqs_only,freqs_fields,fields_only,
- *             doc_ids_only,raw_doc_ids_only}.rs                     (tests: tests/integration/codec/)
+ *             doc_ids_only,raw_doc_ids_only,freqs_offsets,offsets_only,fields_offsets}.rs incl. the
+ *             *Wide variants (u128 field masks as varints)            (tests: tests/integration/codec/)
  *   index     src/redisearch_rs/inverted_index/src/index/core.rs:235-358
  *   reader    src/redisearch_rs/inverted_index/src/reader/core.rs:245-345,391-440
  *   leaf      src/redisearch_rs/rqe_iterators/src/inverted_index/core.rs:237-350
@@ -69,6 +70,35 @@ size_t orc_varint_decode(const uint8_t *in, uint64_t *v) {
     size_t pos = 0;
     uint8_t c = in[pos++];
     uint64_t val = c & 0x7f;
+    while (c & 0x80) {
+        val += 1;
+        c = in[pos++];
+        val = (val << 7) | (c & 0x7f);
+    }
+    *v = val;
+    return pos;
+}
+
+/* varint/src/lib.rs impl_encode!(u128, 19): the same scheme over 128 bits (field masks of the *Wide codecs) */
+typedef unsigned __int128 orc_u128;
+static size_t varint_encode_u128(orc_u128 v, uint8_t *out) {
+    uint8_t buf[24];
+    int pos = 23;
+    buf[pos] = (uint8_t)(v & 0x7f);
+    v >>= 7;
+    while (v) {
+        pos--;
+        v -= 1;
+        buf[pos] = (uint8_t)(0x80 | (uint8_t)(v & 0x7f));
+        v >>= 7;
+    }
+    memcpy(out, buf + pos, (size_t)(24 - pos));
+    return (size_t)(24 - pos);
+}
+static size_t varint_decode_u128(const uint8_t *in, orc_u128 *v) {
+    size_t pos = 0;
+    uint8_t c = in[pos++];
+    orc_u128 val = c & 0x7f;
     while (c & 0x80) {
         val += 1;
         c = in[pos++];
@@ -141,6 +171,12 @@ static Block *push_block(OrcInvIndex *ii, uint64_t doc_id) {
 
 size_t orc_ii_add(OrcInvIndex *ii, uint64_t doc_id, uint32_t freq, uint32_t field_mask, const uint8_t *offsets,
                   uint32_t offsets_len) {
+    return orc_ii_add_wide(ii, doc_id, freq, field_mask, 0, offsets, offsets_len);
+}
+size_t orc_ii_add_wide(OrcInvIndex *ii, uint64_t doc_id, uint32_t freq, uint64_t mask_lo, uint64_t mask_hi, const uint8_t *offsets,
+                       uint32_t offsets_len) {
+    const uint32_t field_mask = (uint32_t)mask_lo; /* the narrow codecs take a u32 mask (the reference panics on a wider one) */
+    const orc_u128 wide_mask = ((orc_u128)mask_hi << 64) | mask_lo;
     /* index/core.rs:244-256: none of the codecs here allow duplicates -> a repeated docId is dropped */
     if (ii->nblocks && ii->blocks[ii->nblocks - 1].last_id == doc_id) return 0;
     /* take_block (:339-358) */
@@ -158,7 +194,7 @@ size_t orc_ii_add(OrcInvIndex *ii, uint64_t doc_id, uint32_t freq, uint32_t fiel
     }
     const uint32_t delta = (uint32_t)delta64;
     const size_t before = b->len;
-    block_reserve(b, 32 + offsets_len);
+    block_reserve(b, 64 + offsets_len);
     uint8_t *w = b->buf + b->len;
     size_t nw = 0;
     switch (ii->codec) {
@@ -186,6 +222,53 @@ size_t orc_ii_add(OrcInvIndex *ii, uint64_t doc_id, uint32_t freq, uint32_t fiel
     }
     case ORC_CODEC_DOCIDS_ONLY: nw = orc_varint_encode(delta, w); break;
     case ORC_CODEC_RAW_DOCIDS_ONLY: memcpy(w, &delta, 4); nw = 4; break;
+    case ORC_CODEC_FREQS_OFFSETS: { /* freqs_offsets.rs:32-50 */
+        uint32_t v[3] = {delta, freq, offsets_len};
+        nw = orc_qint_encode(v, 3, w);
+        if (offsets_len) memcpy(w + nw, offsets, offsets_len);
+        nw += offsets_len;
+        break;
+    }
+    case ORC_CODEC_OFFSETS_ONLY: { /* offsets_only.rs:31-48 */
+        uint32_t v[2] = {delta, offsets_len};
+        nw = orc_qint_encode(v, 2, w);
+        if (offsets_len) memcpy(w + nw, offsets, offsets_len);
+        nw += offsets_len;
+        break;
+    }
+    case ORC_CODEC_FIELDS_OFFSETS: { /* fields_offsets.rs:36-60 */
+        uint32_t v[3] = {delta, field_mask, offsets_len};
+        nw = orc_qint_encode(v, 3, w);
+        if (offsets_len) memcpy(w + nw, offsets, offsets_len);
+        nw += offsets_len;
+        break;
+    }
+    case ORC_CODEC_FULL_WIDE: { /* full.rs:197-217 */
+        uint32_t v[3] = {delta, freq, offsets_len};
+        nw = orc_qint_encode(v, 3, w);
+        nw += varint_encode_u128(wide_mask, w + nw);
+        if (offsets_len) memcpy(w + nw, offsets, offsets_len);
+        nw += offsets_len;
+        break;
+    }
+    case ORC_CODEC_FREQS_FIELDS_WIDE: { /* freqs_fields.rs:114-126 */
+        uint32_t v[2] = {delta, freq};
+        nw = orc_qint_encode(v, 2, w);
+        nw += varint_encode_u128(wide_mask, w + nw);
+        break;
+    }
+    case ORC_CODEC_FIELDS_ONLY_WIDE: /* fields_only.rs:109-121: two varints */
+        nw = orc_varint_encode(delta, w);
+        nw += varint_encode_u128(wide_mask, w + nw);
+        break;
+    case ORC_CODEC_FIELDS_OFFSETS_WIDE: { /* fields_offsets.rs:138-160 */
+        uint32_t v[2] = {delta, offsets_len};
+        nw = orc_qint_encode(v, 2, w);
+        nw += varint_encode_u128(wide_mask, w + nw);
+        if (offsets_len) memcpy(w + nw, offsets, offsets_len);
+        nw += offsets_len;
+        break;
+    }
     }
     b->len += nw;
     b->n++;
@@ -197,7 +280,7 @@ size_t orc_ii_add(OrcInvIndex *ii, uint64_t doc_id, uint32_t freq, uint32_t fiel
 /* ------------------------------------------------------------------ reader ------------------ */
 struct OrcReader {
     const OrcInvIndex *ii;
-    uint32_t mask;
+    orc_u128 mask;
     size_t cur_block, buf_pos;
     uint64_t last_doc_id;
     uint16_t entry_in_block;
@@ -210,9 +293,12 @@ static void set_block(OrcReader *r, size_t idx) { /* reader/core.rs:430-440 */
     r->entry_in_block = 0;
 }
 OrcReader *orc_reader_new(const OrcInvIndex *ii, uint32_t field_mask_filter) {
+    return orc_reader_new_wide(ii, field_mask_filter, 0);
+}
+OrcReader *orc_reader_new_wide(const OrcInvIndex *ii, uint64_t filter_lo, uint64_t filter_hi) {
     OrcReader *r = (OrcReader *)calloc(1, sizeof(*r));
     r->ii = ii;
-    r->mask = field_mask_filter;
+    r->mask = ((orc_u128)filter_hi << 64) | filter_lo;
     orc_reader_rewind(r);
     return r;
 }
@@ -226,12 +312,12 @@ void orc_reader_rewind(OrcReader *r) {
 
 /* decode one record at the cursor; base = previous docId (or block first id for raw ids) */
 static void decode_at(const OrcReader *r, const Block *b, size_t *pos, uint64_t base, uint64_t *doc_id, uint32_t *freq,
-                      uint32_t *mask) {
+                      orc_u128 *mask) {
     const uint8_t *in = b->buf + *pos;
     uint32_t v[4];
     uint64_t u;
     *freq = 1;
-    *mask = 0xFFFFFFFFu; /* codecs without a mask match every field (RS_FIELDMASK_ALL) */
+    *mask = ~(orc_u128)0; /* codecs without a mask match every field (RS_FIELDMASK_ALL) */
     switch (r->ii->codec) {
     case ORC_CODEC_FULL:
         *pos += orc_qint_decode(in, 4, v);
@@ -267,10 +353,57 @@ static void decode_at(const OrcReader *r, const Block *b, size_t *pos, uint64_t 
         *doc_id = b->first_id + d;
         break;
     }
+    case ORC_CODEC_FREQS_OFFSETS: /* freqs_offsets.rs:52-64 */
+        *pos += orc_qint_decode(in, 3, v);
+        *doc_id = base + v[0];
+        *freq = v[1];
+        *pos += v[2];
+        break;
+    case ORC_CODEC_OFFSETS_ONLY: /* offsets_only.rs:50-62: freq 1 */
+        *pos += orc_qint_decode(in, 2, v);
+        *doc_id = base + v[0];
+        *pos += v[1];
+        break;
+    case ORC_CODEC_FIELDS_OFFSETS: /* fields_offsets.rs:62-84: freq 1 */
+        *pos += orc_qint_decode(in, 3, v);
+        *doc_id = base + v[0];
+        *mask = v[1];
+        *pos += v[2];
+        break;
+    case ORC_CODEC_FULL_WIDE: { /* full.rs:219-232 */
+        size_t q = orc_qint_decode(in, 3, v);
+        q += varint_decode_u128(in + q, mask);
+        *pos += q + v[2];
+        *doc_id = base + v[0];
+        *freq = v[1];
+        break;
+    }
+    case ORC_CODEC_FREQS_FIELDS_WIDE: { /* freqs_fields.rs:128-145 */
+        size_t q = orc_qint_decode(in, 2, v);
+        q += varint_decode_u128(in + q, mask);
+        *pos += q;
+        *doc_id = base + v[0];
+        *freq = v[1];
+        break;
+    }
+    case ORC_CODEC_FIELDS_ONLY_WIDE: { /* fields_only.rs:123-137 */
+        size_t q = orc_varint_decode(in, &u);
+        q += varint_decode_u128(in + q, mask);
+        *pos += q;
+        *doc_id = base + u;
+        break;
+    }
+    case ORC_CODEC_FIELDS_OFFSETS_WIDE: { /* fields_offsets.rs:162-185: freq 1 */
+        size_t q = orc_qint_decode(in, 2, v);
+        q += varint_decode_u128(in + q, mask);
+        *pos += q + v[1];
+        *doc_id = base + v[0];
+        break;
+    }
     }
 }
 
-static int next_unfiltered(OrcReader *r, uint64_t *doc_id, uint32_t *freq, uint32_t *mask) { /* :245-277 */
+static int next_unfiltered(OrcReader *r, uint64_t *doc_id, uint32_t *freq, orc_u128 *mask) { /* :245-277 */
     const OrcInvIndex *ii = r->ii;
     if (ii->nblocks == 0) return 0;
     if (ii->blocks[r->cur_block].len <= r->buf_pos) {
@@ -284,11 +417,26 @@ static int next_unfiltered(OrcReader *r, uint64_t *doc_id, uint32_t *freq, uint3
     return 1;
 }
 
-int orc_reader_next(OrcReader *r, uint64_t *doc_id, uint32_t *freq, uint32_t *field_mask) {
+static int reader_next128(OrcReader *r, uint64_t *doc_id, uint32_t *freq, orc_u128 *mask) {
     for (;;) {
-        if (!next_unfiltered(r, doc_id, freq, field_mask)) return 0;
-        if (r->mask == 0 || (*field_mask & r->mask)) return 1; /* reader/field_mask.rs */
+        if (!next_unfiltered(r, doc_id, freq, mask)) return 0;
+        if (r->mask == 0 || (*mask & r->mask)) return 1; /* reader/field_mask.rs */
     }
+}
+int orc_reader_next(OrcReader *r, uint64_t *doc_id, uint32_t *freq, uint32_t *field_mask) {
+    orc_u128 m;
+    const int ok = reader_next128(r, doc_id, freq, &m);
+    if (ok) *field_mask = (uint32_t)m;
+    return ok;
+}
+int orc_reader_next_wide(OrcReader *r, uint64_t *doc_id, uint32_t *freq, uint64_t *mask_lo, uint64_t *mask_hi) {
+    orc_u128 m;
+    const int ok = reader_next128(r, doc_id, freq, &m);
+    if (ok) {
+        *mask_lo = (uint64_t)m;
+        *mask_hi = (uint64_t)(m >> 64);
+    }
+    return ok;
 }
 
 static int skip_to_block(OrcReader *r, uint64_t target) { /* :309-345 */
@@ -316,14 +464,16 @@ static int skip_to_block(OrcReader *r, uint64_t target) { /* :309-345 */
 int orc_reader_seek(OrcReader *r, uint64_t target, uint64_t *doc_id, uint32_t *freq, uint32_t *field_mask) {
     if (!skip_to_block(r, target)) return 0; /* :279-306 */
     const Block *b = &r->ii->blocks[r->cur_block];
+    orc_u128 m = 0;
     for (;;) { /* Decoder::seek: decode forward until docId >= target */
         if (b->len <= r->buf_pos) return 0;
-        decode_at(r, b, &r->buf_pos, r->last_doc_id, doc_id, freq, field_mask);
+        decode_at(r, b, &r->buf_pos, r->last_doc_id, doc_id, freq, &m);
         r->entry_in_block++;
         r->last_doc_id = *doc_id;
         if (*doc_id >= target) break;
     }
-    if (r->mask == 0 || (*field_mask & r->mask)) return 1;
+    *field_mask = (uint32_t)m;
+    if (r->mask == 0 || (m & r->mask)) return 1;
     return orc_reader_next(r, doc_id, freq, field_mask); /* filtered reader keeps reading (field_mask.rs) */
 }
 

@@ -2,6 +2,7 @@
 // points, scoring, ranking and the QueryIterator facade.  Contract: include/ii_b200.h.
 #include "../../include/ii_b200.h"
 #include "ii_kernels.h"
+#include "ii_codec.h"
 
 #include <dlfcn.h>
 
@@ -198,82 +199,33 @@ struct II_ResultSet {
 // host decoders (one block at a time; blocks are independent: the delta base restarts at first_doc_id)
 // ------------------------------------------------------------------------------------------------
 namespace {
-inline uint32_t rd(const uint8_t *p, int nb) {
-    uint32_t v = p[0];
-    if (nb > 1) v |= (uint32_t)p[1] << 8;
-    if (nb > 2) v |= (uint32_t)p[2] << 16;
-    if (nb > 3) v |= (uint32_t)p[3] << 24;
-    return v;
-}
-// returns false on a malformed block (cursor ran past the buffer)
-bool decode_block(const II_BlockView &b, II_Codec codec, uint32_t *ids, uint32_t *freqs, uint32_t *masks) {
+// returns false on a malformed block (cursor ran past the buffer).  masks: the 32-bit field mask, or for the *Wide codecs
+// whether the u128 mask meets (wf_lo, wf_hi) — same convention as the device decoder (mask_word in ii_kernels.cu)
+bool decode_block(const II_BlockView &b, II_Codec codec, uint64_t wf_lo, uint64_t wf_hi, uint32_t *ids, uint32_t *freqs, uint32_t *masks) {
     const uint8_t *p = b.data, *end = b.data + b.len;
     uint64_t last = b.first_doc_id;
     for (uint32_t e = 0; e < b.num_entries; e++) {
-        uint32_t freq = 1, mask = 0xFFFFFFFFu;
-        uint64_t id;
         if (p >= end) return false;
-        switch (codec) {
-        case II_CODEC_RAW_DOCIDS_ONLY:
-            if (p + 4 > end) return false;
-            id = b.first_doc_id + rd(p, 4);
-            p += 4;
-            break;
-        case II_CODEC_DOCIDS_ONLY: {
-            uint8_t c = *p++;
-            uint64_t val = c & 0x7f;
-            while (c & 0x80) {
-                if (p >= end) return false;
-                val += 1;
-                c = *p++;
-                val = (val << 7) | (c & 0x7f);
-            }
-            id = last + val;
-            break;
-        }
-        default: {
-            const uint8_t lead = *p++;
-            const int nvals = (codec == II_CODEC_FULL) ? 4 : (codec == II_CODEC_FREQS_FIELDS) ? 3 : 2;
-            uint32_t v[4] = {0, 0, 0, 0};
-            for (int i = 0; i < nvals; i++) {
-                const int nb = ((lead >> (2 * i)) & 3) + 1;
-                if (p + nb > end) return false;
-                v[i] = rd(p, nb);
-                p += nb;
-            }
-            id = last + v[0];
-            if (codec == II_CODEC_FULL) {
-                freq = v[1];
-                mask = v[2];
-                if (p + v[3] > end) return false;
-                p += v[3];
-            } else if (codec == II_CODEC_FREQS_ONLY) {
-                freq = v[1];
-            } else if (codec == II_CODEC_FREQS_FIELDS) {
-                freq = v[1];
-                mask = v[2];
-            } else {
-                mask = v[1];
-            }
-        }
-        }
+        IIRecord r;
+        p = ii_decode_record<true>(p, end, (int)codec, r);
+        if (!p) return false;
+        const uint64_t id = (codec == II_CODEC_RAW_DOCIDS_ONLY ? b.first_doc_id : last) + r.delta;
         if (id > 0xFFFFFFFEull) return false;
         last = id;
         ids[e] = (uint32_t)id;
-        freqs[e] = freq;
-        if (masks) masks[e] = mask;
+        freqs[e] = r.freq;
+        if (masks)
+            masks[e] = ii_codec_is_wide((int)codec) ? (((r.mask_lo & wf_lo) | (r.mask_hi & wf_hi)) != 0 ? 1u : 0u) : (uint32_t)r.mask_lo;
     }
     return true;
 }
 } // namespace
 
-// Decode MANY posting lists in one go: ONE gather of all block bytes + block tables into pinned staging, ONE H2D copy,
-// ONE decode launch (decode_blocks_staged_kernel), ONE synchronisation.  The lists share two device arrays (ids, freqs).
-// keep_offsets (Full codec): the encoded bytes stay resident and every posting records where its term positions are.
 static size_t from_blocks_batch(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec, bool keep_offsets,
                                 II_PostingList **out) {
-    keep_offsets = keep_offsets && codec == II_CODEC_FULL;
     for (size_t i = 0; i < n_lists; i++) out[i] = nullptr;
+    if ((int)codec < 0 || (int)codec >= kNumCodecs) return 0;
+    keep_offsets = keep_offsets && ii_codec_has_offsets((int)codec);
     if (n_lists == 0) return 0;
     Ctx &c = ctx();
     std::lock_guard<std::mutex> g(c.mu);
@@ -418,6 +370,17 @@ int II_PostingList_HasOffsets(const II_PostingList *pl) { return pl->d_off_len !
 
 II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nblocks, II_Codec codec,
                                           uint32_t field_mask_filter, int decode_on_device) {
+    const uint64_t wide[2] = {field_mask_filter, 0};
+    return II_PostingList_FromBlocksWideMask(blocks, nblocks, codec, wide, decode_on_device);
+}
+II_PostingList *II_PostingList_FromBlocksWideMask(const II_BlockView *blocks, size_t nblocks, II_Codec codec, const uint64_t filter128[2],
+                                                  int decode_on_device) {
+    if ((int)codec < 0 || (int)codec >= kNumCodecs) return nullptr;
+    const uint64_t wf_lo = filter128 ? filter128[0] : 0, wf_hi = filter128 ? filter128[1] : 0;
+    const bool wide = ii_codec_is_wide((int)codec);
+    if (!wide && (wf_hi != 0 || wf_lo > 0xFFFFFFFFull)) return nullptr; // a 32-bit mask codec cannot meet bits above 31: ask the wide codec
+    // what the ordered compaction tests: the 32-bit mask itself, or the decoder's "meets the u128 filter" flag
+    const uint32_t field_mask_filter = wide ? ((wf_lo | wf_hi) ? 1u : 0u) : (uint32_t)wf_lo;
     if (decode_on_device && field_mask_filter == 0) { // the common case rides the batch decoder (one copy, one launch, one sync)
         II_PostingList *one = nullptr;
         const II_BlockView *bl[1] = {blocks};
@@ -438,8 +401,7 @@ II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nbl
     const size_t n = entry_off[nblocks];
     auto *pl = new II_PostingList();
     pl->estimated = n;
-    const bool need_mask = field_mask_filter != 0 &&
-                           (codec == II_CODEC_FULL || codec == II_CODEC_FREQS_FIELDS || codec == II_CODEC_FIELDS_ONLY);
+    const bool need_mask = field_mask_filter != 0 && ii_codec_has_mask((int)codec);
     uint32_t *d_ids = dalloc<uint32_t>(n), *d_freqs = dalloc<uint32_t>(n), *d_masks = need_mask ? dalloc<uint32_t>(n) : nullptr;
     bool ok = d_ids && d_freqs && (!need_mask || d_masks);
     if (ok && n) {
@@ -480,7 +442,7 @@ II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nbl
             ok = ok && cudaMemcpyAsync(d_boff, byte_off.data(), (nblocks + 1) * 8, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
             ok = ok && cudaMemcpyAsync(d_first, first, nblocks * 8, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
             ok = ok && cudaMemcpyAsync(d_eoff, entry_off.data(), (nblocks + 1) * 4, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
-            ok = ok && ii_launch_decode(d_bytes, d_boff, d_first, d_eoff, (uint32_t)nblocks, (int)codec, d_ids, d_freqs, d_masks,
+            ok = ok && ii_launch_decode(d_bytes, d_boff, d_first, d_eoff, (uint32_t)nblocks, (int)codec, wf_lo, wf_hi, d_ids, d_freqs, d_masks,
                                         c.stream) == cudaSuccess;
             ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
             c.stats.h2d_us = now_us() - t0;
@@ -501,7 +463,7 @@ II_PostingList *II_PostingList_FromBlocks(const II_BlockView *blocks, size_t nbl
                 for (unsigned t = 0; t < nt; t++)
                     th.emplace_back([&, t] {
                         for (size_t b = t; b < nblocks; b += nt)
-                            if (!decode_block(blocks[b], codec, h_ids + entry_off[b], h_freqs + entry_off[b],
+                            if (!decode_block(blocks[b], codec, wf_lo, wf_hi, h_ids + entry_off[b], h_freqs + entry_off[b],
                                               h_masks ? h_masks + entry_off[b] : nullptr))
                                 good[t] = 0;
                     });
@@ -1344,7 +1306,7 @@ struct FusedScratch { // grow-only, owned by the batch entry point (serialised b
             q_cap = 0;
             const size_t cap = std::max<size_t>(nq, 1024);
             if (cudaMallocHost(&h_q, cap * sizeof(FusedQuery)) != cudaSuccess || cudaMalloc(&d_q, cap * sizeof(FusedQuery)) != cudaSuccess ||
-                cudaMalloc(&d_hits, cap * 4) != cudaSuccess || cudaMallocHost(&h_hits, cap * 4) != cudaSuccess)
+                cudaMalloc(&d_hits, cap * 8) != cudaSuccess /* survivors + candidate fill */ || cudaMallocHost(&h_hits, cap * 4) != cudaSuccess)
                 return false;
             q_cap = cap;
         }

@@ -16,6 +16,7 @@
 // (RS/inverted_index/src/reader/core.rs:245-277, codec/*.rs), the default scorers
 // (src/ext/default.c:68-461) and RPSorter's ranking (src/result_processor.c:752-850).
 #include "ii_kernels.h"
+#include "ii_codec.h"
 #include "topk_common.cuh"
 
 #include <algorithm>
@@ -23,19 +24,18 @@
 namespace rsb200 {
 
 // ------------------------------------------------------------------------------------------------
-// device decode: one thread per IndexBlock
+// device decode: one thread per IndexBlock; the record layouts live in ii_codec.h (shared with the host decoder)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t qint_value(const uint8_t *p, int bytes) {
-    uint32_t v = p[0];
-    if (bytes > 1) v |= (uint32_t)p[1] << 8;
-    if (bytes > 2) v |= (uint32_t)p[2] << 16;
-    if (bytes > 3) v |= (uint32_t)p[3] << 24;
-    return v;
+// What lands in out_masks: the record's 32-bit field mask, or — for the u128 masks of the *Wide codecs — whether it meets the
+// 128-bit filter (1 / 0), so that the ordered compaction downstream stays a 32-bit `mask & filter` test (filter 1).
+__device__ __forceinline__ uint32_t mask_word(const IIRecord &r, int codec, uint64_t wf_lo, uint64_t wf_hi) {
+    if (!ii_codec_is_wide(codec)) return (uint32_t)r.mask_lo;
+    return ((r.mask_lo & wf_lo) | (r.mask_hi & wf_hi)) != 0 ? 1u : 0u;
 }
 
 __global__ void decode_blocks_kernel(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ byte_off,
                                      const uint64_t *__restrict__ first_id, const uint32_t *__restrict__ entry_off,
-                                     uint32_t nblocks, int codec, uint32_t *__restrict__ out_ids,
+                                     uint32_t nblocks, int codec, uint64_t wf_lo, uint64_t wf_hi, uint32_t *__restrict__ out_ids,
                                      uint32_t *__restrict__ out_freqs, uint32_t *__restrict__ out_masks) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
@@ -45,47 +45,13 @@ __global__ void decode_blocks_kernel(const uint8_t *__restrict__ bytes, const ui
     const uint64_t base0 = first_id[b];
     uint64_t last = base0; // reader resets the delta base to first_doc_id on block entry (reader/core.rs:430-440)
     for (uint32_t e = 0; e < n; e++, o++) {
-        uint32_t freq = 1, mask = 0xFFFFFFFFu;
-        uint64_t id;
-        if (codec == 5) { // raw doc ids: u32 delta from the block's first id
-            id = base0 + qint_value(p, 4);
-            p += 4;
-        } else if (codec == 4) { // varint delta (RS/varint/src/lib.rs read_as_varint)
-            uint8_t c = *p++;
-            uint64_t val = c & 0x7f;
-            while (c & 0x80) {
-                val += 1;
-                c = *p++;
-                val = (val << 7) | (c & 0x7f);
-            }
-            id = last + val;
-        } else {
-            const uint8_t lead = *p++;
-            const int nvals = (codec == 0) ? 4 : (codec == 2) ? 3 : 2;
-            uint32_t v[4] = {0, 0, 0, 0};
-            for (int i = 0; i < nvals; i++) {
-                const int nb = ((lead >> (2 * i)) & 3) + 1;
-                v[i] = qint_value(p, nb);
-                p += nb;
-            }
-            id = last + v[0];
-            if (codec == 0) { // Full: delta, freq, fieldMask, offsetsLen + offsets bytes
-                freq = v[1];
-                mask = v[2];
-                p += v[3];
-            } else if (codec == 1) { // FreqsOnly
-                freq = v[1];
-            } else if (codec == 2) { // FreqsFields
-                freq = v[1];
-                mask = v[2];
-            } else { // FieldsOnly
-                mask = v[1];
-            }
-        }
+        IIRecord r;
+        p = ii_decode_record<false>(p, nullptr, codec, r);
+        const uint64_t id = (codec == 5 ? base0 : last) + r.delta; // raw doc ids: delta from the block's first id
         last = id;
         out_ids[o] = (uint32_t)id;
-        out_freqs[o] = freq;
-        if (out_masks) out_masks[o] = mask;
+        out_freqs[o] = r.freq;
+        if (out_masks) out_masks[o] = mask_word(r, codec, wf_lo, wf_hi);
     }
 }
 
@@ -125,53 +91,17 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_blocks_staged_kernel(co
     const uint32_t base0 = first_id[b];
     uint32_t last = base0; // the reader resets the delta base to first_doc_id on block entry (reader/core.rs:430-440)
     for (uint32_t e = 0; e < n; e++, o++) {
-        uint32_t freq = 1, mask = 0xFFFFFFFFu, id;
-        if (codec == 5) { // raw doc ids: u32 delta from the block's first id
-            id = base0 + qint_value(p, 4);
-            p += 4;
-        } else if (codec == 4) { // varint delta (RS/varint/src/lib.rs read_as_varint)
-            uint8_t c = *p++;
-            uint32_t val = c & 0x7f;
-            while (c & 0x80) {
-                val += 1;
-                c = *p++;
-                val = (val << 7) | (c & 0x7f);
-            }
-            id = last + val;
-        } else {
-            const uint8_t lead = *p++;
-            const int nvals = (codec == 0) ? 4 : (codec == 2) ? 3 : 2;
-            uint32_t v[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (i < nvals) {
-                    const int nb = ((lead >> (2 * i)) & 3) + 1;
-                    v[i] = qint_value(p, nb);
-                    p += nb;
-                }
-            }
-            id = last + v[0];
-            if (codec == 0) { // Full: delta, freq, fieldMask, offsetsLen + offsets bytes
-                freq = v[1];
-                mask = v[2];
-                if (out_off_pos) { // the term's position bytes stay where they are, in the gathered stream kept on the device
-                    out_off_pos[o] = stream0 + (uint32_t)(p - p0);
-                    out_off_len[o] = v[3];
-                }
-                p += v[3];
-            } else if (codec == 1) { // FreqsOnly
-                freq = v[1];
-            } else if (codec == 2) { // FreqsFields
-                freq = v[1];
-                mask = v[2];
-            } else { // FieldsOnly
-                mask = v[1];
-            }
+        IIRecord r;
+        p = ii_decode_record<false>(p, nullptr, codec, r);
+        const uint32_t id = (codec == 5 ? base0 : last) + (uint32_t)r.delta;
+        if (out_off_pos) { // the term's position bytes stay where they are, in the gathered stream kept on the device
+            out_off_pos[o] = stream0 + (uint32_t)(r.offsets - p0);
+            out_off_len[o] = r.off_len;
         }
         last = id;
         out_ids[o] = id;
-        out_freqs[o] = freq;
-        if (out_masks) out_masks[o] = mask;
+        out_freqs[o] = r.freq;
+        if (out_masks) out_masks[o] = (uint32_t)r.mask_lo;
     }
 }
 
@@ -773,8 +703,9 @@ __global__ void __launch_bounds__(256) fused_window_kernel(const FusedQuery *__r
 __global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQuery *__restrict__ queries, const uint32_t *__restrict__ item_q,
                                                                const uint2 *__restrict__ win, const FusedCommon fc, uint32_t top_n,
                                                                uint64_t *__restrict__ cand_keys, uint32_t *__restrict__ cand_ids,
-                                                               uint32_t *__restrict__ hits) {
+                                                               uint32_t *__restrict__ hits, uint32_t *__restrict__ cand_fill) {
     __shared__ uint32_t sB[kIISmemElems];
+    __shared__ uint32_t s_base;
     __shared__ uint64_t s_keys[kIIChunk];
     __shared__ uint32_t s_ids[kIIChunk];
     __shared__ uint32_t s_warp[kIIThreads / 32];
@@ -853,14 +784,65 @@ __global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQue
                     }
                 }
             } else {
+                // a window far longer than the chunk (a rare term against a frequent one): kPivots evenly spaced entries of the
+                // window go to shared memory, every entry first finds its bucket there (no HBM latency), then finishes inside
+                // the bucket with its searches advancing in lockstep (one round trip per step for all of a thread's entries
+                // instead of one per entry per step: ncu showed this path at ~17-23 dependent loads x 4 entries per thread)
+                constexpr uint32_t kPivots = 2048;
+                const uint32_t step = (range + kPivots - 1) / kPivots; // bucket b = [lo + b*step, lo + (b+1)*step)
+                const uint32_t nbuckets = (range + step - 1) / step;
+                for (uint32_t t = threadIdx.x; t < nbuckets; t += kIIThreads) sB[t] = B[lo + t * step]; // first entry of bucket t
+                __syncthreads();
+                uint32_t l[kIIItems], h[kIIItems];
 #pragma unroll
                 for (int i = 0; i < kIIItems; i++) {
+                    l[i] = h[i] = 0;
                     if (alive[i]) {
-                        const uint32_t p = lower_bound_u32(B, lo, hi, doc[i]);
-                        alive[i] = (p < hi) && B[p] == doc[i];
-                        pos[j - 1][i] = p;
+                        // last bucket whose first entry is <= doc: upper_bound - 1; the bucket before the first one cannot match
+                        uint32_t a = 0, b = nbuckets;
+                        while (a < b) {
+                            const uint32_t mid = a + ((b - a) >> 1);
+                            if (sB[mid] <= doc[i])
+                                a = mid + 1;
+                            else
+                                b = mid;
+                        }
+                        if (a == 0) {
+                            alive[i] = false; // below the window's first entry
+                        } else {
+                            l[i] = lo + (a - 1) * step;
+                            h[i] = min(l[i] + step, hi);
+                        }
                     }
                 }
+                bool more = true;
+                while (more) {
+                    uint32_t mid[kIIItems], v[kIIItems];
+#pragma unroll
+                    for (int i = 0; i < kIIItems; i++) {
+                        mid[i] = l[i] + ((h[i] - l[i]) >> 1);
+                        v[i] = (alive[i] && l[i] < h[i]) ? B[mid[i]] : 0u;
+                    }
+                    more = false;
+#pragma unroll
+                    for (int i = 0; i < kIIItems; i++)
+                        if (alive[i] && l[i] < h[i]) {
+                            if (v[i] < doc[i])
+                                l[i] = mid[i] + 1;
+                            else
+                                h[i] = mid[i];
+                            more |= l[i] < h[i];
+                        }
+                }
+                uint32_t fv[kIIItems];
+#pragma unroll
+                for (int i = 0; i < kIIItems; i++) fv[i] = (alive[i] && l[i] < hi) ? B[l[i]] : 0xFFFFFFFFu;
+#pragma unroll
+                for (int i = 0; i < kIIItems; i++)
+                    if (alive[i]) {
+                        alive[i] = l[i] < hi && fv[i] == doc[i];
+                        pos[j - 1][i] = l[i];
+                    }
             }
             bool any = false;
 #pragma unroll
@@ -914,54 +896,51 @@ __global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQue
         for (uint32_t t = total + threadIdx.x; t < nsort; t += kIIThreads) s_keys[t] = 0xFFFFFFFFFFFFFFFFull, s_ids[t] = 0xFFFFFFFFu;
         bitonic_sort_pairs(s_keys, s_ids, nsort); // entry syncs inside
     }
-    for (uint32_t t = threadIdx.x; t < top_n; t += kIIThreads) {
-        const bool v = t < total;
-        cand_keys[(size_t)item * top_n + t] = v ? s_keys[t] : 0xFFFFFFFFFFFFFFFFull;
-        cand_ids[(size_t)item * top_n + t] = v ? s_ids[t] : 0xFFFFFFFFu;
+    // the CTA's candidates go behind those of the query's other items: a compact list per query (at most top_n per item, so the
+    // query's nchunks * top_n slots always suffice); their order is whatever the atomics make it, the per-query pass sorts
+    const uint32_t keep = min(total, top_n);
+    if (threadIdx.x == 0 && total) {
+        s_base = atomicAdd(&cand_fill[q], keep);
+        atomicAdd(&hits[q], total);
     }
-    if (threadIdx.x == 0 && total) atomicAdd(&hits[q], total);
+    __syncthreads();
+    const size_t qbase = (size_t)Q.item0 * top_n + s_base;
+    for (uint32_t t = threadIdx.x; t < keep; t += kIIThreads) {
+        cand_keys[qbase + t] = s_keys[t];
+        cand_ids[qbase + t] = s_ids[t];
+    }
 }
 
-// one CTA per query: best top_n of its items' candidate lists (each ascending, ~0-padded)
+// one CTA per query: best top_n of the query's compact candidate list (cand_fill[q] entries at item0 * top_n)
 __global__ void __launch_bounds__(256) fused_topn_kernel(const FusedQuery *__restrict__ queries, uint32_t top_n,
                                                          const uint64_t *__restrict__ cand_keys, const uint32_t *__restrict__ cand_ids,
-                                                         uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_ids) {
+                                                         const uint32_t *__restrict__ cand_fill, uint64_t *__restrict__ out_keys,
+                                                         uint32_t *__restrict__ out_ids) {
     constexpr uint32_t kTile = 1024;
     __shared__ uint64_t s_keys[2 * kTile];
     __shared__ uint32_t s_ids[2 * kTile];
-    __shared__ uint32_t s_fill;
     const FusedQuery &Q = queries[blockIdx.x];
-    const size_t base = (size_t)Q.item0 * top_n, total = (size_t)Q.nchunks * top_n;
+    const size_t base = (size_t)Q.item0 * top_n;
+    const uint32_t total = cand_fill[blockIdx.x];
     // running best in [0, top_n); the next tile is appended behind it, the buffer sorted, the head kept
-    for (uint32_t t = threadIdx.x; t < 2 * kTile; t += blockDim.x) s_keys[t] = 0xFFFFFFFFFFFFFFFFull, s_ids[t] = 0xFFFFFFFFu;
-    if (threadIdx.x == 0) s_fill = top_n;
-    __syncthreads();
-    // the fill level is tracked in registers (block-uniform, from the barrier's own count): reading s_fill for the fold decision
-    // would race with the next round's atomicAdd of a faster warp and could split the CTA across the barriers below
-    uint32_t fill = top_n;
-    for (size_t off = 0; off < total; off += blockDim.x) {
-        const size_t i = off + threadIdx.x;
-        const uint64_t k = i < total ? cand_keys[base + i] : 0xFFFFFFFFFFFFFFFFull;
-        const bool real = k != 0xFFFFFFFFFFFFFFFFull || (i < total && cand_ids[base + i] != 0xFFFFFFFFu);
-        const uint32_t m = __ballot_sync(0xffffffffu, real);
-        uint32_t wbase = 0;
-        if ((threadIdx.x & 31) == 0 && m) wbase = atomicAdd(&s_fill, (uint32_t)__popc(m));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (real) {
-            const uint32_t p = wbase + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
-            s_keys[p] = k;
-            s_ids[p] = cand_ids[base + i];
+    for (uint32_t t = threadIdx.x; t < top_n; t += blockDim.x) s_keys[t] = 0xFFFFFFFFFFFFFFFFull, s_ids[t] = 0xFFFFFFFFu;
+    uint32_t fill = top_n; // block-uniform
+    for (uint32_t off = 0; off < total; off += blockDim.x) {
+        const uint32_t i = off + threadIdx.x;
+        if (i < total) {
+            s_keys[fill + threadIdx.x] = cand_keys[base + i];
+            s_ids[fill + threadIdx.x] = cand_ids[base + i];
         }
-        fill += (uint32_t)__syncthreads_count(real);
+        fill += min((uint32_t)blockDim.x, total - off);
         if (fill + blockDim.x > 2 * kTile || off + blockDim.x >= total) { // buffer (nearly) full, or last round: fold
             const uint32_t nsort = max(32u, next_pow2(fill));
-            for (uint32_t t = fill + threadIdx.x; t < nsort; t += blockDim.x) s_keys[t] = 0xFFFFFFFFFFFFFFFFull, s_ids[t] = 0xFFFFFFFFu;
-            bitonic_sort_pairs(s_keys, s_ids, nsort);
-            if (threadIdx.x == 0) s_fill = top_n;
-            fill = top_n;
             __syncthreads();
+            for (uint32_t t = fill + threadIdx.x; t < nsort; t += blockDim.x) s_keys[t] = 0xFFFFFFFFFFFFFFFFull, s_ids[t] = 0xFFFFFFFFu;
+            bitonic_sort_pairs(s_keys, s_ids, nsort); // entry syncs inside, one at the end
+            fill = top_n;
         }
     }
+    __syncthreads();
     for (uint32_t t = threadIdx.x; t < top_n; t += blockDim.x) {
         out_keys[(size_t)blockIdx.x * top_n + t] = s_keys[t];
         out_ids[(size_t)blockIdx.x * top_n + t] = s_ids[t];
@@ -973,17 +952,18 @@ cudaError_t ii_launch_fused_search(const FusedQuery *d_queries, uint32_t nq, uin
                                    uint32_t *d_hits, uint64_t *d_out_keys, uint32_t *d_out_ids, cudaStream_t s) {
     if (nq == 0 || top_n == 0 || top_n > (uint32_t)kFusedMaxTopN || max_children == 0 || max_children > (uint32_t)kFusedMaxLists)
         return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemsetAsync(d_hits, 0, (size_t)nq * 4, s);
+    cudaError_t e = cudaMemsetAsync(d_hits, 0, (size_t)nq * 8, s); // [nq] survivors per query, then [nq] candidate fill levels
     if (e != cudaSuccess) return e;
+    uint32_t *d_fill = d_hits + nq;
     if (total_items) {
         fused_itemq_kernel<<<nq, 128, 0, s>>>(d_queries, nq, d_item_q);
         if (max_children > 1) {
             const uint64_t searches = (uint64_t)total_items * (max_children - 1);
             fused_window_kernel<<<(uint32_t)((searches + 255) / 256), 256, 0, s>>>(d_queries, d_item_q, total_items, max_children - 1, d_win);
         }
-        fused_and_kernel<<<total_items, kIIThreads, 0, s>>>(d_queries, d_item_q, d_win, fc, top_n, d_cand_keys, d_cand_ids, d_hits);
+        fused_and_kernel<<<total_items, kIIThreads, 0, s>>>(d_queries, d_item_q, d_win, fc, top_n, d_cand_keys, d_cand_ids, d_hits, d_fill);
     }
-    fused_topn_kernel<<<nq, 256, 0, s>>>(d_queries, top_n, d_cand_keys, d_cand_ids, d_out_keys, d_out_ids);
+    fused_topn_kernel<<<nq, 256, 0, s>>>(d_queries, top_n, d_cand_keys, d_cand_ids, d_fill, d_out_keys, d_out_ids);
     return cudaGetLastError();
 }
 
@@ -1233,11 +1213,11 @@ static inline uint32_t grid_for(size_t n, uint32_t threads, uint32_t cap) {
 }
 
 cudaError_t ii_launch_decode(const uint8_t *d_bytes, const uint64_t *d_byte_off, const uint64_t *d_first_id,
-                             const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint32_t *d_ids, uint32_t *d_freqs,
-                             uint32_t *d_masks, cudaStream_t s) {
+                             const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint64_t wide_filter_lo, uint64_t wide_filter_hi,
+                             uint32_t *d_ids, uint32_t *d_freqs, uint32_t *d_masks, cudaStream_t s) {
     if (!nblocks) return cudaSuccess;
-    decode_blocks_kernel<<<(nblocks + 127) / 128, 128, 0, s>>>(d_bytes, d_byte_off, d_first_id, d_entry_off, nblocks, codec,
-                                                              d_ids, d_freqs, d_masks);
+    decode_blocks_kernel<<<(nblocks + 127) / 128, 128, 0, s>>>(d_bytes, d_byte_off, d_first_id, d_entry_off, nblocks, codec, wide_filter_lo,
+                                                              wide_filter_hi, d_ids, d_freqs, d_masks);
     return cudaGetLastError();
 }
 cudaError_t ii_launch_decode_staged(const uint8_t *d_bytes, const uint32_t *d_byte_off, const uint32_t *d_first_id,

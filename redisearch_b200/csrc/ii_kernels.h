@@ -125,14 +125,15 @@ struct FusedCommon {
 // item's docIds; (3) one CTA per work item — every window staged in shared memory at once (list by list when they do not fit),
 // membership, freqs of the matches, the scorer, and the CTA's best `top_n` hits into cand_keys / cand_ids [item][top_n] (padded
 // with ~0); hits[q] += survivors; (4) one CTA per query selects the best top_n by (score desc, docId asc) over its items'
-// candidates into out_keys / out_ids [nq][top_n].  d_item_q: [total_items]; d_win: [total_items][kFusedMaxLists - 1].
+// candidates into out_keys / out_ids [nq][top_n].  d_item_q: [total_items]; d_win: [total_items][kFusedMaxLists - 1];
+// d_hits: [2 * nq] (survivors per query, then the fill level of each query's compact candidate list).
 cudaError_t ii_launch_fused_search(const FusedQuery *d_queries, uint32_t nq, uint32_t total_items, uint32_t max_children, const FusedCommon &fc,
                                    uint32_t top_n, uint32_t *d_item_q, uint2 *d_win, uint64_t *d_cand_keys, uint32_t *d_cand_ids,
                                    uint32_t *d_hits, uint64_t *d_out_keys, uint32_t *d_out_ids, cudaStream_t s);
 
 cudaError_t ii_launch_decode(const uint8_t *d_bytes, const uint64_t *d_byte_off, const uint64_t *d_first_id,
-                             const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint32_t *d_ids, uint32_t *d_freqs,
-                             uint32_t *d_masks, cudaStream_t s);
+                             const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint64_t wide_filter_lo, uint64_t wide_filter_hi,
+                             uint32_t *d_ids, uint32_t *d_freqs, uint32_t *d_masks, cudaStream_t s);
 // batch decode: 32-bit tables (byte_off[nblocks+1] into the 16-byte-aligned, 16-byte-padded gathered stream, first_id[nblocks],
 // entry_off[nblocks+1] into the output arrays), blocks of MANY lists back to back
 cudaError_t ii_launch_decode_staged(const uint8_t *d_bytes, const uint32_t *d_byte_off, const uint32_t *d_first_id,

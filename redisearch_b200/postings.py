@@ -91,6 +91,7 @@ SIGNATURES = [
     ("II_MergeShardTopN", _SZ, [_P, _P, _P, _SZ, _SZ, _SZ, _P, _P]),
     ("II_NewResultIterator", _QI, [_P, C.c_double]),
     ("II_IntersectEx", _P, [_P, _P, _SZ]),
+    ("II_PostingList_FromBlocksWideMask", _P, [_P, _SZ, C.c_int, _P, C.c_int]),
     ("II_IntersectPhrase", _P, [_P, _P, _SZ, C.c_int32, C.c_int]),
     ("NewIntersectionIterator", _QI, [_P, _SZ, C.c_int32, C.c_bool, C.c_double]),
     ("NewUnionIterator", _QI, [_P, C.c_int32, C.c_bool, C.c_double, C.c_int, C.c_char_p, _P]),
@@ -153,6 +154,9 @@ class PostingList:
             buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
             keep.append(buf)
             arr[i] = II_BlockView(first, last, n, C.cast(buf, C.POINTER(C.c_uint8)), len(data))
+        if field_mask_filter >> 32:  # a u128 field-mask filter (the *Wide codecs)
+            flt = (C.c_uint64 * 2)(field_mask_filter & 0xFFFFFFFFFFFFFFFF, field_mask_filter >> 64)
+            return cls(lib().II_PostingList_FromBlocksWideMask(arr, len(blocks), codec, flt, int(on_device)))
         return cls(lib().II_PostingList_FromBlocks(arr, len(blocks), codec, field_mask_filter, int(on_device)))
 
     def __len__(self):

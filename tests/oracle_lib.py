@@ -319,7 +319,15 @@ def to_type(x32: np.ndarray, vtype: int) -> np.ndarray:
 # ---------------------------------------------------------------------------------------------
 # postings / scorers (oracle/postings_oracle.c, scorer_oracle.c, oracle/_ref/libscorers_ref.so)
 # ---------------------------------------------------------------------------------------------
-CODEC_FULL, CODEC_FREQS_ONLY, CODEC_FREQS_FIELDS, CODEC_FIELDS_ONLY, CODEC_DOCIDS_ONLY, CODEC_RAW_DOCIDS_ONLY = range(6)
+(CODEC_FULL, CODEC_FREQS_ONLY, CODEC_FREQS_FIELDS, CODEC_FIELDS_ONLY, CODEC_DOCIDS_ONLY, CODEC_RAW_DOCIDS_ONLY, CODEC_FREQS_OFFSETS,
+ CODEC_OFFSETS_ONLY, CODEC_FIELDS_OFFSETS, CODEC_FULL_WIDE, CODEC_FREQS_FIELDS_WIDE, CODEC_FIELDS_ONLY_WIDE,
+ CODEC_FIELDS_OFFSETS_WIDE) = range(13)
+N_CODECS = 13
+CODECS_WITH_OFFSETS = (CODEC_FULL, CODEC_FREQS_OFFSETS, CODEC_OFFSETS_ONLY, CODEC_FIELDS_OFFSETS, CODEC_FULL_WIDE, CODEC_FIELDS_OFFSETS_WIDE)
+CODECS_WITH_MASK = (CODEC_FULL, CODEC_FREQS_FIELDS, CODEC_FIELDS_ONLY, CODEC_FIELDS_OFFSETS, CODEC_FULL_WIDE, CODEC_FREQS_FIELDS_WIDE,
+                    CODEC_FIELDS_ONLY_WIDE, CODEC_FIELDS_OFFSETS_WIDE)
+CODECS_WIDE = (CODEC_FULL_WIDE, CODEC_FREQS_FIELDS_WIDE, CODEC_FIELDS_ONLY_WIDE, CODEC_FIELDS_OFFSETS_WIDE)
+CODECS_WITH_FREQ = (CODEC_FULL, CODEC_FREQS_ONLY, CODEC_FREQS_FIELDS, CODEC_FREQS_OFFSETS, CODEC_FULL_WIDE, CODEC_FREQS_FIELDS_WIDE)
 SCORER_BM25STD, SCORER_BM25, SCORER_TFIDF, SCORER_TFIDF_DOCNORM, SCORER_DOCSCORE, SCORER_BM25STD_TANH, SCORER_DISMAX = range(7)
 SCORER_NAMES = {SCORER_BM25STD: b"BM25STD", SCORER_BM25: b"BM25", SCORER_TFIDF: b"TFIDF",
                 SCORER_TFIDF_DOCNORM: b"TFIDF.DOCNORM", SCORER_DOCSCORE: b"DOCSCORE",
@@ -362,6 +370,12 @@ def postings():
         L.orc_ii_free.argtypes = [_P]
         L.orc_ii_add.restype = _SZ
         L.orc_ii_add.argtypes = [_P, C.c_uint64, C.c_uint32, C.c_uint32, _P, C.c_uint32]
+        L.orc_ii_add_wide.restype = _SZ
+        L.orc_ii_add_wide.argtypes = [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _P, C.c_uint32]
+        L.orc_reader_new_wide.restype = _P
+        L.orc_reader_new_wide.argtypes = [_P, C.c_uint64, C.c_uint64]
+        L.orc_reader_next_wide.restype = C.c_int
+        L.orc_reader_next_wide.argtypes = [_P, _P, _P, _P, _P]
         L.orc_ii_num_blocks.restype = _SZ
         L.orc_ii_num_blocks.argtypes = [_P]
         L.orc_ii_num_docs.restype = _SZ
@@ -446,7 +460,7 @@ class InvIndex:
 
     def add(self, doc_id, freq=1, mask=1, offsets=b""):
         buf = (C.c_uint8 * max(1, len(offsets))).from_buffer_copy(offsets or b"\0")
-        return self.L.orc_ii_add(self.h, doc_id, freq, mask, buf, len(offsets))
+        return self.L.orc_ii_add_wide(self.h, doc_id, freq, mask & 0xFFFFFFFFFFFFFFFF, mask >> 64, buf, len(offsets))
 
     def num_docs(self):
         return self.L.orc_ii_num_docs(self.h)
@@ -461,14 +475,16 @@ class InvIndex:
         return out
 
     def reader(self, mask=0):
-        return self.L.orc_reader_new(self.h, mask)
+        return self.L.orc_reader_new_wide(self.h, mask & 0xFFFFFFFFFFFFFFFF, mask >> 64)
 
     def read_all(self, mask=0):
+        """[(docId, freq, fieldMask)]; the mask is 128 bits wide for the *Wide codecs, its low 32 bits otherwise"""
         r = self.reader(mask)
-        d, f, m = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        d, f, lo, hi = C.c_uint64(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+        wide = self.codec in CODECS_WIDE
         out = []
-        while self.L.orc_reader_next(r, C.byref(d), C.byref(f), C.byref(m)):
-            out.append((d.value, f.value, m.value))
+        while self.L.orc_reader_next_wide(r, C.byref(d), C.byref(f), C.byref(lo), C.byref(hi)):
+            out.append((d.value, f.value, (lo.value | (hi.value << 64)) if wide else (lo.value & 0xFFFFFFFF)))
         self.L.orc_reader_free(r)
         return out
 

@@ -85,9 +85,24 @@ def test_codec_golden_bytes():
         assert list(_single_record_bytes(ol.CODEC_DOCIDS_ONLY, delta, 1, 1)) == expected
     for delta, expected in G["raw_doc_ids_only"]:
         assert list(_single_record_bytes(ol.CODEC_RAW_DOCIDS_ONLY, delta, 1, 1)) == expected
+    # the codecs that carry term offsets without the full record, and the u128 field-mask (*Wide) variants
+    for delta, freq, offs, expected in G["freqs_offsets"]["cases"]:
+        assert list(_single_record_bytes(ol.CODEC_FREQS_OFFSETS, delta, freq, 1, bytes(offs))) == expected
+    for delta, offs, expected in G["offsets_only"]["cases"]:
+        assert list(_single_record_bytes(ol.CODEC_OFFSETS_ONLY, delta, 1, 1, bytes(offs))) == expected
+    for delta, mask, offs, expected in G["fields_offsets"]["cases"]:
+        assert list(_single_record_bytes(ol.CODEC_FIELDS_OFFSETS, delta, 1, mask, bytes(offs))) == expected
+    for delta, mask, offs, expected in G["fields_offsets_wide"]["cases"]:
+        assert list(_single_record_bytes(ol.CODEC_FIELDS_OFFSETS_WIDE, delta, 1, int(mask), bytes(offs))) == expected
+    for delta, freq, mask, offs, expected in G["full_wide"]["cases"]:
+        assert list(_single_record_bytes(ol.CODEC_FULL_WIDE, delta, freq, int(mask), bytes(offs))) == expected
+    for delta, freq, mask, expected in G["freqs_fields_wide"]["cases"]:
+        assert list(_single_record_bytes(ol.CODEC_FREQS_FIELDS_WIDE, delta, freq, int(mask))) == expected
+    for delta, mask, expected in G["fields_only_wide"]["cases"]:
+        assert list(_single_record_bytes(ol.CODEC_FIELDS_ONLY_WIDE, delta, 1, int(mask))) == expected
 
 
-@pytest.mark.parametrize("codec", range(6))
+@pytest.mark.parametrize("codec", range(ol.N_CODECS))
 def test_blocks_and_reader_roundtrip(codec):
     """index/core.rs:235-358 + reader/core.rs: 100 (1000) entries per block, first record delta 0,
     a delta that overflows u32 opens a new block, repeated docIds are dropped."""
@@ -95,8 +110,13 @@ def test_blocks_and_reader_roundtrip(codec):
     ids = np.cumsum(rng.integers(1, 50, 2500)).astype(np.uint64)
     ids[1200:] += np.uint64(1 << 33)  # force a >u32 delta
     freqs = rng.integers(1, 300, len(ids))
-    masks = rng.integers(1, 1 << 20, len(ids))
-    ix = ol.InvIndex(codec, ids, freqs, masks)
+    masks = rng.integers(1, 1 << 20, len(ids)).tolist()
+    if codec in ol.CODECS_WIDE:  # field masks beyond 32 / 64 bits
+        masks = [m << int(s_) for m, s_ in zip(masks, rng.integers(0, 100, len(ids)))]
+    ix = ol.InvIndex(codec)
+    for i, d in enumerate(ids.tolist()):
+        ob = bytes(rng.integers(1, 100, int(rng.integers(0, 4)), dtype=np.uint8).tolist()) if codec in ol.CODECS_WITH_OFFSETS else b""
+        ix.add(d, int(freqs[i]), masks[i], ob)
     assert ix.add(int(ids[-1]), 5, 5) == 0  # duplicate docId silently skipped
     per = 1000 if codec in (ol.CODEC_DOCIDS_ONLY, ol.CODEC_RAW_DOCIDS_ONLY) else 100
     blocks = ix.blocks()
@@ -105,10 +125,15 @@ def test_blocks_and_reader_roundtrip(codec):
         assert any(b[0] == int(ids[1200]) for b in blocks)  # the overflow opened a block at that doc
     got = ix.read_all()
     assert [g[0] for g in got] == ids.tolist()
-    if codec in (ol.CODEC_FULL, ol.CODEC_FREQS_ONLY, ol.CODEC_FREQS_FIELDS):
+    if codec in ol.CODECS_WITH_FREQ:
         assert [g[1] for g in got] == freqs.tolist()
-    if codec in (ol.CODEC_FULL, ol.CODEC_FREQS_FIELDS, ol.CODEC_FIELDS_ONLY):
-        assert [g[2] for g in got] == masks.tolist()
+    else:
+        assert all(g[1] == 1 for g in got)
+    if codec in ol.CODECS_WITH_MASK:
+        assert [g[2] for g in got] == masks
+        # FilterMaskReader (reader/field_mask.rs) over the wide masks too
+        flt = (1 << 3) | (1 << 70)
+        assert [g[0] for g in ix.read_all(flt)] == [int(d) for d, m_ in zip(ids.tolist(), masks) if m_ & flt]
     # seek: first record >= target, from the start and monotonically
     L = ol.postings()
     r = ix.reader()

@@ -42,17 +42,19 @@ def make_lists(ps, codec, id_lists, freq_lists=None, on_device=False):
 # ------------------------------------------------------------------------------------------------
 # block decoding: every codec, host and device decoders, vs the oracle reader
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("codec", range(6))
+@pytest.mark.parametrize("codec", range(ol.N_CODECS))
 @pytest.mark.parametrize("on_device", [False, True])
 def test_decode_blocks_all_codecs(ps, codec, on_device):
     rng = np.random.default_rng(codec * 2 + on_device)
     ids = np.cumsum(rng.integers(1, 5000, 5321)).astype(np.uint64)
     freqs = rng.integers(1, 70000, len(ids))
-    masks = rng.integers(1, 1 << 30, len(ids))
+    masks = rng.integers(1, 1 << 30, len(ids)).tolist()
+    if codec in ol.CODECS_WIDE:
+        masks = [m << int(s_) for m, s_ in zip(masks, rng.integers(0, 98, len(ids)))]
     offs = [bytes(rng.integers(0, 255, int(rng.integers(0, 6))).astype(np.uint8)) for _ in ids]
     ix = ol.InvIndex(codec)
-    for d, f, m, o in zip(ids.tolist(), freqs.tolist(), masks.tolist(), offs):
-        ix.add(d, f, m, o if codec == ol.CODEC_FULL else b"")
+    for d, f, m, o in zip(ids.tolist(), freqs.tolist(), masks, offs):
+        ix.add(d, f, m, o if codec in ol.CODECS_WITH_OFFSETS else b"")
     pl = ps.PostingList.from_blocks(ix.blocks(), codec, on_device=on_device)
     assert len(pl) == len(ids) == pl.num_estimated()
     rs = ps.union([pl])
@@ -62,19 +64,31 @@ def test_decode_blocks_all_codecs(ps, codec, on_device):
     assert got_fr[0].tolist() == [e[1] for e in exp]
 
 
-@pytest.mark.parametrize("codec", [ol.CODEC_FULL, ol.CODEC_FREQS_FIELDS, ol.CODEC_FIELDS_ONLY])
-def test_field_mask_filter(ps, codec):
-    """FilterMaskReader: records whose fieldMask misses the query mask are dropped; estimate unchanged."""
+@pytest.mark.parametrize("codec", ol.CODECS_WITH_MASK)
+@pytest.mark.parametrize("on_device", [False, True])
+def test_field_mask_filter(ps, codec, on_device):
+    """FilterMaskReader: records whose fieldMask misses the query mask are dropped; estimate unchanged.  The *Wide codecs carry
+    u128 masks (more than 32 fields) and take a 128-bit filter."""
     rng = np.random.default_rng(3)
     ids = np.cumsum(rng.integers(1, 9, 3000)).astype(np.uint64)
-    masks = rng.integers(1, 16, len(ids))
-    ix = ol.InvIndex(codec, ids, [2] * len(ids), masks)
-    for flt in (1, 6, 8):
-        pl = ps.PostingList.from_blocks(ix.blocks(), codec, field_mask_filter=flt)
+    masks = rng.integers(1, 16, len(ids)).tolist()
+    filters = (1, 6, 8)
+    if codec in ol.CODECS_WIDE:
+        masks = [m << int(s_) for m, s_ in zip(masks, rng.choice([0, 30, 62, 100], len(ids)))]
+        filters = (1, 6, 1 << 33, (1 << 64) | (1 << 101), (1 << 3) | (1 << 65))
+    ix = ol.InvIndex(codec)
+    for d, m in zip(ids.tolist(), masks):
+        ix.add(d, 2, m, b"\5" if codec in ol.CODECS_WITH_OFFSETS else b"")
+    for flt in filters:
+        pl = ps.PostingList.from_blocks(ix.blocks(), codec, field_mask_filter=flt, on_device=on_device)
         exp = ix.read_all(flt)
-        assert len(pl) == len(exp) and pl.num_estimated() == len(ids)
-        got, _, _ = ps.union([pl]).fetch()
-        assert got.tolist() == [e[0] for e in exp]
+        assert len(pl) == len(exp) and pl.num_estimated() == len(ids), (codec, flt)
+        if len(exp):
+            got, _, _ = ps.union([pl]).fetch()
+            assert got.tolist() == [e[0] for e in exp]
+    if codec not in ol.CODECS_WIDE:  # bits above 31 cannot be met by a 32-bit mask codec: refused, not silently truncated
+        with pytest.raises(RuntimeError):
+            ps.PostingList.from_blocks(ix.blocks(), codec, field_mask_filter=1 << 40)
 
 
 def test_golden_codec_bytes_decode(ps):
@@ -531,7 +545,7 @@ def _block_views(ps, blocks):
     return arr, keep
 
 
-@pytest.mark.parametrize("codec", range(6))
+@pytest.mark.parametrize("codec", range(ol.N_CODECS))
 def test_batch_decode_of_many_lists_matches_the_oracle_reader(ps, codec):
     """II_PostingList_FromBlocksBatch: the blocks of MANY lists in one gather / one copy / one decode launch (bytes staged in
     shared memory, one thread per block).  Every list must read back exactly like the oracle reader: long lists, a one-entry
@@ -544,8 +558,9 @@ def test_batch_decode_of_many_lists_matches_the_oracle_reader(ps, codec):
         doc = 0
         for _ in range(n):
             doc += int(rng.integers(1, gap + 1))
-            off = bytes(rng.integers(0, 255, int(rng.integers(0, 9))).astype(np.uint8)) if codec == ol.CODEC_FULL else b""
-            ix.add(doc, int(rng.integers(1, 1 << int(rng.integers(1, 31)))), int(rng.integers(1, 1 << 30)), off)
+            off = bytes(rng.integers(0, 255, int(rng.integers(0, 9))).astype(np.uint8)) if codec in ol.CODECS_WITH_OFFSETS else b""
+            mask = int(rng.integers(1, 1 << 30)) << (int(rng.integers(0, 98)) if codec in ol.CODECS_WIDE else 0)
+            ix.add(doc, int(rng.integers(1, 1 << int(rng.integers(1, 31)))), mask, off)
         bl = ix.blocks()
         arr, k = _block_views(ps, bl)
         idx.append(ix)
@@ -697,11 +712,11 @@ def _positions_to_offsets(positions):
     return out
 
 
-def _phrase_corpus(rng, n_docs, n_terms, density, doc_words):
-    """Full-codec indexes of n_terms terms with random term positions; returns (indexes, per term {doc: offsets bytes})"""
+def _phrase_corpus(rng, n_docs, n_terms, density, doc_words, codec=ol.CODEC_FULL):
+    """indexes of n_terms terms with random term positions (a codec that stores them); returns (indexes, per term {doc: offsets bytes})"""
     idx, offs = [], []
     for t in range(n_terms):
-        ix = ol.InvIndex(ol.CODEC_FULL)
+        ix = ol.InvIndex(codec)
         docs = np.flatnonzero(rng.random(n_docs) < density[t]) + 1
         m = {}
         for d in docs.tolist():
@@ -864,6 +879,26 @@ def test_hamming_scorer_matches_the_reference(ps):
     assert seen == {True, False}
     rs.score_hamming(dt, b"")  # an empty query payload never matches (payload length 0 is "no payload")
     assert not rs.fetch()[1].any()
+
+
+@pytest.mark.parametrize("codec", [ol.CODEC_FREQS_OFFSETS, ol.CODEC_OFFSETS_ONLY, ol.CODEC_FIELDS_OFFSETS, ol.CODEC_FULL_WIDE,
+                                   ol.CODEC_FIELDS_OFFSETS_WIDE])
+def test_phrase_intersection_over_the_other_offset_codecs(ps, codec):
+    """every codec that stores term positions keeps them on the device: same phrase answers as the Full codec path"""
+    rng = np.random.default_rng(1500 + codec)
+    idx, offs = _phrase_corpus(rng, 30_000, 3, [0.5, 0.4, 0.6], 40, codec)
+    pls = ps.postings_with_offsets([ix.blocks() for ix in idx], codec)
+    assert all(ps.lib().II_PostingList_HasOffsets(p.h) for p in pls)
+    hits = ol.run_intersect(idx)
+    freq_of = [dict((d, f) for d, f, _ in ix.read_all()) for ix in idx]
+    for slop, in_order in ((0, True), (2, False), (5, True)):
+        rs = ps.intersect_phrase(pls, slop, in_order)
+        order = rs.child_order().tolist()
+        exp = [d for d, _ in hits if ol.within_range([offs[c][d] for c in order], slop, in_order)]
+        got_ids, _, got_fr = rs.fetch()
+        assert got_ids.tolist() == exp and 0 < len(exp) < len(hits)
+        for slot, c in enumerate(order):
+            assert got_fr[slot].tolist() == [freq_of[c][d] for d in exp]
 
 
 def test_phrase_constructor_takes_slop_and_in_order(ps):
