@@ -237,6 +237,48 @@ typedef struct {
     size_t flatBufferSize;
 } VecSimIndexStatsInfo;
 
+/* VecSimIndexDebugInfo (vec_sim_common.h:372-457): returned BY VALUE by VecSimIndex_DebugInfo, so the whole union has to keep
+ * the reference's size and member offsets even though a FLAT index only fills commonInfo and bfInfo. */
+typedef struct {
+    VecSimIndexBasicInfo basicInfo;
+    size_t indexSize;       /* current count of vectors */
+    size_t indexLabelCount; /* current unique count of labels */
+    uint64_t memory;
+    VecSearchMode lastMode; /* the mode in which the last query ran */
+} CommonInfo;
+typedef struct { size_t M, efConstruction, efRuntime; double epsilon; size_t max_level, entrypoint, visitedNodesPoolSize,
+                 numberOfMarkedDeletedNodes; } hnswInfoStruct;
+typedef struct { char dummy; } bfInfoStruct;
+typedef struct {
+    VecSimSvsQuantBits quantBits;
+    float alpha;
+    size_t graphMaxDegree, constructionWindowSize, maxCandidatePoolSize, pruneTo;
+    bool useSearchHistory;
+    size_t numThreads, lastReservedThreads, numberOfMarkedDeletedNodes, searchWindowSize, searchBufferCapacity, leanvecDim;
+    double epsilon;
+} svsInfoStruct;
+typedef struct HnswTieredInfo { size_t pendingSwapJobsThreshold; } HnswTieredInfo;
+typedef struct SvsTieredInfo { size_t trainingTriggerThreshold, updateTriggerThreshold, updateJobWaitTime; bool indexUpdateScheduled; } SvsTieredInfo;
+typedef struct {
+    union { hnswInfoStruct hnswInfo; svsInfoStruct svsInfo; } backendInfo;
+    union { HnswTieredInfo hnswTieredInfo; SvsTieredInfo svsTieredInfo; } specificTieredBackendInfo;
+    CommonInfo backendCommonInfo;
+    CommonInfo frontendCommonInfo;
+    bfInfoStruct bfInfo;
+    uint64_t management_layer_memory;
+    VecSimBool backgroundIndexing;
+    size_t bufferLimit;
+} tieredInfoStruct;
+typedef struct {
+    CommonInfo commonInfo;
+    union {
+        bfInfoStruct bfInfo;
+        hnswInfoStruct hnswInfo;
+        svsInfoStruct svsInfo;
+        tieredInfoStruct tieredInfo;
+    };
+} VecSimIndexDebugInfo;
+
 /* Debug-info iterator (info_iterator.h:17-44).  Fields reported for FLAT: ALGORITHM, TYPE,
  * DIMENSION, METRIC, IS_MULTI_VALUE, IS_DISK, INDEX_SIZE, INDEX_LABEL_COUNT, MEMORY,
  * LAST_SEARCH_MODE, BLOCK_SIZE (brute_force.h:327-365). */
@@ -358,6 +400,7 @@ size_t VecSimParams_GetQueryBlobSize(VecSimType type, size_t dim, VecSimMetric m
 
 VecSimIndexBasicInfo VecSimIndex_BasicInfo(VecSimIndex *index);               /* vec_sim.h:178 */
 VecSimIndexStatsInfo VecSimIndex_StatsInfo(VecSimIndex *index);               /* vec_sim.h:185 */
+VecSimIndexDebugInfo VecSimIndex_DebugInfo(VecSimIndex *index);               /* vec_sim.h:170; FLAT: BruteForceIndex::debugInfo, brute_force.h:318-325 */
 VecSimDebugInfoIterator *VecSimIndex_DebugInfoIterator(VecSimIndex *index);   /* vec_sim.h:193 */
 size_t VecSimDebugInfoIterator_NumberOfFields(VecSimDebugInfoIterator *it);   /* info_iterator.h:50 */
 bool VecSimDebugInfoIterator_HasNextField(VecSimDebugInfoIterator *it);
@@ -372,6 +415,8 @@ void VecSim_SetMemoryFunctions(VecSimMemoryFunctions memoryfunctions);   /* vec_
 void VecSim_SetTimeoutCallbackFunction(timeoutCallbackFunction callback); /* vec_sim.h:295 */
 void VecSim_SetLogCallbackFunction(logCallbackFunction callback);        /* vec_sim.h:302 */
 void VecSim_SetWriteMode(VecSimWriteMode mode);                           /* no-op, vec_sim.h:320 */
+void VecSim_SetTestLogContext(const char *test_name, const char *test_type); /* vec_sim.h:303: names the log file of the reference's
+                                                                                 test logger; kept and shown by the default log sink */
 void VecSim_UpdateThreadPoolSize(size_t new_size);                        /* no-op, vec_sim.h:330 */
 size_t VecSim_GetSharedMemory(void);                                      /* 0,    vec_sim.h:338 */
 

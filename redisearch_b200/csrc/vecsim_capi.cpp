@@ -209,6 +209,7 @@ size_t VecSimParams_GetQueryBlobSize(VecSimType type, size_t dim, VecSimMetric m
 
 VecSimIndexBasicInfo VecSimIndex_BasicInfo(VecSimIndex *index) { return IX(index)->basic_info(); }
 VecSimIndexStatsInfo VecSimIndex_StatsInfo(VecSimIndex *index) { return IX(index)->stats_info(); }
+VecSimIndexDebugInfo VecSimIndex_DebugInfo(VecSimIndex *index) { return IX(index)->debug_info(); }
 VecSimDebugInfoIterator *VecSimIndex_DebugInfoIterator(VecSimIndex *index) { return IX(index)->debug_iterator(); }
 size_t VecSimDebugInfoIterator_NumberOfFields(VecSimDebugInfoIterator *it) { return it->fields.size(); }
 bool VecSimDebugInfoIterator_HasNextField(VecSimDebugInfoIterator *it) { return it->pos < it->fields.size(); }
@@ -225,6 +226,12 @@ void VecSim_SetMemoryFunctions(VecSimMemoryFunctions f) { rsb200::globals().mem 
 void VecSim_SetTimeoutCallbackFunction(timeoutCallbackFunction cb) { rsb200::globals().timeout_cb.store(cb); }
 void VecSim_SetLogCallbackFunction(logCallbackFunction cb) { rsb200::globals().log_cb.store(cb); }
 void VecSim_SetWriteMode(VecSimWriteMode) {}
+void VecSim_SetTestLogContext(const char *test_name, const char *test_type) {
+    auto &g = rsb200::globals();
+    std::lock_guard<std::mutex> lk(g.test_ctx_mu);
+    g.test_name = test_name ? test_name : "";
+    g.test_type = test_type ? test_type : "";
+}
 void VecSim_UpdateThreadPoolSize(size_t) {}
 size_t VecSim_GetSharedMemory(void) { return 0; }
 

@@ -1616,6 +1616,18 @@ static const char *mode_name(VecSearchMode m) { // vec_utils.cpp VecSimSearchMod
     }
 }
 
+VecSimIndexDebugInfo FlatIndex::debug_info() const {
+    VecSimIndexDebugInfo info;
+    memset(&info, 0, sizeof(info));
+    info.commonInfo.basicInfo = basic_info();
+    info.commonInfo.indexSize = count_;
+    info.commonInfo.indexLabelCount = multi_ ? label_to_ids_.size() : label_to_id_.size();
+    info.commonInfo.memory = stats_info().memory;
+    info.commonInfo.lastMode = last_mode_;
+    info.bfInfo.dummy = 0;
+    return info;
+}
+
 VecSimDebugInfoIterator *FlatIndex::debug_iterator() const {
     auto *it = new VecSimDebugInfoIterator();
     auto str = [&](const char *name, const char *v) {

@@ -44,6 +44,8 @@ struct Globals {
     std::atomic<timeoutCallbackFunction> timeout_cb{nullptr};
     std::atomic<logCallbackFunction> log_cb{nullptr};
     VecSimMemoryFunctions mem{};
+    std::mutex test_ctx_mu; // VecSim_SetTestLogContext
+    std::string test_name, test_type;
 };
 Globals &globals();
 void set_coarse_mode(int mode); // -1 env default, 0 exact scans only, 1 coarse pass on fp16 shadow rows, 2 TF32 coarse pass
@@ -138,6 +140,7 @@ class FlatIndex {
 
     VecSimIndexBasicInfo basic_info() const;
     VecSimIndexStatsInfo stats_info() const;
+    VecSimIndexDebugInfo debug_info() const; // BruteForceIndex::debugInfo, brute_force.h:318-325
     VecSimDebugInfoIterator *debug_iterator() const;
     void set_last_mode(VecSearchMode m) { last_mode_ = m; }
     VecSimB200_Stats get_stats(bool reset);

@@ -59,6 +59,16 @@ class _FieldValue(C.Union):
                 ("stringValue", C.c_char_p), ("iteratorValue", C.c_void_p)]
 
 
+class CommonInfo(C.Structure):
+    _fields_ = [("basicInfo", VecSimIndexBasicInfo), ("indexSize", C.c_size_t), ("indexLabelCount", C.c_size_t), ("memory", C.c_uint64),
+                ("lastMode", C.c_int)]
+
+
+class VecSimIndexDebugInfo(C.Structure):
+    """vec_sim_common.h:449-457; the union behind commonInfo is carried as opaque bytes (a FLAT index fills bfInfo only)"""
+    _fields_ = [("commonInfo", CommonInfo), ("_union", C.c_uint8 * 296)]
+
+
 class VecSim_InfoField(C.Structure):
     _fields_ = [("fieldName", C.c_char_p), ("fieldType", C.c_int), ("fieldValue", _FieldValue)]
 
@@ -109,6 +119,7 @@ SIGNATURES = [
     ("VecSimParams_GetQueryBlobSize", _SZ, [C.c_int, _SZ, C.c_int]),
     ("VecSimIndex_BasicInfo", VecSimIndexBasicInfo, [_P]),
     ("VecSimIndex_StatsInfo", VecSimIndexStatsInfo, [_P]),
+    ("VecSimIndex_DebugInfo", VecSimIndexDebugInfo, [_P]),
     ("VecSimIndex_DebugInfoIterator", _P, [_P]),
     ("VecSimDebugInfoIterator_NumberOfFields", _SZ, [_P]),
     ("VecSimDebugInfoIterator_HasNextField", C.c_bool, [_P]),
@@ -120,6 +131,7 @@ SIGNATURES = [
     ("VecSim_SetTimeoutCallbackFunction", None, [TIMEOUT_CB]),
     ("VecSim_SetLogCallbackFunction", None, [LOG_CB]),
     ("VecSim_SetWriteMode", None, [C.c_int]),
+    ("VecSim_SetTestLogContext", None, [C.c_char_p, C.c_char_p]),
     ("VecSim_UpdateThreadPoolSize", None, [_SZ]),
     ("VecSim_GetSharedMemory", _SZ, []),
     ("VecSimB200_TopKQueryBatch", C.c_int, [_P, _P, _SZ, _SZ, _SZ, C.POINTER(VecSimQueryParams), _P, _P]),

@@ -7,6 +7,10 @@
 int main(void){
  S(VecSimParams); S(AlgoParams); S(BFParams); S(HNSWParams); S(SVSParams); S(TieredIndexParams);
  S(VecSimQueryParams); S(VecSimIndexBasicInfo); S(VecSimIndexStatsInfo); S(VecSimRawParam); S(VecSim_InfoField); S(VecSimMemoryFunctions);
+ S(VecSimIndexDebugInfo); S(CommonInfo); S(tieredInfoStruct); S(svsInfoStruct); S(hnswInfoStruct);
+ O(VecSimIndexDebugInfo,commonInfo); O(VecSimIndexDebugInfo,bfInfo); O(VecSimIndexDebugInfo,tieredInfo);
+ O(CommonInfo,basicInfo); O(CommonInfo,indexSize); O(CommonInfo,indexLabelCount); O(CommonInfo,memory); O(CommonInfo,lastMode);
+ O(tieredInfoStruct,backendCommonInfo); O(tieredInfoStruct,frontendCommonInfo); O(tieredInfoStruct,bfInfo); O(tieredInfoStruct,management_layer_memory); O(tieredInfoStruct,backgroundIndexing); O(tieredInfoStruct,bufferLimit);
  O(VecSimParams,algo); O(VecSimParams,algoParams); O(VecSimParams,logCtx);
  O(BFParams,type); O(BFParams,dim); O(BFParams,metric); O(BFParams,multi); O(BFParams,initialCapacity); O(BFParams,blockSize);
  O(VecSimQueryParams,batchSize); O(VecSimQueryParams,searchMode); O(VecSimQueryParams,timeoutCtx);

@@ -411,6 +411,12 @@ def test_swap_delete_update_readd(vs):
     info = g.debug_info()
     assert info["INDEX_SIZE"] == g.size() and info["ALGORITHM"] == "FLAT" and info["METRIC"] == "COSINE"
     assert g.stats_info().memory > 0
+    # the by-value struct of VecSimIndex_DebugInfo (BruteForceIndex::debugInfo, brute_force.h:318-325) says the same
+    di = vs.lib().VecSimIndex_DebugInfo(g.h)
+    assert C.sizeof(di) == 360 and di.commonInfo.indexSize == g.size() and di.commonInfo.indexLabelCount == info["INDEX_LABEL_COUNT"]
+    assert di.commonInfo.basicInfo.metric == COS and di.commonInfo.basicInfo.dim == dim and di.commonInfo.memory == info["MEMORY"]
+    assert di.commonInfo.lastMode == vs.STANDARD_KNN
+    vs.lib().VecSim_SetTestLogContext(b"parity", b"unit")
 
 
 def test_multi_value_index(vs):
