@@ -39,7 +39,8 @@ typedef uint64_t t_docId;
 typedef enum { ITERATOR_OK = 0, ITERATOR_NOTFOUND = 1, ITERATOR_EOF = 2, ITERATOR_TIMEOUT = 3 } IteratorStatus;
 typedef enum { VALIDATE_OK = 0, VALIDATE_MOVED = 1, VALIDATE_ABORTED = 2, VALIDATE_TIMEOUT = 3 } ValidateStatus;
 /* RS/headers/rqe_iterator_type.h */
-enum { II_IteratorType_Union = 6, II_IteratorType_Intersect = 7, II_IteratorType_Empty = 13,
+enum { II_IteratorType_InvIdxWildcard = 2, II_IteratorType_Union = 6, II_IteratorType_Intersect = 7, II_IteratorType_Wildcard = 12,
+       II_IteratorType_Empty = 13,
        II_IteratorType_MetricSortedById = 16 };
 /* RS/headers/index_result_rs.h RawResultData_Active_Tag */
 enum { II_ResultData_Union = 1, II_ResultData_Intersection = 2, II_ResultData_Term = 4, II_ResultData_Virtual = 8,
@@ -302,6 +303,11 @@ II_QueryIterator *NewIntersectionIterator(II_QueryIterator **its, size_t num, in
 II_QueryIterator *NewUnionIterator(II_QueryIterator **its, int32_t num, bool quick_exit, double weight, int /* QueryNodeType */ type_,
                                    const char *q_str, const void /* IteratorsConfig */ *config);
 II_QueryIterator *II_NewEmptyIterator(void);
+/* rqe_iterators/src/wildcard.rs:83-180: every docId 1..top_id as a virtual result (freq 1, all fields) of the given weight; the
+ * second name is the reference's (RS/headers/iterators_ffi.h:647).  Stripped by our AND, taken over by a quick OR
+ * (union_reducer.rs:41-53), a device list 1..top_id inside a full OR. */
+II_QueryIterator *II_NewWildcardIterator(t_docId top_id, double weight);
+II_QueryIterator *NewWildcardIterator_NonOptimized(t_docId max_id, double weight);
 /* Term leaf over a device posting list (what NewInvIndIterator_TermQuery, iterators_ffi.h:404, yields): weight = the query
  * node's weight, idf / bm25_idf = QueryTerm_GetIDF / QueryTerm_GetBM25_IDF of the term. */
 II_QueryIterator *II_NewTermIterator(II_PostingList *pl, int take_ownership, double weight, double idf, double bm25_idf);

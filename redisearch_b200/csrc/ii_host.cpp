@@ -564,6 +564,28 @@ II_PostingList *II_PostingList_FromDevice(const uint32_t *d_doc_ids, const uint3
     return pl;
 }
 
+// every docId 1..top_id with freq 1 (what a wildcard child contributes to an aggregate)
+static II_PostingList *posting_list_all_docs(uint64_t top_id) {
+    if (top_id > 0xFFFFFFFEull) return nullptr;
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    auto *pl = new II_PostingList();
+    const size_t n = (size_t)top_id;
+    pl->d_ids = dalloc<uint32_t>(n ? n : 1);
+    pl->d_freqs = dalloc<uint32_t>(n ? n : 1);
+    bool ok = pl->d_ids && pl->d_freqs;
+    ok = ok && ii_launch_iota(pl->d_ids, pl->d_freqs, (uint32_t)n, c.stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+    if (!ok) {
+        delete pl;
+        return nullptr;
+    }
+    pl->n = pl->estimated = n;
+    pl->last_id = (uint32_t)top_id;
+    return pl;
+}
+
 size_t II_PostingList_Len(const II_PostingList *pl) { return pl->n; }
 size_t II_PostingList_NumEstimated(const II_PostingList *pl) { return pl->estimated; }
 void II_PostingList_Free(II_PostingList *pl) { delete pl; }
@@ -1793,7 +1815,7 @@ namespace {
 constexpr uint64_t kNodeMagic = 0xB200D15C0FFEE5ull;
 const II_DocTable *g_default_docs = nullptr;
 
-enum NodeKind { NODE_LEAF = 0, NODE_RESULT = 1, NODE_EMPTY = 2 };
+enum NodeKind { NODE_LEAF = 0, NODE_RESULT = 1, NODE_EMPTY = 2, NODE_WILDCARD = 3 };
 enum LeafMode { LEAF_REQUIRED = 0, LEAF_NOT = 1, LEAF_OPTIONAL = 2 };
 
 struct NodeIter {
@@ -1806,7 +1828,8 @@ struct NodeIter {
     II_TermCache *cache = nullptr; // non-NULL: pl is pinned in this cache (released, not freed)
     II_TermParams term{1.0, 0.0, 0.0};
     LeafMode mode = LEAF_REQUIRED;
-    uint64_t max_doc_id = 0; // NOT / OPTIONAL: the universe is 1..max_doc_id
+    uint64_t max_doc_id = 0; // NOT / OPTIONAL: the universe is 1..max_doc_id; wildcard: top_id
+    bool past_end = false;   // wildcard: a read / skip found nothing (wildcard.rs `past_end`)
     // result of an evaluated AND / OR (or a leaf that is read directly)
     II_ResultSet *rs = nullptr;
     std::vector<II_TermParams> terms; // per child, in the order of the constructor's `its`
@@ -1926,6 +1949,47 @@ void node_rewind(II_QueryIterator *b) {
 }
 void node_free(II_QueryIterator *b) { delete NI(b); }
 
+// ---- wildcard (rqe_iterators/src/wildcard.rs:83-180): a counter over 1..top_id yielding one virtual result
+size_t wc_num_estimated(const II_QueryIterator *b) { return (size_t) reinterpret_cast<const NodeIter *>(b)->max_doc_id; }
+bool wc_exhausted(NodeIter *it) {
+    if (it->past_end || it->base.lastDocId >= it->max_doc_id) {
+        it->past_end = true;
+        it->base.atEOF = true;
+        it->base.current = nullptr;
+        return true;
+    }
+    return false;
+}
+IteratorStatus wc_read(II_QueryIterator *b) {
+    NodeIter *it = NI(b);
+    if (wc_exhausted(it)) return ITERATOR_EOF;
+    b->lastDocId += 1;
+    it->res.docId = b->lastDocId;
+    b->current = &it->res;
+    return ITERATOR_OK;
+}
+IteratorStatus wc_skip_to(II_QueryIterator *b, t_docId doc) {
+    NodeIter *it = NI(b);
+    if (wc_exhausted(it)) return ITERATOR_EOF;
+    if (doc > it->max_doc_id) { // beyond the last document: the position stays where the last yield left it
+        it->past_end = true;
+        b->atEOF = true;
+        b->current = nullptr;
+        return ITERATOR_EOF;
+    }
+    b->lastDocId = doc;
+    it->res.docId = doc;
+    b->current = &it->res;
+    return ITERATOR_OK;
+}
+void wc_rewind(II_QueryIterator *b) {
+    NodeIter *it = NI(b);
+    it->past_end = false;
+    b->atEOF = false;
+    b->lastDocId = 0;
+    b->current = nullptr;
+}
+
 NodeIter *new_node(NodeKind kind, uint32_t type, double weight) {
     auto *it = new NodeIter();
     memset(&it->base, 0, sizeof(it->base));
@@ -1977,6 +2041,12 @@ bool child_view(II_QueryIterator *c, ChildView &v) {
             v.term = n->term;
             return v.pl != nullptr;
         }
+        if (n->kind == NODE_WILDCARD) { // every document, as a virtual result with freq 1: a leaf with idf = 1 scores the same
+            v.pl = posting_list_all_docs(n->max_doc_id);
+            v.temp = true;
+            v.term = II_TermParams{n->res.weight, 1.0, 1.0};
+            return v.pl != nullptr;
+        }
         if (n->kind == NODE_RESULT && n->rs) { // nested AND / OR: its docIds, freq = sum over its children
             if (!node_host(n)) return false;
             std::vector<uint32_t> fr(n->ids.size(), 1u);
@@ -2008,6 +2078,25 @@ bool child_is_empty(const II_QueryIterator *c) {
 void II_SetDefaultDocTable(const II_DocTable *docs) { g_default_docs = docs; }
 
 II_QueryIterator *II_NewEmptyIterator(void) { return &new_node(NODE_EMPTY, II_IteratorType_Empty, 1.0)->base; }
+
+// NewWildcardIterator_NonOptimized (RS/headers/iterators_ffi.h; rqe_iterators/src/wildcard.rs:83-96): every docId 1..top_id as a
+// VIRTUAL result with freq 1, field mask ALL and the given weight.  As a child of our AND it is stripped, as a child of a quick
+// union it becomes the union (union_reducer.rs:41-53), in a full union / under NOT / OPTIONAL it takes part as the device list
+// 1..top_id.
+II_QueryIterator *II_NewWildcardIterator(t_docId top_id, double weight) {
+    NodeIter *n = new_node(NODE_WILDCARD, II_IteratorType_Wildcard, weight);
+    n->max_doc_id = top_id;
+    n->base.NumEstimated = wc_num_estimated;
+    n->base.Read = wc_read;
+    n->base.SkipTo = wc_skip_to;
+    n->base.Rewind = wc_rewind;
+    n->res.data.tag = II_ResultData_Virtual;
+    memset(n->res.data._rest, 0, sizeof(n->res.data._rest)); // a virtual result carries no payload (and no scorer back-pointer)
+    n->res.freq = 1;
+    return &n->base;
+}
+// the reference's own name and signature (RS/headers/iterators_ffi.h:647)
+II_QueryIterator *NewWildcardIterator_NonOptimized(t_docId max_id, double weight) { return II_NewWildcardIterator(max_id, weight); }
 
 II_QueryIterator *II_NewTermIterator(II_PostingList *pl, int take_ownership, double weight, double idf, double bm25_idf) {
     if (!pl) return nullptr;
@@ -2125,6 +2214,16 @@ static II_QueryIterator *build_aggregate(II_QueryIterator **its, size_t num, boo
             continue; // dropped
         }
         kids.push_back(c);
+    }
+    if (is_union && quick_exit) { // union_reducer.rs:41-53: a quick union with a wildcard child IS that wildcard
+        for (size_t k = 0; k < kids.size(); k++)
+            if (kids[k]->type == 12 /* Wildcard */ || kids[k]->type == 2 /* InvIdxWildcard */) {
+                II_QueryIterator *keep = kids[k];
+                for (size_t i = 0; i < num; i++)
+                    if (its[i] && its[i] != keep && its[i]->Free) its[i]->Free(its[i]);
+                host_free(its);
+                return keep;
+            }
     }
     if (kids.empty()) {
         // all wildcards -> the last one is returned (AND); nothing left -> empty (OR)

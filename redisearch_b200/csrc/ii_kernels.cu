@@ -1287,6 +1287,18 @@ cudaError_t ii_launch_hamming(const uint32_t *d_docs, const uint32_t *d_len, uin
     hamming_kernel<<<grid_for(cap_len, 256, 148 * 8), 256, 0, s>>>(d_docs, d_len, cap_len, d_payloads, d_payload_off, d_qdata, qlen, d_scores);
     return cudaGetLastError();
 }
+// docIds 1..n with freq 1: the wildcard iterator's documents (rqe_iterators/src/wildcard.rs) as a device list
+__global__ void iota_kernel(uint32_t *__restrict__ ids, uint32_t *__restrict__ freqs, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        ids[i] = i + 1;
+        freqs[i] = 1;
+    }
+}
+cudaError_t ii_launch_iota(uint32_t *d_ids, uint32_t *d_freqs, uint32_t n, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    iota_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(d_ids, d_freqs, n);
+    return cudaGetLastError();
+}
 uint32_t ii_topn_lists(uint32_t m) { return grid_for(m, 256, 148 * 2) * 8; }
 cudaError_t ii_launch_topn(const uint32_t *d_docs, const double *d_scores, const uint32_t *d_len, uint32_t cap_len, uint32_t k,
                            uint64_t *d_keys, uint32_t *d_ids, cudaStream_t s) {

@@ -155,6 +155,7 @@ cudaError_t ii_launch_union(const uint32_t *const *d_ids, const uint32_t *const 
 // payload or the lengths differ.  payload_off[d] .. payload_off[d+1] delimit the payload of docId d inside `payloads`.
 cudaError_t ii_launch_hamming(const uint32_t *d_docs, const uint32_t *d_len, uint32_t cap_len, const uint8_t *d_payloads,
                               const uint64_t *d_payload_off, const uint8_t *d_qdata, uint32_t qlen, double *d_scores, cudaStream_t s);
+cudaError_t ii_launch_iota(uint32_t *d_ids, uint32_t *d_freqs, uint32_t n, cudaStream_t s);
 uint32_t ii_topn_lists(uint32_t m);
 cudaError_t ii_launch_topn(const uint32_t *d_docs, const double *d_scores, const uint32_t *d_len, uint32_t cap_len, uint32_t k,
                            uint64_t *d_keys, uint32_t *d_ids, cudaStream_t s);

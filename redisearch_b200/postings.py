@@ -91,6 +91,8 @@ SIGNATURES = [
     ("II_MergeShardTopN", _SZ, [_P, _P, _P, _SZ, _SZ, _SZ, _P, _P]),
     ("II_NewResultIterator", _QI, [_P, C.c_double]),
     ("II_IntersectEx", _P, [_P, _P, _SZ]),
+    ("II_NewWildcardIterator", _QI, [C.c_uint64, C.c_double]),
+    ("NewWildcardIterator_NonOptimized", _QI, [C.c_uint64, C.c_double]),
     ("II_PostingList_FromBlocksWideMask", _P, [_P, _SZ, C.c_int, _P, C.c_int]),
     ("II_IntersectPhrase", _P, [_P, _P, _SZ, C.c_int32, C.c_int]),
     ("NewIntersectionIterator", _QI, [_P, _SZ, C.c_int32, C.c_bool, C.c_double]),

@@ -129,3 +129,36 @@ def test_merge_shard_topn_is_host_code_with_cmpbyscore_order():
     got = L.II_MergeShardTopN(scores.ctypes.data, ids.ctypes.data, counts.ctypes.data, G, per, 50, np.zeros(50, dtype=np.uint64).ctypes.data,
                               np.zeros(50).ctypes.data)
     assert got == 9
+
+
+def test_wildcard_iterator_contract_known_answers():
+    """rqe_iterators/tests/integration/wildcard.rs (initial_state, read_sequential, skip_to_valid_targets, skip_to_beyond_range,
+    rewind): the wildcard iterator is host code (a counter), so its QueryIterator contract is checked without a GPU."""
+    from redisearch_b200 import postings as ps
+
+    L = ps.lib()
+    it = L.NewWildcardIterator_NonOptimized(10, 5.0)
+    q = it.contents
+    assert q.type == 12 and q.lastDocId == 0 and not q.atEOF and q.NumEstimated(it) == 10  # initial_state
+    q.Free(it)
+    it = L.II_NewWildcardIterator(5, 0.5)
+    q = it.contents
+    for expected in range(1, 6):  # read_sequential
+        assert q.Read(it) == ps.ITERATOR_OK and q.lastDocId == expected and not q.atEOF
+        cur = q.current.contents
+        assert cur.docId == expected and cur.weight == 0.5 and cur.freq == 1 and cur.data.tag == 8  # a virtual result
+    assert q.Read(it) == ps.ITERATOR_EOF and q.atEOF and not q.current
+    assert q.Read(it) == ps.ITERATOR_EOF
+    q.Rewind(it)
+    assert q.lastDocId == 0 and not q.atEOF and q.Read(it) == ps.ITERATOR_OK and q.lastDocId == 1
+    q.Free(it)
+    it = L.II_NewWildcardIterator(10, 5.0)
+    q = it.contents
+    assert q.SkipTo(it, 5) == ps.ITERATOR_OK and q.lastDocId == 5 and not q.atEOF  # skip_to_valid_targets
+    assert q.SkipTo(it, 10) == ps.ITERATOR_OK and q.lastDocId == 10 and not q.atEOF
+    assert q.Read(it) == ps.ITERATOR_EOF and q.atEOF and not q.current
+    q.Rewind(it)
+    assert q.SkipTo(it, 3) == ps.ITERATOR_OK
+    assert q.SkipTo(it, 11) == ps.ITERATOR_EOF and q.atEOF and q.lastDocId == 3  # beyond the range: the position stays
+    assert q.SkipTo(it, 4) == ps.ITERATOR_EOF
+    q.Free(it)
