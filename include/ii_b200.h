@@ -141,6 +141,17 @@ size_t II_PostingList_FromBlocksBatch(size_t n_lists, const II_BlockView *const 
 size_t II_PostingList_FromBlocksBatchOffsets(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec,
                                              II_PostingList **out);
 int II_PostingList_HasOffsets(const II_PostingList *pl);
+/* NUMERIC index blocks (the leaves of the reference's numeric range tree; RS/inverted_index/src/codec/numeric.rs: header byte,
+ * 0-7 delta bytes, tiny / integer / f32 / f64 / infinite value; duplicates of a docId allowed = multi-value documents) decoded on
+ * the device into (docId, value) arrays, and range filters over them (NumericFilter::value_in_range, reader/numeric.rs:80-85):
+ * II_NumericList_Filter yields the matching docIds ascending, one per document, as a posting list (freq 1) that takes part in
+ * AND / OR / hybrid pre-filters like a term leaf. */
+typedef struct II_NumericList II_NumericList;
+II_NumericList *II_NumericList_FromBlocks(const II_BlockView *blocks, size_t nblocks);
+size_t II_NumericList_Len(const II_NumericList *nl);
+int II_NumericList_Fetch(const II_NumericList *nl, uint64_t *doc_ids, double *values); /* either may be NULL */
+II_PostingList *II_NumericList_Filter(const II_NumericList *nl, double min, double max, int min_inclusive, int max_inclusive);
+void II_NumericList_Free(II_NumericList *nl);
 /* From already-decoded host arrays (freqs may be NULL = all 1).  docIds strictly ascending. */
 II_PostingList *II_PostingList_FromArrays(const uint64_t *doc_ids, const uint32_t *freqs, size_t n);
 /* Adopt COPIES of device arrays (docIds u32 ascending, freqs u32). */

@@ -144,6 +144,12 @@ size_t orc_intersect_skipto(OrcReader **children, size_t n, const uint64_t *targ
 size_t orc_union_skipto(OrcReader **children, size_t n, const uint64_t *targets, size_t nt, int *status,
                         uint64_t *landed);
 
+/* Numeric codec (RS/inverted_index/src/codec/numeric.rs): one record = header, docId delta (< 2^56), value.  Returns the bytes
+ * written / consumed.  compress_floats selects NumericFloatCompression. */
+size_t orc_numeric_encode(uint64_t delta, double value, int compress_floats, uint8_t *out /* >= 16 bytes */);
+size_t orc_numeric_decode(const uint8_t *in, uint64_t *delta, double *value);
+int orc_numeric_in_range(double value, double min, double max, int min_inclusive, int max_inclusive);
+
 /* IDF (RS/idf/src/lib.rs:36-110). */
 double orc_idf(uint64_t total_docs, uint64_t term_docs);
 double orc_idf_bm25(uint64_t total_docs, uint64_t term_docs);

@@ -1040,3 +1040,105 @@ int orc_within_range(size_t n_children, const uint8_t *const *offsets, const siz
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------ numeric codec ----------- */
+/* RS/inverted_index/src/codec/numeric.rs: header byte = (type-specific << 5) | (type << 3) | delta_bytes, then the docId delta
+ * (0-7 bytes LE, trailing zero bytes trimmed), then the value.  Value::from (:790-838) picks the representation; encode_value
+ * (:363-520) writes it; decode (:553-626) reads it back.  compress_floats = NumericFloatCompression (f32 when the loss is below
+ * 0.01).  Golden bytes: inverted_index/tests/integration/codec/numeric.rs:220-600. */
+static size_t trim_le(uint64_t v, uint8_t *out) { /* little endian without trailing zero bytes; returns the length (0 for 0) */
+    size_t n = 0;
+    while (v) {
+        out[n++] = (uint8_t)v;
+        v >>= 8;
+    }
+    return n;
+}
+size_t orc_numeric_encode(uint64_t delta, double value, int compress_floats, uint8_t *out) {
+    uint8_t dbytes[8], vbytes[8];
+    const size_t nd = trim_le(delta, dbytes); /* callers keep delta below 2^56 (NumericDelta::from_u64 :297-305) */
+    size_t nv = 0;
+    uint8_t type = 0, upper = 0;
+    const double abs_val = fabs(value);
+    /* `abs_val as u64` saturates in Rust: NaN -> 0, >= 2^64 -> u64::MAX */
+    uint64_t u64_val;
+    if (!(abs_val == abs_val))
+        u64_val = 0;
+    else if (abs_val >= 18446744073709551616.0)
+        u64_val = UINT64_MAX;
+    else
+        u64_val = (uint64_t)abs_val;
+    if ((double)u64_val == abs_val) {
+        const uint64_t tiny = u64_val & 7;
+        if ((double)tiny == value) { /* TINY: 0..7 (and -0.0, which compares equal to 0) */
+            type = 0;
+            upper = (uint8_t)u64_val;
+        } else {
+            type = signbit(value) ? 3 : 2; /* INT_NEG / INT_POS: magnitude, trailing zeros trimmed, length - 1 in the header */
+            nv = trim_le(u64_val, vbytes);
+            upper = (uint8_t)(nv - 1);
+        }
+    } else if (isinf(value)) {
+        type = 1;
+        upper = value > 0 ? 1 : 3; /* FLOAT_INFINITE / FLOAT_NEGATIVE_INFINITE */
+    } else {
+        type = 1;
+        const float f32v = (float)abs_val;
+        const double back = (double)f32v;
+        if (back == abs_val || (compress_floats && fabs(abs_val - (double)f32v) < 0.01)) {
+            if (f32v == 0.0f) { /* collapsed onto zero: the canonical zero */
+                type = 0;
+                upper = 0;
+            } else {
+                upper = signbit(value) ? 2 : 0; /* FLOAT32_NEGATIVE / FLOAT32_POSITIVE: the magnitude's f32 bits */
+                memcpy(vbytes, &f32v, 4);
+                nv = 4;
+            }
+        } else {
+            upper = signbit(value) ? 6 : 4; /* FLOAT64_NEGATIVE / FLOAT64_POSITIVE */
+            memcpy(vbytes, &abs_val, 8);
+            nv = 8;
+        }
+    }
+    out[0] = (uint8_t)((upper << 5) | (type << 3) | (uint8_t)nd);
+    memcpy(out + 1, dbytes, nd);
+    memcpy(out + 1 + nd, vbytes, nv);
+    return 1 + nd + nv;
+}
+size_t orc_numeric_decode(const uint8_t *in, uint64_t *delta, double *value) {
+    const uint8_t header = in[0];
+    const size_t nd = header & 7;
+    const uint8_t type = (header >> 3) & 3, upper = header >> 5;
+    uint64_t d = 0;
+    for (size_t i = 0; i < nd; i++) d |= (uint64_t)in[1 + i] << (8 * i);
+    *delta = d;
+    const uint8_t *v = in + 1 + nd;
+    size_t nv = 0;
+    if (type == 0) {
+        *value = (double)upper;
+    } else if (type == 2 || type == 3) {
+        nv = (size_t)upper + 1;
+        uint64_t m = 0;
+        for (size_t i = 0; i < nv; i++) m |= (uint64_t)v[i] << (8 * i);
+        *value = type == 3 ? copysign((double)m, -1.0) : (double)m;
+    } else if (upper == 0 || upper == 2) {
+        float f;
+        memcpy(&f, v, 4);
+        nv = 4;
+        *value = upper == 2 ? (double)copysignf(f, -1.0f) : (double)f;
+    } else if (upper == 4 || upper == 6) {
+        double f;
+        memcpy(&f, v, 8);
+        nv = 8;
+        *value = upper == 6 ? copysign(f, -1.0) : f;
+    } else {
+        *value = (upper == 1 || upper == 5) ? INFINITY : -INFINITY; /* 0b101 / 0b111 are the unused twins (:607-616) */
+    }
+    return 1 + nd + nv;
+}
+/* NumericFilter::value_in_range, RS/inverted_index/src/reader/numeric.rs:80-85 */
+int orc_numeric_in_range(double value, double min, double max, int min_inclusive, int max_inclusive) {
+    const int min_ok = value > min || (min_inclusive && value == min);
+    const int max_ok = value < max || (max_inclusive && value == max);
+    return min_ok && max_ok;
+}

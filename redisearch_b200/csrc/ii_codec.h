@@ -171,4 +171,56 @@ II_HD const uint8_t *ii_decode_record(const uint8_t *p, const uint8_t *end, int 
 #undef II_NEED
 }
 
+// One record of a NUMERIC index block (RS/inverted_index/src/codec/numeric.rs:553-626): header byte = (type-specific << 5) |
+// (type << 3) | delta_bytes; delta (0-7 bytes LE); value: TINY 0-7 in the header, INT_POS / INT_NEG a 1-8 byte magnitude, FLOAT an
+// f32 / f64 magnitude with the sign in the header, or an infinity.  Returns the next record (nullptr past `end` when kChecked).
+template <bool kChecked>
+II_HD const uint8_t *ii_decode_numeric(const uint8_t *p, const uint8_t *end, uint64_t &delta, double &value) {
+    if (kChecked && p >= end) return nullptr;
+    const uint8_t header = *p++;
+    const int nd = header & 7;
+    const int type = (header >> 3) & 3, upper = header >> 5;
+    int nv = 0;
+    if (type == 2 || type == 3)
+        nv = upper + 1;
+    else if (type == 1)
+        nv = (upper == 0 || upper == 2) ? 4 : (upper == 4 || upper == 6) ? 8 : 0;
+    if (kChecked && p + nd + nv > end) return nullptr;
+    uint64_t d = 0;
+    for (int i = 0; i < nd; i++) d |= (uint64_t)p[i] << (8 * i);
+    p += nd;
+    delta = d;
+    uint64_t m = 0;
+    for (int i = 0; i < nv; i++) m |= (uint64_t)p[i] << (8 * i);
+    p += nv;
+    if (type == 0) {
+        value = (double)upper;
+    } else if (type == 2) {
+        value = (double)m;
+    } else if (type == 3) {
+        value = -(double)m; // (num as f64).copysign(-1.0): the magnitude is non-negative
+    } else if (nv == 4) {
+        union { uint32_t u; float f; } c;
+        c.u = (uint32_t)m;
+        const double a = (double)c.f;
+        value = upper == 2 ? -(a < 0 ? -a : a) : a;
+    } else if (nv == 8) {
+        union { uint64_t u; double f; } c;
+        c.u = m;
+        const double a = c.f;
+        value = upper == 6 ? -(a < 0 ? -a : a) : a;
+    } else {
+        union { uint64_t u; double f; } c;
+        c.u = (upper == 1 || upper == 5) ? 0x7FF0000000000000ull : 0xFFF0000000000000ull; // +inf / -inf
+        value = c.f;
+    }
+    return p;
+}
+// NumericFilter::value_in_range, RS/inverted_index/src/reader/numeric.rs:80-85
+II_HD bool ii_numeric_in_range(double value, double min, double max, bool min_inclusive, bool max_inclusive) {
+    const bool min_ok = value > min || (min_inclusive && value == min);
+    const bool max_ok = value < max || (max_inclusive && value == max);
+    return min_ok && max_ok;
+}
+
 } // namespace rsb200

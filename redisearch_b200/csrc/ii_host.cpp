@@ -564,6 +564,110 @@ II_PostingList *II_PostingList_FromDevice(const uint32_t *d_doc_ids, const uint3
     return pl;
 }
 
+// ---- numeric index blocks (RS/inverted_index/src/codec/numeric.rs) -> device (docId, value) arrays; range filters over them
+struct II_NumericList {
+    uint32_t *d_ids = nullptr;
+    double *d_values = nullptr;
+    size_t n = 0;
+    ~II_NumericList() {
+        dfree(d_ids);
+        dfree(d_values);
+    }
+};
+II_NumericList *II_NumericList_FromBlocks(const II_BlockView *blocks, size_t nblocks) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init()) return nullptr;
+    std::vector<uint32_t> entry_off(nblocks + 1, 0);
+    std::vector<uint64_t> byte_off(nblocks + 1, 0), first(nblocks, 0);
+    for (size_t b = 0; b < nblocks; b++) {
+        entry_off[b + 1] = entry_off[b] + blocks[b].num_entries;
+        byte_off[b + 1] = byte_off[b] + blocks[b].len;
+        first[b] = blocks[b].first_doc_id;
+        if (blocks[b].last_doc_id > 0xFFFFFFFEull) return nullptr;
+        // validate on the host what the device decoder trusts: every record stays inside its block
+        const uint8_t *p = blocks[b].data, *end = p + blocks[b].len;
+        for (uint32_t e = 0; e < blocks[b].num_entries; e++) {
+            uint64_t d;
+            double v;
+            p = ii_decode_numeric<true>(p, end, d, v);
+            if (!p) return nullptr;
+        }
+    }
+    const size_t n = entry_off[nblocks], nbytes = byte_off[nblocks];
+    auto *nl = new II_NumericList();
+    nl->n = n;
+    nl->d_ids = dalloc<uint32_t>(n ? n : 1);
+    nl->d_values = dalloc<double>(n ? n : 1);
+    uint8_t *stg = c.stage(nbytes + 16);
+    uint8_t *d_bytes = dalloc<uint8_t>(nbytes + 16);
+    uint64_t *d_boff = dalloc<uint64_t>(nblocks + 1), *d_first = dalloc<uint64_t>(nblocks + 1);
+    uint32_t *d_eoff = dalloc<uint32_t>(nblocks + 1);
+    bool ok = nl->d_ids && nl->d_values && stg && d_bytes && d_boff && d_first && d_eoff;
+    if (ok && n) {
+        for (size_t b = 0; b < nblocks; b++) memcpy(stg + byte_off[b], blocks[b].data, blocks[b].len);
+        ok = cudaMemcpyAsync(d_bytes, stg, nbytes, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(d_boff, byte_off.data(), (nblocks + 1) * 8, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(d_first, first.data(), nblocks * 8, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(d_eoff, entry_off.data(), (nblocks + 1) * 4, cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+        ok = ok && ii_launch_decode_numeric(d_bytes, d_boff, d_first, d_eoff, (uint32_t)nblocks, nl->d_ids, nl->d_values, c.stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+        c.stats.kernel_launches += 1;
+    }
+    dfree(d_bytes);
+    dfree(d_boff);
+    dfree(d_first);
+    dfree(d_eoff);
+    if (!ok) {
+        delete nl;
+        return nullptr;
+    }
+    return nl;
+}
+size_t II_NumericList_Len(const II_NumericList *nl) { return nl->n; }
+void II_NumericList_Free(II_NumericList *nl) { delete nl; }
+int II_NumericList_Fetch(const II_NumericList *nl, uint64_t *doc_ids, double *values) {
+    if (!nl->n) return 0;
+    std::vector<uint32_t> ids(nl->n);
+    bool ok = copy_sync(ids.data(), nl->d_ids, nl->n * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (values) ok = ok && copy_sync(values, nl->d_values, nl->n * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (doc_ids)
+        for (size_t i = 0; i < nl->n; i++) doc_ids[i] = ids[i];
+    return ok ? 0 : -1;
+}
+// FilterNumericReader (reader/numeric.rs:80-170) + one result per document (the numeric iterator skips the further records of a
+// multi-value document): ascending docIds, freq 1.  The list is a term-like leaf for AND / OR / hybrid pre-filters.
+II_PostingList *II_NumericList_Filter(const II_NumericList *nl, double min, double max, int min_inclusive, int max_inclusive) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init() || !nl) return nullptr;
+    const size_t n = nl->n;
+    auto *pl = new II_PostingList();
+    pl->d_ids = dalloc<uint32_t>(n ? n : 1);
+    pl->d_freqs = dalloc<uint32_t>(n ? n : 1);
+    const uint32_t chunks = (uint32_t)((n + 1023) / 1024);
+    uint32_t *d_counts = dalloc<uint32_t>(chunks ? chunks : 1), *d_offs = dalloc<uint32_t>(chunks ? chunks : 1);
+    bool ok = pl->d_ids && pl->d_freqs && d_counts && d_offs;
+    size_t kept = 0;
+    if (ok && n) {
+        ok = ii_launch_numeric_filter(nl->d_ids, nl->d_values, (uint32_t)n, min, max, min_inclusive != 0, max_inclusive != 0, d_counts, d_offs,
+                                      c.d_total, pl->d_ids, pl->d_freqs, c.stream) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(c.h_total, c.d_total, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+        c.stats.kernel_launches += 3;
+        if (ok) kept = *c.h_total;
+        if (ok && kept) ok = copy_sync(&pl->last_id, pl->d_ids + kept - 1, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    dfree(d_counts);
+    dfree(d_offs);
+    if (!ok) {
+        delete pl;
+        return nullptr;
+    }
+    pl->n = pl->estimated = kept;
+    return pl;
+}
+
 // every docId 1..top_id with freq 1 (what a wildcard child contributes to an aggregate)
 static II_PostingList *posting_list_all_docs(uint64_t top_id) {
     if (top_id > 0xFFFFFFFEull) return nullptr;

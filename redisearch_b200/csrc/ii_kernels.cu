@@ -105,6 +105,65 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_blocks_staged_kernel(co
     }
 }
 
+// numeric index blocks -> (docId, value) arrays, one thread per block (records are a dependent chain like the term codecs)
+__global__ void decode_numeric_blocks_kernel(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ byte_off,
+                                             const uint64_t *__restrict__ first_id, const uint32_t *__restrict__ entry_off, uint32_t nblocks,
+                                             uint32_t *__restrict__ out_ids, double *__restrict__ out_values) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const uint8_t *p = bytes + byte_off[b];
+    const uint32_t n = entry_off[b + 1] - entry_off[b];
+    uint32_t o = entry_off[b];
+    uint64_t last = first_id[b];
+    for (uint32_t e = 0; e < n; e++, o++) {
+        uint64_t delta;
+        double v;
+        p = ii_decode_numeric<false>(p, nullptr, delta, v);
+        last += delta;
+        out_ids[o] = (uint32_t)last;
+        out_values[o] = v;
+    }
+}
+// FilterNumericReader + the numeric iterator's one-result-per-document rule (a multi-value document has several records with
+// the same docId, adjacent: the first one in range is the hit): flag, count per chunk, ordered compaction
+__device__ __forceinline__ bool numeric_keep(const uint32_t *ids, const double *values, uint32_t i, double mn, double mx, bool mni, bool mxi) {
+    if (!ii_numeric_in_range(values[i], mn, mx, mni, mxi)) return false;
+    for (uint32_t k = i; k > 0 && ids[k - 1] == ids[i]; k--)
+        if (ii_numeric_in_range(values[k - 1], mn, mx, mni, mxi)) return false; // an earlier record of the same document already hit
+    return true;
+}
+__global__ void numeric_flags_kernel(const uint32_t *__restrict__ ids, const double *__restrict__ values, uint32_t n, double mn, double mx,
+                                     int mni, int mxi, uint32_t *__restrict__ chunk_counts) {
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * 1024u;
+    uint32_t c = 0;
+    for (uint32_t i = threadIdx.x; i < 1024u; i += blockDim.x)
+        if (base + i < n && numeric_keep(ids, values, base + i, mn, mx, mni, mxi)) c++;
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_counts[blockIdx.x] = s_cnt;
+}
+__global__ void numeric_compact_kernel(const uint32_t *__restrict__ ids, const double *__restrict__ values, uint32_t n, double mn, double mx,
+                                       int mni, int mxi, const uint32_t *__restrict__ chunk_off, uint32_t *__restrict__ out_ids,
+                                       uint32_t *__restrict__ out_freqs) {
+    const uint32_t base = blockIdx.x * 1024u;
+    uint32_t o = chunk_off[blockIdx.x];
+    const int lane = threadIdx.x;
+    for (uint32_t i0 = 0; i0 < 1024u; i0 += 32) {
+        const uint32_t i = base + i0 + lane;
+        const bool keep = i < n && numeric_keep(ids, values, i, mn, mx, mni, mxi);
+        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const uint32_t dst = o + __popc(mask & ((1u << lane) - 1u));
+            out_ids[dst] = ids[i];
+            out_freqs[dst] = 1; // RSIndexResult::build_numeric: freq 1
+        }
+        o += __popc(mask);
+    }
+}
+
 // keep records with (mask & filter) != 0, in order: flags -> scan done by the caller (scan_kernel)
 __global__ void mask_flags_kernel(const uint32_t *__restrict__ masks, uint32_t n, uint32_t filter,
                                   uint32_t *__restrict__ chunk_counts) {
@@ -148,6 +207,25 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t 
             hi = mid;
     }
     return lo;
+}
+
+// lower_bound of kIIItems keys at once over the same [0, range) of a shared-memory window: a fixed trip count and no
+// data-dependent branches, so the compiler interleaves the independent chains (one LDS latency per step for all of a thread's
+// entries; the per-entry loop above spent ~20 % of the fused kernel's samples waiting on its compares)
+template <int N>
+__device__ __forceinline__ void lower_bound_lockstep(const uint32_t *w, uint32_t range, const uint32_t (&key)[N], uint32_t (&out)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; i++) out[i] = 0;
+    if (range == 0) return;
+    uint32_t n = range;
+    while (n > 1) {
+        const uint32_t half = n >> 1;
+#pragma unroll
+        for (int i = 0; i < N; i++) out[i] += (w[out[i] + half - 1] < key[i]) ? half : 0u;
+        n -= half;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) out[i] += (w[out[i]] < key[i]) ? 1u : 0u;
 }
 
 // lower_bound by a whole warp: 32 pivots per round instead of one dependent load per bisection step
@@ -755,13 +833,13 @@ __global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQue
             if (j < (int)n) {
                 const uint32_t *W = sB + w_off[j - 1];
                 const uint32_t range = w_len[j - 1];
+                uint32_t p[kIIItems];
+                lower_bound_lockstep<kIIItems>(W, range, doc, p);
 #pragma unroll
-                for (int i = 0; i < kIIItems; i++)
-                    if (alive[i]) {
-                        const uint32_t p = lower_bound_u32(W, 0, range, doc[i]);
-                        alive[i] = (p < range) && W[p] == doc[i];
-                        pos[j - 1][i] = w_lo[j - 1] + p;
-                    }
+                for (int i = 0; i < kIIItems; i++) {
+                    alive[i] = alive[i] && (p[i] < range) && W[min(p[i], range ? range - 1 : 0u)] == doc[i];
+                    pos[j - 1][i] = w_lo[j - 1] + p[i];
+                }
             }
     } else {
         // a window larger than the staging buffer (a short list against a much longer one): list by list, large windows
@@ -775,13 +853,12 @@ __global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQue
             if (range <= (uint32_t)kIISmemElems) {
                 for (uint32_t t = threadIdx.x; t < range; t += kIIThreads) sB[t] = B[lo + t];
                 __syncthreads();
+                uint32_t p[kIIItems];
+                lower_bound_lockstep<kIIItems>(sB, range, doc, p);
 #pragma unroll
                 for (int i = 0; i < kIIItems; i++) {
-                    if (alive[i]) {
-                        const uint32_t p = lower_bound_u32(sB, 0, range, doc[i]);
-                        alive[i] = (p < range) && sB[p] == doc[i];
-                        pos[j - 1][i] = lo + p;
-                    }
+                    alive[i] = alive[i] && (p[i] < range) && sB[min(p[i], range ? range - 1 : 0u)] == doc[i];
+                    pos[j - 1][i] = lo + p[i];
                 }
             } else {
                 // a window far longer than the chunk (a rare term against a frequent one): kPivots evenly spaced entries of the
@@ -911,36 +988,64 @@ __global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQue
     }
 }
 
-// one CTA per query: best top_n of the query's compact candidate list (cand_fill[q] entries at item0 * top_n)
+// one CTA per query: best top_n of the query's compact candidate list (cand_fill[q] entries at item0 * top_n).  After the first
+// fold the current top_n-th best is a threshold: candidates that cannot beat it are dropped on arrival, so a query with tens of
+// thousands of candidates (three frequent terms) folds twice instead of once per 1,792 candidates (ncu: this kernel took 0.55 ms
+// for the whole batch because of that one query)
 __global__ void __launch_bounds__(256) fused_topn_kernel(const FusedQuery *__restrict__ queries, uint32_t top_n,
                                                          const uint64_t *__restrict__ cand_keys, const uint32_t *__restrict__ cand_ids,
                                                          const uint32_t *__restrict__ cand_fill, uint64_t *__restrict__ out_keys,
                                                          uint32_t *__restrict__ out_ids) {
-    constexpr uint32_t kTile = 1024;
+    constexpr uint32_t kTile = 1024, kPerThread = 4;
     __shared__ uint64_t s_keys[2 * kTile];
     __shared__ uint32_t s_ids[2 * kTile];
+    __shared__ uint32_t s_fill;
     const FusedQuery &Q = queries[blockIdx.x];
     const size_t base = (size_t)Q.item0 * top_n;
     const uint32_t total = cand_fill[blockIdx.x];
-    // running best in [0, top_n); the next tile is appended behind it, the buffer sorted, the head kept
+    // running best in [0, top_n); accepted candidates are appended behind it, the buffer sorted, the head kept
     for (uint32_t t = threadIdx.x; t < top_n; t += blockDim.x) s_keys[t] = 0xFFFFFFFFFFFFFFFFull, s_ids[t] = 0xFFFFFFFFu;
-    uint32_t fill = top_n; // block-uniform
-    for (uint32_t off = 0; off < total; off += blockDim.x) {
-        const uint32_t i = off + threadIdx.x;
-        if (i < total) {
-            s_keys[fill + threadIdx.x] = cand_keys[base + i];
-            s_ids[fill + threadIdx.x] = cand_ids[base + i];
+    if (threadIdx.x == 0) s_fill = top_n;
+    __syncthreads();
+    uint32_t fill = top_n; // block-uniform, from the barriers' own counts (s_fill is only ever touched by atomics and the reset)
+    uint64_t thr_key = 0xFFFFFFFFFFFFFFFFull;
+    uint32_t thr_id = 0xFFFFFFFFu;
+    for (uint32_t off = 0; off < total; off += blockDim.x * kPerThread) {
+        uint64_t k[kPerThread];
+        uint32_t id[kPerThread];
+        bool ok[kPerThread];
+#pragma unroll
+        for (uint32_t j = 0; j < kPerThread; j++) { // all loads of the round in flight together
+            const uint32_t i = off + j * blockDim.x + threadIdx.x;
+            ok[j] = i < total;
+            k[j] = ok[j] ? cand_keys[base + i] : 0xFFFFFFFFFFFFFFFFull;
+            id[j] = ok[j] ? cand_ids[base + i] : 0xFFFFFFFFu;
         }
-        fill += min((uint32_t)blockDim.x, total - off);
-        if (fill + blockDim.x > 2 * kTile || off + blockDim.x >= total) { // buffer (nearly) full, or last round: fold
+#pragma unroll
+        for (uint32_t j = 0; j < kPerThread; j++) {
+            const bool take = ok[j] && cand_less(k[j], id[j], thr_key, thr_id);
+            const uint32_t m = __ballot_sync(0xffffffffu, take);
+            uint32_t wbase = 0;
+            if ((threadIdx.x & 31) == 0 && m) wbase = atomicAdd(&s_fill, (uint32_t)__popc(m));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (take) {
+                const uint32_t p = wbase + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+                s_keys[p] = k[j];
+                s_ids[p] = id[j];
+            }
+            fill += (uint32_t)__syncthreads_count(take);
+        }
+        if (fill > kTile || off + blockDim.x * kPerThread >= total) { // no room for another full round, or the last one: fold
             const uint32_t nsort = max(32u, next_pow2(fill));
-            __syncthreads();
             for (uint32_t t = fill + threadIdx.x; t < nsort; t += blockDim.x) s_keys[t] = 0xFFFFFFFFFFFFFFFFull, s_ids[t] = 0xFFFFFFFFu;
             bitonic_sort_pairs(s_keys, s_ids, nsort); // entry syncs inside, one at the end
+            thr_key = s_keys[top_n - 1];
+            thr_id = s_ids[top_n - 1];
+            if (threadIdx.x == 0) s_fill = top_n;
             fill = top_n;
+            __syncthreads();
         }
     }
-    __syncthreads();
     for (uint32_t t = threadIdx.x; t < top_n; t += blockDim.x) {
         out_keys[(size_t)blockIdx.x * top_n + t] = s_keys[t];
         out_ids[(size_t)blockIdx.x * top_n + t] = s_ids[t];
@@ -1232,6 +1337,22 @@ cudaError_t ii_launch_decode_staged(const uint8_t *d_bytes, const uint32_t *d_by
     }
     decode_blocks_staged_kernel<<<(nblocks + kDecodeThreads - 1) / kDecodeThreads, kDecodeThreads, kDecodeSmem, s>>>(
         d_bytes, d_byte_off, d_first_id, d_entry_off, nblocks, codec, d_ids, d_freqs, d_masks, d_off_pos, d_off_len);
+    return cudaGetLastError();
+}
+cudaError_t ii_launch_decode_numeric(const uint8_t *d_bytes, const uint64_t *d_byte_off, const uint64_t *d_first_id, const uint32_t *d_entry_off,
+                                     uint32_t nblocks, uint32_t *d_ids, double *d_values, cudaStream_t s) {
+    if (!nblocks) return cudaSuccess;
+    decode_numeric_blocks_kernel<<<(nblocks + 127) / 128, 128, 0, s>>>(d_bytes, d_byte_off, d_first_id, d_entry_off, nblocks, d_ids, d_values);
+    return cudaGetLastError();
+}
+cudaError_t ii_launch_numeric_filter(const uint32_t *d_ids, const double *d_values, uint32_t n, double mn, double mx, bool min_inclusive,
+                                     bool max_inclusive, uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_total, uint32_t *d_out_ids,
+                                     uint32_t *d_out_freqs, cudaStream_t s) {
+    if (!n) return cudaMemsetAsync(d_total, 0, 4, s);
+    const uint32_t chunks = (n + 1023) / 1024;
+    numeric_flags_kernel<<<chunks, 256, 0, s>>>(d_ids, d_values, n, mn, mx, min_inclusive, max_inclusive, d_counts);
+    scan_kernel<<<1, 1024, 0, s>>>(d_counts, chunks, d_offsets, d_total);
+    numeric_compact_kernel<<<chunks, 32, 0, s>>>(d_ids, d_values, n, mn, mx, min_inclusive, max_inclusive, d_offsets, d_out_ids, d_out_freqs);
     return cudaGetLastError();
 }
 cudaError_t ii_launch_mask_filter(const uint32_t *d_ids, const uint32_t *d_freqs, const uint32_t *d_masks, uint32_t n,

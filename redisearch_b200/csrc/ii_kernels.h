@@ -139,6 +139,13 @@ cudaError_t ii_launch_decode(const uint8_t *d_bytes, const uint64_t *d_byte_off,
 cudaError_t ii_launch_decode_staged(const uint8_t *d_bytes, const uint32_t *d_byte_off, const uint32_t *d_first_id,
                                     const uint32_t *d_entry_off, uint32_t nblocks, int codec, uint32_t *d_ids, uint32_t *d_freqs,
                                     uint32_t *d_masks, uint32_t *d_off_pos, uint32_t *d_off_len, cudaStream_t s);
+// numeric index (RS/inverted_index/src/codec/numeric.rs): blocks -> (docId u32, value f64); range filter -> ordered docIds, one per
+// document (freq 1)
+cudaError_t ii_launch_decode_numeric(const uint8_t *d_bytes, const uint64_t *d_byte_off, const uint64_t *d_first_id, const uint32_t *d_entry_off,
+                                     uint32_t nblocks, uint32_t *d_ids, double *d_values, cudaStream_t s);
+cudaError_t ii_launch_numeric_filter(const uint32_t *d_ids, const double *d_values, uint32_t n, double mn, double mx, bool min_inclusive,
+                                     bool max_inclusive, uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_total, uint32_t *d_out_ids,
+                                     uint32_t *d_out_freqs, cudaStream_t s);
 cudaError_t ii_launch_mask_filter(const uint32_t *d_ids, const uint32_t *d_freqs, const uint32_t *d_masks, uint32_t n,
                                   uint32_t filter, uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_total,
                                   uint32_t *d_out_ids, uint32_t *d_out_freqs, cudaStream_t s);

@@ -91,6 +91,11 @@ SIGNATURES = [
     ("II_MergeShardTopN", _SZ, [_P, _P, _P, _SZ, _SZ, _SZ, _P, _P]),
     ("II_NewResultIterator", _QI, [_P, C.c_double]),
     ("II_IntersectEx", _P, [_P, _P, _SZ]),
+    ("II_NumericList_FromBlocks", _P, [C.POINTER(II_BlockView), _SZ]),
+    ("II_NumericList_Len", _SZ, [_P]),
+    ("II_NumericList_Fetch", C.c_int, [_P, _P, _P]),
+    ("II_NumericList_Filter", _P, [_P, C.c_double, C.c_double, C.c_int, C.c_int]),
+    ("II_NumericList_Free", None, [_P]),
     ("II_NewWildcardIterator", _QI, [C.c_uint64, C.c_double]),
     ("NewWildcardIterator_NonOptimized", _QI, [C.c_uint64, C.c_double]),
     ("II_PostingList_FromBlocksWideMask", _P, [_P, _SZ, C.c_int, _P, C.c_int]),
@@ -175,6 +180,43 @@ class PostingList:
     def __del__(self):
         try:
             self.close()
+        except Exception:
+            pass
+
+
+class NumericList:
+    """II_NumericList: a numeric index leaf decoded on the device"""
+
+    def __init__(self, blocks):
+        self.L = lib()
+        arr = (II_BlockView * max(1, len(blocks)))()
+        self._keep = []
+        for i, (first, last, n, data) in enumerate(blocks):
+            buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+            self._keep.append(buf)
+            arr[i] = II_BlockView(first, last, n, C.cast(buf, C.POINTER(C.c_uint8)), len(data))
+        self.h = self.L.II_NumericList_FromBlocks(arr, len(blocks))
+        if not self.h:
+            raise RuntimeError("II_NumericList_FromBlocks failed")
+
+    def __len__(self):
+        return self.L.II_NumericList_Len(self.h)
+
+    def fetch(self):
+        n = len(self)
+        ids, vals = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.float64)
+        if self.L.II_NumericList_Fetch(self.h, _ptr(ids), _ptr(vals)) != 0:
+            raise RuntimeError("II_NumericList_Fetch failed")
+        return ids, vals
+
+    def filter(self, lo, hi, lo_inclusive=True, hi_inclusive=True):
+        return PostingList(self.L.II_NumericList_Filter(self.h, lo, hi, int(lo_inclusive), int(hi_inclusive)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.II_NumericList_Free(self.h)
+                self.h = None
         except Exception:
             pass
 

@@ -413,6 +413,12 @@ def postings():
         L.orc_ii_fill_synth.argtypes = [_P, C.c_uint64, C.c_uint64]
         L.orc_within_range.restype = C.c_int
         L.orc_within_range.argtypes = [_SZ, _P, _P, C.c_int, C.c_uint32, C.c_int]
+        L.orc_numeric_encode.restype = _SZ
+        L.orc_numeric_encode.argtypes = [C.c_uint64, C.c_double, C.c_int, _P]
+        L.orc_numeric_decode.restype = _SZ
+        L.orc_numeric_decode.argtypes = [_P, _P, _P]
+        L.orc_numeric_in_range.restype = C.c_int
+        L.orc_numeric_in_range.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
         L.orc_min_offset_delta.restype = C.c_int
         L.orc_min_offset_delta.argtypes = [_SZ, _P, _P, _SZ, _P]
         L.orc_time_search3.restype = C.c_double
@@ -496,6 +502,37 @@ def within_range(offset_bytes, max_slop, in_order):
     ptrs = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
     lens = (C.c_size_t * n)(*[len(b) for b in offset_bytes])
     return bool(postings().orc_within_range(n, ptrs, lens, 0 if max_slop is None else 1, 0 if max_slop is None else max_slop, int(in_order)))
+
+
+def numeric_encode(delta, value, compress=False):
+    out = (C.c_uint8 * 24)()
+    n = postings().orc_numeric_encode(delta, value, int(compress), out)
+    return bytes(out[:n])
+
+
+def numeric_decode(data):
+    buf = (C.c_uint8 * (len(data) + 16)).from_buffer_copy(bytes(data) + b"\0" * 16)
+    d, v = C.c_uint64(), C.c_double()
+    n = postings().orc_numeric_decode(buf, C.byref(d), C.byref(v))
+    return n, d.value, v.value
+
+
+def numeric_blocks(doc_ids, values, compress=False, per_block=100):
+    """IndexBlocks of a numeric inverted index (index/core.rs:235-358 with the Numeric encoder: duplicates allowed, 100 entries per
+    block, delta from the previous docId, a fresh block when the delta needs more than 7 bytes): [(first, last, n, bytes)]"""
+    blocks, cur, first, last, n = [], b"", 0, 0, 0
+    for d, v in zip(doc_ids, values):
+        d = int(d)
+        if n == 0 or n >= per_block or (d - last) >> 56:
+            if n:
+                blocks.append((first, last, n, cur))
+            cur, first, last, n = b"", d, d, 0
+        cur += numeric_encode(d - last, float(v), compress)
+        last = d
+        n += 1
+    if n:
+        blocks.append((first, last, n, cur))
+    return blocks
 
 
 def _slop_args(positions, virtual):

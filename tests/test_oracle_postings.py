@@ -383,6 +383,44 @@ def test_proximity_known_answers_of_the_reference():
     assert ol.within_range([enc(300), enc(302)], 1, True) and not ol.within_range([enc(300), enc(303)], 1, True)
 
 
+def test_numeric_codec_golden_bytes():
+    """RS/inverted_index/src/codec/numeric.rs against the byte vectors of inverted_index/tests/integration/codec/numeric.rs:220-600
+    (tiny / positive / negative integers, f32, f64, infinities, 0-7 delta bytes) and its stored-value edge cases (:62-86)."""
+    D7 = 72_057_594_037_927_935
+    f64_3124 = [203, 161, 69, 182, 243, 253, 8, 64]
+    cases = [
+        (0, 2.0, [0b010_00_000]), (2, 7.0, [0b111_00_001, 2]), (D7, 0.0, [0b000_00_111] + [255] * 7), (0, 0.0, [0]), (0, -0.0, [0]),
+        (1, 16.0, [0b000_10_001, 1, 16]), (0, 256.0, [0b001_10_000, 0, 1]), (D7, float(2**64 - 1), [0b111_10_111] + [255] * 15),
+        (0, -16.0, [0b000_11_000, 16]), (1, -16.0, [0b000_11_001, 1, 16]), (0, -256.0, [0b001_11_000, 0, 1]),
+        (D7, -float(2**64 - 1), [0b111_11_111] + [255] * 15),
+        (0, 3.125, [0b000_01_000, 0, 0, 72, 64]), (D7, 3.125, [0b000_01_111] + [255] * 7 + [0, 0, 72, 64]),
+        (0, -3.125, [0b010_01_000, 0, 0, 72, 64]), (D7, -3.125, [0b010_01_111] + [255] * 7 + [0, 0, 72, 64]),
+        (0, math.inf, [0b001_01_000]), (D7, math.inf, [0b001_01_111] + [255] * 7),
+        (0, -math.inf, [0b011_01_000]), (D7, -math.inf, [0b011_01_111] + [255] * 7),
+        (0, 3.124, [0b100_01_000] + f64_3124), (D7, 3.124, [0b100_01_111] + [255] * 7 + f64_3124),
+        (0, -3.124, [0b110_01_000] + f64_3124), (D7, -3.124, [0b110_01_111] + [255] * 7 + f64_3124),
+    ]
+    for delta, value, expected in cases:
+        assert list(ol.numeric_encode(delta, value)) == expected, (delta, value)
+        n, d, v = ol.numeric_decode(bytes(expected))
+        assert n == len(expected) and d == delta and (v == value or abs(value) >= 2.0**63), (delta, value, v)
+    # float compression (numeric.rs:625-700): 3.124 is within 0.01 of its f32, 1e-9 is stored as the canonical zero... only when it
+    # collapses: |1e-9 - f32(1e-9)| < 0.01 and f32(1e-9) != 0 -> f32
+    assert len(ol.numeric_encode(0, 3.124, compress=True)) == 5 and len(ol.numeric_encode(0, 3.124)) == 9
+    n, _, v = ol.numeric_decode(ol.numeric_encode(0, 3.124, compress=True))
+    assert v == float(np.float32(3.124))
+    for value in (0.0, -0.0, 1.0, 7.0, 8.0, -1.0, -8.0, 0.5, -0.5, 100.500001, 1e-9, 9_007_199_254_740_993.0, 4_503_599_627_370_496.0,
+                  1.7976931348623157e308, -1.7976931348623157e308, 2.2250738585072014e-308, math.inf, -math.inf):
+        for compress in (False, True):
+            n, _, v = ol.numeric_decode(ol.numeric_encode(5, value, compress))
+            if not compress or value in (math.inf, -math.inf):
+                assert v == value and (math.copysign(1, v) == math.copysign(1, value) or value == 0)
+            else:
+                assert abs(v - value) < 0.01
+            # stored_value is idempotent (numeric.rs:44-57)
+            assert ol.numeric_decode(ol.numeric_encode(0, v, compress))[2] == v
+
+
 def test_min_offset_delta_equals_the_reference():
     """GetSlop of the legacy scorers: the restatement against the reference's own index_result.c, and its doc-comment example."""
     assert ol.min_offset_delta([[2, 4, 8], [0, 5, 12]]) == 1           # index_result.c:47-50: abs(4-5)

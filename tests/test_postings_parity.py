@@ -942,3 +942,87 @@ def test_phrase_constructor_takes_slop_and_in_order(ps):
         lf.contents.Free(lf)
     libc.free.argtypes = [C.c_void_p]
     libc.free(arr)
+
+
+def test_wildcard_children_of_the_constructors(ps):
+    """A wildcard child (rqe_iterators/src/wildcard.rs) under the constructors: stripped by an AND (intersection.rs:363-417), it
+    takes over a quick OR (union_reducer.rs:41-53), and inside a full OR it contributes every docId 1..top_id."""
+    rng = np.random.default_rng(77)
+    top = 5000
+    a = np.unique(rng.integers(1, top, 700)).astype(np.uint64)
+    b = np.unique(rng.integers(1, top, 900)).astype(np.uint64)
+    pa, pb = ps.PostingList.from_arrays(a), ps.PostingList.from_arrays(b)
+    L = ps.lib()
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+
+    def its_of(children):
+        arr = libc.malloc(8 * len(children))
+        view = (C.c_void_p * len(children)).from_address(arr)
+        for i, c in enumerate(children):
+            view[i] = C.cast(c, C.c_void_p).value
+        return arr
+
+    def drain(qi):
+        got = []
+        while qi.contents.Read(qi) == 0:
+            got.append(qi.contents.lastDocId)
+        qi.contents.Free(qi)
+        return got
+
+    leaf = lambda p: L.II_NewTermIterator(p.h, 0, 1.0, 1.0, 1.0)
+    # AND(a, *, b) == AND(a, b)
+    qi = L.NewIntersectionIterator(its_of([leaf(pa), L.II_NewWildcardIterator(top, 1.0), leaf(pb)]), 3, -1, False, 1.0)
+    assert drain(qi) == np.intersect1d(a, b).tolist()
+    # quick OR with a wildcard child IS the wildcard
+    qi = L.NewUnionIterator(its_of([leaf(pa), L.II_NewWildcardIterator(top, 1.0)]), 2, True, 1.0, 0, None, None)
+    assert qi.contents.type == 12 and drain(qi) == list(range(1, top + 1))
+    # full OR: every document, the term children's freqs where present
+    qi = L.NewUnionIterator(its_of([leaf(pa), L.II_NewWildcardIterator(top, 1.0), leaf(pb)]), 3, False, 1.0, 0, None, None)
+    assert qi.contents.type == 6 and drain(qi) == list(range(1, top + 1))
+
+
+@pytest.mark.parametrize("compress", [False, True])
+def test_numeric_index_decode_and_range_filter(ps, compress):
+    """Numeric index leaves (RS/inverted_index/src/codec/numeric.rs) decoded on the device and filtered by range
+    (NumericFilter::value_in_range, reader/numeric.rs:80-85): values bit-equal to the oracle decoder for every value class (tiny,
+    +/- integers, f32, f64, infinities), multi-value documents (repeated docIds) yield one hit, and the filtered list intersects
+    with a term list like any leaf (the hybrid pre-filter shape)."""
+    rng = np.random.default_rng(2024 + compress)
+    n = 40_000
+    ids = np.cumsum(rng.integers(0, 4, n)) + 1  # steps of 0: multi-value documents
+    pool = np.concatenate([rng.integers(0, 8, n // 4).astype(np.float64), rng.integers(-5000, 70_000, n // 4).astype(np.float64),
+                           rng.integers(0, 200, n // 4) * 0.125, rng.normal(0, 50, n - 3 * (n // 4))])
+    rng.shuffle(pool)
+    pool[:6] = [np.inf, -np.inf, -0.0, 2.0**60, -(2.0**40), 1e-9]
+    blocks = ol.numeric_blocks(ids.tolist(), pool.tolist(), compress)
+    exp_vals = []
+    for first, last, cnt, data in blocks:  # what the reference's decoder returns for these bytes
+        pos = 0
+        for _ in range(cnt):
+            used, _, v = ol.numeric_decode(data[pos:])
+            pos += used
+            exp_vals.append(v)
+        assert pos == len(data)
+    nl = ps.NumericList(blocks)
+    got_ids, got_vals = nl.fetch()
+    assert got_ids.tolist() == ids.tolist()
+    assert got_vals.tobytes() == np.array(exp_vals, dtype=np.float64).tobytes()
+    P = ol.postings()
+    term = np.unique(rng.integers(1, int(ids[-1]), 9000)).astype(np.uint64)
+    tl = ps.PostingList.from_arrays(term)
+    for lo, hi, li, hi_i in ((0.0, 7.0, True, True), (0.0, 7.0, False, False), (-np.inf, np.inf, True, True), (-100.5, 12.125, True, False),
+                             (3.0, 3.0, True, True), (5.0, 1.0, True, True), (2.0**60, np.inf, True, False)):
+        pl = nl.filter(lo, hi, li, hi_i)
+        seen, exp = set(), []
+        for d, v in zip(ids.tolist(), exp_vals):
+            if d not in seen and P.orc_numeric_in_range(v, lo, hi, int(li), int(hi_i)):
+                seen.add(d)
+                exp.append(d)
+        assert len(pl) == len(exp), (lo, hi, li, hi_i)
+        if exp:
+            got, _, fr = ps.union([pl]).fetch()
+            assert got.tolist() == exp and (fr[0] == 1).all()
+            both, _, _ = ps.intersect([pl, tl]).fetch()
+            assert both.tolist() == np.intersect1d(np.array(exp, dtype=np.uint64), term).tolist()
