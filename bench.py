@@ -676,11 +676,19 @@ def run_config3(args):
                 order = np.lexsort((ids, sc))[:k]
                 local.append((ids[order], sc[order]))
         dl, ds = out_labels.cpu().numpy(), out_scores.cpu().numpy()
-        worst, id_overlap = 0.0, 1.0
+        # |delta| <= tol * max(|d_ref|, scale), tol = 1e-2 for fp16; scale = |q||x| for raw inner products (~256 for
+        # these rows).  The check below uses the STRICTER scale 1: a pass here is a pass of the survey's bar.  (The reference's own
+        # tiers differ from each other at this level: the AVX512-FP16 tier accumulates in half precision, SURVEY finding 5.)
+        worst, worst_rel, id_overlap = 0.0, 0.0, 1.0
         for i, q in enumerate(pick):
-            worst = max(worst, float(np.abs(ds[q] - local[i][1].astype(np.float32)).max()))
+            ref = local[i][1].astype(np.float32)
+            diff = np.abs(ds[q] - ref)
+            worst = max(worst, float(diff.max()))
+            worst_rel = max(worst_rel, float((diff / np.maximum(np.abs(ref), 1.0)).max()))
             id_overlap = min(id_overlap, len(set(dl[q].tolist()) & set(local[i][0].tolist())) / k)
-        parity = {"queries": 8, "max_abs_score_diff": worst, "tolerance": 1e-2, "within_tolerance": worst <= 1e-2, "min_id_overlap": id_overlap,
+        parity = {"queries": 8, "max_abs_score_diff": worst, "max_rel_score_diff": worst_rel, "tolerance": 1e-2,
+                  "tolerance_is": "relative: |delta| <= 1e-2 * max(|d_ref|, 1)", "within_tolerance": worst_rel <= 1e-2,
+                  "min_id_overlap": id_overlap,
                   "checker": f"{chk_kind}: reference fp16 distance kernel (the CPU's own tier) + heap over the device's rows"}
     tpeak, tsust, tsrc = load_tensor_peak()
     flops = 2.0 * nq * rows * DIM

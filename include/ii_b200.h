@@ -182,9 +182,12 @@ typedef struct II_ResultSet II_ResultSet;
  * num_estimated ascending, stable, exactly like Intersection::new (:103-169); per-hit child freqs
  * are kept in that order for the scorers. */
 II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n);
-/* OR of n (1..32) posting lists — UnionFlat::read_full (RS/rqe_iterators/src/union_flat.rs:324-348; above
- * min_union_iter_heap = 20 children the reference picks union_heap.rs: same docIds, same aggregate per docId)
- * run to EOF; quick_exit != 0 keeps docIds only (quick mode reports a single child, :433-524). */
+/* OR of n (1..1024) posting lists run to EOF — a prefix / fuzzy expansion is a union of up to MAXEXPANSIONS (200) terms.
+ * Up to min_union_iter_heap = 20 children the reference uses UnionFlat (RS/rqe_iterators/src/union_flat.rs:324-348): the per-hit
+ * children come back in ITS aggregate order (the active array after swap_remove_child :174-180), so scores are bit-equal.  Above
+ * 20 it uses UnionHeap (union_heap.rs), whose aggregate order follows the heap array: same docIds, same children per docId, the
+ * scorer's sum is taken in list order here (last-bit differences possible).  quick_exit != 0 keeps docIds only (quick mode
+ * reports a single child, union_flat.rs:433-524). */
 II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit);
 /* AND with NOT / OPTIONAL children — the "a -b" / "a ~b" query shapes (RS/rqe_iterators/src/not.rs, optional.rs as children of
  * an Intersection): modes[i] 0 = required, 1 = NOT (docIds of lists[i] are excluded), 2 = OPTIONAL (never rejects; where

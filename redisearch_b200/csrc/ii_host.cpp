@@ -172,7 +172,7 @@ struct II_ResultSet {
     uint32_t *d_len = nullptr; // hit count on the device (valid in stream order right after the AND/OR kernels)
     size_t cap = 0, len = 0;
     uint32_t n_children = 0;
-    uint32_t child_order[kIIMaxLists] = {0};
+    std::vector<uint32_t> child_order; // aggregate child i = lists[child_order[i]]
     bool is_union = false, has_freqs = true, scored = false;
     // term positions of the hits, kept when a child list carries them: GetSlop of the legacy scorers walks them
     // (IndexResult_MinOffsetDelta, src/index_result/index_result.c:51-108) the first time such a scorer is asked for
@@ -182,7 +182,9 @@ struct II_ResultSet {
         const uint8_t *bytes = nullptr;
         const uint32_t *off_pos = nullptr, *off_len = nullptr;
         std::shared_ptr<SharedDeviceBlock> keep_tables, keep_bytes; // the lists may be released before the scorer runs
-    } child_off[kIIMaxLists];
+    };
+    std::vector<ChildOffsets> child_off;
+    double *d_ext = nullptr; // wide unions: the scorer's per-child tables in device memory (ScoreArgs::ext)
     UnionOrder *d_order = nullptr; // unions: the reference's aggregate child order per docId epoch
     ~II_ResultSet() {
         dfree(d_docs);
@@ -192,6 +194,7 @@ struct II_ResultSet {
         dfree(d_hit_pos);
         dfree(d_slop);
         dfree(d_order);
+        dfree(d_ext);
     }
 };
 
@@ -786,7 +789,8 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
         if (mode_of(order[i]) == 0 && (drv == n || lists[order[i]]->n < lists[order[drv]]->n)) drv = i;
     if (drv == n) return false;
     rs->n_children = (uint32_t)n;
-    for (size_t i = 0; i < n; i++) rs->child_order[i] = order[i];
+    rs->child_order.assign(order.begin(), order.end());
+    rs->child_off.assign(n, II_ResultSet::ChildOffsets());
     *trivially_empty = false;
     for (size_t i = 0; i < n; i++) *trivially_empty |= mode_of(i) == 0 && lists[i]->n == 0;
     if (*trivially_empty) return true;
@@ -924,7 +928,9 @@ bool union_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int quick_exi
     rs->is_union = true;
     rs->n_children = (uint32_t)n;
     rs->has_freqs = !quick_exit;
+    rs->child_order.resize(n);
     for (size_t i = 0; i < n; i++) rs->child_order[i] = (uint32_t)i;
+    rs->child_off.assign(n, II_ResultSet::ChildOffsets());
     uint32_t max_id = 0;
     size_t total_in = 0;
     for (size_t i = 0; i < n; i++) {
@@ -947,7 +953,8 @@ bool union_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int quick_exi
     // swapped-in child examined at once.  (Above min_union_iter_heap = 20 children the reference uses UnionHeap, whose
     // aggregate order follows its heap array: same docIds and children, sums may differ in the last bit.)
     UnionOrder uo{};
-    if (rs->has_freqs) {
+    const bool flat_order = rs->has_freqs && n <= (size_t)kIIUnionFlatMax; // more children: UnionHeap, whose order follows its heap array
+    if (flat_order) {
         std::vector<uint32_t> active(n);
         for (size_t i = 0; i < n; i++) active[i] = (uint32_t)i;
         size_t num_active = n;
@@ -974,10 +981,10 @@ bool union_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int quick_exi
         rs->d_order = dalloc<UnionOrder>(1);
     }
     bool keep_pos = false;
-    for (size_t i = 0; i < n && n > 1 && rs->has_freqs; i++) keep_pos |= lists[i]->d_off_len != nullptr;
+    for (size_t i = 0; i < n && n > 1 && n <= (size_t)kIIMaxLists && rs->has_freqs; i++) keep_pos |= lists[i]->d_off_len != nullptr;
     if (keep_pos) rs->d_hit_pos = dalloc<uint32_t>(rs->cap * n);
     bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && rs->d_len && bitmap && blocksum && blockoff && wordoff &&
-              (!rs->has_freqs || rs->d_order) && (!keep_pos || rs->d_hit_pos);
+              (!flat_order || rs->d_order) && (!keep_pos || rs->d_hit_pos);
     if (ok) {
         std::vector<const uint32_t *> ids(n), freqs(n);
         std::vector<uint32_t> lens(n);
@@ -1023,17 +1030,32 @@ void finish_len(Ctx &c, II_ResultSet *rs) {
     if (cudaEventElapsedTime(&ms, c.e0, c.e1) == cudaSuccess) c.stats.intersect_device_us = ms * 1000.0;
 }
 
-ScoreArgs make_score_args(const II_ResultSet *rs, II_Scorer scorer, const II_TermParams *terms, double agg_weight,
+ScoreArgs make_score_args(II_ResultSet *rs, II_Scorer scorer, const II_TermParams *terms, double agg_weight,
                           const II_IndexStats *stats, const II_DocTable *docs, double min_score, uint64_t tanh_factor) {
     ScoreArgs sa{};
     sa.scorer = (int)scorer;
     sa.is_union = rs->is_union;
     sa.n_children = rs->n_children;
-    for (uint32_t i = 0; i < rs->n_children; i++) {
-        const II_TermParams &t = terms[rs->child_order[i]];
-        sa.weight[i] = t.weight;
-        sa.idf[i] = t.idf;
-        sa.bm25_idf[i] = t.bm25_idf;
+    if (rs->n_children <= (uint32_t)kIIMaxLists) {
+        for (uint32_t i = 0; i < rs->n_children; i++) {
+            const II_TermParams &t = terms[rs->child_order[i]];
+            sa.weight[i] = t.weight;
+            sa.idf[i] = t.idf;
+            sa.bm25_idf[i] = t.bm25_idf;
+        }
+    } else { // a wide union: the tables do not fit the kernel arguments (pageable source: staged before the copy call returns)
+        const uint32_t n = rs->n_children;
+        std::vector<double> ext(3 * (size_t)n);
+        for (uint32_t i = 0; i < n; i++) {
+            const II_TermParams &t = terms[rs->child_order[i]];
+            ext[i] = t.weight;
+            ext[n + i] = t.idf;
+            ext[2 * (size_t)n + i] = t.bm25_idf;
+        }
+        if (!rs->d_ext) rs->d_ext = dalloc<double>(ext.size());
+        if (rs->d_ext) cudaMemcpyAsync(rs->d_ext, ext.data(), ext.size() * 8, cudaMemcpyHostToDevice, ctx().stream);
+        sa.ext = rs->d_ext;
+        sa.n_children = rs->d_ext ? n : 0; // no table, no children: the launch scores nothing rather than reading past the inline arrays
     }
     sa.agg_weight = agg_weight;
     sa.avg_doc_len = stats ? stats->avgDocLen : 0.0;
@@ -1209,7 +1231,7 @@ II_ResultSet *II_IntersectPhrase(II_PostingList *const *lists, const int *modes,
 }
 
 II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit) {
-    if (n == 0 || n > (size_t)kIIMaxLists) return nullptr;
+    if (n == 0 || n > (size_t)kIIMaxUnionLists) return nullptr;
     Ctx &c = ctx();
     std::lock_guard<std::mutex> g(c.mu);
     if (!c.init()) return nullptr;
@@ -1379,7 +1401,7 @@ size_t II_SearchTopN(II_PostingList *const *lists, size_t n, int is_union, II_Sc
                      double agg_weight, const II_IndexStats *stats, const II_DocTable *docs, size_t top_n, uint64_t *doc_ids,
                      double *scores, size_t *total_hits) {
     if (total_hits) *total_hits = 0;
-    if (n == 0 || n > (size_t)kIIMaxLists || top_n == 0) return 0;
+    if (n == 0 || n > (size_t)(is_union ? kIIMaxUnionLists : kIIMaxLists) || top_n == 0) return 0;
     if (top_n > 1024) { // wide LIMITs take the unfused route
         II_ResultSet *rs = is_union ? II_Union(lists, n, 0) : II_Intersect(lists, n);
         if (!rs) return 0;
@@ -1579,7 +1601,7 @@ int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const siz
     }();
     std::vector<size_t> fusable, rest;
     for (size_t i = 0; i < nq; i++) {
-        if (n_lists[i] == 0 || n_lists[i] > (size_t)kIIMaxLists) continue;
+        if (n_lists[i] == 0 || n_lists[i] > (size_t)(is_union ? kIIMaxUnionLists : kIIMaxLists)) continue;
         bool empty = false;
         for (size_t t = 0; t < n_lists[i]; t++) empty |= lists[i][t]->n == 0;
         if (!is_union && empty) continue; // an empty child: the AND is empty (intersection.rs:363-417)
@@ -2350,7 +2372,7 @@ static II_QueryIterator *build_aggregate(II_QueryIterator **its, size_t num, boo
         host_free(its);
         return keep;
     }
-    if (kids.size() > (size_t)kIIMaxLists) {
+    if (kids.size() > (size_t)(is_union ? kIIMaxUnionLists : kIIMaxLists)) {
         free_children();
         return nullptr;
     }

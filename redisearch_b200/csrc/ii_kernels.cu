@@ -410,6 +410,9 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
     const uint32_t doc_len = s.doc_len ? s.doc_len[doc] : 0u;
     const ChildOrder co = child_order_of(s.is_union ? s.order : nullptr, s.n_children, doc);
 #define II_FOR_CHILDREN(c) for (uint32_t ci_ = 0, c = 0; ci_ < co.n && ((c = co.perm ? co.perm[ci_] : ci_), true); ci_++)
+#define II_W(c) (s.ext ? s.ext[c] : s.weight[c])
+#define II_IDF(c) (s.ext ? s.ext[s.n_children + (c)] : s.idf[c])
+#define II_BIDF(c) (s.ext ? s.ext[2 * s.n_children + (c)] : s.bm25_idf[c])
     uint32_t slop = 1;
     if (s.scorer >= 1 && s.scorer <= 3) { // the legacy scorers divide by GetSlop (:130-131, :226-227)
         if (s.slop) {
@@ -428,7 +431,7 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
         double ret = 0;
         II_FOR_CHILDREN(c) {
             const uint32_t f = freqs[c * fstride + o];
-            if (f) ret = __dadd_rn(ret, bm25std_leaf(s.bm25_idf[c], (double)f, (int)doc_len, s.avg_doc_len, s.weight[c]));
+            if (f) ret = __dadd_rn(ret, bm25std_leaf(II_BIDF(c), (double)f, (int)doc_len, s.avg_doc_len, II_W(c)));
         }
         ret = __dmul_rn(ret, s.agg_weight);
         const double score = __dmul_rn((double)doc_score, ret);
@@ -439,7 +442,7 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
         double ret = 0;
         II_FOR_CHILDREN(c) {
             const uint32_t f = freqs[c * fstride + o];
-            if (f) ret = __dadd_rn(ret, bm25_leaf(s.idf[c], (double)f, s.avg_doc_len, s.weight[c]));
+            if (f) ret = __dadd_rn(ret, bm25_leaf(II_IDF(c), (double)f, s.avg_doc_len, II_W(c)));
         }
         ret = __dmul_rn(ret, s.agg_weight);
         const double score = __dmul_rn((double)doc_score, ret);
@@ -454,7 +457,7 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
         double raw = 0;
         II_FOR_CHILDREN(c) {
             const uint32_t f = freqs[c * fstride + o];
-            if (f) raw = __dadd_rn(raw, __dmul_rn(__dmul_rn(s.weight[c], (double)f), s.idf[c]));
+            if (f) raw = __dadd_rn(raw, __dmul_rn(__dmul_rn(II_W(c), (double)f), II_IDF(c)));
         }
         raw = __dmul_rn(s.agg_weight, raw);
         const double tfidf = __ddiv_rn(__dmul_rn((double)doc_score, raw), (double)norm);
@@ -467,7 +470,7 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
         II_FOR_CHILDREN(c) {
             const uint32_t f = freqs[c * fstride + o];
             if (!f) continue;
-            const double leaf = __dmul_rn(s.weight[c], (double)f);
+            const double leaf = __dmul_rn(II_W(c), (double)f);
             if (s.is_union)
                 ret = (leaf > ret) ? leaf : ret;
             else
@@ -477,6 +480,9 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
     }
     }
 #undef II_FOR_CHILDREN
+#undef II_W
+#undef II_IDF
+#undef II_BIDF
     return 0.0;
 }
 

@@ -10,7 +10,10 @@ constexpr int kIIThreads = 256;
 constexpr int kIIItems = 4;
 constexpr int kIIChunk = kIIThreads * kIIItems; // entries of the driving list per CTA
 constexpr int kIISmemElems = 8192;              // 32 KB window of the probed list staged per CTA
-constexpr int kIIMaxLists = 32; // children of one AND / OR (the reference switches its union to the heap variant above 20: same docIds)
+constexpr int kIIMaxLists = 32;        // children of one AND (kernel argument tables)
+constexpr int kIIMaxUnionLists = 1024; // children of one OR: a prefix / fuzzy / wildcard expansion is a union of up to MAXEXPANSIONS
+                                       // (default 200) terms; the union kernels take one list per launch and need no tables
+constexpr int kIIUnionFlatMax = 20;    // above it the reference's union is UnionHeap (min_union_iter_heap, union_reducer.rs:106)
 
 struct IntersectArgs {
     const uint32_t *ids[kIIMaxLists]; // [0] = the shortest list (drives), others ascending by length
@@ -96,6 +99,8 @@ struct ScoreArgs {
     // else the value IndexResult_MinOffsetDelta returns without offsets: children - 1 (1 for a single child)
     const uint32_t *slop;      // per hit, may be NULL
     const UnionOrder *order;   // unions: child order per docId epoch (device memory), may be NULL
+    const double *ext;         // more than kIIMaxLists children (unions): weight[n], idf[n], bm25_idf[n] in device memory instead of
+                               // the inline tables above
 };
 
 // ---- fused batch search: AND + scorer + top-N of MANY queries in two launches --------------------------------------

@@ -1026,3 +1026,35 @@ def test_numeric_index_decode_and_range_filter(ps, compress):
             assert got.tolist() == exp and (fr[0] == 1).all()
             both, _, _ = ps.intersect([pl, tl]).fetch()
             assert both.tolist() == np.intersect1d(np.array(exp, dtype=np.uint64), term).tolist()
+
+
+def test_union_of_an_expansion_sized_child_set(ps):
+    """A prefix / fuzzy expansion is a union of up to MAXEXPANSIONS (200) terms: docIds = the set union, per-child freqs exact,
+    BM25STD = the scorer oracle over the present children (the reference runs UnionHeap above 20 children, whose aggregate
+    order follows its heap array: the sum may differ from list order in the last bits, hence 1e-13 relative here)."""
+    rng = np.random.default_rng(404)
+    n_docs, n_children = 200_000, 200
+    lists = [np.unique(rng.integers(1, n_docs, int(rng.integers(1, 4000)))).astype(np.uint64) for _ in range(n_children)]
+    freqs = [rng.integers(1, 30, len(l)).astype(np.uint32) for l in lists]
+    pls = [ps.PostingList.from_arrays(l, f) for l, f in zip(lists, freqs)]
+    doc_len = rng.integers(1, 900, n_docs + 1).astype(np.uint32)
+    dt = ps.DocTable(n_docs, doc_len)
+    P = ol.postings()
+    terms = [(float(rng.choice([1.0, 0.5, 2.0])), P.orc_idf(n_docs, len(l)), P.orc_idf_bm25(n_docs, len(l))) for l in lists]
+    rs = ps.union(pls)
+    rs.score(ps.SCORER_BM25STD, terms, 0.9, n_docs, 300.0, dt)
+    ids, scores, fr = rs.fetch()
+    assert ids.tolist() == np.unique(np.concatenate(lists)).tolist()
+    maps = [dict(zip(l.tolist(), f.tolist())) for l, f in zip(lists, freqs)]
+    for i in range(0, len(ids), max(1, len(ids) // 150)):
+        d = int(ids[i])
+        present = [c for c in range(n_children) if d in maps[c]]
+        assert [int(fr[c, i]) for c in present] == [maps[c][d] for c in present] and int(fr[:, i].astype(bool).sum()) == len(present)
+        s = ol.oracle_score(ol.SCORER_BM25STD, [maps[c][d] for c in present], [terms[c][1] for c in present], [terms[c][2] for c in present],
+                            [terms[c][0] for c in present], 0.9, int(doc_len[d]), 1, 1.0, n_docs, 300.0)
+        assert abs(s - scores[i]) <= 1e-13 * max(1.0, abs(s)), (d, s, scores[i])
+    quick, _, _ = ps.union(pls, quick_exit=True).fetch(want_freqs=False)
+    assert quick.tolist() == ids.tolist()
+    top_ids, top_scores, total = ps.search_topn(pls, True, ps.SCORER_BM25STD, terms, 0.9, n_docs, 300.0, dt, 10)
+    order = np.lexsort((ids, -scores))[:10]
+    assert total == len(ids) and top_ids.tolist() == ids[order].tolist()
