@@ -189,6 +189,9 @@ II_ResultSet *II_Intersect(II_PostingList *const *lists, size_t n);
  * scorer's sum is taken in list order here (last-bit differences possible).  quick_exit != 0 keeps docIds only (quick mode
  * reports a single child, union_flat.rs:433-524). */
 II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit);
+/* nq independent ANDs in one call (e.g. the pre-filters of a batch of hybrid queries): all of them are enqueued, each on its own
+ * stream, before anything is waited for.  out[i] = the result set of lists[i][0 .. n_lists[i]) or NULL; returns how many were built. */
+size_t II_IntersectBatch(size_t nq, II_PostingList *const *const *lists, const size_t *n_lists, II_ResultSet **out);
 /* AND with NOT / OPTIONAL children — the "a -b" / "a ~b" query shapes (RS/rqe_iterators/src/not.rs, optional.rs as children of
  * an Intersection): modes[i] 0 = required, 1 = NOT (docIds of lists[i] are excluded), 2 = OPTIONAL (never rejects; where
  * the docId is present its freq is kept).  Excluded / absent children yield the reference's virtual results: freq 0, no

@@ -514,6 +514,11 @@ int VecSimB200_HybridTopK(VecSimIndex *index, const void *queryBlob, size_t k, v
  * labels too sparse for the dense docId -> row table) — the caller then stays on VecSimIndex_GetDistanceFrom_Unsafe. */
 int VecSimB200_TopKFiltered(VecSimIndex *index, const void *queryBlob, size_t k, const uint32_t *doc_ids, size_t n, int ids_on_device,
                             size_t *out_labels, double *out_scores, size_t *out_count);
+/* The same for nq hybrid queries in one call (k <= 128): queryBlobs[i] with the DEVICE-resident ascending docId list
+ * d_doc_ids[i] of counts[i] entries (its filter's AND / OR result).  Every query's kernel chain is enqueued on its own stream
+ * before anything is waited for.  out_labels / out_scores are [nq][k], out_counts[i] the entries written for query i. */
+int VecSimB200_TopKFilteredBatch(VecSimIndex *index, const void *const *queryBlobs, size_t nq, size_t k, const uint32_t *const *d_doc_ids,
+                                 const size_t *counts, size_t *out_labels, double *out_scores, size_t *out_counts);
 /* Batched fp32 queries (cosine, and in mode 1 also L2 and raw inner product; nq >= 16, k <= 16, dim % 8 == 0,
  * >= 65536 rows) take a tcgen05 coarse
  * pass + exact rescoring from the fp32 rows + a per-query completeness proof, with the exact scan as

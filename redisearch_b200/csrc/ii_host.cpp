@@ -1230,6 +1230,60 @@ II_ResultSet *II_IntersectPhrase(II_PostingList *const *lists, const int *modes,
     return rs;
 }
 
+// nq independent ANDs in one call (the filters of a batch of hybrid queries): every intersection is enqueued on its own stream
+// before anything is waited for; out[i] = NULL where it could not be built (an empty child yields an empty result set).
+size_t II_IntersectBatch(size_t nq, II_PostingList *const *const *lists, const size_t *n_lists, II_ResultSet **out) {
+    constexpr size_t kSlots = 16;
+    struct Pool {
+        std::mutex mu;
+        Ctx slot[kSlots];
+    };
+    static Pool pool;
+    std::lock_guard<std::mutex> g(pool.mu);
+    size_t built = 0;
+    for (size_t q0 = 0; q0 < nq; q0 += kSlots) {
+        const size_t q1 = std::min(nq, q0 + kSlots);
+        bool pending[kSlots] = {false};
+        for (size_t qi = q0; qi < q1; qi++) {
+            out[qi] = nullptr;
+            const size_t sl = qi - q0, n = n_lists[qi];
+            if (n == 0 || n > (size_t)kIIMaxLists) continue;
+            CtxScope scope(&pool.slot[sl]);
+            Ctx &c = pool.slot[sl];
+            if (!c.init()) continue;
+            auto *rs = new II_ResultSet();
+            bool empty = false;
+            bool ok = intersect_enqueue(c, lists[qi], n, rs, &empty);
+            if (ok && !empty) {
+                ok = cudaMemcpyAsync(c.h_total, rs->d_len, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+                pending[sl] = ok;
+            }
+            if (!ok) {
+                cudaStreamSynchronize(c.stream);
+                delete rs;
+                continue;
+            }
+            out[qi] = rs;
+        }
+        for (size_t qi = q0; qi < q1; qi++) {
+            const size_t sl = qi - q0;
+            if (!out[qi]) continue;
+            CtxScope scope(&pool.slot[sl]);
+            Ctx &c = pool.slot[sl];
+            if (pending[sl]) {
+                if (cudaStreamSynchronize(c.stream) != cudaSuccess) {
+                    delete out[qi];
+                    out[qi] = nullptr;
+                    continue;
+                }
+                finish_len(c, out[qi]);
+            }
+            built++;
+        }
+    }
+    return built;
+}
+
 II_ResultSet *II_Union(II_PostingList *const *lists, size_t n, int quick_exit) {
     if (n == 0 || n > (size_t)kIIMaxUnionLists) return nullptr;
     Ctx &c = ctx();

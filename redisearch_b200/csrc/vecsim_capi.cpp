@@ -276,6 +276,10 @@ int VecSimB200_TopKFiltered(VecSimIndex *index, const void *queryBlob, size_t k,
     size_t dummy = 0;
     return IX(index)->topk_filtered(queryBlob, k, doc_ids, n, ids_on_device != 0, out_labels, out_scores, out_count ? out_count : &dummy);
 }
+int VecSimB200_TopKFilteredBatch(VecSimIndex *index, const void *const *queryBlobs, size_t nq, size_t k, const uint32_t *const *d_doc_ids,
+                                 const size_t *counts, size_t *out_labels, double *out_scores, size_t *out_counts) {
+    return IX(index)->topk_filtered_batch(queryBlobs, nq, k, d_doc_ids, counts, out_labels, out_scores, out_counts);
+}
 int VecSimB200_LastBatchPath(VecSimIndex *index) { return IX(index)->last_batch_path(); }
 void VecSimB200_SetCoarseMode(int mode) { rsb200::set_coarse_mode(mode); }
 int VecSimB200_LastCoarseFlags(VecSimIndex *index, uint32_t *out_ok, size_t nq) { return IX(index)->last_coarse_flags(out_ok, nq); }

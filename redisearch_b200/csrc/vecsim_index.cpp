@@ -1494,6 +1494,91 @@ int FlatIndex::topk_filtered(const void *q, size_t k, const uint32_t *doc_ids, s
 }
 
 
+// The same for MANY queries (BASELINE configs[4]: a batch of hybrid queries, each with its own filter set): every query's chain
+// (labels -> rows, gathered distances, selection, label pick, D2H) is enqueued on its own context's stream before anything is
+// waited for, so the chains overlap and the host pays one round of synchronisations instead of two per query.  Device-resident
+// id lists only (the filters' AND / OR results).
+int FlatIndex::topk_filtered_batch(const void *const *queries, size_t nq, size_t k, const uint32_t *const *d_doc_ids, const size_t *counts,
+                                   size_t *out_labels, double *out_scores, size_t *out_counts) {
+    for (size_t i = 0; i < nq; i++) out_counts[i] = 0;
+    last_mode_ = HYBRID_ADHOC_BF;
+    if (k == 0 || nq == 0) return 0;
+    if (multi_ || k > (size_t)kMaxFusedK) return -2;
+    if (!flush()) return -1;
+    if (count_ == 0) return 0;
+    if (!sync_label_table()) return -2;
+    const size_t qpitch = (stored_bytes_ + 15) & ~(size_t)15;
+    constexpr size_t kWave = 16; // contexts in flight at once
+    int rc = 0;
+    for (size_t q0 = 0; q0 < nq && rc == 0; q0 += kWave) {
+        const size_t q1 = std::min(nq, q0 + kWave);
+        struct Job {
+            std::unique_ptr<QueryCtx> c;
+            size_t want = 0;
+            bool ok = false;
+        };
+        std::vector<Job> jobs(q1 - q0);
+        LaunchCounters lc;
+        for (size_t qi = q0; qi < q1; qi++) {
+            Job &j = jobs[qi - q0];
+            const size_t n = counts[qi];
+            if (n == 0) continue;
+            if (n > 0xFFFFFFF0ull) {
+                rc = -2;
+                break;
+            }
+            j.c = checkout();
+            if (!j.c) {
+                rc = -1;
+                break;
+            }
+            QueryCtx &c = *j.c;
+            j.want = std::min(k, n);
+            const uint32_t lists = plan_select_scores_lists((uint32_t)n);
+            bool ok = c.need_query(qpitch) && c.need_ids(2 * n + 256) && c.need_scores(n) && c.need_out(j.want + 1) &&
+                      c.need_cand((size_t)lists * j.want);
+            if (ok) {
+                memset(c.h_query, 0, qpitch);
+                preprocess_query(queries[qi], c.h_query);
+                ok = upload_query(c, c.h_query, 1);
+            }
+            const uint32_t *d_labels = d_doc_ids[qi];
+            ok = ok && launch_map_labels(d_labels, (uint32_t)n, d_label_to_id_, (uint32_t)l2i_size_, c.d_ids, c.stream, &lc) == cudaSuccess;
+            ok = ok && launch_gather_distances(view(), c.d_query, c.d_ids, (uint32_t)n, c.d_scores, c.stream, &lc) == cudaSuccess;
+            ok = ok && launch_select_scores(c.d_scores, (uint32_t)n, nullptr, (uint32_t)j.want, c.d_cand, c.stream, &lc) == cudaSuccess;
+            ok = ok && launch_final_select(c.d_cand, 1, lists * (uint32_t)j.want, (uint32_t)j.want, c.d_out, c.stream, &lc) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(c.h_out, c.d_out, j.want * 8, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+            // the selected positions -> labels (empty slots pick nothing that is read back: they are cut below)
+            ok = ok && launch_pick_labels(c.d_out, (uint32_t)j.want, d_labels, c.d_ids, c.stream, &lc) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(c.h_ids, c.d_ids, j.want * 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+            j.ok = ok;
+            if (!ok) rc = -1;
+        }
+        launches_total_ += lc.launches;
+        for (size_t qi = q0; qi < q1; qi++) { // one round of waits; contexts go back even on failure
+            Job &j = jobs[qi - q0];
+            if (!j.c) continue;
+            const bool synced = cudaStreamSynchronize(j.c->stream) == cudaSuccess;
+            if (j.ok && synced && rc == 0) {
+                size_t w = 0;
+                for (size_t i = 0; i < j.want; i++) {
+                    if (j.c->h_out[i] == kEmptySlot) break;
+                    const float d = key_to_float((uint32_t)(j.c->h_out[i] >> 32));
+                    if (std::isnan(d)) continue;
+                    out_labels[qi * k + w] = j.c->h_ids[i];
+                    out_scores[qi * k + w] = (double)d;
+                    w++;
+                }
+                out_counts[qi] = w;
+            } else if (!synced) {
+                rc = -1;
+            }
+            checkin(std::move(j.c));
+        }
+    }
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // request combiner for the stock single-query entry point (opt-in)
 // ------------------------------------------------------------------------------------------------

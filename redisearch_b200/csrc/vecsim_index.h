@@ -137,6 +137,8 @@ class FlatIndex {
     // fused hybrid ad-hoc query: k nearest among the rows whose labels are listed (ascending) in doc_ids
     int topk_filtered(const void *q, size_t k, const uint32_t *doc_ids, size_t n, bool ids_on_device, size_t *out_labels,
                       double *out_scores, size_t *out_count);
+    int topk_filtered_batch(const void *const *queries, size_t nq, size_t k, const uint32_t *const *d_doc_ids, const size_t *counts,
+                            size_t *out_labels, double *out_scores, size_t *out_counts);
 
     VecSimIndexBasicInfo basic_info() const;
     VecSimIndexStatsInfo stats_info() const;

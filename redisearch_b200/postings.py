@@ -91,6 +91,7 @@ SIGNATURES = [
     ("II_MergeShardTopN", _SZ, [_P, _P, _P, _SZ, _SZ, _SZ, _P, _P]),
     ("II_NewResultIterator", _QI, [_P, C.c_double]),
     ("II_IntersectEx", _P, [_P, _P, _SZ]),
+    ("II_IntersectBatch", _SZ, [_SZ, _P, _P, _P]),
     ("II_NumericList_FromBlocks", _P, [C.POINTER(II_BlockView), _SZ]),
     ("II_NumericList_Len", _SZ, [_P]),
     ("II_NumericList_Fetch", C.c_int, [_P, _P, _P]),

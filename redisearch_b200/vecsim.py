@@ -120,6 +120,7 @@ SIGNATURES = [
     ("VecSimIndex_BasicInfo", VecSimIndexBasicInfo, [_P]),
     ("VecSimIndex_StatsInfo", VecSimIndexStatsInfo, [_P]),
     ("VecSimIndex_DebugInfo", VecSimIndexDebugInfo, [_P]),
+    ("VecSimB200_TopKFilteredBatch", C.c_int, [_P, _P, _SZ, _SZ, _P, _P, _P, _P, _P]),
     ("VecSimIndex_DebugInfoIterator", _P, [_P]),
     ("VecSimDebugInfoIterator_NumberOfFields", _SZ, [_P]),
     ("VecSimDebugInfoIterator_HasNextField", C.c_bool, [_P]),

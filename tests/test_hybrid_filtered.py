@@ -88,3 +88,59 @@ def test_filter_from_device_intersection_feeds_the_knn():
     exp = _oracle_adhoc(p, qn, filt, k)
     assert labels.tolist() == [d for _, d in exp]
     assert np.asarray(scores, dtype=np.float32).tobytes() == np.array([s for s, _ in exp], dtype=np.float32).tobytes()
+
+
+@pytest.mark.gpu
+def test_batched_filters_and_batched_filtered_knn_equal_the_single_calls():
+    """configs[4] in one call each: II_IntersectBatch (the filters of many queries) + VecSimB200_TopKFilteredBatch (their filtered
+    KNN): ids and score bits equal to the per-query calls and to the oracle's ad-hoc loop; empty filters and filters smaller than k
+    included."""
+    import ctypes as C
+
+    from redisearch_b200 import postings as ps
+    from redisearch_b200 import vecsim as vs
+
+    n, dim, k, nq = 60_000, 64, 10, 20
+    rows = ol.synth_rows(ol.F32, 42, 0, n, dim)
+    g = vs.VecSimIndex(vs.VecSimType_FLOAT32, dim, vs.VecSimMetric_Cosine)
+    p = ol.PortIndex(ol.F32, dim, ol.COS, tier=ol.TIER_AVX512)
+    g.add_many(rows, label0=1)
+    p.add_many(rows, 1)
+    rng = np.random.default_rng(12)
+    sizes = [30_000, 20_000, 9_000, 400, 60, 5, 0]
+    pool = [np.unique(rng.integers(1, n + 1, s)).astype(np.uint64) for s in sizes]
+    pls = [ps.PostingList.from_arrays(x) for x in pool]
+    pairs = [(int(rng.integers(0, len(pool))), int(rng.integers(0, len(pool)))) for _ in range(nq)]
+    pairs[0], pairs[1] = (0, 6), (4, 5)  # an empty filter, a filter smaller than k
+    P, L = ps.lib(), vs.lib()
+    arrays = [(C.c_void_p * 2)(pls[a].h, pls[b].h) for a, b in pairs]
+    lists_pp = (C.c_void_p * nq)(*[C.cast(a, C.c_void_p) for a in arrays])
+    n_lists = (C.c_size_t * nq)(*([2] * nq))
+    rs_out = (C.c_void_p * nq)()
+    built = P.II_IntersectBatch(nq, lists_pp, n_lists, rs_out)
+    assert built == nq
+    qs = ol.synth_rows(ol.F32, 43, 0, nq, dim)
+    q_ptrs = (C.c_void_p * nq)(*[qs[i].ctypes.data for i in range(nq)])
+    id_ptrs, counts = (C.c_void_p * nq)(), (C.c_size_t * nq)()
+    filters = []
+    for i, (a, b) in enumerate(pairs):
+        filt = np.intersect1d(pool[a], pool[b])
+        filters.append(filt)
+        assert P.II_ResultSet_Len(rs_out[i]) == len(filt)
+        counts[i] = len(filt)
+        id_ptrs[i] = P.II_ResultSet_DeviceDocIds(rs_out[i]) if len(filt) else None
+    out_l = np.zeros((nq, k), dtype=np.uint64)
+    out_s = np.zeros((nq, k), dtype=np.float64)
+    out_c = (C.c_size_t * nq)()
+    assert L.VecSimB200_TopKFilteredBatch(g.h, q_ptrs, nq, k, id_ptrs, counts, out_l.ctypes.data, out_s.ctypes.data, out_c) == 0
+    for i in range(nq):
+        qn = qs[i].copy()
+        ol.port().orc_normalize(ol._p(qn), dim, ol.F32)
+        exp = _oracle_adhoc(p, qn, filters[i], k)
+        assert out_c[i] == len(exp), (i, pairs[i])
+        assert out_l[i, :out_c[i]].tolist() == [d for _, d in exp]
+        assert out_s[i, :out_c[i]].astype(np.float32).tobytes() == np.array([s for s, _ in exp], dtype=np.float32).tobytes()
+        if len(filters[i]):
+            labels, scores, rc = g.topk_filtered(qs[i], k, id_ptrs[i], n=len(filters[i]))
+            assert rc == 0 and labels.tolist() == out_l[i, :out_c[i]].tolist()
+        P.II_ResultSet_Free(rs_out[i])
