@@ -146,6 +146,69 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
                  "h"(mask)
                  : "memory");
 }
+// ---- CTA pair (cta_group::2) plumbing --------------------------------------------------------------------------------
+// address of `local_smem_addr` in the shared memory of CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier of another CTA of the cluster (release at cluster scope: what this thread has observed is published)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with acquire at cluster scope (the arrivals come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_spin_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+// D[tmem of both CTAs] (+)= A * B^T with M = 256 across the pair: A = each CTA's own 128 queries (tensor memory / shared memory),
+// B = 128 rows, 64 in each CTA's shared memory at the same offset.  Issued by the leader CTA only.
+__device__ __forceinline__ void umma_ts_f16_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ss_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this offset in EVERY CTA of `mask` when all previously issued pair MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -653,7 +716,11 @@ __device__ __forceinline__ uint32_t select_keep(uint64_t *lists, int q, uint32_t
 //            fixed bound needs.  (An earlier version ran the adaptive lists here: with ~10 tiles per CTA they never left
 //            their warm-up — 435 us for 1 % of the rows, ncu launch list profiles/r2c_launches.md.)
 //   tile_stride > 1: only every tile_stride-th row tile is visited (the sample pass)
-template <bool kDirect, int kEpl, int kOp, int kMode>
+//   kPair    the two query groups of a row range (cluster of 2) run as a CTA pair: ONE tcgen05.mma.cta_group::2 stream issued
+//            by the leader computes both groups (M = 256), each CTA streams only ITS half of every row tile (rows 64 * rank ..)
+//            into its own shared memory — no multicast, half the L2 -> SM and shared-memory operand traffic per SM.  The
+//            kernel runs at the board power limit (ncu: 1.37 GHz inside a launch), so operand traffic is clock.  fp32 main pass.
+template <bool kDirect, int kEpl, int kOp, int kMode, bool kPair = false>
 __global__ void __launch_bounds__(kCoarseThreads, 1)
 coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t *__restrict__ shadow, size_t row_pitch,
                     const uint8_t *__restrict__ q16, size_t q16_pitch, const float *__restrict__ row_norm2,
@@ -664,6 +731,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
     constexpr bool kFixed = kMode == 1, kSample = kMode == 2;
     static_assert(kMode == 0 || (!kDirect && (kOp == 0 || kOp == 3)) || (kDirect && kOp == 0),
                   "fixed bound / sample pass: the fp32 route and 16-bit corpora (inner product / cosine)");
+    static_assert(!kPair || (!kDirect && kMode == 1), "CTA pairs: the fp32 main pass");
     constexpr int kSliceSets = (int)kCoarseSampleSlices / (kQN / 32); // tiles i, i + kSliceSets, ... share a slice set
     constexpr int kQListCap = kEpl * 32;
     if (nq_dev) { // second tier: the number of live queries is only known on the device; nothing to do = every CTA leaves
@@ -683,6 +751,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
     uint64_t *lists = list_scratch + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (kQListCap * kQListStride);
     uint64_t *qbar = tempty + kAccStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(qbar + 1);
+    uint64_t *pfull = reinterpret_cast<uint64_t *>(tmem_slot + 2); // kPair, leader: "the peer's half of stage s has landed"
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t q_base = blockIdx.y * kQM;
@@ -691,17 +760,24 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < nstages; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], csize); // one commit per CTA of the cluster: all of them read the multicast stage
+            // multicast clusters: one commit per CTA (all of them read the stage); a pair: ONE commit, multicast to both CTAs
+            mbar_init(&empty[s], kPair ? 1u : csize);
+            if constexpr (kPair) mbar_init(&pfull[s], 1);
         }
         for (int a = 0; a < kAccStages; a++) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 128);
+            mbar_init(&tempty[a], kPair ? 128 + 4 : 128); // pair: + one arrival per epilogue warp of the peer
         }
-        mbar_init(qbar, 128);
+        mbar_init(qbar, kPair ? 128 + 4 : 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) {
+        if constexpr (kPair)
+            tmem_alloc_pair(tmem_slot, 512);
+        else
+            tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -725,7 +801,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                 const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
                 mbar_wait_spin(&empty[s], ph ^ 1);
                 if (elect_one_sync()) {
-                    const uint32_t bytes = kbn * kQBlockBytes;
+                    const uint32_t bytes = kPair ? kbn * (kQBlockBytes / 2) : kbn * kQBlockBytes; // a pair member loads half tiles
                     mbar_expect_tx(&full[s], bytes);
                     if constexpr (kDirect) {
                         // row-major 16-bit corpus: one 128B-swizzle box of (128 / csize) rows x 64 elements per K block
@@ -738,6 +814,13 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                             else
                                 tma_load_2d(dst, &map_rows, &full[s], c0, c1);
                         }
+                    } else if constexpr (kPair) {
+                        // this CTA's half of the tile: rows 64 * rank .. 64 * rank + 63 of every K block (8 KB each, a whole
+                        // number of 8-row swizzle atoms), at the START of the K block's slot — the pair MMA reads 64 rows of B
+                        // from each CTA at the same shared-memory offset
+                        const uint8_t *src = shadow + ((size_t)tile * num_kb + kb0) * kQBlockBytes + crank * (kQBlockBytes / 2);
+                        for (uint32_t j = 0; j < kbn; j++)
+                            bulk_load_1d(sB + (size_t)s * kQStageBytes + j * kQBlockBytes, src + (size_t)j * kQBlockBytes, kQBlockBytes / 2, &full[s]);
                     } else {
                         // the shadow copy is stored tile by tile in the swizzled shared-memory image (to_f16_tiled_kernel):
                         // the K blocks of a stage are one contiguous run in HBM
@@ -754,13 +837,43 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                 if (++s == nstages) s = 0, ph ^= 1;
             }
         }
+#define UMMA_TS(d, a, b, i, acc)                          \
+    do {                                                   \
+        if constexpr (kPair)                               \
+            umma_ts_f16_pair(d, a, b, i, acc);             \
+        else                                               \
+            umma_ts<kOp>(d, a, b, i, acc);                 \
+    } while (0)
+#define UMMA_SS(d, a, b, i, acc)                          \
+    do {                                                   \
+        if constexpr (kPair)                               \
+            umma_ss_f16_pair(d, a, b, i, acc);             \
+        else                                               \
+            umma_ss2<kOp>(d, a, b, i, acc);                \
+    } while (0)
     } else if (warp == 1) {
         // ===== MMA issuer: D[128 queries x 128 rows] += Q[tmem] * rows[smem]^T =====
         // Everything that does not change from stage to stage is hoisted, and a stage takes one of two branch-free
         // bodies (all K blocks from tensor memory / all from shared memory): ncu showed this thread spending half its
         // time on descriptor arithmetic and per-MMA branches while the tensor pipe sat at 53 %.
-        mbar_wait(qbar, 0);
+        if (kPair && crank != 0) {
+            // ===== peer of a CTA pair: no MMAs to issue — relay "my half of stage s has landed" to the leader =====
+            uint32_t s = 0, ph = 0;
+            const uint32_t leader_pfull = mapa_u32(smem_u32(pfull), 0);
+            for (uint32_t i = 0; i < my_tiles; i++)
+                for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kQKbPerStage) {
+                    mbar_wait_spin(&full[s], ph);
+                    if (elect_one_sync()) mbar_arrive_remote(leader_pfull + s * 8);
+                    __syncwarp();
+                    if (++s == nstages) s = 0, ph ^= 1;
+                }
+        } else {
+        if constexpr (kPair)
+            mbar_wait_spin_cluster(qbar, 0); // both CTAs' queries are in place (the peer's warps arrive remotely)
+        else
+            mbar_wait(qbar, 0);
         tc_fence_after();
+        const uint32_t idesc_mma = kPair ? ((idesc & ~(0x1Fu << 24)) | (16u << 24)) : idesc; // M = 256 across the pair
         uint32_t s = 0, ph = 0;
         const uint64_t bdesc_first = make_smem_desc(smem_u32(sB));
         const uint64_t adesc_first = make_smem_desc(smem_u32(sQ));
@@ -769,36 +882,40 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         const bool multi = csize > 1;
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t a = (nacc == 2) ? (i & 1u) : 0u, aph = (nacc == 2) ? ((i >> 1) & 1u) : (i & 1u);
-            mbar_wait_spin(&tempty[a], aph ^ 1);
+            if constexpr (kPair)
+                mbar_wait_spin_cluster(&tempty[a], aph ^ 1);
+            else
+                mbar_wait_spin(&tempty[a], aph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + a * kQN;
             for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kQKbPerStage) {
                 mbar_wait_spin(&full[s], ph);
+                if constexpr (kPair) mbar_wait_spin_cluster(&pfull[s], ph); // ... and the peer's half
                 tc_fence_after();
                 if (elect_one_sync()) {
                     if (kb0 + kQKbPerStage <= kb_tmem) {
                         // both K blocks of the stage: queries from tensor memory (8 columns per instruction), 16 halves
                         // (32 bytes of the swizzled row tile) per instruction
                         const uint32_t at = tmem_q + kb0 * 32;
-                        umma_ts<kOp>(d_tmem, at, bdesc_s, idesc, kb0 != 0);
-                        umma_ts<kOp>(d_tmem, at + 8, bdesc_s + 2, idesc, 1);
-                        umma_ts<kOp>(d_tmem, at + 16, bdesc_s + 4, idesc, 1);
-                        umma_ts<kOp>(d_tmem, at + 24, bdesc_s + 6, idesc, 1);
-                        umma_ts<kOp>(d_tmem, at + 32, bdesc_s + kBlockStep, idesc, 1);
-                        umma_ts<kOp>(d_tmem, at + 40, bdesc_s + kBlockStep + 2, idesc, 1);
-                        umma_ts<kOp>(d_tmem, at + 48, bdesc_s + kBlockStep + 4, idesc, 1);
-                        umma_ts<kOp>(d_tmem, at + 56, bdesc_s + kBlockStep + 6, idesc, 1);
+                        UMMA_TS(d_tmem, at, bdesc_s, idesc_mma, kb0 != 0);
+                        UMMA_TS(d_tmem, at + 8, bdesc_s + 2, idesc_mma, 1);
+                        UMMA_TS(d_tmem, at + 16, bdesc_s + 4, idesc_mma, 1);
+                        UMMA_TS(d_tmem, at + 24, bdesc_s + 6, idesc_mma, 1);
+                        UMMA_TS(d_tmem, at + 32, bdesc_s + kBlockStep, idesc_mma, 1);
+                        UMMA_TS(d_tmem, at + 40, bdesc_s + kBlockStep + 2, idesc_mma, 1);
+                        UMMA_TS(d_tmem, at + 48, bdesc_s + kBlockStep + 4, idesc_mma, 1);
+                        UMMA_TS(d_tmem, at + 56, bdesc_s + kBlockStep + 6, idesc_mma, 1);
                     } else if (kb0 >= kb_tmem && kb0 + kQKbPerStage <= num_kb) {
                         // both K blocks: queries from shared memory
                         const uint64_t ad = adesc_first + (uint64_t)(kb0 - kb_tmem) * kBlockStep;
-                        umma_ss2<kOp>(d_tmem, ad, bdesc_s, idesc, kb0 != 0);
-                        umma_ss2<kOp>(d_tmem, ad + 2, bdesc_s + 2, idesc, 1);
-                        umma_ss2<kOp>(d_tmem, ad + 4, bdesc_s + 4, idesc, 1);
-                        umma_ss2<kOp>(d_tmem, ad + 6, bdesc_s + 6, idesc, 1);
-                        umma_ss2<kOp>(d_tmem, ad + kBlockStep, bdesc_s + kBlockStep, idesc, 1);
-                        umma_ss2<kOp>(d_tmem, ad + kBlockStep + 2, bdesc_s + kBlockStep + 2, idesc, 1);
-                        umma_ss2<kOp>(d_tmem, ad + kBlockStep + 4, bdesc_s + kBlockStep + 4, idesc, 1);
-                        umma_ss2<kOp>(d_tmem, ad + kBlockStep + 6, bdesc_s + kBlockStep + 6, idesc, 1);
+                        UMMA_SS(d_tmem, ad, bdesc_s, idesc_mma, kb0 != 0);
+                        UMMA_SS(d_tmem, ad + 2, bdesc_s + 2, idesc_mma, 1);
+                        UMMA_SS(d_tmem, ad + 4, bdesc_s + 4, idesc_mma, 1);
+                        UMMA_SS(d_tmem, ad + 6, bdesc_s + 6, idesc_mma, 1);
+                        UMMA_SS(d_tmem, ad + kBlockStep, bdesc_s + kBlockStep, idesc_mma, 1);
+                        UMMA_SS(d_tmem, ad + kBlockStep + 2, bdesc_s + kBlockStep + 2, idesc_mma, 1);
+                        UMMA_SS(d_tmem, ad + kBlockStep + 4, bdesc_s + kBlockStep + 4, idesc_mma, 1);
+                        UMMA_SS(d_tmem, ad + kBlockStep + 6, bdesc_s + kBlockStep + 6, idesc_mma, 1);
                     } else {
                         // a stage that straddles the tensor-memory / shared-memory split, or the odd last K block
                         const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
@@ -807,20 +924,22 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                             const uint64_t bd = bdesc_s + (uint64_t)j * kBlockStep;
                             if (kb < kb_tmem) {
                                 const uint32_t at = tmem_q + kb * 32;
-                                umma_ts<kOp>(d_tmem, at, bd, idesc, kb != 0);
-                                umma_ts<kOp>(d_tmem, at + 8, bd + 2, idesc, 1);
-                                umma_ts<kOp>(d_tmem, at + 16, bd + 4, idesc, 1);
-                                umma_ts<kOp>(d_tmem, at + 24, bd + 6, idesc, 1);
+                                UMMA_TS(d_tmem, at, bd, idesc_mma, kb != 0);
+                                UMMA_TS(d_tmem, at + 8, bd + 2, idesc_mma, 1);
+                                UMMA_TS(d_tmem, at + 16, bd + 4, idesc_mma, 1);
+                                UMMA_TS(d_tmem, at + 24, bd + 6, idesc_mma, 1);
                             } else {
                                 const uint64_t ad = adesc_first + (uint64_t)(kb - kb_tmem) * kBlockStep;
-                                umma_ss2<kOp>(d_tmem, ad, bd, idesc, kb != 0);
-                                umma_ss2<kOp>(d_tmem, ad + 2, bd + 2, idesc, 1);
-                                umma_ss2<kOp>(d_tmem, ad + 4, bd + 4, idesc, 1);
-                                umma_ss2<kOp>(d_tmem, ad + 6, bd + 6, idesc, 1);
+                                UMMA_SS(d_tmem, ad, bd, idesc_mma, kb != 0);
+                                UMMA_SS(d_tmem, ad + 2, bd + 2, idesc_mma, 1);
+                                UMMA_SS(d_tmem, ad + 4, bd + 4, idesc_mma, 1);
+                                UMMA_SS(d_tmem, ad + 6, bd + 6, idesc_mma, 1);
                             }
                         }
                     }
-                    if (multi)
+                    if constexpr (kPair)
+                        umma_commit_pair(&empty[s], 0b11); // both halves of stage s are free: tell both producers
+                    else if (multi)
                         umma_commit_mc(&empty[s], cmask); // this CTA is done with stage s: tell every producer of the cluster
                     else
                         umma_commit(&empty[s]);
@@ -829,9 +948,17 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                 bdesc_s += kStageStep;
                 if (++s == nstages) s = 0, ph ^= 1, bdesc_s = bdesc_first;
             }
-            if (elect_one_sync()) umma_commit(&tfull[a]);
+            if (elect_one_sync()) {
+                if constexpr (kPair)
+                    umma_commit_pair(&tfull[a], 0b11); // the accumulators of BOTH CTAs are complete
+                else
+                    umma_commit(&tfull[a]);
+            }
             __syncwarp();
         }
+        } // leader / single CTA
+#undef UMMA_TS
+#undef UMMA_SS
     } else if (warp >= 4) {
         const int ew = warp - 4;          // TMEM lane quadrant
         const int et = threadIdx.x - 128; // 0..127 = query slot = TMEM lane
@@ -861,7 +988,12 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes of sQ -> tensor-core reads
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(qbar);
+            if (kPair && crank != 0) { // the MMAs are issued by the leader: one arrival per warp on ITS barrier
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(qbar), 0));
+            } else {
+                mbar_arrive(qbar);
+            }
         }
         // ===== epilogue: this thread's query against 128 rows per tile =====
         uint32_t thr = 0xFFFFFFFFu, cnt = 0;
@@ -915,7 +1047,12 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
             for (int h = 0; h < kQN / 32; h++) tmem_ld32_nowait(tmem_base + lane_addr + a * kQN + h * 32, v[h]);
             tmem_wait_ld();
             tc_fence_before();
-            mbar_arrive(&tempty[a]);
+            if (kPair && crank != 0) { // hand the accumulator stage back to the leader's issuer
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&tempty[a]), 0));
+            } else {
+                mbar_arrive(&tempty[a]);
+            }
 #pragma unroll
             for (int h = 0; h < kQN / 32; h++) {
                 const uint32_t row0 = tile * kQN + h * 32;
@@ -1092,7 +1229,10 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
     if (csize > 1) cluster_sync_all(); // no CTA may exit while peers can still write its shared memory / barriers
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (kPair)
+            tmem_dealloc_pair(tmem_base, 512);
+        else
+            tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -1406,7 +1546,9 @@ static uint32_t qtmem_nacc() {
     }
     return (uint32_t)v;
 }
-static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl, bool int_cos, int mode = 0) {
+static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl, bool int_cos, int mode = 0, bool pair = false) {
+    if (pair) // the fp32 main pass as a CTA pair (cta_group::2)
+        return int_cos ? (const void *)coarse_qtmem_kernel<false, 3, 3, 1, true> : (const void *)coarse_qtmem_kernel<false, 3, 0, 1, true>;
     if (kind == CoarseDirect16) {
         if (mode == 1) return (const void *)coarse_qtmem_kernel<true, 8, 0, 1>; // fixed bound, lists of 256
         if (mode == 2) return (const void *)coarse_qtmem_kernel<true, 3, 0, 2>; // sample pass
@@ -1426,7 +1568,7 @@ static const void *qtmem_kernel_fn(CoarseKind kind, uint32_t epl, bool int_cos, 
 static size_t qtmem_fixed_smem(uint32_t num_kb) {
     const uint32_t kb_t = (512u - qtmem_nacc() * kQN) / 32u;
     const uint32_t kb_smem = num_kb > kb_t ? num_kb - kb_t : 0; // query K blocks that do not fit tensor memory
-    return 1024 + (size_t)kb_smem * kQBlockBytes + (2 * kQMaxStages + 2 * kAccStages + 1) * 8 + 64;
+    return 1024 + (size_t)kb_smem * kQBlockBytes + (2 * kQMaxStages + 2 * kAccStages + 1) * 8 + 64 + kQMaxStages * 8 /* pfull (CTA pairs) */;
 }
 // fp16 with the queries in tensor memory (first 512 dims) + shared memory (the rest): keep >= 4 ring stages
 static bool qtmem_fits_bytes(uint32_t row_bytes) { return qtmem_fixed_smem((row_bytes + 127) / 128) + 4 * (size_t)kQStageBytes <= kSmemLimit; }
@@ -1496,7 +1638,14 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32
                 p.csize = cs;
                 break;
             }
-        const void *kfn = qtmem_kernel_fn(kind, p.epl, kind == CoarseF16 ? c.metric == MT_L2 : c.metric == MT_COS, p.mode);
+        // CTA pairs: the fp32 main pass with exactly two query groups per row range (the BASELINE batch of 256)
+        static int pair_on = -1; // VECSIM_B200_PAIR=1 enables
+        if (pair_on < 0) {
+            const char *e = getenv("VECSIM_B200_PAIR");
+            pair_on = e ? atoi(e) : 0;
+        }
+        p.pair = pair_on != 0 && kind == CoarseF16 && p.mode == 1 && p.csize == 2 && p.grid_y == 2;
+        const void *kfn = qtmem_kernel_fn(kind, p.epl, kind == CoarseF16 ? c.metric == MT_L2 : c.metric == MT_COS, p.mode, p.pair);
         if (p.csize > 1) {
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
             cudaLaunchConfig_t cfg{};
@@ -1552,7 +1701,7 @@ cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim
                           uint64_t *d_scratch, cudaStream_t s, const uint32_t *d_nq_dev, const float *d_thr_fixed, uint32_t *d_overflow) {
     if (p.kind == CoarseF16 || p.kind == CoarseDirect16 || p.kind == CoarseDirect8) {
         if (p.mode == 1 && (!d_thr_fixed || !d_overflow)) return cudaErrorInvalidValue;
-        const void *kfn = qtmem_kernel_fn(p.kind, p.epl, o.int_cosine != 0, p.mode); // (CoarseF16: the flag selects the L2 epilogue)
+        const void *kfn = qtmem_kernel_fn(p.kind, p.epl, o.int_cosine != 0, p.mode, p.pair); // (CoarseF16: the flag selects the L2 epilogue)
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
         if (e != cudaSuccess) return e;
         CUtensorMap mr{};

@@ -32,6 +32,8 @@ struct CoarsePlan {
     uint32_t tile_stride; // 1 = every row tile; n = every n-th (the sample pass)
     int mode;        // CoarseF16: 0 adaptive top-`keep` lists, 1 fixed admission bound per query (main pass), 2 sample pass (slice minima)
     uint32_t csize;  // thread-block cluster size along y (query groups sharing multicast row tiles); 1 = none
+    bool pair;       // the two query groups of a row range run as a CTA PAIR: tcgen05.mma.cta_group::2 (M = 256 across the two SMs of a
+                     // TPC), each CTA loads only its half of every row tile — no multicast, half the operand traffic per SM
     size_t cand_elems; // uint64 per (query, list, keep)
     size_t scratch_elems; // uint64 of per-CTA candidate-list scratch (CoarseF16), 0 otherwise
     size_t smem_bytes;
