@@ -1703,7 +1703,10 @@ cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim
         if (p.mode == 1 && (!d_thr_fixed || !d_overflow)) return cudaErrorInvalidValue;
         const void *kfn = qtmem_kernel_fn(p.kind, p.epl, o.int_cosine != 0, p.mode, p.pair); // (CoarseF16: the flag selects the L2 epilogue)
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
-        if (e != cudaSuccess) return e;
+        if (e != cudaSuccess) {
+            fprintf(stderr, "vecsim_b200: coarse pass: %zu bytes of shared memory refused: %s\n", p.smem_bytes, cudaGetErrorString(e));
+            return e;
+        }
         CUtensorMap mr{};
         // UMMA instruction descriptor: c_format [4,6) (F32 = 1, S32 = 2), a/b format [7,10)/[10,13), N>>3 [17,23), M>>4 [24,29)
         uint32_t cfmt = 1, fmt = 0; // kind::f16: F16 = 0, BF16 = 1; kind::i8: UINT8 = 0, INT8 = 1
@@ -1737,7 +1740,11 @@ cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim
         void *args[] = {&mr,    &rows,   &rp,   &qs,   &qp,     &rn2, &qn2, &a_nrows, &a_nq,      &a_dim, &a_rb,
                         &a_kb,  &a_tiles, &a_keep, &a_st, &a_cs, &a_nacc,  &a_idesc, &d_scratch, &d_cand, &d_nq_dev,
                         &a_stride, &d_thr_fixed, &d_overflow};
-        return cudaLaunchKernelExC(&cfg, kfn, args);
+        const cudaError_t le = cudaLaunchKernelExC(&cfg, kfn, args);
+        if (le != cudaSuccess)
+            fprintf(stderr, "vecsim_b200: coarse pass launch failed (kind %d mode %d pair %d csize %u grid %u x %u smem %zu): %s\n", (int)p.kind,
+                    p.mode, (int)p.pair, p.csize, p.grid_x, p.grid_y, p.smem_bytes, cudaGetErrorString(le));
+        return le;
     }
     return launch_coarse_t<CfgTF32>(o.rows, o.pitch, n_rows, dim, o.queries, o.qpitch, nq, p, d_cand, s);
 }
