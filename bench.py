@@ -326,6 +326,72 @@ def build_shard(env, vtype, metric, rows, row0_global, dim=DIM, normalize=True):
     return index, time.perf_counter() - t0
 
 
+def bench_clustered(env, rows, nq, k, steps, check):
+    """The proof tiers on a corpus that is NOT uniform: a mixture of tight Gaussians (every centre has ~rows / centres members
+    within sigma, i.e. hundreds of near-duplicates of whatever a query is close to), queries drawn near centres.  On such data
+    a query's admission bound lets far more than `keep` rows of one row range through, so the first tier overflows and the second
+    (adaptive lists of 128) or, failing that, the exact scan answers.  Reports which tier proved how many queries, the step time,
+    and parity of a few queries against the reference's kernels over the device's own rows."""
+    import numpy as np
+
+    vs, L, torch = env.vs, env.L, env.torch
+    dev = env.dev
+    centres_n, sigma = 2000, 0.015
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242)
+    centres = torch.rand((centres_n, DIM), generator=g, device=dev) * 2 - 1
+    centres = centres / centres.norm(dim=1, keepdim=True)
+    index = vs.VecSimIndex(vs.VecSimType_FLOAT32, DIM, vs.VecSimMetric_Cosine)
+    assert L.VecSimB200_Reserve(index.h, rows) == 0
+    done, chunk = 0, 250_000
+    while done < rows:
+        n = min(chunk, rows - done)
+        which = torch.randint(0, centres_n, (n,), generator=g, device=dev)
+        buf = centres[which] + sigma * torch.randn((n, DIM), generator=g, device=dev)
+        buf = (buf / buf.norm(dim=1, keepdim=True)).contiguous()
+        torch.cuda.synchronize()
+        assert L.VecSimB200_AddVectorsDevice(index.h, buf.data_ptr(), n, done + 1) == n
+        done += n
+    qwhich = torch.randint(0, centres_n, (nq,), generator=g, device=dev)
+    q = centres[qwhich] + sigma * torch.randn((nq, DIM), generator=g, device=dev)
+    q = (q / q.norm(dim=1, keepdim=True)).contiguous()
+    out_labels = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+
+    def step():
+        assert L.VecSimB200_TopKQueryBatchDevice(index.h, q.data_ptr(), nq, k, out_labels.data_ptr(), out_scores.data_ptr(), env.sp) == 0
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    flags = np.zeros(nq, dtype=np.uint32)
+    tiers = None
+    if L.VecSimB200_LastCoarseFlags(index.h, flags.ctypes.data, nq) == 0:
+        tiers = {"tier1": int((flags == 1).sum()), "tier2": int((flags == 2).sum()), "exact_scan": int((flags == 0).sum())}
+    parity = None
+    if check:
+        pick = [(i * nq) // 8 for i in range(8)]
+        qh = q.cpu().numpy()
+        chk, _, kind = reference_scan_of_device_rows(env, index, rows, 0, np.ascontiguousarray(qh[pick]), k, 0, 2, usable_cores())
+        dl, ds = out_labels.cpu().numpy(), out_scores.cpu().numpy()
+        ids_ok = all(dl[qq].tolist() == chk.result(i)[0].tolist() for i, qq in enumerate(pick))
+        bits_ok = all(ds[qq].tobytes() == chk.result(i)[1].astype(np.float32).tobytes() for i, qq in enumerate(pick))
+        parity = {"queries": 8, "ids_equal": bool(ids_ok), "score_bits_equal": bool(bits_ok), "checker": kind}
+    del index
+    torch.cuda.empty_cache()
+    return {"workload": f"FLAT {rows} x {DIM} fp32 cosine k={k} batch={nq}; corpus = {centres_n} unit centres + N(0, {sigma}^2) noise per coordinate "
+                        f"(~{rows // centres_n} near-duplicates per centre), queries drawn the same way",
+            "value": nq / (ms / 1000.0), "unit": "queries/s", "ms_per_step": ms, "proven_by_tier": tiers, "parity": parity,
+            }
+
+
 def reference_scan_of_device_rows(env, index, rows, row0_global, q_stored, k, vtype_code, metric_code, threads):
     """The parity checker at full size: copy this rank's stored rows back from HBM 500K at a time and feed them to the
     reference's own distance kernels + heap (tests/oracle_lib.StreamingTopK -> oracle/_ref Ref_ScanTopKChunk).  Returns
@@ -583,8 +649,16 @@ def run_knn(args):
         if args.scaling == "weak" and world > 1:
             line["shard_query_rate"] = {"value": world * value, "unit": "queries x 10M-row shards / s"}
         line.update(single)
-        if world == 1 and not args.no_postings:
+        if world == 1 and not args.no_clustered:
             del index
+            index = None
+            torch.cuda.empty_cache()
+            try:
+                line["clustered_corpus"] = bench_clustered(env, args.clustered_rows, nq, K, max(3, min(args.steps, 10)), check=not args.no_parity)
+            except Exception as e:
+                line["clustered_corpus"] = {"value": None, "error": repr(e)}
+        if world == 1 and not args.no_postings:
+            index = None
             torch.cuda.empty_cache()
             try:
                 line["bm25_intersect"] = bench_postings(torch, dev, sp, args.posting_docs, max(1, min(args.steps, 5)), load_peaks()[0],
@@ -734,6 +808,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-postings", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-clustered", action="store_true", help="skip the clustered-corpus leg (proof tiers on non-uniform data)")
+    ap.add_argument("--clustered-rows", type=int, default=2_000_000)
     ap.add_argument("--posting-docs", type=int, default=50_000_000)
     args = ap.parse_args()
 
