@@ -729,6 +729,11 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                     uint64_t *__restrict__ list_scratch, uint64_t *__restrict__ cand_out, const uint32_t *__restrict__ nq_dev,
                     uint32_t tile_stride, const float *__restrict__ thr_fixed, uint32_t *__restrict__ overflow) {
     constexpr bool kFixed = kMode == 1, kSample = kMode == 2;
+    // logical coordinates: bx = row range, by = query group.  A CTA pair must be two CTAs adjacent along x of the cluster (the
+    // hardware pairs cluster ranks 2i / 2i + 1 of the x dimension: a (1, 2, 1) cluster fails to launch with "cluster
+    // misconfiguration"), so the pair build is launched as grid (2, row ranges) with cluster (2, 1, 1) and the roles of x / y swap.
+    const uint32_t bx = kPair ? blockIdx.y : blockIdx.x, by = kPair ? blockIdx.x : blockIdx.y;
+    const uint32_t gx = kPair ? gridDim.y : gridDim.x;
     static_assert(kMode == 0 || (!kDirect && (kOp == 0 || kOp == 3)) || (kDirect && kOp == 0),
                   "fixed bound / sample pass: the fp32 route and 16-bit corpora (inner product / cosine)");
     static_assert(!kPair || (!kDirect && kMode == 1), "CTA pairs: the fp32 main pass");
@@ -748,14 +753,14 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
     uint64_t *bars = reinterpret_cast<uint64_t *>(sQ + (size_t)(num_kb - kb_tmem) * kQBlockBytes);
     uint64_t *full = bars, *empty = bars + kQMaxStages, *tfull = bars + 2 * kQMaxStages, *tempty = tfull + kAccStages;
     // this CTA's candidate lists [kQListCap][kQListStride]
-    uint64_t *lists = list_scratch + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (kQListCap * kQListStride);
+    uint64_t *lists = list_scratch + (size_t)(by * gx + bx) * (kQListCap * kQListStride);
     uint64_t *qbar = tempty + kAccStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(qbar + 1);
     uint64_t *pfull = reinterpret_cast<uint64_t *>(tmem_slot + 2); // kPair, leader: "the peer's half of stage s has landed"
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t q_base = blockIdx.y * kQM;
-    const uint32_t my_tiles = (tiles_total > blockIdx.x) ? (tiles_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t q_base = by * kQM;
+    const uint32_t my_tiles = (tiles_total > bx) ? (tiles_total - bx + gx - 1) / gx : 0;
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < nstages; s++) {
@@ -796,7 +801,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         uint32_t s = 0, ph = 0;
         const uint32_t slice_full = kQStageBytes / csize, slice_tail = ((num_kb % kQKbPerStage) * kQBlockBytes) / csize;
         for (uint32_t i = 0; i < my_tiles; i++) {
-            const uint32_t tile = (blockIdx.x + i * gridDim.x) * tile_stride;
+            const uint32_t tile = (bx + i * gx) * tile_stride;
             for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kQKbPerStage) {
                 const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
                 mbar_wait_spin(&empty[s], ph ^ 1);
@@ -1022,7 +1027,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         }
         if (q >= nq) thr_dot = __int_as_float(0x7f800000); // padding lanes of a partial query group: nothing ever passes
         for (uint32_t i = 0; i < my_tiles; i++) {
-            const uint32_t tile = (blockIdx.x + i * gridDim.x) * tile_stride;
+            const uint32_t tile = (bx + i * gx) * tile_stride;
             const uint32_t a = (nacc == 2) ? (i & 1u) : 0u, aph = (nacc == 2) ? ((i >> 1) & 1u) : (i & 1u);
             float nrm[kQN / 32]; // kOp 2 / 3: lane l holds the norm / squared norm of rows h*32 + l of the tile
             if constexpr (kOp == 3) {
@@ -1194,7 +1199,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         }
         if constexpr (kSample) { // keep == 8: the slice minima as composites (the row id is not needed by threshold_kernel)
             if (q < nq) {
-                uint64_t *dst = cand_out + ((size_t)q * gridDim.x + blockIdx.x) * keep;
+                uint64_t *dst = cand_out + ((size_t)q * gx + bx) * keep;
 #pragma unroll
                 for (int x = 0; x < kSliceSets; x++)
 #pragma unroll
@@ -1218,7 +1223,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
             }
             if (qq < nq) {
                 // unordered: final_select (direct routes) and refine_kernel (fp32 route) take the lists in any order
-                uint64_t *dst = cand_out + ((size_t)qq * gridDim.x + blockIdx.x) * keep;
+                uint64_t *dst = cand_out + ((size_t)qq * gx + bx) * keep;
                 __syncwarp();
                 for (uint32_t r = lane; r < keep; r += 32) dst[r] = r < c ? lists[r * kQListStride + ew * 32 + src] : kEmptySlot;
             }
@@ -1650,11 +1655,11 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
             cudaLaunchConfig_t cfg{};
             cudaLaunchAttribute at[1];
-            cfg.gridDim = dim3(1, p.grid_y, 1);
+            cfg.gridDim = p.pair ? dim3(2, 1, 1) : dim3(1, p.grid_y, 1);
             cfg.blockDim = dim3(kCoarseThreads);
             cfg.dynamicSmemBytes = p.smem_bytes;
             at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 1, at[0].val.clusterDim.y = p.csize, at[0].val.clusterDim.z = 1;
+            at[0].val.clusterDim.x = p.pair ? 2 : 1, at[0].val.clusterDim.y = p.pair ? 1 : p.csize, at[0].val.clusterDim.z = 1;
             cfg.attrs = at, cfg.numAttrs = 1;
             int nclusters = 0;
             if (cudaOccupancyMaxActiveClusters(&nclusters, kfn, &cfg) != cudaSuccess || nclusters < 1) {
@@ -1725,12 +1730,12 @@ cudaError_t launch_coarse(const CoarseOperands &o, uint32_t n_rows, uint32_t dim
         const uint32_t idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kQN >> 3) << 17) | ((uint32_t)(kQM >> 4) << 24);
         cudaLaunchConfig_t cfg{};
         cudaLaunchAttribute at[1];
-        cfg.gridDim = dim3(p.grid_x, p.grid_y, 1);
+        cfg.gridDim = p.pair ? dim3(2, p.grid_x, 1) : dim3(p.grid_x, p.grid_y, 1); // a CTA pair lies along x (see the kernel)
         cfg.blockDim = dim3(kCoarseThreads);
         cfg.dynamicSmemBytes = p.smem_bytes;
         cfg.stream = s;
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 1, at[0].val.clusterDim.y = p.csize, at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = p.pair ? 2 : 1, at[0].val.clusterDim.y = p.pair ? 1 : p.csize, at[0].val.clusterDim.z = 1;
         cfg.attrs = at, cfg.numAttrs = 1;
         const uint8_t *rows = static_cast<const uint8_t *>(o.rows), *qs = static_cast<const uint8_t *>(o.queries);
         size_t rp = o.pitch, qp = o.qpitch;
