@@ -784,7 +784,10 @@ __global__ void __launch_bounds__(256) fused_window_kernel(const FusedQuery *__r
     win[(size_t)item * (kFusedMaxLists - 1) + (j - 1)] = make_uint2(lo0, lo1);
 }
 
-__global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQuery *__restrict__ queries, const uint32_t *__restrict__ item_q,
+// kN = the largest child count of the batch, rounded up to {2, 3, 4, 8}: the loops over the children unroll to kN, so the
+// common 3-term batch carries a third of the code and of the per-entry position registers of the 8-child build
+template <int kN>
+__global__ void __launch_bounds__(kIIThreads, (kN <= 3 ? 5 : 4)) fused_and_kernel(const FusedQuery *__restrict__ queries, const uint32_t *__restrict__ item_q,
                                                                const uint2 *__restrict__ win, const FusedCommon fc, uint32_t top_n,
                                                                uint64_t *__restrict__ cand_keys, uint32_t *__restrict__ cand_ids,
                                                                uint32_t *__restrict__ hits, uint32_t *__restrict__ cand_fill) {
@@ -801,7 +804,7 @@ __global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQue
     const uint32_t start = chunk * kIIChunk;
     const uint32_t end = min(start + (uint32_t)kIIChunk, Q.len[0]);
     const uint32_t *A = Q.ids[0];
-    uint32_t doc[kIIItems], pos[kFusedMaxLists - 1][kIIItems];
+    uint32_t doc[kIIItems], pos[kN - 1][kIIItems];
     bool alive[kIIItems];
 #pragma unroll
     for (int i = 0; i < kIIItems; i++) {
@@ -810,11 +813,11 @@ __global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQue
         doc[i] = alive[i] ? A[idx] : 0xFFFFFFFFu;
     }
     // the windows of the other children (block-uniform), and where each would sit in shared memory
-    uint32_t w_lo[kFusedMaxLists - 1], w_off[kFusedMaxLists - 1], w_len[kFusedMaxLists - 1];
+    uint32_t w_lo[kN - 1], w_off[kN - 1], w_len[kN - 1];
     uint32_t total_range = 0;
     bool all_fit = true;
 #pragma unroll
-    for (int j = 1; j < kFusedMaxLists; j++) {
+    for (int j = 1; j < kN; j++) {
         w_lo[j - 1] = w_off[j - 1] = w_len[j - 1] = 0;
         if (j < (int)n) {
             const uint2 w = win[(size_t)item * (kFusedMaxLists - 1) + (j - 1)];
@@ -828,14 +831,14 @@ __global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQue
     if (all_fit) {
         // every window at once: one round of loads, one barrier, then each entry walks the children on its own
 #pragma unroll
-        for (int j = 1; j < kFusedMaxLists; j++)
+        for (int j = 1; j < kN; j++)
             if (j < (int)n) {
                 const uint32_t *B = Q.ids[j] + w_lo[j - 1];
                 for (uint32_t t = threadIdx.x; t < w_len[j - 1]; t += kIIThreads) sB[w_off[j - 1] + t] = B[t];
             }
         __syncthreads();
 #pragma unroll
-        for (int j = 1; j < kFusedMaxLists; j++)
+        for (int j = 1; j < kN; j++)
             if (j < (int)n) {
                 const uint32_t *W = sB + w_off[j - 1];
                 const uint32_t range = w_len[j - 1];
@@ -852,7 +855,7 @@ __global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQue
         // searched in place
         bool any_alive = true;
 #pragma unroll
-        for (int j = 1; j < kFusedMaxLists; j++) {
+        for (int j = 1; j < kN; j++) {
             if (j >= (int)n || !any_alive) break;
             const uint32_t *B = Q.ids[j];
             const uint32_t lo = w_lo[j - 1], range = w_len[j - 1], hi = lo + range;
@@ -946,7 +949,7 @@ __global__ void __launch_bounds__(kIIThreads, 4) fused_and_kernel(const FusedQue
         ScoreAcc acc{0.0};
         score_child(fc, acc, Q.weight[0], Q.idf[0], Q.bm25_idf[0], Q.freqs[0][start + threadIdx.x * kIIItems + i], dl);
 #pragma unroll
-        for (int j = 1; j < kFusedMaxLists; j++)
+        for (int j = 1; j < kN; j++)
             if (j < (int)n) score_child(fc, acc, Q.weight[j], Q.idf[j], Q.bm25_idf[j], Q.freqs[j][pos[j - 1][i]], dl);
         key[i] = rank_key(score_finish(fc, acc, d, dl, n));
     }
@@ -1072,7 +1075,23 @@ cudaError_t ii_launch_fused_search(const FusedQuery *d_queries, uint32_t nq, uin
             const uint64_t searches = (uint64_t)total_items * (max_children - 1);
             fused_window_kernel<<<(uint32_t)((searches + 255) / 256), 256, 0, s>>>(d_queries, d_item_q, total_items, max_children - 1, d_win);
         }
-        fused_and_kernel<<<total_items, kIIThreads, 0, s>>>(d_queries, d_item_q, d_win, fc, top_n, d_cand_keys, d_cand_ids, d_hits, d_fill);
+        static bool carveout_set = false; // 5 CTAs x 45 KB of static shared memory per SM need (nearly) the whole carve-out
+        if (!carveout_set) {
+            cudaFuncSetAttribute(fused_and_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(fused_and_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(fused_and_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(fused_and_kernel<kFusedMaxLists>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carveout_set = true;
+        }
+        if (max_children <= 2)
+            fused_and_kernel<2><<<total_items, kIIThreads, 0, s>>>(d_queries, d_item_q, d_win, fc, top_n, d_cand_keys, d_cand_ids, d_hits, d_fill);
+        else if (max_children == 3)
+            fused_and_kernel<3><<<total_items, kIIThreads, 0, s>>>(d_queries, d_item_q, d_win, fc, top_n, d_cand_keys, d_cand_ids, d_hits, d_fill);
+        else if (max_children == 4)
+            fused_and_kernel<4><<<total_items, kIIThreads, 0, s>>>(d_queries, d_item_q, d_win, fc, top_n, d_cand_keys, d_cand_ids, d_hits, d_fill);
+        else
+            fused_and_kernel<kFusedMaxLists><<<total_items, kIIThreads, 0, s>>>(d_queries, d_item_q, d_win, fc, top_n, d_cand_keys, d_cand_ids, d_hits,
+                                                                                 d_fill);
     }
     fused_topn_kernel<<<nq, 256, 0, s>>>(d_queries, top_n, d_cand_keys, d_cand_ids, d_fill, d_out_keys, d_out_ids);
     return cudaGetLastError();
