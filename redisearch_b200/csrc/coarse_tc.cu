@@ -603,7 +603,7 @@ coarse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 constexpr int kQM = 128;            // queries per CTA
 constexpr int kQN = 128;            // rows per tile = N of one MMA (measured: N=64 58 clk, N=128 76 clk per instruction)
-constexpr int kQMaxStages = 8;
+constexpr int kQMaxStages = 16; // (a 32 KB stage fits 7 times; the CTA-pair build packs 16 KB half-stages)
 constexpr int kQKbPerStage = 2;     // K blocks per pipeline stage: amortises the barrier round trip over 8 MMAs
 // candidate lists: kEpl entries per lane of the compacting warp -> kEpl*32 slots per query; a list is cut back to
 // `keep` when it holds more than (slots - 32) entries after a 32-row chunk.  kEpl = 3 (96 slots) serves keep <= 32,
@@ -749,7 +749,10 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
     // K blocks of the queries in tensor memory (all 512 columns minus the nacc accumulator stages); the rest in sQ
     const uint32_t kb_tmem = min(num_kb, (512u - nacc * kQN) / 32u);
     uint8_t *sB = smem;                                            // nstages x kQKbPerStage x [128 x 128B]
-    uint8_t *sQ = sB + (size_t)nstages * kQStageBytes;             // (num_kb - kb_tmem) x [128 queries x 128B], swizzled
+    // a pair member holds 64 rows of every K block: half-size blocks and stages, twice as many of them in the ring (the stage
+    // hand-over of a pair is longer — the peer's arrival is relayed to the leader — so the ring has to look further ahead)
+    constexpr uint32_t kBlkB = kPair ? kQBlockBytes / 2 : kQBlockBytes, kStgB = kPair ? kQStageBytes / 2 : kQStageBytes;
+    uint8_t *sQ = sB + (size_t)nstages * kStgB;                    // (num_kb - kb_tmem) x [128 queries x 128B], swizzled
     uint64_t *bars = reinterpret_cast<uint64_t *>(sQ + (size_t)(num_kb - kb_tmem) * kQBlockBytes);
     uint64_t *full = bars, *empty = bars + kQMaxStages, *tfull = bars + 2 * kQMaxStages, *tempty = tfull + kAccStages;
     // this CTA's candidate lists [kQListCap][kQListStride]
@@ -825,7 +828,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                         // from each CTA at the same shared-memory offset
                         const uint8_t *src = shadow + ((size_t)tile * num_kb + kb0) * kQBlockBytes + crank * (kQBlockBytes / 2);
                         for (uint32_t j = 0; j < kbn; j++)
-                            bulk_load_1d(sB + (size_t)s * kQStageBytes + j * kQBlockBytes, src + (size_t)j * kQBlockBytes, kQBlockBytes / 2, &full[s]);
+                            bulk_load_1d(sB + (size_t)s * kStgB + j * kBlkB, src + (size_t)j * kQBlockBytes, kQBlockBytes / 2, &full[s]);
                     } else {
                         // the shadow copy is stored tile by tile in the swizzled shared-memory image (to_f16_tiled_kernel):
                         // the K blocks of a stage are one contiguous run in HBM
@@ -882,7 +885,8 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         uint32_t s = 0, ph = 0;
         const uint64_t bdesc_first = make_smem_desc(smem_u32(sB));
         const uint64_t adesc_first = make_smem_desc(smem_u32(sQ));
-        constexpr uint64_t kStageStep = kQStageBytes >> 4, kBlockStep = kQBlockBytes >> 4;
+        constexpr uint64_t kStageStep = kStgB >> 4, kBlockStep = kBlkB >> 4; // B descriptors; the query blocks in sQ keep 16 KB
+        constexpr uint64_t kQBlockStep = kQBlockBytes >> 4;
         uint64_t bdesc_s = bdesc_first; // descriptor of ring stage s
         const bool multi = csize > 1;
         for (uint32_t i = 0; i < my_tiles; i++) {
@@ -912,15 +916,15 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                         UMMA_TS(d_tmem, at + 56, bdesc_s + kBlockStep + 6, idesc_mma, 1);
                     } else if (kb0 >= kb_tmem && kb0 + kQKbPerStage <= num_kb) {
                         // both K blocks: queries from shared memory
-                        const uint64_t ad = adesc_first + (uint64_t)(kb0 - kb_tmem) * kBlockStep;
+                        const uint64_t ad = adesc_first + (uint64_t)(kb0 - kb_tmem) * kQBlockStep;
                         UMMA_SS(d_tmem, ad, bdesc_s, idesc_mma, kb0 != 0);
                         UMMA_SS(d_tmem, ad + 2, bdesc_s + 2, idesc_mma, 1);
                         UMMA_SS(d_tmem, ad + 4, bdesc_s + 4, idesc_mma, 1);
                         UMMA_SS(d_tmem, ad + 6, bdesc_s + 6, idesc_mma, 1);
-                        UMMA_SS(d_tmem, ad + kBlockStep, bdesc_s + kBlockStep, idesc_mma, 1);
-                        UMMA_SS(d_tmem, ad + kBlockStep + 2, bdesc_s + kBlockStep + 2, idesc_mma, 1);
-                        UMMA_SS(d_tmem, ad + kBlockStep + 4, bdesc_s + kBlockStep + 4, idesc_mma, 1);
-                        UMMA_SS(d_tmem, ad + kBlockStep + 6, bdesc_s + kBlockStep + 6, idesc_mma, 1);
+                        UMMA_SS(d_tmem, ad + kQBlockStep, bdesc_s + kBlockStep, idesc_mma, 1);
+                        UMMA_SS(d_tmem, ad + kQBlockStep + 2, bdesc_s + kBlockStep + 2, idesc_mma, 1);
+                        UMMA_SS(d_tmem, ad + kQBlockStep + 4, bdesc_s + kBlockStep + 4, idesc_mma, 1);
+                        UMMA_SS(d_tmem, ad + kQBlockStep + 6, bdesc_s + kBlockStep + 6, idesc_mma, 1);
                     } else {
                         // a stage that straddles the tensor-memory / shared-memory split, or the odd last K block
                         const uint32_t kbn = min((uint32_t)kQKbPerStage, num_kb - kb0);
@@ -934,7 +938,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                                 UMMA_TS(d_tmem, at + 16, bd + 4, idesc_mma, 1);
                                 UMMA_TS(d_tmem, at + 24, bd + 6, idesc_mma, 1);
                             } else {
-                                const uint64_t ad = adesc_first + (uint64_t)(kb - kb_tmem) * kBlockStep;
+                                const uint64_t ad = adesc_first + (uint64_t)(kb - kb_tmem) * kQBlockStep;
                                 UMMA_SS(d_tmem, ad, bd, idesc_mma, kb != 0);
                                 UMMA_SS(d_tmem, ad + 2, bd + 2, idesc_mma, 1);
                                 UMMA_SS(d_tmem, ad + 4, bd + 4, idesc_mma, 1);
@@ -1650,6 +1654,10 @@ CoarsePlan plan_coarse(const CorpusView &c, uint32_t nq, CoarseKind kind, uint32
             pair_on = e ? atoi(e) : 0;
         }
         p.pair = pair_on != 0 && kind == CoarseF16 && p.mode == 1 && p.csize == 2 && p.grid_y == 2;
+        if (p.pair) { // half-size stages, twice as many
+            p.stages = (uint32_t)std::min<size_t>(kQMaxStages, (kSmemLimit - qtmem_fixed_smem(p.num_kb)) / (kQStageBytes / 2));
+            p.smem_bytes = qtmem_fixed_smem(p.num_kb) + (size_t)p.stages * (kQStageBytes / 2);
+        }
         const void *kfn = qtmem_kernel_fn(kind, p.epl, kind == CoarseF16 ? c.metric == MT_L2 : c.metric == MT_COS, p.mode, p.pair);
         if (p.csize > 1) {
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
