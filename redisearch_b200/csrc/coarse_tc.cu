@@ -876,10 +876,7 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
                     if (++s == nstages) s = 0, ph ^= 1;
                 }
         } else {
-        if constexpr (kPair)
-            mbar_wait_spin_cluster(qbar, 0); // both CTAs' queries are in place (the peer's warps arrive remotely)
-        else
-            mbar_wait(qbar, 0);
+        mbar_wait(qbar, 0); // pair: both CTAs' queries are in place (the peer's warps arrive remotely)
         tc_fence_after();
         const uint32_t idesc_mma = kPair ? ((idesc & ~(0x1Fu << 24)) | (16u << 24)) : idesc; // M = 256 across the pair
         uint32_t s = 0, ph = 0;
@@ -891,15 +888,14 @@ coarse_qtmem_kernel(const __grid_constant__ CUtensorMap map_rows, const uint8_t 
         const bool multi = csize > 1;
         for (uint32_t i = 0; i < my_tiles; i++) {
             const uint32_t a = (nacc == 2) ? (i & 1u) : 0u, aph = (nacc == 2) ? ((i >> 1) & 1u) : (i & 1u);
-            if constexpr (kPair)
-                mbar_wait_spin_cluster(&tempty[a], aph ^ 1);
-            else
-                mbar_wait_spin(&tempty[a], aph ^ 1);
+            mbar_wait_spin(&tempty[a], aph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + a * kQN;
             for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kQKbPerStage) {
                 mbar_wait_spin(&full[s], ph);
-                if constexpr (kPair) mbar_wait_spin_cluster(&pfull[s], ph); // ... and the peer's half
+                // ... and the peer's half.  A plain (CTA-scope) wait, as CUTLASS's ClusterBarrier does for remotely signalled
+                // barriers: the first pair build polled with .acquire.cluster and every poll cost ~1 us (5.86 ms per pass)
+                if constexpr (kPair) mbar_wait_spin(&pfull[s], ph);
                 tc_fence_after();
                 if (elect_one_sync()) {
                     if (kb0 + kQKbPerStage <= kb_tmem) {
