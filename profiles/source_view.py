@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line view of an ncu capture taken with --import-source on.
 
-  python profiles/source_view.py <capture.ncu-rep> <library.so> <kernel substring> [out.md]
+  python profiles/source_view.py <capture.ncu-rep> <library.so> <kernel substring | "mangled|demangled"> [out.md]
 
 ncu's `--page source --csv` lists warp-state samples per SASS instruction (by address); `nvdisasm --print-line-info` of the same
 build lists the CUDA line of every SASS instruction in the same order.  The two streams are aligned by instruction index and
@@ -66,8 +66,10 @@ def ncu_samples(rep, kernel):
 def main():
     rep, so, kernel = sys.argv[1], sys.argv[2], sys.argv[3]
     out = sys.argv[4] if len(sys.argv) > 4 else None
-    sass = sass_lines(so, kernel)
-    samp = ncu_samples(rep, kernel)
+    # "<mangled substring>|<demangled substring>" when the two differ (template instantiations)
+    k_sass, k_ncu = (kernel.split("|") + [kernel])[:2]
+    sass = sass_lines(so, k_sass)
+    samp = ncu_samples(rep, k_ncu)
     n = min(len(sass), len(samp))
     per_line, total = {}, 0
     mismatch = 0

@@ -228,6 +228,14 @@ __device__ __forceinline__ void lower_bound_lockstep(const uint32_t *w, uint32_t
     for (int i = 0; i < N; i++) out[i] += (w[out[i]] < key[i]) ? 1u : 0u;
 }
 
+// asynchronous 4-byte copies global -> shared (LDGSTS): a window copy written as `sB[t] = B[t]` in a loop waits for every load
+// before the next one is issued (ncu source view, profiles/r2o_fused_and_source_view.md: 43 % of the fused kernel's samples sat on
+// the three staging loops); with cp.async all of a thread's copies are in flight at once and the CTA waits once
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // lower_bound by a whole warp: 32 pivots per round instead of one dependent load per bisection step
 // (the probed list has up to 10^7 entries in HBM: 5 rounds of latency instead of 23)
 __device__ __forceinline__ uint32_t warp_lower_bound_u32(const uint32_t *a, uint32_t lo, uint32_t hi, uint32_t key, int lane) {
@@ -278,7 +286,8 @@ __global__ void __launch_bounds__(kIIThreads) intersect_kernel(const IntersectAr
         const int mode = a.mode[j];
         const bool staged = range <= (uint32_t)kIISmemElems;
         if (staged) {
-            for (uint32_t t = threadIdx.x; t < range; t += kIIThreads) sB[t] = B[lo + t];
+            for (uint32_t t = threadIdx.x; t < range; t += kIIThreads) cp_async4(&sB[t], B + lo + t);
+            cp_async_wait_all();
             __syncthreads();
         }
 #pragma unroll
@@ -834,8 +843,9 @@ __global__ void __launch_bounds__(kIIThreads, (kN <= 3 ? 5 : 4)) fused_and_kerne
         for (int j = 1; j < kN; j++)
             if (j < (int)n) {
                 const uint32_t *B = Q.ids[j] + w_lo[j - 1];
-                for (uint32_t t = threadIdx.x; t < w_len[j - 1]; t += kIIThreads) sB[w_off[j - 1] + t] = B[t];
+                for (uint32_t t = threadIdx.x; t < w_len[j - 1]; t += kIIThreads) cp_async4(&sB[w_off[j - 1] + t], B + t);
             }
+        cp_async_wait_all();
         __syncthreads();
 #pragma unroll
         for (int j = 1; j < kN; j++)
@@ -860,7 +870,8 @@ __global__ void __launch_bounds__(kIIThreads, (kN <= 3 ? 5 : 4)) fused_and_kerne
             const uint32_t *B = Q.ids[j];
             const uint32_t lo = w_lo[j - 1], range = w_len[j - 1], hi = lo + range;
             if (range <= (uint32_t)kIISmemElems) {
-                for (uint32_t t = threadIdx.x; t < range; t += kIIThreads) sB[t] = B[lo + t];
+                for (uint32_t t = threadIdx.x; t < range; t += kIIThreads) cp_async4(&sB[t], B + lo + t);
+                cp_async_wait_all();
                 __syncthreads();
                 uint32_t p[kIIItems];
                 lower_bound_lockstep<kIIItems>(sB, range, doc, p);
@@ -877,7 +888,8 @@ __global__ void __launch_bounds__(kIIThreads, (kN <= 3 ? 5 : 4)) fused_and_kerne
                 constexpr uint32_t kPivots = 2048;
                 const uint32_t step = (range + kPivots - 1) / kPivots; // bucket b = [lo + b*step, lo + (b+1)*step)
                 const uint32_t nbuckets = (range + step - 1) / step;
-                for (uint32_t t = threadIdx.x; t < nbuckets; t += kIIThreads) sB[t] = B[lo + t * step]; // first entry of bucket t
+                for (uint32_t t = threadIdx.x; t < nbuckets; t += kIIThreads) cp_async4(&sB[t], B + lo + (size_t)t * step); // first entry of bucket t
+                cp_async_wait_all();
                 __syncthreads();
                 uint32_t l[kIIItems], h[kIIItems];
 #pragma unroll
