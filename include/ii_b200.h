@@ -319,6 +319,24 @@ II_QueryIterator *II_NewResultIterator(II_ResultSet *rs, double weight);
 II_QueryIterator *NewIntersectionIterator(II_QueryIterator **its, size_t num, int32_t max_slop, bool in_order, double weight);
 II_QueryIterator *NewUnionIterator(II_QueryIterator **its, int32_t num, bool quick_exit, double weight, int /* QueryNodeType */ type_,
                                    const char *q_str, const void /* IteratorsConfig */ *config);
+/* The term leaf under the reference's own name and signature (RS/headers/iterators_ffi.h:404; Term::new,
+ * RS/rqe_iterators/src/inverted_index/term.rs:77-100).  Everything it needs from the host is resolved with dlsym in the host
+ * process: InvertedIndex_Flags / _NumDocs and the block accessors (inverted_index_ffi.h), IndexSpec_GetStats (src/spec.h:509),
+ * QueryTerm_SetIDFs / Term_Free (query_term_ffi.h:108,119); `sctx` is read as {redisCtx, spec, ...} (src/search_ctx.h:60-64).
+ * Decoded lists go through the cache set with II_SetDefaultTermCache (NULL: decoded per iterator).  Returns NULL with nothing
+ * consumed when an accessor is missing or the index is not a term index: the caller keeps the reference's iterator. */
+typedef struct {
+    uint8_t tag; /* 0 = Index (field index, used for expiration checks only), 1 = Mask — RS/headers/field.h:29-57 */
+    unsigned __int128 mask __attribute__((aligned(16)));
+} II_FieldMaskOrIndex;
+II_QueryIterator *NewInvIndIterator_TermQuery(const void *idx, const void *sctx, II_FieldMaskOrIndex field_mask_or_index, void *term,
+                                              double weight);
+void II_SetDefaultTermCache(II_TermCache *cache);
+/* DocIdsOnly indexes: 1 = the host runs with raw docId encoding (RawDocIdsOnly), which the index flags do not say */
+void II_SetRawDocIdEncoding(int raw);
+/* IndexFlags (src/spec.h:171-181) -> II_Codec, the table of NewInvertedIndex_Ex (inverted_index_ffi/src/lib.rs:49-165); -1 = not a
+ * term index */
+int II_CodecFromIndexFlags(uint32_t flags, int raw_doc_id_encoding);
 II_QueryIterator *II_NewEmptyIterator(void);
 /* rqe_iterators/src/wildcard.rs:83-180: every docId 1..top_id as a virtual result (freq 1, all fields) of the given weight; the
  * second name is the reference's (RS/headers/iterators_ffi.h:647).  Stripped by our AND, taken over by a quick OR

@@ -2008,6 +2008,8 @@ struct NodeIter {
     II_TermCache *cache = nullptr; // non-NULL: pl is pinned in this cache (released, not freed)
     II_TermParams term{1.0, 0.0, 0.0};
     LeafMode mode = LEAF_REQUIRED;
+    void *host_term = nullptr;               // the host's RSQueryTerm (NewInvIndIterator_TermQuery): owned, released with
+    void (*host_term_free)(void *) = nullptr; // the host's Term_Free
     uint64_t max_doc_id = 0; // NOT / OPTIONAL: the universe is 1..max_doc_id; wildcard: top_id
     bool past_end = false;   // wildcard: a read / skip found nothing (wildcard.rs `past_end`)
     // result of an evaluated AND / OR (or a leaf that is read directly)
@@ -2024,6 +2026,7 @@ struct NodeIter {
     size_t pos = 0;
     II_IndexResult res;
     ~NodeIter() {
+        if (host_term && host_term_free) host_term_free(host_term);
         if (pl) {
             if (cache)
                 II_TermCache_Release(cache, 1, &pl);
@@ -2342,6 +2345,123 @@ II_QueryIterator *II_NewTermIterator_FromIndex(const void *inverted_index, II_Co
     if (!pl) return nullptr;
     II_QueryIterator *it = II_NewTermIterator(pl, cache ? 0 : 1, weight, idf, bm25_idf);
     if (it && cache) NI(it)->cache = cache;
+    return it;
+}
+
+// ---- the term leaf with the reference's OWN name and signature (RS/headers/iterators_ffi.h:404) ---------------------------
+// What Term::new does (RS/rqe_iterators/src/inverted_index/term.rs:77-100) with what the host process exports:
+//   codec        <- InvertedIndex_Flags(idx) & INDEX_STORAGE_MASK   (the table of NewInvertedIndex_Ex,
+//                   RS/c_entrypoint/inverted_index_ffi/src/lib.rs:49-165; II_CodecFromIndexFlags)
+//   total_docs   <- IndexSpec_GetStats(sctx->spec, &stats).numDocs  (src/spec.c:1830; RedisSearchCtx = {redisCtx, spec, ...},
+//                   src/search_ctx.h:60-64)
+//   term_docs    <- InvertedIndex_NumDocs(idx)                      (unique docs, inverted_index_ffi.h:434)
+//   the IDFs are computed (RS/idf/src/lib.rs) and stored into the term with QueryTerm_SetIDFs so that the host's scorers see
+//   them too; the term is owned by the iterator and released with Term_Free.
+// The field-mask filter of the Mask variant is applied at decode time (FilterMaskReader); the Index variant only selects
+// field-expiration checks, which this library does not do.  NULL (nothing consumed, the term still the caller's) when the host
+// does not export an accessor, or the index cannot be represented: the caller keeps the reference's iterator.
+namespace {
+II_TermCache *g_default_cache = nullptr;
+int g_raw_docid_encoding = 0;
+struct RSIndexStatsHost { // src/redisearch.h:245-249
+    size_t numDocs, numTerms;
+    double avgDocLen;
+};
+} // namespace
+void II_SetDefaultTermCache(II_TermCache *cache) { g_default_cache = cache; }
+void II_SetRawDocIdEncoding(int raw) { g_raw_docid_encoding = raw; }
+int II_CodecFromIndexFlags(uint32_t flags, int raw_doc_id_encoding) {
+    constexpr uint32_t kOffsets = 0x01, kFields = 0x02, kFreqs = 0x10, kNumeric = 0x20, kWide = 0x80; // src/spec.h:171-181
+    switch (flags & (kOffsets | kFields | kFreqs | kNumeric | kWide)) {
+    case kFreqs | kOffsets | kFields: return II_CODEC_FULL;
+    case kFreqs | kOffsets | kFields | kWide: return II_CODEC_FULL_WIDE;
+    case kFreqs | kFields: return II_CODEC_FREQS_FIELDS;
+    case kFreqs | kFields | kWide: return II_CODEC_FREQS_FIELDS_WIDE;
+    case kFreqs: return II_CODEC_FREQS_ONLY;
+    case kFields: return II_CODEC_FIELDS_ONLY;
+    case kFields | kWide: return II_CODEC_FIELDS_ONLY_WIDE;
+    case kFields | kOffsets: return II_CODEC_FIELDS_OFFSETS;
+    case kFields | kOffsets | kWide: return II_CODEC_FIELDS_OFFSETS_WIDE;
+    case kOffsets: return II_CODEC_OFFSETS_ONLY;
+    case kFreqs | kOffsets: return II_CODEC_FREQS_OFFSETS;
+    case 0: return raw_doc_id_encoding ? II_CODEC_RAW_DOCIDS_ONLY : II_CODEC_DOCIDS_ONLY;
+    default: return -1; // numeric (II_NumericList_*) or a combination NewInvertedIndex_Ex panics on
+    }
+}
+II_QueryIterator *NewInvIndIterator_TermQuery(const void *idx, const void *sctx, II_FieldMaskOrIndex field_mask_or_index, void *term,
+                                              double weight) {
+    struct Api {
+        uint32_t (*Flags)(const void *) = nullptr;
+        uint32_t (*NumDocs)(const void *) = nullptr;
+        void (*GetStats)(void *, RSIndexStatsHost *) = nullptr;
+        void (*SetIDFs)(void *, double, double) = nullptr;
+        void (*TermFree)(void *) = nullptr;
+        bool ok = false;
+    };
+    static Api api = [] {
+        Api a;
+        a.Flags = reinterpret_cast<decltype(a.Flags)>(dlsym(RTLD_DEFAULT, "InvertedIndex_Flags"));
+        a.NumDocs = reinterpret_cast<decltype(a.NumDocs)>(dlsym(RTLD_DEFAULT, "InvertedIndex_NumDocs"));
+        a.GetStats = reinterpret_cast<decltype(a.GetStats)>(dlsym(RTLD_DEFAULT, "IndexSpec_GetStats"));
+        a.SetIDFs = reinterpret_cast<decltype(a.SetIDFs)>(dlsym(RTLD_DEFAULT, "QueryTerm_SetIDFs"));
+        a.TermFree = reinterpret_cast<decltype(a.TermFree)>(dlsym(RTLD_DEFAULT, "Term_Free"));
+        a.ok = a.Flags && a.NumDocs && a.GetStats && a.SetIDFs && a.TermFree;
+        return a;
+    }();
+    if (!api.ok || !idx || !sctx || !term) return nullptr;
+    const int codec = II_CodecFromIndexFlags(api.Flags(idx), g_raw_docid_encoding);
+    if (codec < 0) return nullptr;
+    void *spec = static_cast<void *const *>(sctx)[1];
+    if (!spec) return nullptr;
+    RSIndexStatsHost st{};
+    api.GetStats(spec, &st);
+    const size_t term_docs = api.NumDocs(idx);
+    const double idf = II_CalculateIDF(st.numDocs, term_docs), bm25_idf = II_CalculateIDF_BM25(st.numDocs, term_docs);
+    II_QueryIterator *it = nullptr;
+    const bool masked = field_mask_or_index.tag == 1 /* FieldMaskOrIndex_Mask */ && ~field_mask_or_index.mask != 0 /* not RS_FIELDMASK_ALL */ &&
+                        ii_codec_has_mask(codec);
+    if (!masked) {
+        it = II_NewTermIterator_FromIndex(idx, (II_Codec)codec, weight, idf, bm25_idf, g_default_cache);
+    } else { // FilterMaskReader: decode with the filter (not cached: the cache holds unfiltered lists)
+        struct BlockApi {
+            size_t (*NumBlocks)(const void *) = nullptr;
+            const void *(*BlockRef)(const void *, size_t) = nullptr;
+            const char *(*Data)(const void *) = nullptr;
+            size_t (*DataLen)(const void *) = nullptr;
+            uint64_t (*FirstId)(const void *) = nullptr;
+            uint64_t (*LastId)(const void *) = nullptr;
+            uint16_t (*NumEntries)(const void *) = nullptr;
+        } b;
+        b.NumBlocks = reinterpret_cast<decltype(b.NumBlocks)>(dlsym(RTLD_DEFAULT, "InvertedIndex_NumBlocks"));
+        b.BlockRef = reinterpret_cast<decltype(b.BlockRef)>(dlsym(RTLD_DEFAULT, "InvertedIndex_BlockRef"));
+        b.Data = reinterpret_cast<decltype(b.Data)>(dlsym(RTLD_DEFAULT, "IndexBlock_Data"));
+        b.DataLen = reinterpret_cast<decltype(b.DataLen)>(dlsym(RTLD_DEFAULT, "IndexBlock_DataLen"));
+        b.FirstId = reinterpret_cast<decltype(b.FirstId)>(dlsym(RTLD_DEFAULT, "IndexBlock_FirstId"));
+        b.LastId = reinterpret_cast<decltype(b.LastId)>(dlsym(RTLD_DEFAULT, "IndexBlock_LastId"));
+        b.NumEntries = reinterpret_cast<decltype(b.NumEntries)>(dlsym(RTLD_DEFAULT, "IndexBlock_NumEntries"));
+        if (!(b.NumBlocks && b.BlockRef && b.Data && b.DataLen && b.FirstId && b.LastId && b.NumEntries)) return nullptr;
+        const size_t nb = b.NumBlocks(idx);
+        std::vector<II_BlockView> views(nb);
+        for (size_t i = 0; i < nb; i++) {
+            const void *blk = b.BlockRef(idx, i);
+            views[i] = II_BlockView{b.FirstId(blk), b.LastId(blk), b.NumEntries(blk), reinterpret_cast<const uint8_t *>(b.Data(blk)), b.DataLen(blk)};
+        }
+        const uint64_t f128[2] = {(uint64_t)field_mask_or_index.mask, (uint64_t)(field_mask_or_index.mask >> 64)};
+        II_PostingList *pl = nullptr;
+        if (ii_codec_is_wide(codec)) {
+            pl = II_PostingList_FromBlocksWideMask(views.data(), nb, (II_Codec)codec, f128, 1);
+        } else if ((uint32_t)f128[0] == 0) {
+            it = II_NewEmptyIterator(); // a 32-bit-mask index cannot meet a filter whose low 32 bits are clear
+        } else {
+            pl = II_PostingList_FromBlocks(views.data(), nb, (II_Codec)codec, (uint32_t)f128[0], 1);
+        }
+        if (pl) it = II_NewTermIterator(pl, 1, weight, idf, bm25_idf);
+    }
+    if (!it) return nullptr;
+    api.SetIDFs(term, idf, bm25_idf);
+    NI(it)->host_term = term;
+    NI(it)->host_term_free = api.TermFree;
+    if (it->type != II_IteratorType_Empty) it->type = 1; // IteratorType_InvIdxTerm
     return it;
 }
 

@@ -92,6 +92,9 @@ SIGNATURES = [
     ("II_NewResultIterator", _QI, [_P, C.c_double]),
     ("II_IntersectEx", _P, [_P, _P, _SZ]),
     ("II_IntersectBatch", _SZ, [_SZ, _P, _P, _P]),
+    ("II_SetDefaultTermCache", None, [_P]),
+    ("II_SetRawDocIdEncoding", None, [C.c_int]),
+    ("II_CodecFromIndexFlags", C.c_int, [C.c_uint32, C.c_int]),
     ("II_NumericList_FromBlocks", _P, [C.POINTER(II_BlockView), _SZ]),
     ("II_NumericList_Len", _SZ, [_P]),
     ("II_NumericList_Fetch", C.c_int, [_P, _P, _P]),

@@ -44,6 +44,18 @@ uint64_t IndexBlock_FirstId(const void *b) { return ((const ToyBlock *)b)->first
 uint64_t IndexBlock_LastId(const void *b) { return ((const ToyBlock *)b)->last; }
 uint16_t IndexBlock_NumEntries(const void *b) { return ((const ToyBlock *)b)->n; }
 
+/* what NewInvIndIterator_TermQuery resolves in the host besides the block accessors */
+uint32_t InvertedIndex_Flags(const void *ii) { (void)ii; return 0x10; /* Index_StoreFreqs: the FreqsOnly encoding */ }
+uint32_t InvertedIndex_NumDocs(const void *ii) { return (uint32_t)((const ToyIndex *)ii)->entries; }
+typedef struct { size_t numDocs, numTerms; double avgDocLen; } ToyStats;
+typedef struct { ToyStats stats; } ToySpec;                    /* stands for IndexSpec */
+typedef struct { void *redisCtx; ToySpec *spec; } ToySearchCtx; /* src/search_ctx.h:60-64 */
+void IndexSpec_GetStats(void *sp, ToyStats *out) { *out = ((ToySpec *)sp)->stats; }
+typedef struct { double idf, bm25_idf; int freed; } ToyTerm;    /* stands for RSQueryTerm */
+void QueryTerm_SetIDFs(void *t, double idf, double bm25_idf) { ((ToyTerm *)t)->idf = idf, ((ToyTerm *)t)->bm25_idf = bm25_idf; }
+static int g_terms_freed;
+void Term_Free(void *t) { ((ToyTerm *)t)->freed = 1; g_terms_freed++; }
+
 static size_t put(uint8_t *p, uint32_t v) { /* minimal little-endian bytes, at least one */
     size_t n = 0;
     do {
@@ -295,6 +307,37 @@ int main(int argc, char **argv) {
         it->Free(it);
         II_TermCacheStats cs = II_TermCache_GetStats(cache);
         printf("cache hits %zu misses %zu\n", cs.hits, cs.misses);
+    }
+    /* variant 4: A & B with the leaves built by NewInvIndIterator_TermQuery — the reference's own constructor signature; codec,
+     * IDFs and ownership of the term come from the host accessors above */
+    {
+        typedef II_QueryIterator *(*TermFn)(const void *, const void *, II_FieldMaskOrIndex, void *, double);
+        typedef void (*SetCacheFn)(II_TermCache *);
+        SYM(TermFn, NewInvIndIterator_TermQuery);
+        SYM(SetCacheFn, II_SetDefaultTermCache);
+        II_SetDefaultTermCache(cache);
+        ToySpec spec = {{n_docs, 0, avg}};
+        ToySearchCtx sctx = {NULL, &spec};
+        ToyTerm *ta = calloc(1, sizeof(*ta)), *tb = calloc(1, sizeof(*tb));
+        II_FieldMaskOrIndex all;
+        memset(&all, 0, sizeof(all));
+        all.tag = 1;
+        all.mask = ~(unsigned __int128)0; /* RS_FIELDMASK_ALL */
+        II_QueryIterator **its = malloc(2 * sizeof(*its));
+        its[0] = NewInvIndIterator_TermQuery(ix[0], &sctx, all, ta, 1.0);
+        its[1] = NewInvIndIterator_TermQuery(ix[1], &sctx, all, tb, 1.0);
+        if (!its[0] || !its[1]) return 20;
+        if (its[0]->type != 1) return 21;
+        if (ta->idf != II_CalculateIDF(n_docs, n[0]) || tb->bm25_idf != II_CalculateIDF_BM25(n_docs, n[1])) return 22; /* stored into the terms */
+        II_QueryIterator *it = NewIntersectionIterator(its, 2, -1, false, 1.0);
+        if (!it) return 23;
+        if (g_terms_freed != 2) return 24; /* the leaves owned the terms; the constructor consumed the leaves */
+        printf("variant 4 estimated %zu\n", it->NumEstimated(it));
+        while (it->Read(it) == ITERATOR_OK) printf("%llu %a %u\n", (unsigned long long)it->lastDocId, bm25(&args, it->current, NULL, 0.0), it->current->freq);
+        it->Free(it);
+        II_TermCacheStats cs = II_TermCache_GetStats(cache);
+        printf("cache hits %zu misses %zu\n", cs.hits, cs.misses);
+        II_SetDefaultTermCache(NULL);
     }
     /* union of A and foreign C through the reference's NewUnionIterator signature */
     {

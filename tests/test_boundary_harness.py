@@ -96,8 +96,9 @@ def test_constructors_and_scorer_extension_from_a_c_host(tmp_path):
             out.append((int(d), float.fromhex(s), int(f)))
         raise AssertionError("no cache line")
 
+    # variant 4: the leaves came from NewInvIndIterator_TermQuery (the reference's signature): same rows as a plain A & B
     for variant, exp in ((0, expect(["a", "b", "c"], foreign=("c",))), (1, expect(["a", "b", "c"], foreign=("c",))),
-                         (2, expect(["a", "b"], excluded=("d",))), (3, expect(["a", "b"], optional=("e",)))):
+                         (2, expect(["a", "b"], excluded=("d",))), (3, expect(["a", "b"], optional=("e",))), (4, expect(["a", "b"]))):
         got, cache_line = block(variant)
         assert len(got) == len(exp) and len(exp) > 100, (variant, len(got), len(exp))
         assert [g[0] for g in got] == [e[0] for e in exp], variant

@@ -162,3 +162,18 @@ def test_wildcard_iterator_contract_known_answers():
     assert q.SkipTo(it, 11) == ps.ITERATOR_EOF and q.atEOF and q.lastDocId == 3  # beyond the range: the position stays
     assert q.SkipTo(it, 4) == ps.ITERATOR_EOF
     q.Free(it)
+
+
+def test_index_flags_to_codec_table():
+    """II_CodecFromIndexFlags == the match of NewInvertedIndex_Ex (RS/c_entrypoint/inverted_index_ffi/src/lib.rs:49-165) over the
+    storage flags of src/spec.h:171-181."""
+    from redisearch_b200 import postings as ps
+
+    L = ps.lib()
+    OFF, FLD, FRQ, NUM, BYTEOFF, WIDE = 0x01, 0x02, 0x10, 0x20, 0x40, 0x80
+    table = {FRQ | OFF | FLD: ps.CODEC_FULL, FRQ | OFF | FLD | WIDE: 9, FRQ | FLD: ps.CODEC_FREQS_FIELDS, FRQ | FLD | WIDE: 10,
+             FRQ: ps.CODEC_FREQS_ONLY, FLD: ps.CODEC_FIELDS_ONLY, FLD | WIDE: 11, FLD | OFF: 8, FLD | OFF | WIDE: 12, OFF: 7, FRQ | OFF: 6}
+    for flags, codec in table.items():
+        assert L.II_CodecFromIndexFlags(flags, 0) == codec and L.II_CodecFromIndexFlags(flags | BYTEOFF | 0x100, 1) == codec
+    assert L.II_CodecFromIndexFlags(0, 0) == ps.CODEC_DOCIDS_ONLY and L.II_CodecFromIndexFlags(0, 1) == ps.CODEC_RAW_DOCIDS_ONLY
+    assert L.II_CodecFromIndexFlags(NUM, 0) == -1 and L.II_CodecFromIndexFlags(FRQ | WIDE, 0) == -1
