@@ -141,6 +141,22 @@ size_t II_PostingList_FromBlocksBatch(size_t n_lists, const II_BlockView *const 
 size_t II_PostingList_FromBlocksBatchOffsets(size_t n_lists, const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec,
                                              II_PostingList **out);
 int II_PostingList_HasOffsets(const II_PostingList *pl);
+/* The index WRITER — InvertedIndex::add_record (RS/inverted_index/src/index/core.rs:235-358): 100 entries per block (1000 for the
+ * docId-only codecs), delta from the previous docId (from the block's first docId for RawDocIdsOnly), a fresh block when the delta
+ * does not fit the encoder, a repeated docId dropped (term codecs) or kept in the same block (numeric: multi-value documents).
+ * The blocks are byte-identical to the reference's for the same records.  Host code; no device involved. */
+typedef struct II_IndexWriter II_IndexWriter;
+II_IndexWriter *II_IndexWriter_New(II_Codec codec);
+II_IndexWriter *II_IndexWriter_NewNumeric(int compress_floats); /* Numeric / NumericFloatCompression */
+/* bytes appended (0: the record was dropped).  mask = {lo, hi} halves of the u128 field mask; offsets = varint position deltas */
+size_t II_IndexWriter_Add(II_IndexWriter *w, uint64_t doc_id, uint32_t freq, uint64_t mask_lo, uint64_t mask_hi, const uint8_t *offsets,
+                          uint32_t offsets_len);
+size_t II_IndexWriter_AddNumeric(II_IndexWriter *w, uint64_t doc_id, double value);
+size_t II_IndexWriter_NumBlocks(const II_IndexWriter *w);
+size_t II_IndexWriter_NumDocs(const II_IndexWriter *w); /* unique documents */
+int II_IndexWriter_Block(const II_IndexWriter *w, size_t i, II_BlockView *out); /* valid until the next Add / Free */
+void II_IndexWriter_Free(II_IndexWriter *w);
+
 /* NUMERIC index blocks (the leaves of the reference's numeric range tree; RS/inverted_index/src/codec/numeric.rs: header byte,
  * 0-7 delta bytes, tiny / integer / f32 / f64 / infinite value; duplicates of a docId allowed = multi-value documents) decoded on
  * the device into (docId, value) arrays, and range filters over them (NumericFilter::value_in_range, reader/numeric.rs:80-85):

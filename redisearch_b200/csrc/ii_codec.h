@@ -223,4 +223,125 @@ II_HD bool ii_numeric_in_range(double value, double min, double max, bool min_in
     return min_ok && max_ok;
 }
 
+// ---- encoders (host side: the index writer, II_IndexWriter) — the inverse of the decoders above ---------------------------
+// qint (RS/qint/src/lib.rs:149-215): lead byte + each value in its minimal number of little-endian bytes (at least one)
+inline size_t ii_qint_encode(const uint32_t *vals, int n, uint8_t *out) {
+    uint8_t lead = 0;
+    size_t pos = 1;
+    for (int i = 0; i < n; i++) {
+        uint32_t v = vals[i];
+        int bytes = 0;
+        do {
+            out[pos++] = (uint8_t)v;
+            bytes++;
+            v >>= 8;
+        } while (v);
+        lead |= (uint8_t)((bytes - 1) << (2 * i));
+    }
+    out[0] = lead;
+    return pos;
+}
+// varint of up to 128 bits (RS/varint/src/lib.rs:113-160): 7-bit groups, most significant first, minus one per continuation
+inline size_t ii_varint_encode(uint64_t lo, uint64_t hi, uint8_t *out) {
+    uint8_t buf[24];
+    int pos = 23;
+    unsigned __int128 v = ((unsigned __int128)hi << 64) | lo;
+    buf[pos] = (uint8_t)(v & 0x7f);
+    v >>= 7;
+    while (v) {
+        pos--;
+        v -= 1;
+        buf[pos] = (uint8_t)(0x80 | (uint8_t)(v & 0x7f));
+        v >>= 7;
+    }
+    for (int i = pos; i < 24; i++) out[i - pos] = buf[i];
+    return (size_t)(24 - pos);
+}
+// one term record; `out` needs 48 + off_len bytes.  The narrow codecs take the low 32 bits of the mask.
+inline size_t ii_encode_record(int codec, uint32_t delta, uint32_t freq, uint64_t mask_lo, uint64_t mask_hi, const uint8_t *offsets,
+                               uint32_t off_len, uint8_t *out) {
+    size_t n = 0;
+    const uint32_t m32 = (uint32_t)mask_lo;
+    bool with_offsets = false;
+    switch (codec) {
+    case 0: { const uint32_t v[4] = {delta, freq, m32, off_len}; n = ii_qint_encode(v, 4, out); with_offsets = true; break; }
+    case 1: { const uint32_t v[2] = {delta, freq}; n = ii_qint_encode(v, 2, out); break; }
+    case 2: { const uint32_t v[3] = {delta, freq, m32}; n = ii_qint_encode(v, 3, out); break; }
+    case 3: { const uint32_t v[2] = {delta, m32}; n = ii_qint_encode(v, 2, out); break; }
+    case 4: n = ii_varint_encode(delta, 0, out); break;
+    case 5: out[0] = (uint8_t)delta, out[1] = (uint8_t)(delta >> 8), out[2] = (uint8_t)(delta >> 16), out[3] = (uint8_t)(delta >> 24); n = 4; break;
+    case 6: { const uint32_t v[3] = {delta, freq, off_len}; n = ii_qint_encode(v, 3, out); with_offsets = true; break; }
+    case 7: { const uint32_t v[2] = {delta, off_len}; n = ii_qint_encode(v, 2, out); with_offsets = true; break; }
+    case 8: { const uint32_t v[3] = {delta, m32, off_len}; n = ii_qint_encode(v, 3, out); with_offsets = true; break; }
+    case 9: { const uint32_t v[3] = {delta, freq, off_len}; n = ii_qint_encode(v, 3, out); n += ii_varint_encode(mask_lo, mask_hi, out + n); with_offsets = true; break; }
+    case 10: { const uint32_t v[2] = {delta, freq}; n = ii_qint_encode(v, 2, out); n += ii_varint_encode(mask_lo, mask_hi, out + n); break; }
+    case 11: n = ii_varint_encode(delta, 0, out); n += ii_varint_encode(mask_lo, mask_hi, out + n); break;
+    case 12: { const uint32_t v[2] = {delta, off_len}; n = ii_qint_encode(v, 2, out); n += ii_varint_encode(mask_lo, mask_hi, out + n); with_offsets = true; break; }
+    default: return 0;
+    }
+    if (with_offsets) {
+        for (uint32_t i = 0; i < off_len; i++) out[n + i] = offsets[i];
+        n += off_len;
+    }
+    return n;
+}
+// one numeric record (RS/inverted_index/src/codec/numeric.rs: Value::from :790-838, encode_value :363-520); out >= 17 bytes
+inline size_t ii_encode_numeric(uint64_t delta, double value, bool compress_floats, uint8_t *out) {
+    auto trim = [](uint64_t v, uint8_t *dst) {
+        size_t n = 0;
+        while (v) {
+            dst[n++] = (uint8_t)v;
+            v >>= 8;
+        }
+        return n;
+    };
+    uint8_t d[8], v[8];
+    const size_t nd = trim(delta, d);
+    size_t nv = 0;
+    uint8_t type = 0, upper = 0;
+    union { double f; uint64_t u; } cv;
+    cv.f = value;
+    const bool neg = (cv.u >> 63) != 0;
+    const double a = neg ? -value : value; // |value| (NaN stays NaN)
+    uint64_t u = 0; // `abs as u64` saturates: NaN -> 0, >= 2^64 -> u64::MAX
+    if (a == a) u = a >= 18446744073709551616.0 ? ~0ull : (uint64_t)a;
+    const bool is_inf = a > 1.7976931348623157e308;
+    if ((double)u == a) {
+        if ((double)(u & 7) == value) {
+            type = 0, upper = (uint8_t)u; // TINY (also -0.0)
+        } else {
+            type = neg ? 3 : 2;
+            nv = trim(u, v);
+            upper = (uint8_t)(nv - 1);
+        }
+    } else if (is_inf) {
+        type = 1, upper = neg ? 3 : 1;
+    } else {
+        type = 1;
+        const float f32 = (float)a;
+        const double diff = a - (double)f32;
+        if ((double)f32 == a || (compress_floats && (diff < 0 ? -diff : diff) < 0.01)) {
+            if (f32 == 0.0f) {
+                type = 0, upper = 0;
+            } else {
+                upper = neg ? 2 : 0;
+                union { float f; uint32_t w; } c32;
+                c32.f = f32;
+                v[0] = (uint8_t)c32.w, v[1] = (uint8_t)(c32.w >> 8), v[2] = (uint8_t)(c32.w >> 16), v[3] = (uint8_t)(c32.w >> 24);
+                nv = 4;
+            }
+        } else {
+            upper = neg ? 6 : 4;
+            union { double f; uint64_t w; } c64;
+            c64.f = a;
+            for (int i = 0; i < 8; i++) v[i] = (uint8_t)(c64.w >> (8 * i));
+            nv = 8;
+        }
+    }
+    out[0] = (uint8_t)((upper << 5) | (type << 3) | (uint8_t)nd);
+    for (size_t i = 0; i < nd; i++) out[1 + i] = d[i];
+    for (size_t i = 0; i < nv; i++) out[1 + nd + i] = v[i];
+    return 1 + nd + nv;
+}
+
 } // namespace rsb200

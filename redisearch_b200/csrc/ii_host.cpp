@@ -3,6 +3,7 @@
 #include "../../include/ii_b200.h"
 #include "ii_kernels.h"
 #include "ii_codec.h"
+#include <functional>
 
 #include <dlfcn.h>
 
@@ -565,6 +566,92 @@ II_PostingList *II_PostingList_FromDevice(const uint32_t *d_doc_ids, const uint3
     }
     pl->n = pl->estimated = n;
     return pl;
+}
+
+// ---- the index WRITER: InvertedIndex::add_record (RS/inverted_index/src/index/core.rs:235-358) for every term codec and the
+// numeric one — the ingest side of posting storage: the IndexBlocks it produces are byte-identical to the reference's
+// (tests/test_index_writer.py against the oracle restatement and the reference's golden vectors), so a host can keep its postings
+// in this library's blocks and hand them to the decoders above without an encoding of its own.
+struct II_IndexWriter {
+    struct Block {
+        uint64_t first = 0, last = 0;
+        uint16_t n = 0;
+        std::vector<uint8_t> buf;
+    };
+    int codec = 0; // 0..12 term codecs, 13 numeric
+    bool compress_floats = false;
+    std::vector<Block> blocks;
+    size_t unique_docs = 0;
+    bool multi_value = false;
+    uint16_t per_block() const { return (codec == II_CODEC_DOCIDS_ONLY || codec == II_CODEC_RAW_DOCIDS_ONLY) ? 1000 : 100; } // codec/mod.rs:69
+};
+static size_t writer_add(II_IndexWriter *w, uint64_t doc_id, const std::function<size_t(uint64_t delta, uint8_t *out)> &encode, uint64_t max_delta,
+                         bool allow_duplicates, size_t reserve) {
+    const bool have_last = !w->blocks.empty();
+    const bool same_doc = have_last && w->blocks.back().last == doc_id;
+    if (same_doc && !allow_duplicates) return 0; // :244-256: a repeated docId carries nothing new for these codecs
+    if (have_last && doc_id < w->blocks.back().last) return 0; // documents arrive in docId order
+    // take_block :339-358: a full block is only left for a NEW document (the records of one document stay together)
+    if (!have_last || (!same_doc && w->blocks.back().n >= w->per_block())) {
+        w->blocks.emplace_back();
+        w->blocks.back().first = w->blocks.back().last = doc_id;
+    }
+    II_IndexWriter::Block *b = &w->blocks.back();
+    const uint64_t base = (w->codec == II_CODEC_RAW_DOCIDS_ONLY) ? b->first : b->last; // raw_doc_ids_only.rs:40-47
+    uint64_t delta = doc_id - base;
+    if (delta > max_delta) { // :272-285: the delta does not fit this encoder: a fresh block, delta 0
+        w->blocks.emplace_back();
+        b = &w->blocks.back();
+        b->first = b->last = doc_id;
+        delta = 0;
+    }
+    const size_t before = b->buf.size();
+    b->buf.resize(before + reserve);
+    const size_t n = encode(delta, b->buf.data() + before);
+    b->buf.resize(before + n);
+    b->n++;
+    b->last = doc_id;
+    if (same_doc)
+        w->multi_value = true;
+    else
+        w->unique_docs++;
+    return n;
+}
+II_IndexWriter *II_IndexWriter_New(II_Codec codec) {
+    if ((int)codec < 0 || (int)codec >= kNumCodecs) return nullptr;
+    auto *w = new II_IndexWriter();
+    w->codec = (int)codec;
+    return w;
+}
+II_IndexWriter *II_IndexWriter_NewNumeric(int compress_floats) {
+    auto *w = new II_IndexWriter();
+    w->codec = 13;
+    w->compress_floats = compress_floats != 0;
+    return w;
+}
+void II_IndexWriter_Free(II_IndexWriter *w) { delete w; }
+size_t II_IndexWriter_Add(II_IndexWriter *w, uint64_t doc_id, uint32_t freq, uint64_t mask_lo, uint64_t mask_hi, const uint8_t *offsets,
+                          uint32_t offsets_len) {
+    if (!w || w->codec > 12) return 0;
+    if (!ii_codec_has_offsets(w->codec)) offsets_len = 0;
+    return writer_add(
+        w, doc_id,
+        [&](uint64_t delta, uint8_t *out) { return ii_encode_record(w->codec, (uint32_t)delta, freq, mask_lo, mask_hi, offsets, offsets_len, out); },
+        0xFFFFFFFFull, false, 64 + (size_t)offsets_len);
+}
+size_t II_IndexWriter_AddNumeric(II_IndexWriter *w, uint64_t doc_id, double value) {
+    if (!w || w->codec != 13) return 0;
+    return writer_add(
+        w, doc_id, [&](uint64_t delta, uint8_t *out) { return ii_encode_numeric(delta, value, w->compress_floats, out); },
+        ((uint64_t)1 << 56) - 1 /* NumericDelta: 7 bytes, numeric.rs:297-305 */, true /* ALLOW_DUPLICATES :323 */, 24);
+}
+size_t II_IndexWriter_NumBlocks(const II_IndexWriter *w) { return w->blocks.size(); }
+size_t II_IndexWriter_NumDocs(const II_IndexWriter *w) { return w->unique_docs; }
+int II_IndexWriter_Block(const II_IndexWriter *w, size_t i, II_BlockView *out) {
+    if (!w || i >= w->blocks.size() || !out) return -1;
+    const auto &b = w->blocks[i];
+    *out = II_BlockView{b.first, b.last, b.n, b.buf.data(), b.buf.size()};
+    return 0;
 }
 
 // ---- numeric index blocks (RS/inverted_index/src/codec/numeric.rs) -> device (docId, value) arrays; range filters over them

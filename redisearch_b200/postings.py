@@ -92,6 +92,14 @@ SIGNATURES = [
     ("II_NewResultIterator", _QI, [_P, C.c_double]),
     ("II_IntersectEx", _P, [_P, _P, _SZ]),
     ("II_IntersectBatch", _SZ, [_SZ, _P, _P, _P]),
+    ("II_IndexWriter_New", _P, [C.c_int]),
+    ("II_IndexWriter_NewNumeric", _P, [C.c_int]),
+    ("II_IndexWriter_Add", _SZ, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _P, C.c_uint32]),
+    ("II_IndexWriter_AddNumeric", _SZ, [_P, C.c_uint64, C.c_double]),
+    ("II_IndexWriter_NumBlocks", _SZ, [_P]),
+    ("II_IndexWriter_NumDocs", _SZ, [_P]),
+    ("II_IndexWriter_Block", C.c_int, [_P, _SZ, C.POINTER(II_BlockView)]),
+    ("II_IndexWriter_Free", None, [_P]),
     ("II_SetDefaultTermCache", None, [_P]),
     ("II_SetRawDocIdEncoding", None, [C.c_int]),
     ("II_CodecFromIndexFlags", C.c_int, [C.c_uint32, C.c_int]),
@@ -184,6 +192,42 @@ class PostingList:
     def __del__(self):
         try:
             self.close()
+        except Exception:
+            pass
+
+
+class IndexWriter:
+    """II_IndexWriter: the reference's add_record on the host (byte-identical IndexBlocks)"""
+
+    def __init__(self, codec=None, numeric=False, compress_floats=False):
+        self.L = lib()
+        self.h = self.L.II_IndexWriter_NewNumeric(int(compress_floats)) if numeric else self.L.II_IndexWriter_New(codec)
+        if not self.h:
+            raise RuntimeError("II_IndexWriter_New failed")
+
+    def add(self, doc_id, freq=1, mask=1, offsets=b""):
+        buf = (C.c_uint8 * max(1, len(offsets))).from_buffer_copy(offsets or b"\0")
+        return self.L.II_IndexWriter_Add(self.h, doc_id, freq, mask & 0xFFFFFFFFFFFFFFFF, mask >> 64, buf, len(offsets))
+
+    def add_numeric(self, doc_id, value):
+        return self.L.II_IndexWriter_AddNumeric(self.h, doc_id, float(value))
+
+    def num_docs(self):
+        return self.L.II_IndexWriter_NumDocs(self.h)
+
+    def blocks(self):
+        out = []
+        for i in range(self.L.II_IndexWriter_NumBlocks(self.h)):
+            v = II_BlockView()
+            assert self.L.II_IndexWriter_Block(self.h, i, C.byref(v)) == 0
+            out.append((v.first_doc_id, v.last_doc_id, v.num_entries, bytes(C.cast(v.data, C.POINTER(C.c_uint8 * v.len)).contents) if v.len else b""))
+        return out
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.II_IndexWriter_Free(self.h)
+                self.h = None
         except Exception:
             pass
 

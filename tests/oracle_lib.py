@@ -523,7 +523,7 @@ def numeric_blocks(doc_ids, values, compress=False, per_block=100):
     blocks, cur, first, last, n = [], b"", 0, 0, 0
     for d, v in zip(doc_ids, values):
         d = int(d)
-        if n == 0 or n >= per_block or (d - last) >> 56:
+        if n == 0 or (n >= per_block and d != last) or (d - last) >> 56:  # take_block: a full block is left for a NEW document only
             if n:
                 blocks.append((first, last, n, cur))
             cur, first, last, n = b"", d, d, 0
