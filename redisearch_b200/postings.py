@@ -472,4 +472,17 @@ def smoke(ol) -> None:
         s = ol.oracle_score(ol.SCORER_BM25STD, [f for _, f in ch], [terms[c][1] for c, _ in ch], [terms[c][2] for c, _ in ch],
                             [1.0] * len(ch), 1.0, int(doc_len[doc]), 1, 1.0, n_docs, avg)
         assert np.float64(s).tobytes() == np.float64(scores[i]).tobytes(), (s, scores[i])
-    print(f"smoke postings ok: {len(ids)} hits of 3-term AND, BM25STD bit-equal to the oracle")
+    # the fused batch route (II_SearchTopNBatch: window pre-pass + membership + scorer + top-N for every query of the batch):
+    # top-10 of the same AND and of two 2-term ANDs, ranked (score desc, docId asc) like RPSorter
+    dt = DocTable(n_docs, doc_len)
+    combos = [(0, 1, 2), (0, 1), (1, 2)]
+    batch = SearchBatch([([pls[c] for c in cb], [terms[c] for c in cb]) for cb in combos], 10)
+    out = batch.run(False, SCORER_BM25STD, 1.0, n_docs, avg, dt)
+    for cb, (bids, bscores, total) in zip(combos, out):
+        r2 = intersect([pls[c] for c in cb])
+        r2.score(SCORER_BM25STD, [terms[c] for c in cb], 1.0, n_docs, avg, dt)
+        i2, s2, _ = r2.fetch()
+        top = np.lexsort((i2, -s2))[:10]
+        assert total == len(i2) and bids.tolist() == i2[top].tolist(), "fused batch top-N differs from the per-query chain"
+        assert bscores.tobytes() == s2[top].tobytes()
+    print(f"smoke postings ok: {len(ids)} hits of 3-term AND, BM25STD bit-equal to the oracle; fused batch top-10 of {len(combos)} queries equal")
