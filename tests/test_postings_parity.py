@@ -522,6 +522,17 @@ def test_fused_batch_search_equals_the_per_query_chains(ps, scorer):
             assert gt == et, (scorer, top_n, gt, et)
             assert gi.tolist() == ei.tolist(), (scorer, top_n, len(lists))
             assert gs.tobytes() == es.tobytes()
+    # batches whose largest child count is 2 and 3: the kernel is instantiated per child count (2 / 3 / 4 / 8)
+    for kmax in (2, 3):
+        small = []
+        for _ in range(40):
+            q = tuple(int(x) for x in rng.choice(6, int(rng.integers(1, kmax + 1)), replace=False))
+            small.append(([pls[i] for i in q], terms_of(q)))
+        small.append(([pls[i] for i in range(kmax)], terms_of(tuple(range(kmax)))))
+        got = ps.SearchBatch(small, 10).run(False, scorer, 1.0, n_docs, avg, dt)
+        for (lists, terms), (gi, gs, gt) in zip(small, got):
+            ei, es, et = ps.search_topn(lists, False, scorer, terms, 1.0, n_docs, avg, dt, 10)
+            assert gt == et and gi.tolist() == ei.tolist() and gs.tobytes() == es.tobytes(), (kmax, len(lists))
     # a few hundred random queries in one call
     many = []
     for _ in range(300):
