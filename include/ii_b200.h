@@ -313,7 +313,7 @@ size_t II_TermCache_Acquire(II_TermCache *cache, size_t n, const uint64_t *keys,
                             const II_BlockView *const *blocks, const size_t *nblocks, II_Codec codec, II_PostingList **out);
 void II_TermCache_Release(II_TermCache *cache, size_t n, II_PostingList *const *lists);
 void II_TermCache_Invalidate(II_TermCache *cache, uint64_t key); /* from the index writer / GC, when it is cheaper than versions */
-/* on: lists decoded from now on keep their term positions (Full codec) so that phrase / slop intersections can use them */
+/* on: lists decoded from now on keep their term positions (any codec that stores them: Full, FreqsOffsets, OffsetsOnly, FieldsOffsets and the wide variants) so that phrase / slop intersections can use them */
 void II_TermCache_KeepOffsets(II_TermCache *cache, int on);
 II_TermCacheStats II_TermCache_GetStats(II_TermCache *cache);
 
