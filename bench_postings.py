@@ -363,37 +363,56 @@ def run_config5(args, Env, build_shard, ClockSampler, load_peaks, usable_cores):
     filt_total = int(fs.sum().item())
     # parity: the reference's distance kernel over the filtered rows of a few queries (ids + fp32 distance bits)
     parity = None
-    if not args.no_parity and world == 1:
+    if not args.no_parity:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as ol
 
-        checked, ids_ok, bits_ok = 0, True, True
-        for i, (r1, r2) in enumerate(HYBRID_TERM_PAIRS):
-            if not (0 < filt_sizes[i] <= 4000):
-                continue
+        # every rank: the reference's answer over ITS shard's filtered rows for the checked queries; the per-shard answers are
+        # merged by (distance, docId) like the device merge and compared with the merged device result
+        fs_host = fs.cpu().numpy()  # global filter sizes
+        pick = [i for i in range(nq) if 0 < fs_host[i] <= 4000 * world][:8]
+        local = []
+        for i in pick:
+            r1, r2 = HYBRID_TERM_PAIRS[i]
             arr = (C.c_void_p * 2)(lists[r1], lists[r2])
             rs = P.II_Intersect(arr, 2)
-            m = P.II_ResultSet_Len(rs)
+            m = P.II_ResultSet_Len(rs) if rs else 0
             ids = np.zeros(m, dtype=np.uint64)
-            assert P.II_ResultSet_Fetch(rs, ids.ctypes.data, None, None) == 0
-            P.II_ResultSet_Free(rs)
+            if m:
+                assert P.II_ResultSet_Fetch(rs, ids.ctypes.data, None, None) == 0
+            if rs:
+                P.II_ResultSet_Free(rs)
             rowbuf = np.empty((m, DIM), dtype=np.float32)
             for j, d in enumerate(ids.tolist()):
                 assert L.VecSimB200_ReadRows(index.h, int(d) - 1 - lo, 1, rowbuf[j].ctypes.data) == 0
             qn = qh[i].copy()
             ol.port().orc_normalize(ol._p(qn), DIM, ol.F32)
             dist = np.empty(m, dtype=np.float32)
-            if ol.ref_vecsim() is not None:
+            if m and ol.ref_vecsim() is not None:
                 ol.ref_vecsim().Ref_Distances(ol.F32, ol.COS, DIM, ol._p(rowbuf), rowbuf.strides[0], m, ol._p(qn), ol._p(dist))
             else:
                 for j in range(m):
                     dist[j] = ol.port().orc_distance(ol.F32, ol.COS, DIM, ol._p(rowbuf[j]), ol._p(qn), ol.TIER_AVX512)
             order = np.lexsort((ids, dist))[:k]
-            ids_ok &= res_l[i][:len(order)].tolist() == ids[order].astype(np.int64).tolist()
-            bits_ok &= res_s[i][:len(order)].astype(np.float32).tobytes() == dist[order].tobytes()
-            checked += 1
-        parity = {"queries": checked, "ids_equal": bool(ids_ok), "score_bits_equal": bool(bits_ok),
-                  "checker": "reference distance kernel (oracle/_ref) over the filtered rows read back from HBM, heap order (distance, docId)"}
+            local.append((ids[order].astype(np.int64), dist[order]))
+        if world > 1:
+            gathered = [None] * world
+            env.dist.all_gather_object(gathered, local)
+            merged = []
+            for x in range(len(pick)):
+                ids = np.concatenate([g[x][0] for g in gathered])
+                dist = np.concatenate([g[x][1] for g in gathered])
+                order = np.lexsort((ids, dist))[:k]
+                merged.append((ids[order], dist[order]))
+            local = merged
+        ids_ok, bits_ok = True, True
+        for x, i in enumerate(pick):
+            n_exp = len(local[x][0])
+            ids_ok &= res_l[i][:n_exp].tolist() == local[x][0].tolist()
+            bits_ok &= res_s[i][:n_exp].astype(np.float32).tobytes() == local[x][1].astype(np.float32).tobytes()
+        parity = {"queries": len(pick), "ids_equal": bool(ids_ok), "score_bits_equal": bool(bits_ok),
+                  "checker": "reference distance kernel (oracle/_ref) over the filtered rows read back from HBM, heap order (distance, docId)"
+                             + ("; per-shard reference answers merged by (distance, docId)" if world > 1 else "")}
     peak, _ = load_peaks()
     if rank == 0:
         alg = filt_total * (DIM * 4 + 12)
