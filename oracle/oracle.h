@@ -188,6 +188,28 @@ double orc_score(int scorer, const OrcIndexStats *st, const OrcScoreDoc *d, int 
  * results: decoded positions of child i at pos[i*stride .. i*stride + npos[i]). */
 int orc_min_offset_delta(size_t n, const uint32_t *npos, const uint32_t *pos, size_t stride, const int *is_virtual);
 
+/* ---- tree_oracle.c: result TREES (nested aggregates) ---------------------------------------------
+ * Node 0 is the root; parent[i] < i; the children of a node are the nodes naming it as parent, in index order (= the
+ * aggregate's child order).  Term nodes carry their varint-delta position bytes (off_len 0 = none). */
+enum { ORC_KIND_TERM = 0, ORC_KIND_INTERSECTION, ORC_KIND_UNION, ORC_KIND_VIRTUAL, ORC_KIND_NUMERIC };
+typedef struct {
+    size_t n_nodes;
+    const int32_t *parent; /* -1 for the root */
+    const int32_t *kind;   /* ORC_KIND_* */
+    const uint32_t *freq;
+    const double *weight, *idf, *bm25_idf;
+    const uint32_t *off_start, *off_len;
+    const uint8_t *bytes;
+} OrcTree;
+/* slop < 0: GetSlop = orc_tree_min_offset_delta of the tree */
+double orc_score_tree(int scorer, const OrcIndexStats *st, const OrcTree *t, uint32_t doc_len, uint32_t max_freq, float doc_score,
+                      int slop, double min_score, double tanh_factor);
+/* RSIndexResult_IterateOffsets of a node: every position in the order yielded; returns the count (out filled up to cap) */
+size_t orc_tree_offsets(const OrcTree *t, size_t node, uint32_t *out, size_t cap);
+int orc_tree_has_offsets(const OrcTree *t, size_t node);
+int orc_tree_min_offset_delta(const OrcTree *t);
+int orc_tree_within_range(const OrcTree *t, int has_slop, uint32_t max_slop, int in_order);
+
 /* Bulk-add every member of vocabulary rank `rank` (synthetic Zipf corpus below); returns the count. */
 size_t orc_ii_fill_synth(OrcInvIndex *ii, uint64_t n_docs, uint64_t rank);
 /* CPU baseline: nq 3-term AND + BM25STD + top-N queries (terms = nq*3 indexes), one query per thread. */

@@ -17,32 +17,64 @@
 #include "types_ffi.h"
 #include "query_term_ffi.h"
 #include "score_explain.h"
+#include "varint_ffi.h"
+#include "buffer.h"
+
+#include <stddef.h>
 
 #define MAX_TERMS 32
+#define MAX_NODES 512
 
 typedef struct {
   double idf, bm25_idf;
   char str[8];
 } HarnessTerm;
 
-static RSIndexResult g_leaves[MAX_TERMS];
-static const RSIndexResult *g_leaf_ptrs[MAX_TERMS];
-static HarnessTerm g_terms[MAX_TERMS];
-static size_t g_nleaves;
-static RSIndexResult g_root;
+/* Result nodes live in a pool; what the Rust side of the reference keeps inside RSIndexResult.data (the children of an
+ * aggregate, the term's offsets and query term) sits in a side table at the same index. */
+typedef struct {
+  size_t nkids;
+  const RSIndexResult *kids[MAX_TERMS];
+  HarnessTerm term;
+  const char *off; /* varint-delta position bytes */
+  uint32_t off_len;
+} Side;
+static RSIndexResult g_nodes[MAX_NODES];
+static Side g_side[MAX_NODES];
+#define g_root g_nodes[0]
+static size_t node_index(const RSIndexResult *r) { return (size_t)(r - g_nodes); }
+static Side *side_of_agg(const RSAggregateResult *agg) {
+  const RSIndexResult *r = (const RSIndexResult *)((const char *)agg - offsetof(RSIndexResult, data));
+  return &g_side[node_index(r)];
+}
+static void pool_reset(void) {
+  memset(g_nodes, 0, sizeof(g_nodes));
+  memset(g_side, 0, sizeof(g_side));
+}
 
-/* ---- accessors default.c needs on the scoring path ---------------------------------------- */
+/* ---- accessors default.c / index_result.c / offset_vector.c need ---------------------------- */
 const RSAggregateResult *IndexResult_AggregateRefUnchecked(const RSIndexResult *r) {
   return (const RSAggregateResult *)&r->data;
 }
+const RSAggregateResult *IndexResult_AggregateRef(const RSIndexResult *r) {
+  return (r->data.tag & (RSResultData_Intersection | RSResultData_Union)) ? (const RSAggregateResult *)&r->data : NULL;
+}
 struct AggregateRecordsSlice AggregateResult_GetRecordsSlice(const RSAggregateResult *agg) {
-  struct AggregateRecordsSlice s = {g_leaf_ptrs, g_nleaves};
+  Side *sd = side_of_agg(agg);
+  struct AggregateRecordsSlice s = {sd->kids, sd->nkids};
   return s;
 }
-size_t AggregateResult_NumChildren(const RSAggregateResult *agg) { return g_nleaves; }
-const RSIndexResult *AggregateResult_Get(const RSAggregateResult *agg, size_t index) { return g_leaf_ptrs[index]; }
+size_t AggregateResult_NumChildren(const RSAggregateResult *agg) { return side_of_agg(agg)->nkids; }
+const RSIndexResult *AggregateResult_Get(const RSAggregateResult *agg, size_t index) { return side_of_agg(agg)->kids[index]; }
+const RSIndexResult *AggregateResult_GetUnchecked(const RSAggregateResult *agg, size_t index) { return side_of_agg(agg)->kids[index]; }
+uint8_t AggregateResult_KindMask(const RSAggregateResult *agg) {
+  Side *sd = side_of_agg(agg);
+  uint8_t m = 0;
+  for (size_t i = 0; i < sd->nkids; i++) m |= (uint8_t)sd->kids[i]->data.tag;
+  return m;
+}
 struct RSQueryTerm *IndexResult_QueryTermRef(const RSIndexResult *r) {
-  return (struct RSQueryTerm *)&g_terms[r - g_leaves];
+  return (struct RSQueryTerm *)&g_side[node_index(r)].term;
 }
 double QueryTerm_GetIDF(const struct RSQueryTerm *t) { return ((const HarnessTerm *)t)->idf; }
 double QueryTerm_GetBM25_IDF(const struct RSQueryTerm *t) { return ((const HarnessTerm *)t)->bm25_idf; }
@@ -51,6 +83,32 @@ const char *QueryTerm_GetStrAndLen(const struct RSQueryTerm *t, size_t *out_len)
   return ((const HarnessTerm *)t)->str;
 }
 void explain(RSScoreExplain *scrExp, char *fmt, ...) {}
+/* term offsets: the slice handle is the side entry itself */
+const RSOffsetSlice *IndexResult_TermOffsetsRef(const RSIndexResult *r) { return (const RSOffsetSlice *)&g_side[node_index(r)]; }
+uint32_t RSOffsetVector_Len(const RSOffsetSlice *offsets) { return ((const Side *)offsets)->off_len; }
+const char *RSOffsetVector_GetData(const RSOffsetSlice *offsets, uint32_t *len) {
+  *len = ((const Side *)offsets)->off_len;
+  return ((const Side *)offsets)->off;
+}
+/* RS/varint (Rust): 7-bit groups, most significant first, +1 per continuation byte (golden vectors: tests/golden) */
+uint32_t ReadVarint(BufferReader *b) {
+  unsigned char c = (unsigned char)BUFFER_READ_BYTE(b);
+  uint32_t val = c & 127;
+  while (c >> 7) {
+    ++val;
+    c = (unsigned char)BUFFER_READ_BYTE(b);
+    val = (val << 7) | (c & 127);
+  }
+  return val;
+}
+static size_t write_varint(uint32_t value, char *out) { /* the inverse, for callers that hand in decoded positions */
+  unsigned char tmp[8];
+  size_t pos = sizeof(tmp) - 1;
+  tmp[pos] = value & 127;
+  while (value >>= 7) tmp[--pos] = 128 | (--value & 127);
+  memcpy(out, tmp + pos, sizeof(tmp) - pos);
+  return sizeof(tmp) - pos;
+}
 
 /* ---- capture the static scorer function pointers ------------------------------------------- */
 #define MAX_SCORERS 16
@@ -85,18 +143,18 @@ double RefScore(const char *scorer, int is_union, size_t n, const uint32_t *freq
   for (int i = 0; i < g_nscorers; i++)
     if (!strcmp(g_scorers[i].name, scorer)) fn = g_scorers[i].fn;
   if (!fn || n > MAX_TERMS) return NAN;
-  memset(&g_root, 0, sizeof(g_root));
-  memset(g_leaves, 0, sizeof(g_leaves));
-  g_nleaves = n;
+  pool_reset();
   uint32_t total = 0;
+  g_side[0].nkids = n;
   for (size_t i = 0; i < n; i++) {
-    g_leaves[i].data.tag = RSResultData_Term;
-    g_leaves[i].freq = freq[i];
-    g_leaves[i].weight = weight[i];
-    g_leaf_ptrs[i] = &g_leaves[i];
-    g_terms[i].idf = idf[i];
-    g_terms[i].bm25_idf = bm25_idf[i];
-    g_terms[i].str[0] = 't';
+    RSIndexResult *leaf = &g_nodes[1 + i];
+    leaf->data.tag = RSResultData_Term;
+    leaf->freq = freq[i];
+    leaf->weight = weight[i];
+    g_side[0].kids[i] = leaf;
+    g_side[1 + i].term.idf = idf[i];
+    g_side[1 + i].term.bm25_idf = bm25_idf[i];
+    g_side[1 + i].term.str[0] = 't';
     total += freq[i];
   }
   g_root.data.tag = is_union ? RSResultData_Union : RSResultData_Intersection;
@@ -118,63 +176,103 @@ double RefScore(const char *scorer, int is_union, size_t n, const uint32_t *freq
 }
 
 
-/* ---- GetSlop: the reference's own IndexResult_MinOffsetDelta (src/index_result/index_result.c:51-108, compiled in place by
- * oracle/Makefile) over DECODED term positions held in a side table.  The accessors below are the ones that file needs;
- * RSIndexResult_IterateOffsets (src/offset_vector.c:147-180) is reduced to its term / virtual cases: an aggregate of term
- * leaves is the only shape the hot path produces. ------------------------------------------------------------------------- */
-#define MAX_POS 256
-static uint32_t g_pos[MAX_TERMS][MAX_POS];
-static uint32_t g_npos[MAX_TERMS];
-typedef struct { uint32_t leaf, i; } PosIter;
-static uint32_t positer_next(void *ctx, RSQueryTerm **t) {
-  PosIter *it = ctx;
-  if (it->i >= g_npos[it->leaf]) return RS_OFFSETVECTOR_EOF;
-  return g_pos[it->leaf][it->i++];
-}
-static void positer_rewind(void *ctx) { ((PosIter *)ctx)->i = 0; }
-static void positer_free(void *ctx) { free(ctx); }
-static uint32_t emptyiter_next(void *ctx, RSQueryTerm **t) { return RS_OFFSETVECTOR_EOF; }
-static void emptyiter_noop(void *ctx) {}
-RSOffsetIterator RSIndexResult_IterateOffsets(const RSIndexResult *res) {
-  if (res->data.tag != RSResultData_Term) {
-    RSOffsetIterator e = {.ctx = NULL, .Next = emptyiter_next, .Rewind = emptyiter_noop, .Free = emptyiter_noop};
-    return e;
-  }
-  PosIter *it = malloc(sizeof(*it));
-  it->leaf = (uint32_t)(res - g_leaves);
-  it->i = 0;
-  RSOffsetIterator r = {.ctx = it, .Next = positer_next, .Rewind = positer_rewind, .Free = positer_free};
-  return r;
-}
-const RSOffsetSlice *IndexResult_TermOffsetsRef(const RSIndexResult *r) { return (const RSOffsetSlice *)&g_npos[r - g_leaves]; }
-uint32_t RSOffsetVector_Len(const RSOffsetSlice *offsets) { return *(const uint32_t *)offsets; }
-const RSAggregateResult *IndexResult_AggregateRef(const RSIndexResult *r) {
-  return (r->data.tag & (RSResultData_Intersection | RSResultData_Union)) ? (const RSAggregateResult *)&r->data : NULL;
-}
-const RSIndexResult *AggregateResult_GetUnchecked(const RSAggregateResult *agg, size_t index) { return g_leaf_ptrs[index]; }
-uint8_t AggregateResult_KindMask(const RSAggregateResult *agg) {
-  uint8_t m = 0;
-  for (size_t i = 0; i < g_nleaves; i++) m |= (uint8_t)g_leaves[i].data.tag;
-  return m;
-}
+/* ---- GetSlop: the reference's own IndexResult_MinOffsetDelta (src/index_result/index_result.c:51-108) over the reference's own
+ * offset iterators (src/offset_vector.c: the term iterator reading varint deltas, the aggregate iterator merging its children),
+ * both compiled in place by oracle/Makefile. ------------------------------------------------------------------------------- */
 int IndexResult_MinOffsetDelta(const RSIndexResult *r);
+int RSIndexResult_HasOffsets(const RSIndexResult *res);
+static char g_bytes[1 << 16];
 
 /* n children of an intersection / union; child i is a term leaf with npos[i] decoded positions pos[i*stride ..] (npos 0 = a term
  * without offsets), or a virtual result when is_virtual[i] (NOT / absent OPTIONAL children).  Returns what GetSlop returns. */
 int RefMinOffsetDelta(int is_union, size_t n, const uint32_t *npos, const uint32_t *pos, size_t stride, const int *is_virtual) {
   if (n > MAX_TERMS) return -1;
-  memset(&g_root, 0, sizeof(g_root));
-  memset(g_leaves, 0, sizeof(g_leaves));
-  g_nleaves = n;
+  pool_reset();
+  size_t used = 0;
+  g_side[0].nkids = n;
   for (size_t i = 0; i < n; i++) {
-    if (npos[i] > MAX_POS) return -1;
-    g_leaves[i].data.tag = (is_virtual && is_virtual[i]) ? RSResultData_Virtual : RSResultData_Term;
-    g_leaf_ptrs[i] = &g_leaves[i];
-    g_npos[i] = npos[i];
-    memcpy(g_pos[i], pos + i * stride, npos[i] * sizeof(uint32_t));
+    RSIndexResult *leaf = &g_nodes[1 + i];
+    leaf->data.tag = (is_virtual && is_virtual[i]) ? RSResultData_Virtual : RSResultData_Term;
+    g_side[0].kids[i] = leaf;
+    if (used + 5 * (size_t)npos[i] > sizeof(g_bytes)) return -1;
+    g_side[1 + i].off = g_bytes + used;
+    uint32_t last = 0;
+    for (uint32_t k = 0; k < npos[i]; k++) {
+      used += write_varint(pos[i * stride + k] - last, g_bytes + used);
+      last = pos[i * stride + k];
+    }
+    g_side[1 + i].off_len = (uint32_t)((g_bytes + used) - g_side[1 + i].off);
   }
   g_root.data.tag = is_union ? RSResultData_Union : RSResultData_Intersection;
   return IndexResult_MinOffsetDelta(&g_root);
+}
+
+/* ---- result TREES: node 0 is the root, parent[i] < i, children in index order; kind 0 term, 1 intersection, 2 union, 3 virtual,
+ * 4 numeric (the numbering of oracle.h's ORC_KIND_*).  Term nodes: varint-delta position bytes bytes[off_start .. +off_len). */
+static const uint8_t kTag[5] = {RSResultData_Term, RSResultData_Intersection, RSResultData_Union, RSResultData_Virtual, RSResultData_Numeric};
+int RefTreeLoad(size_t n_nodes, const int32_t *parent, const int32_t *kind, const uint32_t *freq, const double *weight,
+                const double *idf, const double *bm25_idf, const uint32_t *off_start, const uint32_t *off_len, const char *bytes) {
+  if (n_nodes == 0 || n_nodes > MAX_NODES) return -1;
+  pool_reset();
+  for (size_t i = 0; i < n_nodes; i++) {
+    if (kind[i] < 0 || kind[i] > 4) return -1;
+    g_nodes[i].data.tag = kTag[kind[i]];
+    g_nodes[i].freq = freq[i];
+    g_nodes[i].weight = weight[i];
+    g_side[i].term.idf = idf[i];
+    g_side[i].term.bm25_idf = bm25_idf[i];
+    g_side[i].term.str[0] = 't';
+    g_side[i].off = bytes + off_start[i];
+    g_side[i].off_len = kind[i] == 0 ? off_len[i] : 0;
+    if (i > 0) {
+      if (parent[i] < 0 || (size_t)parent[i] >= i) return -1;
+      Side *ps = &g_side[parent[i]];
+      if (ps->nkids >= MAX_TERMS) return -1;
+      ps->kids[ps->nkids++] = &g_nodes[i];
+    }
+  }
+  return 0;
+}
+int RefTreeMinOffsetDelta(void) { return IndexResult_MinOffsetDelta(&g_root); }
+int RefTreeHasOffsets(size_t node) { return RSIndexResult_HasOffsets(&g_nodes[node]); }
+size_t RefTreeOffsets(size_t node, uint32_t *out, size_t cap) {
+  RSOffsetIterator it = RSIndexResult_IterateOffsets(&g_nodes[node]);
+  size_t n = 0;
+  for (;;) {
+    const uint32_t p = it.Next(it.ctx, NULL);
+    if (p == RS_OFFSETVECTOR_EOF) break;
+    if (n < cap) out[n] = p;
+    n++;
+  }
+  it.Free(it.ctx);
+  return n;
+}
+static int tree_slop(const RSIndexResult *r) { return IndexResult_MinOffsetDelta(r); }
+/* the loaded tree through the reference's scorer; slop < 0: GetSlop is the reference's IndexResult_MinOffsetDelta
+ * (src/extension.c:159 wires exactly that) */
+double RefTreeScore(const char *scorer, uint32_t doc_len, uint32_t max_freq, float doc_score, size_t num_docs, double avg_doc_len,
+                    int slop, double min_score, uint64_t tanh_factor) {
+  if (!g_nscorers) {
+    RSExtensionCtx ctx = {reg_scorer, reg_expander};
+    DefaultExtensionInit(&ctx);
+  }
+  RSScoringFunction fn = NULL;
+  for (int i = 0; i < g_nscorers; i++)
+    if (!strcmp(g_scorers[i].name, scorer)) fn = g_scorers[i].fn;
+  if (!fn) return NAN;
+  RSDocumentMetadata dmd;
+  memset(&dmd, 0, sizeof(dmd));
+  dmd.score = doc_score;
+  dmd.docLen = doc_len;
+  dmd.maxTermFreq = max_freq;
+  ScoringFunctionArgs args;
+  memset(&args, 0, sizeof(args));
+  args.indexStats.numDocs = num_docs;
+  args.indexStats.avgDocLen = avg_doc_len;
+  args.GetSlop = slop < 0 ? tree_slop : harness_slop;
+  args.tanhFactor = tanh_factor;
+  g_slop = slop;
+  return fn(&args, &g_root, &dmd, min_score);
 }
 
 
@@ -199,6 +297,6 @@ double RefHamming(const char *payload, size_t payload_len, const char *qdata, si
   memset(&args, 0, sizeof(args));
   args.qdata = qdata;
   args.qdatalen = qdatalen;
-  memset(&g_root, 0, sizeof(g_root));
+  pool_reset();
   return fn(&args, &g_root, &dmd, 0);
 }

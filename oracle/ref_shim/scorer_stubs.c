@@ -23,3 +23,8 @@ ABORT_STUB(sb_stemmer_delete)
 ABORT_STUB(sb_stemmer_stem)
 ABORT_STUB(sb_stemmer_length)
 
+
+/* src/util/mempool/mempool.c reads RSGlobalConfig.noMemPool and logs through RedisModule_Log when REDISEARCH_NO_MEMPOOL is set:
+ * a zeroed configuration (pools enabled) and no logger */
+char RSGlobalConfig[1 << 16];
+void *RedisModule_Log;

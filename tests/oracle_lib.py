@@ -345,6 +345,11 @@ class OrcScoreDoc(C.Structure):
                 ("doc_len", C.c_uint32), ("max_freq", C.c_uint32), ("doc_score", C.c_float)]
 
 
+class OrcTree(C.Structure):
+    _fields_ = [("n_nodes", C.c_size_t), ("parent", C.c_void_p), ("kind", C.c_void_p), ("freq", C.c_void_p), ("weight", C.c_void_p),
+                ("idf", C.c_void_p), ("bm25_idf", C.c_void_p), ("off_start", C.c_void_p), ("off_len", C.c_void_p), ("bytes", C.c_void_p)]
+
+
 class OrcIndexStats(C.Structure):
     _fields_ = [("num_docs", C.c_uint64), ("num_terms", C.c_uint64), ("avg_doc_len", C.c_double)]
 
@@ -421,6 +426,17 @@ def postings():
         L.orc_numeric_in_range.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
         L.orc_min_offset_delta.restype = C.c_int
         L.orc_min_offset_delta.argtypes = [_SZ, _P, _P, _SZ, _P]
+        L.orc_score_tree.restype = C.c_double
+        L.orc_score_tree.argtypes = [C.c_int, C.POINTER(OrcIndexStats), C.POINTER(OrcTree), C.c_uint32, C.c_uint32, C.c_float, C.c_int,
+                                     C.c_double, C.c_double]
+        L.orc_tree_offsets.restype = _SZ
+        L.orc_tree_offsets.argtypes = [C.POINTER(OrcTree), _SZ, _P, _SZ]
+        L.orc_tree_has_offsets.restype = C.c_int
+        L.orc_tree_has_offsets.argtypes = [C.POINTER(OrcTree), _SZ]
+        L.orc_tree_min_offset_delta.restype = C.c_int
+        L.orc_tree_min_offset_delta.argtypes = [C.POINTER(OrcTree)]
+        L.orc_tree_within_range.restype = C.c_int
+        L.orc_tree_within_range.argtypes = [C.POINTER(OrcTree), C.c_int, C.c_uint32, C.c_int]
         L.orc_time_search3.restype = C.c_double
         L.orc_time_search3.argtypes = [_P, _SZ, _P, C.c_uint64, C.c_double, _SZ, C.c_int, _P, _P, _P]
         _post_bound = True
@@ -444,6 +460,15 @@ def ref_scorers():
         L.RefHamming.argtypes = [C.c_char_p, _SZ, C.c_char_p, _SZ]
         L.RefMinOffsetDelta.restype = C.c_int
         L.RefMinOffsetDelta.argtypes = [C.c_int, _SZ, _P, _P, _SZ, _P]
+        L.RefTreeLoad.restype = C.c_int
+        L.RefTreeLoad.argtypes = [_SZ, _P, _P, _P, _P, _P, _P, _P, _P, C.c_char_p]
+        L.RefTreeMinOffsetDelta.restype = C.c_int
+        L.RefTreeHasOffsets.restype = C.c_int
+        L.RefTreeHasOffsets.argtypes = [_SZ]
+        L.RefTreeOffsets.restype = _SZ
+        L.RefTreeOffsets.argtypes = [_SZ, _P, _SZ]
+        L.RefTreeScore.restype = C.c_double
+        L.RefTreeScore.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_float, _SZ, C.c_double, C.c_int, C.c_double, C.c_uint64]
         _ref_scorers = L
     return _ref_scorers
 
@@ -604,3 +629,101 @@ def reference_score(scorer, freqs, idf, bm25_idf, weights, agg_weight, doc_len, 
     wa = (C.c_double * n)(*weights)
     return L.RefScore(SCORER_NAMES[scorer], int(is_union), n, fa, ia, ba, wa, agg_weight, doc_len, max_freq, doc_score,
                       num_docs, avg_doc_len, slop, min_score, int(tanh_factor))
+
+
+# ---- result trees (nested aggregates): tree_oracle.c and the reference's own code over the same flattened arrays ----
+KIND_TERM, KIND_AND, KIND_OR, KIND_VIRTUAL, KIND_NUMERIC = range(5)
+
+
+def varint_deltas(positions):
+    """ascending term positions -> the offsets payload of a record (RS/varint deltas)"""
+    buf = (C.c_uint8 * 16)()
+    out, last = bytearray(), 0
+    for p in positions:
+        n = postings().orc_varint_encode(int(p) - last, buf)
+        out += bytes(buf[:n])
+        last = int(p)
+    return bytes(out)
+
+
+class ResultTree:
+    """One document's result as the scorers see it.  Nodes are dicts:
+         {"kind": KIND_TERM, "freq", "weight", "idf", "bm25_idf", "positions": [...]}   (positions may be empty / absent)
+         {"kind": KIND_AND | KIND_OR, "weight", "children": [...]}                      (freq = sum of the children's)
+         {"kind": KIND_VIRTUAL | KIND_NUMERIC, "freq", "weight"}"""
+
+    def __init__(self, root):
+        self.nodes = []
+        self._flatten(root, -1)
+        n = len(self.nodes)
+        self.parent = np.array([x[0] for x in self.nodes], dtype=np.int32)
+        self.kind = np.array([x[1] for x in self.nodes], dtype=np.int32)
+        self.freq = np.array([x[2] for x in self.nodes], dtype=np.uint32)
+        self.weight = np.array([x[3] for x in self.nodes], dtype=np.float64)
+        self.idf = np.array([x[4] for x in self.nodes], dtype=np.float64)
+        self.bm25 = np.array([x[5] for x in self.nodes], dtype=np.float64)
+        blobs = [x[6] for x in self.nodes]
+        self.off_len = np.array([len(b) for b in blobs], dtype=np.uint32)
+        self.off_start = np.concatenate([[0], np.cumsum(self.off_len)[:-1]]).astype(np.uint32) if n else np.zeros(0, np.uint32)
+        self.bytes = b"".join(blobs) + b"\0"
+        self._buf = C.create_string_buffer(self.bytes, len(self.bytes))
+        self.c = OrcTree(n, _p(self.parent), _p(self.kind), _p(self.freq), _p(self.weight), _p(self.idf), _p(self.bm25),
+                         _p(self.off_start), _p(self.off_len), C.cast(self._buf, C.c_void_p))
+
+    def _flatten(self, node, parent):
+        me = len(self.nodes)
+        k = node["kind"]
+        if k in (KIND_AND, KIND_OR):
+            self.nodes.append(None)
+            total = 0
+            for ch in node["children"]:
+                total += self._flatten(ch, me)
+            self.nodes[me] = (parent, k, total, node.get("weight", 1.0), 0.0, 0.0, b"")
+            return total
+        blob = varint_deltas(node.get("positions", ())) if k == KIND_TERM else b""
+        self.nodes.append((parent, k, node.get("freq", 1), node.get("weight", 1.0), node.get("idf", 0.0), node.get("bm25_idf", 0.0), blob))
+        return node.get("freq", 1)
+
+    # the C restatement
+    def score(self, scorer, doc_len, max_freq, doc_score, num_docs, avg_doc_len, slop=-1, min_score=0.0, tanh_factor=4.0):
+        st = OrcIndexStats(num_docs, 0, avg_doc_len)
+        return postings().orc_score_tree(scorer, C.byref(st), C.byref(self.c), doc_len, max_freq, doc_score, slop, min_score, tanh_factor)
+
+    def offsets(self, node=0):
+        out = np.zeros(4096, dtype=np.uint32)
+        n = postings().orc_tree_offsets(C.byref(self.c), node, _p(out), out.size)
+        return out[:n].tolist()
+
+    def has_offsets(self, node=0):
+        return bool(postings().orc_tree_has_offsets(C.byref(self.c), node))
+
+    def min_offset_delta(self):
+        return postings().orc_tree_min_offset_delta(C.byref(self.c))
+
+    def within_range(self, max_slop, in_order):
+        return bool(postings().orc_tree_within_range(C.byref(self.c), 0 if max_slop is None else 1, 0 if max_slop is None else max_slop,
+                                                     int(in_order)))
+
+    # the reference's own code (libscorers_ref.so)
+    def _ref_load(self):
+        L = ref_scorers()
+        rc = L.RefTreeLoad(len(self.nodes), _p(self.parent), _p(self.kind), _p(self.freq), _p(self.weight), _p(self.idf), _p(self.bm25),
+                           _p(self.off_start), _p(self.off_len), C.cast(self._buf, C.c_char_p))
+        assert rc == 0
+        return L
+
+    def ref_score(self, scorer, doc_len, max_freq, doc_score, num_docs, avg_doc_len, slop=-1, min_score=0.0, tanh_factor=4):
+        return self._ref_load().RefTreeScore(SCORER_NAMES[scorer], doc_len, max_freq, doc_score, num_docs, avg_doc_len, slop, min_score,
+                                             int(tanh_factor))
+
+    def ref_offsets(self, node=0):
+        L = self._ref_load()
+        out = np.zeros(4096, dtype=np.uint32)
+        n = L.RefTreeOffsets(node, _p(out), out.size)
+        return out[:n].tolist()
+
+    def ref_has_offsets(self, node=0):
+        return bool(self._ref_load().RefTreeHasOffsets(node))
+
+    def ref_min_offset_delta(self):
+        return self._ref_load().RefTreeMinOffsetDelta()
