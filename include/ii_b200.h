@@ -248,6 +248,19 @@ typedef struct {
 double II_CalculateIDF(size_t total_docs, size_t term_docs);      /* RS/idf/src/lib.rs:67 */
 double II_CalculateIDF_BM25(size_t total_docs, size_t term_docs); /* RS/idf/src/lib.rs:103 */
 
+/* NESTED aggregates: an evaluated AND / OR becomes ONE child of another aggregate — `(a|b) c`, the expansions of a stemmed term
+ * under an AND, a phrase inside a larger query.  Returns the list view of its hits (docIds; freq = the sum of its children's,
+ * like RSAggregateResult) that II_Intersect* / II_Union accept; the view carries the set, so that
+ *   - the scorers recurse into it: weight * sum (DISMAX over a union: max) over ITS children
+ *     (src/ext/default.c:75-95 tfidfRecursive, :183-199 bm25Recursive, :272-289 bm25StdRecursive, :393-438 dismaxRecursive);
+ *   - the proximity checks and GetSlop see the k-way merge of its children's term positions, duplicates kept
+ *     (src/offset_vector.c:100-140,216-239; RS/index_result/src/core/proximity.rs:53-67), and it COUNTS as having offsets by
+ *     the kind mask of its children (src/index_result/index_result.c:23-35) whatever the streams hold.
+ * CONSUMES rs (also on failure: NULL).  terms: of rs's children in the order they were given to its constructor; weight: the
+ * nested node's own; the parent's II_TermParams entry for this child is not read.  with_positions != 0 builds the merged
+ * positions now (a parent with slop / in-order needs them up front; GetSlop builds them on demand).  Quick unions (no per-child
+ * freqs) cannot be nested this way. */
+II_PostingList *II_ResultSet_IntoChild(II_ResultSet *rs, const II_TermParams *terms, double weight, int with_positions);
 /* Score every hit of `rs` on device.  agg_weight = weight of the intersection/union node.
  * Returns 0, or -1 on failure. */
 int II_Score(II_ResultSet *rs, II_Scorer scorer, const II_TermParams *terms, double agg_weight,

@@ -144,8 +144,13 @@ struct II_PostingList {
     const uint8_t *d_bytes = nullptr;
     const uint32_t *d_off_pos = nullptr, *d_off_len = nullptr;
     std::shared_ptr<SharedDeviceBlock> bytes_owner;
+    // a child that is not a term leaf: an evaluated AND / OR taking part in another aggregate (II_ResultSet_IntoChild; the
+    // arrays above then belong to it), a numeric / wildcard list (result_tag)
+    std::shared_ptr<struct NestedSet> nested;
+    uint8_t result_tag = 4;   // RSResultData tag of the results this child yields: 4 term, 8 virtual, 16 numeric, 1 union, 2 intersection
+    double sort_weight = 1.0; // intersection_sort_weight (rqe_iterators: 1 / children for an intersection, else 1)
     ~II_PostingList() {
-        if (!owner) {
+        if (!owner && !nested) {
             dfree(d_ids);
             dfree(d_freqs);
         }
@@ -187,6 +192,11 @@ struct II_ResultSet {
     std::vector<ChildOffsets> child_off;
     double *d_ext = nullptr; // wide unions: the scorer's per-child tables in device memory (ScoreArgs::ext)
     UnionOrder *d_order = nullptr; // unions: the reference's aggregate child order per docId epoch
+    // nested aggregates: child j (aggregate order) is itself an evaluated AND / OR (NULL: a leaf); its hits' positions inside it
+    // are row j of d_hit_pos
+    std::vector<std::shared_ptr<struct NestedSet>> nested;
+    std::vector<uint8_t> child_tag; // RSResultData tag per child (aggregate order)
+    size_t estimated = 0;           // num_estimated by the reference's rule: min over the children (AND), their sum (OR)
     ~II_ResultSet() {
         dfree(d_docs);
         dfree(d_freqs);
@@ -196,6 +206,28 @@ struct II_ResultSet {
         dfree(d_slop);
         dfree(d_order);
         dfree(d_ext);
+    }
+};
+
+// An evaluated AND / OR as ONE child of another aggregate — `(a|b) c`, the expansions of a stemmed term under an AND, a phrase
+// inside a larger query.  The scorers recurse into it (src/ext/default.c:75-95,183-199,272-289,393-438: weight * sum / max over ITS
+// children), the proximity checks and GetSlop merge its children's term positions (src/offset_vector.c:100-140,216-239).
+struct NestedSet {
+    std::unique_ptr<II_ResultSet> rs;
+    std::vector<II_TermParams> terms; // of rs's children, in the order they were given to the constructor
+    double weight = 1.0;
+    uint32_t *d_fsum = nullptr; // [rs->len] freq of the aggregate result = sum of its children's
+    double *d_sub = nullptr;    // [rs->len] recursive score of every hit for the scorer being evaluated
+    // merged term positions of every hit, re-encoded as varint deltas (built when a parent needs them)
+    bool merged = false;
+    uint8_t *d_mbytes = nullptr;
+    uint32_t *d_moff_pos = nullptr, *d_moff_len = nullptr;
+    ~NestedSet() {
+        dfree(d_fsum);
+        dfree(d_sub);
+        dfree(d_mbytes);
+        dfree(d_moff_pos);
+        dfree(d_moff_len);
     }
 };
 
@@ -755,6 +787,7 @@ II_PostingList *II_NumericList_Filter(const II_NumericList *nl, double min, doub
         return nullptr;
     }
     pl->n = pl->estimated = kept;
+    pl->result_tag = 16; // numeric results
     return pl;
 }
 
@@ -777,6 +810,7 @@ static II_PostingList *posting_list_all_docs(uint64_t top_id) {
     }
     pl->n = pl->estimated = n;
     pl->last_id = (uint32_t)top_id;
+    pl->result_tag = 8; // virtual results
     return pl;
 }
 
@@ -865,7 +899,8 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
     // children estimate max_doc_id (not.rs / optional.rs num_estimated): they sort behind every term, in their given order
     std::vector<uint32_t> order(n);
     for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
-    auto est = [&](uint32_t a) { return mode_of(a) ? (size_t)1 << 62 : lists[a]->estimated; };
+    // sort key of Intersection::new_with_slop_order (:110-120): num_estimated * intersection_sort_weight, as doubles
+    auto est = [&](uint32_t a) { return mode_of(a) ? 0x1p62 : (double)lists[a]->estimated * lists[a]->sort_weight; };
     // an in-order intersection keeps the children as given: their order is the order the terms must appear in
     // (intersection.rs new_sorted_by: `if !in_order { children.sort_by(compare) }`)
     if (!(phrase && phrase->in_order)) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return est(a) < est(b); });
@@ -878,6 +913,19 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
     rs->n_children = (uint32_t)n;
     rs->child_order.assign(order.begin(), order.end());
     rs->child_off.assign(n, II_ResultSet::ChildOffsets());
+    rs->nested.assign(n, nullptr);
+    rs->child_tag.assign(n, 4);
+    bool any_nested = false;
+    rs->estimated = (size_t)-1;
+    for (size_t j = 0; j < n; j++) {
+        const II_PostingList *L = lists[order[j]];
+        rs->child_tag[j] = mode_of(order[j]) == 1 ? 8 : L->result_tag;
+        if (mode_of(order[j]) == 0) rs->estimated = std::min(rs->estimated, L->estimated); // NOT / OPTIONAL estimate max_doc_id
+        if (L->nested && mode_of(order[j]) != 1) {
+            rs->nested[j] = L->nested;
+            any_nested = true;
+        }
+    }
     *trivially_empty = false;
     for (size_t i = 0; i < n; i++) *trivially_empty |= mode_of(i) == 0 && lists[i]->n == 0;
     if (*trivially_empty) return true;
@@ -895,6 +943,7 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
     // keep the hits' posting positions when a child carries term positions: GetSlop needs them later (II_Score)
     bool keep_pos = false;
     for (size_t i = 0; i < n && n > 1; i++) keep_pos |= mode_of(i) != 1 && lists[i]->d_off_len != nullptr;
+    keep_pos |= any_nested; // the scorers reach a nested child's recursive value through the hit's position inside it
     if (keep_pos) rs->d_hit_pos = dalloc<uint32_t>(rs->cap * n);
     const uint32_t pchunks = (uint32_t)((rs->cap + 1023) / 1024);
     // phrase path: the gather fills scratch rows, the filter compacts the survivors into the result set
@@ -991,9 +1040,80 @@ bool intersect_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, II_Result
     return ok;
 }
 
+// Merged term positions of a nested set's hits (MergeOffsetsArgs): its own nested children first, then two passes over its hits.
+// One host synchronisation (the size of the byte buffer).
+bool ensure_merged(Ctx &c, NestedSet *ns) {
+    if (ns->merged) return true;
+    II_ResultSet *rs = ns->rs.get();
+    const size_t m = rs->len;
+    if (rs->n_children > (uint32_t)kIIMaxLists) return false;
+    if (!rs->has_freqs && !rs->d_hit_pos) return false; // a quick union does not know which children matched
+    MergeOffsetsArgs a{};
+    a.n = rs->n_children;
+    a.is_union = rs->is_union ? 1 : 0;
+    a.pos = rs->d_hit_pos;
+    a.freqs = rs->d_freqs;
+    a.fstride = rs->cap;
+    for (uint32_t j = 0; j < rs->n_children; j++) {
+        if (j < rs->nested.size() && rs->nested[j]) {
+            NestedSet *ch = rs->nested[j].get();
+            if (!ensure_merged(c, ch)) return false;
+            II_ResultSet::ChildOffsets &co = rs->child_off[j];
+            co.bytes = ch->d_mbytes;
+            co.off_pos = ch->d_moff_pos;
+            co.off_len = ch->d_moff_len;
+        }
+        a.bytes[j] = rs->child_off[j].bytes;
+        a.off_pos[j] = rs->child_off[j].off_pos;
+        a.off_len[j] = rs->child_off[j].off_len;
+        a.tag[j] = j < rs->child_tag.size() ? rs->child_tag[j] : 4;
+    }
+    const uint32_t chunks = (uint32_t)((m + 255) / 256);
+    uint32_t *ub = dalloc<uint32_t>(m ? m : 1), *csum = dalloc<uint32_t>(chunks ? chunks : 1), *coff = dalloc<uint32_t>(chunks ? chunks : 1);
+    uint32_t *tot32 = dalloc<uint32_t>(4);
+    unsigned long long *tot64 = dalloc<unsigned long long>(1);
+    ns->d_moff_pos = dalloc<uint32_t>(m ? m : 1);
+    ns->d_moff_len = dalloc<uint32_t>(m ? m : 1);
+    bool ok = ub && csum && coff && tot32 && tot64 && ns->d_moff_pos && ns->d_moff_len;
+    unsigned long long total = 0;
+    ok = ok && ii_launch_merge_offsets_bounds(a, nullptr, (uint32_t)m, ub, csum, coff, tot32, tot64, c.stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(&total, tot64, 8, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+    ok = ok && total < 0xFFFFFFFFull;
+    if (ok) {
+        ns->d_mbytes = dalloc<uint8_t>((size_t)total + 16);
+        ok = ns->d_mbytes != nullptr;
+    }
+    ok = ok && ii_launch_merge_offsets_write(a, nullptr, (uint32_t)m, ub, coff, ns->d_mbytes, ns->d_moff_pos, ns->d_moff_len, c.stream) == cudaSuccess;
+    c.stats.kernel_launches += 3;
+    dfree(ub);
+    dfree(csum);
+    dfree(coff);
+    dfree(tot32);
+    dfree(tot64);
+    ns->merged = ok;
+    return ok;
+}
+
+// the offsets tables of the nested children of `rs` (their merged streams), for the kernels that walk term positions
+bool ensure_child_offsets(Ctx &c, II_ResultSet *rs) {
+    for (uint32_t j = 0; j < rs->n_children && j < rs->nested.size(); j++) {
+        if (!rs->nested[j]) continue;
+        NestedSet *ch = rs->nested[j].get();
+        if (!ensure_merged(c, ch)) return false;
+        II_ResultSet::ChildOffsets &co = rs->child_off[j];
+        co.bytes = ch->d_mbytes;
+        co.off_pos = ch->d_moff_pos;
+        co.off_len = ch->d_moff_len;
+    }
+    return true;
+}
+
 // GetSlop per hit, once per result set and only when a legacy scorer asks for it.  d_len / cap_len as for the scorer launch.
 bool ensure_slop(Ctx &c, II_ResultSet *rs, const uint32_t *d_len, uint32_t cap_len) {
     if (!rs->d_hit_pos || rs->d_slop) return true;
+    if (rs->n_children > (uint32_t)kIIMaxLists) return true;
+    if (!ensure_child_offsets(c, rs)) return false;
     rs->d_slop = dalloc<uint32_t>(rs->cap);
     if (!rs->d_slop) return false;
     SlopArgs sa{};
@@ -1011,6 +1131,29 @@ bool ensure_slop(Ctx &c, II_ResultSet *rs, const uint32_t *d_len, uint32_t cap_l
     return ii_launch_min_offset_delta(sa, rs->d_docs, d_len, cap_len, rs->d_slop, c.stream) == cudaSuccess;
 }
 
+ScoreArgs make_score_args(II_ResultSet *rs, II_Scorer scorer, const II_TermParams *terms, double agg_weight,
+                          const II_IndexStats *stats, const II_DocTable *docs, double min_score, uint64_t tanh_factor);
+
+// The recursive value of every hit of every nested child of `rs` for `scorer` (ScoreArgs::sub), innermost first.
+bool prepare_nested_scores(Ctx &c, II_ResultSet *rs, II_Scorer scorer, const II_IndexStats *stats, const II_DocTable *docs) {
+    if (scorer == II_SCORER_DOCSCORE || scorer == II_SCORER_HAMMING) return true;
+    for (uint32_t j = 0; j < rs->n_children && j < rs->nested.size(); j++) {
+        if (!rs->nested[j]) continue;
+        NestedSet *ns = rs->nested[j].get();
+        II_ResultSet *in = ns->rs.get();
+        if (!in->has_freqs) return false;
+        if (!prepare_nested_scores(c, in, scorer, stats, docs)) return false;
+        if (!ns->d_sub) ns->d_sub = dalloc<double>(in->len ? in->len : 1);
+        if (!ns->d_sub) return false;
+        ScoreArgs sa = make_score_args(in, scorer, ns->terms.data(), ns->weight, stats, docs, 0.0, 4);
+        sa.sub_only = 1;
+        sa.slop = nullptr;
+        if (ii_launch_score(sa, in->d_docs, in->d_freqs, in->cap, nullptr, (uint32_t)in->len, ns->d_sub, c.stream) != cudaSuccess) return false;
+        c.stats.kernel_launches += 1;
+    }
+    return true;
+}
+
 bool union_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int quick_exit, II_ResultSet *rs, bool *trivially_empty) {
     rs->is_union = true;
     rs->n_children = (uint32_t)n;
@@ -1018,12 +1161,23 @@ bool union_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int quick_exi
     rs->child_order.resize(n);
     for (size_t i = 0; i < n; i++) rs->child_order[i] = (uint32_t)i;
     rs->child_off.assign(n, II_ResultSet::ChildOffsets());
+    rs->nested.assign(n, nullptr);
+    rs->child_tag.assign(n, 4);
+    bool any_nested = false;
     uint32_t max_id = 0;
     size_t total_in = 0;
+    rs->estimated = 0;
     for (size_t i = 0; i < n; i++) {
         if (lists[i]->n) max_id = std::max(max_id, lists[i]->last_id);
         total_in += lists[i]->n;
+        rs->estimated += lists[i]->estimated; // union_flat.rs:102
+        rs->child_tag[i] = lists[i]->result_tag;
+        if (lists[i]->nested) {
+            rs->nested[i] = lists[i]->nested;
+            any_nested = true;
+        }
     }
+    if (any_nested && (n > (size_t)kIIMaxLists || quick_exit)) return false; // nested children need the per-child position rows
     *trivially_empty = total_in == 0;
     if (*trivially_empty) return true;
     const uint32_t nwords = max_id / 32 + 1, nblk = (nwords + 31) / 32;
@@ -1069,6 +1223,7 @@ bool union_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int quick_exi
     }
     bool keep_pos = false;
     for (size_t i = 0; i < n && n > 1 && n <= (size_t)kIIMaxLists && rs->has_freqs; i++) keep_pos |= lists[i]->d_off_len != nullptr;
+    keep_pos |= any_nested;
     if (keep_pos) rs->d_hit_pos = dalloc<uint32_t>(rs->cap * n);
     bool ok = rs->d_docs && rs->d_freqs && rs->d_scores && rs->d_len && bitmap && blocksum && blockoff && wordoff &&
               (!flat_order || rs->d_order) && (!keep_pos || rs->d_hit_pos);
@@ -1153,6 +1308,10 @@ ScoreArgs make_score_args(II_ResultSet *rs, II_Scorer scorer, const II_TermParam
     sa.max_freq = docs ? docs->d_maxf : nullptr;
     sa.slop = rs->d_slop; // NULL: no term positions on the device, the kernel uses `children - 1`
     sa.order = rs->d_order;
+    for (uint32_t i = 0; i < rs->n_children && i < rs->nested.size() && i < (uint32_t)kIIMaxLists; i++)
+        if (rs->nested[i]) sa.sub[i] = rs->nested[i]->d_sub;
+    sa.pos = rs->d_hit_pos;
+    sa.pstride = rs->cap;
     return sa;
 }
 
@@ -1200,6 +1359,7 @@ bool search_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int is_union
     const uint32_t k = (uint32_t)top_n;
     if (scorer == II_SCORER_BM25 || scorer == II_SCORER_TFIDF || scorer == II_SCORER_TFIDF_DOCNORM)
         ok = ensure_slop(c, &rs, rs.d_len, (uint32_t)rs.cap);
+    ok = ok && prepare_nested_scores(c, &rs, scorer, stats, docs);
     const ScoreArgs sa = make_score_args(&rs, scorer, terms, agg_weight, stats, docs, 0.0, 4);
     ok = ok && ii_launch_score(sa, rs.d_docs, rs.d_freqs, rs.cap, rs.d_len, (uint32_t)rs.cap, rs.d_scores, c.stream) == cudaSuccess;
     const uint32_t nl = ii_topn_lists((uint32_t)rs.cap);
@@ -1397,6 +1557,47 @@ void II_ResultSet_ChildOrder(const II_ResultSet *rs, uint32_t *child_order) {
     for (uint32_t i = 0; i < rs->n_children; i++) child_order[i] = rs->child_order[i];
 }
 void II_ResultSet_Free(II_ResultSet *rs) { delete rs; }
+
+// An evaluated AND / OR becomes ONE child of another aggregate (`(a|b) c`): the list view of its hits (docIds, freq = the sum of
+// its children's) that II_Intersect* / II_Union take, carrying the set itself so that the scorers recurse into it and the
+// proximity checks / GetSlop see its merged term positions.  CONSUMES rs (also on failure).  terms: of rs's children in the order
+// they were given to its constructor; weight: the nested node's own.  with_positions: build the merged positions now (a parent
+// with slop / in-order needs them up front; GetSlop builds them on demand).
+II_PostingList *II_ResultSet_IntoChild(II_ResultSet *rs, const II_TermParams *terms, double weight, int with_positions) {
+    if (!rs) return nullptr;
+    auto ns = std::make_shared<NestedSet>();
+    ns->rs.reset(rs);
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.init() || !rs->has_freqs || !terms) return nullptr;
+    ns->terms.assign(terms, terms + rs->n_children);
+    ns->weight = weight;
+    const size_t m = rs->len;
+    ns->d_fsum = dalloc<uint32_t>(m ? m : 1);
+    bool ok = ns->d_fsum != nullptr;
+    ok = ok && ii_launch_sum_freq_rows(rs->d_freqs, rs->n_children, rs->cap, nullptr, (uint32_t)m, ns->d_fsum, c.stream) == cudaSuccess;
+    c.stats.kernel_launches += 1;
+    uint32_t last = 0;
+    if (ok && m) ok = cudaMemcpyAsync(&last, rs->d_docs + m - 1, 4, cudaMemcpyDeviceToHost, c.stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c.stream) == cudaSuccess;
+    if (ok && with_positions) ok = ensure_merged(c, ns.get());
+    if (!ok) return nullptr;
+    auto *pl = new II_PostingList();
+    pl->d_ids = rs->d_docs;
+    pl->d_freqs = ns->d_fsum;
+    pl->n = m;
+    pl->estimated = rs->estimated;
+    pl->last_id = last;
+    pl->result_tag = rs->is_union ? 1 : 2;
+    pl->sort_weight = rs->is_union ? 1.0 : 1.0 / (double)std::max<uint32_t>(1, rs->n_children); // union_flat.rs:817, intersection.rs:580
+    if (ns->merged) {
+        pl->d_bytes = ns->d_mbytes;
+        pl->d_off_pos = ns->d_moff_pos;
+        pl->d_off_len = ns->d_moff_len;
+    }
+    pl->nested = std::move(ns);
+    return pl;
+}
 const uint32_t *II_ResultSet_DeviceDocIds(const II_ResultSet *rs) { return rs->d_docs; }
 const double *II_ResultSet_DeviceScores(const II_ResultSet *rs) { return rs->d_scores; }
 
@@ -1430,6 +1631,7 @@ int II_Score(II_ResultSet *rs, II_Scorer scorer, const II_TermParams *terms, dou
     bool ok = true;
     if (scorer == II_SCORER_BM25 || scorer == II_SCORER_TFIDF || scorer == II_SCORER_TFIDF_DOCNORM)
         ok = ensure_slop(c, rs, nullptr, (uint32_t)rs->len);
+    ok = ok && prepare_nested_scores(c, rs, scorer, stats, docs);
     const ScoreArgs sa = make_score_args(rs, scorer, terms, agg_weight, stats, docs, min_score, tanh_factor);
     ok = ok && ii_launch_score(sa, rs->d_docs, rs->d_freqs, rs->cap, nullptr, (uint32_t)rs->len, rs->d_scores, c.stream) == cudaSuccess;
     cudaEventRecord(c.e1, c.stream);
@@ -1750,6 +1952,7 @@ int II_SearchTopNBatch(size_t nq, II_PostingList *const *const *lists, const siz
         bool wants_positions = false;
         if (scorer == II_SCORER_BM25 || scorer == II_SCORER_TFIDF || scorer == II_SCORER_TFIDF_DOCNORM)
             for (size_t t = 0; t < n_lists[i] && n_lists[i] > 1; t++) wants_positions |= lists[i][t]->d_off_len != nullptr;
+        for (size_t t = 0; t < n_lists[i]; t++) wants_positions |= lists[i][t]->nested != nullptr; // nested sets: the chain recurses into them
         if (fused_on && !is_union && !wants_positions && n_lists[i] <= (size_t)kFusedMaxLists && top_n <= (size_t)kFusedMaxTopN)
             fusable.push_back(i);
         else
@@ -2176,7 +2379,7 @@ void node_publish(NodeIter *it, size_t i) {
 size_t node_num_estimated(const II_QueryIterator *b) {
     const NodeIter *it = reinterpret_cast<const NodeIter *>(b);
     if (it->kind == NODE_EMPTY) return 0;
-    if (it->rs) return it->rs->len;
+    if (it->rs) return it->kind == NODE_RESULT ? it->rs->estimated : it->rs->len; // AND: min over the children, OR: their sum
     if (it->mode != LEAF_REQUIRED) return (size_t)it->max_doc_id; // not.rs / optional.rs num_estimated = max_doc_id
     return it->pl ? it->pl->estimated : 0;
 }
@@ -2285,13 +2488,19 @@ NodeIter *new_node(NodeKind kind, uint32_t type, double weight) {
 }
 
 // a FOREIGN iterator -> device posting list (docIds ascending as the contract guarantees; freq = current->freq)
-II_PostingList *drain_foreign(II_QueryIterator *f) {
+II_PostingList *drain_foreign(II_QueryIterator *f, uint8_t *tag, double *weight) {
     std::vector<uint64_t> ids;
     std::vector<uint32_t> freqs;
     if (f->Rewind) f->Rewind(f);
+    bool first = true;
     while (f->Read(f) == ITERATOR_OK) {
         ids.push_back(f->lastDocId);
         freqs.push_back(f->current ? f->current->freq : 1u);
+        if (first && f->current) { // what kind of result the child yields, and its weight (the scorers treat the kinds differently)
+            *tag = (uint8_t)f->current->data.tag;
+            *weight = f->current->weight;
+            first = false;
+        }
     }
     return II_PostingList_FromArrays(ids.data(), freqs.data(), ids.size());
 }
@@ -2302,7 +2511,7 @@ struct ChildView { // what the algebra needs from a child
     LeafMode mode = LEAF_REQUIRED;
     II_TermParams term{1.0, 1.0, 1.0};
 };
-bool child_view(II_QueryIterator *c, ChildView &v) {
+bool child_view(II_QueryIterator *c, ChildView &v, bool need_offsets) {
     if (is_node(c)) {
         NodeIter *n = NI(c);
         if (n->kind == NODE_LEAF) {
@@ -2317,19 +2526,38 @@ bool child_view(II_QueryIterator *c, ChildView &v) {
             v.term = II_TermParams{n->res.weight, 1.0, 1.0};
             return v.pl != nullptr;
         }
-        if (n->kind == NODE_RESULT && n->rs) { // nested AND / OR: its docIds, freq = sum over its children
+        if (n->kind == NODE_RESULT && n->rs) {
+            // nested AND / OR: stays on the device as one child (the scorers recurse into it, its term positions are merged);
+            // the child node gives its result set away
+            if (n->rs->has_freqs && n->rs->n_children <= (uint32_t)kIIMaxLists && !n->host_ready) {
+                II_ResultSet *inner = n->rs;
+                n->rs = nullptr;
+                v.pl = II_ResultSet_IntoChild(inner, n->terms.data(), n->agg_weight, need_offsets ? 1 : 0);
+                v.temp = true;
+                v.term = II_TermParams{n->agg_weight, 1.0, 1.0}; // not read: the nested set carries its own
+                return v.pl != nullptr;
+            }
+            if (need_offsets) return false;
+            // a quick union (no per-child freqs: never scored): its docIds as a flat list
             if (!node_host(n)) return false;
             std::vector<uint32_t> fr(n->ids.size(), 1u);
             for (size_t i = 0; i < fr.size() && i < n->freq_sum.size(); i++) fr[i] = n->freq_sum[i];
             v.pl = II_PostingList_FromArrays(n->ids.data(), fr.data(), n->ids.size());
             v.temp = true;
             v.term = II_TermParams{n->agg_weight, 1.0, 1.0};
+            if (v.pl) v.pl->result_tag = n->rs->is_union ? 1 : 2;
             return v.pl != nullptr;
         }
         return false;
     }
-    v.pl = drain_foreign(c);
+    if (need_offsets) return false;
+    uint8_t tag = 8;
+    double w = 1.0;
+    v.pl = drain_foreign(c, &tag, &w);
     v.temp = true;
+    if (v.pl) v.pl->result_tag = tag;
+    // a numeric / metric result is an "irrelevant token" for BM25STD (default.c:296-300) and weight * freq for TFIDF (:104)
+    v.term = II_TermParams{w, 1.0, (tag == 16 || tag == 32) ? 0.0 : 1.0};
     return v.pl != nullptr;
 }
 bool child_is_empty(const II_QueryIterator *c) {
@@ -2639,7 +2867,7 @@ static II_QueryIterator *build_aggregate(II_QueryIterator **its, size_t num, boo
     }
     std::vector<ChildView> views(kids.size());
     bool ok = true;
-    for (size_t i = 0; i < kids.size() && ok; i++) ok = child_view(kids[i], views[i]);
+    for (size_t i = 0; i < kids.size() && ok; i++) ok = child_view(kids[i], views[i], phrase != nullptr);
     NodeIter *out = nullptr;
     if (ok) {
         std::vector<II_PostingList *> pls;
@@ -2677,9 +2905,10 @@ static II_QueryIterator *build_aggregate(II_QueryIterator **its, size_t num, boo
 }
 
 // RS/headers/iterators_ffi.h:309.  max_slop >= 0 / in_order (phrase constraints) are evaluated on the device when every child
-// is one of OUR term leaves carrying its term positions (Full codec decoded with offsets kept, at most kPhraseMaxLists
-// children); for anything else (foreign children, nested unions whose positions the reference merges, leaves without
-// positions) NULL is returned BEFORE anything is consumed and the caller keeps the reference's own iterator for that node.
+// is one of OUR term leaves carrying its term positions (a codec with offsets, decoded with offsets kept) or a nested B200
+// AND / OR (its children's positions are merged like the reference's aggregate offset iterator), at most kPhraseMaxLists
+// children; for anything else (foreign children, leaves without positions) NULL is returned BEFORE anything is consumed and
+// the caller keeps the reference's own iterator for that node.
 II_QueryIterator *NewIntersectionIterator(II_QueryIterator **its, size_t num, int32_t max_slop, bool in_order, double weight) {
     if (!its || num == 0) {
         if (its) host_free(its);
@@ -2691,7 +2920,13 @@ II_QueryIterator *NewIntersectionIterator(II_QueryIterator **its, size_t num, in
             II_QueryIterator *c = its[i];
             if (!c) return nullptr;
             if (child_is_empty(c)) continue; // reduces the AND to empty whatever the constraint
-            if (!is_node(c) || NI(c)->kind != NODE_LEAF || !NI(c)->pl) return nullptr;
+            if (!is_node(c)) return nullptr;
+            if (NI(c)->kind == NODE_RESULT && NI(c)->rs) { // a nested AND / OR: the positions of its children are merged
+                if (!NI(c)->rs->has_freqs || NI(c)->rs->n_children > (uint32_t)kIIMaxLists || NI(c)->host_ready) return nullptr;
+                continue;
+            }
+            if (NI(c)->kind == NODE_WILDCARD) continue; // stripped from the AND
+            if (NI(c)->kind != NODE_LEAF || !NI(c)->pl) return nullptr;
             if (NI(c)->mode != LEAF_NOT && !NI(c)->pl->d_off_len) return nullptr;
         }
         const PhraseSpec ph{max_slop < 0 ? 0xFFFFFFFFu : (uint32_t)max_slop, in_order};

@@ -422,8 +422,16 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
 #define II_W(c) (s.ext ? s.ext[c] : s.weight[c])
 #define II_IDF(c) (s.ext ? s.ext[s.n_children + (c)] : s.idf[c])
 #define II_BIDF(c) (s.ext ? s.ext[2 * s.n_children + (c)] : s.bm25_idf[c])
+    // a nested aggregate child: its recursive value, computed over the child's own hits, through the hit's position inside it
+#define II_NESTED(c) (!s.ext && s.sub[c] != nullptr)
+#define II_SUB(c, dst, present)                                          \
+    do {                                                                 \
+        const uint32_t p_ = s.pos[(size_t)(c) * s.pstride + o];         \
+        (present) = p_ != 0xFFFFFFFFu;                                   \
+        if (present) (dst) = s.sub[c][p_];                               \
+    } while (0)
     uint32_t slop = 1;
-    if (s.scorer >= 1 && s.scorer <= 3) { // the legacy scorers divide by GetSlop (:130-131, :226-227)
+    if (s.scorer >= 1 && s.scorer <= 3 && !s.sub_only) { // the legacy scorers divide by GetSlop (:130-131, :226-227)
         if (s.slop) {
             slop = s.slop[o];
         } else if (s.is_union) {
@@ -439,10 +447,18 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
     case 5: { // BM25STD.TANH       :339-359
         double ret = 0;
         II_FOR_CHILDREN(c) {
+            if (II_NESTED(c)) {
+                double v = 0;
+                bool present;
+                II_SUB(c, v, present);
+                if (present) ret = __dadd_rn(ret, v);
+                continue;
+            }
             const uint32_t f = freqs[c * fstride + o];
             if (f) ret = __dadd_rn(ret, bm25std_leaf(II_BIDF(c), (double)f, (int)doc_len, s.avg_doc_len, II_W(c)));
         }
         ret = __dmul_rn(ret, s.agg_weight);
+        if (s.sub_only) return ret;
         const double score = __dmul_rn((double)doc_score, ret);
         if (s.scorer == 5) return tanh(__dmul_rn(__ddiv_rn(1.0, (double)s.tanh_factor), score));
         return score;
@@ -450,25 +466,43 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
     case 1: { // BM25 (legacy)      :164-233
         double ret = 0;
         II_FOR_CHILDREN(c) {
+            if (II_NESTED(c)) {
+                double v = 0;
+                bool present;
+                II_SUB(c, v, present);
+                if (present) ret = __dadd_rn(ret, v);
+                continue;
+            }
             const uint32_t f = freqs[c * fstride + o];
             if (f) ret = __dadd_rn(ret, bm25_leaf(II_IDF(c), (double)f, s.avg_doc_len, II_W(c)));
         }
         ret = __dmul_rn(ret, s.agg_weight);
+        if (s.sub_only) return ret;
         const double score = __dmul_rn((double)doc_score, ret);
         if (score < s.min_score) return 0.0;
         return __ddiv_rn(score, (double)(int)slop); // `score /= slop` with an int slop
     }
     case 2:   // TFIDF              :68-146
     case 3: { // TFIDF.DOCNORM
-        if (doc_score == 0.0f) return 0.0;
         const uint32_t norm = (s.scorer == 2) ? (s.max_freq ? s.max_freq[doc] : 1u) : doc_len;
-        if (norm == 0) return 0.0;
+        if (!s.sub_only) {
+            if (doc_score == 0.0f) return 0.0;
+            if (norm == 0) return 0.0;
+        }
         double raw = 0;
         II_FOR_CHILDREN(c) {
+            if (II_NESTED(c)) {
+                double v = 0;
+                bool present;
+                II_SUB(c, v, present);
+                if (present) raw = __dadd_rn(raw, v);
+                continue;
+            }
             const uint32_t f = freqs[c * fstride + o];
             if (f) raw = __dadd_rn(raw, __dmul_rn(__dmul_rn(II_W(c), (double)f), II_IDF(c)));
         }
         raw = __dmul_rn(s.agg_weight, raw);
+        if (s.sub_only) return raw;
         const double tfidf = __ddiv_rn(__dmul_rn((double)doc_score, raw), (double)norm);
         if (tfidf < s.min_score) return 0.0;
         return __ddiv_rn(tfidf, (double)(int)slop);
@@ -477,9 +511,17 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
     case 6: {                         // DISMAX   :378-461: intersection sums, union takes the max
         double ret = 0;
         II_FOR_CHILDREN(c) {
-            const uint32_t f = freqs[c * fstride + o];
-            if (!f) continue;
-            const double leaf = __dmul_rn(II_W(c), (double)f);
+            double leaf;
+            if (II_NESTED(c)) {
+                bool present;
+                leaf = 0;
+                II_SUB(c, leaf, present);
+                if (!present) continue;
+            } else {
+                const uint32_t f = freqs[c * fstride + o];
+                if (!f) continue;
+                leaf = __dmul_rn(II_W(c), (double)f);
+            }
             if (s.is_union)
                 ret = (leaf > ret) ? leaf : ret;
             else
@@ -488,6 +530,8 @@ __device__ double score_hit(const ScoreArgs &s, uint32_t doc, const uint32_t *fr
         return __dmul_rn(s.agg_weight, ret);
     }
     }
+#undef II_NESTED
+#undef II_SUB
 #undef II_FOR_CHILDREN
 #undef II_W
 #undef II_IDF
@@ -1143,8 +1187,9 @@ __global__ void phrase_filter_kernel(const PhraseArgs a, const uint32_t *__restr
         uint32_t n = 0;
         for (uint32_t j = 0; j < a.n; j++) {
             const uint32_t p = a.pos[(size_t)j * a.fstride + o];
-            const uint32_t len = (a.off_len[j] && p != 0xFFFFFFFFu) ? a.off_len[j][p] : 0u; // virtual results carry no offsets
-            if (len) { // has_offsets
+            const uint32_t raw = (a.off_len[j] && p != 0xFFFFFFFFu) ? a.off_len[j][p] : 0u; // virtual results carry no offsets
+            if (raw) { // has_offsets (a nested aggregate: by its kind mask, bit 31, whatever the stream holds)
+                const uint32_t len = raw & ~kIIOffLenHas;
                 it[n].p = a.bytes[j] + a.off_pos[j][p];
                 it[n].end = it[n].p + len;
                 it[n].last = 0;
@@ -1308,8 +1353,9 @@ __global__ void min_offset_delta_kernel(const SlopArgs a, const uint32_t *__rest
             const uint32_t p = a.pos[(size_t)c * a.fstride + o];
             if (a.is_union && p == 0xFFFFFFFFu) continue; // not part of this document's aggregate
             num++;
-            const uint32_t len = (a.off_len[c] && p != 0xFFFFFFFFu) ? a.off_len[c][p] : 0u;
-            if (!len) continue; // RSIndexResult_HasOffsets :19-42: virtual results / empty offset vectors are skipped
+            const uint32_t raw = (a.off_len[c] && p != 0xFFFFFFFFu) ? a.off_len[c][p] : 0u;
+            if (!raw) continue; // RSIndexResult_HasOffsets :19-42: virtual results / empty offset vectors are skipped
+            const uint32_t len = raw & ~kIIOffLenHas; // nested aggregates: bit 31 = counts as having offsets (kind mask)
             OffCur cur;
             cur.p = a.bytes[c] + a.off_pos[c][p];
             cur.end = cur.p + len;
@@ -1343,6 +1389,152 @@ cudaError_t ii_launch_min_offset_delta(const SlopArgs &a, const uint32_t *d_docs
                                        uint32_t *d_slop, cudaStream_t s) {
     if (!cap_len) return cudaSuccess;
     min_offset_delta_kernel<<<std::max(1u, std::min((cap_len + 127) / 128, 148u * 16)), 128, 0, s>>>(a, d_docs, d_len, cap_len, d_slop);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// nested aggregates: summed freqs and merged term positions of every hit
+// ------------------------------------------------------------------------------------------------
+__global__ void sum_freq_rows_kernel(const uint32_t *__restrict__ freqs, uint32_t n, size_t fstride, const uint32_t *__restrict__ d_len,
+                                     uint32_t cap_len, uint32_t *__restrict__ out) {
+    const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
+    for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < m; o += gridDim.x * blockDim.x) {
+        uint32_t t = 0;
+        for (uint32_t j = 0; j < n; j++) t += freqs[(size_t)j * fstride + o];
+        out[o] = t;
+    }
+}
+cudaError_t ii_launch_sum_freq_rows(const uint32_t *d_freqs, uint32_t n, size_t fstride, const uint32_t *d_len, uint32_t cap_len,
+                                    uint32_t *d_out, cudaStream_t s) {
+    if (!cap_len) return cudaSuccess;
+    sum_freq_rows_kernel<<<std::max(1u, std::min((cap_len + 255) / 256, 148u * 8)), 256, 0, s>>>(d_freqs, n, fstride, d_len, cap_len, d_out);
+    return cudaGetLastError();
+}
+
+constexpr uint32_t kMergeChunk = 256;
+// is child c part of hit o's aggregate, and as what kind of result
+__device__ __forceinline__ uint32_t merge_child_tag(const MergeOffsetsArgs &a, uint32_t c, uint32_t o, uint32_t &p) {
+    p = a.pos ? a.pos[(size_t)c * a.fstride + o] : 0u;
+    const bool there = a.pos ? p != 0xFFFFFFFFu : a.freqs[(size_t)c * a.fstride + o] != 0;
+    if (a.is_union) return there ? a.tag[c] : 0u; // a union's aggregate holds the matching children only
+    return there ? a.tag[c] : 8u;                  // NOT / absent OPTIONAL children of an intersection are virtual results
+}
+__global__ void __launch_bounds__(kMergeChunk) merge_bounds_kernel(const MergeOffsetsArgs a, const uint32_t *__restrict__ d_len, uint32_t cap_len,
+                                                                   uint32_t *__restrict__ ub, uint32_t *__restrict__ chunk_sum,
+                                                                   unsigned long long *__restrict__ total64) {
+    __shared__ uint32_t s_sum;
+    const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const uint32_t o = blockIdx.x * kMergeChunk + threadIdx.x;
+    uint32_t b = 0;
+    if (o < m) {
+        for (uint32_t c = 0; c < a.n; c++) {
+            uint32_t p;
+            const uint32_t tag = merge_child_tag(a, c, o, p);
+            if (tag && tag != 8u && a.off_len[c] && a.pos) b += a.off_len[c][p] & ~kIIOffLenHas;
+        }
+        ub[o] = b;
+    }
+    if (b) atomicAdd(&s_sum, b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        chunk_sum[blockIdx.x] = s_sum;
+        if (s_sum) atomicAdd(total64, (unsigned long long)s_sum);
+    }
+}
+__device__ __forceinline__ uint32_t varint_put(uint32_t v, uint8_t *out) { // RS/varint: most significant group first, +1 per continuation
+    uint8_t buf[5];
+    int at = 4;
+    buf[at] = (uint8_t)(v & 0x7f);
+    while (v >>= 7) {
+        v -= 1;
+        buf[--at] = (uint8_t)(0x80 | (v & 0x7f));
+    }
+    for (int i = at; i < 5; i++) out[i - at] = buf[i];
+    return (uint32_t)(5 - at);
+}
+__global__ void __launch_bounds__(kMergeChunk) merge_write_kernel(const MergeOffsetsArgs a, const uint32_t *__restrict__ d_len, uint32_t cap_len,
+                                                                  const uint32_t *__restrict__ ub, const uint32_t *__restrict__ chunk_off,
+                                                                  uint8_t *__restrict__ bytes, uint32_t *__restrict__ off_pos,
+                                                                  uint32_t *__restrict__ off_len) {
+    __shared__ uint32_t s_warp[kMergeChunk / 32];
+    const uint32_t m = d_len ? min(*d_len, cap_len) : cap_len;
+    const uint32_t o = blockIdx.x * kMergeChunk + threadIdx.x;
+    const uint32_t mine = o < m ? ub[o] : 0u;
+    // exclusive scan of the chunk's bounds
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t base = chunk_off[blockIdx.x];
+    for (int w = 0; w < warp; w++) base += s_warp[w];
+    if (o >= m) return;
+    const uint32_t start = base + incl - mine;
+    OffCur it[kIIMaxLists];
+    uint32_t head[kIIMaxLists];
+    uint32_t n = 0, mask = 0;
+    for (uint32_t c = 0; c < a.n; c++) {
+        uint32_t p;
+        const uint32_t tag = merge_child_tag(a, c, o, p);
+        mask |= tag;
+        if (!tag || tag == 8u || !a.off_len[c] || !a.pos) continue;
+        const uint32_t len = a.off_len[c][p] & ~kIIOffLenHas;
+        if (!len) continue;
+        it[n].p = a.bytes[c] + a.off_pos[c][p];
+        it[n].end = it[n].p + len;
+        it[n].last = 0;
+        if (off_next(it[n], head[n])) n++;
+    }
+    uint8_t *out = bytes + start;
+    uint32_t written = 0, last = 0;
+    while (n) { // _aoi_Next: the first child holding the smallest look-ahead yields it and advances
+        uint32_t mi = 0, mv = head[0];
+        for (uint32_t i = 1; i < n; i++)
+            if (head[i] < mv) {
+                mv = head[i];
+                mi = i;
+            }
+        uint8_t tmp[5];
+        const uint32_t k = varint_put(mv - last, tmp);
+        if (written + k > mine) break; // cannot happen for ascending streams (a merged delta never exceeds the original's)
+        for (uint32_t i = 0; i < k; i++) out[written + i] = tmp[i];
+        written += k;
+        last = mv;
+        if (!off_next(it[mi], head[mi])) { // exhausted: close the gap, keeping the children's order
+            for (uint32_t i = mi + 1; i < n; i++) {
+                it[i - 1] = it[i];
+                head[i - 1] = head[i];
+            }
+            n--;
+        }
+    }
+    off_pos[o] = start;
+    // RSIndexResult_HasOffsets of an aggregate: its kind mask is neither Virtual alone nor exactly Numeric|Metric
+    const bool has = mask != 8u && mask != (16u | 32u);
+    off_len[o] = written | (has ? kIIOffLenHas : 0u);
+}
+cudaError_t ii_launch_merge_offsets_bounds(const MergeOffsetsArgs &a, const uint32_t *d_len, uint32_t cap_len, uint32_t *d_ub,
+                                           uint32_t *d_chunk_sum, uint32_t *d_chunk_off, uint32_t *d_total32,
+                                           unsigned long long *d_total64, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(d_total64, 0, 8, s);
+    if (e != cudaSuccess || !cap_len) return e;
+    const uint32_t chunks = (cap_len + kMergeChunk - 1) / kMergeChunk;
+    merge_bounds_kernel<<<chunks, kMergeChunk, 0, s>>>(a, d_len, cap_len, d_ub, d_chunk_sum, d_total64);
+    scan_kernel<<<1, 1024, 0, s>>>(d_chunk_sum, chunks, d_chunk_off, d_total32);
+    return cudaGetLastError();
+}
+cudaError_t ii_launch_merge_offsets_write(const MergeOffsetsArgs &a, const uint32_t *d_len, uint32_t cap_len, const uint32_t *d_ub,
+                                          const uint32_t *d_chunk_off, uint8_t *d_bytes, uint32_t *d_off_pos, uint32_t *d_off_len,
+                                          cudaStream_t s) {
+    if (!cap_len) return cudaSuccess;
+    const uint32_t chunks = (cap_len + kMergeChunk - 1) / kMergeChunk;
+    merge_write_kernel<<<chunks, kMergeChunk, 0, s>>>(a, d_len, cap_len, d_ub, d_chunk_off, d_bytes, d_off_pos, d_off_len);
     return cudaGetLastError();
 }
 

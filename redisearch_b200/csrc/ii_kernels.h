@@ -75,6 +75,36 @@ struct SlopArgs {
 cudaError_t ii_launch_min_offset_delta(const SlopArgs &a, const uint32_t *d_docs, const uint32_t *d_len, uint32_t cap_len,
                                        uint32_t *d_slop, cudaStream_t s);
 
+// ---- nested aggregates as children ------------------------------------------------------------------------------------
+// freq of an aggregate result = the sum of its children's (RSAggregateResult push: result.freq += child.freq)
+cudaError_t ii_launch_sum_freq_rows(const uint32_t *d_freqs, uint32_t n, size_t fstride, const uint32_t *d_len, uint32_t cap_len,
+                                    uint32_t *d_out, cudaStream_t s);
+// Term positions of an aggregate = the k-way merge of its children's offset iterators, duplicates kept
+// (src/offset_vector.c:216-239 _aoi_Next, RS/index_result/src/core/proximity.rs:53-67 OffsetIter::Merge).  The merged stream of
+// every hit is re-encoded as varint deltas so that the aggregate then looks like a term leaf to the phrase filter and to GetSlop:
+// d_off_pos[o] / d_off_len[o] delimit it inside d_bytes.  Bit 31 of d_off_len[o] says the aggregate COUNTS as having offsets
+// (by the kind mask of its children at this document, index_result.c:23-35 — even when the stream is empty).
+constexpr uint32_t kIIOffLenHas = 0x80000000u;
+struct MergeOffsetsArgs {
+    const uint8_t *bytes[kIIMaxLists];
+    const uint32_t *off_pos[kIIMaxLists];
+    const uint32_t *off_len[kIIMaxLists]; // NULL: the child carries no offsets
+    uint8_t tag[kIIMaxLists];             // RSResultData tag of the child's results: 1 union, 2 intersection, 4 term, 8 virtual, 16 numeric
+    const uint32_t *pos;                  // [n][fstride], may be NULL (then presence comes from the freq rows)
+    const uint32_t *freqs;                // [n][fstride]
+    size_t fstride;
+    uint32_t n;
+    int is_union;
+};
+// pass 1: d_ub[o] = upper bound of the merged stream's bytes (the sum of the children's), per 256-hit chunk sums, their exclusive
+// scan and the grand total (64-bit); pass 2 writes the streams (d_off_pos[o] = chunk offset + scan of d_ub inside the chunk)
+cudaError_t ii_launch_merge_offsets_bounds(const MergeOffsetsArgs &a, const uint32_t *d_len, uint32_t cap_len, uint32_t *d_ub,
+                                           uint32_t *d_chunk_sum, uint32_t *d_chunk_off, uint32_t *d_total32,
+                                           unsigned long long *d_total64, cudaStream_t s);
+cudaError_t ii_launch_merge_offsets_write(const MergeOffsetsArgs &a, const uint32_t *d_len, uint32_t cap_len, const uint32_t *d_ub,
+                                          const uint32_t *d_chunk_off, uint8_t *d_bytes, uint32_t *d_off_pos, uint32_t *d_off_len,
+                                          cudaStream_t s);
+
 // UnionFlat keeps its children in an "active" array and swap-removes a child when it is exhausted (union_flat.rs:174-180,
 // advance_and_find_min :218-258): the aggregate's child order for a document is the active array's order at that moment.
 // For a union read front to back that order is a function of the docId alone: epoch e covers docIds in (bound[e-1], bound[e]].
@@ -101,6 +131,13 @@ struct ScoreArgs {
     const UnionOrder *order;   // unions: child order per docId epoch (device memory), may be NULL
     const double *ext;         // more than kIIMaxLists children (unions): weight[n], idf[n], bm25_idf[n] in device memory instead of
                                // the inline tables above
+    // NESTED aggregates (a child that is itself an evaluated AND / OR): sub[c] = the child's recursive score per hit OF THE
+    // CHILD (what tfidfRecursive / bm25Recursive / bm25StdRecursive / dismaxRecursive return for it, its own weight applied:
+    // src/ext/default.c:75-95,183-199,272-289,393-438), looked up through the hit's position inside the child
+    const double *sub[kIIMaxLists]; // NULL: a leaf
+    const uint32_t *pos;            // [n_children][pstride] position of the hit inside child c (0xFFFFFFFF: absent / virtual)
+    size_t pstride;
+    int sub_only;                   // 1: write the recursive value of THIS aggregate (no document-level factor): it is a nested child
 };
 
 // ---- fused batch search: AND + scorer + top-N of MANY queries in two launches --------------------------------------

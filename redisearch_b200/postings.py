@@ -74,6 +74,7 @@ SIGNATURES = [
     ("II_Union", _P, [_P, _SZ, C.c_int]),
     ("II_ResultSet_Len", _SZ, [_P]),
     ("II_ResultSet_Free", None, [_P]),
+    ("II_ResultSet_IntoChild", _P, [_P, _P, C.c_double, C.c_int]),
     ("II_CalculateIDF", C.c_double, [_SZ, _SZ]),
     ("II_CalculateIDF_BM25", C.c_double, [_SZ, _SZ]),
     ("II_ScoreHamming", C.c_int, [_P, _P, _P, _SZ]),
@@ -345,6 +346,16 @@ class ResultSet:
         scores = np.zeros(n, dtype=np.float64)
         got = self.L.II_ResultSet_TopN(self.h, n, _ptr(ids), _ptr(scores))
         return ids[:got], scores[:got]
+
+    def into_child(self, terms, weight=1.0, with_positions=False):
+        """II_ResultSet_IntoChild: this evaluated AND / OR becomes ONE child (a PostingList view) of another aggregate; terms =
+        (weight, idf, bm25_idf) of ITS children in their original order.  The result set is consumed."""
+        arr = (II_TermParams * len(terms))(*[II_TermParams(*t) for t in terms])
+        h = self.L.II_ResultSet_IntoChild(self.h, arr, weight, int(with_positions))
+        self.h = None
+        if not h:
+            raise RuntimeError("II_ResultSet_IntoChild failed")
+        return PostingList(h)
 
     def into_iterator(self, weight=1.0):
         it = self.L.II_NewResultIterator(self.h, weight)

@@ -280,6 +280,7 @@ int main(int argc, char **argv) {
             fo->base.NumEstimated = f_est, fo->base.Read = f_read, fo->base.SkipTo = f_skip, fo->base.Rewind = f_rewind;
             fo->base.Free = f_free, fo->base.Revalidate = f_reval;
             fo->ids = ids[2], fo->freqs = fr[2], fo->n = n[2], fo->freed = &freed;
+            fo->res.data.tag = II_ResultData_Numeric, fo->res.weight = 1.0; /* what the host's numeric iterator yields */
             its[k++] = &fo->base;
         } else if (variant == 2) {
             II_QueryIterator *ld = II_NewTermIterator_FromIndex(ix[3], II_CODEC_FREQS_ONLY, 1.0, II_CalculateIDF(n_docs, n[3]), II_CalculateIDF_BM25(n_docs, n[3]), cache);
@@ -339,6 +340,29 @@ int main(int argc, char **argv) {
         printf("cache hits %zu misses %zu\n", cs.hits, cs.misses);
         II_SetDefaultTermCache(NULL);
     }
+    /* variant 5: (A | E) & B — a NESTED union under the intersection, both through the reference's constructor signatures.  The
+     * union's result set moves into the intersection; the scorers recurse into it (weight 0.5 * sum over its matching children) */
+    {
+        II_QueryIterator **inner = malloc(2 * sizeof(*inner));
+        inner[0] = II_NewTermIterator_FromIndex(ix[0], II_CODEC_FREQS_ONLY, 1.0, II_CalculateIDF(n_docs, n[0]), II_CalculateIDF_BM25(n_docs, n[0]), cache);
+        inner[1] = II_NewTermIterator_FromIndex(ix[4], II_CODEC_FREQS_ONLY, 2.0, II_CalculateIDF(n_docs, n[4]), II_CalculateIDF_BM25(n_docs, n[4]), cache);
+        II_QueryIterator *un = NewUnionIterator(inner, 2, false, 0.5, 0, NULL, NULL);
+        if (!un) return 30;
+        II_QueryIterator **its = malloc(2 * sizeof(*its));
+        its[0] = un;
+        its[1] = II_NewTermIterator_FromIndex(ix[1], II_CODEC_FREQS_ONLY, 1.0, II_CalculateIDF(n_docs, n[1]), II_CalculateIDF_BM25(n_docs, n[1]), cache);
+        II_QueryIterator *it = NewIntersectionIterator(its, 2, -1, false, 1.5);
+        if (!it) return 31;
+        printf("variant 5 estimated %zu\n", it->NumEstimated(it));
+        while (it->Read(it) == ITERATOR_OK) {
+            const double s1 = bm25(&args, it->current, NULL, 0.0);
+            const double s2 = tfidf(&args, it->current, NULL, 0.0);
+            printf("%llu %a %u %a\n", (unsigned long long)it->lastDocId, s1, it->current->freq, s2);
+        }
+        it->Free(it);
+        II_TermCacheStats cs = II_TermCache_GetStats(cache);
+        printf("cache hits %zu misses %zu\n", cs.hits, cs.misses);
+    }
     /* union of A and foreign C through the reference's NewUnionIterator signature */
     {
         II_QueryIterator **its = malloc(2 * sizeof(*its));
@@ -347,6 +371,7 @@ int main(int argc, char **argv) {
         fo->base.NumEstimated = f_est, fo->base.Read = f_read, fo->base.SkipTo = f_skip, fo->base.Rewind = f_rewind;
         fo->base.Free = f_free, fo->base.Revalidate = f_reval;
         fo->ids = ids[2], fo->freqs = fr[2], fo->n = n[2];
+        fo->res.data.tag = II_ResultData_Numeric, fo->res.weight = 1.0;
         its[1] = &fo->base;
         II_QueryIterator *it = NewUnionIterator(its, 2, false, 1.0, 0, NULL, NULL);
         if (!it) return 14;

@@ -60,7 +60,9 @@ def test_constructors_and_scorer_extension_from_a_c_host(tmp_path):
 
     def params(name, weight=1.0, foreign=False):
         n = len(lists[name][0])
-        return (weight, 1.0, 1.0) if foreign else (weight, P.orc_idf(n_docs, n), P.orc_idf_bm25(n_docs, n))
+        # the host's numeric iterator yields Numeric results: an "irrelevant token" for BM25STD (default.c:296-300 -> contributes 0),
+        # weight * freq for TFIDF (:104)
+        return (weight, 1.0, 0.0) if foreign else (weight, P.orc_idf(n_docs, n), P.orc_idf_bm25(n_docs, n))
 
     def expect(required, excluded=(), optional=(), foreign=(), opt_weight=2.0):
         docs = None
@@ -105,6 +107,37 @@ def test_constructors_and_scorer_extension_from_a_c_host(tmp_path):
         for g, e in zip(got, exp):
             assert np.float64(g[1]).tobytes() == np.float64(e[1]).tobytes(), (variant, g, e)
             assert g[2] == e[2]
+    # variant 5: (a | e) & b with the union NESTED under the intersection: each hit rebuilt as the reference's result tree and scored
+    # by the tree oracle (pinned on the reference's default.c recursion in test_oracle_trees.py); BM25STD and TFIDF bits
+    i5 = lines.index(next(l for l in lines if l.startswith("variant 5 ")))
+    na, ne, nb = (len(lists[x][0]) for x in "aeb")
+    assert lines[i5] == f"variant 5 estimated {min(na + ne, nb)}"  # AND: min over the children; OR: their sum
+    rows5 = []
+    for l in lines[i5 + 1:]:
+        if l.startswith("cache"):
+            break
+        d, s1, f, s2 = l.split()
+        rows5.append((int(d), float.fromhex(s1), int(f), float.fromhex(s2)))
+    ma, me, mb = lookup("a"), lookup("e"), lookup("b")
+    docs5 = sorted((set(ma) | set(me)) & set(mb))
+    assert [r[0] for r in rows5] == docs5 and len(docs5) > 100
+
+    def term_node(name, m, d, weight):
+        w, idf, bidf = params(name, weight)
+        return {"kind": ol.KIND_TERM, "freq": m[d], "weight": w, "idf": idf, "bm25_idf": bidf}
+
+    for d, s1, f, s2 in rows5:
+        un = {"kind": ol.KIND_OR, "weight": 0.5,
+              "children": [term_node(x, m, d, w) for x, m, w in (("a", ma, 1.0), ("e", me, 2.0)) if d in m]}
+        kids = [un, term_node("b", mb, d, 1.0)]
+        if nb < na + ne:  # children ascending by num_estimated * sort weight (stable)
+            kids.reverse()
+        t = ol.ResultTree({"kind": ol.KIND_AND, "weight": 1.5, "children": kids})
+        e1 = t.score(ol.SCORER_BM25STD, int(doc_len[d]), 1, 1.0, n_docs, avg)
+        e2 = t.score(ol.SCORER_TFIDF, int(doc_len[d]), 1, 1.0, n_docs, avg)
+        assert np.float64(s1).tobytes() == np.float64(e1).tobytes(), (d, s1, e1)
+        assert np.float64(s2).tobytes() == np.float64(e2).tobytes(), (d, s2, e2)
+        assert f == sum(m[d] for m in (ma, me, mb) if d in m)
     # the term cache decoded a and b once: later constructions hit
     assert block(0)[1] == "cache hits 0 misses 2" and block(1)[1] == "cache hits 2 misses 2"
     assert f"union {len(np.union1d(lists['a'][0], lists['c'][0]))}" in lines
