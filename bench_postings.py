@@ -13,6 +13,18 @@ N_RANDOM_QUERIES = 1000
 CPU_SAMPLE_QUERIES = 48
 
 
+def _ncu_traffic(kernel, n_docs, n_queries):
+    """dram bytes per launch from the committed ncu --set full capture of this workload (profiles/r2_traffic.json), else None"""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_traffic.json")) as f:
+            t = json.load(f).get(kernel)
+        if t and (t["docs"], t["queries"]) == (n_docs, n_queries):
+            return t["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def query_set():
     """1,000 queries x 3 distinct vocabulary ranks drawn log-uniformly from [1, 10^4] (seed 13), plus fixed
     probes ((1,2,3), (1,100,10^4), (10,20,30)-style)."""
@@ -232,7 +244,8 @@ def bench_postings(torch, dev, stream_ptr, n_docs, steps, peak, check=True):
                 "note": "FreqsOnly IndexBlocks in host memory -> II_TermCache_Acquire on a COLD cache (one gather of all blocks into pinned "
                         "staging, one H2D copy, one decode launch for every distinct term) -> II_SearchTopNBatch; the cache is freed after the step"},
         "roofline": {"bound": "hbm", "achieved": alg_bytes / dev_s / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": alg_bytes / dev_s / 1e9 / peak, "traffic": None, "kernel": "fused_and_kernel + fused_topn_kernel",
+                     "frac": alg_bytes / dev_s / 1e9 / peak, "traffic": _ncu_traffic("fused_and_kernel", n_docs, len(queries)),
+                     "kernel": "fused_and_kernel + fused_topn_kernel",
                      "device_ms_per_query_set": dev_s * 1000.0, "algorithmic_bytes": alg_bytes,
                      "note": "algorithmic bytes = 8 B per input posting + 16 B per match (SURVEY §8d); the kernel reads only the windows "
                              "of the longer lists that overlap a chunk of the shortest one, and freqs of matches only"},
