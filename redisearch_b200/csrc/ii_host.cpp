@@ -2780,13 +2780,35 @@ II_QueryIterator *NewInvIndIterator_TermQuery(const void *idx, const void *sctx,
     return it;
 }
 
-// NOT / OPTIONAL over one of OUR term leaves (RS/rqe_iterators/src/not.rs, optional.rs): inside an AND they become an
-// exclusion / an optional contribution of the membership kernel; read on their own they walk 1..max_doc_id.
+// `-(a|b)`, `~(a b)`: an evaluated nested AND / OR under NOT / OPTIONAL becomes a leaf whose list is the nested set's view
+// (II_ResultSet_IntoChild): excluded docIds for NOT; for OPTIONAL the set's recursive score where it matches, with the OPTIONAL's
+// weight as the aggregate's own (optional.rs:260,302 `real.weight = self.weight`).  false: not convertible, the node is untouched.
+static bool nested_node_to_leaf(II_QueryIterator *child, double weight) {
+    if (!is_node(child)) return false;
+    NodeIter *n = NI(child);
+    if (n->kind != NODE_RESULT || !n->rs || !n->rs->has_freqs || n->rs->n_children > (uint32_t)kIIMaxLists || n->host_ready) return false;
+    II_ResultSet *inner = n->rs;
+    n->rs = nullptr; // consumed either way
+    II_PostingList *pl = II_ResultSet_IntoChild(inner, n->terms.data(), weight, 0);
+    if (!pl) {
+        n->kind = NODE_EMPTY;
+        return false;
+    }
+    n->kind = NODE_LEAF;
+    n->pl = pl;
+    n->owns_pl = true;
+    n->term = II_TermParams{weight, 1.0, 1.0};
+    return true;
+}
+
+// NOT / OPTIONAL over one of OUR term leaves or nested AND / OR nodes (RS/rqe_iterators/src/not.rs, optional.rs): inside an AND
+// they become an exclusion / an optional contribution of the membership kernel; read on their own they walk 1..max_doc_id.
 II_QueryIterator *II_NewNotIterator(II_QueryIterator *child, t_docId max_doc_id, double weight) {
     if (child_is_empty(child)) { // NOT of nothing = every document: needs the universe, which only the host's wildcard iterator has
         if (child && child->Free) child->Free(child);
         return nullptr;
     }
+    if (is_node(child) && NI(child)->kind == NODE_RESULT && !nested_node_to_leaf(child, 1.0)) return nullptr;
     if (!is_node(child) || NI(child)->kind != NODE_LEAF || NI(child)->mode != LEAF_REQUIRED) return nullptr;
     NodeIter *n = NI(child);
     n->mode = LEAF_NOT;
@@ -2797,6 +2819,7 @@ II_QueryIterator *II_NewNotIterator(II_QueryIterator *child, t_docId max_doc_id,
     return child;
 }
 II_QueryIterator *II_NewOptionalIterator(II_QueryIterator *child, t_docId max_doc_id, double weight) {
+    if (is_node(child) && NI(child)->kind == NODE_RESULT && !nested_node_to_leaf(child, weight)) return nullptr;
     if (!is_node(child) || NI(child)->kind != NODE_LEAF || NI(child)->mode != LEAF_REQUIRED) return nullptr;
     NodeIter *n = NI(child);
     n->mode = LEAF_OPTIONAL;
