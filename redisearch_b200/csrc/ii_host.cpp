@@ -2337,6 +2337,11 @@ void host_free(void *p) { // `its` arrays come from the Redis allocator
         free(p);
 }
 
+void *host_alloc(size_t n) { // what the host frees with rm_free must come from the Redis allocator
+    static void *(**rm_alloc)(size_t) = reinterpret_cast<void *(**)(size_t)>(dlsym(RTLD_DEFAULT, "RedisModule_Alloc"));
+    return (rm_alloc && *rm_alloc) ? (*rm_alloc)(n) : malloc(n);
+}
+
 // a leaf that is read directly (single-term query: the reducers hand the child back) becomes a 1-child result
 bool node_materialise(NodeIter *it) {
     if (it->kind == NODE_LEAF && !it->rs) {
@@ -3022,7 +3027,29 @@ double b200_scorer(const ScoringFunctionArgsC *args, const void *res_v, const vo
     }
     // `res` is the iterator's current result: pos points one past it
     const size_t i = it->pos ? it->pos - 1 : 0;
-    return i < it->scores.size() ? it->scores[i] : 0.0;
+    const double score = i < it->scores.size() ? it->scores[i] : 0.0;
+    if (args->scrExp) {
+        // EXPLAINSCORE (src/result_processor.c:582-584 hands the node to the reply, src/score_explain.c:19-21 prints `str`
+        // unconditionally): the per-term break-down of the reference's scorers is not itemised here, but the node must carry a
+        // string owned by the host's allocator
+        struct ScoreExplainC { // src/score_explain.h:20-24
+            char *str;
+            int numChildren;
+            ScoreExplainC *children;
+        };
+        static const char *const kNames[] = {"BM25STD", "BM25", "TFIDF", "TFIDF.DOCNORM", "DOCSCORE", "BM25STD.TANH", "DISMAX", "HAMMING"};
+        auto *e = static_cast<ScoreExplainC *>(args->scrExp);
+        char buf[192];
+        const int len = snprintf(buf, sizeof(buf), "Final %s.B200 : %.2f (scored on the device with the whole result set; per-term break-down not itemised)",
+                                 kNames[kScorer], score);
+        char *str = static_cast<char *>(host_alloc((size_t)len + 1));
+        if (str) {
+            memcpy(str, buf, (size_t)len + 1);
+            if (e->str) host_free(e->str);
+            e->str = str;
+        }
+    }
+    return score;
 }
 } // namespace
 extern "C" {

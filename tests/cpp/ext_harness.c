@@ -354,7 +354,17 @@ int main(int argc, char **argv) {
         II_QueryIterator *it = NewIntersectionIterator(its, 2, -1, false, 1.5);
         if (!it) return 31;
         printf("variant 5 estimated %zu\n", it->NumEstimated(it));
+        int explained = 0;
         while (it->Read(it) == ITERATOR_OK) {
+            if (!explained) { /* EXPLAINSCORE: the node handed in must come back with a string (score_explain.c prints it as is) */
+                struct { char *str; int numChildren; void *children; } exp = {NULL, 0, NULL};
+                args.scrExp = &exp;
+                const double se = bm25(&args, it->current, NULL, 0.0);
+                args.scrExp = NULL;
+                if (!exp.str || !strstr(exp.str, "BM25STD.B200") || se != bm25(&args, it->current, NULL, 0.0)) return 32;
+                free(exp.str);
+                explained = 1;
+            }
             const double s1 = bm25(&args, it->current, NULL, 0.0);
             const double s2 = tfidf(&args, it->current, NULL, 0.0);
             printf("%llu %a %u %a\n", (unsigned long long)it->lastDocId, s1, it->current->freq, s2);
