@@ -45,6 +45,7 @@ QueryCtx::~QueryCtx() {
     cudaFree(d_scores);
     cudaFree(d_count);
     cudaFreeHost(h_count);
+    cudaFreeHost(h_abort);
     cudaFree(d_ids);
     cudaFreeHost(h_ids);
     cudaFree(d_dist);
@@ -59,6 +60,11 @@ bool QueryCtx::init() {
     CU_OK(cudaEventCreate(&ev_stop));
     CU_OK(cudaMalloc(&d_count, 16));
     CU_OK(cudaMallocHost(&h_count, 16));
+    CU_OK(cudaHostAlloc(&h_abort, 64, cudaHostAllocMapped));
+    *h_abort = 0;
+    void *dp = nullptr;
+    CU_OK(cudaHostGetDevicePointer(&dp, h_abort, 0));
+    d_abort = static_cast<const uint32_t *>(dp);
     return true;
 }
 bool QueryCtx::need_query(size_t bytes) {
@@ -237,6 +243,7 @@ std::unique_ptr<QueryCtx> FlatIndex::checkout() {
             if (c->abandoned) { // its last user timed out and left: let that work drain before the buffers are reused
                 cudaStreamSynchronize(c->stream);
                 c->abandoned = false;
+                *c->h_abort = 0;
             }
             return c;
         }
@@ -598,7 +605,7 @@ VecSimQueryReply *FlatIndex::topk(const void *q, size_t k, VecSimQueryParams *qp
             ok = c->need_cand(plan.cand_elems) && c->need_out(ke);
             if (ok) {
                 cudaEventRecord(c->ev_start, c->stream);
-                ok = launch_scan_topk(v, c->d_query, qpitch, 1, ke, plan, c->d_cand, c->stream, &lc) == cudaSuccess;
+                ok = launch_scan_topk(v, c->d_query, qpitch, 1, ke, plan, c->d_cand, c->stream, &lc, nullptr, c->d_abort) == cudaSuccess;
                 cudaEventRecord(c->ev_stop, c->stream);
             }
             ok = ok && launch_final_select(c->d_cand, 1, plan.lists_per_query * ke, ke, c->d_out, c->stream, &lc) == cudaSuccess;
@@ -609,6 +616,7 @@ VecSimQueryReply *FlatIndex::topk(const void *q, size_t k, VecSimQueryParams *qp
             const int w = wait_polling(c->stream, tctx);
             if (w == 1) { // deadline passed while the scan was running
                 c->abandoned = true;
+                *c->h_abort = 1; // the kernels still running on its stream wind down
                 launches_total_ += lc.launches;
                 checkin(std::move(c));
                 rep->code = VecSim_QueryReply_TimedOut;
@@ -913,7 +921,7 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
     if (!coarse) {
         if (!c.need_cand(sp.cand_elems) || !c.need_out((size_t)nq * ke)) return false;
         cudaEventRecord(c.ev_start, st);
-        bool ok = launch_scan_topk(v, d_q, qpitch, nq, ke, sp, c.d_cand, st, &lc) == cudaSuccess;
+        bool ok = launch_scan_topk(v, d_q, qpitch, nq, ke, sp, c.d_cand, st, &lc, nullptr, c.d_abort) == cudaSuccess;
         cudaEventRecord(c.ev_stop, st);
         ok = ok && launch_final_select(c.d_cand, nq, sp.lists_per_query * ke, ke, c.d_out, st, &lc) == cudaSuccess;
         *d_result = c.d_out;
@@ -1008,7 +1016,7 @@ bool FlatIndex::batch_scan(QueryCtx &c, const void *d_q, size_t qpitch, uint32_t
         lc.launches += 4;
     }
     // exact fallback, entirely on device: CTAs whose queries are all verified exit at once
-    ok = ok && launch_scan_topk(v, d_q, qpitch, nq, ke, sp, cand2, st, &lc, d_ok) == cudaSuccess;
+    ok = ok && launch_scan_topk(v, d_q, qpitch, nq, ke, sp, cand2, st, &lc, d_ok, c.d_abort) == cudaSuccess;
     ok = ok && launch_final_select(cand2, nq, sp.lists_per_query * ke, ke, out2, st, &lc) == cudaSuccess;
     ok = ok && launch_blend(d_ok, out1, out2, nq, ke, c.d_out, st, &lc) == cudaSuccess;
     coarse_batches_++;
@@ -1063,6 +1071,7 @@ int FlatIndex::topk_batch(const void *qs, size_t qstride, size_t nq, size_t k, V
         const int w = wait_polling(c->stream, tctx); // a 414 ms exact-scan fallback no longer holds a timed-out caller
         if (w == 1) {
             c->abandoned = true;
+                *c->h_abort = 1; // the kernels still running on its stream wind down
             checkin(std::move(c));
             return VecSim_QueryReply_TimedOut;
         }

@@ -70,6 +70,10 @@ struct QueryCtx {
     float *d_dist = nullptr, *h_dist = nullptr;
     size_t ids_cap = 0;
     bool abandoned = false; // a timed-out caller left while kernels were still running on `stream`: synchronise before reuse
+    // raised by the host when a caller times out: the exact-scan kernel polls it (mapped pinned memory) and winds down, so the GPU
+    // does not finish a pass nobody waits for
+    uint32_t *h_abort = nullptr;
+    const uint32_t *d_abort = nullptr;
     ~QueryCtx();
     bool init();
     bool need_query(size_t bytes);

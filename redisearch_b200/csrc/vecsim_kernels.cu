@@ -87,6 +87,8 @@ struct ScanArgs {
     uint32_t nq, k, wq, lists_per_query;
     uint64_t *cand;
     const uint32_t *q_ok; // optional: queries already answered (coarse path verified) are skipped
+    const uint32_t *abort; // optional (mapped host memory): non-zero = the caller has left (timeout), stop scanning
+    uint32_t poll_mask;    // the flag is read every poll_mask + 1 tiles of a warp
 };
 
 template <int DT, int MT, int RT, int QT, bool QSMEM>
@@ -145,7 +147,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
         active = !all_ok;
     }
     if (active) {
+        uint32_t since_poll = 0;
         for (uint32_t t = blockIdx.x * WR + rg; t < ntiles; t += gridDim.x * WR) {
+            if (a.abort && (since_poll++ & a.poll_mask) == a.poll_mask) { // a host flag over PCIe: one lane reads it now and then
+                uint32_t f = 0;
+                if (lane == 0) f = *reinterpret_cast<const volatile uint32_t *>(a.abort);
+                if (__shfl_sync(0xffffffffu, f, 0)) break; // the partial lists are published and then ignored by the host
+            }
             const uint32_t r0 = t * RT;
             const uint8_t *rowb[RT];
 #pragma unroll
@@ -496,7 +504,7 @@ cudaError_t launch_blend(const uint32_t *d_ok, const uint64_t *d_a, const uint64
 
 cudaError_t launch_scan_topk(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq, uint32_t k,
                              const ScanPlan &plan, uint64_t *d_cand, cudaStream_t s, LaunchCounters *ctr,
-                             const uint32_t *d_q_ok) {
+                             const uint32_t *d_q_ok, const uint32_t *d_abort) {
     if (nq == 0 || k == 0 || k > (uint32_t)kMaxFusedK || c.n_rows == 0) return cudaErrorInvalidValue;
     ScanArgs a{};
     a.rows = static_cast<const uint8_t *>(c.rows);
@@ -512,6 +520,8 @@ cudaError_t launch_scan_topk(const CorpusView &c, const void *d_queries, size_t 
     a.lists_per_query = plan.lists_per_query;
     a.cand = d_cand;
     a.q_ok = d_q_ok;
+    a.abort = d_abort;
+    a.poll_mask = nq >= 16 ? 15u : 255u; // a batched tile costs ~100x a single-query tile: keep the reaction time in milliseconds
     const bool qsmem = (size_t)plan.wq * plan.qt * a.q_smem_pitch <= kMaxQuerySmem;
     cudaError_t e = cudaErrorInvalidValue;
 #define CALL_SCAN(DT, MT) e = launch_scan_dm<DT, MT>(a, plan, qsmem, s)

@@ -39,7 +39,7 @@ ScanPlan plan_scan_topk(const CorpusView &c, uint32_t nq, uint32_t k);
 // d_queries: nq device blobs, qpitch bytes apart, already in stored form (normalised etc.).
 cudaError_t launch_scan_topk(const CorpusView &c, const void *d_queries, size_t qpitch, uint32_t nq,
                              uint32_t k, const ScanPlan &plan, uint64_t *d_cand, cudaStream_t s,
-                             LaunchCounters *ctr, const uint32_t *d_q_ok = nullptr);
+                             LaunchCounters *ctr, const uint32_t *d_q_ok = nullptr, const uint32_t *d_abort = nullptr);
 // out[q] = ok[q] ? a[q] : b[q] for [nq][k] composite arrays
 cudaError_t launch_blend(const uint32_t *d_ok, const uint64_t *d_a, const uint64_t *d_b, uint32_t nq, uint32_t k, uint64_t *d_out,
                          cudaStream_t s, LaunchCounters *ctr);

@@ -522,6 +522,56 @@ def test_timeout_fires_while_the_scan_is_running(vs):
     L.VecSimB200_SetCoarseMode(-1)
 
 
+def test_abandoned_scan_winds_down_on_the_device(vs):
+    """A caller that timed out has left; the exact-scan kernel polls a host flag (mapped pinned memory) and stops, so the GPU does
+    not finish a long pass nobody waits for: after the timed-out call the device drains in a fraction of the pass."""
+    import time
+
+    import torch
+
+    L = vs.lib()
+    L.VecSimB200_SetCoarseMode(0)
+    try:
+        n, dim, nq, k = 2_000_000, 256, 256, 10
+        g = vs.VecSimIndex(F32, dim, L2)
+        for r0 in range(0, n, 500_000):
+            g.add_many(ol.synth_rows(ol.F32, 5, r0, 500_000, dim), label0=1 + r0)
+        qs = ol.synth_rows(ol.F32, 6, 0, nq, dim)
+        g.topk_batch(qs, k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        labels, scores, rc = g.topk_batch(qs, k)
+        full_s = time.perf_counter() - t0
+        assert rc == vs.VecSim_QueryReply_OK and full_s > 0.01, full_s
+        calls = {"n": 0}
+
+        def fire_after_a_few_polls(ctx):
+            calls["n"] += 1
+            return 1 if calls["n"] > 4 else 0
+
+        cb = vs.TIMEOUT_CB(fire_after_a_few_polls)
+        cb_off = vs.TIMEOUT_CB(lambda ctx: 0)
+        _KEEPALIVE.extend([cb, cb_off])
+        qp = vs.VecSimQueryParams()
+        out_l = np.zeros((nq, k), dtype=np.uint64)
+        out_s = np.zeros((nq, k), dtype=np.float64)
+        L.VecSim_SetTimeoutCallbackFunction(cb)
+        try:
+            t0 = time.perf_counter()
+            rc = L.VecSimB200_TopKQueryBatch(g.h, qs.ctypes.data, qs.strides[0], nq, k, C.byref(qp), out_l.ctypes.data, out_s.ctypes.data)
+            early_s = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            drained_s = time.perf_counter() - t0
+        finally:
+            L.VecSim_SetTimeoutCallbackFunction(cb_off)
+        assert rc == vs.VecSim_QueryReply_TimedOut
+        assert early_s < 0.5 * full_s and drained_s < 0.5 * full_s, (early_s, drained_s, full_s)
+        l2, s2, rc2 = g.topk_batch(qs, k)  # the flag is cleared when the scratch is reused
+        assert rc2 == vs.VecSim_QueryReply_OK and (l2 == labels).all() and s2.tobytes() == scores.tobytes()
+    finally:
+        L.VecSimB200_SetCoarseMode(-1)
+
+
 def test_resolve_params(vs):
     """vec_sim.cpp:270-343 for a FLAT index."""
     L = vs.lib()
