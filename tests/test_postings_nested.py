@@ -306,3 +306,29 @@ def test_optional_and_not_over_nested_sets(ps, scorer):
     assert got == exp_docs
     both = cp.docs(q_opt)
     assert freqs == [cp.freq[0][d] + ((cp.freq[1][d] + cp.freq[2][d]) if d in both else 0) for d in exp_docs]
+
+
+@pytest.mark.parametrize("scorer", [ol.SCORER_BM25STD, ol.SCORER_TFIDF])
+def test_search_topn_over_a_nested_child(ps, scorer):
+    """II_SearchTopN / II_SearchTopNBatch (AND -> scorer -> top-N in one call) with a nested set among the lists: the per-query chain
+    recurses into it; same rows as scoring the result set and sorting on the host (score desc, docId asc: RPSorter's order)."""
+    rng = np.random.default_rng(5100 + scorer)
+    n_docs = 30_000
+    cp = Corpus(ps, rng, n_docs, [0.3, 0.25, 0.5])
+    doc_len = rng.integers(1, 900, n_docs + 1).astype(np.uint32)
+    dt = ps.DocTable(n_docs, doc_len, None, rng.integers(1, 60, n_docs + 1).astype(np.uint32))
+    q = SHAPES["(a|b) c"]()
+    avg = 200.0
+    rs, terms = cp.evaluate(q)
+    rs.score(scorer, terms, q.weight, n_docs, avg, dt, 0.0, 4)
+    ids, scores, _ = rs.fetch()
+    order = np.lexsort((ids, -scores))[:10]
+    views = [cp.child_list(k) for k in q.kids]
+    got_ids, got_scores, total = ps.search_topn([v[0] for v in views], False, scorer, [v[1] for v in views], q.weight, n_docs, avg, dt, 10)
+    assert total == len(ids)
+    assert got_ids.tolist() == ids[order].tolist()
+    assert got_scores.tobytes() == scores[order].tobytes()
+    views2 = [cp.child_list(k) for k in q.kids]
+    batch = ps.SearchBatch([([v[0] for v in views2], [v[1] for v in views2])], 10)
+    b_ids, b_scores, b_total = batch.run(False, scorer, q.weight, n_docs, avg, dt)[0]
+    assert b_total == len(ids) and b_ids.tolist() == ids[order].tolist() and b_scores.tobytes() == scores[order].tobytes()
