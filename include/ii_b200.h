@@ -402,6 +402,14 @@ typedef struct {
     double h2d_us;
 } II_Stats;
 II_Stats II_GetStats(bool reset);
+/* EXPLAINSCORE of ONE result given as a flattened result tree (node 0 the root, parent[i] < i, children in index order; kind 0 term,
+ * 1 intersection, 2 union, 3 virtual, 4 numeric; term_str: the text printed for term leaves, may be NULL): the explanation tree the
+ * reference's scorer builds with its EXPLAIN macro (src/ext/default.c:68-497, strExpCreateParent :58-65), serialised one node per
+ * line as "<depth> <string>\n" in pre-order; *score_out = the score.  Host code, no device.  Returns the bytes needed (excluding NUL).
+ * The *.B200 scorers use the same builder when ScoringFunctionArgs.scrExp is set. */
+size_t II_ExplainTree(int scorer, size_t n_nodes, const int32_t *parent, const int32_t *kind, const uint32_t *freq, const double *weight,
+                      const double *idf, const double *bm25_idf, const char *term_str, uint32_t doc_len, uint32_t max_freq, float doc_score,
+                      double avg_doc_len, int slop, double min_score, uint64_t tanh_factor, double *score_out, char *buf, size_t cap);
 const char *II_Version(void);
 
 #ifdef __cplusplus

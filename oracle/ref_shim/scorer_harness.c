@@ -21,6 +21,7 @@
 #include "buffer.h"
 
 #include <stddef.h>
+#include <stdarg.h>
 
 #define MAX_TERMS 32
 #define MAX_NODES 512
@@ -82,7 +83,15 @@ const char *QueryTerm_GetStrAndLen(const struct RSQueryTerm *t, size_t *out_len)
   *out_len = 1;
   return ((const HarnessTerm *)t)->str;
 }
-void explain(RSScoreExplain *scrExp, char *fmt, ...) {}
+/* src/score_explain.c:62-72 (the file itself pulls in the reply machinery; this is its one function the scorers call) */
+void explain(RSScoreExplain *scrExp, char *fmt, ...) {
+  char *old = scrExp->str;
+  va_list ap;
+  va_start(ap, fmt);
+  if (vasprintf(&scrExp->str, fmt, ap) < 0) scrExp->str = NULL;
+  va_end(ap);
+  free(old);
+}
 /* term offsets: the slice handle is the side entry itself */
 const RSOffsetSlice *IndexResult_TermOffsetsRef(const RSIndexResult *r) { return (const RSOffsetSlice *)&g_side[node_index(r)]; }
 uint32_t RSOffsetVector_Len(const RSOffsetSlice *offsets) { return ((const Side *)offsets)->off_len; }
@@ -299,4 +308,59 @@ double RefHamming(const char *payload, size_t payload_len, const char *qdata, si
   args.qdatalen = qdatalen;
   pool_reset();
   return fn(&args, &g_root, &dmd, 0);
+}
+
+/* EXPLAINSCORE of the loaded tree: the reference's scorer run with ScoringFunctionArgs.scrExp set, the resulting RSScoreExplain tree
+ * (rooted where ctx->scrExp points AFTER the call: strExpCreateParent re-roots it, default.c:58-65) serialised one node per line as
+ * "<depth> <string>\n" in pre-order.  Returns the bytes needed. */
+static size_t ser(const RSScoreExplain *e, int depth, char *buf, size_t cap, size_t at) {
+  char head[16];
+  const int hn = snprintf(head, sizeof(head), "%d ", depth);
+  const char *str = e->str ? e->str : "(null)";
+  const size_t sn = strlen(str);
+  if (buf && at + hn + sn + 1 < cap) {
+    memcpy(buf + at, head, hn);
+    memcpy(buf + at + hn, str, sn);
+    buf[at + hn + sn] = '\n';
+  }
+  at += hn + sn + 1;
+  for (int i = 0; i < e->numChildren; i++) at = ser(&e->children[i], depth + 1, buf, cap, at);
+  return at;
+}
+static void free_exp(RSScoreExplain *e) {
+  for (int i = 0; i < e->numChildren; i++) free_exp(&e->children[i]);
+  free(e->children);
+  free(e->str);
+}
+size_t RefTreeExplain(const char *scorer, uint32_t doc_len, uint32_t max_freq, float doc_score, size_t num_docs, double avg_doc_len,
+                      int slop, double min_score, uint64_t tanh_factor, double *score_out, char *buf, size_t cap) {
+  if (!g_nscorers) {
+    RSExtensionCtx ctx = {reg_scorer, reg_expander};
+    DefaultExtensionInit(&ctx);
+  }
+  RSScoringFunction fn = NULL;
+  for (int i = 0; i < g_nscorers; i++)
+    if (!strcmp(g_scorers[i].name, scorer)) fn = g_scorers[i].fn;
+  if (!fn) return 0;
+  RSDocumentMetadata dmd;
+  memset(&dmd, 0, sizeof(dmd));
+  dmd.score = doc_score;
+  dmd.docLen = doc_len;
+  dmd.maxTermFreq = max_freq;
+  ScoringFunctionArgs args;
+  memset(&args, 0, sizeof(args));
+  args.indexStats.numDocs = num_docs;
+  args.indexStats.avgDocLen = avg_doc_len;
+  args.GetSlop = slop < 0 ? tree_slop : harness_slop;
+  args.tanhFactor = tanh_factor;
+  args.scrExp = calloc(1, sizeof(RSScoreExplain));
+  g_slop = slop;
+  const double sc = fn(&args, &g_root, &dmd, min_score);
+  if (score_out) *score_out = sc;
+  RSScoreExplain *root = args.scrExp;
+  const size_t n = ser(root, 0, buf, cap, 0);
+  if (buf && cap) buf[n < cap ? n : cap - 1] = 0;
+  free_exp(root);
+  free(root);
+  return n;
 }

@@ -1,6 +1,7 @@
 // Host side of libii_b200.so: posting-list objects, block decoding, the iterator algebra entry
 // points, scoring, ranking and the QueryIterator facade.  Contract: include/ii_b200.h.
 #include "../../include/ii_b200.h"
+#include "ii_explain.h"
 #include "ii_kernels.h"
 #include "ii_codec.h"
 #include <functional>
@@ -3098,5 +3099,45 @@ size_t II_MergeShardTopN(const double *scores, const uint64_t *doc_ids, const si
     return k;
 }
 const char *II_Version(void) { return "ii_b200 0.1 (sm_100a)"; }
+
+// EXPLAINSCORE of one result given as a flattened tree (node 0 the root, parent[i] < i, children in index order; kind 0 term,
+// 1 intersection, 2 union, 3 virtual, 4 numeric; term_str: every term leaf's text, may be NULL): the explanation the reference's
+// scorer builds (src/ext/default.c), serialised one node per line as "<depth> <string>\n" in pre-order.  Host code (no device):
+// what the *.B200 scorers call when ScoringFunctionArgs.scrExp is set.  Returns the bytes needed (excluding the NUL).
+size_t II_ExplainTree(int scorer, size_t n_nodes, const int32_t *parent, const int32_t *kind, const uint32_t *freq, const double *weight,
+                      const double *idf, const double *bm25_idf, const char *term_str, uint32_t doc_len, uint32_t max_freq, float doc_score,
+                      double avg_doc_len, int slop, double min_score, uint64_t tanh_factor, double *score_out, char *buf, size_t cap) {
+    if (!n_nodes) return 0;
+    std::vector<iiexplain::TreeNode> flat(n_nodes);
+    for (size_t i = 0; i < n_nodes; i++) {
+        flat[i].kind = kind[i];
+        flat[i].freq = freq[i];
+        flat[i].weight = weight[i];
+        flat[i].idf = idf[i];
+        flat[i].bm25_idf = bm25_idf[i];
+        if (term_str) flat[i].term = term_str;
+    }
+    for (size_t i = n_nodes; i-- > 1;) { // children were appended after their parents: fold from the back, keeping index order
+        if (parent[i] < 0 || (size_t)parent[i] >= i) return 0;
+        iiexplain::TreeNode &p = flat[parent[i]];
+        p.kids.insert(p.kids.begin(), std::move(flat[i]));
+    }
+    iiexplain::Explain e;
+    const iiexplain::DocParams d{doc_len, max_freq, doc_score, avg_doc_len};
+    const double score = iiexplain::explain_score(scorer, flat[0], d, slop, min_score, tanh_factor, e);
+    if (score_out) *score_out = score;
+    std::string out;
+    std::function<void(const iiexplain::Explain &, int)> walk = [&](const iiexplain::Explain &n, int depth) {
+        out += std::to_string(depth) + " " + n.str + "\n";
+        for (const auto &k : n.kids) walk(k, depth + 1);
+    };
+    walk(e, 0);
+    if (buf && cap) {
+        const size_t m = std::min(cap - 1, out.size());
+        memcpy(buf, out.data(), m);
+        buf[m] = 0;
+    }
+    return out.size();
+}
 
 } // extern "C"

@@ -74,6 +74,8 @@ SIGNATURES = [
     ("II_Union", _P, [_P, _SZ, C.c_int]),
     ("II_ResultSet_Len", _SZ, [_P]),
     ("II_ResultSet_Free", None, [_P]),
+    ("II_ExplainTree", C.c_size_t, [C.c_int, C.c_size_t, _P, _P, _P, _P, _P, _P, C.c_char_p, C.c_uint32, C.c_uint32, C.c_float, C.c_double,
+                        C.c_int, C.c_double, C.c_uint64, _P, _P, C.c_size_t]),
     ("II_ResultSet_IntoChild", _P, [_P, _P, C.c_double, C.c_int]),
     ("II_CalculateIDF", C.c_double, [_SZ, _SZ]),
     ("II_CalculateIDF_BM25", C.c_double, [_SZ, _SZ]),

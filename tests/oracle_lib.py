@@ -467,6 +467,8 @@ def ref_scorers():
         L.RefTreeHasOffsets.argtypes = [_SZ]
         L.RefTreeOffsets.restype = _SZ
         L.RefTreeOffsets.argtypes = [_SZ, _P, _SZ]
+        L.RefTreeExplain.restype = _SZ
+        L.RefTreeExplain.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_float, _SZ, C.c_double, C.c_int, C.c_double, C.c_uint64, _P, _P, _SZ]
         L.RefTreeScore.restype = C.c_double
         L.RefTreeScore.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_float, _SZ, C.c_double, C.c_int, C.c_double, C.c_uint64]
         _ref_scorers = L
@@ -715,6 +717,15 @@ class ResultTree:
     def ref_score(self, scorer, doc_len, max_freq, doc_score, num_docs, avg_doc_len, slop=-1, min_score=0.0, tanh_factor=4):
         return self._ref_load().RefTreeScore(SCORER_NAMES[scorer], doc_len, max_freq, doc_score, num_docs, avg_doc_len, slop, min_score,
                                              int(tanh_factor))
+
+    def ref_explain(self, scorer, doc_len, max_freq, doc_score, num_docs, avg_doc_len, slop=-1, min_score=0.0, tanh_factor=4):
+        """(score, explanation) of the reference's scorer run with scrExp set; one "<depth> <string>" line per node, pre-order"""
+        L = self._ref_load()
+        buf = C.create_string_buffer(1 << 16)
+        sc = C.c_double(0)
+        L.RefTreeExplain(SCORER_NAMES[scorer], doc_len, max_freq, doc_score, num_docs, avg_doc_len, slop, min_score, int(tanh_factor),
+                         C.byref(sc), buf, len(buf))
+        return sc.value, buf.value.decode()
 
     def ref_offsets(self, node=0):
         L = self._ref_load()

@@ -159,3 +159,40 @@ def test_tree_scores_are_bit_equal_to_the_reference(scorer):
         a = t.score(scorer, doc_len, max_freq, doc_score, 10_000, avg, slop=-1, min_score=min_score, tanh_factor=4.0)
         b = t.ref_score(scorer, doc_len, max_freq, doc_score, 10_000, avg, slop=-1, min_score=min_score, tanh_factor=4)
         assert bits(a) == bits(b), (i, a, b)
+
+
+# ---- EXPLAINSCORE: the PRODUCT's host-side explanation builder (libii_b200.so II_ExplainTree, no device) against the reference's
+# scorers run with scrExp set (the EXPLAIN strings of src/ext/default.c, re-rooted by strExpCreateParent) ------------------------
+def product_explain(t, scorer, doc_len, max_freq, doc_score, avg, slop, min_score, tanh_factor=4):
+    import ctypes as C
+
+    from redisearch_b200 import postings
+
+    L = postings.lib()
+    buf = C.create_string_buffer(1 << 16)
+    sc = C.c_double(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    L.II_ExplainTree(scorer, len(t.nodes), p(t.parent), p(t.kind), p(t.freq), p(t.weight), p(t.idf), p(t.bm25), b"t", doc_len, max_freq,
+                     doc_score, avg, slop, min_score, tanh_factor, C.byref(sc), buf, len(buf))
+    return sc.value, buf.value.decode()
+
+
+@needs_ref
+@pytest.mark.parametrize("scorer", [ol.SCORER_BM25STD, ol.SCORER_BM25, ol.SCORER_TFIDF, ol.SCORER_TFIDF_DOCNORM, ol.SCORER_DOCSCORE,
+                                    ol.SCORER_BM25STD_TANH, ol.SCORER_DISMAX])
+def test_explainscore_strings_equal_the_reference(scorer):
+    rng = np.random.default_rng(700 + scorer)
+    shapes = set()
+    for i in range(250):
+        t = ResultTree(random_tree(rng))
+        doc_len, max_freq = int(rng.integers(0, 400)), int(rng.integers(0, 12))
+        doc_score = float(np.float32(rng.choice([1.0, 0.5, 0.0, 2.5])))
+        avg = float(rng.uniform(5.0, 300.0))
+        min_score = float(rng.choice([0.0, 0.0, 0.05, 1.0]))
+        slop = t.min_offset_delta()
+        ref_score, ref_text = t.ref_explain(scorer, doc_len, max_freq, doc_score, 10_000, avg, slop=slop, min_score=min_score)
+        got_score, got_text = product_explain(t, scorer, doc_len, max_freq, doc_score, avg, slop, min_score)
+        assert got_text == ref_text, (i, got_text, ref_text)
+        assert bits(got_score) == bits(ref_score) or scorer == ol.SCORER_BM25STD_TANH and abs(got_score - ref_score) < 1e-15
+        shapes.add(ref_text.count("\n"))
+    assert len(shapes) >= 4 or scorer == ol.SCORER_DOCSCORE  # trees of several sizes, the early-out forms included
