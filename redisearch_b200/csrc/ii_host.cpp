@@ -198,6 +198,7 @@ struct II_ResultSet {
     std::vector<std::shared_ptr<struct NestedSet>> nested;
     std::vector<uint8_t> child_tag; // RSResultData tag per child (aggregate order)
     size_t estimated = 0;           // num_estimated by the reference's rule: min over the children (AND), their sum (OR)
+    std::unique_ptr<UnionOrder> h_order; // host copy of d_order (EXPLAINSCORE walks one hit's children in aggregate order)
     ~II_ResultSet() {
         dfree(d_docs);
         dfree(d_freqs);
@@ -216,6 +217,7 @@ struct II_ResultSet {
 struct NestedSet {
     std::unique_ptr<II_ResultSet> rs;
     std::vector<II_TermParams> terms; // of rs's children, in the order they were given to the constructor
+    std::vector<std::string> term_strs; // their texts where known (EXPLAINSCORE of BM25STD prints them)
     double weight = 1.0;
     uint32_t *d_fsum = nullptr; // [rs->len] freq of the aggregate result = sum of its children's
     double *d_sub = nullptr;    // [rs->len] recursive score of every hit for the scorer being evaluated
@@ -1240,6 +1242,7 @@ bool union_enqueue(Ctx &c, II_PostingList *const *lists, size_t n, int quick_exi
         if (rs->has_freqs) ok = cudaMemsetAsync(rs->d_freqs, 0, rs->cap * n * 4, c.stream) == cudaSuccess;
         if (rs->d_order) { // pageable source: the copy is staged before the call returns
             ok = ok && cudaMemcpyAsync(rs->d_order, &uo, sizeof(uo), cudaMemcpyHostToDevice, c.stream) == cudaSuccess;
+            rs->h_order.reset(new UnionOrder(uo));
         }
         if (keep_pos) {
             ok = ok && cudaMemsetAsync(rs->d_hit_pos, 0xFF, rs->cap * n * 4, c.stream) == cudaSuccess;
@@ -2306,6 +2309,8 @@ struct NodeIter {
     // result of an evaluated AND / OR (or a leaf that is read directly)
     II_ResultSet *rs = nullptr;
     std::vector<II_TermParams> terms; // per child, in the order of the constructor's `its`
+    std::vector<std::string> term_strs; // per child: the term's text where the host gave one (EXPLAINSCORE)
+    std::string term_str;               // leaf: QueryTerm_GetStrAndLen of host_term
     double agg_weight = 1.0;
     int scored_with = -1; // II_Scorer the host score array holds
     const II_DocTable *docs = nullptr;
@@ -2350,6 +2355,7 @@ bool node_materialise(NodeIter *it) {
         it->rs = II_Union(one, 1, 0);
         if (!it->rs) return false;
         it->terms.assign(1, it->term);
+        it->term_strs.assign(1, it->term_str);
         it->agg_weight = 1.0;
     }
     return true;
@@ -2516,6 +2522,7 @@ struct ChildView { // what the algebra needs from a child
     bool temp = false; // built here (foreign / nested result): freed after the evaluation
     LeafMode mode = LEAF_REQUIRED;
     II_TermParams term{1.0, 1.0, 1.0};
+    std::string str;
 };
 bool child_view(II_QueryIterator *c, ChildView &v, bool need_offsets) {
     if (is_node(c)) {
@@ -2524,6 +2531,8 @@ bool child_view(II_QueryIterator *c, ChildView &v, bool need_offsets) {
             v.pl = n->pl;
             v.mode = n->mode;
             v.term = n->term;
+            v.str = n->term_str;
+            if (v.pl && v.pl->nested && v.pl->nested->term_strs.empty()) v.pl->nested->term_strs = n->term_strs; // -(a|b), ~(a b)
             return v.pl != nullptr;
         }
         if (n->kind == NODE_WILDCARD) { // every document, as a virtual result with freq 1: a leaf with idf = 1 scores the same
@@ -2539,6 +2548,7 @@ bool child_view(II_QueryIterator *c, ChildView &v, bool need_offsets) {
                 II_ResultSet *inner = n->rs;
                 n->rs = nullptr;
                 v.pl = II_ResultSet_IntoChild(inner, n->terms.data(), n->agg_weight, need_offsets ? 1 : 0);
+                if (v.pl && v.pl->nested) v.pl->nested->term_strs = n->term_strs;
                 v.temp = true;
                 v.term = II_TermParams{n->agg_weight, 1.0, 1.0}; // not read: the nested set carries its own
                 return v.pl != nullptr;
@@ -2780,6 +2790,13 @@ II_QueryIterator *NewInvIndIterator_TermQuery(const void *idx, const void *sctx,
     }
     if (!it) return nullptr;
     api.SetIDFs(term, idf, bm25_idf);
+    {
+        static const char *(*get_str)(const void *, size_t *) =
+            reinterpret_cast<const char *(*)(const void *, size_t *)>(dlsym(RTLD_DEFAULT, "QueryTerm_GetStrAndLen"));
+        size_t len = 0;
+        const char *str = get_str ? get_str(term, &len) : nullptr;
+        if (str && is_node(it)) NI(it)->term_str.assign(str, len);
+    }
     NI(it)->host_term = term;
     NI(it)->host_term_free = api.TermFree;
     if (it->type != II_IteratorType_Empty) it->type = 1; // IteratorType_InvIdxTerm
@@ -2902,10 +2919,12 @@ static II_QueryIterator *build_aggregate(II_QueryIterator **its, size_t num, boo
         std::vector<II_PostingList *> pls;
         std::vector<int> modes;
         std::vector<II_TermParams> terms;
+        std::vector<std::string> strs;
         for (auto &v : views) {
             pls.push_back(v.pl);
             modes.push_back((int)v.mode);
             terms.push_back(v.term);
+            strs.push_back(v.str);
         }
         bool any_mode = false, any_required = false;
         for (int m : modes) any_mode |= m != LEAF_REQUIRED, any_required |= m == LEAF_REQUIRED;
@@ -2924,6 +2943,7 @@ static II_QueryIterator *build_aggregate(II_QueryIterator **its, size_t num, boo
             out = new_node(NODE_RESULT, is_union ? II_IteratorType_Union : II_IteratorType_Intersect, weight);
             out->rs = rs;
             out->terms = terms;
+            out->term_strs = strs;
             out->agg_weight = weight;
         }
     }
@@ -2998,6 +3018,90 @@ struct RSExtensionCtxC { // src/redisearch.h:282-287
     int (*RegisterQueryExpander)(const char *alias, void *exp, void (*ff)(void *), void *privdata);
 };
 
+// ---- EXPLAINSCORE: the result tree of ONE hit read back from the device --------------------------------------------
+// column i of a [n][stride] device array
+bool fetch_column(const uint32_t *d, size_t stride, uint32_t n, size_t i, uint32_t *out) {
+    return cudaMemcpy2D(out, 4, d + i, stride * 4, 4, n, cudaMemcpyDeviceToHost) == cudaSuccess;
+}
+// The reference's RSIndexResult tree for hit i of rs (document `doc`): children in aggregate order, a union's matching children only,
+// NOT / absent OPTIONAL children of an intersection as virtual results, nested sets recursively through the hit's position in them.
+bool hit_tree(const II_ResultSet *rs, const II_TermParams *terms, const std::vector<std::string> &strs, double weight, size_t i, uint32_t doc,
+              iiexplain::TreeNode &out) {
+    const uint32_t n = rs->n_children;
+    if (n == 0 || n > (uint32_t)kIIMaxLists || !rs->has_freqs || i >= rs->len) return false;
+    out = iiexplain::TreeNode();
+    out.kind = rs->is_union ? iiexplain::Union : iiexplain::Intersection;
+    out.weight = weight;
+    uint32_t fr[kIIMaxLists], pos[kIIMaxLists];
+    if (!fetch_column(rs->d_freqs, rs->cap, n, i, fr)) return false;
+    const bool have_pos = rs->d_hit_pos != nullptr;
+    if (have_pos && !fetch_column(rs->d_hit_pos, rs->cap, n, i, pos)) return false;
+    // aggregate order: the constructor's for an intersection, the active array's epoch for a flat union (UnionOrder)
+    uint32_t order[kIIMaxLists], cnt = n;
+    for (uint32_t c = 0; c < n; c++) order[c] = c;
+    if (rs->is_union && rs->h_order) {
+        const UnionOrder &uo = *rs->h_order;
+        uint32_t e = 0;
+        while (e + 1 < uo.n_epochs && doc > uo.bound[e]) e++;
+        cnt = uo.n_active[e];
+        for (uint32_t c = 0; c < cnt; c++) order[c] = uo.perm[e][c];
+    }
+    for (uint32_t ci = 0; ci < cnt; ci++) {
+        const uint32_t c = order[ci];
+        const bool there = have_pos ? pos[c] != 0xFFFFFFFFu : fr[c] != 0;
+        if (rs->is_union && !there) continue;
+        iiexplain::TreeNode kid;
+        const uint8_t tag = c < rs->child_tag.size() ? rs->child_tag[c] : 4;
+        if (!there || tag == 8) { // NOT / absent OPTIONAL: a virtual result without weight; a wildcard child: virtual, freq 1
+            kid.kind = iiexplain::Virtual;
+            kid.freq = there ? fr[c] : 0;
+            kid.weight = there ? terms[rs->child_order[c]].weight : 0.0;
+        } else if (c < rs->nested.size() && rs->nested[c]) {
+            const NestedSet *ns = rs->nested[c].get();
+            if (!have_pos || !hit_tree(ns->rs.get(), ns->terms.data(), ns->term_strs, ns->weight, pos[c], doc, kid)) return false;
+        } else {
+            const II_TermParams &t = terms[rs->child_order[c]];
+            kid.kind = tag == 16 || tag == 32 ? iiexplain::Numeric : iiexplain::Term;
+            kid.freq = fr[c];
+            kid.weight = t.weight;
+            kid.idf = t.idf;
+            kid.bm25_idf = t.bm25_idf;
+            const uint32_t si = rs->child_order[c];
+            if (si < strs.size()) kid.term = strs[si];
+        }
+        out.freq += kid.freq;
+        out.kids.push_back(std::move(kid));
+    }
+    return true;
+}
+void *host_calloc(size_t n, size_t sz) {
+    void *p = host_alloc(n * sz);
+    if (p) memset(p, 0, n * sz);
+    return p;
+}
+struct ScoreExplainC { // src/score_explain.h:20-24
+    char *str;
+    int numChildren;
+    ScoreExplainC *children;
+};
+// the explanation into nodes owned by the host's allocator: `dst` is filled in place (str, a children array of its own)
+bool explain_to_host(const iiexplain::Explain &e, ScoreExplainC *dst) {
+    char *str = static_cast<char *>(host_alloc(e.str.size() + 1));
+    if (!str) return false;
+    memcpy(str, e.str.c_str(), e.str.size() + 1);
+    if (dst->str) host_free(dst->str);
+    dst->str = str;
+    dst->numChildren = 0;
+    dst->children = nullptr;
+    if (e.kids.empty()) return true;
+    dst->children = static_cast<ScoreExplainC *>(host_calloc(e.kids.size(), sizeof(ScoreExplainC)));
+    if (!dst->children) return false;
+    dst->numChildren = (int)e.kids.size();
+    for (size_t k = 0; k < e.kids.size(); k++)
+        if (!explain_to_host(e.kids[k], &dst->children[k])) return false;
+    return true;
+}
+
 template <int kScorer>
 double b200_scorer(const ScoringFunctionArgsC *args, const void *res_v, const void *dmd, double min_score) {
     (void)dmd;
@@ -3031,24 +3135,54 @@ double b200_scorer(const ScoringFunctionArgsC *args, const void *res_v, const vo
     const double score = i < it->scores.size() ? it->scores[i] : 0.0;
     if (args->scrExp) {
         // EXPLAINSCORE (src/result_processor.c:582-584 hands the node to the reply, src/score_explain.c:19-21 prints `str`
-        // unconditionally): the per-term break-down of the reference's scorers is not itemised here, but the node must carry a
-        // string owned by the host's allocator
-        struct ScoreExplainC { // src/score_explain.h:20-24
-            char *str;
-            int numChildren;
-            ScoreExplainC *children;
-        };
-        static const char *const kNames[] = {"BM25STD", "BM25", "TFIDF", "TFIDF.DOCNORM", "DOCSCORE", "BM25STD.TANH", "DISMAX", "HAMMING"};
+        // unconditionally): the hit's result tree is read back from the device and explained with the reference's own strings
+        // (ii_explain.cpp); the node RPScorer handed in becomes the root, filled in place
         auto *e = static_cast<ScoreExplainC *>(args->scrExp);
-        char buf[192];
-        const int len = snprintf(buf, sizeof(buf), "Final %s.B200 : %.2f (scored on the device with the whole result set; per-term break-down not itemised)",
-                                 kNames[kScorer], score);
-        char *str = static_cast<char *>(host_alloc((size_t)len + 1));
-        if (str) {
-            memcpy(str, buf, (size_t)len + 1);
-            if (e->str) host_free(e->str);
-            e->str = str;
+        iiexplain::Explain ex;
+        bool itemised = false;
+        if (kScorer == II_SCORER_HAMMING) {
+            iiexplain::explain_hamming(score, args->qdatalen, ex);
+            itemised = true;
+        } else if (i < it->ids.size()) {
+            Ctx &c = ctx();
+            std::lock_guard<std::mutex> g(c.mu);
+            const uint32_t doc = (uint32_t)it->ids[i];
+            iiexplain::TreeNode tree;
+            iiexplain::DocParams dp;
+            dp.avg_doc_len = args->indexStats.avgDocLen;
+            dp.doc_score = 1.0f;
+            dp.max_freq = 1;
+            bool ok = c.init() && cudaStreamSynchronize(c.stream) == cudaSuccess && hit_tree(it->rs, it->terms.data(), it->term_strs, it->agg_weight, i, doc, tree);
+            const II_DocTable *dt = it->docs;
+            if (ok && dt && doc <= dt->max_doc) {
+                if (dt->d_len) ok = ok && cudaMemcpy(&dp.doc_len, dt->d_len + doc, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+                if (dt->d_score) ok = ok && cudaMemcpy(&dp.doc_score, dt->d_score + doc, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+                if (dt->d_maxf) ok = ok && cudaMemcpy(&dp.max_freq, dt->d_maxf + doc, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+            }
+            uint32_t slop = 1;
+            if (ok && (kScorer == II_SCORER_BM25 || kScorer == II_SCORER_TFIDF || kScorer == II_SCORER_TFIDF_DOCNORM)) {
+                if (it->rs->d_slop)
+                    ok = cudaMemcpy(&slop, it->rs->d_slop + i, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+                else
+                    slop = tree.kids.size() <= 1 ? 1u : (uint32_t)tree.kids.size() - 1u; // IndexResult_MinOffsetDelta without offsets
+            }
+            if (ok) {
+                if (it->kind == NODE_LEAF && tree.kids.size() == 1) { // a term read directly: the reference's root IS the term result
+                    iiexplain::TreeNode only = std::move(tree.kids[0]);
+                    tree = std::move(only);
+                }
+                iiexplain::explain_score(kScorer, tree, dp, (int)slop, min_score, args->tanhFactor ? args->tanhFactor : 4, ex);
+                itemised = true;
+            }
         }
+        if (!itemised) {
+            static const char *const kNames[] = {"BM25STD", "BM25", "TFIDF", "TFIDF.DOCNORM", "DOCSCORE", "BM25STD.TANH", "DISMAX", "HAMMING"};
+            char buf[160];
+            snprintf(buf, sizeof(buf), "Final %s.B200 : %.2f (per-term break-down not available for this result)", kNames[kScorer], score);
+            ex = iiexplain::Explain();
+            ex.str = buf;
+        }
+        explain_to_host(ex, e);
     }
     return score;
 }

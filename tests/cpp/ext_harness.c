@@ -189,6 +189,21 @@ static RSScoringFunction scorer(const char *name) {
 
 #define SYM(T, name) T name = (T)dlsym(lib, #name); if (!name) { fprintf(stderr, "missing %s\n", #name); return 2; }
 
+typedef struct ExplainNode { /* src/score_explain.h:20-24 */
+    char *str;
+    int numChildren;
+    struct ExplainNode *children;
+} ExplainNode;
+static void print_explain(const ExplainNode *e, int depth) {
+    printf("%d %s\n", depth, e->str ? e->str : "(null)");
+    for (int i = 0; i < e->numChildren; i++) print_explain(&e->children[i], depth + 1);
+}
+static void free_explain(ExplainNode *e) { /* recExplainDestroy, src/score_explain.c:34-41 */
+    for (int i = 0; i < e->numChildren; i++) free_explain(&e->children[i]);
+    free(e->children);
+    free(e->str);
+}
+
 int main(int argc, char **argv) {
     if (argc < 5) return 2;
     void *lib = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
@@ -356,13 +371,16 @@ int main(int argc, char **argv) {
         printf("variant 5 estimated %zu\n", it->NumEstimated(it));
         int explained = 0;
         while (it->Read(it) == ITERATOR_OK) {
-            if (!explained) { /* EXPLAINSCORE: the node handed in must come back with a string (score_explain.c prints it as is) */
-                struct { char *str; int numChildren; void *children; } exp = {NULL, 0, NULL};
+            if (!explained) { /* EXPLAINSCORE: the node handed in comes back as the root of the reference's explanation tree */
+                ExplainNode exp = {NULL, 0, NULL};
                 args.scrExp = &exp;
-                const double se = bm25(&args, it->current, NULL, 0.0);
+                const double se = tfidf(&args, it->current, NULL, 0.0);
                 args.scrExp = NULL;
-                if (!exp.str || !strstr(exp.str, "BM25STD.B200") || se != bm25(&args, it->current, NULL, 0.0)) return 32;
-                free(exp.str);
+                if (!exp.str || se != tfidf(&args, it->current, NULL, 0.0)) return 32;
+                printf("explain %llu\n", (unsigned long long)it->lastDocId);
+                print_explain(&exp, 0);
+                printf("explain-end\n");
+                free_explain(&exp);
                 explained = 1;
             }
             const double s1 = bm25(&args, it->current, NULL, 0.0);

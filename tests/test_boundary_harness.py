@@ -113,9 +113,19 @@ def test_constructors_and_scorer_extension_from_a_c_host(tmp_path):
     na, ne, nb = (len(lists[x][0]) for x in "aeb")
     assert lines[i5] == f"variant 5 estimated {min(na + ne, nb)}"  # AND: min over the children; OR: their sum
     rows5 = []
+    explain_doc, explain_lines, in_explain = None, [], False
     for l in lines[i5 + 1:]:
         if l.startswith("cache"):
             break
+        if l.startswith("explain "):
+            explain_doc, in_explain = int(l.split()[1]), True
+            continue
+        if l == "explain-end":
+            in_explain = False
+            continue
+        if in_explain:
+            explain_lines.append(l)
+            continue
         d, s1, f, s2 = l.split()
         rows5.append((int(d), float.fromhex(s1), int(f), float.fromhex(s2)))
     ma, me, mb = lookup("a"), lookup("e"), lookup("b")
@@ -138,6 +148,14 @@ def test_constructors_and_scorer_extension_from_a_c_host(tmp_path):
         assert np.float64(s1).tobytes() == np.float64(e1).tobytes(), (d, s1, e1)
         assert np.float64(s2).tobytes() == np.float64(e2).tobytes(), (d, s2, e2)
         assert f == sum(m[d] for m in (ma, me, mb) if d in m)
+        if d == explain_doc:
+            # EXPLAINSCORE through TFIDF.B200 (scrExp set): the tree read back from the device, explained with the reference's strings
+            want = "\n".join(explain_lines) + "\n"
+            if ol.ref_scorers() is not None:
+                assert t.ref_explain(ol.SCORER_TFIDF, int(doc_len[d]), 1, 1.0, n_docs, avg, slop=t.min_offset_delta())[1] == want
+            assert explain_lines[0].startswith("0 Final TFIDF : words TFIDF ") and explain_lines[1].startswith("1 (Weight 1.50 * total children TFIDF")
+            assert sum(1 for l in explain_lines if "= Weight" in l and "TF " in l) == sum(1 for m in (ma, me, mb) if d in m)
+    assert explain_doc == docs5[0] and len(explain_lines) >= 4
     # the term cache decoded a and b once: later constructions hit
     assert block(0)[1] == "cache hits 0 misses 2" and block(1)[1] == "cache hits 2 misses 2"
     assert f"union {len(np.union1d(lists['a'][0], lists['c'][0]))}" in lines
