@@ -1075,6 +1075,10 @@ bool ensure_merged(Ctx &c, NestedSet *ns) {
     uint32_t *ub = dalloc<uint32_t>(m ? m : 1), *csum = dalloc<uint32_t>(chunks ? chunks : 1), *coff = dalloc<uint32_t>(chunks ? chunks : 1);
     uint32_t *tot32 = dalloc<uint32_t>(4);
     unsigned long long *tot64 = dalloc<unsigned long long>(1);
+    dfree(ns->d_moff_pos); // a previous attempt that failed half-way
+    dfree(ns->d_moff_len);
+    dfree(ns->d_mbytes);
+    ns->d_mbytes = nullptr;
     ns->d_moff_pos = dalloc<uint32_t>(m ? m : 1);
     ns->d_moff_len = dalloc<uint32_t>(m ? m : 1);
     bool ok = ub && csum && coff && tot32 && tot64 && ns->d_moff_pos && ns->d_moff_len;
@@ -2805,7 +2809,8 @@ II_QueryIterator *NewInvIndIterator_TermQuery(const void *idx, const void *sctx,
 
 // `-(a|b)`, `~(a b)`: an evaluated nested AND / OR under NOT / OPTIONAL becomes a leaf whose list is the nested set's view
 // (II_ResultSet_IntoChild): excluded docIds for NOT; for OPTIONAL the set's recursive score where it matches, with the OPTIONAL's
-// weight as the aggregate's own (optional.rs:260,302 `real.weight = self.weight`).  false: not convertible, the node is untouched.
+// weight as the aggregate's own (optional.rs:260,302 `real.weight = self.weight`).  false: not convertible (the node is untouched,
+// or — when the device refused the view — left empty).
 static bool nested_node_to_leaf(II_QueryIterator *child, double weight) {
     if (!is_node(child)) return false;
     NodeIter *n = NI(child);
