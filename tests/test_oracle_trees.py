@@ -196,3 +196,33 @@ def test_explainscore_strings_equal_the_reference(scorer):
         assert bits(got_score) == bits(ref_score) or scorer == ol.SCORER_BM25STD_TANH and abs(got_score - ref_score) < 1e-15
         shapes.add(ref_text.count("\n"))
     assert len(shapes) >= 4 or scorer == ol.SCORER_DOCSCORE  # trees of several sizes, the early-out forms included
+
+
+@needs_ref
+def test_wide_and_deep_trees_equal_the_reference():
+    """up to 32 children per aggregate (the harness' and the device kernels' table size) and four levels of nesting: scores of every
+    scorer bit-equal, offsets / GetSlop equal, explanations byte-equal"""
+    rng = np.random.default_rng(4242)
+
+    def wide(depth):
+        nk = int(rng.integers(1, 33 if depth == 0 else 7))
+        kids = []
+        for _ in range(nk):
+            if depth < 3 and rng.random() < 0.25:
+                kids.append(wide(depth + 1))
+            else:
+                p = sorted(set(rng.integers(1, 2000, int(rng.integers(0, 5))).tolist()))
+                kids.append(term(p, freq=max(1, len(p)), weight=float(rng.choice([1.0, 0.5])), idf=float(rng.uniform(0.1, 9.0)),
+                                 bm25_idf=float(rng.uniform(0.01, 6.0))))
+        return agg(KIND_AND if rng.random() < 0.5 else KIND_OR, kids, weight=float(rng.choice([1.0, 0.7, 2.0])))
+
+    for i in range(60):
+        t = ResultTree(wide(0))
+        assert t.offsets(0) == t.ref_offsets(0)
+        slop = t.min_offset_delta()
+        assert slop == t.ref_min_offset_delta()
+        for scorer in (ol.SCORER_BM25STD, ol.SCORER_BM25, ol.SCORER_TFIDF, ol.SCORER_TFIDF_DOCNORM, ol.SCORER_DISMAX):
+            a = t.score(scorer, 120, 7, 1.0, 10_000, 88.5, slop=-1)
+            b = t.ref_score(scorer, 120, 7, 1.0, 10_000, 88.5, slop=-1)
+            assert bits(a) == bits(b), (i, scorer, a, b)
+            assert product_explain(t, scorer, 120, 7, 1.0, 88.5, slop, 0.0)[1] == t.ref_explain(scorer, 120, 7, 1.0, 10_000, 88.5, slop=slop)[1]
